@@ -1,0 +1,218 @@
+"""ctypes binding of the C ABI (include/alll_b200.h) -- the only way Python reaches the kernels.
+
+There is no CPU fallback: if ``liballl_b200.so`` is missing, or no B200-class device is
+present, every entry point raises.  (The CPU oracle lives in ``oracle/`` and is test
+infrastructure; this package never imports it.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liballl_b200.so")
+
+OK, MAX_ROUNDS, EMPTY_CLAUSE, BAD_ARG, CUDA_ERROR, NCCL_ERROR, NO_INSTANCE, CAPACITY = range(8)
+STATUS_NAMES = ["OK", "MAX_ROUNDS", "EMPTY_CLAUSE", "BAD_ARG", "CUDA_ERROR", "NCCL_ERROR", "NO_INSTANCE", "CAPACITY"]
+FLAG_NO_BUCKETING = 1
+
+#: every symbol include/alll_b200.h declares (tests check the library exports exactly these)
+SYMBOLS = [
+    "alll_abi_version", "alll_create", "alll_destroy", "alll_last_error",
+    "alll_upload_fixedk", "alll_upload_fixedk_device", "alll_upload_csr",
+    "alll_set_assignment", "alll_get_assignment", "alll_randomize",
+    "alll_eval", "alll_verify", "alll_round", "alll_solve",
+    "alll_time_sweep", "alll_launch_count", "alll_layout_info",
+]
+
+
+class AlllError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{STATUS_NAMES[status] if 0 <= status < len(STATUS_NAMES) else status}: {message}")
+        self.status = status
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("sweep_smem_bytes", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class StatsC(C.Structure):
+    _fields_ = [("n_iterations", C.c_uint64), ("n_resamples", C.c_uint64), ("avg_mis_size", C.c_uint64),
+                ("sum_mis_size", C.c_uint64), ("n_clause_evals", C.c_uint64), ("n_luby_steps", C.c_uint64),
+                ("n_kernel_launches", C.c_uint64), ("solve_ms", C.c_double), ("sweep_ms", C.c_double),
+                ("status", C.c_int32), ("reserved", C.c_int32)]
+
+
+@dataclass
+class Stats:
+    """Mirror of ``Statistics`` (SATInstance.h:25-32) plus device counters."""
+    n_iterations: int
+    n_resamples: int
+    avg_mis_size: int
+    sum_mis_size: int
+    n_clause_evals: int
+    n_luby_steps: int
+    n_kernel_launches: int
+    solve_ms: float
+    sweep_ms: float
+    status: int
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the C-ABI library; raises if it has not been built (``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            f"{LIB_PATH} is missing: build it with `make -C alllsatisfiabilitysolver_b200/csrc` "
+            "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32 = C.c_void_p, C.c_uint64, C.c_uint32
+    L.alll_abi_version.restype = C.c_int
+    L.alll_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.alll_destroy.argtypes = [vp]
+    L.alll_last_error.restype = C.c_char_p
+    L.alll_last_error.argtypes = [vp]
+    L.alll_upload_fixedk.argtypes = [vp, u64, u64, u32, vp]
+    L.alll_upload_fixedk_device.argtypes = [vp, u64, u64, u32, vp]
+    L.alll_upload_csr.argtypes = [vp, u64, u64, vp, vp]
+    L.alll_set_assignment.argtypes = [vp, vp]
+    L.alll_get_assignment.argtypes = [vp, vp]
+    L.alll_randomize.argtypes = [vp, u64]
+    L.alll_eval.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.alll_verify.argtypes = [vp, C.POINTER(C.c_int)]
+    L.alll_round.argtypes = [vp, u64, u32, vp, u64, C.POINTER(u64), vp, u64, C.POINTER(u64), C.POINTER(u64)]
+    L.alll_solve.argtypes = [vp, u64, u64, C.POINTER(StatsC)]
+    L.alll_time_sweep.argtypes = [vp, u32, C.POINTER(C.c_double), C.POINTER(u64)]
+    L.alll_launch_count.argtypes = [vp, C.POINTER(u64)]
+    L.alll_layout_info.argtypes = [vp, C.POINTER(u64)]
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int and name not in ("alll_abi_version",):
+            pass
+    _lib = L
+    return L
+
+
+class Solver:
+    """Thin owner of one ``alll_handle`` (one CUDA device, one stream)."""
+
+    def __init__(self, device: int = -1, sweep_smem_bytes: int = 0, flags: int = 0):
+        self.lib = load()
+        self.h = C.c_void_p()
+        cfg = Config(device, sweep_smem_bytes, flags, 0)
+        rc = self.lib.alll_create(C.byref(cfg), C.byref(self.h))
+        if rc != OK:
+            raise AlllError(rc, self.lib.alll_last_error(None).decode())
+        self.n_vars = 0
+        self.m = 0
+
+    # -- plumbing ---------------------------------------------------------------------
+    def _check(self, rc: int, allow=(OK,)):
+        if rc not in allow:
+            raise AlllError(rc, self.lib.alll_last_error(self.h).decode())
+        return rc
+
+    def close(self):
+        if self.h:
+            self.lib.alll_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- upload -------------------------------------------------------------------------
+    def upload_fixedk(self, n_vars: int, lits: np.ndarray):
+        lits = np.ascontiguousarray(lits, np.uint32)
+        m, k = lits.shape
+        self._check(self.lib.alll_upload_fixedk(self.h, n_vars, m, k, lits.ctypes.data))
+        self.n_vars, self.m = n_vars, m
+
+    def upload_fixedk_device(self, n_vars: int, m: int, k: int, device_ptr: int):
+        """``device_ptr``: raw device address of a row-major [m][k] uint32 buffer (e.g. ``tensor.data_ptr()``)."""
+        self._check(self.lib.alll_upload_fixedk_device(self.h, n_vars, m, k, C.c_void_p(device_ptr)))
+        self.n_vars, self.m = n_vars, m
+
+    def upload_csr(self, n_vars: int, off: np.ndarray, lit: np.ndarray):
+        off = np.ascontiguousarray(off, np.uint64)
+        lit = np.ascontiguousarray(lit, np.uint32)
+        m = len(off) - 1
+        self._check(self.lib.alll_upload_csr(self.h, n_vars, m, off.ctypes.data, lit.ctypes.data if len(lit) else None))
+        self.n_vars, self.m = n_vars, m
+
+    # -- assignment ---------------------------------------------------------------------
+    def set_assignment(self, bools: np.ndarray):
+        bools = np.ascontiguousarray(bools, np.uint8)
+        assert bools.shape == (self.n_vars,)
+        self._check(self.lib.alll_set_assignment(self.h, bools.ctypes.data))
+
+    def get_assignment(self) -> np.ndarray:
+        out = np.empty(self.n_vars, np.uint8)
+        self._check(self.lib.alll_get_assignment(self.h, out.ctypes.data))
+        return out
+
+    def randomize(self, seed: int):
+        self._check(self.lib.alll_randomize(self.h, seed))
+
+    # -- hot path -----------------------------------------------------------------------
+    def eval(self, want_ids: bool = True):
+        n = C.c_uint64(0)
+        if not want_ids:
+            self._check(self.lib.alll_eval(self.h, None, 0, C.byref(n)))
+            return int(n.value), None
+        buf = np.empty(max(self.m, 1), np.uint32)
+        self._check(self.lib.alll_eval(self.h, buf.ctypes.data, len(buf), C.byref(n)))
+        return int(n.value), buf[: n.value].copy()
+
+    def verify(self) -> bool:
+        v = C.c_int(0)
+        self._check(self.lib.alll_verify(self.h, C.byref(v)))
+        return bool(v.value)
+
+    def round(self, seed: int, rnd: int):
+        """One Moser-Tardos round; returns (U ids, S ids, n_resampled), ids in unspecified order."""
+        u = np.empty(max(self.m, 1), np.uint32)
+        s = np.empty(max(self.m, 1), np.uint32)
+        n_u, n_s, n_r = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.alll_round(self.h, seed, rnd, u.ctypes.data, len(u), C.byref(n_u),
+                                        s.ctypes.data, len(s), C.byref(n_s), C.byref(n_r)))
+        return u[: n_u.value].copy(), s[: n_s.value].copy(), int(n_r.value)
+
+    def solve(self, seed: int, max_rounds: int = 1 << 20) -> Stats:
+        st = StatsC()
+        self._check(self.lib.alll_solve(self.h, seed, max_rounds, C.byref(st)), allow=(OK, MAX_ROUNDS))
+        return Stats(st.n_iterations, st.n_resamples, st.avg_mis_size, st.sum_mis_size, st.n_clause_evals,
+                     st.n_luby_steps, st.n_kernel_launches, st.solve_ms, st.sweep_ms, st.status)
+
+    # -- measurement ----------------------------------------------------------------------
+    def time_sweep(self, reps: int):
+        ms = C.c_double(0.0)
+        n = C.c_uint64(0)
+        self._check(self.lib.alll_time_sweep(self.h, reps, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+    def launch_count(self) -> int:
+        n = C.c_uint64(0)
+        self._check(self.lib.alll_launch_count(self.h, C.byref(n)))
+        return int(n.value)
+
+    def layout_info(self) -> dict:
+        info = (C.c_uint64 * 6)()
+        self._check(self.lib.alll_layout_info(self.h, info))
+        return dict(m=info[0], k=info[1], n_buckets=info[2], m_padded=info[3], literal_bytes=info[4], sweep_smem_bytes=info[5])

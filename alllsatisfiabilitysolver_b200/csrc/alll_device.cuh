@@ -1,0 +1,142 @@
+// alll_device.cuh -- shared device helpers and kernel parameter blocks (sm_100a).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace alll {
+
+// ---- deterministic round specification (mirrors oracle/alll_oracle.c, which is the checker) ----
+constexpr uint32_t STREAM_INIT = 0u;
+constexpr uint32_t STREAM_RESAMPLE = 1u;
+constexpr uint32_t STREAM_PRIORITY = 2u;
+
+constexpr uint32_t SWEEP_THREADS = 1024;          // one CTA per SM: the staged assignment owns the shared memory
+constexpr uint32_t CLAUSES_PER_THREAD = 4;        // one 128-bit load per literal plane
+constexpr uint32_t TILE = SWEEP_THREADS * CLAUSES_PER_THREAD;   // clause slots per sweep tile
+constexpr uint32_t WBUF = 64;                     // per-warp violated-id staging entries
+constexpr uint32_t MAX_BUCKETS = 256;
+constexpr uint32_t MAX_K = 32;
+constexpr uint32_t INVALID_ID = 0xFFFFFFFFu;
+
+constexpr unsigned long long CLAIM_FREE = ~0ull;  // nobody claims this variable
+constexpr unsigned long long CLAIM_TAKEN = 0ull;  // variable belongs to a clause already in the independent set
+constexpr uint32_t TAGS = 62;                     // claim tag = TAGS - (step % TAGS), in bits 63..58
+
+struct Philox {
+    uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ Philox philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+#ifdef __CUDA_ARCH__
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+#else
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return Philox{c0, c1, c2, c3};
+}
+
+// Fair bit for variable v in (stream, round): word (v>>5)&3, bit v&31 of Philox(ctr={v>>7, round, stream, 0}).
+__device__ __forceinline__ uint32_t random_bit(uint64_t seed, uint32_t stream, uint32_t round, uint32_t v)
+{
+    const Philox o = philox4x32_10(v >> 7, round, stream, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint32_t sel = (v >> 5) & 3u;
+    const uint32_t word = sel == 0 ? o.x : sel == 1 ? o.y : sel == 2 ? o.z : o.w;
+    return (word >> (v & 31u)) & 1u;
+}
+
+// 26-bit priority of clause id c in a round; MIS order is (priority, id) ascending.
+__device__ __forceinline__ uint32_t clause_priority(uint64_t seed, uint32_t round, uint32_t c)
+{
+    return philox4x32_10(c, round, STREAM_PRIORITY, 0u, (uint32_t)seed, (uint32_t)(seed >> 32)).x >> 6;
+}
+
+__device__ __forceinline__ unsigned long long claim_key(uint32_t step, uint32_t prio26, uint32_t id)
+{
+    const unsigned long long tag = TAGS - (step % TAGS);          // 62 .. 1: later steps always undercut stale claims
+    return (tag << 58) | ((unsigned long long)prio26 << 32) | id;
+}
+
+// ---- streaming 128-bit load that does not pollute L1 (the literal planes are read exactly once per sweep)
+__device__ __forceinline__ uint4 ld_stream_v4(const uint32_t *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// ---- clause access for the sparse kernels (MIS / resample / id mapping) ----
+struct ClauseView {
+    // fixed-k literal planes: lit j of slot p is planes[j * m_pad + p]
+    const uint32_t *planes;
+    uint64_t m_pad;
+    uint32_t k;                 // 0 => CSR
+    // CSR
+    const uint64_t *off;
+    const uint32_t *csr_lit;
+    // slot -> caller clause id (NULL = identity)
+    const uint32_t *orig_id;
+
+    __device__ __forceinline__ uint32_t width(uint32_t p) const
+    {
+        return k ? k : (uint32_t)(off[p + 1] - off[p]);
+    }
+    __device__ __forceinline__ uint32_t literal(uint32_t p, uint32_t j) const
+    {
+        return k ? planes[(uint64_t)j * m_pad + p] : csr_lit[off[p] + j];
+    }
+    __device__ __forceinline__ uint32_t id(uint32_t p) const { return orig_id ? orig_id[p] : p; }
+};
+
+// Device-side counters of one handle.
+struct Counters {
+    unsigned int n_viol;        // |U| of the current sweep
+    unsigned int n_s;           // |S| of the current round
+    unsigned int step_live[64]; // clauses still undecided entering Luby step (index = step % 64)
+    unsigned long long n_resampled_round;
+    // running totals of a solve
+    unsigned long long n_iterations;
+    unsigned long long sum_mis;
+    unsigned long long n_resamples;
+    unsigned long long n_luby_steps;
+    // snapshot left by the most recent MIS kernel (what the host reads); n_viol/n_s/n_resampled_round are
+    // zeroed by that kernel so the next sweep starts from a clean slate without an extra launch
+    unsigned int last_n_viol;
+    unsigned int last_n_s;
+    unsigned long long last_resampled;
+};
+
+struct BucketSeg {
+    uint32_t tile_begin;        // first sweep tile of this bucket
+    uint32_t slot_end;          // one past the last valid clause slot of this bucket
+};
+
+struct SweepParams {
+    const uint32_t *planes;     // [k][m_pad]
+    uint64_t m_pad;
+    const uint32_t *bits;       // bit-packed assignment, n_words (padded to a multiple of 4) words
+    uint32_t n_words;
+    uint32_t bucket_words;      // words of assignment staged per bucket (multiple of 4)
+    uint32_t n_buckets;
+    uint32_t n_tiles;
+    const BucketSeg *segs;      // [n_buckets]
+    uint32_t *viol;             // out: violated slots
+    Counters *ctr;
+    uint32_t k;
+};
+
+} // namespace alll

@@ -1,0 +1,40 @@
+// alll_host.h -- launcher prototypes shared between the kernel translation units and the C ABI.
+#pragma once
+
+#include "alll_device.cuh"
+
+namespace alll {
+
+struct MisParams;   // mis.cu
+
+// sweep.cu
+size_t sweep_planes_smem_bytes(uint32_t bucket_words);
+cudaError_t configure_sweep_planes(const SweepParams &p, bool resident_all);
+cudaError_t launch_sweep_planes(const SweepParams &p, bool resident_all, uint32_t grid, cudaStream_t s);
+cudaError_t launch_sweep_csr(const uint64_t *off, const uint32_t *lit, uint64_t m, const uint32_t *bits,
+                             uint32_t *viol, Counters *ctr, uint32_t grid, cudaStream_t s);
+
+// mis.cu
+cudaError_t mis_max_grid(int device, uint32_t *grid_out);
+cudaError_t launch_mis_resample_args(const ClauseView &cv, const uint32_t *viol, uint8_t *state, uint32_t *s_slots,
+                                     unsigned long long *claim, uint32_t *bits, Counters *ctr, uint64_t seed,
+                                     uint32_t round, uint32_t grid, cudaStream_t s);
+cudaError_t launch_reset_counters(Counters *c, int reset_totals, cudaStream_t s);
+cudaError_t launch_map_ids(const uint32_t *slots, const uint32_t *orig_id, uint32_t n, uint32_t *out, cudaStream_t s);
+
+// layout.cu
+cudaError_t launch_transpose(const uint32_t *lit, uint64_t m, uint32_t k, uint64_t n_vars, uint32_t *planes,
+                             uint64_t m_pad, uint32_t *err, cudaStream_t s);
+cudaError_t launch_validate_csr(const uint32_t *lit, uint64_t n_lit, uint64_t n_vars, uint32_t *err, cudaStream_t s);
+uint32_t bucket_pass_ctas(uint64_t m);
+cudaError_t launch_bucket_count(const uint32_t *lit, uint64_t m, uint32_t k, uint64_t n_vars, uint32_t bucket_vars,
+                                uint32_t n_buckets, uint8_t *bkt, uint32_t *cta_counts, uint32_t *err, cudaStream_t s);
+cudaError_t launch_bucket_scatter(const uint32_t *lit, uint64_t m, uint32_t k, uint32_t bucket_vars, uint32_t n_buckets,
+                                  const uint8_t *bkt, const uint32_t *cta_base, uint32_t *planes, uint64_t m_pad,
+                                  uint32_t *orig_id, cudaStream_t s);
+cudaError_t launch_pack_bits(const uint8_t *bools, uint64_t n_vars, uint32_t *bits, uint32_t n_words_alloc, cudaStream_t s);
+cudaError_t launch_unpack_bits(const uint32_t *bits, uint64_t n_vars, uint8_t *bools, cudaStream_t s);
+cudaError_t launch_randomize(uint32_t *bits, uint64_t n_vars, uint32_t n_words_alloc, uint64_t seed, cudaStream_t s);
+cudaError_t launch_fill_u64(unsigned long long *p, uint64_t n, unsigned long long value, cudaStream_t s);
+
+} // namespace alll

@@ -1,0 +1,557 @@
+// capi.cu -- the extern "C" boundary (include/alll_b200.h) and the host-side round loop.
+//
+// Host control flow replaces SATInstance::solve -> parallel_solve (SATInstance.h:60-66, :217-320).  There is
+// no CPU compute path in this file: every clause evaluation, independent-set decision and resample happens
+// in the kernels of sweep.cu / mis.cu / layout.cu.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/alll_b200.h"
+#include "alll_host.h"
+
+using namespace alll;
+
+namespace {
+
+thread_local std::string g_create_error = "";
+
+constexpr uint32_t DEFAULT_SWEEP_SMEM = 192u * 1024u;
+constexpr int MAX_TIMED_ROUNDS = 256;
+
+} // namespace
+
+struct alll_solver {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    uint32_t smem_budget = DEFAULT_SWEEP_SMEM;
+    uint32_t flags = 0;
+    std::string err;
+    uint64_t launches = 0;
+
+    // instance
+    bool has_instance = false;
+    uint64_t n_vars = 0, m = 0, m_pad = 0;
+    uint32_t k = 0;                      // 0 = CSR
+    uint32_t n_words_alloc = 0, bucket_words = 0, n_buckets = 1, n_tiles = 0;
+    bool resident_all = true;
+    uint32_t *d_planes = nullptr, *d_orig_id = nullptr;
+    BucketSeg *d_segs = nullptr;
+    uint64_t *d_off = nullptr;
+    uint32_t *d_csr_lit = nullptr;
+    uint64_t n_lit = 0;
+    uint32_t *d_bits = nullptr;
+    unsigned long long *d_claim = nullptr;
+    uint32_t *d_viol = nullptr, *d_s = nullptr, *d_ids_out = nullptr;
+    uint8_t *d_state = nullptr, *d_bools = nullptr;
+    Counters *d_ctr = nullptr;
+    Counters *h_ctr = nullptr;           // pinned
+    uint32_t sweep_grid = 1, mis_grid = 1;
+    std::vector<cudaEvent_t> ev;         // 2 * MAX_TIMED_ROUNDS + 2
+};
+
+namespace {
+
+int fail(alll_handle h, int status, const std::string &msg)
+{
+    if (h) h->err = msg; else g_create_error = msg;
+    return status;
+}
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(h, ALLL_CUDA_ERROR, std::string(#call) + ": " + cudaGetErrorString(e__));       \
+    } while (0)
+
+template <typename T> void dfree(T *&p)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+void free_instance(alll_handle h)
+{
+    dfree(h->d_planes); dfree(h->d_orig_id); dfree(h->d_segs); dfree(h->d_off); dfree(h->d_csr_lit);
+    dfree(h->d_bits); dfree(h->d_claim); dfree(h->d_viol); dfree(h->d_s); dfree(h->d_ids_out);
+    dfree(h->d_state); dfree(h->d_bools);
+    h->has_instance = false;
+}
+
+inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+ClauseView clause_view(alll_handle h)
+{
+    ClauseView cv;
+    cv.planes = h->d_planes; cv.m_pad = h->m_pad; cv.k = h->k;
+    cv.off = h->d_off; cv.csr_lit = h->d_csr_lit; cv.orig_id = h->d_orig_id;
+    return cv;
+}
+
+// Buffers every instance needs regardless of the clause layout.
+int alloc_common(alll_handle h)
+{
+    const uint64_t m1 = std::max<uint64_t>(h->m, 1), n1 = std::max<uint64_t>(h->n_vars, 1);
+    CK(cudaMalloc(&h->d_bits, (size_t)std::max<uint32_t>(h->n_words_alloc, 4) * 4));
+    CK(cudaMemsetAsync(h->d_bits, 0, (size_t)std::max<uint32_t>(h->n_words_alloc, 4) * 4, h->stream));
+    CK(cudaMalloc(&h->d_claim, n1 * 8));
+    CK(launch_fill_u64(h->d_claim, n1, CLAIM_FREE, h->stream)); h->launches++;
+    CK(cudaMalloc(&h->d_viol, m1 * 4));
+    CK(cudaMalloc(&h->d_s, m1 * 4));
+    CK(cudaMalloc(&h->d_ids_out, m1 * 4));
+    CK(cudaMalloc(&h->d_state, m1));
+    CK(cudaMalloc(&h->d_bools, n1));
+    CK(launch_reset_counters(h->d_ctr, 1, h->stream)); h->launches++;
+    return ALLL_OK;
+}
+
+int check_sizes(alll_handle h, uint64_t n_vars, uint64_t m)
+{
+    if (n_vars == 0 || n_vars > (1ull << 31)) return fail(h, ALLL_BAD_ARG, "n_vars must be in [1, 2^31] (literals are uint32 2*var+neg)");
+    if (m > 0xFFFFFFFFull - 2 * TILE) return fail(h, ALLL_BAD_ARG, "m must be below 2^32 (clause ids are uint32)");
+    return ALLL_OK;
+}
+
+int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *d_lit)
+{
+    free_instance(h);
+    if (int rc = check_sizes(h, n_vars, m)) return rc;
+    if (k < 1 || k > MAX_K) return fail(h, ALLL_BAD_ARG, "k must be in [1, 32] for the fixed-width layout");
+    h->n_vars = n_vars; h->m = m; h->k = k;
+
+    const uint32_t n_words4 = (uint32_t)align_up((n_vars + 31) / 32, 4);
+    const uint32_t budget_words = h->smem_budget / 16 * 4;
+    if (n_words4 <= budget_words || (h->flags & ALLL_FLAG_NO_BUCKETING)) {
+        h->n_buckets = 1;
+        h->bucket_words = std::min(n_words4, budget_words);
+        h->resident_all = h->bucket_words >= n_words4;
+    } else {
+        uint32_t nb = (n_words4 + budget_words - 1) / budget_words;
+        if (nb > MAX_BUCKETS) { nb = MAX_BUCKETS; h->bucket_words = budget_words; }
+        else h->bucket_words = (uint32_t)align_up((n_words4 + nb - 1) / nb, 4);
+        h->n_buckets = nb;
+        h->resident_all = false;
+    }
+    h->n_words_alloc = std::max<uint32_t>(n_words4, h->n_buckets * h->bucket_words);
+
+    uint32_t *d_err = nullptr;
+    CK(cudaMalloc(&d_err, 4));
+    CK(cudaMemsetAsync(d_err, 0, 4, h->stream));
+    std::vector<BucketSeg> segs(h->n_buckets);
+
+    if (h->n_buckets == 1) {
+        h->m_pad = align_up(m, TILE);
+        if (h->m_pad) {
+            CK(cudaMalloc(&h->d_planes, h->m_pad * k * 4));
+            CK(cudaMemsetAsync(h->d_planes, 0, h->m_pad * k * 4, h->stream));
+        }
+        CK(launch_transpose(d_lit, m, k, n_vars, h->d_planes, h->m_pad, d_err, h->stream)); h->launches++;
+        segs[0] = BucketSeg{0u, (uint32_t)m};
+    } else {
+        const uint32_t bucket_vars = h->bucket_words * 32u, nb = h->n_buckets;
+        const uint32_t n_cta = bucket_pass_ctas(m);
+        uint8_t *d_bkt = nullptr;
+        uint32_t *d_cnt = nullptr;
+        CK(cudaMalloc(&d_bkt, std::max<uint64_t>(m, 1)));
+        CK(cudaMalloc(&d_cnt, (size_t)nb * std::max<uint32_t>(n_cta, 1) * 4));
+        if (m) { CK(launch_bucket_count(d_lit, m, k, n_vars, bucket_vars, nb, d_bkt, d_cnt, d_err, h->stream)); h->launches++; }
+        std::vector<uint32_t> cnt((size_t)nb * n_cta);
+        CK(cudaMemcpyAsync(cnt.data(), d_cnt, cnt.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        // exclusive scan: bucket segments start on a sweep-tile boundary, CTAs keep their order inside a segment
+        uint64_t pos = 0;
+        for (uint32_t b = 0; b < nb; b++) {
+            pos = align_up(pos, TILE);
+            segs[b].tile_begin = (uint32_t)(pos / TILE);
+            for (uint32_t c = 0; c < n_cta; c++) {
+                const uint32_t t = cnt[(size_t)b * n_cta + c];
+                cnt[(size_t)b * n_cta + c] = (uint32_t)pos;
+                pos += t;
+            }
+            segs[b].slot_end = (uint32_t)pos;
+        }
+        h->m_pad = align_up(pos, TILE);
+        CK(cudaMemcpyAsync(d_cnt, cnt.data(), cnt.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        if (h->m_pad) {
+            CK(cudaMalloc(&h->d_planes, h->m_pad * k * 4));
+            CK(cudaMemsetAsync(h->d_planes, 0, h->m_pad * k * 4, h->stream));
+            CK(cudaMalloc(&h->d_orig_id, h->m_pad * 4));
+            CK(cudaMemsetAsync(h->d_orig_id, 0xFF, h->m_pad * 4, h->stream));
+        }
+        if (m) {
+            CK(launch_bucket_scatter(d_lit, m, k, bucket_vars, nb, d_bkt, d_cnt, h->d_planes, h->m_pad, h->d_orig_id, h->stream));
+            h->launches++;
+        }
+        CK(cudaStreamSynchronize(h->stream));
+        cudaFree(d_bkt);
+        cudaFree(d_cnt);
+    }
+    h->n_tiles = (uint32_t)(h->m_pad / TILE);
+    CK(cudaMalloc(&h->d_segs, sizeof(BucketSeg) * h->n_buckets));
+    CK(cudaMemcpyAsync(h->d_segs, segs.data(), sizeof(BucketSeg) * h->n_buckets, cudaMemcpyHostToDevice, h->stream));
+
+    uint32_t err_flags = 0;
+    CK(cudaMemcpyAsync(&err_flags, d_err, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_err);
+    if (err_flags) { free_instance(h); return fail(h, ALLL_BAD_ARG, "a literal references a variable >= n_vars"); }
+
+    if (int rc = alloc_common(h)) return rc;
+    SweepParams sp{};
+    sp.bucket_words = h->bucket_words; sp.k = k;
+    CK(configure_sweep_planes(sp, h->resident_all));
+    h->sweep_grid = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)h->sm_count, h->n_tiles));
+    CK(cudaStreamSynchronize(h->stream));
+    h->has_instance = true;
+    return ALLL_OK;
+}
+
+// Enqueues one sweep.  Invariant: ctr->n_viol == 0 on entry (kept by the MIS kernel / reset kernel).
+int enqueue_sweep(alll_handle h)
+{
+    if (h->k) {
+        if (h->n_tiles == 0) return ALLL_OK;
+        SweepParams sp{};
+        sp.planes = h->d_planes; sp.m_pad = h->m_pad; sp.bits = h->d_bits; sp.n_words = h->n_words_alloc;
+        sp.bucket_words = h->bucket_words; sp.n_buckets = h->n_buckets; sp.n_tiles = h->n_tiles;
+        sp.segs = h->d_segs; sp.viol = h->d_viol; sp.ctr = h->d_ctr; sp.k = h->k;
+        CK(launch_sweep_planes(sp, h->resident_all, h->sweep_grid, h->stream));
+    } else {
+        if (h->m == 0) return ALLL_OK;
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((h->m + 255) / 256, (uint64_t)h->sm_count * 8);
+        CK(launch_sweep_csr(h->d_off, h->d_csr_lit, h->m, h->d_bits, h->d_viol, h->d_ctr, grid, h->stream));
+    }
+    h->launches++;
+    return ALLL_OK;
+}
+
+int enqueue_mis_resample(alll_handle h, uint64_t seed, uint32_t round)
+{
+    CK(launch_mis_resample_args(clause_view(h), h->d_viol, h->d_state, h->d_s, h->d_claim, h->d_bits, h->d_ctr,
+                                seed, round, h->mis_grid, h->stream));
+    h->launches++;
+    return ALLL_OK;
+}
+
+int fetch_counters(alll_handle h)
+{
+    CK(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return ALLL_OK;
+}
+
+// device slots -> caller ids -> host buffer
+int copy_ids_out(alll_handle h, const uint32_t *d_slots, uint64_t n, uint32_t *out, uint64_t cap)
+{
+    const uint64_t n_copy = std::min(n, cap);
+    if (!out || n_copy == 0) return ALLL_OK;
+    CK(launch_map_ids(d_slots, h->d_orig_id, (uint32_t)n_copy, h->d_ids_out, h->stream)); h->launches++;
+    CK(cudaMemcpyAsync(out, h->d_ids_out, n_copy * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return ALLL_OK;
+}
+
+#define NEED_INSTANCE()                                                                   \
+    do {                                                                                  \
+        if (!h) return ALLL_BAD_ARG;                                                      \
+        if (!h->has_instance) return fail(h, ALLL_NO_INSTANCE, "no instance uploaded");   \
+        CK(cudaSetDevice(h->device));                                                     \
+    } while (0)
+
+} // namespace
+
+extern "C" {
+
+int alll_abi_version(void) { return ALLL_ABI_VERSION; }
+
+const char *alll_last_error(alll_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int alll_create(const alll_config *cfg, alll_handle *out)
+{
+    alll_handle h = nullptr;   // CK() routes the message to g_create_error while h == NULL
+    if (!out) return fail(nullptr, ALLL_BAD_ARG, "out == NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(nullptr, ALLL_CUDA_ERROR, std::string("no CUDA device: the solver has no CPU fallback (") +
+                                                  cudaGetErrorString(e) + ")");
+    int device = cfg ? cfg->device : -1;
+    if (device < 0) CK(cudaGetDevice(&device));
+    if (device >= n_dev) return fail(nullptr, ALLL_BAD_ARG, "device ordinal out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(nullptr, ALLL_CUDA_ERROR, "device is not sm_100-class; this library carries only sm_100a code");
+    alll_solver *s = new alll_solver;
+    s->device = device;
+    s->sm_count = prop.multiProcessorCount;
+    s->flags = cfg ? cfg->flags : 0;
+    const uint32_t wbuf_bytes = (SWEEP_THREADS / 32) * WBUF * 4;
+    const uint32_t max_bits = (uint32_t)prop.sharedMemPerBlockOptin - wbuf_bytes - 1024;
+    s->smem_budget = (cfg && cfg->sweep_smem_bytes) ? cfg->sweep_smem_bytes : DEFAULT_SWEEP_SMEM;
+    s->smem_budget = std::max<uint32_t>(16, std::min(s->smem_budget, max_bits));
+    h = s;
+    auto bail = [&](int rc) { std::string m = h->err; alll_destroy(h); g_create_error = m; return rc; };
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaStreamCreate failed"));
+    if (cudaMalloc(&s->d_ctr, sizeof(Counters)) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaMalloc(counters) failed"));
+    if (cudaMallocHost(&s->h_ctr, sizeof(Counters)) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaMallocHost failed"));
+    if (mis_max_grid(device, &s->mis_grid) != cudaSuccess || s->mis_grid == 0) return bail(fail(h, ALLL_CUDA_ERROR, "occupancy query failed"));
+    s->ev.resize(2 * MAX_TIMED_ROUNDS + 2);
+    for (auto &ev : s->ev)
+        if (cudaEventCreate(&ev) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaEventCreate failed"));
+    *out = s;
+    return ALLL_OK;
+}
+
+int alll_destroy(alll_handle h)
+{
+    if (!h) return ALLL_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_instance(h);
+    for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+    if (h->d_ctr) cudaFree(h->d_ctr);
+    if (h->h_ctr) cudaFreeHost(h->h_ctr);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return ALLL_OK;
+}
+
+int alll_upload_fixedk_device(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *d_lit)
+{
+    if (!h) return ALLL_BAD_ARG;
+    if (m && !d_lit) return fail(h, ALLL_BAD_ARG, "d_lit == NULL");
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());   // the caller's buffer may have been produced on another stream
+    return upload_fixedk_device_impl(h, n_vars, m, k, d_lit);
+}
+
+int alll_upload_fixedk(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit)
+{
+    if (!h) return ALLL_BAD_ARG;
+    if (m && !lit) return fail(h, ALLL_BAD_ARG, "lit == NULL");
+    if (k < 1 || k > MAX_K) return fail(h, ALLL_BAD_ARG, "k must be in [1, 32] for the fixed-width layout");
+    CK(cudaSetDevice(h->device));
+    free_instance(h);
+    uint32_t *d_stage = nullptr;
+    const size_t bytes = (size_t)std::max<uint64_t>(m * k, 1) * 4;
+    CK(cudaMalloc(&d_stage, bytes));
+    if (m) CK(cudaMemcpyAsync(d_stage, lit, (size_t)m * k * 4, cudaMemcpyHostToDevice, h->stream));
+    const int rc = upload_fixedk_device_impl(h, n_vars, m, k, d_stage);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(d_stage);
+    return rc;
+}
+
+int alll_upload_csr(alll_handle h, uint64_t n_vars, uint64_t m, const uint64_t *off, const uint32_t *lit)
+{
+    if (!h) return ALLL_BAD_ARG;
+    if (!off || (m && off[m] > off[0] && !lit)) return fail(h, ALLL_BAD_ARG, "off/lit == NULL");
+    CK(cudaSetDevice(h->device));
+    // width scan: refuse empty clauses (Clause.h:35-45 makes them unsatisfiable), route uniform width to planes
+    bool uniform = m > 0;
+    const uint64_t k0 = m ? off[1] - off[0] : 0;
+    for (uint64_t c = 0; c < m; c++) {
+        if (off[c + 1] < off[c]) return fail(h, ALLL_BAD_ARG, "offsets must be non-decreasing");
+        const uint64_t w = off[c + 1] - off[c];
+        if (w == 0) return fail(h, ALLL_EMPTY_CLAUSE, "clause " + std::to_string(c) + " is empty and can never be satisfied");
+        uniform &= (w == k0);
+    }
+    if (uniform && k0 <= MAX_K) return alll_upload_fixedk(h, n_vars, m, (uint32_t)k0, lit + off[0]);
+
+    free_instance(h);
+    if (int rc = check_sizes(h, n_vars, m)) return rc;
+    h->n_vars = n_vars; h->m = m; h->k = 0; h->m_pad = m; h->n_buckets = 1; h->n_tiles = 0;
+    h->n_words_alloc = (uint32_t)align_up((n_vars + 31) / 32, 4);
+    h->bucket_words = 0; h->resident_all = false;
+    h->n_lit = m ? off[m] - off[0] : 0;
+    std::vector<uint64_t> off0(m + 1);
+    for (uint64_t c = 0; c <= m; c++) off0[c] = off[c] - off[0];
+    CK(cudaMalloc(&h->d_off, (m + 1) * 8));
+    CK(cudaMemcpyAsync(h->d_off, off0.data(), (m + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMalloc(&h->d_csr_lit, std::max<uint64_t>(h->n_lit, 1) * 4));
+    if (h->n_lit) CK(cudaMemcpyAsync(h->d_csr_lit, lit + off[0], h->n_lit * 4, cudaMemcpyHostToDevice, h->stream));
+    uint32_t *d_err = nullptr;
+    CK(cudaMalloc(&d_err, 4));
+    CK(cudaMemsetAsync(d_err, 0, 4, h->stream));
+    CK(launch_validate_csr(h->d_csr_lit, h->n_lit, n_vars, d_err, h->stream)); h->launches++;
+    uint32_t err_flags = 0;
+    CK(cudaMemcpyAsync(&err_flags, d_err, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_err);
+    if (err_flags) { free_instance(h); return fail(h, ALLL_BAD_ARG, "a literal references a variable >= n_vars"); }
+    if (int rc = alloc_common(h)) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    h->has_instance = true;
+    return ALLL_OK;
+}
+
+int alll_set_assignment(alll_handle h, const uint8_t *bools)
+{
+    NEED_INSTANCE();
+    if (!bools) return fail(h, ALLL_BAD_ARG, "bools == NULL");
+    CK(cudaMemcpyAsync(h->d_bools, bools, h->n_vars, cudaMemcpyHostToDevice, h->stream));
+    CK(launch_pack_bits(h->d_bools, h->n_vars, h->d_bits, h->n_words_alloc, h->stream)); h->launches++;
+    CK(cudaStreamSynchronize(h->stream));
+    return ALLL_OK;
+}
+
+int alll_get_assignment(alll_handle h, uint8_t *bools)
+{
+    NEED_INSTANCE();
+    if (!bools) return fail(h, ALLL_BAD_ARG, "bools == NULL");
+    CK(launch_unpack_bits(h->d_bits, h->n_vars, h->d_bools, h->stream)); h->launches++;
+    CK(cudaMemcpyAsync(bools, h->d_bools, h->n_vars, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return ALLL_OK;
+}
+
+int alll_randomize(alll_handle h, uint64_t seed)
+{
+    NEED_INSTANCE();
+    CK(launch_randomize(h->d_bits, h->n_vars, h->n_words_alloc, seed, h->stream)); h->launches++;
+    CK(cudaStreamSynchronize(h->stream));
+    return ALLL_OK;
+}
+
+int alll_eval(alll_handle h, uint32_t *ids, uint64_t cap, uint64_t *n_violated)
+{
+    NEED_INSTANCE();
+    if (int rc = enqueue_sweep(h)) return rc;
+    if (int rc = fetch_counters(h)) return rc;
+    const uint64_t n = h->h_ctr->n_viol;
+    if (n_violated) *n_violated = n;
+    if (int rc = copy_ids_out(h, h->d_viol, n, ids, cap)) return rc;
+    CK(launch_reset_counters(h->d_ctr, 0, h->stream)); h->launches++;
+    CK(cudaStreamSynchronize(h->stream));
+    return ALLL_OK;
+}
+
+int alll_verify(alll_handle h, int *valid)
+{
+    uint64_t n = 0;
+    const int rc = alll_eval(h, nullptr, 0, &n);
+    if (rc == ALLL_OK && valid) *valid = n == 0;
+    return rc;
+}
+
+int alll_round(alll_handle h, uint64_t seed, uint32_t round, uint32_t *u_ids, uint64_t u_cap, uint64_t *n_u,
+               uint32_t *s_ids, uint64_t s_cap, uint64_t *n_s, uint64_t *n_resampled)
+{
+    NEED_INSTANCE();
+    if (int rc = enqueue_sweep(h)) return rc;
+    if (int rc = enqueue_mis_resample(h, seed, round)) return rc;
+    if (int rc = fetch_counters(h)) return rc;
+    const Counters &c = *h->h_ctr;
+    if (n_u) *n_u = c.last_n_viol;
+    if (n_s) *n_s = c.last_n_s;
+    if (n_resampled) *n_resampled = c.last_resampled;
+    if (int rc = copy_ids_out(h, h->d_viol, c.last_n_viol, u_ids, u_cap)) return rc;
+    if (int rc = copy_ids_out(h, h->d_s, c.last_n_s, s_ids, s_cap)) return rc;
+    return ALLL_OK;
+}
+
+int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *stats)
+{
+    NEED_INSTANCE();
+    if (!stats) return fail(h, ALLL_BAD_ARG, "stats == NULL");
+    std::memset(stats, 0, sizeof(*stats));
+    const uint64_t launches0 = h->launches;
+    CK(launch_reset_counters(h->d_ctr, 1, h->stream)); h->launches++;
+    cudaEvent_t ev_begin = h->ev[2 * MAX_TIMED_ROUNDS], ev_end = h->ev[2 * MAX_TIMED_ROUNDS + 1];
+    CK(cudaEventRecord(ev_begin, h->stream));
+    int status = ALLL_OK;
+    uint64_t round = 0;
+    int timed = 0;
+    for (;;) {
+        const bool time_this = timed < MAX_TIMED_ROUNDS;
+        if (time_this) CK(cudaEventRecord(h->ev[2 * timed], h->stream));
+        if (int rc = enqueue_sweep(h)) return rc;
+        if (time_this) { CK(cudaEventRecord(h->ev[2 * timed + 1], h->stream)); timed++; }
+        if (int rc = enqueue_mis_resample(h, seed, (uint32_t)round)) return rc;
+        if (int rc = fetch_counters(h)) return rc;
+        if (h->h_ctr->last_n_viol == 0) break;            // SATInstance.h:285-287
+        round++;
+        if (round >= max_rounds) { status = ALLL_MAX_ROUNDS; break; }
+    }
+    CK(cudaEventRecord(ev_end, h->stream));
+    CK(cudaEventSynchronize(ev_end));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+    double sweep_ms = 0.0;
+    for (int i = 0; i < timed; i++) {
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, h->ev[2 * i], h->ev[2 * i + 1]));
+        sweep_ms += t;
+    }
+    const Counters &c = *h->h_ctr;
+    stats->n_iterations = c.n_iterations;
+    stats->n_resamples = c.n_resamples;
+    stats->sum_mis_size = c.sum_mis;
+    stats->avg_mis_size = c.n_iterations ? c.sum_mis / c.n_iterations : 0;     // SATInstance.h:317
+    stats->n_clause_evals = h->m * c.n_iterations;
+    stats->n_luby_steps = c.n_luby_steps;
+    stats->n_kernel_launches = h->launches - launches0;
+    stats->solve_ms = ms;
+    stats->sweep_ms = timed ? sweep_ms * ((double)c.n_iterations / timed) : 0.0;
+    stats->status = status;
+    return status;
+}
+
+int alll_time_sweep(alll_handle h, uint32_t reps, double *ms_per_sweep, uint64_t *n_violated)
+{
+    NEED_INSTANCE();
+    if (reps == 0) return fail(h, ALLL_BAD_ARG, "reps == 0");
+    double total = 0.0;
+    uint32_t done = 0;
+    while (done < reps) {
+        const uint32_t batch = std::min<uint32_t>(reps - done, MAX_TIMED_ROUNDS);
+        for (uint32_t i = 0; i < batch; i++) {
+            CK(cudaEventRecord(h->ev[2 * i], h->stream));
+            if (int rc = enqueue_sweep(h)) return rc;
+            CK(cudaEventRecord(h->ev[2 * i + 1], h->stream));
+            if (i + 1 < batch || done + batch < reps) { CK(launch_reset_counters(h->d_ctr, 0, h->stream)); h->launches++; }
+        }
+        CK(cudaStreamSynchronize(h->stream));
+        for (uint32_t i = 0; i < batch; i++) {
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, h->ev[2 * i], h->ev[2 * i + 1]));
+            total += t;
+        }
+        done += batch;
+    }
+    if (int rc = fetch_counters(h)) return rc;
+    if (n_violated) *n_violated = h->h_ctr->n_viol;
+    CK(launch_reset_counters(h->d_ctr, 0, h->stream)); h->launches++;
+    CK(cudaStreamSynchronize(h->stream));
+    if (ms_per_sweep) *ms_per_sweep = total / reps;
+    return ALLL_OK;
+}
+
+int alll_launch_count(alll_handle h, uint64_t *n)
+{
+    if (!h || !n) return ALLL_BAD_ARG;
+    *n = h->launches;
+    return ALLL_OK;
+}
+
+int alll_layout_info(alll_handle h, uint64_t info[6])
+{
+    if (!h || !info) return ALLL_BAD_ARG;
+    if (!h->has_instance) return fail(h, ALLL_NO_INSTANCE, "no instance uploaded");
+    info[0] = h->m;
+    info[1] = h->k;
+    info[2] = h->n_buckets;
+    info[3] = h->m_pad;
+    info[4] = h->k ? h->m_pad * h->k * 4 : h->n_lit * 4 + (h->m + 1) * 8;
+    info[5] = h->k ? sweep_planes_smem_bytes(h->bucket_words) : 0;
+    return ALLL_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,236 @@
+// layout.cu -- one-time (per upload) kernels that turn the caller's flattened clauses into the HBM layout
+// the sweep streams, plus assignment pack/unpack/randomise.
+//
+// Replaces the reference's heap object graph (Clause.h:17-28: vector<tV>* per clause, >= 3 heap blocks each)
+// and bool vars[n] (VariablesArray.h:18-35) by: k literal-major uint32 planes [k][m_pad] and a bit-packed
+// assignment.  When the assignment does not fit the sweep's shared-memory budget, clauses are stably
+// counting-sorted into variable-range buckets (the bucket holding most of their variables) and each
+// clause's literals are reordered bucket-resident first; orig_id[] maps slots back to caller clause ids.
+#include "alll_device.cuh"
+
+namespace alll {
+
+constexpr uint32_t LAYOUT_THREADS = 1024;   // clauses per CTA in the bucketing passes (one per thread)
+
+// error flags (bit-ored into *err)
+constexpr uint32_t ERR_LITERAL_RANGE = 1u;
+
+// ---- no bucketing: transpose row-major [m][k] into planes, validating literals -------------------
+__global__ void __launch_bounds__(256) transpose_kernel(const uint32_t *__restrict__ lit, uint64_t m, uint32_t k,
+                                                         uint64_t n_vars, uint32_t *__restrict__ planes,
+                                                         uint64_t m_pad, uint32_t *err)
+{
+    const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m) return;
+    uint32_t bad = 0;
+    for (uint32_t j = 0; j < k; j++) {
+        const uint32_t l = lit[c * k + j];
+        bad |= ((uint64_t)(l >> 1) >= n_vars);
+        planes[(uint64_t)j * m_pad + c] = l;
+    }
+    if (bad) atomicOr(err, ERR_LITERAL_RANGE);
+}
+
+__global__ void __launch_bounds__(256) validate_csr_kernel(const uint32_t *__restrict__ lit, uint64_t n_lit,
+                                                            uint64_t n_vars, uint32_t *err)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_lit && (uint64_t)(lit[i] >> 1) >= n_vars) atomicOr(err, ERR_LITERAL_RANGE);
+}
+
+// ---- bucketing pass 1: bucket of every clause + per-CTA histogram --------------------------------
+// bucket(c) = the variable-range bucket that holds most of c's variables (ties: lowest bucket).
+__global__ void __launch_bounds__(LAYOUT_THREADS) bucket_count_kernel(const uint32_t *__restrict__ lit, uint64_t m,
+                                                                       uint32_t k, uint64_t n_vars,
+                                                                       uint32_t bucket_vars, uint32_t n_buckets,
+                                                                       uint8_t *__restrict__ bkt,
+                                                                       uint32_t *__restrict__ cta_counts, uint32_t *err)
+{
+    __shared__ uint32_t hist[MAX_BUCKETS];
+    for (uint32_t i = threadIdx.x; i < n_buckets; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const uint64_t c = (uint64_t)blockIdx.x * LAYOUT_THREADS + threadIdx.x;
+    if (c < m) {
+        uint32_t b_of[MAX_K];
+        uint32_t bad = 0;
+        for (uint32_t j = 0; j < k; j++) {
+            const uint32_t v = lit[c * k + j] >> 1;
+            bad |= ((uint64_t)v >= n_vars);
+            b_of[j] = v / bucket_vars;          // may be >= n_buckets when n_buckets was clamped: never resident
+        }
+        if (bad) atomicOr(err, ERR_LITERAL_RANGE);
+        uint32_t best = 0, best_cnt = 0;
+        for (uint32_t j = 0; j < k; j++) {
+            if (b_of[j] >= n_buckets) continue;
+            uint32_t cnt = 0;
+            for (uint32_t i = 0; i < k; i++) cnt += (b_of[i] == b_of[j]);
+            if (cnt > best_cnt || (cnt == best_cnt && b_of[j] < best)) { best_cnt = cnt; best = b_of[j]; }
+        }
+        bkt[c] = (uint8_t)best;
+        atomicAdd(&hist[best], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_buckets; i += blockDim.x)
+        cta_counts[(uint64_t)i * gridDim.x + blockIdx.x] = hist[i];
+}
+
+// ---- bucketing pass 2: stable scatter into planes, bucket-resident literals first -----------------
+// cta_base[b * n_cta + cta] = first slot for this CTA's clauses of bucket b (exclusive scan done on the host).
+__global__ void __launch_bounds__(LAYOUT_THREADS) bucket_scatter_kernel(const uint32_t *__restrict__ lit, uint64_t m,
+                                                                         uint32_t k, uint32_t bucket_vars,
+                                                                         uint32_t n_buckets,
+                                                                         const uint8_t *__restrict__ bkt,
+                                                                         const uint32_t *__restrict__ cta_base,
+                                                                         uint32_t *__restrict__ planes, uint64_t m_pad,
+                                                                         uint32_t *__restrict__ orig_id)
+{
+    __shared__ uint16_t warp_cnt[(LAYOUT_THREADS / 32) * MAX_BUCKETS];   // [warp][bucket], then exclusive over warps
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    for (uint32_t i = threadIdx.x; i < (LAYOUT_THREADS / 32) * n_buckets; i += blockDim.x) warp_cnt[i] = 0;
+    __syncthreads();
+    const uint64_t c = (uint64_t)blockIdx.x * LAYOUT_THREADS + threadIdx.x;
+    const bool active = c < m;
+    const uint32_t act = __ballot_sync(0xffffffffu, active);
+    uint32_t b = 0, rank = 0;
+    if (active) {
+        b = bkt[c];
+        const uint32_t peers = __match_any_sync(act, b);
+        rank = __popc(peers & ((1u << lane) - 1u));
+        if (rank == 0) warp_cnt[warp * n_buckets + b] = (uint16_t)__popc(peers);
+    }
+    __syncthreads();
+    for (uint32_t bb = threadIdx.x; bb < n_buckets; bb += blockDim.x) {
+        uint32_t run = 0;
+        for (uint32_t w = 0; w < LAYOUT_THREADS / 32; w++) {
+            const uint32_t t = warp_cnt[w * n_buckets + bb];
+            warp_cnt[w * n_buckets + bb] = (uint16_t)run;
+            run += t;
+        }
+    }
+    __syncthreads();
+    if (!active) return;
+    const uint64_t dst = (uint64_t)cta_base[(uint64_t)b * gridDim.x + blockIdx.x] + warp_cnt[warp * n_buckets + b] + rank;
+    orig_id[dst] = (uint32_t)c;
+    const uint32_t lo = b * bucket_vars;
+    uint32_t j_out = 0;
+    for (uint32_t j = 0; j < k; j++) {             // resident literals first, original order kept
+        const uint32_t l = lit[c * k + j];
+        if ((l >> 1) - lo < bucket_vars) planes[(uint64_t)(j_out++) * m_pad + dst] = l;
+    }
+    for (uint32_t j = 0; j < k; j++) {
+        const uint32_t l = lit[c * k + j];
+        if (!((l >> 1) - lo < bucket_vars)) planes[(uint64_t)(j_out++) * m_pad + dst] = l;
+    }
+}
+
+// ---- assignment ------------------------------------------------------------------------------
+// bools (1 byte per variable, VariablesArray.h:21) -> packed words; one word per thread.
+__global__ void __launch_bounds__(256) pack_bits_kernel(const uint8_t *__restrict__ bools, uint64_t n_vars,
+                                                         uint32_t *__restrict__ bits, uint32_t n_words_alloc)
+{
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words_alloc) return;
+    uint32_t word = 0;
+    const uint64_t base = (uint64_t)w * 32;
+    for (uint32_t i = 0; i < 32 && base + i < n_vars; i++) word |= (bools[base + i] != 0 ? 1u : 0u) << i;
+    bits[w] = word;
+}
+
+__global__ void __launch_bounds__(256) unpack_bits_kernel(const uint32_t *__restrict__ bits, uint64_t n_vars,
+                                                           uint8_t *__restrict__ bools)
+{
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < n_vars) bools[v] = (bits[v >> 5] >> (v & 31u)) & 1u;
+}
+
+// bit v = Philox(ctr={v>>7, 0, INIT, 0}, key=seed) word (v>>5)&3 bit v&31; one Philox call per 4 words.
+__global__ void __launch_bounds__(256) randomize_kernel(uint32_t *__restrict__ bits, uint64_t n_vars,
+                                                         uint32_t n_words_alloc, uint64_t seed)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;       // group of 128 variables
+    if ((uint64_t)g * 4 >= n_words_alloc) return;
+    const Philox o = philox4x32_10(g, 0u, STREAM_INIT, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint32_t out[4] = {o.x, o.y, o.z, o.w};
+    for (uint32_t i = 0; i < 4; i++) {
+        const uint32_t w = g * 4 + i;
+        if (w >= n_words_alloc) break;
+        const uint64_t base = (uint64_t)w * 32;
+        uint32_t word = out[i];
+        if (base >= n_vars) word = 0;
+        else if (n_vars - base < 32) word &= (1u << (uint32_t)(n_vars - base)) - 1u;
+        bits[w] = word;
+    }
+}
+
+__global__ void __launch_bounds__(256) fill_u64_kernel(unsigned long long *p, uint64_t n, unsigned long long value)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = value;
+}
+
+// ---- launchers ---------------------------------------------------------------------------------
+static inline uint32_t blocks_for(uint64_t n, uint32_t threads) { return (uint32_t)((n + threads - 1) / threads); }
+
+cudaError_t launch_transpose(const uint32_t *lit, uint64_t m, uint32_t k, uint64_t n_vars, uint32_t *planes,
+                             uint64_t m_pad, uint32_t *err, cudaStream_t s)
+{
+    if (m == 0) return cudaSuccess;
+    transpose_kernel<<<blocks_for(m, 256), 256, 0, s>>>(lit, m, k, n_vars, planes, m_pad, err);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_validate_csr(const uint32_t *lit, uint64_t n_lit, uint64_t n_vars, uint32_t *err, cudaStream_t s)
+{
+    if (n_lit == 0) return cudaSuccess;
+    validate_csr_kernel<<<blocks_for(n_lit, 256), 256, 0, s>>>(lit, n_lit, n_vars, err);
+    return cudaGetLastError();
+}
+
+uint32_t bucket_pass_ctas(uint64_t m) { return blocks_for(m, LAYOUT_THREADS); }
+
+cudaError_t launch_bucket_count(const uint32_t *lit, uint64_t m, uint32_t k, uint64_t n_vars, uint32_t bucket_vars,
+                                uint32_t n_buckets, uint8_t *bkt, uint32_t *cta_counts, uint32_t *err, cudaStream_t s)
+{
+    bucket_count_kernel<<<bucket_pass_ctas(m), LAYOUT_THREADS, 0, s>>>(lit, m, k, n_vars, bucket_vars, n_buckets, bkt,
+                                                                         cta_counts, err);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bucket_scatter(const uint32_t *lit, uint64_t m, uint32_t k, uint32_t bucket_vars, uint32_t n_buckets,
+                                  const uint8_t *bkt, const uint32_t *cta_base, uint32_t *planes, uint64_t m_pad,
+                                  uint32_t *orig_id, cudaStream_t s)
+{
+    bucket_scatter_kernel<<<bucket_pass_ctas(m), LAYOUT_THREADS, 0, s>>>(lit, m, k, bucket_vars, n_buckets, bkt, cta_base,
+                                                                           planes, m_pad, orig_id);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_bits(const uint8_t *bools, uint64_t n_vars, uint32_t *bits, uint32_t n_words_alloc, cudaStream_t s)
+{
+    pack_bits_kernel<<<blocks_for(n_words_alloc, 256), 256, 0, s>>>(bools, n_vars, bits, n_words_alloc);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_bits(const uint32_t *bits, uint64_t n_vars, uint8_t *bools, cudaStream_t s)
+{
+    if (n_vars == 0) return cudaSuccess;
+    unpack_bits_kernel<<<blocks_for(n_vars, 256), 256, 0, s>>>(bits, n_vars, bools);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_randomize(uint32_t *bits, uint64_t n_vars, uint32_t n_words_alloc, uint64_t seed, cudaStream_t s)
+{
+    randomize_kernel<<<blocks_for((n_words_alloc + 3) / 4, 256), 256, 0, s>>>(bits, n_vars, n_words_alloc, seed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill_u64(unsigned long long *p, uint64_t n, unsigned long long value, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    uint32_t grid = blocks_for(n, 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    fill_u64_kernel<<<grid, 256, 0, s>>>(p, n, value);
+    return cudaGetLastError();
+}
+
+} // namespace alll

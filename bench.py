@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on the north-star workload (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4] [--impl reference]
+
+A *step* is one complete Moser-Tardos solve (random assignment -> all clauses satisfied) of the workload
+instance; the metric is clause-evals/sec = m x sweeps / device time of the round loop, with resample
+rounds/sec, time-to-SAT and the sweep kernel's HBM roofline alongside.  Workload at N=1: BASELINE config 4,
+bounded-degree 8-SAT n=10M m~40M -- the configuration the north-star target is quoted on; its 1.28 GB literal
+stream is ~10x the 126 MB L2, so no L2 flush is needed between iterations.
+
+Prints ONE JSON line (rank 0).  ``--impl reference`` times the unmodified reference headers
+(oracle/_ref, OpenMP, all host threads) on a bounded sample of the same shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from alllsatisfiabilitysolver_b200.instances import CONFIGS, INSTANCE_SEED_BASE  # noqa: E402
+
+METRIC = "clause_evals_per_sec"
+UNIT = "clause-evals/s"
+
+
+def workload_shape(name: str, scale: float):
+    cfg = dict(CONFIGS[name])
+    cfg["n"] = max(int(cfg["n"] * scale), 1000)
+    if cfg["kind"] == "uniform":
+        cfg["m"] = max(int(cfg["m"] * scale), 1000)
+    return cfg
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.samples = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 6:
+                self.samples.append(parts)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, s[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the unmodified reference headers on host cores (oracle/_ref)
+# ------------------------------------------------------------------------------------------------
+
+def reference_sample(shape: dict, steps: int, warmup: int, budget_s: float = 150.0):
+    """Times SATInstance::solve (the -p OpenMP path) on a bounded sample of the workload shape."""
+    from alllsatisfiabilitysolver_b200.instances import bounded_degree_ksat, uniform_ksat
+    from oracle.oracle import Reference, have_reference, to_csr
+
+    if not have_reference():
+        return None
+    ref = Reference()
+    cores = ref.num_procs()
+    # bounded sample: same (k, d) shape at n = 1M variables at most (cfg4 itself would need ~5 GB of Clause
+    # objects and minutes per solve in the reference's quadratic greedy independent set)
+    n = min(shape["n"], 1_000_000)
+    if shape["kind"] == "bounded":
+        lits = bounded_degree_ksat(n, shape["k"], shape["d"], seed=INSTANCE_SEED_BASE)
+        desc = f"bounded-degree {shape['k']}-SAT d={shape['d']} n={n} m={lits.shape[0]}"
+    else:
+        m = int(shape["m"] * n / shape["n"])
+        lits = uniform_ksat(n, shape["k"], m, seed=INSTANCE_SEED_BASE)
+        desc = f"uniform {shape['k']}-SAT n={n} m={m}"
+    off, lit = to_csr(lits)
+    m = lits.shape[0]
+    evals, secs, its = 0, 0.0, []
+    t_start = time.time()
+    with ref.instance(n, off, lit, cores) as ri:
+        done = 0
+        for i in range(warmup + steps):
+            ri.rerandomize()
+            st = ri.solve()
+            assert ri.verify(), "reference produced an invalid assignment"
+            if i >= warmup:
+                evals += m * st.n_iterations
+                secs += st.seconds
+                its.append(st.n_iterations)
+                done += 1
+            if time.time() - t_start > budget_s and done >= 1:
+                break
+    return dict(value=evals / secs, unit=UNIT, cores=cores, kind="reference",
+                sample=f"{desc}; {done} full SATInstance::solve runs with n_threads={cores} (unmodified reference headers, "
+                       f"-Ofast -fopenmp), mean {np.mean(its):.1f} iterations, {secs / done * 1e3:.1f} ms per solve",
+                ms_per_step=secs / done * 1e3, steps=done)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    shape = workload_shape(args.workload, args.scale)
+    r = reference_sample(shape, args.steps, args.warmup)
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/liballl_ref.so not built"}))
+        return 0
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": describe(shape, args.workload), "sample": r["sample"]},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def describe(shape, name):
+    if shape["kind"] == "bounded":
+        return f"{name}: bounded-degree random {shape['k']}-SAT, n={shape['n']} vars, every var <= {shape['d']} occurrences"
+    return f"{name}: uniform random {shape['k']}-SAT, n={shape['n']} vars, m={shape['m']} clauses"
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from alllsatisfiabilitysolver_b200 import capi
+    from alllsatisfiabilitysolver_b200.instances import bounded_degree_ksat_torch, uniform_ksat_torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the solver has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    shape = workload_shape(args.workload, args.scale)
+    k, n = shape["k"], shape["n"]
+    # weak scaling over the natural shard: one independent instance (own instance seed) per GPU
+    inst_seed = INSTANCE_SEED_BASE + int(args.workload[3:]) + 1000 * rank
+    if shape["kind"] == "bounded":
+        lits_t = bounded_degree_ksat_torch(n, k, shape["d"], inst_seed)
+    else:
+        lits_t = uniform_ksat_torch(n, k, shape["m"], inst_seed)
+    m = int(lits_t.shape[0])
+    torch.cuda.synchronize()
+
+    solver = capi.Solver(device=local_rank)
+    solver.upload_fixedk_device(n, m, k, lits_t.data_ptr())
+    layout = solver.layout_info()
+    max_rounds = args.max_rounds
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(i):
+        solver.randomize(1000 + i)
+        return solver.solve(1000 + i, max_rounds)
+
+    for i in range(args.warmup):
+        one_step(-1 - i)
+
+    # ---- timed region: exactly K steps, inputs resident in HBM ----
+    barrier()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = solver.launch_count()
+    t0 = time.perf_counter()
+    stats = [one_step(i) for i in range(args.steps)]
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = solver.launch_count() - launches0
+    clk = clocks.stop() if clocks else None
+
+    dev_ms = sum(s.solve_ms for s in stats)                 # CUDA events on the solver's stream
+    evals = sum(s.n_clause_evals for s in stats)
+    sweeps = sum(s.n_iterations for s in stats)
+    sweep_ms = sum(s.sweep_ms for s in stats)
+    rounds = sum(s.n_iterations - 1 for s in stats)
+    all_sat = all(s.status == 0 for s in stats)
+    verified = solver.verify() if all_sat else False
+
+    # ---- e2e: the reference-facing call with HOST buffers (upload + solve + assignment read-back) ----
+    lits_host = torch.empty(lits_t.shape, dtype=lits_t.dtype, pin_memory=True)
+    lits_host.copy_(lits_t)
+    torch.cuda.synchronize()
+    host_np = lits_host.numpy().view(np.uint32)
+    e2e_solver = capi.Solver(device=local_rank)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_evals = 0
+
+    def e2e_step(i):
+        e2e_solver.upload_fixedk(n, host_np)
+        e2e_solver.randomize(2000 + i)
+        st = e2e_solver.solve(2000 + i, max_rounds)
+        e2e_solver.get_assignment()
+        return st
+
+    e2e_step(-1)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_evals += e2e_step(i).n_clause_evals
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_solver.close()
+
+    # ---- reduce over ranks: MAX time, SUM work ----
+    red = torch.tensor([dev_ms, wall_ms, e2e_s], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([evals, sweeps, rounds, e2e_evals, launches, int(all_sat and verified)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    dev_ms_max, wall_ms_max, e2e_s_max = [float(x) for x in red.tolist()]
+    evals_all, sweeps_all, rounds_all, e2e_evals_all, launches_all, n_ok = [float(x) for x in tot.tolist()]
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        sweep_avg_ms = sweep_ms / max(sweeps, 1)
+        alg_bytes = 4 * k * m + n // 8               # 4k bytes per clause-eval + the packed assignment once
+        achieved = alg_bytes / (sweep_avg_ms * 1e-3) / 1e9 if sweep_avg_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "sweep_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.workload)
+            except Exception:
+                traffic = None
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = reference_sample(shape, steps=3, warmup=1, budget_s=60.0)
+            if cpu:
+                cpu = {kk: cpu[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+        line = {
+            "metric": METRIC, "value": evals_all / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": describe(shape, args.workload), "m_clauses_per_gpu": m, "k": k,
+                       "step": "one full solve: random assignment -> verified satisfying assignment",
+                       "parallelism": f"{world} x independent instance per GPU" if world > 1 else "single GPU",
+                       "l2": "literal stream (4*k*m bytes) is larger than L2; no flush needed" if 4 * k * m > 126e6 else
+                             "literal stream fits L2 (126 MB): sweeps after the first are L2-resident",
+                       "layout": layout},
+            "time_to_sat_ms": dev_ms_max / args.steps,
+            "rounds_per_sec": rounds_all / (dev_ms_max * 1e-3),
+            "sweeps_per_solve": sweeps / args.steps,
+            "all_runs_sat_and_verified": bool(n_ok == world),
+            "wall_ms_per_step": wall_ms_max / args.steps,
+            "roofline": {"bound": "hbm", "kernel": "sweep_planes_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": sweep_avg_ms,
+                         "frac_of_nominal_8TBps": achieved / 8000.0},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_evals_all / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": 4 * k * m,
+                    "d2h_bytes_per_step": n, "ms_per_step": e2e_s_max / e2e_steps * 1e3, "steps": e2e_steps,
+                    "call": "alll_upload_fixedk(host) + alll_randomize + alll_solve + alll_get_assignment(host)"},
+            "gpu_launches": int(launches_all),
+            "clocks": clk,
+        }
+        print(json.dumps(line))
+    solver.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=sorted(CONFIGS))
+    ap.add_argument("--scale", type=float, default=1.0, help="scale n (and m) of the workload; 1.0 = BASELINE size")
+    ap.add_argument("--max-rounds", type=int, default=100000)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        print(f"note: warmup {args.warmup} < 3; timing rules ask for >= 3", file=sys.stderr)
+    return run_reference(args) if args.impl == "reference" else run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

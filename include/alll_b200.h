@@ -1,0 +1,145 @@
+/*
+ * alll_b200.h -- C ABI of the B200 (sm_100a) parallel Moser-Tardos resampling path.
+ *
+ * This is the drop-in boundary underneath the reference's public solver surface
+ * (/root/reference/library/include/SATInstance.h).  The reference has no FFI of its
+ * own -- it is a header-only C++ template library -- so the boundary is inserted
+ * directly beneath SATInstance<T>::solve / verify_validity; the same-named C++
+ * headers in alllsatisfiabilitysolver_b200/include/ call only the functions below.
+ * Each entry point cites the reference interface it replaces (file:line relative
+ * to /root/reference).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a HOST pointer unless the
+ *     parameter name starts with d_ (device pointer on the handle's device);
+ *   - literal encoding lit = 2*var + neg, var 0-based (example/main.cpp:168, Clause.h:40);
+ *   - clause ids are positions in the concatenation of the caller's batches
+ *     (SATInstance.h:60-66 receives vector<ClauseArray*>; batches are contiguous);
+ *   - every function returns an alll_status; ALLL_OK == 0;
+ *   - blocking calls from one host thread per handle (like SATInstance::solve);
+ *   - there is NO CPU fallback: without a CUDA device every call fails with
+ *     ALLL_CUDA_ERROR.
+ */
+#ifndef ALLL_B200_H
+#define ALLL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALLL_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define ALLL_API __attribute__((visibility("default")))
+#else
+#define ALLL_API
+#endif
+
+typedef enum {
+    ALLL_OK = 0,
+    ALLL_MAX_ROUNDS = 1,    /* round cap hit before all clauses were satisfied (reference: loops forever, SATInstance.h:260) */
+    ALLL_EMPTY_CLAUSE = 2,  /* an empty clause can never be satisfied (Clause.h:35-45) -- refused at upload              */
+    ALLL_BAD_ARG = 3,
+    ALLL_CUDA_ERROR = 4,
+    ALLL_NCCL_ERROR = 5,
+    ALLL_NO_INSTANCE = 6,   /* call needs an uploaded instance */
+    ALLL_CAPACITY = 7       /* caller buffer too small */
+} alll_status;
+
+typedef struct alll_solver *alll_handle;
+
+typedef struct {
+    int32_t  device;            /* CUDA device ordinal; -1 = current device                                    */
+    uint32_t sweep_smem_bytes;  /* shared-memory budget for the staged assignment; 0 = default (192 KiB)      */
+    uint32_t flags;             /* ALLL_FLAG_* */
+    uint32_t reserved;
+} alll_config;
+
+#define ALLL_FLAG_NO_BUCKETING 1u  /* keep clause order; gather non-resident assignment words from L2 (debug / comparison) */
+
+/* Statistics{} of SATInstance.h:25-32 plus device-side counters.
+ * n_iterations = resample rounds + 1 (the terminal all-satisfied sweep counts, :261,:285-287);
+ * n_resamples  = sum over rounds of sum_{c in S} k_c (variables, not clauses, :363);
+ * avg_mis_size = floor(sum|S| / n_iterations) (:291,:317). */
+typedef struct {
+    uint64_t n_iterations;
+    uint64_t n_resamples;
+    uint64_t avg_mis_size;
+    uint64_t sum_mis_size;      /* sum |S| before the division                         */
+    uint64_t n_clause_evals;    /* m * n_iterations                                    */
+    uint64_t n_luby_steps;      /* claim/win iterations summed over rounds             */
+    uint64_t n_kernel_launches; /* kernels launched by this call                       */
+    double   solve_ms;          /* device-timed: first sweep launched -> last kernel done (upload excluded) */
+    double   sweep_ms;          /* device time inside the clause-evaluation sweeps     */
+    int32_t  status;            /* alll_status of the solve                            */
+    int32_t  reserved;
+} alll_stats;
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+
+/* Replaces: SATInstance(VariablesArray<T>*, int n_threads), SATInstance.h:51-56. */
+ALLL_API int alll_create(const alll_config *cfg, alll_handle *out);
+ALLL_API int alll_destroy(alll_handle h);
+/* Last error text of this handle (or of the failed alll_create when h == NULL). Never NULL. */
+ALLL_API const char *alll_last_error(alll_handle h);
+ALLL_API int alll_abi_version(void);
+
+/* ---- instance upload (the flattening of vector<ClauseArray*> that solve() receives) - */
+
+/* Fixed clause width k (1..32): lit is row-major [m][k].  Device layout: k literal-major
+ * planes, clauses bucketed by variable range when the bit-packed assignment exceeds the
+ * shared-memory budget.  Replaces the Clause object graph of Clause.h:17-28. */
+ALLL_API int alll_upload_fixedk(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit);
+/* Same, literals already in device memory (row-major [m][k]); the buffer is only read during the call. */
+ALLL_API int alll_upload_fixedk_device(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *d_lit);
+/* Variable width: off[m+1] into lit[].  Uniform-width inputs are routed to the fixed-k layout. */
+ALLL_API int alll_upload_csr(alll_handle h, uint64_t n_vars, uint64_t m, const uint64_t *off, const uint32_t *lit);
+
+/* ---- assignment (VariablesArray<T>::vars, VariablesArray.h:18-35; 1 byte per variable on the host) */
+
+ALLL_API int alll_set_assignment(alll_handle h, const uint8_t *bools);
+ALLL_API int alll_get_assignment(alll_handle h, uint8_t *bools);
+/* Uniform random assignment from Philox4x32-10 keyed by `seed` (replaces VariablesArray.h:24-33). */
+ALLL_API int alll_randomize(alll_handle h, uint64_t seed);
+
+/* ---- the hot path --------------------------------------------------------------------- */
+
+/* Violated-clause sweep + compaction (K1+K2).  Replaces SATInstance.h:273-280 /
+ * Clause::is_not_satisfied (Clause.h:34-46).  ids (may be NULL) receives up to `cap`
+ * violated clause ids in unspecified order; *n_violated is always the full count. */
+ALLL_API int alll_eval(alll_handle h, uint32_t *ids, uint64_t cap, uint64_t *n_violated);
+
+/* verify_validity, SATInstance.h:156-173: *valid = 1 iff no clause is violated. */
+ALLL_API int alll_verify(alll_handle h, int *valid);
+
+/* One full Moser-Tardos round on the device: sweep -> maximal independent set of the
+ * violated clauses (fixed-priority Luby with atomicMin claims == greedy in ascending
+ * (Philox priority, clause id) order; replaces populate_mis_parallel, SATInstance.h:391-451)
+ * -> resample (replaces resample_clauses, SATInstance.h:340-365).
+ * u_ids / s_ids (may be NULL) receive the violated set and the independent set, unspecified order. */
+ALLL_API int alll_round(alll_handle h, uint64_t seed, uint32_t round,
+               uint32_t *u_ids, uint64_t u_cap, uint64_t *n_u,
+               uint32_t *s_ids, uint64_t s_cap, uint64_t *n_s,
+               uint64_t *n_resampled);
+
+/* Round loop until no clause is violated or max_rounds resample rounds were done.
+ * Replaces SATInstance::solve(vector<ClauseArray*>*), SATInstance.h:60-66 -> parallel_solve :217-320.
+ * The assignment on the device is the in/out state; fetch it with alll_get_assignment. */
+ALLL_API int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *stats);
+
+/* ---- measurement hooks -------------------------------------------------------------- */
+
+/* `reps` back-to-back sweeps of the current assignment; *ms_per_sweep is the mean kernel
+ * duration from CUDA events recorded around each launch on the launching stream. */
+ALLL_API int alll_time_sweep(alll_handle h, uint32_t reps, double *ms_per_sweep, uint64_t *n_violated);
+/* Kernels launched through this handle so far. */
+ALLL_API int alll_launch_count(alll_handle h, uint64_t *n);
+/* Layout facts: {m, k (0 = CSR), n_buckets, m_padded, bytes of literal planes, smem bytes of the sweep}. */
+ALLL_API int alll_layout_info(alll_handle h, uint64_t info[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALLL_B200_H */
