@@ -1,0 +1,27 @@
+// cnf_io.h -- DIMACS CNF loading behind the cnf_io API the reference CLI uses
+// (example/cnf_io/cnf_io.h:13,16 of the reference: cnf_header_read / cnf_data_read, return TRUE ON ERROR).
+//
+// A from-scratch single-pass loader: the file is read once into memory and scanned with a hand-written
+// integer tokenizer; cnf_header_read caches the parse so the cnf_data_read that follows does not touch the
+// file again (the reference parses the text twice, copying the rest of the line for every token).
+//
+// Dialect: 'c'/'C' comment lines anywhere; first other non-blank line is
+// "p cnf V C" (case-insensitive, any blanks); clauses are integer streams terminated by 0, may span lines,
+// several per line.  Deliberate deviations from the reference's hazards: a last line without '\n' IS
+// parsed; tabs and '\r' separate tokens; a line starting with '%' ends the data (SATLIB trailer) instead of
+// triggering an out-of-bounds write; counts that contradict the header are reported as an error.
+#ifndef ALLL_B200_CNF_IO_H
+#define ALLL_B200_CNF_IO_H
+
+#include <string>
+
+using namespace std;
+
+// Reads V, C from the problem line and counts the non-zero literals.  Returns true on error.
+bool cnf_header_read(const string &cnf_file_name, int *v_num, int *c_num, int *l_num);
+
+// Fills l_c_num[c_num] (literals per clause) and l_val[l_num] (signed literals, clause by clause).
+// Never writes outside the given sizes.  Returns true on error (unreadable file, bad token, count mismatch).
+bool cnf_data_read(const string &cnf_file_name, int v_num, int c_num, int l_num, int l_c_num[], int l_val[]);
+
+#endif

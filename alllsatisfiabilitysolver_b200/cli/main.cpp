@@ -1,0 +1,199 @@
+// main.cpp -- command-line driver with the observable behaviour of the reference's example/main.cpp
+// (flags :56-61, thread rule :76-84, file naming :102-108, log lines :120-123,184-189,213-226,
+// INFORMATION block :192-194, STATISTICS block :236-246, six-field csv :196-200,228-230,248-251,
+// "Variable i = b" dump :272-276, exit code :283,294), written without Boost and driving the B200 path
+// through the drop-in SATInstance.h.
+//
+//   alll_solve [-h] [-o] [-p n_threads] --sat <file.cnf> [--seed S] [--max-rounds R] [--gpu ORDINAL]
+//
+// Deviations: the INFORMATION block and csv field 3 carry the true clause count
+// (Q1); a positional path is accepted as well as --sat (Q3); paths shorter than 4 characters get
+// ".out"/".csv" appended instead of overwriting (Q12); -p only sizes the per-thread statistics block --
+// the work runs on the GPU.
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <thread>
+
+#include "../include/SATInstance.h"
+#include "cnf_io/cnf_io.h"
+
+typedef uint32_t UINT_T;
+typedef SATInstance<UINT_T>::ClauseArray ClauseArray;
+
+static void output(const string &str, ofstream *out_f, bool dump)
+{
+    cout << str;
+    if (dump) *out_f << str;
+}
+
+static string now_string()
+{
+    auto t = chrono::system_clock::to_time_t(chrono::system_clock::now());
+    string s(ctime(&t));
+    if (!s.empty() && s.back() == '\n') s.pop_back();
+    return s;
+}
+
+static string sibling_path(const string &path, const char *ext)
+{
+    string p = path;
+    if (p.size() >= 4) p.replace(p.size() - 4, 4, ext);
+    else p += ext;
+    return p;
+}
+
+static void usage()
+{
+    cout << "Options:\n"
+            "  -h [ --help ]              Help\n"
+            "  -o [ --output ]            Output meta-data and statistics to separate files\n"
+            "  -p [ --parallel ] arg (=0) Use parallel solver\n"
+            "  --sat arg                  Path to SAT instance in DIMACS-CNF format\n"
+            "  --seed arg                 Solver seed (default: random_device)\n"
+            "  --max-rounds arg           Resample-round cap (default: unbounded)\n"
+            "  --gpu arg                  CUDA device ordinal (default: current device)\n";
+}
+
+int main(int argc, char *argv[])
+{
+    int n_threads = 1;
+    bool dump = false, have_seed = false;
+    string cnf_fpath;
+    uint64_t seed = 0, max_rounds = ~0ull;
+    int gpu = -1;
+    const int n_procs = (int)std::max(1u, std::thread::hardware_concurrency());
+
+    for (int i = 1; i < argc; i++) {
+        const string a = argv[i];
+        auto value = [&](const char *name) -> string {
+            if (i + 1 >= argc) { cerr << "the required argument for option '" << name << "' is missing" << endl; exit(1); }
+            return argv[++i];
+        };
+        if (a == "-h" || a == "--help") { usage(); return 0; }
+        else if (a == "-o" || a == "--output") dump = true;
+        else if (a == "-p" || a == "--parallel") {
+            const int p = atoi(value("--parallel").c_str());
+            if (p < 0 || p > n_procs) n_threads = n_procs;
+            else if (p > 0) n_threads = p;
+            else n_threads = 1;
+        }
+        else if (a == "--sat") cnf_fpath = value("--sat");
+        else if (a == "--seed") { seed = strtoull(value("--seed").c_str(), nullptr, 0); have_seed = true; }
+        else if (a == "--max-rounds") max_rounds = strtoull(value("--max-rounds").c_str(), nullptr, 0);
+        else if (a == "--gpu") gpu = atoi(value("--gpu").c_str());
+        else if (!a.empty() && a[0] != '-' && cnf_fpath.empty()) cnf_fpath = a;
+        else { cerr << "unrecognised option '" << a << "'" << endl; return 1; }
+    }
+    if (cnf_fpath.empty()) { cerr << "the option '--sat' is required but missing" << endl; return 1; }
+
+    ofstream *out_f = nullptr, *stat_f = nullptr;
+    if (dump) {
+        out_f = new ofstream(sibling_path(cnf_fpath, ".out"));
+        stat_f = new ofstream(sibling_path(cnf_fpath, ".csv"));
+    }
+
+    // ---- load ------------------------------------------------------------------------------------
+    output("Log " + now_string() + ": Reading CNF file\n", out_f, dump);
+    auto start = chrono::high_resolution_clock::now();
+
+    int c_num = 0, v_num = 0, l_num = 0;
+    if (cnf_header_read(cnf_fpath, &v_num, &c_num, &l_num)) {
+        cout << "The header information could not be read. Exiting..." << endl;
+        return 1;
+    }
+    int *l_c_num = new int[c_num > 0 ? c_num : 1];
+    int *l_val = new int[l_num > 0 ? l_num : 1];
+    if (cnf_data_read(cnf_fpath, v_num, c_num, l_num, l_c_num, l_val)) {
+        cout << "The clause data does not match the header. Exiting..." << endl;
+        return 1;
+    }
+
+    // literal encoding x>0 -> 2x-2, -x -> 2x-1; n_threads batches of ceil(c/n_threads) clauses
+    const long long chunk = (c_num + (long long)n_threads - 1) / n_threads;
+    auto clauses = new vector<ClauseArray *>();
+    for (int t = 0; t < n_threads; t++) clauses->push_back(new ClauseArray());
+    long long l = 0;
+    for (int c = 0; c < c_num; c++) {
+        auto literals = new vector<UINT_T>;
+        literals->reserve((size_t)l_c_num[c]);
+        for (int j = 0; j < l_c_num[c]; j++, l++) {
+            const long long x = l_val[l];
+            literals->push_back((UINT_T)(x > 0 ? 2 * x - 2 : -2 * x - 1));
+        }
+        const unsigned short t = (unsigned short)std::min<long long>(chunk ? c / chunk : 0, n_threads - 1);
+        clauses->at(t)->push_back(new Clause<UINT_T>(literals, t));
+    }
+    delete[] l_c_num;
+    delete[] l_val;
+
+    auto var_arr = have_seed ? new VariablesArray<UINT_T>((UINT_T)v_num, (unsigned long)seed) : new VariablesArray<UINT_T>((UINT_T)v_num);
+    auto satInstance = new SATInstance<UINT_T>(var_arr, n_threads);
+    satInstance->n_clauses = (ull)c_num;
+    if (have_seed) satInstance->set_seed(seed);
+    satInstance->set_max_rounds(max_rounds);
+    satInstance->set_device(gpu);
+
+    auto stop = chrono::high_resolution_clock::now();
+    auto read_duration = chrono::duration_cast<chrono::milliseconds>(stop - start);
+    output("Log " + now_string() + ": Read complete; Duration: " + to_string(read_duration.count() / 1000.0) + "s\n\n", out_f, dump);
+
+    output("------------ INFORMATION ------------\n\t\t\t# Variables\t= " + to_string(satInstance->n_vars) +
+               "\n\t\t\t# Clauses\t= " + to_string(satInstance->n_clauses) + "\n-------------------------------------\n\n",
+           out_f, dump);
+    if (dump) {
+        *stat_f << to_string(read_duration.count() / 1000.0) + ",";
+        *stat_f << to_string(satInstance->n_vars) + ",";
+        *stat_f << to_string(satInstance->n_clauses) + ",";
+    }
+
+    // ---- solve -----------------------------------------------------------------------------------
+    output("Log " + now_string() + ": Starting parallel solve (# Threads = " + to_string(n_threads) + ")\n", out_f, dump);
+    start = chrono::high_resolution_clock::now();
+    Statistics *statistics = nullptr;
+    try {
+        statistics = satInstance->solve(clauses);
+    } catch (const std::exception &e) {
+        output(string("ERROR: ") + e.what() + "\n", out_f, dump);
+        return 1;
+    }
+    stop = chrono::high_resolution_clock::now();
+    auto solve_duration = chrono::duration_cast<chrono::milliseconds>(stop - start);
+    output("Log " + now_string() + ": Completed solve; Duration: " + to_string(solve_duration.count() / 1000.0) + "s\n\n", out_f, dump);
+    if (dump) *stat_f << to_string(solve_duration.count()) + ",";
+
+    // ---- statistics -------------------------------------------------------------------------------
+    output("------------ STATISTICS -------------\n# Iterations\t= " + to_string(statistics->n_iterations) +
+               "\n# Resamples\t= " + to_string(statistics->n_resamples), out_f, dump);
+    for (int t = 0; t < n_threads; t++)
+        output("\n\tThread " + to_string(t + 1) + ": " + to_string(statistics->n_thread_resamples.at(t)), out_f, dump);
+    output("\n\nAvg. UNSAT MIS Size = " + to_string(statistics->avg_mis_size) + "\n-------------------------------------\n\n", out_f, dump);
+    if (dump) {
+        *stat_f << to_string(n_threads) + ",";
+        *stat_f << to_string(statistics->n_iterations) + "\n";
+    }
+
+    // ---- verify -----------------------------------------------------------------------------------
+    int rc = 1;
+    if (satInstance->last_status() == ALLL_MAX_ROUNDS) {
+        output("UNKNOWN: round cap reached before all clauses were satisfied\n", out_f, dump);
+    } else if (satInstance->verify_validity(clauses)) {
+        output("SATISFIABLE\n", out_f, dump);
+        if (dump)
+            for (ull i = 0; i < satInstance->n_vars; i++)
+                *out_f << "\nVariable " + to_string(i + 1) + " = " + to_string((satInstance->var_arr->vars)[i]);
+        rc = 0;
+    } else {
+        output("ERROR: Solver converged to an invalid solution!\n", out_f, dump);
+    }
+    if (dump) {
+        stat_f->close();
+        out_f->close();
+    }
+    return rc;
+}

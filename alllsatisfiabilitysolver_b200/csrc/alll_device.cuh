@@ -11,11 +11,12 @@ constexpr uint32_t STREAM_INIT = 0u;
 constexpr uint32_t STREAM_RESAMPLE = 1u;
 constexpr uint32_t STREAM_PRIORITY = 2u;
 
-constexpr uint32_t SWEEP_THREADS = 1024;          // one CTA per SM: the staged assignment owns the shared memory
+constexpr uint32_t SWEEP_THREADS = 512;           // one CTA per SM (the staged assignment owns the shared memory), <=128 regs/thread
 constexpr uint32_t CLAUSES_PER_THREAD = 4;        // one 128-bit load per literal plane
 constexpr uint32_t TILE = SWEEP_THREADS * CLAUSES_PER_THREAD;   // clause slots per sweep tile
 constexpr uint32_t WBUF = 64;                     // per-warp violated-id staging entries
 constexpr uint32_t MAX_BUCKETS = 256;
+constexpr uint32_t RESIDENT_CAP = 4;              // at most this many literals of a clause are placed as bucket-resident
 constexpr uint32_t MAX_K = 32;
 constexpr uint32_t INVALID_ID = 0xFFFFFFFFu;
 
@@ -137,6 +138,7 @@ struct SweepParams {
     uint32_t *viol;             // out: violated slots
     Counters *ctr;
     uint32_t k;
+    uint32_t min_resident;      // min over clauses of the number of resident-placed literals (0 when unknown)
 };
 
 } // namespace alll

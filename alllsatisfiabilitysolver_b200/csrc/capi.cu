@@ -38,6 +38,7 @@ struct alll_solver {
     uint32_t k = 0;                      // 0 = CSR
     uint32_t n_words_alloc = 0, bucket_words = 0, n_buckets = 1, n_tiles = 0;
     bool resident_all = true;
+    uint32_t min_resident = 0;           // measured by the bucketing pass; selects the sweep specialisation
     uint32_t *d_planes = nullptr, *d_orig_id = nullptr;
     BucketSeg *d_segs = nullptr;
     uint64_t *d_off = nullptr;
@@ -138,10 +139,12 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     }
     h->n_words_alloc = std::max<uint32_t>(n_words4, h->n_buckets * h->bucket_words);
 
-    uint32_t *d_err = nullptr;
-    CK(cudaMalloc(&d_err, 4));
-    CK(cudaMemsetAsync(d_err, 0, 4, h->stream));
+    uint32_t *d_err = nullptr;                       // [0] error flags, [1] min resident-placed literals per clause
+    CK(cudaMalloc(&d_err, 8));
+    const uint32_t err_init[2] = {0u, 0xFFFFFFFFu};
+    CK(cudaMemcpyAsync(d_err, err_init, 8, cudaMemcpyHostToDevice, h->stream));
     std::vector<BucketSeg> segs(h->n_buckets);
+    h->min_resident = 0;
 
     if (h->n_buckets == 1) {
         h->m_pad = align_up(m, TILE);
@@ -183,7 +186,7 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
             CK(cudaMemsetAsync(h->d_orig_id, 0xFF, h->m_pad * 4, h->stream));
         }
         if (m) {
-            CK(launch_bucket_scatter(d_lit, m, k, bucket_vars, nb, d_bkt, d_cnt, h->d_planes, h->m_pad, h->d_orig_id, h->stream));
+            CK(launch_bucket_scatter(d_lit, m, k, bucket_vars, nb, d_bkt, d_cnt, h->d_planes, h->m_pad, h->d_orig_id, d_err + 1, h->stream));
             h->launches++;
         }
         CK(cudaStreamSynchronize(h->stream));
@@ -194,15 +197,16 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     CK(cudaMalloc(&h->d_segs, sizeof(BucketSeg) * h->n_buckets));
     CK(cudaMemcpyAsync(h->d_segs, segs.data(), sizeof(BucketSeg) * h->n_buckets, cudaMemcpyHostToDevice, h->stream));
 
-    uint32_t err_flags = 0;
-    CK(cudaMemcpyAsync(&err_flags, d_err, 4, cudaMemcpyDeviceToHost, h->stream));
+    uint32_t err_out[2] = {0, 0};
+    CK(cudaMemcpyAsync(err_out, d_err, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     cudaFree(d_err);
-    if (err_flags) { free_instance(h); return fail(h, ALLL_BAD_ARG, "a literal references a variable >= n_vars"); }
+    if (err_out[0]) { free_instance(h); return fail(h, ALLL_BAD_ARG, "a literal references a variable >= n_vars"); }
+    if (h->n_buckets > 1 && m > 0 && err_out[1] != 0xFFFFFFFFu) h->min_resident = err_out[1];
 
     if (int rc = alloc_common(h)) return rc;
     SweepParams sp{};
-    sp.bucket_words = h->bucket_words; sp.k = k;
+    sp.bucket_words = h->bucket_words; sp.k = k; sp.min_resident = h->min_resident;
     CK(configure_sweep_planes(sp, h->resident_all));
     h->sweep_grid = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)h->sm_count, h->n_tiles));
     CK(cudaStreamSynchronize(h->stream));
@@ -218,7 +222,7 @@ int enqueue_sweep(alll_handle h)
         SweepParams sp{};
         sp.planes = h->d_planes; sp.m_pad = h->m_pad; sp.bits = h->d_bits; sp.n_words = h->n_words_alloc;
         sp.bucket_words = h->bucket_words; sp.n_buckets = h->n_buckets; sp.n_tiles = h->n_tiles;
-        sp.segs = h->d_segs; sp.viol = h->d_viol; sp.ctr = h->d_ctr; sp.k = h->k;
+        sp.segs = h->d_segs; sp.viol = h->d_viol; sp.ctr = h->d_ctr; sp.k = h->k; sp.min_resident = h->min_resident;
         CK(launch_sweep_planes(sp, h->resident_all, h->sweep_grid, h->stream));
     } else {
         if (h->m == 0) return ALLL_OK;

@@ -12,8 +12,9 @@
 //     (placed in the first planes) hit the bucket staged by the CTA; remaining literals are only
 //     looked up (from L2) for clauses still unsatisfied after the resident ones -- ~0.3 L2 sectors
 //     per clause instead of ~2;
-//   * evaluation is lazy per clause (expected 2 lookups), level-major so the 4 clauses of a
-//     thread keep 4 independent lookups in flight;
+//   * evaluation is lazy per clause (expected 2 lookups) and branch-free; non-resident lookups are
+//     issued in two batches (planes [0,5) then [5,k)) so a tile costs two dependent L2 round trips
+//     instead of up to k; the next tile's literals are already in flight (register double buffering);
 //   * violated slots are compacted per warp with __ballot_sync/__popc into a shared-memory staging
 //     buffer and flushed with one global atomicAdd per >= 32 entries.
 #include "alll_device.cuh"
@@ -29,7 +30,7 @@ struct WarpCompactor {
     uint32_t count;      // warp-uniform
     uint32_t lane;
 
-    __device__ __forceinline__ void flush()
+    __device__ __noinline__ void flush()
     {
         __syncwarp();
         unsigned int g = 0;
@@ -76,28 +77,21 @@ __device__ __forceinline__ uint32_t literal_true(uint32_t l, const uint32_t *sbi
 
 } // namespace
 
-// K > 0: compile-time clause width (all planes loaded up front, 8 x 128-bit loads in flight per thread for K=8).
-// K == 0: run-time width p.k (planes loaded lazily, level by level).
-template <int K, bool RESIDENT_ALL>
-__global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const SweepParams p)
-{
-    extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t *sbits = smem;
-    const uint32_t lane = threadIdx.x & 31u;
-    WarpCompactor comp{smem + p.bucket_words + (threadIdx.x >> 5) * WBUF, p.viol, p.ctr, 0u, lane};
+// ---- per-tile bookkeeping shared by both plane kernels ---------------------------------------------
+struct TileCursor {
+    uint32_t b, bucket_tile_end, slot_end, loaded;
 
-    const uint32_t t0 = (uint32_t)(((uint64_t)blockIdx.x * p.n_tiles) / gridDim.x);
-    const uint32_t t1 = (uint32_t)(((uint64_t)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
-    if (t0 >= t1) return;
-
-    uint32_t b = 0;
-    while (b + 1 < p.n_buckets && p.segs[b + 1].tile_begin <= t0) ++b;
-    uint32_t bucket_tile_end = (b + 1 < p.n_buckets) ? p.segs[b + 1].tile_begin : p.n_tiles;
-    uint32_t slot_end = p.segs[b].slot_end;
-    uint32_t loaded = 0xFFFFFFFFu;
-    const uint32_t bucket_vars = p.bucket_words * 32u;
-
-    for (uint32_t tile = t0; tile < t1; ++tile) {
+    __device__ __forceinline__ void init(const SweepParams &p, uint32_t t0)
+    {
+        b = 0;
+        while (b + 1 < p.n_buckets && p.segs[b + 1].tile_begin <= t0) ++b;
+        bucket_tile_end = (b + 1 < p.n_buckets) ? p.segs[b + 1].tile_begin : p.n_tiles;
+        slot_end = p.segs[b].slot_end;
+        loaded = 0xFFFFFFFFu;
+    }
+    // Moves to `tile`; (re)stages the bucket's slice of the assignment into shared memory when it changes.
+    __device__ __forceinline__ void enter(const SweepParams &p, uint32_t tile, uint32_t *sbits)
+    {
         while (tile >= bucket_tile_end) {
             ++b;
             bucket_tile_end = (b + 1 < p.n_buckets) ? p.segs[b + 1].tile_begin : p.n_tiles;
@@ -111,33 +105,177 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const Sw
             __syncthreads();
             loaded = b;
         }
-        const uint32_t vbase = b * bucket_vars;
+    }
+};
+
+// ---- literal evaluation, branch-free ------------------------------------------------------------------
+// The upload pass orders every clause's literals bucket-resident first (at most RC of them), so the planes
+// fall into three static classes and each class gets the cheapest code:
+//   planes [0, RB)  : resident for EVERY clause           -> shared-memory lookup, no range test
+//   planes [RB, RC) : resident for some clauses            -> range test, shared memory or L2 gather
+//   planes [RC, K)  : never treated as resident           -> L2 gather only
+// (RB = K means the whole assignment is staged and nothing is ever gathered.)
+// All lookups are predicated on the clause still being alive: a dead lane issues no request, so it costs
+// neither a bank conflict nor an L2 sector.
+
+// sadj = sbits - (vbase >> 5): indexable by the absolute word index v >> 5 of a resident variable.
+__device__ __forceinline__ void resident_only_step(uint32_t l, uint32_t &alive, const uint32_t *sadj)
+{
+    const bool go = alive != 0;
+    const uint32_t w = go ? sadj[l >> 6] : 0u;
+    const uint32_t lit_true = (__funnelshift_r(w, 0u, l >> 1) ^ l) & 1u;   // bit (v & 31) of w, xor the negation flag
+    alive = (go && lit_true) ? 0u : alive;
+}
+
+__device__ __forceinline__ void resident_mixed_step(uint32_t l, uint32_t &alive, const uint32_t *sadj, uint32_t vbase,
+                                                    uint32_t bucket_vars)
+{
+    const uint32_t v = l >> 1;
+    const bool go = alive != 0 && (v - vbase) < bucket_vars;               // v - vbase wraps when v < vbase
+    const uint32_t w = go ? sadj[v >> 5] : 0u;
+    const uint32_t lit_true = (__funnelshift_r(w, 0u, v) ^ l) & 1u;
+    alive = (go && lit_true) ? 0u : alive;
+}
+
+template <bool TEST_RANGE>
+__device__ __forceinline__ void gather_issue(uint32_t l, uint32_t alive, const uint32_t *gbits, uint32_t vbase,
+                                             uint32_t bucket_vars, uint32_t &w, bool &go)
+{
+    const uint32_t v = l >> 1;
+    go = TEST_RANGE ? (alive != 0 && (v - vbase) >= bucket_vars) : (alive != 0);
+    w = go ? __ldg(gbits + (v >> 5)) : 0u;
+}
+__device__ __forceinline__ void gather_apply(uint32_t l, uint32_t &alive, uint32_t w, bool go)
+{
+    const uint32_t lit_true = (__funnelshift_r(w, 0u, l >> 1) ^ l) & 1u;
+    alive = (go && lit_true) ? 0u : alive;
+}
+
+__device__ __forceinline__ uint32_t comp(const uint4 &v, int q) { return q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w; }
+
+// Gathers for planes [J0, J1): all issued back to back (one L2 round trip), then applied.
+template <int K, int RB, int RC, int J0, int J1>
+__device__ __forceinline__ void gather_round(const uint4 (&L)[K], uint32_t (&a)[4], const uint32_t *gbits,
+                                             uint32_t vbase, uint32_t bucket_vars)
+{
+    if constexpr (J1 > J0) {
+        uint32_t w[J1 - J0][4];
+        bool go[J1 - J0][4];
+#pragma unroll
+        for (int j = J0; j < J1; j++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (j < RC) gather_issue<true>(comp(L[j], q), a[q], gbits, vbase, bucket_vars, w[j - J0][q], go[j - J0][q]);
+                else gather_issue<false>(comp(L[j], q), a[q], gbits, vbase, bucket_vars, w[j - J0][q], go[j - J0][q]);
+            }
+#pragma unroll
+        for (int j = J0; j < J1; j++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) gather_apply(comp(L[j], q), a[q], w[j - J0][q], go[j - J0][q]);
+    }
+}
+
+// Evaluates the 4 clauses held in L[0..K) (component q of every plane = clause slot0+q); returns the
+// violated mask (bit q).  Phase R: shared memory.  Phases G1/G2: non-resident literals of planes [RB, 5)
+// and [5, K) -- two dependent L2 round trips instead of up to K.
+template <int K, int RB, int RC>
+__device__ __forceinline__ uint32_t eval4(const uint4 (&L)[K], uint32_t valid_mask, const uint32_t *sadj,
+                                          const uint32_t *gbits, uint32_t vbase, uint32_t bucket_vars)
+{
+    uint32_t a[4] = {valid_mask & 1u, valid_mask & 2u, valid_mask & 4u, valid_mask & 8u};
+#pragma unroll
+    for (int j = 0; j < RC; j++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (j < RB) resident_only_step(comp(L[j], q), a[q], sadj);
+            else resident_mixed_step(comp(L[j], q), a[q], sadj, vbase, bucket_vars);
+        }
+    if (RB < K) {
+        constexpr int SPLIT = K < 5 ? K : 5;
+        gather_round<K, RB, RC, RB, SPLIT>(L, a, gbits, vbase, bucket_vars);
+        gather_round<K, RB, RC, SPLIT, K>(L, a, gbits, vbase, bucket_vars);
+    }
+    return (a[0] ? 1u : 0u) | (a[1] ? 2u : 0u) | (a[2] ? 4u : 0u) | (a[3] ? 8u : 0u);
+}
+
+// Compile-time clause width K.  One CTA per SM; each thread owns 4 consecutive clause slots of a tile and
+// keeps TWO tiles of literals in registers: the next tile's K x 128-bit loads are in flight while the
+// current tile is evaluated (register double buffering; 512 threads x <=128 registers).
+template <int K, int RB, int RC>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const SweepParams p)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t *sbits = smem;
+    const uint32_t lane = threadIdx.x & 31u;
+    WarpCompactor comp{smem + p.bucket_words + (threadIdx.x >> 5) * WBUF, p.viol, p.ctr, 0u, lane};
+
+    const uint32_t t0 = (uint32_t)(((uint64_t)blockIdx.x * p.n_tiles) / gridDim.x);
+    const uint32_t t1 = (uint32_t)(((uint64_t)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
+    if (t0 >= t1) return;
+
+    TileCursor cur;
+    cur.init(p, t0);
+    const uint32_t bucket_vars = p.bucket_words * 32u;
+    const uint32_t *base = p.planes + threadIdx.x * CLAUSES_PER_THREAD;
+
+    auto load = [&](uint4 (&L)[K], uint32_t tile) {
+        const uint32_t *src = base + (uint64_t)tile * TILE;
+#pragma unroll
+        for (int j = 0; j < K; j++) L[j] = ld_stream_v4(src + (uint64_t)j * p.m_pad);
+    };
+    auto process = [&](const uint4 (&L)[K], uint32_t tile) {
+        cur.enter(p, tile, sbits);
+        const uint32_t slot0 = tile * TILE + threadIdx.x * CLAUSES_PER_THREAD;
+        uint32_t valid = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) valid |= (slot0 + q < cur.slot_end) ? (1u << q) : 0u;
+        const uint32_t vbase = cur.b * bucket_vars;
+        const uint32_t vmask = eval4<K, RB, RC>(L, valid, sbits - (vbase >> 5), p.bits, vbase, bucket_vars);
+        comp.push4(vmask, slot0);
+    };
+
+    uint4 A[K], B[K];
+    load(A, t0);
+    for (uint32_t tile = t0; tile < t1; tile += 2) {
+        if (tile + 1 < t1) load(B, tile + 1);
+        process(A, tile);
+        if (tile + 1 >= t1) break;
+        if (tile + 2 < t1) load(A, tile + 2);
+        process(B, tile + 1);
+    }
+    if (comp.count) comp.flush();
+}
+
+// Run-time clause width (k > 8): planes are loaded lazily level by level; no prefetch.
+template <bool RESIDENT_ALL>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_generic_kernel(const SweepParams p)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t *sbits = smem;
+    const uint32_t lane = threadIdx.x & 31u;
+    WarpCompactor comp{smem + p.bucket_words + (threadIdx.x >> 5) * WBUF, p.viol, p.ctr, 0u, lane};
+
+    const uint32_t t0 = (uint32_t)(((uint64_t)blockIdx.x * p.n_tiles) / gridDim.x);
+    const uint32_t t1 = (uint32_t)(((uint64_t)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
+    if (t0 >= t1) return;
+    TileCursor cur;
+    cur.init(p, t0);
+    const uint32_t bucket_vars = p.bucket_words * 32u;
+
+    for (uint32_t tile = t0; tile < t1; ++tile) {
+        cur.enter(p, tile, sbits);
+        const uint32_t vbase = cur.b * bucket_vars;
         const uint32_t slot0 = tile * TILE + threadIdx.x * CLAUSES_PER_THREAD;
         const uint32_t *src = p.planes + slot0;
-
         uint32_t alive = 0;
 #pragma unroll
-        for (int q = 0; q < 4; q++) alive |= (slot0 + q < slot_end) ? (1u << q) : 0u;
-
-        if (K > 0) {
-            uint4 L[K > 0 ? K : 1];
-#pragma unroll
-            for (int j = 0; j < K; j++) L[j] = ld_stream_v4(src + (uint64_t)j * p.m_pad);
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-                if (alive & 1u) alive &= ~(literal_true<RESIDENT_ALL>(L[j].x, sbits, p.bits, vbase, bucket_vars) << 0);
-                if (alive & 2u) alive &= ~(literal_true<RESIDENT_ALL>(L[j].y, sbits, p.bits, vbase, bucket_vars) << 1);
-                if (alive & 4u) alive &= ~(literal_true<RESIDENT_ALL>(L[j].z, sbits, p.bits, vbase, bucket_vars) << 2);
-                if (alive & 8u) alive &= ~(literal_true<RESIDENT_ALL>(L[j].w, sbits, p.bits, vbase, bucket_vars) << 3);
-            }
-        } else {
-            for (uint32_t j = 0; j < p.k && alive; j++) {
-                const uint4 Lj = ld_stream_v4(src + (uint64_t)j * p.m_pad);
-                if (alive & 1u) alive &= ~(literal_true<RESIDENT_ALL>(Lj.x, sbits, p.bits, vbase, bucket_vars) << 0);
-                if (alive & 2u) alive &= ~(literal_true<RESIDENT_ALL>(Lj.y, sbits, p.bits, vbase, bucket_vars) << 1);
-                if (alive & 4u) alive &= ~(literal_true<RESIDENT_ALL>(Lj.z, sbits, p.bits, vbase, bucket_vars) << 2);
-                if (alive & 8u) alive &= ~(literal_true<RESIDENT_ALL>(Lj.w, sbits, p.bits, vbase, bucket_vars) << 3);
-            }
+        for (int q = 0; q < 4; q++) alive |= (slot0 + q < cur.slot_end) ? (1u << q) : 0u;
+        for (uint32_t j = 0; j < p.k && alive; j++) {
+            const uint4 Lj = ld_stream_v4(src + (uint64_t)j * p.m_pad);
+            if (alive & 1u) alive &= ~(literal_true<RESIDENT_ALL>(Lj.x, sbits, p.bits, vbase, bucket_vars) << 0);
+            if (alive & 2u) alive &= ~(literal_true<RESIDENT_ALL>(Lj.y, sbits, p.bits, vbase, bucket_vars) << 1);
+            if (alive & 4u) alive &= ~(literal_true<RESIDENT_ALL>(Lj.z, sbits, p.bits, vbase, bucket_vars) << 2);
+            if (alive & 8u) alive &= ~(literal_true<RESIDENT_ALL>(Lj.w, sbits, p.bits, vbase, bucket_vars) << 3);
         }
         comp.push4(alive, slot0);
     }
@@ -178,28 +316,49 @@ __global__ void __launch_bounds__(256) sweep_csr_kernel(const uint64_t *__restri
 
 // ---- launchers ------------------------------------------------------------------------
 
-template <int K, bool R>
+template <int K, int RB, int RC>
 static cudaError_t launch_planes(const SweepParams &p, uint32_t grid, size_t smem, cudaStream_t s, bool configure_only)
 {
     if (configure_only)   // function attributes are per device: the handle configures its kernel once at upload
-        return cudaFuncSetAttribute(sweep_planes_kernel<K, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    sweep_planes_kernel<K, R><<<grid, SWEEP_THREADS, smem, s>>>(p);
+        return cudaFuncSetAttribute(sweep_planes_kernel<K, RB, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sweep_planes_kernel<K, RB, RC><<<grid, SWEEP_THREADS, smem, s>>>(p);
     return cudaGetLastError();
 }
 
 template <bool R>
-static cudaError_t dispatch_k(const SweepParams &p, uint32_t grid, size_t smem, cudaStream_t s, bool cfg)
+static cudaError_t launch_generic(const SweepParams &p, uint32_t grid, size_t smem, cudaStream_t s, bool configure_only)
+{
+    if (configure_only)
+        return cudaFuncSetAttribute(sweep_planes_generic_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sweep_planes_generic_kernel<R><<<grid, SWEEP_THREADS, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+// resident_all: every plane is resident-only (RB = RC = K).  Otherwise RC = min(K, RESIDENT_CAP) and
+// RB = min(p.min_resident, 2, RC) as measured by the upload pass.
+template <int K>
+static cudaError_t dispatch_class(const SweepParams &p, bool resident_all, uint32_t grid, size_t smem, cudaStream_t s, bool cfg)
+{
+    constexpr int RC = K < (int)RESIDENT_CAP ? K : (int)RESIDENT_CAP;
+    if (resident_all) return launch_planes<K, K, K>(p, grid, smem, s, cfg);
+    const uint32_t rb = p.min_resident < 2u ? p.min_resident : 2u;
+    if (rb >= 2 && RC >= 2) return launch_planes<K, (RC < 2 ? RC : 2), RC>(p, grid, smem, s, cfg);
+    if (rb >= 1) return launch_planes<K, 1, RC>(p, grid, smem, s, cfg);
+    return launch_planes<K, 0, RC>(p, grid, smem, s, cfg);
+}
+
+static cudaError_t dispatch_k(const SweepParams &p, bool resident_all, uint32_t grid, size_t smem, cudaStream_t s, bool cfg)
 {
     switch (p.k) {
-    case 1: return launch_planes<1, R>(p, grid, smem, s, cfg);
-    case 2: return launch_planes<2, R>(p, grid, smem, s, cfg);
-    case 3: return launch_planes<3, R>(p, grid, smem, s, cfg);
-    case 4: return launch_planes<4, R>(p, grid, smem, s, cfg);
-    case 5: return launch_planes<5, R>(p, grid, smem, s, cfg);
-    case 6: return launch_planes<6, R>(p, grid, smem, s, cfg);
-    case 7: return launch_planes<7, R>(p, grid, smem, s, cfg);
-    case 8: return launch_planes<8, R>(p, grid, smem, s, cfg);
-    default: return launch_planes<0, R>(p, grid, smem, s, cfg);
+    case 1: return dispatch_class<1>(p, resident_all, grid, smem, s, cfg);
+    case 2: return dispatch_class<2>(p, resident_all, grid, smem, s, cfg);
+    case 3: return dispatch_class<3>(p, resident_all, grid, smem, s, cfg);
+    case 4: return dispatch_class<4>(p, resident_all, grid, smem, s, cfg);
+    case 5: return dispatch_class<5>(p, resident_all, grid, smem, s, cfg);
+    case 6: return dispatch_class<6>(p, resident_all, grid, smem, s, cfg);
+    case 7: return dispatch_class<7>(p, resident_all, grid, smem, s, cfg);
+    case 8: return dispatch_class<8>(p, resident_all, grid, smem, s, cfg);
+    default: return resident_all ? launch_generic<true>(p, grid, smem, s, cfg) : launch_generic<false>(p, grid, smem, s, cfg);
     }
 }
 
@@ -211,13 +370,13 @@ size_t sweep_planes_smem_bytes(uint32_t bucket_words)
 cudaError_t configure_sweep_planes(const SweepParams &p, bool resident_all)
 {
     const size_t smem = sweep_planes_smem_bytes(p.bucket_words);
-    return resident_all ? dispatch_k<true>(p, 0, smem, 0, true) : dispatch_k<false>(p, 0, smem, 0, true);
+    return dispatch_k(p, resident_all, 0, smem, 0, true);
 }
 
 cudaError_t launch_sweep_planes(const SweepParams &p, bool resident_all, uint32_t grid, cudaStream_t s)
 {
     const size_t smem = sweep_planes_smem_bytes(p.bucket_words);
-    return resident_all ? dispatch_k<true>(p, grid, smem, s, false) : dispatch_k<false>(p, grid, smem, s, false);
+    return dispatch_k(p, resident_all, grid, smem, s, false);
 }
 
 cudaError_t launch_sweep_csr(const uint64_t *off, const uint32_t *lit, uint64_t m, const uint32_t *bits,
