@@ -21,22 +21,26 @@
 
 namespace alll {
 
+// All shared-memory traffic indexes this array directly (never through a stored pointer): a generic
+// pointer would make the compiler rebuild the shared-window base (S2R SR_CgaCtaId + LEA) at every lookup.
+extern __shared__ __align__(16) uint32_t g_smem[];
+
 namespace {
 
 struct WarpCompactor {
-    uint32_t *wbuf;      // this warp's staging buffer (WBUF entries)
+    uint32_t wbuf;       // index in g_smem of this warp's staging buffer (WBUF entries)
     uint32_t *viol;
     Counters *ctr;
     uint32_t count;      // warp-uniform
     uint32_t lane;
 
-    __device__ __noinline__ void flush()
+    __device__ __forceinline__ void flush()
     {
         __syncwarp();
         unsigned int g = 0;
         if (lane == 0) g = atomicAdd(&ctr->n_viol, count);
         g = __shfl_sync(0xffffffffu, g, 0);
-        for (uint32_t i = lane; i < count; i += 32) viol[g + i] = wbuf[i];
+        for (uint32_t i = lane; i < count; i += 32) viol[g + i] = g_smem[wbuf + i];
         __syncwarp();
         count = 0;
     }
@@ -51,7 +55,7 @@ struct WarpCompactor {
             const bool mine = (vmask >> q) & 1u;
             const uint32_t bal = __ballot_sync(0xffffffffu, mine);
             if (bal) {
-                if (mine) wbuf[count + __popc(bal & lt)] = slot0 + q;
+                if (mine) g_smem[wbuf + count + __popc(bal & lt)] = slot0 + q;
                 count += __popc(bal);
                 if (count >= 32) flush();
             }
@@ -61,16 +65,15 @@ struct WarpCompactor {
 
 // true iff literal l is TRUE under the assignment
 template <bool RESIDENT_ALL>
-__device__ __forceinline__ uint32_t literal_true(uint32_t l, const uint32_t *sbits, const uint32_t *gbits,
-                                                 uint32_t vbase, uint32_t bucket_vars)
+__device__ __forceinline__ uint32_t literal_true(uint32_t l, const uint32_t *gbits, uint32_t vbase, uint32_t bucket_vars)
 {
     const uint32_t v = l >> 1;
     uint32_t w;
     if (RESIDENT_ALL) {
-        w = sbits[v >> 5];
+        w = g_smem[v >> 5];
     } else {
         const uint32_t rel = v - vbase;                 // wraps to a huge value when v < vbase
-        w = (rel < bucket_vars) ? sbits[rel >> 5] : __ldg(gbits + (v >> 5));
+        w = (rel < bucket_vars) ? g_smem[rel >> 5] : __ldg(gbits + (v >> 5));
     }
     return ((w >> (v & 31u)) ^ l) & 1u;
 }
@@ -90,7 +93,7 @@ struct TileCursor {
         loaded = 0xFFFFFFFFu;
     }
     // Moves to `tile`; (re)stages the bucket's slice of the assignment into shared memory when it changes.
-    __device__ __forceinline__ void enter(const SweepParams &p, uint32_t tile, uint32_t *sbits)
+    __device__ __forceinline__ void enter(const SweepParams &p, uint32_t tile)
     {
         while (tile >= bucket_tile_end) {
             ++b;
@@ -100,8 +103,8 @@ struct TileCursor {
         if (b != loaded) {
             __syncthreads();                      // everyone is done with the previous bucket's bits
             const uint4 *src = reinterpret_cast<const uint4 *>(p.bits + (uint64_t)b * p.bucket_words);
-            uint4 *dst = reinterpret_cast<uint4 *>(sbits);
-            for (uint32_t i = threadIdx.x; i < p.bucket_words / 4; i += SWEEP_THREADS) dst[i] = __ldg(src + i);
+            for (uint32_t i = threadIdx.x; i < p.bucket_words / 4; i += SWEEP_THREADS)
+                reinterpret_cast<uint4 *>(g_smem)[i] = __ldg(src + i);
             __syncthreads();
             loaded = b;
         }
@@ -118,21 +121,34 @@ struct TileCursor {
 // All lookups are predicated on the clause still being alive: a dead lane issues no request, so it costs
 // neither a bank conflict nor an L2 sector.
 
-// sadj = sbits - (vbase >> 5): indexable by the absolute word index v >> 5 of a resident variable.
-__device__ __forceinline__ void resident_only_step(uint32_t l, uint32_t &alive, const uint32_t *sadj)
+// Shared-memory word load from a 32-bit shared-window byte address.  The hot lookups use this instead of
+// g_smem[...]: with the address base held in an (opaque) register the lookup is SHF + LEA + LDS, whereas
+// nvcc rebuilds the window base (S2R SR_CgaCtaId, MOV, LEA) for every predicated g_smem[] access.
+// Not volatile on purpose (the scheduler may interleave lookups freely); ordering against the staging
+// barrier comes from the address base, which is re-materialised through an opaque asm after each barrier.
+__device__ __forceinline__ uint32_t lds32(uint32_t byte_addr)
+{
+    uint32_t w;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(byte_addr));
+    return w;
+}
+
+// sadj = shared byte address of staged word 0 minus 4 * (vbase >> 5): sadj + 4 * (v >> 5) addresses the word
+// of a resident variable v.
+__device__ __forceinline__ void resident_only_step(uint32_t l, uint32_t &alive, uint32_t sadj)
 {
     const bool go = alive != 0;
-    const uint32_t w = go ? sadj[l >> 6] : 0u;
+    const uint32_t w = go ? lds32(sadj + ((l >> 6) << 2)) : 0u;
     const uint32_t lit_true = (__funnelshift_r(w, 0u, l >> 1) ^ l) & 1u;   // bit (v & 31) of w, xor the negation flag
     alive = (go && lit_true) ? 0u : alive;
 }
 
-__device__ __forceinline__ void resident_mixed_step(uint32_t l, uint32_t &alive, const uint32_t *sadj, uint32_t vbase,
+__device__ __forceinline__ void resident_mixed_step(uint32_t l, uint32_t &alive, uint32_t sadj, uint32_t vbase,
                                                     uint32_t bucket_vars)
 {
     const uint32_t v = l >> 1;
     const bool go = alive != 0 && (v - vbase) < bucket_vars;               // v - vbase wraps when v < vbase
-    const uint32_t w = go ? sadj[v >> 5] : 0u;
+    const uint32_t w = go ? lds32(sadj + ((v >> 5) << 2)) : 0u;
     const uint32_t lit_true = (__funnelshift_r(w, 0u, v) ^ l) & 1u;
     alive = (go && lit_true) ? 0u : alive;
 }
@@ -179,7 +195,7 @@ __device__ __forceinline__ void gather_round(const uint4 (&L)[K], uint32_t (&a)[
 // violated mask (bit q).  Phase R: shared memory.  Phases G1/G2: non-resident literals of planes [RB, 5)
 // and [5, K) -- two dependent L2 round trips instead of up to K.
 template <int K, int RB, int RC>
-__device__ __forceinline__ uint32_t eval4(const uint4 (&L)[K], uint32_t valid_mask, const uint32_t *sadj,
+__device__ __forceinline__ uint32_t eval4(const uint4 (&L)[K], uint32_t valid_mask, uint32_t sadj,
                                           const uint32_t *gbits, uint32_t vbase, uint32_t bucket_vars)
 {
     uint32_t a[4] = {valid_mask & 1u, valid_mask & 2u, valid_mask & 4u, valid_mask & 8u};
@@ -204,10 +220,8 @@ __device__ __forceinline__ uint32_t eval4(const uint4 (&L)[K], uint32_t valid_ma
 template <int K, int RB, int RC>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const SweepParams p)
 {
-    extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t *sbits = smem;
     const uint32_t lane = threadIdx.x & 31u;
-    WarpCompactor comp{smem + p.bucket_words + (threadIdx.x >> 5) * WBUF, p.viol, p.ctr, 0u, lane};
+    WarpCompactor comp{p.bucket_words + (threadIdx.x >> 5) * WBUF, p.viol, p.ctr, 0u, lane};
 
     const uint32_t t0 = (uint32_t)(((uint64_t)blockIdx.x * p.n_tiles) / gridDim.x);
     const uint32_t t1 = (uint32_t)(((uint64_t)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
@@ -217,6 +231,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const Sw
     cur.init(p, t0);
     const uint32_t bucket_vars = p.bucket_words * 32u;
     const uint32_t *base = p.planes + threadIdx.x * CLAUSES_PER_THREAD;
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(g_smem);
 
     auto load = [&](uint4 (&L)[K], uint32_t tile) {
         const uint32_t *src = base + (uint64_t)tile * TILE;
@@ -224,13 +239,15 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const Sw
         for (int j = 0; j < K; j++) L[j] = ld_stream_v4(src + (uint64_t)j * p.m_pad);
     };
     auto process = [&](const uint4 (&L)[K], uint32_t tile) {
-        cur.enter(p, tile, sbits);
+        cur.enter(p, tile);
         const uint32_t slot0 = tile * TILE + threadIdx.x * CLAUSES_PER_THREAD;
         uint32_t valid = 0;
 #pragma unroll
         for (int q = 0; q < 4; q++) valid |= (slot0 + q < cur.slot_end) ? (1u << q) : 0u;
         const uint32_t vbase = cur.b * bucket_vars;
-        const uint32_t vmask = eval4<K, RB, RC>(L, valid, sbits - (vbase >> 5), p.bits, vbase, bucket_vars);
+        uint32_t sb = smem_base;
+        asm volatile("" : "+r"(sb));          // opaque: lookups below cannot be hoisted above the staging barrier
+        const uint32_t vmask = eval4<K, RB, RC>(L, valid, sb - ((vbase >> 5) << 2), p.bits, vbase, bucket_vars);
         comp.push4(vmask, slot0);
     };
 
@@ -250,10 +267,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const Sw
 template <bool RESIDENT_ALL>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_generic_kernel(const SweepParams p)
 {
-    extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t *sbits = smem;
     const uint32_t lane = threadIdx.x & 31u;
-    WarpCompactor comp{smem + p.bucket_words + (threadIdx.x >> 5) * WBUF, p.viol, p.ctr, 0u, lane};
+    WarpCompactor comp{p.bucket_words + (threadIdx.x >> 5) * WBUF, p.viol, p.ctr, 0u, lane};
 
     const uint32_t t0 = (uint32_t)(((uint64_t)blockIdx.x * p.n_tiles) / gridDim.x);
     const uint32_t t1 = (uint32_t)(((uint64_t)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
@@ -263,7 +278,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_generic_kernel(
     const uint32_t bucket_vars = p.bucket_words * 32u;
 
     for (uint32_t tile = t0; tile < t1; ++tile) {
-        cur.enter(p, tile, sbits);
+        cur.enter(p, tile);
         const uint32_t vbase = cur.b * bucket_vars;
         const uint32_t slot0 = tile * TILE + threadIdx.x * CLAUSES_PER_THREAD;
         const uint32_t *src = p.planes + slot0;
@@ -272,10 +287,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_generic_kernel(
         for (int q = 0; q < 4; q++) alive |= (slot0 + q < cur.slot_end) ? (1u << q) : 0u;
         for (uint32_t j = 0; j < p.k && alive; j++) {
             const uint4 Lj = ld_stream_v4(src + (uint64_t)j * p.m_pad);
-            if (alive & 1u) alive &= ~(literal_true<RESIDENT_ALL>(Lj.x, sbits, p.bits, vbase, bucket_vars) << 0);
-            if (alive & 2u) alive &= ~(literal_true<RESIDENT_ALL>(Lj.y, sbits, p.bits, vbase, bucket_vars) << 1);
-            if (alive & 4u) alive &= ~(literal_true<RESIDENT_ALL>(Lj.z, sbits, p.bits, vbase, bucket_vars) << 2);
-            if (alive & 8u) alive &= ~(literal_true<RESIDENT_ALL>(Lj.w, sbits, p.bits, vbase, bucket_vars) << 3);
+            if (alive & 1u) alive &= ~(literal_true<RESIDENT_ALL>(Lj.x, p.bits, vbase, bucket_vars) << 0);
+            if (alive & 2u) alive &= ~(literal_true<RESIDENT_ALL>(Lj.y, p.bits, vbase, bucket_vars) << 1);
+            if (alive & 4u) alive &= ~(literal_true<RESIDENT_ALL>(Lj.z, p.bits, vbase, bucket_vars) << 2);
+            if (alive & 8u) alive &= ~(literal_true<RESIDENT_ALL>(Lj.w, p.bits, vbase, bucket_vars) << 3);
         }
         comp.push4(alive, slot0);
     }
@@ -288,9 +303,8 @@ __global__ void __launch_bounds__(256) sweep_csr_kernel(const uint64_t *__restri
                                                          uint64_t m, const uint32_t *__restrict__ bits,
                                                          uint32_t *viol, Counters *ctr)
 {
-    __shared__ uint32_t wbuf_all[8 * WBUF];
-    const uint32_t lane = threadIdx.x & 31u;
-    WarpCompactor comp{wbuf_all + (threadIdx.x >> 5) * WBUF, viol, ctr, 0u, lane};
+    const uint32_t lane = threadIdx.x & 31u;                       // launched with 8 * WBUF words of dynamic smem
+    WarpCompactor comp{(threadIdx.x >> 5) * WBUF, viol, ctr, 0u, lane};
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t m_round = (m + 31) / 32 * 32;
     for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < m_round; c += stride) {
@@ -306,7 +320,7 @@ __global__ void __launch_bounds__(256) sweep_csr_kernel(const uint64_t *__restri
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, violated);
         if (bal) {
-            if (violated) comp.wbuf[comp.count + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)c;
+            if (violated) g_smem[comp.wbuf + comp.count + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)c;
             comp.count += __popc(bal);
             if (comp.count >= 32) comp.flush();
         }
@@ -382,7 +396,7 @@ cudaError_t launch_sweep_planes(const SweepParams &p, bool resident_all, uint32_
 cudaError_t launch_sweep_csr(const uint64_t *off, const uint32_t *lit, uint64_t m, const uint32_t *bits,
                              uint32_t *viol, Counters *ctr, uint32_t grid, cudaStream_t s)
 {
-    sweep_csr_kernel<<<grid, 256, 0, s>>>(off, lit, m, bits, viol, ctr);
+    sweep_csr_kernel<<<grid, 256, 8 * WBUF * 4, s>>>(off, lit, m, bits, viol, ctr);
     return cudaGetLastError();
 }
 
