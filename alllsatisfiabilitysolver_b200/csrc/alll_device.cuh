@@ -14,8 +14,10 @@ constexpr uint32_t STREAM_PRIORITY = 2u;
 constexpr uint32_t SWEEP_THREADS = 512;           // one CTA per SM (the staged assignment owns the shared memory), <=128 regs/thread
 constexpr uint32_t CLAUSES_PER_THREAD = 4;        // one 128-bit load per literal plane
 constexpr uint32_t TILE = SWEEP_THREADS * CLAUSES_PER_THREAD;   // clause slots per sweep tile
-constexpr uint32_t WBUF = 64;                     // per-warp violated-id staging entries
+constexpr uint32_t WBUF = 64;                     // per-warp violated-id staging entries (flushed at >= 32, +32 max per push)
+constexpr uint32_t QBUF = 160;                    // per-warp parked-clause queue entries (<= 31 kept + 128 max per push)
 constexpr uint32_t MAX_BUCKETS = 256;
+constexpr uint32_t EAGER_PLANES = 5;              // planes streamed by the sweep; the tail planes are fetched only for surviving clauses
 constexpr uint32_t RESIDENT_CAP = 4;              // at most this many literals of a clause are placed as bucket-resident
 constexpr uint32_t MAX_K = 32;
 constexpr uint32_t INVALID_ID = 0xFFFFFFFFu;

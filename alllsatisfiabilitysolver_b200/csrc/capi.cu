@@ -296,7 +296,7 @@ int alll_create(const alll_config *cfg, alll_handle *out)
     s->device = device;
     s->sm_count = prop.multiProcessorCount;
     s->flags = cfg ? cfg->flags : 0;
-    const uint32_t wbuf_bytes = (SWEEP_THREADS / 32) * WBUF * 4;
+    const uint32_t wbuf_bytes = (SWEEP_THREADS / 32) * (WBUF + QBUF) * 4;
     const uint32_t max_bits = (uint32_t)prop.sharedMemPerBlockOptin - wbuf_bytes - 1024;
     s->smem_budget = (cfg && cfg->sweep_smem_bytes) ? cfg->sweep_smem_bytes : DEFAULT_SWEEP_SMEM;
     s->smem_budget = std::max<uint32_t>(16, std::min(s->smem_budget, max_bits));

@@ -12,9 +12,11 @@
 //     (placed in the first planes) hit the bucket staged by the CTA; remaining literals are only
 //     looked up (from L2) for clauses still unsatisfied after the resident ones -- ~0.3 L2 sectors
 //     per clause instead of ~2;
-//   * evaluation is lazy per clause (expected 2 lookups) and branch-free; non-resident lookups are
-//     issued in two batches (planes [0,5) then [5,k)) so a tile costs two dependent L2 round trips
-//     instead of up to k; the next tile's literals are already in flight (register double buffering);
+//   * only the first E = min(k, 5) planes are streamed.  Evaluation over them is lazy per clause and
+//     branch-free; their non-resident lookups are issued in one batch (one L2 round trip); the next
+//     tile's literals are already in flight (register double buffering).  The 2^-E fraction of clauses
+//     still unsatisfied is parked per warp and finished densely, one clause per lane, fetching the
+//     tail literals only then -- the reference's early exit (Clause.h:42-44) applied to HBM traffic;
 //   * violated slots are compacted per warp with __ballot_sync/__popc into a shared-memory staging
 //     buffer and flushed with one global atomicAdd per >= 32 entries.
 #include "alll_device.cuh"
@@ -43,6 +45,16 @@ struct WarpCompactor {
         for (uint32_t i = lane; i < count; i += 32) viol[g + i] = g_smem[wbuf + i];
         __syncwarp();
         count = 0;
+    }
+
+    // One candidate per lane.  Must be called by the whole warp.
+    __device__ __forceinline__ void push1(bool mine, uint32_t slot)
+    {
+        const uint32_t bal = __ballot_sync(0xffffffffu, mine);
+        if (!bal) return;
+        if (mine) g_smem[wbuf + count + __popc(bal & ((1u << lane) - 1u))] = slot;
+        count += __popc(bal);
+        if (count >= 32) flush();
     }
 
     // vmask: bit q set <=> clause slot (slot0 + q) is violated.  Must be called by the whole warp.
@@ -92,22 +104,29 @@ struct TileCursor {
         slot_end = p.segs[b].slot_end;
         loaded = 0xFFFFFFFFu;
     }
-    // Moves to `tile`; (re)stages the bucket's slice of the assignment into shared memory when it changes.
-    __device__ __forceinline__ void enter(const SweepParams &p, uint32_t tile)
+    // Moves to `tile`; returns true when its bucket differs from the staged one (caller must then stage()).
+    __device__ __forceinline__ bool advance(const SweepParams &p, uint32_t tile)
     {
         while (tile >= bucket_tile_end) {
             ++b;
             bucket_tile_end = (b + 1 < p.n_buckets) ? p.segs[b + 1].tile_begin : p.n_tiles;
             slot_end = p.segs[b].slot_end;
         }
-        if (b != loaded) {
-            __syncthreads();                      // everyone is done with the previous bucket's bits
-            const uint4 *src = reinterpret_cast<const uint4 *>(p.bits + (uint64_t)b * p.bucket_words);
-            for (uint32_t i = threadIdx.x; i < p.bucket_words / 4; i += SWEEP_THREADS)
-                reinterpret_cast<uint4 *>(g_smem)[i] = __ldg(src + i);
-            __syncthreads();
-            loaded = b;
-        }
+        return b != loaded;
+    }
+    // Stages bucket b's slice of the assignment into shared memory (whole CTA).
+    __device__ __forceinline__ void stage(const SweepParams &p)
+    {
+        __syncthreads();                      // everyone is done with the previous bucket's bits
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.bits + (uint64_t)b * p.bucket_words);
+        for (uint32_t i = threadIdx.x; i < p.bucket_words / 4; i += SWEEP_THREADS)
+            reinterpret_cast<uint4 *>(g_smem)[i] = __ldg(src + i);
+        __syncthreads();
+        loaded = b;
+    }
+    __device__ __forceinline__ void enter(const SweepParams &p, uint32_t tile)
+    {
+        if (advance(p, tile)) stage(p);
     }
 };
 
@@ -191,37 +210,94 @@ __device__ __forceinline__ void gather_round(const uint4 (&L)[K], uint32_t (&a)[
     }
 }
 
-// Evaluates the 4 clauses held in L[0..K) (component q of every plane = clause slot0+q); returns the
-// violated mask (bit q).  Phase R: shared memory.  Phases G1/G2: non-resident literals of planes [RB, 5)
-// and [5, K) -- two dependent L2 round trips instead of up to K.
-template <int K, int RB, int RC>
-__device__ __forceinline__ uint32_t eval4(const uint4 (&L)[K], uint32_t valid_mask, uint32_t sadj,
+// Evaluates the first E literals (the planes held in registers) of 4 clauses; component q of every plane is
+// clause slot0+q.  Returns the still-unsatisfied mask (bit q).  Phase R: shared memory.  Phase G: the
+// non-resident literals of planes [RB, E), all issued at once -- one L2 round trip.
+template <int E, int RB, int RC>
+__device__ __forceinline__ uint32_t eval4(const uint4 (&L)[E], uint32_t valid_mask, uint32_t sadj,
                                           const uint32_t *gbits, uint32_t vbase, uint32_t bucket_vars)
 {
+    constexpr int R_END = RC < E ? RC : E;
     uint32_t a[4] = {valid_mask & 1u, valid_mask & 2u, valid_mask & 4u, valid_mask & 8u};
 #pragma unroll
-    for (int j = 0; j < RC; j++)
+    for (int j = 0; j < R_END; j++)
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             if (j < RB) resident_only_step(comp(L[j], q), a[q], sadj);
             else resident_mixed_step(comp(L[j], q), a[q], sadj, vbase, bucket_vars);
         }
-    if (RB < K) {
-        constexpr int SPLIT = K < 5 ? K : 5;
-        gather_round<K, RB, RC, RB, SPLIT>(L, a, gbits, vbase, bucket_vars);
-        gather_round<K, RB, RC, SPLIT, K>(L, a, gbits, vbase, bucket_vars);
-    }
+    gather_round<E, RB, RC, (RB < E ? RB : E), E>(L, a, gbits, vbase, bucket_vars);
     return (a[0] ? 1u : 0u) | (a[1] ? 2u : 0u) | (a[2] ? 4u : 0u) | (a[3] ? 8u : 0u);
 }
 
-// Compile-time clause width K.  One CTA per SM; each thread owns 4 consecutive clause slots of a tile and
-// keeps TWO tiles of literals in registers: the next tile's K x 128-bit loads are in flight while the
-// current tile is evaluated (register double buffering; 512 threads x <=128 registers).
-template <int K, int RB, int RC>
+// Clauses that survive their first E literals (a 2^-E fraction) are parked per warp and finished densely, 32
+// at a time, one clause per lane: only then are their remaining K-E literals fetched (scalar loads) and
+// looked up.  The planes [E, K) are therefore never streamed: like the reference's early exit
+// (Clause.h:42-44), most clauses are decided without reading their tail literals.
+template <int K, int E, bool RESIDENT_ALL>
+struct SurvivorQueue {
+    uint32_t qbuf;       // index in g_smem of this warp's queue (QBUF entries)
+    uint32_t count;      // warp-uniform
+    uint32_t lane;
+
+    __device__ __forceinline__ void push4(uint32_t mask, uint32_t slot0)
+    {
+        if (!__any_sync(0xffffffffu, mask != 0)) return;
+        const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const bool mine = (mask >> q) & 1u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, mine);
+            if (mine) g_smem[qbuf + count + __popc(bal & lt)] = slot0 + q;
+            count += __popc(bal);
+        }
+    }
+
+    // Finishes parked clauses while at least `keep` + 1 are queued (keep = 31: full batches only; 0: everything).
+    __device__ __forceinline__ void drain(uint32_t keep, WarpCompactor &out, const SweepParams &p, uint32_t vbase,
+                                          uint32_t bucket_vars)
+    {
+        while (count > keep) {
+            __syncwarp();
+            const uint32_t n = count < 32u ? count : 32u;
+            const bool act = lane < n;
+            const uint32_t slot = act ? g_smem[qbuf + count - n + lane] : 0u;
+            constexpr int T = K > E ? K - E : 1;     // tail planes (T = 1 only keeps the arrays legal when E == K)
+            uint32_t l[T];
+#pragma unroll
+            for (int j = 0; j < K - E; j++) l[j] = act ? __ldg(p.planes + (uint64_t)(E + j) * p.m_pad + slot) : 0u;
+            uint32_t w[T];
+#pragma unroll
+            for (int j = 0; j < K - E; j++) {                 // all lookups at once: this path is rare and dense
+                const uint32_t v = l[j] >> 1;
+                if (RESIDENT_ALL) w[j] = act ? g_smem[v >> 5] : 0u;
+                else {
+                    const uint32_t rel = v - vbase;
+                    w[j] = !act ? 0u : (rel < bucket_vars) ? g_smem[rel >> 5] : __ldg(p.bits + (v >> 5));
+                }
+            }
+            bool violated = act;
+#pragma unroll
+            for (int j = 0; j < K - E; j++) violated = violated && !(((w[j] >> ((l[j] >> 1) & 31u)) ^ l[j]) & 1u);
+            count -= n;
+            __syncwarp();
+            out.push1(violated, slot);
+        }
+    }
+};
+
+// Compile-time clause width K, of which the first E planes are streamed.  One CTA per SM; each thread owns 4
+// consecutive clause slots of a tile and keeps TWO tiles of literals in registers: the next tile's E x 128-bit
+// loads are in flight while the current tile is evaluated (register double buffering).
+template <int K, int RB, int RC, int E>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const SweepParams p)
 {
+    constexpr bool RESIDENT_ALL = RB >= K;
+    constexpr int RBE = RB < E ? RB : E;
     const uint32_t lane = threadIdx.x & 31u;
-    WarpCompactor comp{p.bucket_words + (threadIdx.x >> 5) * WBUF, p.viol, p.ctr, 0u, lane};
+    const uint32_t warp = threadIdx.x >> 5;
+    WarpCompactor out{p.bucket_words + warp * WBUF, p.viol, p.ctr, 0u, lane};
+    SurvivorQueue<K, E, RESIDENT_ALL> parked{p.bucket_words + (SWEEP_THREADS / 32) * WBUF + warp * QBUF, 0u, lane};
 
     const uint32_t t0 = (uint32_t)(((uint64_t)blockIdx.x * p.n_tiles) / gridDim.x);
     const uint32_t t1 = (uint32_t)(((uint64_t)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
@@ -233,13 +309,17 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const Sw
     const uint32_t *base = p.planes + threadIdx.x * CLAUSES_PER_THREAD;
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(g_smem);
 
-    auto load = [&](uint4 (&L)[K], uint32_t tile) {
+    auto load = [&](uint4 (&L)[E], uint32_t tile) {
         const uint32_t *src = base + (uint64_t)tile * TILE;
 #pragma unroll
-        for (int j = 0; j < K; j++) L[j] = ld_stream_v4(src + (uint64_t)j * p.m_pad);
+        for (int j = 0; j < E; j++) L[j] = ld_stream_v4(src + (uint64_t)j * p.m_pad);
     };
-    auto process = [&](const uint4 (&L)[K], uint32_t tile) {
-        cur.enter(p, tile);
+    auto process = [&](const uint4 (&L)[E], uint32_t tile) {
+        const uint32_t prev_vbase = cur.b * bucket_vars;
+        if (cur.advance(p, tile)) {
+            if constexpr (E < K) parked.drain(0u, out, p, prev_vbase, bucket_vars);   // parked clauses belong to the old bucket
+            cur.stage(p);
+        }
         const uint32_t slot0 = tile * TILE + threadIdx.x * CLAUSES_PER_THREAD;
         uint32_t valid = 0;
 #pragma unroll
@@ -247,11 +327,16 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const Sw
         const uint32_t vbase = cur.b * bucket_vars;
         uint32_t sb = smem_base;
         asm volatile("" : "+r"(sb));          // opaque: lookups below cannot be hoisted above the staging barrier
-        const uint32_t vmask = eval4<K, RB, RC>(L, valid, sb - ((vbase >> 5) << 2), p.bits, vbase, bucket_vars);
-        comp.push4(vmask, slot0);
+        const uint32_t alive = eval4<E, RBE, RC>(L, valid, sb - ((vbase >> 5) << 2), p.bits, vbase, bucket_vars);
+        if constexpr (E < K) {
+            parked.push4(alive, slot0);
+            parked.drain(31u, out, p, vbase, bucket_vars);
+        } else {
+            out.push4(alive, slot0);
+        }
     };
 
-    uint4 A[K], B[K];
+    uint4 A[E], B[E];
     load(A, t0);
     for (uint32_t tile = t0; tile < t1; tile += 2) {
         if (tile + 1 < t1) load(B, tile + 1);
@@ -260,7 +345,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const Sw
         if (tile + 2 < t1) load(A, tile + 2);
         process(B, tile + 1);
     }
-    if (comp.count) comp.flush();
+    if constexpr (E < K) parked.drain(0u, out, p, cur.b * bucket_vars, bucket_vars);
+    if (out.count) out.flush();
 }
 
 // Run-time clause width (k > 8): planes are loaded lazily level by level; no prefetch.
@@ -333,9 +419,10 @@ __global__ void __launch_bounds__(256) sweep_csr_kernel(const uint64_t *__restri
 template <int K, int RB, int RC>
 static cudaError_t launch_planes(const SweepParams &p, uint32_t grid, size_t smem, cudaStream_t s, bool configure_only)
 {
+    constexpr int E = K < (int)EAGER_PLANES ? K : (int)EAGER_PLANES;
     if (configure_only)   // function attributes are per device: the handle configures its kernel once at upload
-        return cudaFuncSetAttribute(sweep_planes_kernel<K, RB, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    sweep_planes_kernel<K, RB, RC><<<grid, SWEEP_THREADS, smem, s>>>(p);
+        return cudaFuncSetAttribute(sweep_planes_kernel<K, RB, RC, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sweep_planes_kernel<K, RB, RC, E><<<grid, SWEEP_THREADS, smem, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -378,7 +465,7 @@ static cudaError_t dispatch_k(const SweepParams &p, bool resident_all, uint32_t 
 
 size_t sweep_planes_smem_bytes(uint32_t bucket_words)
 {
-    return (size_t)bucket_words * 4 + (SWEEP_THREADS / 32) * WBUF * 4;
+    return (size_t)bucket_words * 4 + (SWEEP_THREADS / 32) * (WBUF + QBUF) * 4;   // bits | violated staging | parked queues
 }
 
 cudaError_t configure_sweep_planes(const SweepParams &p, bool resident_all)
