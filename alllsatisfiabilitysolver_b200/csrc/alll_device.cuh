@@ -82,6 +82,13 @@ __device__ __forceinline__ uint4 ld_stream_v4(const uint32_t *p)
     return r;
 }
 
+// TMA bulk prefetch of a contiguous global range into L2 (no destination, no register cost): one thread pulls
+// a whole 8 KB plane segment of a future tile from HBM so that the later 128-bit loads hit L2.
+__device__ __forceinline__ void tma_prefetch_l2(const void *p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(bytes) : "memory");
+}
+
 // ---- clause access for the sparse kernels (MIS / resample / id mapping) ----
 struct ClauseView {
     // fixed-k literal planes: lit j of slot p is planes[j * m_pad + p]
@@ -140,6 +147,8 @@ struct SweepParams {
     uint32_t *viol;             // out: violated slots
     Counters *ctr;
     uint32_t k;
+    uint32_t eager;             // tuning: planes streamed eagerly (0 = default EAGER_PLANES)
+    uint32_t prefetch_tiles;    // tiles of L2 prefetch distance ahead of the register double buffer (0 = off)
     uint32_t min_resident;      // min over clauses of the number of resident-placed literals (0 when unknown)
 };
 

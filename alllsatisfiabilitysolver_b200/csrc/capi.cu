@@ -85,6 +85,13 @@ void free_instance(alll_handle h)
 
 inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
+// flags bits 16..23: L2 prefetch distance in tiles; 0 = default (2, measured best on B200), 0xFF = off
+inline uint32_t prefetch_distance(uint32_t flags)
+{
+    const uint32_t d = (flags >> 16) & 0xFFu;
+    return d == 0 ? 2u : (d == 0xFFu ? 0u : d);
+}
+
 ClauseView clause_view(alll_handle h)
 {
     ClauseView cv;
@@ -206,7 +213,7 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
 
     if (int rc = alloc_common(h)) return rc;
     SweepParams sp{};
-    sp.bucket_words = h->bucket_words; sp.k = k; sp.min_resident = h->min_resident;
+    sp.bucket_words = h->bucket_words; sp.k = k; sp.min_resident = h->min_resident; sp.eager = (h->flags >> 8) & 0xFFu; sp.prefetch_tiles = prefetch_distance(h->flags);
     CK(configure_sweep_planes(sp, h->resident_all));
     h->sweep_grid = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)h->sm_count, h->n_tiles));
     CK(cudaStreamSynchronize(h->stream));
@@ -222,7 +229,7 @@ int enqueue_sweep(alll_handle h)
         SweepParams sp{};
         sp.planes = h->d_planes; sp.m_pad = h->m_pad; sp.bits = h->d_bits; sp.n_words = h->n_words_alloc;
         sp.bucket_words = h->bucket_words; sp.n_buckets = h->n_buckets; sp.n_tiles = h->n_tiles;
-        sp.segs = h->d_segs; sp.viol = h->d_viol; sp.ctr = h->d_ctr; sp.k = h->k; sp.min_resident = h->min_resident;
+        sp.segs = h->d_segs; sp.viol = h->d_viol; sp.ctr = h->d_ctr; sp.k = h->k; sp.min_resident = h->min_resident; sp.eager = (h->flags >> 8) & 0xFFu; sp.prefetch_tiles = prefetch_distance(h->flags);
         CK(launch_sweep_planes(sp, h->resident_all, h->sweep_grid, h->stream));
     } else {
         if (h->m == 0) return ALLL_OK;

@@ -336,13 +336,26 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const Sw
         }
     };
 
+    // HBM -> L2: one thread per CTA bulk-prefetches the E plane segments of the tile `dist` ahead of the register
+    // double buffer, so enough bytes are in flight to cover the loaded DRAM latency without spending registers.
+    const uint32_t dist = p.prefetch_tiles;
+    auto prefetch = [&](uint32_t tile) {
+        if (threadIdx.x == 0 && dist != 0 && tile < t1) {
+#pragma unroll
+            for (int j = 0; j < E; j++) tma_prefetch_l2(p.planes + (uint64_t)j * p.m_pad + (uint64_t)tile * TILE, TILE * 4);
+        }
+    };
+    for (uint32_t d = 2; d < 2 + dist; d++) prefetch(t0 + d);
+
     uint4 A[E], B[E];
     load(A, t0);
     for (uint32_t tile = t0; tile < t1; tile += 2) {
         if (tile + 1 < t1) load(B, tile + 1);
+        prefetch(tile + 2 + dist);
         process(A, tile);
         if (tile + 1 >= t1) break;
         if (tile + 2 < t1) load(A, tile + 2);
+        prefetch(tile + 3 + dist);
         process(B, tile + 1);
     }
     if constexpr (E < K) parked.drain(0u, out, p, cur.b * bucket_vars, bucket_vars);
@@ -416,14 +429,26 @@ __global__ void __launch_bounds__(256) sweep_csr_kernel(const uint64_t *__restri
 
 // ---- launchers ------------------------------------------------------------------------
 
-template <int K, int RB, int RC>
-static cudaError_t launch_planes(const SweepParams &p, uint32_t grid, size_t smem, cudaStream_t s, bool configure_only)
+template <int K, int RB, int RC, int E>
+static cudaError_t launch_planes_e(const SweepParams &p, uint32_t grid, size_t smem, cudaStream_t s, bool configure_only)
 {
-    constexpr int E = K < (int)EAGER_PLANES ? K : (int)EAGER_PLANES;
     if (configure_only)   // function attributes are per device: the handle configures its kernel once at upload
         return cudaFuncSetAttribute(sweep_planes_kernel<K, RB, RC, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     sweep_planes_kernel<K, RB, RC, E><<<grid, SWEEP_THREADS, smem, s>>>(p);
     return cudaGetLastError();
+}
+
+// p.eager (tuning knob, 0 = default) picks how many planes are streamed; only wide clauses have a choice.
+template <int K, int RB, int RC>
+static cudaError_t launch_planes(const SweepParams &p, uint32_t grid, size_t smem, cudaStream_t s, bool configure_only)
+{
+    constexpr int E = K < (int)EAGER_PLANES ? K : (int)EAGER_PLANES;
+    if constexpr (K >= 7) {
+        if (p.eager == 4) return launch_planes_e<K, RB, RC, 4>(p, grid, smem, s, configure_only);
+        if (p.eager == 6) return launch_planes_e<K, RB, RC, 6>(p, grid, smem, s, configure_only);
+        if (p.eager == (uint32_t)K) return launch_planes_e<K, RB, RC, K>(p, grid, smem, s, configure_only);
+    }
+    return launch_planes_e<K, RB, RC, E>(p, grid, smem, s, configure_only);
 }
 
 template <bool R>

@@ -58,6 +58,10 @@ typedef struct {
 } alll_config;
 
 #define ALLL_FLAG_NO_BUCKETING 1u  /* keep clause order; gather non-resident assignment words from L2 (debug / comparison) */
+/* tuning knobs (0 = measured default): bits 8..15 literal planes streamed eagerly (4..8, default 5);
+ * bits 16..23 L2 bulk-prefetch distance in tiles (default 2; 0xFF = off) */
+#define ALLL_FLAG_EAGER_PLANES(e)   ((uint32_t)(e) << 8)
+#define ALLL_FLAG_PREFETCH_TILES(d) ((uint32_t)(d) << 16)
 
 /* Statistics{} of SATInstance.h:25-32 plus device-side counters.
  * n_iterations = resample rounds + 1 (the terminal all-satisfied sweep counts, :261,:285-287);
