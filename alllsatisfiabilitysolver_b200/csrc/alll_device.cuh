@@ -128,6 +128,10 @@ struct Counters {
     unsigned int last_n_viol;
     unsigned int last_n_s;
     unsigned long long last_resampled;
+    // set by the MIS kernel that saw an empty violated set: kernels of rounds the host enqueued speculatively
+    // behind it return immediately, so the round loop never has to wait for the host between rounds
+    unsigned int done;
+    unsigned int pad;
 };
 
 struct BucketSeg {

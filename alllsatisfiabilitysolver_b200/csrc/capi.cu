@@ -20,6 +20,7 @@ thread_local std::string g_create_error = "";
 
 constexpr uint32_t DEFAULT_SWEEP_SMEM = 192u * 1024u;
 constexpr int MAX_TIMED_ROUNDS = 256;
+constexpr int ROUNDS_IN_FLIGHT = 3;      // rounds the host enqueues ahead of the last one it has seen retire
 
 } // namespace
 
@@ -36,6 +37,7 @@ struct alll_solver {
     bool has_instance = false;
     uint64_t n_vars = 0, m = 0, m_pad = 0;
     uint32_t k = 0;                      // 0 = CSR
+    uint32_t kmax = 0;                   // widest clause
     uint32_t n_words_alloc = 0, bucket_words = 0, n_buckets = 1, n_tiles = 0;
     bool resident_all = true;
     uint32_t min_resident = 0;           // measured by the bucketing pass; selects the sweep specialisation
@@ -50,6 +52,8 @@ struct alll_solver {
     uint8_t *d_state = nullptr, *d_bools = nullptr;
     Counters *d_ctr = nullptr;
     Counters *h_ctr = nullptr;           // pinned
+    Counters *h_ring = nullptr;          // pinned [ROUNDS_IN_FLIGHT]: per-round snapshots for the pipelined loop
+    cudaEvent_t ev_round[ROUNDS_IN_FLIGHT] = {};
     uint32_t sweep_grid = 1, mis_grid = 1;
     std::vector<cudaEvent_t> ev;         // 2 * MAX_TIMED_ROUNDS + 2
 };
@@ -114,6 +118,7 @@ int alloc_common(alll_handle h)
     CK(cudaMalloc(&h->d_state, m1));
     CK(cudaMalloc(&h->d_bools, n1));
     CK(launch_reset_counters(h->d_ctr, 1, h->stream)); h->launches++;
+    CK(mis_configure(h->device, h->kmax, &h->mis_grid));
     return ALLL_OK;
 }
 
@@ -129,7 +134,7 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     free_instance(h);
     if (int rc = check_sizes(h, n_vars, m)) return rc;
     if (k < 1 || k > MAX_K) return fail(h, ALLL_BAD_ARG, "k must be in [1, 32] for the fixed-width layout");
-    h->n_vars = n_vars; h->m = m; h->k = k;
+    h->n_vars = n_vars; h->m = m; h->k = k; h->kmax = k;
 
     const uint32_t n_words4 = (uint32_t)align_up((n_vars + 31) / 32, 4);
     const uint32_t budget_words = h->smem_budget / 16 * 4;
@@ -242,9 +247,9 @@ int enqueue_sweep(alll_handle h)
 
 int enqueue_mis_resample(alll_handle h, uint64_t seed, uint32_t round)
 {
-    CK(launch_mis_resample_args(clause_view(h), h->d_viol, h->d_state, h->d_s, h->d_claim, h->d_bits, h->d_ctr,
-                                seed, round, h->mis_grid, h->stream));
-    h->launches++;
+    CK(launch_mis_resample_args(clause_view(h), h->kmax, h->d_viol, h->d_state, h->d_s, h->d_claim, h->d_bits,
+                                h->d_ctr, seed, round, h->mis_grid, h->stream));
+    h->launches += 2;                    // cluster kernel + cooperative grid kernel
     return ALLL_OK;
 }
 
@@ -312,7 +317,9 @@ int alll_create(const alll_config *cfg, alll_handle *out)
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaStreamCreate failed"));
     if (cudaMalloc(&s->d_ctr, sizeof(Counters)) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaMalloc(counters) failed"));
     if (cudaMallocHost(&s->h_ctr, sizeof(Counters)) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaMallocHost failed"));
-    if (mis_max_grid(device, &s->mis_grid) != cudaSuccess || s->mis_grid == 0) return bail(fail(h, ALLL_CUDA_ERROR, "occupancy query failed"));
+    if (cudaMallocHost(&s->h_ring, sizeof(Counters) * ROUNDS_IN_FLIGHT) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaMallocHost failed"));
+    for (auto &ev : s->ev_round)
+        if (cudaEventCreate(&ev) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaEventCreate failed"));
     s->ev.resize(2 * MAX_TIMED_ROUNDS + 2);
     for (auto &ev : s->ev)
         if (cudaEventCreate(&ev) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaEventCreate failed"));
@@ -329,6 +336,8 @@ int alll_destroy(alll_handle h)
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->d_ctr) cudaFree(h->d_ctr);
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
+    if (h->h_ring) cudaFreeHost(h->h_ring);
+    for (auto &ev : h->ev_round) if (ev) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return ALLL_OK;
@@ -368,17 +377,20 @@ int alll_upload_csr(alll_handle h, uint64_t n_vars, uint64_t m, const uint64_t *
     // width scan: refuse empty clauses (Clause.h:35-45 makes them unsatisfiable), route uniform width to planes
     bool uniform = m > 0;
     const uint64_t k0 = m ? off[1] - off[0] : 0;
+    uint64_t kmax = 0;
     for (uint64_t c = 0; c < m; c++) {
         if (off[c + 1] < off[c]) return fail(h, ALLL_BAD_ARG, "offsets must be non-decreasing");
         const uint64_t w = off[c + 1] - off[c];
         if (w == 0) return fail(h, ALLL_EMPTY_CLAUSE, "clause " + std::to_string(c) + " is empty and can never be satisfied");
         uniform &= (w == k0);
+        kmax = std::max(kmax, w);
     }
     if (uniform && k0 <= MAX_K) return alll_upload_fixedk(h, n_vars, m, (uint32_t)k0, lit + off[0]);
 
     free_instance(h);
     if (int rc = check_sizes(h, n_vars, m)) return rc;
-    h->n_vars = n_vars; h->m = m; h->k = 0; h->m_pad = m; h->n_buckets = 1; h->n_tiles = 0;
+    if (kmax > 0xFFFFFFFFull) return fail(h, ALLL_BAD_ARG, "clause too wide");
+    h->n_vars = n_vars; h->m = m; h->k = 0; h->kmax = (uint32_t)kmax; h->m_pad = m; h->n_buckets = 1; h->n_tiles = 0;
     h->n_words_alloc = (uint32_t)align_up((n_vars + 31) / 32, 4);
     h->bucket_words = 0; h->resident_all = false;
     h->n_lit = m ? off[m] - off[0] : 0;
@@ -475,32 +487,49 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
     std::memset(stats, 0, sizeof(*stats));
     const uint64_t launches0 = h->launches;
     CK(launch_reset_counters(h->d_ctr, 1, h->stream)); h->launches++;
-    cudaEvent_t ev_begin = h->ev[2 * MAX_TIMED_ROUNDS], ev_end = h->ev[2 * MAX_TIMED_ROUNDS + 1];
+    cudaEvent_t ev_begin = h->ev[2 * MAX_TIMED_ROUNDS];
     CK(cudaEventRecord(ev_begin, h->stream));
-    int status = ALLL_OK;
-    uint64_t round = 0;
-    int timed = 0;
-    for (;;) {
-        const bool time_this = timed < MAX_TIMED_ROUNDS;
-        if (time_this) CK(cudaEventRecord(h->ev[2 * timed], h->stream));
-        if (int rc = enqueue_sweep(h)) return rc;
-        if (time_this) { CK(cudaEventRecord(h->ev[2 * timed + 1], h->stream)); timed++; }
-        if (int rc = enqueue_mis_resample(h, seed, (uint32_t)round)) return rc;
-        if (int rc = fetch_counters(h)) return rc;
-        if (h->h_ctr->last_n_viol == 0) break;            // SATInstance.h:285-287
-        round++;
-        if (round >= max_rounds) { status = ALLL_MAX_ROUNDS; break; }
+
+    // Pipelined round loop (replaces the per-round host control of SATInstance.h:260-311): up to
+    // ROUNDS_IN_FLIGHT rounds are enqueued ahead of the last round whose counters the host has seen.  The
+    // MIS kernel that finds the violated set empty raises ctr->done; kernels enqueued behind it return at
+    // entry, so the device never idles waiting for the host and nothing runs past the terminal sweep.
+    int status = ALLL_MAX_ROUNDS;
+    uint64_t issued = 0, retired = 0;
+    cudaEvent_t ev_last = ev_begin;
+    if (max_rounds == 0) max_rounds = 1;             // the loop body always runs once (SATInstance.h:260-261)
+    while (retired < max_rounds) {
+        while (issued < max_rounds && issued - retired < (uint64_t)ROUNDS_IN_FLIGHT) {
+            const bool time_this = issued < (uint64_t)MAX_TIMED_ROUNDS;
+            if (time_this) CK(cudaEventRecord(h->ev[2 * issued], h->stream));
+            if (int rc = enqueue_sweep(h)) return rc;
+            if (time_this) CK(cudaEventRecord(h->ev[2 * issued + 1], h->stream));
+            if (int rc = enqueue_mis_resample(h, seed, (uint32_t)issued)) return rc;
+            const int slot = (int)(issued % ROUNDS_IN_FLIGHT);
+            CK(cudaMemcpyAsync(&h->h_ring[slot], h->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaEventRecord(h->ev_round[slot], h->stream));
+            issued++;
+        }
+        const int slot = (int)(retired % ROUNDS_IN_FLIGHT);
+        CK(cudaEventSynchronize(h->ev_round[slot]));
+        ev_last = h->ev_round[slot];
+        retired++;
+        if (h->h_ring[slot].last_n_viol == 0) { status = ALLL_OK; break; }   // SATInstance.h:285-287
     }
-    CK(cudaEventRecord(ev_end, h->stream));
-    CK(cudaEventSynchronize(ev_end));
+    const uint64_t useful_rounds = retired;              // rounds whose sweep actually ran (incl. the terminal one)
     float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+    if (useful_rounds) CK(cudaEventElapsedTime(&ms, ev_begin, ev_last));
+    CK(cudaStreamSynchronize(h->stream));                 // drain the speculative (no-op) rounds
     double sweep_ms = 0.0;
+    const int timed = (int)std::min<uint64_t>(useful_rounds, MAX_TIMED_ROUNDS);
     for (int i = 0; i < timed; i++) {
         float t = 0.f;
         CK(cudaEventElapsedTime(&t, h->ev[2 * i], h->ev[2 * i + 1]));
         sweep_ms += t;
     }
+    if (int rc = fetch_counters(h)) return rc;
+    CK(launch_reset_counters(h->d_ctr, 0, h->stream)); h->launches++;      // clears `done` for the single-step calls
+    CK(cudaStreamSynchronize(h->stream));
     const Counters &c = *h->h_ctr;
     stats->n_iterations = c.n_iterations;
     stats->n_resamples = c.n_resamples;

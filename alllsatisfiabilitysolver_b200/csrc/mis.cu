@@ -1,4 +1,4 @@
-// mis.cu -- K3 (maximal independent set of the violated clauses) + K4 (resample), one cooperative kernel.
+// mis.cu -- K3 (maximal independent set of the violated clauses) + K4 (resample).
 //
 // Replaces populate_mis_parallel (SATInstance.h:391-451; greedy, O(|S|*|U|*k^2), one OpenMP fork/join per
 // picked clause) and resample_clauses (SATInstance.h:340-365).
@@ -17,7 +17,15 @@
 //     written with atomicOr/atomicAnd on the packed word (idempotent, so a variable occurring twice in a
 //     clause is harmless).  The same pass restores claim[var] = FREE for everything U touched.
 //
-// |U| <= SMALL_U runs in CTA 0 alone with __syncthreads(); larger sets use grid-wide barriers.
+// Latency structure: the literals, priority and id of every violated clause are read ONCE into shared
+// memory (they live scattered over k literal planes -- k DRAM round trips), and all claim reads of a
+// phase are issued together, so a phase costs ~2 memory round trips however wide the clauses are.
+//
+// Two kernels are enqueued per round and decide on the device which one acts (the host does not know
+// |U|: rounds are enqueued speculatively, see capi.cu):
+//   mis_cluster_kernel : |U| <= 8192 -- one thread-block cluster of 8 x 1024 threads, one clause per
+//                        thread, phases separated by the hardware cluster barrier;
+//   mis_grid_kernel    : larger |U| -- cooperative launch, phases separated by grid-wide barriers.
 #include <cooperative_groups.h>
 
 #include "alll_device.cuh"
@@ -26,8 +34,12 @@ namespace cg = cooperative_groups;
 
 namespace alll {
 
-constexpr uint32_t MIS_THREADS = 256;
-constexpr uint32_t SMALL_U = 4096;
+constexpr uint32_t GRID_THREADS = 256;
+constexpr uint32_t CL_THREADS = 1024;
+constexpr uint32_t CL_SIZE = 8;
+constexpr uint32_t CLUSTER_U = CL_THREADS * CL_SIZE;    // violated sets up to this size go to the cluster kernel
+constexpr uint32_t GRID_SMEM_WORDS_PER_THREAD = 48;     // 48 KB per 256-thread CTA: 4 CTAs per SM
+constexpr uint32_t EXTRA = 3;                           // cached per clause besides its literals: priority, id, width
 
 enum : uint8_t { UNDECIDED = 0, IN_SET = 1, DROPPED = 2 };
 
@@ -41,102 +53,150 @@ struct MisParams {
     Counters *ctr;
     uint64_t seed;
     uint32_t round;
-    uint32_t do_resample;       // 0: MIS only (alll_round with inspection still resamples; kept for tests)
+    uint32_t kmax;              // widest clause
+    uint32_t cache_items;       // clauses per thread whose literals fit the shared-memory cache
 };
+
+extern __shared__ uint32_t mis_smem[];
 
 // claim[] and the counters are written by other SMs between barriers: read them at L2 (L1 is not coherent).
 __device__ __forceinline__ unsigned long long ld_claim(const unsigned long long *p) { return __ldcg(p); }
 __device__ __forceinline__ unsigned int ld_u32(const unsigned int *p) { return __ldcg(p); }
 
-template <bool SMALL>
-__device__ __forceinline__ void phase_barrier(cg::grid_group &grid)
+struct GridBarrier {
+    cg::grid_group g;
+    __device__ __forceinline__ void sync() { g.sync(); }
+};
+struct ClusterBarrier {
+    __device__ __forceinline__ void sync() { cg::this_cluster().sync(); }
+};
+
+// Per-thread view of one violated clause: cached in shared memory (item < cache_items) or read through.
+struct Item {
+    uint32_t base;      // index of word 0 of this item's cache slot for this thread (stride blockDim.x), or ~0u
+    uint32_t slot, k, prio, id;
+
+    __device__ __forceinline__ uint32_t lit(const MisParams &p, uint32_t j) const
+    {
+        return base != 0xFFFFFFFFu ? mis_smem[base + j * blockDim.x] : p.cv.literal(slot, j);
+    }
+};
+
+__device__ __forceinline__ Item open_item(const MisParams &p, uint32_t it, uint32_t i, bool fill)
 {
-    if (SMALL) __syncthreads(); else grid.sync();
+    Item x;
+    const uint32_t slotw = p.kmax + EXTRA;
+    x.slot = p.viol[i];
+    if (it < p.cache_items) {
+        x.base = it * slotw * blockDim.x + threadIdx.x;
+        if (fill) {
+            x.k = p.cv.width(x.slot);
+            x.id = p.cv.id(x.slot);
+            x.prio = clause_priority(p.seed, p.round, x.id);
+#pragma unroll 8
+            for (uint32_t j = 0; j < x.k; j++) mis_smem[x.base + j * blockDim.x] = p.cv.literal(x.slot, j);
+            mis_smem[x.base + (p.kmax + 0) * blockDim.x] = x.prio;
+            mis_smem[x.base + (p.kmax + 1) * blockDim.x] = x.id;
+            mis_smem[x.base + (p.kmax + 2) * blockDim.x] = x.k;
+        } else {
+            x.prio = mis_smem[x.base + (p.kmax + 0) * blockDim.x];
+            x.id = mis_smem[x.base + (p.kmax + 1) * blockDim.x];
+            x.k = mis_smem[x.base + (p.kmax + 2) * blockDim.x];
+        }
+    } else {
+        x.base = 0xFFFFFFFFu;
+        x.k = p.cv.width(x.slot);
+        x.id = p.cv.id(x.slot);
+        x.prio = clause_priority(p.seed, p.round, x.id);
+    }
+    return x;
 }
 
-template <bool SMALL>
-__device__ void mis_resample_body(const MisParams &p, cg::grid_group &grid, uint32_t n_u)
+// Threads `first`, `first + stride`, ... of the participating group own the same U entries in every phase.
+template <class Barrier>
+__device__ void mis_resample_body(const MisParams &p, Barrier &bar, uint32_t first, uint32_t stride, uint32_t n_u)
 {
     __shared__ unsigned int s_live;
-    const uint32_t stride = SMALL ? blockDim.x : gridDim.x * blockDim.x;
-    const uint32_t first = SMALL ? threadIdx.x : blockIdx.x * blockDim.x + threadIdx.x;
 
-    for (uint32_t i = first; i < n_u; i += stride) p.state[i] = UNDECIDED;
-    if (first < 64) p.ctr->step_live[first] = 0;     // only this kernel touches step_live; visible after the first barrier
-    phase_barrier<SMALL>(grid);
+    {   // ---- gather: one pass over the scattered literal planes
+        uint32_t it = 0;
+        for (uint32_t i = first; i < n_u; i += stride, ++it) {
+            p.state[i] = UNDECIDED;
+            open_item(p, it, i, true);
+        }
+    }
+    if (first < 64) p.ctr->step_live[first] = 0;     // only the acting MIS kernel touches step_live
+    bar.sync();
 
     uint32_t step = 0;
     for (;;) {
         if (step != 0 && step % TAGS == 0) {
             // the step tag wraps: stale claims would now undercut fresh ones, so clear what the survivors touch
-            for (uint32_t i = first; i < n_u; i += stride) {
+            uint32_t it = 0;
+            for (uint32_t i = first; i < n_u; i += stride, ++it) {
                 if (p.state[i] != UNDECIDED) continue;
-                const uint32_t slot = p.viol[i];
-                const uint32_t k = p.cv.width(slot);
-                for (uint32_t j = 0; j < k; j++) {
-                    const uint32_t v = p.cv.literal(slot, j) >> 1;
+                const Item x = open_item(p, it, i, false);
+                for (uint32_t j = 0; j < x.k; j++) {
+                    const uint32_t v = x.lit(p, j) >> 1;
                     if (ld_claim(&p.claim[v]) != CLAIM_TAKEN) p.claim[v] = CLAIM_FREE;
                 }
             }
-            phase_barrier<SMALL>(grid);
+            bar.sync();
         }
         // ---- phase A: drop out next to winners, otherwise claim
         if (threadIdx.x == 0) s_live = 0;
         __syncthreads();
-        uint32_t live = 0;
-        for (uint32_t i = first; i < n_u; i += stride) {
+        uint32_t live = 0, it = 0;
+        for (uint32_t i = first; i < n_u; i += stride, ++it) {
             if (p.state[i] != UNDECIDED) continue;
-            const uint32_t slot = p.viol[i];
-            const uint32_t k = p.cv.width(slot);
+            const Item x = open_item(p, it, i, false);
             bool taken = false;
-            for (uint32_t j = 0; j < k; j++) {
-                const uint32_t v = p.cv.literal(slot, j) >> 1;
-                if (ld_claim(&p.claim[v]) == CLAIM_TAKEN) { taken = true; break; }
-            }
+#pragma unroll 8
+            for (uint32_t j = 0; j < x.k; j++) taken |= ld_claim(&p.claim[x.lit(p, j) >> 1]) == CLAIM_TAKEN;   // no early exit: loads overlap
             if (taken) { p.state[i] = DROPPED; continue; }
-            const uint32_t id = p.cv.id(slot);
-            const unsigned long long key = claim_key(step, clause_priority(p.seed, p.round, id), id);
-            for (uint32_t j = 0; j < k; j++) atomicMin(&p.claim[p.cv.literal(slot, j) >> 1], key);
+            const unsigned long long key = claim_key(step, x.prio, x.id);
+#pragma unroll 8
+            for (uint32_t j = 0; j < x.k; j++) atomicMin(&p.claim[x.lit(p, j) >> 1], key);
             live++;
         }
         if (live) atomicAdd(&s_live, live);
         __syncthreads();
         if (threadIdx.x == 0 && s_live) atomicAdd(&p.ctr->step_live[step & 63u], s_live);
-        phase_barrier<SMALL>(grid);
+        bar.sync();
         const unsigned int total_live = ld_u32(&p.ctr->step_live[step & 63u]);
         if (total_live == 0) break;
 
         // ---- phase B: owners of all their claims win
-        for (uint32_t i = first; i < n_u; i += stride) {
+        it = 0;
+        for (uint32_t i = first; i < n_u; i += stride, ++it) {
             if (p.state[i] != UNDECIDED) continue;
-            const uint32_t slot = p.viol[i];
-            const uint32_t k = p.cv.width(slot);
-            const uint32_t id = p.cv.id(slot);
-            const unsigned long long key = claim_key(step, clause_priority(p.seed, p.round, id), id);
+            const Item x = open_item(p, it, i, false);
+            const unsigned long long key = claim_key(step, x.prio, x.id);
             bool win = true;
-            for (uint32_t j = 0; j < k; j++) {
-                // another winner may be storing TAKEN to ITS variables concurrently; ours still read == key
-                if (ld_claim(&p.claim[p.cv.literal(slot, j) >> 1]) != key) { win = false; break; }
-            }
+            // another winner may be storing TAKEN to ITS variables concurrently; ours still read == key
+#pragma unroll 8
+            for (uint32_t j = 0; j < x.k; j++) win &= ld_claim(&p.claim[x.lit(p, j) >> 1]) == key;
             if (!win) continue;
             p.state[i] = IN_SET;
-            for (uint32_t j = 0; j < k; j++) p.claim[p.cv.literal(slot, j) >> 1] = CLAIM_TAKEN;
-            p.s_slots[atomicAdd(&p.ctr->n_s, 1u)] = slot;
+#pragma unroll 8
+            for (uint32_t j = 0; j < x.k; j++) p.claim[x.lit(p, j) >> 1] = CLAIM_TAKEN;
+            p.s_slots[atomicAdd(&p.ctr->n_s, 1u)] = x.slot;
         }
         // the slot of step+2 (mod 64) is reused two steps from now: clear it while nobody reads it
         if (first == 0) p.ctr->step_live[(step + 2) & 63u] = 0;
-        phase_barrier<SMALL>(grid);
+        bar.sync();
         step++;
     }
 
     // ---- K4 + claim reset.  All claim reads of this round are behind the last barrier.
     unsigned long long resampled = 0;
-    for (uint32_t i = first; i < n_u; i += stride) {
-        const uint32_t slot = p.viol[i];
-        const uint32_t k = p.cv.width(slot);
-        const bool in_s = p.state[i] == IN_SET && p.do_resample;
-        for (uint32_t j = 0; j < k; j++) {
-            const uint32_t v = p.cv.literal(slot, j) >> 1;
+    uint32_t it = 0;
+    for (uint32_t i = first; i < n_u; i += stride, ++it) {
+        const Item x = open_item(p, it, i, false);
+        const bool in_s = p.state[i] == IN_SET;
+#pragma unroll 8
+        for (uint32_t j = 0; j < x.k; j++) {
+            const uint32_t v = x.lit(p, j) >> 1;
             p.claim[v] = CLAIM_FREE;
             if (in_s) {
                 const uint32_t mask = 1u << (v & 31u);
@@ -144,7 +204,7 @@ __device__ void mis_resample_body(const MisParams &p, cg::grid_group &grid, uint
                 else atomicAnd(&p.bits[v >> 5], ~mask);
             }
         }
-        if (p.state[i] == IN_SET) resampled += k;          // SATInstance.h:363 counts literals->size()
+        if (in_s) resampled += x.k;                            // SATInstance.h:363 counts literals->size()
     }
     // warp-reduce then one atomic per warp
     for (int o = 16; o > 0; o >>= 1) resampled += __shfl_down_sync(0xffffffffu, resampled, o);
@@ -152,45 +212,57 @@ __device__ void mis_resample_body(const MisParams &p, cg::grid_group &grid, uint
     if (first == 0) atomicAdd(&p.ctr->n_luby_steps, (unsigned long long)step);
 }
 
-// One launch per round.  n_iterations counts every sweep, including the terminal one (SATInstance.h:261).
-__global__ void __launch_bounds__(MIS_THREADS) mis_resample_kernel(const MisParams p)
+// Round bookkeeping by one thread after the last barrier.  n_iterations counts every sweep (SATInstance.h:261).
+__device__ __forceinline__ void finish_round(Counters *c, uint32_t n_u)
 {
-    cg::grid_group grid = cg::this_grid();
+    c->n_iterations += 1;
+    const unsigned int n_s = ld_u32(&c->n_s);
+    const unsigned long long n_r = __ldcg(&c->n_resampled_round);
+    c->sum_mis += n_s;                                     // SATInstance.h:291
+    c->n_resamples += n_r;                                 // SATInstance.h:313-315
+    c->last_n_viol = n_u;
+    c->last_n_s = n_s;
+    c->last_resampled = n_r;
+    c->n_viol = 0;                                         // clean slate for the next sweep
+    c->n_s = 0;
+    c->n_resampled_round = 0;
+}
+
+// First MIS kernel of a round: owns the terminal case (|U| == 0) and violated sets that fit one cluster.
+__global__ void __cluster_dims__(CL_SIZE, 1, 1) __launch_bounds__(CL_THREADS) mis_cluster_kernel(const MisParams p)
+{
+    if (ld_u32(&p.ctr->done)) return;             // speculative round behind the terminal one
     const uint32_t n_u = ld_u32(&p.ctr->n_viol);  // written by the sweep kernel that ran before us
     if (n_u == 0) {
         if (blockIdx.x == 0 && threadIdx.x == 0) {
-            p.ctr->n_iterations += 1;
+            p.ctr->n_iterations += 1;             // the terminal all-satisfied sweep counts (SATInstance.h:261,285-287)
             p.ctr->last_n_viol = 0;
             p.ctr->last_n_s = 0;
             p.ctr->last_resampled = 0;
+            p.ctr->done = 1;
         }
         return;
     }
-    if (n_u <= SMALL_U) {
-        if (blockIdx.x != 0) return;
-        mis_resample_body<true>(p, grid, n_u);
-        __syncthreads();
-    } else {
-        mis_resample_body<false>(p, grid, n_u);
-        grid.sync();
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        Counters *c = p.ctr;
-        c->n_iterations += 1;
-        const unsigned int n_s = ld_u32(&c->n_s);
-        const unsigned long long n_r = __ldcg(&c->n_resampled_round);
-        c->sum_mis += n_s;                                     // SATInstance.h:291
-        c->n_resamples += n_r;                                 // SATInstance.h:313-315
-        c->last_n_viol = n_u;
-        c->last_n_s = n_s;
-        c->last_resampled = n_r;
-        c->n_viol = 0;                                         // clean slate for the next sweep
-        c->n_s = 0;
-        c->n_resampled_round = 0;
-    }
+    if (n_u > CLUSTER_U) return;                  // the grid kernel behind us takes it
+    ClusterBarrier bar;
+    mis_resample_body(p, bar, blockIdx.x * CL_THREADS + threadIdx.x, CLUSTER_U, n_u);
+    bar.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) finish_round(p.ctr, n_u);
 }
 
-// Per-round scratch reset + (optionally) totals reset, fused into one tiny launch ahead of the sweep.
+// Second MIS kernel of a round (cooperative launch): violated sets too large for one cluster.
+__global__ void __launch_bounds__(GRID_THREADS) mis_grid_kernel(const MisParams p)
+{
+    if (ld_u32(&p.ctr->done)) return;
+    const uint32_t n_u = ld_u32(&p.ctr->n_viol);  // 0 when the cluster kernel already handled this round
+    if (n_u <= CLUSTER_U) return;
+    GridBarrier bar{cg::this_grid()};
+    mis_resample_body(p, bar, blockIdx.x * GRID_THREADS + threadIdx.x, gridDim.x * GRID_THREADS, n_u);
+    bar.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) finish_round(p.ctr, n_u);
+}
+
+// Per-round scratch reset + (optionally) totals reset.
 __global__ void reset_counters_kernel(Counters *c, int reset_totals)
 {
     c->n_viol = 0;
@@ -199,6 +271,7 @@ __global__ void reset_counters_kernel(Counters *c, int reset_totals)
     c->last_n_viol = 0;
     c->last_n_s = 0;
     c->last_resampled = 0;
+    c->done = 0;
     if (reset_totals) {
         c->n_iterations = 0;
         c->sum_mis = 0;
@@ -214,25 +287,46 @@ __global__ void map_ids_kernel(const uint32_t *slots, const uint32_t *orig_id, u
     if (i < n) out[i] = orig_id ? orig_id[slots[i]] : slots[i];
 }
 
-cudaError_t mis_max_grid(int device, uint32_t *grid_out)
+// ---- host side --------------------------------------------------------------------------------------
+
+static uint32_t grid_cache_items(uint32_t kmax) { return GRID_SMEM_WORDS_PER_THREAD / (kmax + EXTRA); }
+static size_t grid_smem_bytes(uint32_t kmax) { return (size_t)grid_cache_items(kmax) * (kmax + EXTRA) * GRID_THREADS * 4; }
+// the cluster kernel caches its one clause per thread whenever that fits the opt-in shared memory
+static uint32_t cluster_cache_items(uint32_t kmax) { return (size_t)(kmax + EXTRA) * CL_THREADS * 4 <= 200u * 1024u ? 1u : 0u; }
+static size_t cluster_smem_bytes(uint32_t kmax) { return (size_t)cluster_cache_items(kmax) * (kmax + EXTRA) * CL_THREADS * 4; }
+
+// Called once per upload on the handle's device: shared-memory opt-in + cooperative grid size.
+cudaError_t mis_configure(int device, uint32_t kmax, uint32_t *grid_out)
 {
+    cudaError_t e = cudaFuncSetAttribute(mis_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)cluster_smem_bytes(kmax));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(mis_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grid_smem_bytes(kmax));
+    if (e != cudaSuccess) return e;
     int per_sm = 0, sms = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mis_resample_kernel, MIS_THREADS, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mis_grid_kernel, GRID_THREADS, grid_smem_bytes(kmax));
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
     if (per_sm > 4) per_sm = 4;          // 4 x 256 threads per SM is plenty for an atomics-bound kernel
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     *grid_out = (uint32_t)(per_sm * sms);
     return cudaSuccess;
 }
 
-cudaError_t launch_mis_resample_args(const ClauseView &cv, const uint32_t *viol, uint8_t *state, uint32_t *s_slots,
-                                     unsigned long long *claim, uint32_t *bits, Counters *ctr, uint64_t seed,
-                                     uint32_t round, uint32_t grid, cudaStream_t s)
+// Enqueues both MIS kernels of one round (2 launches).
+cudaError_t launch_mis_resample_args(const ClauseView &cv, uint32_t kmax, const uint32_t *viol, uint8_t *state,
+                                     uint32_t *s_slots, unsigned long long *claim, uint32_t *bits, Counters *ctr,
+                                     uint64_t seed, uint32_t round, uint32_t grid, cudaStream_t s)
 {
-    MisParams p{cv, viol, state, s_slots, claim, bits, ctr, seed, round, 1u};
+    MisParams p{cv, viol, state, s_slots, claim, bits, ctr, seed, round, kmax, cluster_cache_items(kmax)};
+    mis_cluster_kernel<<<CL_SIZE, CL_THREADS, cluster_smem_bytes(kmax), s>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    p.cache_items = grid_cache_items(kmax);
     void *args[] = {(void *)&p};
-    return cudaLaunchCooperativeKernel((const void *)mis_resample_kernel, dim3(grid), dim3(MIS_THREADS), args, 0, s);
+    return cudaLaunchCooperativeKernel((const void *)mis_grid_kernel, dim3(grid), dim3(GRID_THREADS), args,
+                                       grid_smem_bytes(kmax), s);
 }
 
 cudaError_t launch_reset_counters(Counters *c, int reset_totals, cudaStream_t s)

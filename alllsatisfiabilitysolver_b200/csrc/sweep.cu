@@ -294,6 +294,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const Sw
 {
     constexpr bool RESIDENT_ALL = RB >= K;
     constexpr int RBE = RB < E ? RB : E;
+    if (__ldcg(&p.ctr->done)) return;         // speculatively enqueued behind the terminal round
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = threadIdx.x >> 5;
     WarpCompactor out{p.bucket_words + warp * WBUF, p.viol, p.ctr, 0u, lane};
@@ -366,6 +367,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const Sw
 template <bool RESIDENT_ALL>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_generic_kernel(const SweepParams p)
 {
+    if (__ldcg(&p.ctr->done)) return;
     const uint32_t lane = threadIdx.x & 31u;
     WarpCompactor comp{p.bucket_words + (threadIdx.x >> 5) * WBUF, p.viol, p.ctr, 0u, lane};
 
@@ -402,6 +404,7 @@ __global__ void __launch_bounds__(256) sweep_csr_kernel(const uint64_t *__restri
                                                          uint64_t m, const uint32_t *__restrict__ bits,
                                                          uint32_t *viol, Counters *ctr)
 {
+    if (__ldcg(&ctr->done)) return;
     const uint32_t lane = threadIdx.x & 31u;                       // launched with 8 * WBUF words of dynamic smem
     WarpCompactor comp{(threadIdx.x >> 5) * WBUF, viol, ctr, 0u, lane};
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
