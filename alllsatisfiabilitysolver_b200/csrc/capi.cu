@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -56,6 +57,13 @@ struct alll_solver {
     cudaEvent_t ev_round[ROUNDS_IN_FLIGHT] = {};
     uint32_t sweep_grid = 1, mis_grid = 1;
     std::vector<cudaEvent_t> ev;         // 2 * MAX_TIMED_ROUNDS + 2
+
+    // Device buffers are kept across uploads and only grow: re-uploading an instance of the same shape (the
+    // end-to-end path) then costs no cudaMalloc/cudaFree, which dominate a 1.3 GB upload otherwise.
+    std::map<void **, size_t> caps;
+    bool use_orig_id = false;
+    uint8_t *d_tmp_bkt = nullptr;
+    uint32_t *d_tmp_cnt = nullptr, *d_tmp_err = nullptr, *d_stage = nullptr;
 };
 
 namespace {
@@ -79,13 +87,35 @@ template <typename T> void dfree(T *&p)
     p = nullptr;
 }
 
+// Forgets the current instance; its buffers stay pooled for the next upload.
 void free_instance(alll_handle h)
+{
+    h->has_instance = false;
+    h->use_orig_id = false;
+}
+
+void release_buffers(alll_handle h)
 {
     dfree(h->d_planes); dfree(h->d_orig_id); dfree(h->d_segs); dfree(h->d_off); dfree(h->d_csr_lit);
     dfree(h->d_bits); dfree(h->d_claim); dfree(h->d_viol); dfree(h->d_s); dfree(h->d_ids_out);
-    dfree(h->d_state); dfree(h->d_bools);
+    dfree(h->d_state); dfree(h->d_bools); dfree(h->d_tmp_bkt); dfree(h->d_tmp_cnt); dfree(h->d_tmp_err); dfree(h->d_stage);
+    h->caps.clear();
     h->has_instance = false;
 }
+
+// Grow-only allocation of the buffer behind *slot (a field of the handle).
+template <typename T> int pool_alloc(alll_handle h, T **slot, size_t bytes)
+{
+    void **key = reinterpret_cast<void **>(slot);
+    bytes = std::max<size_t>(bytes, 16);
+    auto it = h->caps.find(key);
+    if (*slot && it != h->caps.end() && it->second >= bytes) return ALLL_OK;
+    if (*slot) { cudaFree(*slot); *slot = nullptr; }
+    CK(cudaMalloc(slot, bytes));
+    h->caps[key] = bytes;
+    return ALLL_OK;
+}
+#define POOL(slot, bytes) do { if (int rc__ = pool_alloc(h, &(slot), (bytes))) return rc__; } while (0)
 
 inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
@@ -100,7 +130,7 @@ ClauseView clause_view(alll_handle h)
 {
     ClauseView cv;
     cv.planes = h->d_planes; cv.m_pad = h->m_pad; cv.k = h->k;
-    cv.off = h->d_off; cv.csr_lit = h->d_csr_lit; cv.orig_id = h->d_orig_id;
+    cv.off = h->d_off; cv.csr_lit = h->d_csr_lit; cv.orig_id = h->use_orig_id ? h->d_orig_id : nullptr;
     return cv;
 }
 
@@ -108,15 +138,15 @@ ClauseView clause_view(alll_handle h)
 int alloc_common(alll_handle h)
 {
     const uint64_t m1 = std::max<uint64_t>(h->m, 1), n1 = std::max<uint64_t>(h->n_vars, 1);
-    CK(cudaMalloc(&h->d_bits, (size_t)std::max<uint32_t>(h->n_words_alloc, 4) * 4));
+    POOL(h->d_bits, (size_t)std::max<uint32_t>(h->n_words_alloc, 4) * 4);
     CK(cudaMemsetAsync(h->d_bits, 0, (size_t)std::max<uint32_t>(h->n_words_alloc, 4) * 4, h->stream));
-    CK(cudaMalloc(&h->d_claim, n1 * 8));
+    POOL(h->d_claim, n1 * 8);
     CK(launch_fill_u64(h->d_claim, n1, CLAIM_FREE, h->stream)); h->launches++;
-    CK(cudaMalloc(&h->d_viol, m1 * 4));
-    CK(cudaMalloc(&h->d_s, m1 * 4));
-    CK(cudaMalloc(&h->d_ids_out, m1 * 4));
-    CK(cudaMalloc(&h->d_state, m1));
-    CK(cudaMalloc(&h->d_bools, n1));
+    POOL(h->d_viol, m1 * 4);
+    POOL(h->d_s, m1 * 4);
+    POOL(h->d_ids_out, m1 * 4);
+    POOL(h->d_state, m1);
+    POOL(h->d_bools, n1);
     CK(launch_reset_counters(h->d_ctr, 1, h->stream)); h->launches++;
     CK(mis_configure(h->device, h->kmax, &h->mis_grid));
     return ALLL_OK;
@@ -151,8 +181,8 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     }
     h->n_words_alloc = std::max<uint32_t>(n_words4, h->n_buckets * h->bucket_words);
 
-    uint32_t *d_err = nullptr;                       // [0] error flags, [1] min resident-placed literals per clause
-    CK(cudaMalloc(&d_err, 8));
+    POOL(h->d_tmp_err, 8);
+    uint32_t *d_err = h->d_tmp_err;                  // [0] error flags, [1] min resident-placed literals per clause
     const uint32_t err_init[2] = {0u, 0xFFFFFFFFu};
     CK(cudaMemcpyAsync(d_err, err_init, 8, cudaMemcpyHostToDevice, h->stream));
     std::vector<BucketSeg> segs(h->n_buckets);
@@ -160,19 +190,17 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
 
     if (h->n_buckets == 1) {
         h->m_pad = align_up(m, TILE);
-        if (h->m_pad) {
-            CK(cudaMalloc(&h->d_planes, h->m_pad * k * 4));
-            CK(cudaMemsetAsync(h->d_planes, 0, h->m_pad * k * 4, h->stream));
-        }
+        // padding slots are never evaluated (masked by slot_end), so the planes need no clearing
+        if (h->m_pad) POOL(h->d_planes, h->m_pad * k * 4);
         CK(launch_transpose(d_lit, m, k, n_vars, h->d_planes, h->m_pad, d_err, h->stream)); h->launches++;
         segs[0] = BucketSeg{0u, (uint32_t)m};
     } else {
         const uint32_t bucket_vars = h->bucket_words * 32u, nb = h->n_buckets;
         const uint32_t n_cta = bucket_pass_ctas(m);
-        uint8_t *d_bkt = nullptr;
-        uint32_t *d_cnt = nullptr;
-        CK(cudaMalloc(&d_bkt, std::max<uint64_t>(m, 1)));
-        CK(cudaMalloc(&d_cnt, (size_t)nb * std::max<uint32_t>(n_cta, 1) * 4));
+        POOL(h->d_tmp_bkt, std::max<uint64_t>(m, 1));
+        POOL(h->d_tmp_cnt, (size_t)nb * std::max<uint32_t>(n_cta, 1) * 4);
+        uint8_t *d_bkt = h->d_tmp_bkt;
+        uint32_t *d_cnt = h->d_tmp_cnt;
         if (m) { CK(launch_bucket_count(d_lit, m, k, n_vars, bucket_vars, nb, d_bkt, d_cnt, d_err, h->stream)); h->launches++; }
         std::vector<uint32_t> cnt((size_t)nb * n_cta);
         CK(cudaMemcpyAsync(cnt.data(), d_cnt, cnt.size() * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -192,27 +220,22 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
         h->m_pad = align_up(pos, TILE);
         CK(cudaMemcpyAsync(d_cnt, cnt.data(), cnt.size() * 4, cudaMemcpyHostToDevice, h->stream));
         if (h->m_pad) {
-            CK(cudaMalloc(&h->d_planes, h->m_pad * k * 4));
-            CK(cudaMemsetAsync(h->d_planes, 0, h->m_pad * k * 4, h->stream));
-            CK(cudaMalloc(&h->d_orig_id, h->m_pad * 4));
-            CK(cudaMemsetAsync(h->d_orig_id, 0xFF, h->m_pad * 4, h->stream));
+            POOL(h->d_planes, h->m_pad * k * 4);
+            POOL(h->d_orig_id, h->m_pad * 4);
         }
+        h->use_orig_id = true;
         if (m) {
             CK(launch_bucket_scatter(d_lit, m, k, bucket_vars, nb, d_bkt, d_cnt, h->d_planes, h->m_pad, h->d_orig_id, d_err + 1, h->stream));
             h->launches++;
         }
-        CK(cudaStreamSynchronize(h->stream));
-        cudaFree(d_bkt);
-        cudaFree(d_cnt);
     }
     h->n_tiles = (uint32_t)(h->m_pad / TILE);
-    CK(cudaMalloc(&h->d_segs, sizeof(BucketSeg) * h->n_buckets));
+    POOL(h->d_segs, sizeof(BucketSeg) * h->n_buckets);
     CK(cudaMemcpyAsync(h->d_segs, segs.data(), sizeof(BucketSeg) * h->n_buckets, cudaMemcpyHostToDevice, h->stream));
 
     uint32_t err_out[2] = {0, 0};
     CK(cudaMemcpyAsync(err_out, d_err, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(d_err);
     if (err_out[0]) { free_instance(h); return fail(h, ALLL_BAD_ARG, "a literal references a variable >= n_vars"); }
     if (h->n_buckets > 1 && m > 0 && err_out[1] != 0xFFFFFFFFu) h->min_resident = err_out[1];
 
@@ -332,7 +355,7 @@ int alll_destroy(alll_handle h)
     if (!h) return ALLL_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    free_instance(h);
+    release_buffers(h);
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->d_ctr) cudaFree(h->d_ctr);
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
@@ -359,13 +382,15 @@ int alll_upload_fixedk(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, c
     if (k < 1 || k > MAX_K) return fail(h, ALLL_BAD_ARG, "k must be in [1, 32] for the fixed-width layout");
     CK(cudaSetDevice(h->device));
     free_instance(h);
-    uint32_t *d_stage = nullptr;
     const size_t bytes = (size_t)std::max<uint64_t>(m * k, 1) * 4;
-    CK(cudaMalloc(&d_stage, bytes));
-    if (m) CK(cudaMemcpyAsync(d_stage, lit, (size_t)m * k * 4, cudaMemcpyHostToDevice, h->stream));
-    const int rc = upload_fixedk_device_impl(h, n_vars, m, k, d_stage);
+    POOL(h->d_stage, bytes);
+    if (m) CK(cudaMemcpyAsync(h->d_stage, lit, (size_t)m * k * 4, cudaMemcpyHostToDevice, h->stream));
+    const int rc = upload_fixedk_device_impl(h, n_vars, m, k, h->d_stage);
     cudaStreamSynchronize(h->stream);
-    cudaFree(d_stage);
+    if (bytes > (4ull << 30)) {          // do not sit on a very large staging buffer
+        dfree(h->d_stage);
+        h->caps.erase(reinterpret_cast<void **>(&h->d_stage));
+    }
     return rc;
 }
 
@@ -396,18 +421,17 @@ int alll_upload_csr(alll_handle h, uint64_t n_vars, uint64_t m, const uint64_t *
     h->n_lit = m ? off[m] - off[0] : 0;
     std::vector<uint64_t> off0(m + 1);
     for (uint64_t c = 0; c <= m; c++) off0[c] = off[c] - off[0];
-    CK(cudaMalloc(&h->d_off, (m + 1) * 8));
+    POOL(h->d_off, (m + 1) * 8);
     CK(cudaMemcpyAsync(h->d_off, off0.data(), (m + 1) * 8, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMalloc(&h->d_csr_lit, std::max<uint64_t>(h->n_lit, 1) * 4));
+    POOL(h->d_csr_lit, std::max<uint64_t>(h->n_lit, 1) * 4);
     if (h->n_lit) CK(cudaMemcpyAsync(h->d_csr_lit, lit + off[0], h->n_lit * 4, cudaMemcpyHostToDevice, h->stream));
-    uint32_t *d_err = nullptr;
-    CK(cudaMalloc(&d_err, 4));
+    POOL(h->d_tmp_err, 8);
+    uint32_t *d_err = h->d_tmp_err;
     CK(cudaMemsetAsync(d_err, 0, 4, h->stream));
     CK(launch_validate_csr(h->d_csr_lit, h->n_lit, n_vars, d_err, h->stream)); h->launches++;
     uint32_t err_flags = 0;
     CK(cudaMemcpyAsync(&err_flags, d_err, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(d_err);
     if (err_flags) { free_instance(h); return fail(h, ALLL_BAD_ARG, "a literal references a variable >= n_vars"); }
     if (int rc = alloc_common(h)) return rc;
     CK(cudaStreamSynchronize(h->stream));
