@@ -30,6 +30,16 @@
 #include <utility>
 #include <vector>
 
+#ifdef _OPENMP
+#include <omp.h>
+#else
+#include <thread>
+// The reference header pulls in <omp.h> (SATInstance.h:16) and its CLI calls omp_get_num_procs()
+// (example/main.cpp:77-78); keep that call compiling without OpenMP.
+static inline int omp_get_num_procs() { const unsigned n = std::thread::hardware_concurrency(); return n ? (int)n : 1; }
+#endif
+#include <cmath>
+
 #include "../../include/alll_b200.h"
 #include "Clause.h"
 #include "ClauseGenerator.h"

@@ -1,0 +1,136 @@
+"""The host side above the C ABI: drop-in C++ headers, the cnf_io loader and the CLI."""
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "alllsatisfiabilitysolver_b200")
+CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+LINK = ["-L" + PKG, "-lalll_b200", "-Wl,-rpath," + PKG, "-pthread"]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    subprocess.run(["make", "-s", "-C", os.path.join(PKG, "csrc")], check=True)
+    return os.path.join(PKG, "liballl_b200.so")
+
+
+@pytest.fixture(scope="module")
+def cli(lib):
+    subprocess.run(["make", "-s", "-C", os.path.join(PKG, "cli")], check=True)
+    return os.path.join(PKG, "cli", "alll_solve")
+
+
+def build(tmp, name, sources, extra=(), libs=()):
+    out = os.path.join(tmp, name)
+    subprocess.run([CXX, "-std=c++20", "-O1", "-w", *extra, *sources, "-o", out, *libs], check=True)
+    return out
+
+
+# ---- CPU -------------------------------------------------------------------------------------------
+
+def test_reference_main_compiles_unchanged_against_dropin_headers(lib, tmp_path):
+    """example/main.cpp of the reference, byte for byte, builds against include/ + cli/cnf_io of this repo
+    (Boost replaced by the 100-line stub in tests/cpp/boost_stub, since Boost is not installed)."""
+    ref_main = "/root/reference/example/main.cpp"
+    if not os.path.exists(ref_main):
+        pytest.skip("/root/reference is not present on this box")
+    build(str(tmp_path), "ref_main", [ref_main, os.path.join(PKG, "cli", "cnf_io", "cnf_io.cpp")],
+          extra=["-I" + os.path.join(ROOT, "tests", "cpp", "boost_stub"), "-I" + os.path.join(PKG, "include"),
+                 "-I" + os.path.join(PKG, "cli")], libs=LINK)
+
+
+def test_cnf_loader_matches_reference_parser_on_wellformed_files(tmp_path):
+    """cnf_header_read / cnf_data_read return what the reference's cnf_io returned (tests/golden/dimacs/expected.json)."""
+    exe = build(str(tmp_path), "cnf_dump", [os.path.join(ROOT, "tests", "cpp", "cnf_dump.cpp"),
+                                            os.path.join(PKG, "cli", "cnf_io", "cnf_io.cpp")], extra=["-I" + os.path.join(PKG, "cli")])
+    exp = json.load(open(os.path.join(GOLDEN, "dimacs", "expected.json")))
+    for name in ("cfg1.cnf", "dialect.cnf"):
+        got = json.loads(subprocess.run([exe, os.path.join(GOLDEN, "dimacs", name)], capture_output=True, text=True, check=True).stdout)
+        assert got["error"] is False
+        for key in ("v_num", "c_num", "l_num", "l_c_num", "l_val"):
+            assert got[key] == exp[name][key], (name, key)
+
+
+def test_cnf_loader_fixes_the_reference_hazards(tmp_path):
+    """Deliberate deviations: last line without newline is parsed; tabs separate tokens;
+    a SATLIB '%' trailer ends the data; contradictory counts and junk tokens are reported, never written out of bounds."""
+    exe = build(str(tmp_path), "cnf_dump", [os.path.join(ROOT, "tests", "cpp", "cnf_dump.cpp"),
+                                            os.path.join(PKG, "cli", "cnf_io", "cnf_io.cpp")], extra=["-I" + os.path.join(PKG, "cli")])
+
+    def parse(text):
+        p = tmp_path / "t.cnf"
+        p.write_text(text)
+        return json.loads(subprocess.run([exe, str(p)], capture_output=True, text=True, check=True).stdout)
+
+    got = parse("p cnf 4 3\n1 2 0\n-3 4 0\n-1 -4 0")                      # reference drops the last clause
+    assert got["error"] is False and got["l_c_num"] == [2, 2, 2] and got["l_val"] == [1, 2, -3, 4, -1, -4]
+    got = parse("p cnf 3 1\n1\t-2\t3 0\n")                                 # reference reads only "1"
+    assert got["error"] is False and got["l_val"] == [1, -2, 3]
+    got = parse("c x\np cnf 2 2\n1 -2 0\n2 0\n%\n0\n")                      # reference writes l_c_num[c_num] out of bounds
+    assert got["error"] is False and got["l_c_num"] == [2, 1]
+    assert parse("p cnf 2 3\n1 -2 0\n2 0\n")["error"] is True              # header promises 3 clauses
+    assert parse("p cnf 2 1\n1 x2 0\n")["error"] == "header"               # junk token
+    assert parse("q cnf 2 1\n1 0\n")["error"] == "header"                  # no problem line
+    assert parse("p cnf 2 1\n1 3 0\n")["error"] is True                    # variable beyond V
+
+
+# ---- GPU -------------------------------------------------------------------------------------------
+
+@pytest.mark.gpu
+def test_cli_outputs_match_reference_format(cli, oracle, tmp_path):
+    """Same observable behaviour as example/main.cpp: log lines, INFORMATION/STATISTICS blocks, six-field csv,
+    'Variable i = b' dump, exit code 0 on a verified solution."""
+    cnf = tmp_path / "cfg1.cnf"
+    cnf.write_bytes(open(os.path.join(GOLDEN, "dimacs", "cfg1.cnf"), "rb").read())
+    r = subprocess.run([cli, "-o", "-p", "4", "--sat", str(cnf), "--seed", "5"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = r.stdout
+    assert re.search(r"^Log .*: Reading CNF file$", out, re.M)
+    assert re.search(r"^Log .*: Read complete; Duration: [0-9.]+s$", out, re.M)
+    assert "------------ INFORMATION ------------\n\t\t\t# Variables\t= 2000\n\t\t\t# Clauses\t= 1195\n" in out
+    assert re.search(r"^Log .*: Starting parallel solve \(# Threads = 4\)$", out, re.M)
+    assert re.search(r"^Log .*: Completed solve; Duration: [0-9.]+s$", out, re.M)
+    m = re.search(r"# Iterations\t= (\d+)\n# Resamples\t= (\d+)\n\tThread 1: (\d+)\n\tThread 2: 0\n\tThread 3: 0\n\tThread 4: 0\n\nAvg. UNSAT MIS Size = (\d+)\n", out)
+    assert m and m.group(2) == m.group(3)
+    assert out.rstrip().endswith("SATISFIABLE")
+    csv = (tmp_path / "cfg1.csv").read_text().strip().split(",")
+    assert len(csv) == 6 and csv[1] == "2000" and csv[2] == "1195" and csv[4] == "4" and csv[5] == m.group(1)
+    float(csv[0]); int(csv[3])
+    dump = (tmp_path / "cfg1.out").read_text()
+    assert dump.startswith(out)                                   # .out is a tee of stdout ...
+    vals = re.findall(r"^Variable (\d+) = ([01])$", dump, re.M)     # ... plus the assignment
+    assert [int(i) for i, _ in vals] == list(range(1, 2001))
+    assign = np.array([int(b) for _, b in vals], np.uint8)
+    exp = json.load(open(os.path.join(GOLDEN, "dimacs", "expected.json")))["cfg1.cnf"]
+    assert oracle.check_signed(exp["l_c_num"], exp["l_val"], assign)   # independent checker (cnf_io.cpp:392-484 semantics)
+    # same seed -> same run
+    r2 = subprocess.run([cli, "--sat", str(cnf), "--seed", "5", "-p", "4"], capture_output=True, text=True)
+    assert re.search(r"# Iterations\t= (\d+)", r2.stdout).group(1) == m.group(1)
+    # unsatisfiable input + round cap -> exit code 1, no SATISFIABLE
+    bad = tmp_path / "unsat.cnf"
+    bad.write_text("p cnf 1 2\n1 0\n-1 0\n")
+    r3 = subprocess.run([cli, "--sat", str(bad), "--max-rounds", "20"], capture_output=True, text=True)
+    assert r3.returncode == 1 and "SATISFIABLE" not in r3.stdout.replace("UNSATISFIABLE", "")
+
+
+@pytest.mark.gpu
+def test_reference_style_user_program(lib, tmp_path):
+    """A program written against the reference's public API only, built with the drop-in headers."""
+    exe = build(str(tmp_path), "dropin_user", [os.path.join(ROOT, "tests", "cpp", "dropin_user.cpp")],
+                extra=["-I" + os.path.join(PKG, "include")], libs=LINK)
+    dimacs = tmp_path / "enum.cnf"
+    r = subprocess.run([exe, str(dimacs)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = json.loads(r.stdout.strip().splitlines()[-1])
+    assert got["valid"] and got["host_ok"] and got["host_ok2"] and got["status"] == 0
+    assert got["thread_entries"] == 3 and got["thread0"] == got["resamples"]
+    assert got["resamples"] % 5 == 0 and got["iterations"] >= 1 and got["iterations2"] >= 1
+    head = dimacs.read_text().splitlines()
+    assert head[0] == f"p cnf 3000 {got['n_clauses']}" and head[1].startswith(" ") and head[1].endswith(" 0")
