@@ -1,6 +1,7 @@
 // Test program written against the reference's public API only (SATInstance.h:51,60,70,156,175; Clause.h:25;
 // VariablesArray.h:23): builds clauses the way example/main.cpp:149-178 does, solves, verifies, and also
 // exercises the enumerated-clause overload and writeDIMACS.  Prints one JSON line.
+#include <algorithm>
 #include <cstdio>
 #include <fstream>
 #include <random>

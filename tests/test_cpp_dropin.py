@@ -81,6 +81,13 @@ def test_cnf_loader_fixes_the_reference_hazards(tmp_path):
     assert parse("p cnf 2 1\n1 3 0\n")["error"] is True                    # variable beyond V
 
 
+def test_user_program_and_cli_build(cli, lib, tmp_path):
+    """Compile-and-link check of the reference-style user program (it runs in the GPU suite)."""
+    build(str(tmp_path), "dropin_user", [os.path.join(ROOT, "tests", "cpp", "dropin_user.cpp")],
+          extra=["-I" + os.path.join(PKG, "include")], libs=LINK)
+    assert os.path.exists(cli)
+
+
 # ---- GPU -------------------------------------------------------------------------------------------
 
 @pytest.mark.gpu
