@@ -26,6 +26,7 @@ SYMBOLS = [
     "alll_set_assignment", "alll_get_assignment", "alll_randomize",
     "alll_eval", "alll_verify", "alll_round", "alll_solve",
     "alll_time_sweep", "alll_launch_count", "alll_layout_info",
+    "alll_set_id_base", "alll_shard_sweep", "alll_shard_round", "alll_get_stats", "alll_reset_stats",
 ]
 
 
@@ -93,10 +94,13 @@ def load() -> C.CDLL:
     L.alll_time_sweep.argtypes = [vp, u32, C.POINTER(C.c_double), C.POINTER(u64)]
     L.alll_launch_count.argtypes = [vp, C.POINTER(u64)]
     L.alll_layout_info.argtypes = [vp, C.POINTER(u64)]
+    L.alll_set_id_base.argtypes = [vp, u64]
+    L.alll_shard_sweep.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.alll_shard_round.argtypes = [vp, vp, C.POINTER(u64), u32, u64, u64, u32, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    L.alll_get_stats.argtypes = [vp, C.POINTER(StatsC)]
+    L.alll_reset_stats.argtypes = [vp]
     for name in SYMBOLS:
-        fn = getattr(L, name)
-        if fn.restype is C.c_int and name not in ("alll_abi_version",):
-            pass
+        getattr(L, name)            # raises AttributeError if the library misses a declared entry point
     _lib = L
     return L
 
@@ -199,6 +203,31 @@ class Solver:
         self._check(self.lib.alll_solve(self.h, seed, max_rounds, C.byref(st)), allow=(OK, MAX_ROUNDS))
         return Stats(st.n_iterations, st.n_resamples, st.avg_mis_size, st.sum_mis_size, st.n_clause_evals,
                      st.n_luby_steps, st.n_kernel_launches, st.solve_ms, st.sweep_ms, st.status)
+
+    # -- clause-range sharded mode (device pointers; the all-gather between the two calls is the caller's) -------
+    def set_id_base(self, id_base: int):
+        self._check(self.lib.alll_set_id_base(self.h, id_base))
+
+    def shard_sweep(self, d_records_ptr: int, cap_records: int) -> int:
+        n = C.c_uint64(0)
+        self._check(self.lib.alll_shard_sweep(self.h, C.c_void_p(d_records_ptr), cap_records, C.byref(n)))
+        return int(n.value)
+
+    def shard_round(self, d_records_ptr: int, counts, block_cap: int, seed: int, rnd: int):
+        arr = (C.c_uint64 * len(counts))(*[int(c) for c in counts])
+        n_t, n_s, n_r = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.alll_shard_round(self.h, C.c_void_p(d_records_ptr), arr, len(counts), block_cap, seed, rnd,
+                                              C.byref(n_t), C.byref(n_s), C.byref(n_r)))
+        return int(n_t.value), int(n_s.value), int(n_r.value)
+
+    def get_stats(self) -> Stats:
+        st = StatsC()
+        self._check(self.lib.alll_get_stats(self.h, C.byref(st)))
+        return Stats(st.n_iterations, st.n_resamples, st.avg_mis_size, st.sum_mis_size, st.n_clause_evals,
+                     st.n_luby_steps, st.n_kernel_launches, st.solve_ms, st.sweep_ms, st.status)
+
+    def reset_stats(self):
+        self._check(self.lib.alll_reset_stats(self.h))
 
     # -- measurement ----------------------------------------------------------------------
     def time_sweep(self, reps: int):

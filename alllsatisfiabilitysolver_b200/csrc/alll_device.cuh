@@ -20,6 +20,7 @@ constexpr uint32_t MAX_BUCKETS = 256;
 constexpr uint32_t EAGER_PLANES = 5;              // planes streamed by the sweep; the tail planes are fetched only for surviving clauses
 constexpr uint32_t RESIDENT_CAP = 4;              // at most this many literals of a clause are placed as bucket-resident
 constexpr uint32_t MAX_K = 32;
+constexpr uint32_t MAX_SHARDS = 64;                // clause-range shards (GPUs) of one instance
 constexpr uint32_t INVALID_ID = 0xFFFFFFFFu;
 
 constexpr unsigned long long CLAIM_FREE = ~0ull;  // nobody claims this variable
@@ -98,8 +99,9 @@ struct ClauseView {
     // CSR
     const uint64_t *off;
     const uint32_t *csr_lit;
-    // slot -> caller clause id (NULL = identity)
+    // slot -> caller clause id (NULL = identity), plus the first id of this clause range (sharded mode)
     const uint32_t *orig_id;
+    uint32_t id_base;
 
     __device__ __forceinline__ uint32_t width(uint32_t p) const
     {
@@ -109,7 +111,7 @@ struct ClauseView {
     {
         return k ? planes[(uint64_t)j * m_pad + p] : csr_lit[off[p] + j];
     }
-    __device__ __forceinline__ uint32_t id(uint32_t p) const { return orig_id ? orig_id[p] : p; }
+    __device__ __forceinline__ uint32_t id(uint32_t p) const { return (orig_id ? orig_id[p] : p) + id_base; }
 };
 
 // Device-side counters of one handle.

@@ -20,7 +20,15 @@ cudaError_t launch_mis_resample_args(const ClauseView &cv, uint32_t kmax, const 
                                      uint32_t *s_slots, unsigned long long *claim, uint32_t *bits, Counters *ctr,
                                      uint64_t seed, uint32_t round, uint32_t grid, cudaStream_t s);
 cudaError_t launch_reset_counters(Counters *c, int reset_totals, cudaStream_t s);
-cudaError_t launch_map_ids(const uint32_t *slots, const uint32_t *orig_id, uint32_t n, uint32_t *out, cudaStream_t s);
+cudaError_t launch_map_ids(const uint32_t *slots, const uint32_t *orig_id, uint32_t id_base, uint32_t n, uint32_t *out,
+                           cudaStream_t s);
+
+// shard.cu
+cudaError_t launch_export_records(const ClauseView &cv, const uint32_t *viol, const Counters *ctr, uint32_t *records,
+                                  uint64_t cap, uint32_t grid, cudaStream_t s);
+cudaError_t launch_repack_records(const uint32_t *records, uint64_t block_cap, uint32_t k, uint32_t n_blocks,
+                                  const uint32_t *prefix, uint32_t *planes, uint64_t dense_cap, uint32_t *ids,
+                                  uint32_t *iota, Counters *ctr, uint32_t grid, cudaStream_t s);
 
 // layout.cu
 cudaError_t launch_transpose(const uint32_t *lit, uint64_t m, uint32_t k, uint64_t n_vars, uint32_t *planes,

@@ -62,6 +62,10 @@ struct alll_solver {
     // end-to-end path) then costs no cudaMalloc/cudaFree, which dominate a 1.3 GB upload otherwise.
     std::map<void **, size_t> caps;
     bool use_orig_id = false;
+    uint32_t id_base = 0;                // first global clause id of this clause range (sharded mode)
+    // sharded mode: dense copy of the gathered violated records
+    uint32_t *d_sh_planes = nullptr, *d_sh_ids = nullptr, *d_sh_iota = nullptr, *d_sh_s = nullptr;
+    uint8_t *d_sh_state = nullptr;
     uint8_t *d_tmp_bkt = nullptr;
     uint32_t *d_tmp_cnt = nullptr, *d_tmp_err = nullptr, *d_stage = nullptr;
 };
@@ -99,6 +103,7 @@ void release_buffers(alll_handle h)
     dfree(h->d_planes); dfree(h->d_orig_id); dfree(h->d_segs); dfree(h->d_off); dfree(h->d_csr_lit);
     dfree(h->d_bits); dfree(h->d_claim); dfree(h->d_viol); dfree(h->d_s); dfree(h->d_ids_out);
     dfree(h->d_state); dfree(h->d_bools); dfree(h->d_tmp_bkt); dfree(h->d_tmp_cnt); dfree(h->d_tmp_err); dfree(h->d_stage);
+    dfree(h->d_sh_planes); dfree(h->d_sh_ids); dfree(h->d_sh_iota); dfree(h->d_sh_s); dfree(h->d_sh_state);
     h->caps.clear();
     h->has_instance = false;
 }
@@ -131,6 +136,7 @@ ClauseView clause_view(alll_handle h)
     ClauseView cv;
     cv.planes = h->d_planes; cv.m_pad = h->m_pad; cv.k = h->k;
     cv.off = h->d_off; cv.csr_lit = h->d_csr_lit; cv.orig_id = h->use_orig_id ? h->d_orig_id : nullptr;
+    cv.id_base = h->id_base;
     return cv;
 }
 
@@ -288,7 +294,7 @@ int copy_ids_out(alll_handle h, const uint32_t *d_slots, uint64_t n, uint32_t *o
 {
     const uint64_t n_copy = std::min(n, cap);
     if (!out || n_copy == 0) return ALLL_OK;
-    CK(launch_map_ids(d_slots, h->d_orig_id, (uint32_t)n_copy, h->d_ids_out, h->stream)); h->launches++;
+    CK(launch_map_ids(d_slots, h->use_orig_id ? h->d_orig_id : nullptr, h->id_base, (uint32_t)n_copy, h->d_ids_out, h->stream)); h->launches++;
     CK(cudaMemcpyAsync(out, h->d_ids_out, n_copy * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return ALLL_OK;
@@ -566,6 +572,102 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
     stats->sweep_ms = timed ? sweep_ms * ((double)c.n_iterations / timed) : 0.0;
     stats->status = status;
     return status;
+}
+
+// ---- clause-range sharded mode ----------------------------------------------------
+
+int alll_set_id_base(alll_handle h, uint64_t id_base)
+{
+    if (!h) return ALLL_BAD_ARG;
+    if (id_base > 0xFFFFFFFFull) return fail(h, ALLL_BAD_ARG, "id_base must fit 32 bits");
+    h->id_base = (uint32_t)id_base;
+    return ALLL_OK;
+}
+
+int alll_shard_sweep(alll_handle h, uint32_t *d_records, uint64_t cap_records, uint64_t *n_local)
+{
+    NEED_INSTANCE();
+    if (!h->k) return fail(h, ALLL_BAD_ARG, "sharded mode needs the fixed-width layout");
+    if (!d_records && cap_records) return fail(h, ALLL_BAD_ARG, "d_records == NULL");
+    if (int rc = enqueue_sweep(h)) return rc;
+    if (cap_records) {
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((cap_records + 255) / 256, (uint64_t)h->sm_count * 8);
+        CK(launch_export_records(clause_view(h), h->d_viol, h->d_ctr, d_records, cap_records, std::max(grid, 1u), h->stream));
+        h->launches++;
+    }
+    if (int rc = fetch_counters(h)) return rc;
+    const uint64_t n = h->h_ctr->n_viol;
+    if (n_local) *n_local = n;
+    CK(launch_reset_counters(h->d_ctr, 0, h->stream)); h->launches++;
+    if (n > cap_records) return fail(h, ALLL_CAPACITY, "record buffer too small for the local violated set");
+    return ALLL_OK;
+}
+
+int alll_shard_round(alll_handle h, const uint32_t *d_records, const uint64_t *counts, uint32_t n_blocks,
+                     uint64_t block_cap, uint64_t seed, uint32_t round, uint64_t *n_total, uint64_t *n_s,
+                     uint64_t *n_resampled)
+{
+    NEED_INSTANCE();
+    if (!h->k) return fail(h, ALLL_BAD_ARG, "sharded mode needs the fixed-width layout");
+    if (!counts || n_blocks == 0 || n_blocks > MAX_SHARDS) return fail(h, ALLL_BAD_ARG, "bad shard count");
+    uint32_t prefix[MAX_SHARDS + 1];
+    uint64_t total = 0;
+    for (uint32_t b = 0; b < n_blocks; b++) {
+        if (counts[b] > block_cap) return fail(h, ALLL_BAD_ARG, "count exceeds block capacity");
+        prefix[b] = (uint32_t)total;
+        total += counts[b];
+    }
+    if (total > 0xFFFFFFF0ull) return fail(h, ALLL_BAD_ARG, "violated set too large");
+    prefix[n_blocks] = (uint32_t)total;
+    if (total && !d_records) return fail(h, ALLL_BAD_ARG, "d_records == NULL");
+    const uint64_t cap = std::max<uint64_t>(align_up(total, 1024), 1024);
+    POOL(h->d_sh_planes, cap * h->k * 4);
+    POOL(h->d_sh_ids, cap * 4);
+    POOL(h->d_sh_iota, cap * 4);
+    POOL(h->d_sh_s, cap * 4);
+    POOL(h->d_sh_state, cap);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((total + 255) / 256 + 1, (uint64_t)h->sm_count * 8);
+    CK(launch_repack_records(d_records, block_cap, h->k, n_blocks, prefix, h->d_sh_planes, cap, h->d_sh_ids,
+                             h->d_sh_iota, h->d_ctr, grid, h->stream));
+    h->launches++;
+    ClauseView cv{};
+    cv.planes = h->d_sh_planes; cv.m_pad = cap; cv.k = h->k; cv.orig_id = h->d_sh_ids; cv.id_base = 0;
+    CK(launch_mis_resample_args(cv, h->k, h->d_sh_iota, h->d_sh_state, h->d_sh_s, h->d_claim, h->d_bits, h->d_ctr,
+                                seed, round, h->mis_grid, h->stream));
+    h->launches += 2;
+    if (int rc = fetch_counters(h)) return rc;
+    const Counters &c = *h->h_ctr;
+    if (n_total) *n_total = total;
+    if (n_s) *n_s = c.last_n_s;
+    if (n_resampled) *n_resampled = c.last_resampled;
+    CK(launch_reset_counters(h->d_ctr, 0, h->stream)); h->launches++;      // clears `done` after a terminal round
+    CK(cudaStreamSynchronize(h->stream));
+    return ALLL_OK;
+}
+
+int alll_get_stats(alll_handle h, alll_stats *stats)
+{
+    NEED_INSTANCE();
+    if (!stats) return fail(h, ALLL_BAD_ARG, "stats == NULL");
+    if (int rc = fetch_counters(h)) return rc;
+    const Counters &c = *h->h_ctr;
+    std::memset(stats, 0, sizeof(*stats));
+    stats->n_iterations = c.n_iterations;
+    stats->n_resamples = c.n_resamples;
+    stats->sum_mis_size = c.sum_mis;
+    stats->avg_mis_size = c.n_iterations ? c.sum_mis / c.n_iterations : 0;
+    stats->n_clause_evals = h->m * c.n_iterations;
+    stats->n_luby_steps = c.n_luby_steps;
+    stats->n_kernel_launches = h->launches;
+    return ALLL_OK;
+}
+
+int alll_reset_stats(alll_handle h)
+{
+    NEED_INSTANCE();
+    CK(launch_reset_counters(h->d_ctr, 1, h->stream)); h->launches++;
+    CK(cudaStreamSynchronize(h->stream));
+    return ALLL_OK;
 }
 
 int alll_time_sweep(alll_handle h, uint32_t reps, double *ms_per_sweep, uint64_t *n_violated)

@@ -281,10 +281,10 @@ __global__ void reset_counters_kernel(Counters *c, int reset_totals)
 }
 
 // slots -> caller clause ids (for alll_eval / alll_round outputs)
-__global__ void map_ids_kernel(const uint32_t *slots, const uint32_t *orig_id, uint32_t n, uint32_t *out)
+__global__ void map_ids_kernel(const uint32_t *slots, const uint32_t *orig_id, uint32_t id_base, uint32_t n, uint32_t *out)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = orig_id ? orig_id[slots[i]] : slots[i];
+    if (i < n) out[i] = (orig_id ? orig_id[slots[i]] : slots[i]) + id_base;
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -335,10 +335,11 @@ cudaError_t launch_reset_counters(Counters *c, int reset_totals, cudaStream_t s)
     return cudaGetLastError();
 }
 
-cudaError_t launch_map_ids(const uint32_t *slots, const uint32_t *orig_id, uint32_t n, uint32_t *out, cudaStream_t s)
+cudaError_t launch_map_ids(const uint32_t *slots, const uint32_t *orig_id, uint32_t id_base, uint32_t n, uint32_t *out,
+                           cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
-    map_ids_kernel<<<(n + 255) / 256, 256, 0, s>>>(slots, orig_id, n, out);
+    map_ids_kernel<<<(n + 255) / 256, 256, 0, s>>>(slots, orig_id, id_base, n, out);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,184 @@
+"""Clause-range sharded solve of one large instance over several GPUs (BASELINE config 4).
+
+One process per GPU.  Every rank holds a contiguous clause range (global clause ids preserved) and a full replica
+of the bit-packed assignment.  Per round:
+
+    1. every rank sweeps its range and exports its violated clauses as records {global id, k literals};
+    2. ``all_gather`` of the record counts, then of the records padded to the largest count
+       (``torch.distributed``: NCCL over NVLink on GPUs, gloo in the CPU tests);
+    3. every rank runs the identical independent-set + resample step on the full violated set.  Priorities and
+       resample bits are Philox functions of (seed, round, global clause id / variable id), so the replicas stay
+       bit-identical with no second exchange and the trajectory equals the single-GPU one for the same seed.
+
+The round loop, partitioning and exchange live here and are backend-agnostic: ``CudaShardBackend`` drives the C ABI
+(``alll_shard_sweep`` / ``alll_shard_round``); the CPU tests plug in a backend built on the oracle to exercise the
+same host logic under gloo.  The reference has no counterpart: it is single-process, shared-memory OpenMP.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def partition(m: int, world: int) -> list[tuple[int, int]]:
+    """Contiguous, balanced clause ranges: rank r owns [lo_r, hi_r); sizes differ by at most one."""
+    base, rem = divmod(m, world)
+    out, lo = [], 0
+    for r in range(world):
+        hi = lo + base + (1 if r < rem else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+@dataclass
+class ShardedStats:
+    n_iterations: int
+    n_resamples: int
+    avg_mis_size: int
+    sum_mis_size: int
+    n_clause_evals: int          # m_global * n_iterations
+    status: int                  # 0 OK, 1 MAX_ROUNDS
+    solve_ms: float              # device-clock interval of the round loop, max over ranks
+    trace_u: list
+    trace_s: list
+
+
+class CudaShardBackend:
+    """One ``alll_handle`` on this rank's GPU; record buffers are torch tensors (device memory is plumbing)."""
+
+    def __init__(self, device: int):
+        from . import capi
+
+        self.capi = capi
+        self.device = torch.device("cuda", device)
+        self.solver = capi.Solver(device=device)
+        self.k = 0
+        self.send = None
+
+    @property
+    def comm_device(self):
+        return self.device
+
+    def upload(self, n_vars: int, lits_local, id_base: int):
+        """``lits_local``: (m_local, k) uint32 numpy array or int32 CUDA tensor with this rank's clause range."""
+        if isinstance(lits_local, torch.Tensor):
+            m, k = lits_local.shape
+            self.solver.upload_fixedk_device(n_vars, int(m), int(k), lits_local.data_ptr())
+        else:
+            m, k = lits_local.shape
+            self.solver.upload_fixedk(n_vars, lits_local)
+        self.solver.set_id_base(id_base)
+        self.solver.reset_stats()
+        self.k, self.m_local = int(k), int(m)
+        cap = max(4096, int(self.m_local * 2.0 ** (-self.k) * 2) + 1024)
+        self.send = torch.empty((cap, self.k + 1), dtype=torch.int32, device=self.device)
+
+    def randomize(self, seed: int):
+        self.solver.randomize(seed)
+
+    def set_assignment(self, bools):
+        self.solver.set_assignment(bools)
+
+    def get_assignment(self):
+        return self.solver.get_assignment()
+
+    def sweep_export(self):
+        """Returns (records tensor [cap, k+1] on the device, n_local)."""
+        while True:
+            try:
+                n = self.solver.shard_sweep(self.send.data_ptr(), self.send.shape[0])
+                return self.send, n
+            except self.capi.AlllError as e:
+                if e.status != self.capi.CAPACITY:
+                    raise
+                self.send = torch.empty((self.send.shape[0] * 4, self.k + 1), dtype=torch.int32, device=self.device)
+
+    def shard_round(self, recs: torch.Tensor, counts, seed: int, rnd: int):
+        """``recs``: [R, cap, k+1] gathered records on the device."""
+        torch.cuda.current_stream(self.device).synchronize()      # the NCCL all-gather ran on torch's stream
+        return self.solver.shard_round(recs.data_ptr(), counts, recs.shape[1], seed, rnd)
+
+    def stats(self):
+        return self.solver.get_stats()
+
+    def clock(self):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        return ev
+
+    @staticmethod
+    def elapsed_ms(a, b):
+        b.synchronize()
+        return a.elapsed_time(b)
+
+
+class ShardedSolver:
+    """Backend-agnostic driver: partition, per-round exchange, termination, statistics."""
+
+    def __init__(self, backend, rank: int = 0, world: int = 1, group=None):
+        self.backend, self.rank, self.world, self.group = backend, rank, world, group
+        self.m_global = 0
+        self.k = 0
+
+    # -- upload -------------------------------------------------------------------------------------------
+    def upload_range(self, n_vars: int, lits_local, m_global: int, id_base: int):
+        """This rank already holds its own clause range."""
+        self.n_vars, self.m_global, self.k = n_vars, int(m_global), int(lits_local.shape[1])
+        self.backend.upload(n_vars, lits_local, id_base)
+
+    def upload_full(self, n_vars: int, lits_full):
+        """Every rank sees the whole (m, k) literal matrix and keeps only its range."""
+        lo, hi = partition(int(lits_full.shape[0]), self.world)[self.rank]
+        self.upload_range(n_vars, lits_full[lo:hi], int(lits_full.shape[0]), lo)
+
+    # -- exchange -----------------------------------------------------------------------------------------
+    def _all_gather_records(self, send: torch.Tensor, n_local: int):
+        dev = send.device
+        if self.world == 1:
+            cap = max(n_local, 1)
+            return send[:cap].unsqueeze(0), [n_local]
+        mine = torch.tensor([n_local], dtype=torch.int64, device=dev)
+        counts_t = torch.empty(self.world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts_t, mine, group=self.group)
+        counts = [int(c) for c in counts_t.tolist()]
+        cap = max(max(counts), 1)
+        if send.shape[0] < cap:                                   # another rank has more violated clauses than our buffer
+            grown = torch.empty((cap, send.shape[1]), dtype=send.dtype, device=dev)
+            grown[: send.shape[0]] = send
+            send = grown
+        recv = torch.empty((self.world, cap, send.shape[1]), dtype=send.dtype, device=dev)
+        dist.all_gather_into_tensor(recv.view(-1), send[:cap].contiguous().view(-1), group=self.group)
+        return recv, counts
+
+    # -- round loop ---------------------------------------------------------------------------------------
+    def solve(self, seed: int, max_rounds: int = 1 << 20) -> ShardedStats:
+        be = self.backend
+        t0 = be.clock()
+        status, rnd = 1, 0
+        n_iter = n_res = sum_mis = 0
+        trace_u, trace_s = [], []
+        max_rounds = max(max_rounds, 1)
+        while rnd < max_rounds:
+            send, n_local = be.sweep_export()
+            recs, counts = self._all_gather_records(send, n_local)
+            n_total, n_s, n_r = be.shard_round(recs, counts, seed, rnd)
+            n_iter += 1                                          # every sweep counts, also the terminal one (SATInstance.h:261)
+            trace_u.append(n_total)
+            trace_s.append(n_s)
+            if n_total == 0:                                     # SATInstance.h:285-287
+                status = 0
+                break
+            sum_mis += n_s
+            n_res += n_r
+            rnd += 1
+        t1 = be.clock()
+        ms = be.elapsed_ms(t0, t1)
+        if self.world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=be.comm_device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            ms = float(t.item())
+        return ShardedStats(n_iter, n_res, sum_mis // n_iter, sum_mis, self.m_global * n_iter, status, ms, trace_u, trace_s)

@@ -133,6 +133,28 @@ ALLL_API int alll_round(alll_handle h, uint64_t seed, uint32_t round,
  * The assignment on the device is the in/out state; fetch it with alll_get_assignment. */
 ALLL_API int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *stats);
 
+/* ---- clause-range sharded mode: one large instance over several GPUs -----------------
+ * Each GPU (one handle, one process) uploads the contiguous clause range [id_base, id_base+m) and holds a full
+ * replica of the assignment.  Per round: alll_shard_sweep on every GPU -> all-gather of the record buffers
+ * (NCCL, done by the caller) -> alll_shard_round on every GPU with identical data.  Replicas stay bit-identical
+ * because priorities and resample bits are keyed on global clause ids / variable ids.  No reference counterpart
+ * (the reference is single-process, shared-memory OpenMP). */
+
+/* First global clause id of this handle's clause range; ids reported and used for priorities are global. */
+ALLL_API int alll_set_id_base(alll_handle h, uint64_t id_base);
+/* Sweep the local range and write its violated clauses as row-major records {global id, k literals}
+ * ((k+1) uint32 each) to the DEVICE buffer d_records (cap_records records).  *n_local = local |U|. */
+ALLL_API int alll_shard_sweep(alll_handle h, uint32_t *d_records, uint64_t cap_records, uint64_t *n_local);
+/* MIS + resample over the gathered records: n_blocks blocks of block_cap records each (DEVICE buffer), counts[b]
+ * valid records in block b (HOST array).  Sum of counts == 0 is the terminal round.  Updates the statistics
+ * (alll_get_stats) exactly like one iteration of alll_solve. */
+ALLL_API int alll_shard_round(alll_handle h, const uint32_t *d_records, const uint64_t *counts, uint32_t n_blocks,
+                     uint64_t block_cap, uint64_t seed, uint32_t round, uint64_t *n_total, uint64_t *n_s,
+                     uint64_t *n_resampled);
+/* Running Statistics totals of the handle (since upload / alll_reset_stats / the start of the last alll_solve). */
+ALLL_API int alll_get_stats(alll_handle h, alll_stats *stats);
+ALLL_API int alll_reset_stats(alll_handle h);
+
 /* ---- measurement hooks -------------------------------------------------------------- */
 
 /* `reps` back-to-back sweeps of the current assignment; *ms_per_sweep is the mean kernel
