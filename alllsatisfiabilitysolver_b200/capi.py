@@ -44,7 +44,7 @@ class StatsC(C.Structure):
     _fields_ = [("n_iterations", C.c_uint64), ("n_resamples", C.c_uint64), ("avg_mis_size", C.c_uint64),
                 ("sum_mis_size", C.c_uint64), ("n_clause_evals", C.c_uint64), ("n_luby_steps", C.c_uint64),
                 ("n_kernel_launches", C.c_uint64), ("solve_ms", C.c_double), ("sweep_ms", C.c_double),
-                ("status", C.c_int32), ("reserved", C.c_int32)]
+                ("status", C.c_int32), ("reserved", C.c_int32), ("between_sweeps_ms", C.c_double)]
 
 
 @dataclass
@@ -60,6 +60,7 @@ class Stats:
     solve_ms: float
     sweep_ms: float
     status: int
+    between_sweeps_ms: float = 0.0
 
 
 _lib = None
@@ -202,7 +203,7 @@ class Solver:
         st = StatsC()
         self._check(self.lib.alll_solve(self.h, seed, max_rounds, C.byref(st)), allow=(OK, MAX_ROUNDS))
         return Stats(st.n_iterations, st.n_resamples, st.avg_mis_size, st.sum_mis_size, st.n_clause_evals,
-                     st.n_luby_steps, st.n_kernel_launches, st.solve_ms, st.sweep_ms, st.status)
+                     st.n_luby_steps, st.n_kernel_launches, st.solve_ms, st.sweep_ms, st.status, st.between_sweeps_ms)
 
     # -- clause-range sharded mode (device pointers; the all-gather between the two calls is the caller's) -------
     def set_id_base(self, id_base: int):

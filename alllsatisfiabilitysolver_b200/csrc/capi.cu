@@ -146,8 +146,8 @@ int alloc_common(alll_handle h)
     const uint64_t m1 = std::max<uint64_t>(h->m, 1), n1 = std::max<uint64_t>(h->n_vars, 1);
     POOL(h->d_bits, (size_t)std::max<uint32_t>(h->n_words_alloc, 4) * 4);
     CK(cudaMemsetAsync(h->d_bits, 0, (size_t)std::max<uint32_t>(h->n_words_alloc, 4) * 4, h->stream));
-    POOL(h->d_claim, n1 * 8);
-    CK(launch_fill_u64(h->d_claim, n1, CLAIM_FREE, h->stream)); h->launches++;
+    POOL(h->d_claim, 2 * n1 * 8);                          // two claim arrays: even / odd Luby steps
+    CK(launch_fill_u64(h->d_claim, 2 * n1, CLAIM_FREE, h->stream)); h->launches++;
     POOL(h->d_viol, m1 * 4);
     POOL(h->d_s, m1 * 4);
     POOL(h->d_ids_out, m1 * 4);
@@ -276,8 +276,8 @@ int enqueue_sweep(alll_handle h)
 
 int enqueue_mis_resample(alll_handle h, uint64_t seed, uint32_t round)
 {
-    CK(launch_mis_resample_args(clause_view(h), h->kmax, h->d_viol, h->d_state, h->d_s, h->d_claim, h->d_bits,
-                                h->d_ctr, seed, round, h->mis_grid, h->stream));
+    CK(launch_mis_resample_args(clause_view(h), h->kmax, h->d_viol, h->d_state, h->d_s, h->d_claim, h->n_vars,
+                                h->d_bits, h->d_ctr, seed, round, h->mis_grid, h->stream));
     h->launches += 2;                    // cluster kernel + cooperative grid kernel
     return ALLL_OK;
 }
@@ -550,12 +550,16 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
     float ms = 0.f;
     if (useful_rounds) CK(cudaEventElapsedTime(&ms, ev_begin, ev_last));
     CK(cudaStreamSynchronize(h->stream));                 // drain the speculative (no-op) rounds
-    double sweep_ms = 0.0;
+    double sweep_ms = 0.0, between_ms = 0.0;
     const int timed = (int)std::min<uint64_t>(useful_rounds, MAX_TIMED_ROUNDS);
     for (int i = 0; i < timed; i++) {
         float t = 0.f;
         CK(cudaEventElapsedTime(&t, h->ev[2 * i], h->ev[2 * i + 1]));
         sweep_ms += t;
+        if (i + 1 < timed) {
+            CK(cudaEventElapsedTime(&t, h->ev[2 * i + 1], h->ev[2 * i + 2]));
+            between_ms += t;
+        }
     }
     if (int rc = fetch_counters(h)) return rc;
     CK(launch_reset_counters(h->d_ctr, 0, h->stream)); h->launches++;      // clears `done` for the single-step calls
@@ -570,6 +574,7 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
     stats->n_kernel_launches = h->launches - launches0;
     stats->solve_ms = ms;
     stats->sweep_ms = timed ? sweep_ms * ((double)c.n_iterations / timed) : 0.0;
+    stats->between_sweeps_ms = timed > 1 ? between_ms * ((double)(c.n_iterations - 1) / (timed - 1)) : 0.0;
     stats->status = status;
     return status;
 }
@@ -632,8 +637,8 @@ int alll_shard_round(alll_handle h, const uint32_t *d_records, const uint64_t *c
     h->launches++;
     ClauseView cv{};
     cv.planes = h->d_sh_planes; cv.m_pad = cap; cv.k = h->k; cv.orig_id = h->d_sh_ids; cv.id_base = 0;
-    CK(launch_mis_resample_args(cv, h->k, h->d_sh_iota, h->d_sh_state, h->d_sh_s, h->d_claim, h->d_bits, h->d_ctr,
-                                seed, round, h->mis_grid, h->stream));
+    CK(launch_mis_resample_args(cv, h->k, h->d_sh_iota, h->d_sh_state, h->d_sh_s, h->d_claim, h->n_vars, h->d_bits,
+                                h->d_ctr, seed, round, h->mis_grid, h->stream));
     h->launches += 2;
     if (int rc = fetch_counters(h)) return rc;
     const Counters &c = *h->h_ctr;

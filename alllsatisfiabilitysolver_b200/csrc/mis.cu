@@ -4,9 +4,9 @@
 // picked clause) and resample_clauses (SATInstance.h:340-365).
 //
 // K3: fixed-priority Luby.  Every violated clause c gets the key (Philox priority(seed, round, id), id).
-//     step:  A) undecided clauses first drop out if one of their variables is TAKEN, otherwise
-//               atomicMin their key into claim[var] for every variable they touch;
-//            B) a clause that still owns all its claims joins S and marks its variables TAKEN.
+//     Every undecided clause atomicMin-s its key into claim[var] for every variable it touches; a clause
+//     that owns all its claims joins S and marks its variables TAKEN; a clause that sees a TAKEN variable
+//     drops out; the rest claim again for the next step (in the other of two claim arrays).
 //     Iterated to a fixed point this is exactly the greedy independent set in ascending key order
 //     (what oracle/alll_oracle.c:alll_oracle_priority_mis computes sequentially) -- independent and
 //     maximal like the reference's set (SATInstance.h:415-447), and a pure function of (seed, round, U):
@@ -18,8 +18,9 @@
 //     clause is harmless).  The same pass restores claim[var] = FREE for everything U touched.
 //
 // Latency structure: the literals, priority and id of every violated clause are read ONCE into shared
-// memory (they live scattered over k literal planes -- k DRAM round trips), and all claim reads of a
-// phase are issued together, so a phase costs ~2 memory round trips however wide the clauses are.
+// memory (they live scattered over k literal planes -- k DRAM round trips), all claim reads of a step are
+// issued together, and deciding step s is fused with claiming for step s+1: one barrier and one memory
+// round trip per Luby step however wide the clauses are.
 //
 // Two kernels are enqueued per round and decide on the device which one acts (the host does not know
 // |U|: rounds are enqueued speculatively, see capi.cu):
@@ -48,7 +49,8 @@ struct MisParams {
     const uint32_t *viol;       // U as clause slots
     uint8_t *state;             // per U entry
     uint32_t *s_slots;          // out: S as clause slots
-    unsigned long long *claim;  // [n_vars], FREE between rounds
+    unsigned long long *claim;  // [2][n_vars] (even / odd Luby steps), FREE between rounds
+    uint64_t n_vars;
     uint32_t *bits;
     Counters *ctr;
     uint64_t seed;
@@ -113,16 +115,27 @@ __device__ __forceinline__ Item open_item(const MisParams &p, uint32_t it, uint3
 }
 
 // Threads `first`, `first + stride`, ... of the participating group own the same U entries in every phase.
+//
+// One barrier and one memory round trip per Luby step: step s decides on the claims standing in array s&1 and,
+// in the same pass, clauses that neither won nor dropped claim for step s+1 in the OTHER array, so readers of
+// step s are never disturbed by claims of step s+1.  A clause that misses a TAKEN mark written concurrently by a
+// winner merely claims once more in vain (its TAKEN variable can never read back its key) and drops out one step
+// later; the set of winners is unchanged: a clause wins only when every neighbour with a smaller key has dropped.
 template <class Barrier>
 __device__ void mis_resample_body(const MisParams &p, Barrier &bar, uint32_t first, uint32_t stride, uint32_t n_u)
 {
     __shared__ unsigned int s_live;
+    unsigned long long *const claim0 = p.claim;
+    unsigned long long *const claim1 = p.claim + p.n_vars;
 
-    {   // ---- gather: one pass over the scattered literal planes
+    {   // ---- gather: one pass over the scattered literal planes, and the claims of step 0
         uint32_t it = 0;
         for (uint32_t i = first; i < n_u; i += stride, ++it) {
             p.state[i] = UNDECIDED;
-            open_item(p, it, i, true);
+            const Item x = open_item(p, it, i, true);
+            const unsigned long long key = claim_key(0, x.prio, x.id);
+#pragma unroll 8
+            for (uint32_t j = 0; j < x.k; j++) atomicMin(&claim0[x.lit(p, j) >> 1], key);
         }
     }
     if (first < 64) p.ctr->step_live[first] = 0;     // only the acting MIS kernel touches step_live
@@ -130,62 +143,62 @@ __device__ void mis_resample_body(const MisParams &p, Barrier &bar, uint32_t fir
 
     uint32_t step = 0;
     for (;;) {
-        if (step != 0 && step % TAGS == 0) {
-            // the step tag wraps: stale claims would now undercut fresh ones, so clear what the survivors touch
+        unsigned long long *const cur = (step & 1u) ? claim1 : claim0;
+        unsigned long long *const nxt = (step & 1u) ? claim0 : claim1;
+        if ((step + 1) % TAGS == 0) {
+            // the tag of step+1 wraps to the largest value: stale claims in `nxt` would undercut fresh ones,
+            // so clear what the still-undecided clauses touch there (nobody reads `nxt` during this step)
             uint32_t it = 0;
             for (uint32_t i = first; i < n_u; i += stride, ++it) {
                 if (p.state[i] != UNDECIDED) continue;
                 const Item x = open_item(p, it, i, false);
                 for (uint32_t j = 0; j < x.k; j++) {
                     const uint32_t v = x.lit(p, j) >> 1;
-                    if (ld_claim(&p.claim[v]) != CLAIM_TAKEN) p.claim[v] = CLAIM_FREE;
+                    if (ld_claim(&nxt[v]) != CLAIM_TAKEN) nxt[v] = CLAIM_FREE;
                 }
             }
             bar.sync();
         }
-        // ---- phase A: drop out next to winners, otherwise claim
         if (threadIdx.x == 0) s_live = 0;
         __syncthreads();
         uint32_t live = 0, it = 0;
         for (uint32_t i = first; i < n_u; i += stride, ++it) {
             if (p.state[i] != UNDECIDED) continue;
             const Item x = open_item(p, it, i, false);
-            bool taken = false;
-#pragma unroll 8
-            for (uint32_t j = 0; j < x.k; j++) taken |= ld_claim(&p.claim[x.lit(p, j) >> 1]) == CLAIM_TAKEN;   // no early exit: loads overlap
-            if (taken) { p.state[i] = DROPPED; continue; }
             const unsigned long long key = claim_key(step, x.prio, x.id);
+            bool win = true, taken = false;
 #pragma unroll 8
-            for (uint32_t j = 0; j < x.k; j++) atomicMin(&p.claim[x.lit(p, j) >> 1], key);
-            live++;
+            for (uint32_t j = 0; j < x.k; j++) {             // no early exit: the loads overlap
+                const unsigned long long c = ld_claim(&cur[x.lit(p, j) >> 1]);
+                win &= c == key;
+                taken |= c == CLAIM_TAKEN;
+            }
+            if (win) {
+                p.state[i] = IN_SET;
+#pragma unroll 8
+                for (uint32_t j = 0; j < x.k; j++) {
+                    const uint32_t v = x.lit(p, j) >> 1;
+                    claim0[v] = CLAIM_TAKEN;
+                    claim1[v] = CLAIM_TAKEN;
+                }
+                p.s_slots[atomicAdd(&p.ctr->n_s, 1u)] = x.slot;
+            } else if (taken) {
+                p.state[i] = DROPPED;
+            } else {
+                const unsigned long long next_key = claim_key(step + 1, x.prio, x.id);
+#pragma unroll 8
+                for (uint32_t j = 0; j < x.k; j++) atomicMin(&nxt[x.lit(p, j) >> 1], next_key);
+                live++;
+            }
         }
         if (live) atomicAdd(&s_live, live);
         __syncthreads();
-        if (threadIdx.x == 0 && s_live) atomicAdd(&p.ctr->step_live[step & 63u], s_live);
-        bar.sync();
-        const unsigned int total_live = ld_u32(&p.ctr->step_live[step & 63u]);
-        if (total_live == 0) break;
-
-        // ---- phase B: owners of all their claims win
-        it = 0;
-        for (uint32_t i = first; i < n_u; i += stride, ++it) {
-            if (p.state[i] != UNDECIDED) continue;
-            const Item x = open_item(p, it, i, false);
-            const unsigned long long key = claim_key(step, x.prio, x.id);
-            bool win = true;
-            // another winner may be storing TAKEN to ITS variables concurrently; ours still read == key
-#pragma unroll 8
-            for (uint32_t j = 0; j < x.k; j++) win &= ld_claim(&p.claim[x.lit(p, j) >> 1]) == key;
-            if (!win) continue;
-            p.state[i] = IN_SET;
-#pragma unroll 8
-            for (uint32_t j = 0; j < x.k; j++) p.claim[x.lit(p, j) >> 1] = CLAIM_TAKEN;
-            p.s_slots[atomicAdd(&p.ctr->n_s, 1u)] = x.slot;
-        }
-        // the slot of step+2 (mod 64) is reused two steps from now: clear it while nobody reads it
-        if (first == 0) p.ctr->step_live[(step + 2) & 63u] = 0;
+        if (threadIdx.x == 0 && s_live) atomicAdd(&p.ctr->step_live[(step + 1) & 63u], s_live);
+        // the slot of step+3 (mod 64) is next written two steps from now: clear it while nobody touches it
+        if (first == 0) p.ctr->step_live[(step + 3) & 63u] = 0;
         bar.sync();
         step++;
+        if (ld_u32(&p.ctr->step_live[step & 63u]) == 0) break;      // nobody claimed for this step: all decided
     }
 
     // ---- K4 + claim reset.  All claim reads of this round are behind the last barrier.
@@ -197,7 +210,8 @@ __device__ void mis_resample_body(const MisParams &p, Barrier &bar, uint32_t fir
 #pragma unroll 8
         for (uint32_t j = 0; j < x.k; j++) {
             const uint32_t v = x.lit(p, j) >> 1;
-            p.claim[v] = CLAIM_FREE;
+            claim0[v] = CLAIM_FREE;
+            claim1[v] = CLAIM_FREE;
             if (in_s) {
                 const uint32_t mask = 1u << (v & 31u);
                 if (random_bit(p.seed, STREAM_RESAMPLE, p.round, v)) atomicOr(&p.bits[v >> 5], mask);
@@ -316,10 +330,10 @@ cudaError_t mis_configure(int device, uint32_t kmax, uint32_t *grid_out)
 
 // Enqueues both MIS kernels of one round (2 launches).
 cudaError_t launch_mis_resample_args(const ClauseView &cv, uint32_t kmax, const uint32_t *viol, uint8_t *state,
-                                     uint32_t *s_slots, unsigned long long *claim, uint32_t *bits, Counters *ctr,
-                                     uint64_t seed, uint32_t round, uint32_t grid, cudaStream_t s)
+                                     uint32_t *s_slots, unsigned long long *claim, uint64_t n_vars, uint32_t *bits,
+                                     Counters *ctr, uint64_t seed, uint32_t round, uint32_t grid, cudaStream_t s)
 {
-    MisParams p{cv, viol, state, s_slots, claim, bits, ctr, seed, round, kmax, cluster_cache_items(kmax)};
+    MisParams p{cv, viol, state, s_slots, claim, n_vars, bits, ctr, seed, round, kmax, cluster_cache_items(kmax)};
     mis_cluster_kernel<<<CL_SIZE, CL_THREADS, cluster_smem_bytes(kmax), s>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ALLL_ABI_VERSION 1
+#define ALLL_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define ALLL_API __attribute__((visibility("default")))
@@ -79,6 +79,8 @@ typedef struct {
     double   sweep_ms;          /* device time inside the clause-evaluation sweeps     */
     int32_t  status;            /* alll_status of the solve                            */
     int32_t  reserved;
+    double   between_sweeps_ms; /* device time from the end of a sweep to the start of the next: independent-set
+                                   and resample kernels plus launch gaps                                       */
 } alll_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------- */

@@ -21,6 +21,7 @@ ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--solves", type=int, default=0)
 ap.add_argument("--smem", type=int, default=0)
 ap.add_argument("--flags", type=int, default=0)
+ap.add_argument("--max-rounds", type=int, default=2000)
 a = ap.parse_args()
 cfg = CONFIGS[a.workload]
 n = int(cfg["n"] * a.scale)
@@ -39,7 +40,7 @@ out = dict(workload=a.workload, n=n, m=m, k=k, layout=s.layout_info(), sweep_ms=
            achieved_GBps=alg / (ms * 1e-3) / 1e9)
 for i in range(a.solves):
     s.randomize(10 + i)
-    st = s.solve(10 + i)
-    out[f"solve{i}"] = dict(ms=st.solve_ms, sweep_ms=st.sweep_ms, iters=st.n_iterations, luby=st.n_luby_steps,
+    st = s.solve(10 + i, a.max_rounds)
+    out[f"solve{i}"] = dict(ms=st.solve_ms, sweep_ms=st.sweep_ms, between_ms=st.between_sweeps_ms, iters=st.n_iterations, luby=st.n_luby_steps,
                             launches=st.n_kernel_launches, status=st.status)
 print(json.dumps(out))
