@@ -15,8 +15,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liballl_b200.so")
 
-OK, MAX_ROUNDS, EMPTY_CLAUSE, BAD_ARG, CUDA_ERROR, NCCL_ERROR, NO_INSTANCE, CAPACITY = range(8)
-STATUS_NAMES = ["OK", "MAX_ROUNDS", "EMPTY_CLAUSE", "BAD_ARG", "CUDA_ERROR", "NCCL_ERROR", "NO_INSTANCE", "CAPACITY"]
+OK, MAX_ROUNDS, EMPTY_CLAUSE, BAD_ARG, CUDA_ERROR, NCCL_ERROR, NO_INSTANCE, CAPACITY, PREEMPTED = range(9)
+STATUS_NAMES = ["OK", "MAX_ROUNDS", "EMPTY_CLAUSE", "BAD_ARG", "CUDA_ERROR", "NCCL_ERROR", "NO_INSTANCE", "CAPACITY", "PREEMPTED"]
 FLAG_NO_BUCKETING = 1
 
 #: every symbol include/alll_b200.h declares (tests check the library exports exactly these)
@@ -27,6 +27,7 @@ SYMBOLS = [
     "alll_eval", "alll_verify", "alll_round", "alll_solve",
     "alll_time_sweep", "alll_launch_count", "alll_layout_info",
     "alll_set_id_base", "alll_shard_sweep", "alll_shard_round", "alll_get_stats", "alll_reset_stats",
+    "alll_batch_upload", "alll_batch_solve",
 ]
 
 
@@ -38,6 +39,11 @@ class AlllError(RuntimeError):
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("sweep_smem_bytes", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class BatchStatsC(C.Structure):
+    _fields_ = [("n_iterations", C.c_uint64), ("n_resamples", C.c_uint64), ("sum_mis_size", C.c_uint64),
+                ("status", C.c_int32), ("reserved", C.c_int32)]
 
 
 class StatsC(C.Structure):
@@ -100,6 +106,8 @@ def load() -> C.CDLL:
     L.alll_shard_round.argtypes = [vp, vp, C.POINTER(u64), u32, u64, u64, u32, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.alll_get_stats.argtypes = [vp, C.POINTER(StatsC)]
     L.alll_reset_stats.argtypes = [vp]
+    L.alll_batch_upload.argtypes = [vp, u32, u64, u32, vp, vp]
+    L.alll_batch_solve.argtypes = [vp, u32, vp, u64, C.c_int, vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     for name in SYMBOLS:
         getattr(L, name)            # raises AttributeError if the library misses a declared entry point
     _lib = L
@@ -229,6 +237,28 @@ class Solver:
 
     def reset_stats(self):
         self._check(self.lib.alll_reset_stats(self.h))
+
+    # -- batched small instances / seed portfolio -------------------------------------------------------
+    def batch_upload(self, n_vars: int, k: int, clause_off: np.ndarray, lits: np.ndarray):
+        """``lits``: row-major (total_clauses, k) uint32; ``clause_off``: (n_instances+1,) row offsets."""
+        clause_off = np.ascontiguousarray(clause_off, np.uint64)
+        lits = np.ascontiguousarray(lits, np.uint32)
+        self._check(self.lib.alll_batch_upload(self.h, len(clause_off) - 1, n_vars, k, clause_off.ctypes.data,
+                                               lits.ctypes.data if lits.size else None))
+        self._batch = (len(clause_off) - 1, n_vars)
+
+    def batch_solve(self, seeds, max_rounds: int = 1 << 20, portfolio: bool = False, want_assignments: bool = True):
+        """Returns (stats structured array, assignments [n_jobs, n_vars] or None, winner, device_ms)."""
+        seeds = np.ascontiguousarray(seeds, np.uint64)
+        n_jobs, n_vars = len(seeds), self._batch[1]
+        stats = np.zeros(n_jobs, dtype=np.dtype([("n_iterations", "<u8"), ("n_resamples", "<u8"), ("sum_mis_size", "<u8"),
+                                                 ("status", "<i4"), ("reserved", "<i4")]))
+        assign = np.zeros((n_jobs, n_vars), np.uint8) if want_assignments else None
+        winner, ms = C.c_int32(-1), C.c_double(0.0)
+        self._check(self.lib.alll_batch_solve(self.h, n_jobs, seeds.ctypes.data, max_rounds, 1 if portfolio else 0,
+                                              assign.ctypes.data if want_assignments else None, stats.ctypes.data,
+                                              C.byref(winner), C.byref(ms)))
+        return stats, assign, int(winner.value), float(ms.value)
 
     # -- measurement ----------------------------------------------------------------------
     def time_sweep(self, reps: int):

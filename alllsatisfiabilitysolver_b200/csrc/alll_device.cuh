@@ -20,6 +20,7 @@ constexpr uint32_t MAX_BUCKETS = 256;
 constexpr uint32_t EAGER_PLANES = 5;              // planes streamed by the sweep; the tail planes are fetched only for surviving clauses
 constexpr uint32_t RESIDENT_CAP = 4;              // at most this many literals of a clause are placed as bucket-resident
 constexpr uint32_t MAX_K = 32;
+constexpr uint32_t MIS_CLUSTER_MAX_U = 8192;       // violated sets up to this size are handled by one 8 x 1024-thread cluster
 constexpr uint32_t MAX_SHARDS = 64;                // clause-range shards (GPUs) of one instance
 constexpr uint32_t INVALID_ID = 0xFFFFFFFFu;
 
@@ -135,6 +136,22 @@ struct Counters {
     unsigned int done;
     unsigned int pad;
 };
+
+// What the round loop on the host needs to know about a finished round.  Lives in pinned host memory; the MIS
+// kernel's last thread stores it directly over PCIe (no copy-engine hop between the kernels of consecutive rounds)
+// and publishes it by writing `seq` last.
+struct RoundNote {
+    unsigned int n_viol;
+    unsigned int n_s;
+    unsigned long long seq;
+};
+
+// Per-job result of the batched small-instance kernel (mirrors alll_batch_stats of the C ABI).
+struct BatchJobStats {
+    unsigned long long n_iterations, n_resamples, sum_mis_size;
+    int status, reserved;
+};
+constexpr int BATCH_PREEMPTED = 8;      // == ALLL_PREEMPTED: portfolio job stopped because another seed finished first
 
 struct BucketSeg {
     uint32_t tile_begin;        // first sweep tile of this bucket

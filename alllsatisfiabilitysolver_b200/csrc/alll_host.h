@@ -18,7 +18,8 @@ cudaError_t launch_sweep_csr(const uint64_t *off, const uint32_t *lit, uint64_t 
 cudaError_t mis_configure(int device, uint32_t kmax, uint32_t *grid_out);
 cudaError_t launch_mis_resample_args(const ClauseView &cv, uint32_t kmax, const uint32_t *viol, uint8_t *state,
                                      uint32_t *s_slots, unsigned long long *claim, uint64_t n_vars, uint32_t *bits,
-                                     Counters *ctr, uint64_t seed, uint32_t round, uint32_t grid, cudaStream_t s);
+                                     Counters *ctr, uint64_t seed, uint32_t round, uint32_t grid, bool with_grid,
+                                     RoundNote *note, unsigned long long seq, cudaStream_t s);
 cudaError_t launch_reset_counters(Counters *c, int reset_totals, cudaStream_t s);
 cudaError_t launch_map_ids(const uint32_t *slots, const uint32_t *orig_id, uint32_t id_base, uint32_t n, uint32_t *out,
                            cudaStream_t s);
@@ -29,6 +30,16 @@ cudaError_t launch_export_records(const ClauseView &cv, const uint32_t *viol, co
 cudaError_t launch_repack_records(const uint32_t *records, uint64_t block_cap, uint32_t k, uint32_t n_blocks,
                                   const uint32_t *prefix, uint32_t *planes, uint64_t dense_cap, uint32_t *ids,
                                   uint32_t *iota, Counters *ctr, uint32_t grid, cudaStream_t s);
+
+// batch.cu
+size_t batch_smem_bytes(uint32_t n_vars, uint32_t n_words, uint32_t m_max);
+cudaError_t launch_batch_solve(const uint32_t *planes, uint64_t m_pad, const uint32_t *inst_off, const uint32_t *inst_m,
+                               uint32_t n_instances, uint32_t n_vars, uint32_t n_words, uint32_t k, uint32_t m_max,
+                               const uint64_t *seeds, uint64_t max_rounds, uint32_t *bits_out, BatchJobStats *stats,
+                               int portfolio, int *winner, uint32_t n_jobs, cudaStream_t s);
+cudaError_t launch_batch_transpose(const uint32_t *lit, const uint64_t *src_off, const uint32_t *inst_off, uint32_t n_instances,
+                                   uint32_t k, uint32_t n_vars, uint32_t *planes, uint64_t m_pad, uint32_t *err, cudaStream_t s);
+cudaError_t launch_batch_unpack(const uint32_t *bits, uint32_t n_words, uint32_t n_vars, uint64_t total, uint8_t *out, cudaStream_t s);
 
 // layout.cu
 cudaError_t launch_transpose(const uint32_t *lit, uint64_t m, uint32_t k, uint64_t n_vars, uint32_t *planes,

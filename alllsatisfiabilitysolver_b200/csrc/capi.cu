@@ -5,6 +5,7 @@
 // in the kernels of sweep.cu / mis.cu / layout.cu.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -53,7 +54,8 @@ struct alll_solver {
     uint8_t *d_state = nullptr, *d_bools = nullptr;
     Counters *d_ctr = nullptr;
     Counters *h_ctr = nullptr;           // pinned
-    Counters *h_ring = nullptr;          // pinned [ROUNDS_IN_FLIGHT]: per-round snapshots for the pipelined loop
+    RoundNote *h_ring = nullptr;         // pinned [ROUNDS_IN_FLIGHT]: written by the MIS kernels, polled by the round loop
+    unsigned long long seq = 0;          // last sequence number handed to a round
     cudaEvent_t ev_round[ROUNDS_IN_FLIGHT] = {};
     uint32_t sweep_grid = 1, mis_grid = 1;
     std::vector<cudaEvent_t> ev;         // 2 * MAX_TIMED_ROUNDS + 2
@@ -66,6 +68,15 @@ struct alll_solver {
     // sharded mode: dense copy of the gathered violated records
     uint32_t *d_sh_planes = nullptr, *d_sh_ids = nullptr, *d_sh_iota = nullptr, *d_sh_s = nullptr;
     uint8_t *d_sh_state = nullptr;
+    // batched small instances
+    bool has_batch = false;
+    uint32_t b_n_inst = 0, b_n_vars = 0, b_n_words = 0, b_k = 0, b_m_max = 0;
+    uint64_t b_m_pad = 0;
+    uint32_t *d_b_planes = nullptr, *d_b_off = nullptr, *d_b_m = nullptr, *d_b_bits = nullptr, *d_b_lit = nullptr;
+    uint64_t *d_b_src_off = nullptr, *d_b_seeds = nullptr;
+    BatchJobStats *d_b_stats = nullptr;
+    uint8_t *d_b_bytes = nullptr;
+    int *d_b_winner = nullptr;
     uint8_t *d_tmp_bkt = nullptr;
     uint32_t *d_tmp_cnt = nullptr, *d_tmp_err = nullptr, *d_stage = nullptr;
 };
@@ -104,6 +115,9 @@ void release_buffers(alll_handle h)
     dfree(h->d_bits); dfree(h->d_claim); dfree(h->d_viol); dfree(h->d_s); dfree(h->d_ids_out);
     dfree(h->d_state); dfree(h->d_bools); dfree(h->d_tmp_bkt); dfree(h->d_tmp_cnt); dfree(h->d_tmp_err); dfree(h->d_stage);
     dfree(h->d_sh_planes); dfree(h->d_sh_ids); dfree(h->d_sh_iota); dfree(h->d_sh_s); dfree(h->d_sh_state);
+    dfree(h->d_b_planes); dfree(h->d_b_off); dfree(h->d_b_m); dfree(h->d_b_bits); dfree(h->d_b_lit); dfree(h->d_b_src_off);
+    dfree(h->d_b_seeds); dfree(h->d_b_stats); dfree(h->d_b_bytes); dfree(h->d_b_winner);
+    h->has_batch = false;
     h->caps.clear();
     h->has_instance = false;
 }
@@ -274,11 +288,12 @@ int enqueue_sweep(alll_handle h)
     return ALLL_OK;
 }
 
-int enqueue_mis_resample(alll_handle h, uint64_t seed, uint32_t round)
+int enqueue_mis_resample(alll_handle h, uint64_t seed, uint32_t round, bool with_grid = true, RoundNote *note = nullptr,
+                         unsigned long long seq = 0)
 {
     CK(launch_mis_resample_args(clause_view(h), h->kmax, h->d_viol, h->d_state, h->d_s, h->d_claim, h->n_vars,
-                                h->d_bits, h->d_ctr, seed, round, h->mis_grid, h->stream));
-    h->launches += 2;                    // cluster kernel + cooperative grid kernel
+                                h->d_bits, h->d_ctr, seed, round, h->mis_grid, with_grid, note, seq, h->stream));
+    h->launches += with_grid ? 2 : 1;    // cluster kernel (+ cooperative grid kernel)
     return ALLL_OK;
 }
 
@@ -346,7 +361,7 @@ int alll_create(const alll_config *cfg, alll_handle *out)
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaStreamCreate failed"));
     if (cudaMalloc(&s->d_ctr, sizeof(Counters)) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaMalloc(counters) failed"));
     if (cudaMallocHost(&s->h_ctr, sizeof(Counters)) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaMallocHost failed"));
-    if (cudaMallocHost(&s->h_ring, sizeof(Counters) * ROUNDS_IN_FLIGHT) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaMallocHost failed"));
+    if (cudaMallocHost(&s->h_ring, sizeof(RoundNote) * ROUNDS_IN_FLIGHT) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaMallocHost failed"));
     for (auto &ev : s->ev_round)
         if (cudaEventCreate(&ev) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaEventCreate failed"));
     s->ev.resize(2 * MAX_TIMED_ROUNDS + 2);
@@ -526,6 +541,10 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
     // entry, so the device never idles waiting for the host and nothing runs past the terminal sweep.
     int status = ALLL_MAX_ROUNDS;
     uint64_t issued = 0, retired = 0;
+    const unsigned long long seq0 = h->seq;
+    const bool trace = getenv("ALLL_TRACE") != nullptr;
+    uint64_t last_seen_u = h->m;          // |U| of the newest retired round: violated sets shrink, so once it fits one
+                                          // cluster the cooperative grid kernel is no longer enqueued
     cudaEvent_t ev_last = ev_begin;
     if (max_rounds == 0) max_rounds = 1;             // the loop body always runs once (SATInstance.h:260-261)
     while (retired < max_rounds) {
@@ -534,22 +553,46 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
             if (time_this) CK(cudaEventRecord(h->ev[2 * issued], h->stream));
             if (int rc = enqueue_sweep(h)) return rc;
             if (time_this) CK(cudaEventRecord(h->ev[2 * issued + 1], h->stream));
-            if (int rc = enqueue_mis_resample(h, seed, (uint32_t)issued)) return rc;
             const int slot = (int)(issued % ROUNDS_IN_FLIGHT);
-            CK(cudaMemcpyAsync(&h->h_ring[slot], h->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
-            CK(cudaEventRecord(h->ev_round[slot], h->stream));
+            if (int rc = enqueue_mis_resample(h, seed, (uint32_t)issued, last_seen_u > MIS_CLUSTER_MAX_U, &h->h_ring[slot],
+                                              seq0 + issued + 1))
+                return rc;
+            CK(cudaEventRecord(h->ev_round[slot], h->stream));      // timing only: marks the end of this round on the device
             issued++;
         }
         const int slot = (int)(retired % ROUNDS_IN_FLIGHT);
-        CK(cudaEventSynchronize(h->ev_round[slot]));
+        {   // wait for the MIS kernel of round `retired` to announce itself in pinned memory
+            volatile unsigned long long *seq = &h->h_ring[slot].seq;
+            uint32_t spins = 0;
+            while (*seq != seq0 + retired + 1) {
+                if ((++spins & 0x3FFu) == 0) {
+                    const cudaError_t q = cudaStreamQuery(h->stream);
+                    if (q == cudaSuccess && *seq != seq0 + retired + 1)
+                        return fail(h, ALLL_CUDA_ERROR, "round finished without announcing itself");
+                    if (q != cudaSuccess && q != cudaErrorNotReady)
+                        return fail(h, ALLL_CUDA_ERROR, std::string("round loop: ") + cudaGetErrorString(q));
+                }
+            }
+        }
         ev_last = h->ev_round[slot];
+        if (trace && retired < (uint64_t)MAX_TIMED_ROUNDS) {
+            // ALLL_TRACE=1: per-round device times on stderr (sweep kernel | sweep end -> MIS kernels done)
+            float t_sweep = 0.f, t_mis = 0.f;
+            cudaEventSynchronize(h->ev_round[slot]);
+            cudaEventElapsedTime(&t_sweep, h->ev[2 * retired], h->ev[2 * retired + 1]);
+            cudaEventElapsedTime(&t_mis, h->ev[2 * retired + 1], h->ev_round[slot]);
+            fprintf(stderr, "[alll trace] round %llu: |U|=%u |S|=%u sweep=%.1f us mis=%.1f us\n",
+                    (unsigned long long)retired, h->h_ring[slot].n_viol, h->h_ring[slot].n_s, t_sweep * 1e3, t_mis * 1e3);
+        }
         retired++;
-        if (h->h_ring[slot].last_n_viol == 0) { status = ALLL_OK; break; }   // SATInstance.h:285-287
+        last_seen_u = h->h_ring[slot].n_viol;
+        if (last_seen_u == 0) { status = ALLL_OK; break; }                    // SATInstance.h:285-287
     }
     const uint64_t useful_rounds = retired;              // rounds whose sweep actually ran (incl. the terminal one)
+    h->seq = seq0 + issued;
+    CK(cudaStreamSynchronize(h->stream));                 // drain the speculative (no-op) rounds
     float ms = 0.f;
     if (useful_rounds) CK(cudaEventElapsedTime(&ms, ev_begin, ev_last));
-    CK(cudaStreamSynchronize(h->stream));                 // drain the speculative (no-op) rounds
     double sweep_ms = 0.0, between_ms = 0.0;
     const int timed = (int)std::min<uint64_t>(useful_rounds, MAX_TIMED_ROUNDS);
     for (int i = 0; i < timed; i++) {
@@ -638,8 +681,8 @@ int alll_shard_round(alll_handle h, const uint32_t *d_records, const uint64_t *c
     ClauseView cv{};
     cv.planes = h->d_sh_planes; cv.m_pad = cap; cv.k = h->k; cv.orig_id = h->d_sh_ids; cv.id_base = 0;
     CK(launch_mis_resample_args(cv, h->k, h->d_sh_iota, h->d_sh_state, h->d_sh_s, h->d_claim, h->n_vars, h->d_bits,
-                                h->d_ctr, seed, round, h->mis_grid, h->stream));
-    h->launches += 2;
+                                h->d_ctr, seed, round, h->mis_grid, total > MIS_CLUSTER_MAX_U, nullptr, 0ull, h->stream));
+    h->launches += total > MIS_CLUSTER_MAX_U ? 2 : 1;
     if (int rc = fetch_counters(h)) return rc;
     const Counters &c = *h->h_ctr;
     if (n_total) *n_total = total;
@@ -672,6 +715,107 @@ int alll_reset_stats(alll_handle h)
     NEED_INSTANCE();
     CK(launch_reset_counters(h->d_ctr, 1, h->stream)); h->launches++;
     CK(cudaStreamSynchronize(h->stream));
+    return ALLL_OK;
+}
+
+// ---- batched small instances / seed portfolio -------------------------------------------------------------
+
+int alll_batch_upload(alll_handle h, uint32_t n_instances, uint64_t n_vars, uint32_t k, const uint64_t *clause_off,
+                      const uint32_t *lit)
+{
+    if (!h) return ALLL_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    h->has_batch = false;
+    if (n_instances == 0 || !clause_off) return fail(h, ALLL_BAD_ARG, "no instances");
+    if (k < 1 || k > MAX_K) return fail(h, ALLL_BAD_ARG, "k must be in [1, 32]");
+    if (n_vars == 0 || n_vars > (1u << 24)) return fail(h, ALLL_BAD_ARG, "n_vars out of range for the batched path");
+    const uint64_t total = clause_off[n_instances] - clause_off[0];
+    if (total && !lit) return fail(h, ALLL_BAD_ARG, "lit == NULL");
+    std::vector<uint32_t> off(n_instances + 1), mm(n_instances);
+    std::vector<uint64_t> src(n_instances + 1);
+    uint64_t pos = 0;
+    uint32_t m_max = 0;
+    for (uint32_t i = 0; i < n_instances; i++) {
+        if (clause_off[i + 1] < clause_off[i]) return fail(h, ALLL_BAD_ARG, "offsets must be non-decreasing");
+        const uint64_t m = clause_off[i + 1] - clause_off[i];
+        if (m > 0x3FFFFFFFull || pos > 0xF0000000ull) return fail(h, ALLL_BAD_ARG, "batch too large");
+        off[i] = (uint32_t)pos;
+        mm[i] = (uint32_t)m;
+        src[i] = clause_off[i] - clause_off[0];
+        m_max = std::max(m_max, (uint32_t)m);
+        pos = align_up(pos + m, 4);
+    }
+    off[n_instances] = (uint32_t)pos;
+    src[n_instances] = total;
+    const uint64_t m_pad = std::max<uint64_t>(align_up(pos, 4), 4);
+    const uint32_t n_words = (uint32_t)((n_vars + 31) / 32);
+    int max_smem = 0;
+    CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    if (batch_smem_bytes((uint32_t)n_vars, n_words, m_max) + 64 > (size_t)max_smem)
+        return fail(h, ALLL_BAD_ARG, "instance too large for the one-CTA-per-instance path (use alll_upload_* + alll_solve)");
+    POOL(h->d_b_lit, std::max<uint64_t>(total * k, 1) * 4);
+    POOL(h->d_b_planes, m_pad * k * 4);
+    POOL(h->d_b_off, (n_instances + 1) * 4);
+    POOL(h->d_b_m, n_instances * 4);
+    POOL(h->d_b_src_off, (n_instances + 1) * 8);
+    POOL(h->d_tmp_err, 8);
+    if (total) CK(cudaMemcpyAsync(h->d_b_lit, lit + clause_off[0] * k, total * k * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_b_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_b_m, mm.data(), mm.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_b_src_off, src.data(), src.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->d_tmp_err, 0, 8, h->stream));
+    CK(cudaMemsetAsync(h->d_b_planes, 0, m_pad * k * 4, h->stream));
+    CK(launch_batch_transpose(h->d_b_lit, h->d_b_src_off, h->d_b_off, n_instances, k, (uint32_t)n_vars, h->d_b_planes, m_pad,
+                              h->d_tmp_err, h->stream));
+    h->launches++;
+    uint32_t err = 0;
+    CK(cudaMemcpyAsync(&err, h->d_tmp_err, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (err) return fail(h, ALLL_BAD_ARG, "a literal references a variable >= n_vars");
+    h->b_n_inst = n_instances; h->b_n_vars = (uint32_t)n_vars; h->b_n_words = n_words; h->b_k = k; h->b_m_max = m_max;
+    h->b_m_pad = m_pad;
+    h->has_batch = true;
+    return ALLL_OK;
+}
+
+int alll_batch_solve(alll_handle h, uint32_t n_jobs, const uint64_t *seeds, uint64_t max_rounds, int portfolio,
+                     uint8_t *assignments, alll_batch_stats *stats, int32_t *winner, double *device_ms)
+{
+    if (!h) return ALLL_BAD_ARG;
+    if (!h->has_batch) return fail(h, ALLL_NO_INSTANCE, "no batch uploaded");
+    CK(cudaSetDevice(h->device));
+    if (n_jobs == 0 || !seeds || !stats) return fail(h, ALLL_BAD_ARG, "n_jobs / seeds / stats");
+    if (!portfolio && n_jobs != h->b_n_inst) return fail(h, ALLL_BAD_ARG, "n_jobs must equal the number of uploaded instances");
+    static_assert(sizeof(alll_batch_stats) == sizeof(BatchJobStats), "ABI mirror");
+    POOL(h->d_b_seeds, (size_t)n_jobs * 8);
+    POOL(h->d_b_stats, (size_t)n_jobs * sizeof(BatchJobStats));
+    POOL(h->d_b_bits, (size_t)n_jobs * h->b_n_words * 4);
+    POOL(h->d_b_winner, 4);
+    const int minus1 = -1;
+    CK(cudaMemcpyAsync(h->d_b_seeds, seeds, (size_t)n_jobs * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_b_winner, &minus1, 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->d_b_bits, 0, (size_t)n_jobs * h->b_n_words * 4, h->stream));
+    cudaEvent_t e0 = h->ev[0], e1 = h->ev[1];
+    CK(cudaEventRecord(e0, h->stream));
+    CK(launch_batch_solve(h->d_b_planes, h->b_m_pad, h->d_b_off, h->d_b_m, h->b_n_inst, h->b_n_vars, h->b_n_words, h->b_k,
+                          h->b_m_max, h->d_b_seeds, max_rounds, h->d_b_bits, h->d_b_stats, portfolio ? 1 : 0, h->d_b_winner,
+                          n_jobs, h->stream));
+    h->launches++;
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaMemcpyAsync(stats, h->d_b_stats, (size_t)n_jobs * sizeof(BatchJobStats), cudaMemcpyDeviceToHost, h->stream));
+    int w = -1;
+    CK(cudaMemcpyAsync(&w, h->d_b_winner, 4, cudaMemcpyDeviceToHost, h->stream));
+    if (assignments) {
+        const uint64_t total = (uint64_t)n_jobs * h->b_n_vars;
+        POOL(h->d_b_bytes, total);
+        CK(launch_batch_unpack(h->d_b_bits, h->b_n_words, h->b_n_vars, total, h->d_b_bytes, h->stream)); h->launches++;
+        CK(cudaMemcpyAsync(assignments, h->d_b_bytes, total, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (device_ms) *device_ms = ms;
+    if (winner) *winner = w;
     return ALLL_OK;
 }
 

@@ -38,7 +38,8 @@ namespace alll {
 constexpr uint32_t GRID_THREADS = 256;
 constexpr uint32_t CL_THREADS = 1024;
 constexpr uint32_t CL_SIZE = 8;
-constexpr uint32_t CLUSTER_U = CL_THREADS * CL_SIZE;    // violated sets up to this size go to the cluster kernel
+constexpr uint32_t CLUSTER_U = MIS_CLUSTER_MAX_U;        // violated sets up to this size go to the cluster kernel
+static_assert(CLUSTER_U == CL_THREADS * CL_SIZE, "one clause per cluster thread");
 constexpr uint32_t GRID_SMEM_WORDS_PER_THREAD = 48;     // 48 KB per 256-thread CTA: 4 CTAs per SM
 constexpr uint32_t EXTRA = 3;                           // cached per clause besides its literals: priority, id, width
 
@@ -57,6 +58,9 @@ struct MisParams {
     uint32_t round;
     uint32_t kmax;              // widest clause
     uint32_t cache_items;       // clauses per thread whose literals fit the shared-memory cache
+    uint32_t grid_follows;      // cluster kernel only: a grid kernel is enqueued behind it and takes large sets
+    RoundNote *note;            // pinned host memory (may be NULL): where the finished round is announced
+    unsigned long long seq;     // value to publish in note->seq
 };
 
 extern __shared__ uint32_t mis_smem[];
@@ -227,8 +231,18 @@ __device__ void mis_resample_body(const MisParams &p, Barrier &bar, uint32_t fir
 }
 
 // Round bookkeeping by one thread after the last barrier.  n_iterations counts every sweep (SATInstance.h:261).
-__device__ __forceinline__ void finish_round(Counters *c, uint32_t n_u)
+__device__ __forceinline__ void announce(const MisParams &p, unsigned int n_viol, unsigned int n_s)
 {
+    if (!p.note) return;
+    p.note->n_viol = n_viol;
+    p.note->n_s = n_s;
+    __threadfence_system();
+    *(volatile unsigned long long *)&p.note->seq = p.seq;
+}
+
+__device__ __forceinline__ void finish_round(const MisParams &p, uint32_t n_u)
+{
+    Counters *c = p.ctr;
     c->n_iterations += 1;
     const unsigned int n_s = ld_u32(&c->n_s);
     const unsigned long long n_r = __ldcg(&c->n_resampled_round);
@@ -240,6 +254,7 @@ __device__ __forceinline__ void finish_round(Counters *c, uint32_t n_u)
     c->n_viol = 0;                                         // clean slate for the next sweep
     c->n_s = 0;
     c->n_resampled_round = 0;
+    announce(p, n_u, n_s);
 }
 
 // First MIS kernel of a round: owns the terminal case (|U| == 0) and violated sets that fit one cluster.
@@ -254,14 +269,15 @@ __global__ void __cluster_dims__(CL_SIZE, 1, 1) __launch_bounds__(CL_THREADS) mi
             p.ctr->last_n_s = 0;
             p.ctr->last_resampled = 0;
             p.ctr->done = 1;
+            announce(p, 0u, 0u);
         }
         return;
     }
-    if (n_u > CLUSTER_U) return;                  // the grid kernel behind us takes it
+    if (n_u > CLUSTER_U && p.grid_follows) return;  // the grid kernel behind us takes it (else: strided, slower, still exact)
     ClusterBarrier bar;
     mis_resample_body(p, bar, blockIdx.x * CL_THREADS + threadIdx.x, CLUSTER_U, n_u);
     bar.sync();
-    if (blockIdx.x == 0 && threadIdx.x == 0) finish_round(p.ctr, n_u);
+    if (blockIdx.x == 0 && threadIdx.x == 0) finish_round(p, n_u);
 }
 
 // Second MIS kernel of a round (cooperative launch): violated sets too large for one cluster.
@@ -273,7 +289,7 @@ __global__ void __launch_bounds__(GRID_THREADS) mis_grid_kernel(const MisParams 
     GridBarrier bar{cg::this_grid()};
     mis_resample_body(p, bar, blockIdx.x * GRID_THREADS + threadIdx.x, gridDim.x * GRID_THREADS, n_u);
     bar.sync();
-    if (blockIdx.x == 0 && threadIdx.x == 0) finish_round(p.ctr, n_u);
+    if (blockIdx.x == 0 && threadIdx.x == 0) finish_round(p, n_u);
 }
 
 // Per-round scratch reset + (optionally) totals reset.
@@ -328,15 +344,18 @@ cudaError_t mis_configure(int device, uint32_t kmax, uint32_t *grid_out)
     return cudaSuccess;
 }
 
-// Enqueues both MIS kernels of one round (2 launches).
+// Enqueues the MIS kernels of one round: the cluster kernel, and (with_grid) the cooperative grid kernel behind it.
+// Callers that know the violated set is small skip the grid kernel: a cooperative launch is not free even as a no-op.
 cudaError_t launch_mis_resample_args(const ClauseView &cv, uint32_t kmax, const uint32_t *viol, uint8_t *state,
                                      uint32_t *s_slots, unsigned long long *claim, uint64_t n_vars, uint32_t *bits,
-                                     Counters *ctr, uint64_t seed, uint32_t round, uint32_t grid, cudaStream_t s)
+                                     Counters *ctr, uint64_t seed, uint32_t round, uint32_t grid, bool with_grid,
+                                     RoundNote *note, unsigned long long seq, cudaStream_t s)
 {
-    MisParams p{cv, viol, state, s_slots, claim, n_vars, bits, ctr, seed, round, kmax, cluster_cache_items(kmax)};
+    MisParams p{cv, viol, state, s_slots, claim, n_vars, bits, ctr, seed, round, kmax, cluster_cache_items(kmax),
+                with_grid ? 1u : 0u, note, seq};
     mis_cluster_kernel<<<CL_SIZE, CL_THREADS, cluster_smem_bytes(kmax), s>>>(p);
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    if (e != cudaSuccess || !with_grid) return e;
     p.cache_items = grid_cache_items(kmax);
     void *args[] = {(void *)&p};
     return cudaLaunchCooperativeKernel((const void *)mis_grid_kernel, dim3(grid), dim3(GRID_THREADS), args,

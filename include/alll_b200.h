@@ -45,7 +45,8 @@ typedef enum {
     ALLL_CUDA_ERROR = 4,
     ALLL_NCCL_ERROR = 5,
     ALLL_NO_INSTANCE = 6,   /* call needs an uploaded instance */
-    ALLL_CAPACITY = 7       /* caller buffer too small */
+    ALLL_CAPACITY = 7,      /* caller buffer too small */
+    ALLL_PREEMPTED = 8      /* portfolio job stopped: another seed reached a satisfying assignment first */
 } alll_status;
 
 typedef struct alll_solver *alll_handle;
@@ -156,6 +157,30 @@ ALLL_API int alll_shard_round(alll_handle h, const uint32_t *d_records, const ui
 /* Running Statistics totals of the handle (since upload / alll_reset_stats / the start of the last alll_solve). */
 ALLL_API int alll_get_stats(alll_handle h, alll_stats *stats);
 ALLL_API int alll_reset_stats(alll_handle h);
+
+/* ---- batched small instances and seed portfolio (BASELINE config 5) --------------------
+ * Many independent small instances (same n_vars and k, e.g. 8,192 x 5-SAT n=10k): one CTA per instance, the whole
+ * solver state in shared memory, ALL rounds inside one kernel launch.  Each instance follows exactly the round
+ * specification of alll_solve (same result for the same seed).  Portfolio: one instance, many seeds, the first
+ * CTA to satisfy everything claims a device-wide winner word and the others stop.  The reference has no batch
+ * API; this replaces running SATInstance::solve (SATInstance.h:60-66) once per instance / per seed. */
+typedef struct {
+    uint64_t n_iterations;   /* Statistics semantics of SATInstance.h:25-32 */
+    uint64_t n_resamples;
+    uint64_t sum_mis_size;   /* avg_mis_size = sum_mis_size / n_iterations */
+    int32_t  status;         /* ALLL_OK, ALLL_MAX_ROUNDS or ALLL_PREEMPTED */
+    int32_t  reserved;
+} alll_batch_stats;
+
+/* clause_off[n_instances+1] indexes the rows of lit (row-major [total_clauses][k], host memory). */
+ALLL_API int alll_batch_upload(alll_handle h, uint32_t n_instances, uint64_t n_vars, uint32_t k,
+                      const uint64_t *clause_off, const uint32_t *lit);
+/* n_jobs == n_instances (portfolio == 0: job i solves instance i with seeds[i], starting from the Philox
+ * assignment of that seed), or any n_jobs with portfolio != 0 (every job solves instance 0).
+ * assignments (host, [n_jobs][n_vars] bytes, may be NULL): rows of finished jobs; in portfolio mode only the
+ * winner's row is written.  *winner: portfolio winner job or -1.  *device_ms: kernel time from CUDA events. */
+ALLL_API int alll_batch_solve(alll_handle h, uint32_t n_jobs, const uint64_t *seeds, uint64_t max_rounds, int portfolio,
+                     uint8_t *assignments, alll_batch_stats *stats, int32_t *winner, double *device_ms);
 
 /* ---- measurement hooks -------------------------------------------------------------- */
 
