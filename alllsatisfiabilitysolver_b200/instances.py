@@ -87,6 +87,30 @@ def bounded_degree_ksat_torch(n: int, k: int, d: int, seed: int, device="cuda"):
     return (tuples * 2 + signs).contiguous()
 
 
+def bounded_degree_batch_torch(n_inst: int, n: int, k: int, d: int, seed: int, device="cuda"):
+    """``n_inst`` independent bounded-degree instances generated on the device in one go (BASELINE config 5).
+
+    Returns (clause_off int64 [n_inst+1] on the host, lits int32 [total, k] on the device)."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    total = n * d
+    m = total // k
+    perm = torch.rand((n_inst, total), generator=g, device=device).argsort(dim=1)[:, : m * k]
+    tuples = (perm // d).to(torch.int32).reshape(n_inst, m, k)
+    del perm
+    srt, _ = torch.sort(tuples, dim=2)
+    ok = (srt[:, :, 1:] != srt[:, :, :-1]).all(dim=2)              # drop clauses with a repeated variable
+    del srt
+    signs = torch.randint(0, 2, tuples.shape, generator=g, device=device, dtype=torch.int32)
+    lits = (tuples * 2 + signs)[ok].contiguous()                   # boolean mask keeps instance order
+    counts = ok.sum(dim=1).cpu()
+    off = torch.zeros(n_inst + 1, dtype=torch.int64)
+    off[1:] = torch.cumsum(counts, 0)
+    return off, lits
+
+
 def uniform_ksat_torch(n: int, k: int, m: int, seed: int, device="cuda"):
     import torch
 
