@@ -28,6 +28,7 @@ SYMBOLS = [
     "alll_time_sweep", "alll_launch_count", "alll_layout_info",
     "alll_set_id_base", "alll_shard_sweep", "alll_shard_round", "alll_get_stats", "alll_reset_stats",
     "alll_batch_upload", "alll_batch_solve",
+    "alll_p2p_create", "alll_p2p_connect", "alll_solve_p2p",
 ]
 
 
@@ -106,6 +107,9 @@ def load() -> C.CDLL:
     L.alll_shard_round.argtypes = [vp, vp, C.POINTER(u64), u32, u64, u64, u32, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.alll_get_stats.argtypes = [vp, C.POINTER(StatsC)]
     L.alll_reset_stats.argtypes = [vp]
+    L.alll_p2p_create.argtypes = [vp, u32, u32, u64, vp]
+    L.alll_p2p_connect.argtypes = [vp, vp]
+    L.alll_solve_p2p.argtypes = [vp, u64, u64, u64, u32, C.POINTER(StatsC)]
     L.alll_batch_upload.argtypes = [vp, u32, u64, u32, vp, vp]
     L.alll_batch_solve.argtypes = [vp, u32, vp, u64, C.c_int, vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     for name in SYMBOLS:
@@ -228,6 +232,22 @@ class Solver:
         self._check(self.lib.alll_shard_round(self.h, C.c_void_p(d_records_ptr), arr, len(counts), block_cap, seed, rnd,
                                               C.byref(n_t), C.byref(n_s), C.byref(n_r)))
         return int(n_t.value), int(n_s.value), int(n_r.value)
+
+    def p2p_create(self, world: int, rank: int, cap_records: int) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        self._check(self.lib.alll_p2p_create(self.h, world, rank, cap_records, buf))
+        return bytes(buf)
+
+    def p2p_connect(self, handles: list):
+        blob = b"".join(handles)
+        arr = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self._check(self.lib.alll_p2p_connect(self.h, arr))
+
+    def solve_p2p(self, seed: int, m_global: int, epoch: int, max_rounds: int = 1 << 19) -> Stats:
+        st = StatsC()
+        self._check(self.lib.alll_solve_p2p(self.h, seed, max_rounds, m_global, epoch, C.byref(st)), allow=(OK, MAX_ROUNDS))
+        return Stats(st.n_iterations, st.n_resamples, st.avg_mis_size, st.sum_mis_size, st.n_clause_evals,
+                     st.n_luby_steps, st.n_kernel_launches, st.solve_ms, st.sweep_ms, st.status, st.between_sweeps_ms)
 
     def get_stats(self) -> Stats:
         st = StatsC()

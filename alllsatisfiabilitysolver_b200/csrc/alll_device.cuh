@@ -134,7 +134,9 @@ struct Counters {
     // set by the MIS kernel that saw an empty violated set: kernels of rounds the host enqueued speculatively
     // behind it return immediately, so the round loop never has to wait for the host between rounds
     unsigned int done;
-    unsigned int pad;
+    unsigned int cta_done;      // sweep CTAs that have finished (sharded P2P mode: the last one publishes the round)
+    unsigned int p2p_error;     // 1: capacity overflow, 2: a peer did not arrive in time
+    unsigned int handled_tag;   // sharded P2P mode: tag of the last round an MIS kernel has completed
 };
 
 // What the round loop on the host needs to know about a finished round.  Lives in pinned host memory; the MIS
@@ -152,6 +154,26 @@ struct BatchJobStats {
     int status, reserved;
 };
 constexpr int BATCH_PREEMPTED = 8;      // == ALLL_PREEMPTED: portfolio job stopped because another seed finished first
+
+// ---- peer-to-peer exchange of the clause-range sharded mode (one process per GPU, CUDA IPC mappings) ----
+// Every GPU owns one exchange region: a header, then records[2 parities][world][cap][k+1].  In round r the sweep
+// kernel of rank q stores its violated records into slot [r & 1][q] of EVERY GPU's region over NVLink, then
+// publishes count and arrival flag; the MIS kernel of each GPU waits for all flags of the round and works on its
+// own region.  Two parities suffice: a rank cannot start sweep r+2 before every peer has finished MIS r.
+struct P2PHeader {
+    unsigned int flag[2][MAX_SHARDS];    // written by peers: tag of the round whose records are complete
+    unsigned int count[2][MAX_SHARDS];   // written by peers: number of records of that round
+    unsigned int abort;                  // set when a peer overflowed its capacity or a wait timed out
+};
+constexpr uint32_t P2P_HEADER_BYTES = 4096;
+static_assert(sizeof(P2PHeader) <= P2P_HEADER_BYTES, "header must fit its page");
+
+struct P2PLink {                         // device-resident, one per handle
+    uint32_t world, rank, k;
+    uint64_t cap;                        // records per (parity, source rank)
+    P2PHeader *hdr[MAX_SHARDS];          // every GPU's header (own one included), peer-mapped
+    uint32_t *rec[MAX_SHARDS];           // every GPU's record area
+};
 
 struct BucketSeg {
     uint32_t tile_begin;        // first sweep tile of this bucket
@@ -173,6 +195,11 @@ struct SweepParams {
     uint32_t eager;             // tuning: planes streamed eagerly (0 = default EAGER_PLANES)
     uint32_t prefetch_tiles;    // tiles of L2 prefetch distance ahead of the register double buffer (0 = off)
     uint32_t min_resident;      // min over clauses of the number of resident-placed literals (0 when unknown)
+    // sharded P2P mode (p2p == NULL otherwise): records go to every peer instead of the local violated list
+    const P2PLink *p2p;
+    uint32_t p2p_parity, p2p_tag;
+    const uint32_t *orig_id;
+    uint32_t id_base;
 };
 
 } // namespace alll

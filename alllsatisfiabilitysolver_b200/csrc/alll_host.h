@@ -19,7 +19,8 @@ cudaError_t mis_configure(int device, uint32_t kmax, uint32_t *grid_out);
 cudaError_t launch_mis_resample_args(const ClauseView &cv, uint32_t kmax, const uint32_t *viol, uint8_t *state,
                                      uint32_t *s_slots, unsigned long long *claim, uint64_t n_vars, uint32_t *bits,
                                      Counters *ctr, uint64_t seed, uint32_t round, uint32_t grid, bool with_grid,
-                                     RoundNote *note, unsigned long long seq, cudaStream_t s);
+                                     RoundNote *note, unsigned long long seq, const P2PLink *p2p, uint32_t p2p_parity,
+                                     uint32_t p2p_tag, cudaStream_t s);
 cudaError_t launch_reset_counters(Counters *c, int reset_totals, cudaStream_t s);
 cudaError_t launch_map_ids(const uint32_t *slots, const uint32_t *orig_id, uint32_t id_base, uint32_t n, uint32_t *out,
                            cudaStream_t s);

@@ -68,6 +68,14 @@ struct alll_solver {
     // sharded mode: dense copy of the gathered violated records
     uint32_t *d_sh_planes = nullptr, *d_sh_ids = nullptr, *d_sh_iota = nullptr, *d_sh_s = nullptr;
     uint8_t *d_sh_state = nullptr;
+    // sharded P2P mode: our exchange region, the peers' mappings, the device-resident link table
+    uint8_t *d_p2p_region = nullptr;
+    size_t p2p_region_bytes = 0;
+    void *p2p_peer[MAX_SHARDS] = {};
+    P2PLink *d_p2p_link = nullptr;
+    uint32_t p2p_world = 0, p2p_rank = 0;
+    uint64_t p2p_cap = 0;
+    bool p2p_ready = false;
     // batched small instances
     bool has_batch = false;
     uint32_t b_n_inst = 0, b_n_vars = 0, b_n_words = 0, b_k = 0, b_m_max = 0;
@@ -118,6 +126,10 @@ void release_buffers(alll_handle h)
     dfree(h->d_b_planes); dfree(h->d_b_off); dfree(h->d_b_m); dfree(h->d_b_bits); dfree(h->d_b_lit); dfree(h->d_b_src_off);
     dfree(h->d_b_seeds); dfree(h->d_b_stats); dfree(h->d_b_bytes); dfree(h->d_b_winner);
     h->has_batch = false;
+    for (uint32_t q = 0; q < MAX_SHARDS; q++)
+        if (h->p2p_peer[q]) { cudaIpcCloseMemHandle(h->p2p_peer[q]); h->p2p_peer[q] = nullptr; }
+    dfree(h->d_p2p_region); dfree(h->d_p2p_link);
+    h->p2p_ready = false;
     h->caps.clear();
     h->has_instance = false;
 }
@@ -270,14 +282,19 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
 }
 
 // Enqueues one sweep.  Invariant: ctr->n_viol == 0 on entry (kept by the MIS kernel / reset kernel).
-int enqueue_sweep(alll_handle h)
+// p2p_tag != 0: sharded P2P mode -- violated records are stored into every GPU's exchange region.
+int enqueue_sweep(alll_handle h, uint32_t p2p_parity = 0, uint32_t p2p_tag = 0)
 {
     if (h->k) {
-        if (h->n_tiles == 0) return ALLL_OK;
+        if (h->n_tiles == 0 && !p2p_tag) return ALLL_OK;      // (a P2P rank without clauses still has to publish its round)
         SweepParams sp{};
         sp.planes = h->d_planes; sp.m_pad = h->m_pad; sp.bits = h->d_bits; sp.n_words = h->n_words_alloc;
         sp.bucket_words = h->bucket_words; sp.n_buckets = h->n_buckets; sp.n_tiles = h->n_tiles;
         sp.segs = h->d_segs; sp.viol = h->d_viol; sp.ctr = h->d_ctr; sp.k = h->k; sp.min_resident = h->min_resident; sp.eager = (h->flags >> 8) & 0xFFu; sp.prefetch_tiles = prefetch_distance(h->flags);
+        if (p2p_tag) {
+            sp.p2p = h->d_p2p_link; sp.p2p_parity = p2p_parity; sp.p2p_tag = p2p_tag;
+            sp.orig_id = h->use_orig_id ? h->d_orig_id : nullptr; sp.id_base = h->id_base;
+        }
         CK(launch_sweep_planes(sp, h->resident_all, h->sweep_grid, h->stream));
     } else {
         if (h->m == 0) return ALLL_OK;
@@ -292,7 +309,7 @@ int enqueue_mis_resample(alll_handle h, uint64_t seed, uint32_t round, bool with
                          unsigned long long seq = 0)
 {
     CK(launch_mis_resample_args(clause_view(h), h->kmax, h->d_viol, h->d_state, h->d_s, h->d_claim, h->n_vars,
-                                h->d_bits, h->d_ctr, seed, round, h->mis_grid, with_grid, note, seq, h->stream));
+                                h->d_bits, h->d_ctr, seed, round, h->mis_grid, with_grid, note, seq, nullptr, 0u, 0u, h->stream));
     h->launches += with_grid ? 2 : 1;    // cluster kernel (+ cooperative grid kernel)
     return ALLL_OK;
 }
@@ -681,7 +698,7 @@ int alll_shard_round(alll_handle h, const uint32_t *d_records, const uint64_t *c
     ClauseView cv{};
     cv.planes = h->d_sh_planes; cv.m_pad = cap; cv.k = h->k; cv.orig_id = h->d_sh_ids; cv.id_base = 0;
     CK(launch_mis_resample_args(cv, h->k, h->d_sh_iota, h->d_sh_state, h->d_sh_s, h->d_claim, h->n_vars, h->d_bits,
-                                h->d_ctr, seed, round, h->mis_grid, total > MIS_CLUSTER_MAX_U, nullptr, 0ull, h->stream));
+                                h->d_ctr, seed, round, h->mis_grid, total > MIS_CLUSTER_MAX_U, nullptr, 0ull, nullptr, 0u, 0u, h->stream));
     h->launches += total > MIS_CLUSTER_MAX_U ? 2 : 1;
     if (int rc = fetch_counters(h)) return rc;
     const Counters &c = *h->h_ctr;
@@ -716,6 +733,151 @@ int alll_reset_stats(alll_handle h)
     CK(launch_reset_counters(h->d_ctr, 1, h->stream)); h->launches++;
     CK(cudaStreamSynchronize(h->stream));
     return ALLL_OK;
+}
+
+// ---- sharded mode with the exchange fused into the kernels (NVLink P2P stores, CUDA IPC mappings) ---------
+
+int alll_p2p_create(alll_handle h, uint32_t world, uint32_t rank, uint64_t cap_records, uint8_t handle_out[64])
+{
+    NEED_INSTANCE();
+    if (!h->k || h->k > 8) return fail(h, ALLL_BAD_ARG, "P2P sharding needs the fixed-width layout with k <= 8");
+    if (world < 1 || world > MAX_SHARDS || rank >= world || !handle_out) return fail(h, ALLL_BAD_ARG, "bad world / rank");
+    if (cap_records == 0) return fail(h, ALLL_BAD_ARG, "cap_records == 0");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    h->p2p_ready = false;
+    for (uint32_t q = 0; q < MAX_SHARDS; q++)
+        if (h->p2p_peer[q]) { cudaIpcCloseMemHandle(h->p2p_peer[q]); h->p2p_peer[q] = nullptr; }
+    const size_t bytes = P2P_HEADER_BYTES + (size_t)2 * world * cap_records * (h->k + 1) * 4;
+    // IPC-exported memory must be its own allocation and must not move: not pooled
+    if (h->d_p2p_region) { cudaFree(h->d_p2p_region); h->d_p2p_region = nullptr; }
+    CK(cudaMalloc(&h->d_p2p_region, bytes));
+    CK(cudaMemset(h->d_p2p_region, 0, bytes));
+    h->p2p_region_bytes = bytes;
+    h->p2p_world = world; h->p2p_rank = rank; h->p2p_cap = cap_records;
+    cudaIpcMemHandle_t ipc;
+    CK(cudaIpcGetMemHandle(&ipc, h->d_p2p_region));
+    std::memcpy(handle_out, &ipc, 64);
+    return ALLL_OK;
+}
+
+int alll_p2p_connect(alll_handle h, const uint8_t *handles)
+{
+    NEED_INSTANCE();
+    if (!h->d_p2p_region || !handles) return fail(h, ALLL_BAD_ARG, "call alll_p2p_create first");
+    P2PLink link{};
+    link.world = h->p2p_world; link.rank = h->p2p_rank; link.k = h->k; link.cap = h->p2p_cap;
+    for (uint32_t q = 0; q < h->p2p_world; q++) {
+        uint8_t *base = nullptr;
+        if (q == h->p2p_rank) base = h->d_p2p_region;
+        else {
+            cudaIpcMemHandle_t ipc;
+            std::memcpy(&ipc, handles + (size_t)q * 64, 64);
+            void *ptr = nullptr;
+            CK(cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess));
+            h->p2p_peer[q] = ptr;
+            base = static_cast<uint8_t *>(ptr);
+        }
+        link.hdr[q] = reinterpret_cast<P2PHeader *>(base);
+        link.rec[q] = reinterpret_cast<uint32_t *>(base + P2P_HEADER_BYTES);
+    }
+    POOL(h->d_p2p_link, sizeof(P2PLink));
+    CK(cudaMemcpy(h->d_p2p_link, &link, sizeof(P2PLink), cudaMemcpyHostToDevice));
+    const uint64_t total_cap = (uint64_t)h->p2p_world * h->p2p_cap;
+    POOL(h->d_sh_s, total_cap * 4);
+    POOL(h->d_sh_state, total_cap);
+    h->p2p_ready = true;
+    return ALLL_OK;
+}
+
+int alll_solve_p2p(alll_handle h, uint64_t seed, uint64_t max_rounds, uint64_t m_global, uint32_t epoch, alll_stats *stats)
+{
+    NEED_INSTANCE();
+    if (!stats) return fail(h, ALLL_BAD_ARG, "stats == NULL");
+    if (!h->p2p_ready) return fail(h, ALLL_BAD_ARG, "call alll_p2p_create / alll_p2p_connect first");
+    std::memset(stats, 0, sizeof(*stats));
+    const uint64_t launches0 = h->launches;
+    CK(launch_reset_counters(h->d_ctr, 1, h->stream)); h->launches++;
+    cudaEvent_t ev_begin = h->ev[2 * MAX_TIMED_ROUNDS];
+    CK(cudaEventRecord(ev_begin, h->stream));
+    if (max_rounds == 0) max_rounds = 1;
+    max_rounds = std::min<uint64_t>(max_rounds, (1u << 20) - 2);       // the round lives in 20 bits of the tag
+    int status = ALLL_MAX_ROUNDS;
+    uint64_t issued = 0, retired = 0;
+    const unsigned long long seq0 = h->seq;
+    uint64_t last_seen_u = m_global;
+    cudaEvent_t ev_last = ev_begin;
+    ClauseView cv{};                                      // unused by the kernels in P2P mode except k
+    cv.k = h->k;
+    bool failed = false;
+    while (retired < max_rounds && !failed) {
+        while (issued < max_rounds && issued - retired < (uint64_t)ROUNDS_IN_FLIGHT) {
+            const uint32_t parity = (uint32_t)(issued & 1u);
+            const uint32_t tag = ((epoch & 0xFFFu) << 20) | (uint32_t)(issued + 1);
+            const bool time_this = issued < (uint64_t)MAX_TIMED_ROUNDS;
+            if (time_this) CK(cudaEventRecord(h->ev[2 * issued], h->stream));
+            if (int rc = enqueue_sweep(h, parity, tag)) return rc;
+            if (time_this) CK(cudaEventRecord(h->ev[2 * issued + 1], h->stream));
+            const int slot = (int)(issued % ROUNDS_IN_FLIGHT);
+            const bool with_grid = last_seen_u > MIS_CLUSTER_MAX_U;
+            CK(launch_mis_resample_args(cv, h->k, nullptr, h->d_sh_state, h->d_sh_s, h->d_claim, h->n_vars, h->d_bits,
+                                        h->d_ctr, seed, (uint32_t)issued, h->mis_grid, with_grid, &h->h_ring[slot],
+                                        seq0 + issued + 1, h->d_p2p_link, parity, tag, h->stream));
+            h->launches += with_grid ? 2 : 1;
+            CK(cudaEventRecord(h->ev_round[slot], h->stream));
+            issued++;
+        }
+        const int slot = (int)(retired % ROUNDS_IN_FLIGHT);
+        {
+            volatile unsigned long long *seq = &h->h_ring[slot].seq;
+            uint32_t spins = 0;
+            while (*seq != seq0 + retired + 1) {
+                if ((++spins & 0x3FFu) == 0) {
+                    const cudaError_t q = cudaStreamQuery(h->stream);
+                    if (q == cudaSuccess && *seq != seq0 + retired + 1) { failed = true; break; }   // kernels returned on `done` after an error
+                    if (q != cudaSuccess && q != cudaErrorNotReady)
+                        return fail(h, ALLL_CUDA_ERROR, std::string("p2p round loop: ") + cudaGetErrorString(q));
+                }
+            }
+        }
+        if (failed) break;
+        ev_last = h->ev_round[slot];
+        retired++;
+        last_seen_u = h->h_ring[slot].n_viol;
+        if (last_seen_u == 0xFFFFFFFFu) { failed = true; break; }
+        if (last_seen_u == 0) { status = ALLL_OK; break; }
+    }
+    h->seq = seq0 + issued;
+    CK(cudaStreamSynchronize(h->stream));
+    if (int rc = fetch_counters(h)) return rc;
+    const Counters c = *h->h_ctr;
+    CK(launch_reset_counters(h->d_ctr, 0, h->stream)); h->launches++;
+    CK(cudaStreamSynchronize(h->stream));
+    if (failed || c.p2p_error)
+        return fail(h, c.p2p_error == 1 ? ALLL_CAPACITY : ALLL_CUDA_ERROR,
+                    c.p2p_error == 1 ? "P2P exchange region too small for a round's violated records"
+                                     : "P2P exchange: a peer did not publish its round in time");
+    float ms = 0.f;
+    if (retired) CK(cudaEventElapsedTime(&ms, ev_begin, ev_last));
+    double sweep_ms = 0.0, between_ms = 0.0;
+    const int timed = (int)std::min<uint64_t>(retired, MAX_TIMED_ROUNDS);
+    for (int i = 0; i < timed; i++) {
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, h->ev[2 * i], h->ev[2 * i + 1]));
+        sweep_ms += t;
+        if (i + 1 < timed) { CK(cudaEventElapsedTime(&t, h->ev[2 * i + 1], h->ev[2 * i + 2])); between_ms += t; }
+    }
+    stats->n_iterations = c.n_iterations;
+    stats->n_resamples = c.n_resamples;
+    stats->sum_mis_size = c.sum_mis;
+    stats->avg_mis_size = c.n_iterations ? c.sum_mis / c.n_iterations : 0;
+    stats->n_clause_evals = m_global * c.n_iterations;
+    stats->n_luby_steps = c.n_luby_steps;
+    stats->n_kernel_launches = h->launches - launches0;
+    stats->solve_ms = ms;
+    stats->sweep_ms = timed ? sweep_ms * ((double)c.n_iterations / timed) : 0.0;
+    stats->between_sweeps_ms = timed > 1 ? between_ms * ((double)(c.n_iterations - 1) / (timed - 1)) : 0.0;
+    stats->status = status;
+    return status;
 }
 
 // ---- batched small instances / seed portfolio -------------------------------------------------------------

@@ -61,6 +61,9 @@ struct MisParams {
     uint32_t grid_follows;      // cluster kernel only: a grid kernel is enqueued behind it and takes large sets
     RoundNote *note;            // pinned host memory (may be NULL): where the finished round is announced
     unsigned long long seq;     // value to publish in note->seq
+    // sharded P2P mode (NULL otherwise): U is the union of the record blocks all ranks stored into OUR exchange region
+    const P2PLink *p2p;
+    uint32_t p2p_parity, p2p_tag;
 };
 
 extern __shared__ uint32_t mis_smem[];
@@ -81,26 +84,41 @@ struct ClusterBarrier {
 struct Item {
     uint32_t base;      // index of word 0 of this item's cache slot for this thread (stride blockDim.x), or ~0u
     uint32_t slot, k, prio, id;
+    const uint32_t *rec;    // sharded P2P mode: this clause's record {id, literals}; NULL otherwise
 
+    __device__ __forceinline__ uint32_t source_lit(const MisParams &p, uint32_t j) const
+    {
+        return rec ? rec[1 + j] : p.cv.literal(slot, j);
+    }
     __device__ __forceinline__ uint32_t lit(const MisParams &p, uint32_t j) const
     {
-        return base != 0xFFFFFFFFu ? mis_smem[base + j * blockDim.x] : p.cv.literal(slot, j);
+        return base != 0xFFFFFFFFu ? mis_smem[base + j * blockDim.x] : source_lit(p, j);
     }
 };
 
-__device__ __forceinline__ Item open_item(const MisParams &p, uint32_t it, uint32_t i, bool fill)
+// prefix: exclusive prefix sums of the per-rank record counts (sharded P2P mode; unused otherwise)
+__device__ __forceinline__ Item open_item(const MisParams &p, const uint32_t *prefix, uint32_t it, uint32_t i, bool fill)
 {
     Item x;
     const uint32_t slotw = p.kmax + EXTRA;
-    x.slot = p.viol[i];
+    if (p.p2p) {
+        const P2PLink &L = *p.p2p;
+        uint32_t q = 0;
+        while (prefix[q + 1] <= i) ++q;
+        x.rec = L.rec[L.rank] + (((uint64_t)p.p2p_parity * L.world + q) * L.cap + (i - prefix[q])) * (L.k + 1);
+        x.slot = i;
+    } else {
+        x.rec = nullptr;
+        x.slot = p.viol[i];
+    }
     if (it < p.cache_items) {
         x.base = it * slotw * blockDim.x + threadIdx.x;
         if (fill) {
-            x.k = p.cv.width(x.slot);
-            x.id = p.cv.id(x.slot);
+            x.k = x.rec ? p.p2p->k : p.cv.width(x.slot);
+            x.id = x.rec ? x.rec[0] : p.cv.id(x.slot);
             x.prio = clause_priority(p.seed, p.round, x.id);
 #pragma unroll 8
-            for (uint32_t j = 0; j < x.k; j++) mis_smem[x.base + j * blockDim.x] = p.cv.literal(x.slot, j);
+            for (uint32_t j = 0; j < x.k; j++) mis_smem[x.base + j * blockDim.x] = x.source_lit(p, j);
             mis_smem[x.base + (p.kmax + 0) * blockDim.x] = x.prio;
             mis_smem[x.base + (p.kmax + 1) * blockDim.x] = x.id;
             mis_smem[x.base + (p.kmax + 2) * blockDim.x] = x.k;
@@ -111,11 +129,37 @@ __device__ __forceinline__ Item open_item(const MisParams &p, uint32_t it, uint3
         }
     } else {
         x.base = 0xFFFFFFFFu;
-        x.k = p.cv.width(x.slot);
-        x.id = p.cv.id(x.slot);
+        x.k = x.rec ? p.p2p->k : p.cv.width(x.slot);
+        x.id = x.rec ? x.rec[0] : p.cv.id(x.slot);
         x.prio = clause_priority(p.seed, p.round, x.id);
     }
     return x;
+}
+
+// Sharded P2P mode: wait until every rank's sweep of this round has published its records in OUR region, then
+// build the prefix sums of the counts.  Returns the total; 0xFFFFFFFF on abort / timeout.  Whole CTA calls it.
+__device__ __forceinline__ uint32_t p2p_wait(const MisParams &p, uint32_t *s_prefix)
+{
+    const P2PLink &L = *p.p2p;
+    if (threadIdx.x == 0) {
+        P2PHeader *me = L.hdr[L.rank];
+        const long long t_start = clock64();
+        bool bad = false;
+        for (uint32_t q = 0; q < L.world && !bad; q++) {
+            while (*(volatile unsigned int *)&me->flag[p.p2p_parity][q] != p.p2p_tag) {
+                if (*(volatile unsigned int *)&me->abort || clock64() - t_start > 6000000000ll) { bad = true; break; }
+            }
+        }
+        __threadfence_system();                       // acquire: the records behind the flags are now visible
+        uint32_t run = 0;
+        for (uint32_t q = 0; q < L.world; q++) {
+            s_prefix[q] = run;
+            run += *(volatile unsigned int *)&me->count[p.p2p_parity][q];
+        }
+        s_prefix[L.world] = bad ? 0xFFFFFFFFu : run;
+    }
+    __syncthreads();
+    return s_prefix[L.world];
 }
 
 // Threads `first`, `first + stride`, ... of the participating group own the same U entries in every phase.
@@ -126,7 +170,8 @@ __device__ __forceinline__ Item open_item(const MisParams &p, uint32_t it, uint3
 // winner merely claims once more in vain (its TAKEN variable can never read back its key) and drops out one step
 // later; the set of winners is unchanged: a clause wins only when every neighbour with a smaller key has dropped.
 template <class Barrier>
-__device__ void mis_resample_body(const MisParams &p, Barrier &bar, uint32_t first, uint32_t stride, uint32_t n_u)
+__device__ void mis_resample_body(const MisParams &p, Barrier &bar, const uint32_t *prefix, uint32_t first, uint32_t stride,
+                                  uint32_t n_u)
 {
     __shared__ unsigned int s_live;
     unsigned long long *const claim0 = p.claim;
@@ -136,7 +181,7 @@ __device__ void mis_resample_body(const MisParams &p, Barrier &bar, uint32_t fir
         uint32_t it = 0;
         for (uint32_t i = first; i < n_u; i += stride, ++it) {
             p.state[i] = UNDECIDED;
-            const Item x = open_item(p, it, i, true);
+            const Item x = open_item(p, prefix, it, i, true);
             const unsigned long long key = claim_key(0, x.prio, x.id);
 #pragma unroll 8
             for (uint32_t j = 0; j < x.k; j++) atomicMin(&claim0[x.lit(p, j) >> 1], key);
@@ -155,7 +200,7 @@ __device__ void mis_resample_body(const MisParams &p, Barrier &bar, uint32_t fir
             uint32_t it = 0;
             for (uint32_t i = first; i < n_u; i += stride, ++it) {
                 if (p.state[i] != UNDECIDED) continue;
-                const Item x = open_item(p, it, i, false);
+                const Item x = open_item(p, prefix, it, i, false);
                 for (uint32_t j = 0; j < x.k; j++) {
                     const uint32_t v = x.lit(p, j) >> 1;
                     if (ld_claim(&nxt[v]) != CLAIM_TAKEN) nxt[v] = CLAIM_FREE;
@@ -168,7 +213,7 @@ __device__ void mis_resample_body(const MisParams &p, Barrier &bar, uint32_t fir
         uint32_t live = 0, it = 0;
         for (uint32_t i = first; i < n_u; i += stride, ++it) {
             if (p.state[i] != UNDECIDED) continue;
-            const Item x = open_item(p, it, i, false);
+            const Item x = open_item(p, prefix, it, i, false);
             const unsigned long long key = claim_key(step, x.prio, x.id);
             bool win = true, taken = false;
 #pragma unroll 8
@@ -209,7 +254,7 @@ __device__ void mis_resample_body(const MisParams &p, Barrier &bar, uint32_t fir
     unsigned long long resampled = 0;
     uint32_t it = 0;
     for (uint32_t i = first; i < n_u; i += stride, ++it) {
-        const Item x = open_item(p, it, i, false);
+        const Item x = open_item(p, prefix, it, i, false);
         const bool in_s = p.state[i] == IN_SET;
 #pragma unroll 8
         for (uint32_t j = 0; j < x.k; j++) {
@@ -254,14 +299,25 @@ __device__ __forceinline__ void finish_round(const MisParams &p, uint32_t n_u)
     c->n_viol = 0;                                         // clean slate for the next sweep
     c->n_s = 0;
     c->n_resampled_round = 0;
+    c->handled_tag = p.p2p_tag;
     announce(p, n_u, n_s);
 }
 
 // First MIS kernel of a round: owns the terminal case (|U| == 0) and violated sets that fit one cluster.
 __global__ void __cluster_dims__(CL_SIZE, 1, 1) __launch_bounds__(CL_THREADS) mis_cluster_kernel(const MisParams p)
 {
+    __shared__ uint32_t s_prefix[MAX_SHARDS + 1];
     if (ld_u32(&p.ctr->done)) return;             // speculative round behind the terminal one
-    const uint32_t n_u = ld_u32(&p.ctr->n_viol);  // written by the sweep kernel that ran before us
+    // |U|: left by the sweep kernel that ran before us, or (sharded P2P mode) the sum over all ranks' record blocks
+    const uint32_t n_u = p.p2p ? p2p_wait(p, s_prefix) : ld_u32(&p.ctr->n_viol);
+    if (n_u == 0xFFFFFFFFu) {                     // a peer overflowed or never arrived: stop the solve
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            p.ctr->p2p_error = p.ctr->p2p_error ? p.ctr->p2p_error : 2;
+            p.ctr->done = 1;
+            announce(p, 0xFFFFFFFFu, 0u);
+        }
+        return;
+    }
     if (n_u == 0) {
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             p.ctr->n_iterations += 1;             // the terminal all-satisfied sweep counts (SATInstance.h:261,285-287)
@@ -269,13 +325,15 @@ __global__ void __cluster_dims__(CL_SIZE, 1, 1) __launch_bounds__(CL_THREADS) mi
             p.ctr->last_n_s = 0;
             p.ctr->last_resampled = 0;
             p.ctr->done = 1;
+            p.ctr->n_viol = 0;
+            p.ctr->handled_tag = p.p2p_tag;
             announce(p, 0u, 0u);
         }
         return;
     }
     if (n_u > CLUSTER_U && p.grid_follows) return;  // the grid kernel behind us takes it (else: strided, slower, still exact)
     ClusterBarrier bar;
-    mis_resample_body(p, bar, blockIdx.x * CL_THREADS + threadIdx.x, CLUSTER_U, n_u);
+    mis_resample_body(p, bar, s_prefix, blockIdx.x * CL_THREADS + threadIdx.x, CLUSTER_U, n_u);
     bar.sync();
     if (blockIdx.x == 0 && threadIdx.x == 0) finish_round(p, n_u);
 }
@@ -283,11 +341,13 @@ __global__ void __cluster_dims__(CL_SIZE, 1, 1) __launch_bounds__(CL_THREADS) mi
 // Second MIS kernel of a round (cooperative launch): violated sets too large for one cluster.
 __global__ void __launch_bounds__(GRID_THREADS) mis_grid_kernel(const MisParams p)
 {
+    __shared__ uint32_t s_prefix[MAX_SHARDS + 1];
     if (ld_u32(&p.ctr->done)) return;
-    const uint32_t n_u = ld_u32(&p.ctr->n_viol);  // 0 when the cluster kernel already handled this round
-    if (n_u <= CLUSTER_U) return;
+    if (p.p2p && ld_u32(&p.ctr->handled_tag) == p.p2p_tag) return;     // the cluster kernel already did this round
+    const uint32_t n_u = p.p2p ? p2p_wait(p, s_prefix) : ld_u32(&p.ctr->n_viol);  // 0 when the cluster kernel handled it
+    if (n_u <= CLUSTER_U || n_u == 0xFFFFFFFFu) return;
     GridBarrier bar{cg::this_grid()};
-    mis_resample_body(p, bar, blockIdx.x * GRID_THREADS + threadIdx.x, gridDim.x * GRID_THREADS, n_u);
+    mis_resample_body(p, bar, s_prefix, blockIdx.x * GRID_THREADS + threadIdx.x, gridDim.x * GRID_THREADS, n_u);
     bar.sync();
     if (blockIdx.x == 0 && threadIdx.x == 0) finish_round(p, n_u);
 }
@@ -302,6 +362,8 @@ __global__ void reset_counters_kernel(Counters *c, int reset_totals)
     c->last_n_s = 0;
     c->last_resampled = 0;
     c->done = 0;
+    c->cta_done = 0;
+    c->p2p_error = 0;
     if (reset_totals) {
         c->n_iterations = 0;
         c->sum_mis = 0;
@@ -349,10 +411,11 @@ cudaError_t mis_configure(int device, uint32_t kmax, uint32_t *grid_out)
 cudaError_t launch_mis_resample_args(const ClauseView &cv, uint32_t kmax, const uint32_t *viol, uint8_t *state,
                                      uint32_t *s_slots, unsigned long long *claim, uint64_t n_vars, uint32_t *bits,
                                      Counters *ctr, uint64_t seed, uint32_t round, uint32_t grid, bool with_grid,
-                                     RoundNote *note, unsigned long long seq, cudaStream_t s)
+                                     RoundNote *note, unsigned long long seq, const P2PLink *p2p, uint32_t p2p_parity,
+                                     uint32_t p2p_tag, cudaStream_t s)
 {
     MisParams p{cv, viol, state, s_slots, claim, n_vars, bits, ctr, seed, round, kmax, cluster_cache_items(kmax),
-                with_grid ? 1u : 0u, note, seq};
+                with_grid ? 1u : 0u, note, seq, p2p, p2p_parity, p2p_tag};
     mis_cluster_kernel<<<CL_SIZE, CL_THREADS, cluster_smem_bytes(kmax), s>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || !with_grid) return e;

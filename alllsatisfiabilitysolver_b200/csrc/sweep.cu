@@ -35,6 +35,7 @@ struct WarpCompactor {
     Counters *ctr;
     uint32_t count;      // warp-uniform
     uint32_t lane;
+    const SweepParams *sp;   // non-NULL with sp->p2p set: sharded P2P mode
 
     __device__ __forceinline__ void flush()
     {
@@ -42,7 +43,27 @@ struct WarpCompactor {
         unsigned int g = 0;
         if (lane == 0) g = atomicAdd(&ctr->n_viol, count);
         g = __shfl_sync(0xffffffffu, g, 0);
-        for (uint32_t i = lane; i < count; i += 32) viol[g + i] = g_smem[wbuf + i];
+        if (sp != nullptr && sp->p2p != nullptr) {
+            // fused compute + collective: the violated clauses go straight into every GPU's receive slot for this
+            // rank and round (NVLink P2P stores), as records {global id, k literals}
+            const P2PLink &L = *sp->p2p;
+            if ((uint64_t)g + count > L.cap) {
+                if (lane == 0) { ctr->p2p_error = 1; for (uint32_t q = 0; q < L.world; q++) L.hdr[q]->abort = 1; }
+            } else {
+                const uint32_t w = L.k + 1;
+                const uint64_t base = (((uint64_t)sp->p2p_parity * L.world + L.rank) * L.cap + g) * w;
+                for (uint32_t i = lane; i < count; i += 32) {
+                    const uint32_t slot = g_smem[wbuf + i];
+                    for (uint32_t j = 0; j < w; j++) {
+                        const uint32_t word = j == 0 ? (sp->orig_id ? sp->orig_id[slot] : slot) + sp->id_base
+                                                     : sp->planes[(uint64_t)(j - 1) * sp->m_pad + slot];
+                        for (uint32_t q = 0; q < L.world; q++) L.rec[q][base + (uint64_t)i * w + j] = word;
+                    }
+                }
+            }
+        } else {
+            for (uint32_t i = lane; i < count; i += 32) viol[g + i] = g_smem[wbuf + i];
+        }
         __syncwarp();
         count = 0;
     }
@@ -74,6 +95,25 @@ struct WarpCompactor {
         }
     }
 };
+
+// Sharded P2P mode, end of the sweep kernel: every CTA orders its record stores before its ticket; the CTA that
+// draws the last ticket publishes this rank's count and arrival flag on every GPU.
+__device__ __forceinline__ void p2p_publish(const SweepParams &p)
+{
+    if (p.p2p == nullptr) return;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    __threadfence_system();
+    const unsigned int t = atomicAdd(&p.ctr->cta_done, 1u);
+    if (t != gridDim.x - 1) return;
+    p.ctr->cta_done = 0;                                   // ready for the next launch (stream-ordered)
+    __threadfence_system();
+    const P2PLink &L = *p.p2p;
+    const unsigned int total = __ldcg(&p.ctr->n_viol);
+    for (uint32_t q = 0; q < L.world; q++) L.hdr[q]->count[p.p2p_parity][L.rank] = total;
+    __threadfence_system();
+    for (uint32_t q = 0; q < L.world; q++) *(volatile unsigned int *)&L.hdr[q]->flag[p.p2p_parity][L.rank] = p.p2p_tag;
+}
 
 // true iff literal l is TRUE under the assignment
 template <bool RESIDENT_ALL>
@@ -297,12 +337,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const Sw
     if (__ldcg(&p.ctr->done)) return;         // speculatively enqueued behind the terminal round
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = threadIdx.x >> 5;
-    WarpCompactor out{p.bucket_words + warp * WBUF, p.viol, p.ctr, 0u, lane};
+    WarpCompactor out{p.bucket_words + warp * WBUF, p.viol, p.ctr, 0u, lane, &p};
     SurvivorQueue<K, E, RESIDENT_ALL> parked{p.bucket_words + (SWEEP_THREADS / 32) * WBUF + warp * QBUF, 0u, lane};
 
     const uint32_t t0 = (uint32_t)(((uint64_t)blockIdx.x * p.n_tiles) / gridDim.x);
     const uint32_t t1 = (uint32_t)(((uint64_t)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
-    if (t0 >= t1) return;
+    if (t0 >= t1) { p2p_publish(p); return; }
 
     TileCursor cur;
     cur.init(p, t0);
@@ -361,6 +401,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const Sw
     }
     if constexpr (E < K) parked.drain(0u, out, p, cur.b * bucket_vars, bucket_vars);
     if (out.count) out.flush();
+    p2p_publish(p);
 }
 
 // Run-time clause width (k > 8): planes are loaded lazily level by level; no prefetch.
@@ -369,7 +410,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_generic_kernel(
 {
     if (__ldcg(&p.ctr->done)) return;
     const uint32_t lane = threadIdx.x & 31u;
-    WarpCompactor comp{p.bucket_words + (threadIdx.x >> 5) * WBUF, p.viol, p.ctr, 0u, lane};
+    WarpCompactor comp{p.bucket_words + (threadIdx.x >> 5) * WBUF, p.viol, p.ctr, 0u, lane, nullptr};
 
     const uint32_t t0 = (uint32_t)(((uint64_t)blockIdx.x * p.n_tiles) / gridDim.x);
     const uint32_t t1 = (uint32_t)(((uint64_t)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
@@ -406,7 +447,7 @@ __global__ void __launch_bounds__(256) sweep_csr_kernel(const uint64_t *__restri
 {
     if (__ldcg(&ctr->done)) return;
     const uint32_t lane = threadIdx.x & 31u;                       // launched with 8 * WBUF words of dynamic smem
-    WarpCompactor comp{(threadIdx.x >> 5) * WBUF, viol, ctr, 0u, lane};
+    WarpCompactor comp{(threadIdx.x >> 5) * WBUF, viol, ctr, 0u, lane, nullptr};
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t m_round = (m + 31) / 32 * 32;
     for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < m_round; c += stride) {

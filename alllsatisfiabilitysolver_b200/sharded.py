@@ -182,3 +182,61 @@ class ShardedSolver:
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
             ms = float(t.item())
         return ShardedStats(n_iter, n_res, sum_mis // n_iter, sum_mis, self.m_global * n_iter, status, ms, trace_u, trace_s)
+
+
+class P2PShardedSolver:
+    """Sharded solve with the exchange fused into the kernels (NVLink P2P stores through CUDA IPC mappings).
+
+    The round loop runs inside ``alll_solve_p2p`` with no NCCL call and no host round trip per round;
+    ``torch.distributed`` is only used once to exchange the 64-byte IPC handles and as a barrier between solves.
+    Needs one process per GPU on one node (peer access between all GPUs)."""
+
+    def __init__(self, device: int, rank: int, world: int, group=None):
+        from . import capi
+
+        self.capi = capi
+        self.solver = capi.Solver(device=device)
+        self.device = torch.device("cuda", device)
+        self.rank, self.world, self.group = rank, world, group
+        self.epoch = 0
+        self.m_global = 0
+
+    def upload_range(self, n_vars: int, lits_local, m_global: int, id_base: int, cap_records: int | None = None):
+        if isinstance(lits_local, torch.Tensor):
+            m, k = lits_local.shape
+            self.solver.upload_fixedk_device(n_vars, int(m), int(k), lits_local.data_ptr())
+        else:
+            m, k = lits_local.shape
+            self.solver.upload_fixedk(n_vars, lits_local)
+        self.solver.set_id_base(id_base)
+        self.m_global = int(m_global)
+        if cap_records is None:                      # a quarter of the widest clause range, with some headroom
+            cap_records = (self.m_global // self.world) // 4 + 8192
+        mine = self.solver.p2p_create(self.world, self.rank, int(cap_records))
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mine, group=self.group)
+        else:
+            handles = [mine]
+        self.solver.p2p_connect(handles)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def randomize(self, seed: int):
+        self.solver.randomize(seed)
+
+    def get_assignment(self):
+        return self.solver.get_assignment()
+
+    def solve(self, seed: int, max_rounds: int = 1 << 19):
+        if self.world > 1:
+            dist.barrier(group=self.group)          # nobody may still be reading the previous solve's rounds
+        self.epoch += 1
+        st = self.solver.solve_p2p(seed, self.m_global, self.epoch, max_rounds)
+        ms = st.solve_ms
+        if self.world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            ms = float(t.item())
+        return ShardedStats(st.n_iterations, st.n_resamples, st.avg_mis_size, st.sum_mis_size, st.n_clause_evals,
+                            st.status, ms, [], [])

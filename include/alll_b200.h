@@ -158,6 +158,20 @@ ALLL_API int alll_shard_round(alll_handle h, const uint32_t *d_records, const ui
 ALLL_API int alll_get_stats(alll_handle h, alll_stats *stats);
 ALLL_API int alll_reset_stats(alll_handle h);
 
+/* Sharded mode with the exchange fused into the kernels: the sweep stores its violated records straight into every
+ * GPU's exchange region over NVLink (CUDA IPC mappings, one process per GPU) and publishes a per-round arrival
+ * flag; the MIS kernel waits on the flags.  No NCCL call and no host round trip inside the round loop.
+ *   1. every rank: alll_upload_fixedk* (its clause range), alll_set_id_base, alll_p2p_create -> 64-byte handle;
+ *   2. exchange the handles (any host mechanism), every rank: alll_p2p_connect(all handles, rank order);
+ *   3. every rank: same initial assignment (alll_randomize with one seed), then alll_solve_p2p with the same
+ *      seed / max_rounds / epoch.  Ranks must not start a solve before all ranks have returned from the previous
+ *      one (a host barrier between solves); epoch distinguishes the solves (same value on all ranks).
+ * cap_records: records one rank may publish per round (ALLL_CAPACITY if exceeded). */
+ALLL_API int alll_p2p_create(alll_handle h, uint32_t world, uint32_t rank, uint64_t cap_records, uint8_t handle_out[64]);
+ALLL_API int alll_p2p_connect(alll_handle h, const uint8_t *handles);
+ALLL_API int alll_solve_p2p(alll_handle h, uint64_t seed, uint64_t max_rounds, uint64_t m_global, uint32_t epoch,
+                   alll_stats *stats);
+
 /* ---- batched small instances and seed portfolio (BASELINE config 5) --------------------
  * Many independent small instances (same n_vars and k, e.g. 8,192 x 5-SAT n=10k): one CTA per instance, the whole
  * solver state in shared memory, ALL rounds inside one kernel launch.  Each instance follows exactly the round

@@ -20,13 +20,14 @@ import torch.distributed as dist  # noqa: E402
 
 from alllsatisfiabilitysolver_b200 import capi  # noqa: E402
 from alllsatisfiabilitysolver_b200.instances import CONFIGS, bounded_degree_ksat_torch, uniform_ksat_torch  # noqa: E402
-from alllsatisfiabilitysolver_b200.sharded import CudaShardBackend, ShardedSolver, partition  # noqa: E402
+from alllsatisfiabilitysolver_b200.sharded import CudaShardBackend, P2PShardedSolver, ShardedSolver, partition  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="cfg4")
 ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--solves", type=int, default=3)
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--p2p", action="store_true", help="exchange fused into the kernels (NVLink P2P) instead of NCCL all-gather")
 a = ap.parse_args()
 
 rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -39,12 +40,17 @@ lits = (bounded_degree_ksat_torch(n, cfg["k"], cfg["d"], 0xA115) if cfg["kind"] 
         else uniform_ksat_torch(n, cfg["k"], int(cfg["m"] * a.scale), 0xA115))
 m, k = int(lits.shape[0]), int(lits.shape[1])
 lo, hi = partition(m, world)[rank]
-be = CudaShardBackend(local)
-ss = ShardedSolver(be, rank, world)
+if a.p2p:
+    ss = P2PShardedSolver(local, rank, world)
+    be = ss
+else:
+    be = CudaShardBackend(local)
+    ss = ShardedSolver(be, rank, world)
 ss.upload_range(n, lits[lo:hi].contiguous(), m, lo)
-out = dict(world=world, n=n, m=m, k=k, solves=[])
+out = dict(world=world, n=n, m=m, k=k, mode="p2p" if a.p2p else "nccl", solves=[])
 for i in range(a.solves):
-    be.solver.reset_stats()
+    if not a.p2p:
+        be.solver.reset_stats()
     be.randomize(100 + i)
     st = ss.solve(100 + i)
     out["solves"].append(dict(ms=st.solve_ms, iters=st.n_iterations, resamples=st.n_resamples, status=st.status,
