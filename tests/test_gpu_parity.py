@@ -249,3 +249,57 @@ def test_cfg4_shape_bucketed_full_path(capi, oracle):
         so = oracle.solve(n, off, flat, v, 11)
         assert (st.n_iterations, st.n_resamples, st.sum_mis_size) == (so.n_iterations, so.n_resamples, so.sum_mis_size)
         assert np.array_equal(s.get_assignment(), v) and oracle.verify(off, flat, v)
+
+
+def test_cfg4_full_size_violated_set_and_verified_solution(capi, oracle):
+    """BASELINE config 4 at FULL size (8-SAT, n=10M, m~40M, 7 buckets): the violated set of a random assignment is
+    bit-exact vs the oracle, and the solve ends in an assignment the independent CPU checker accepts."""
+    import torch
+
+    from alllsatisfiabilitysolver_b200.instances import bounded_degree_ksat_torch
+
+    n, k = 10_000_000, 8
+    lits_t = bounded_degree_ksat_torch(n, k, 32, 0xA115)
+    m = int(lits_t.shape[0])
+    flat = lits_t.cpu().numpy().view(np.uint32).reshape(-1)
+    off = np.arange(m + 1, dtype=np.uint64) * np.uint64(k)
+    with capi.Solver() as s:
+        s.upload_fixedk_device(n, m, k, lits_t.data_ptr())
+        del lits_t
+        torch.cuda.empty_cache()
+        info = s.layout_info()
+        assert info["n_buckets"] == 7 and info["m"] == m
+        s.randomize(77)
+        v0 = oracle.randomize(n, 77)
+        assert np.array_equal(s.get_assignment(), v0)
+        cnt, ids = s.eval()
+        assert np.array_equal(np.sort(ids), oracle.sweep(off, flat, v0))
+        st = s.solve(77)
+        assert st.status == 0 and s.verify()
+        v = s.get_assignment()
+        assert oracle.verify(off, flat, v)
+        # size-independent property: only variables of resampled clauses may differ from the start, and the
+        # number of sweeps is in the range the reference shows for LLL-like sparse instances (SURVEY section 6)
+        assert 5 <= st.n_iterations <= 40 and st.n_resamples % k == 0
+        assert st.n_clause_evals == m * st.n_iterations
+
+
+def test_cfg3_beyond_lll_round_cap(capi, oracle):
+    """BASELINE config 3 shape (uniform 3-SAT, ratio 3.0) does not converge under whole-clause resampling
+    (SURVEY section 7 hard part 3): the round cap must end the solve with MAX_ROUNDS and oracle-identical counters."""
+    from alllsatisfiabilitysolver_b200.instances import uniform_ksat
+
+    n, m = 20_000, 60_000
+    lits = uniform_ksat(n, 3, m, seed=0xA114)
+    off = np.arange(m + 1, dtype=np.uint64) * np.uint64(3)
+    with capi.Solver() as s:
+        s.upload_fixedk(n, lits)
+        s.randomize(1)
+        st = s.solve(1, max_rounds=60)
+        v = oracle.randomize(n, 1)
+        so = oracle.solve(n, off, lits.reshape(-1), v, 1, max_rounds=60)
+        assert st.status == capi.MAX_ROUNDS == so.status
+        assert (st.n_iterations, st.n_resamples, st.sum_mis_size) == (so.n_iterations, so.n_resamples, so.sum_mis_size)
+        assert np.array_equal(s.get_assignment(), v)
+        cnt, _ = s.eval(want_ids=False)
+        assert cnt == len(oracle.sweep(off, lits.reshape(-1), v)) > 0
