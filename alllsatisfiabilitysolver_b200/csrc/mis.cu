@@ -25,7 +25,8 @@
 // Two kernels are enqueued per round and decide on the device which one acts (the host does not know
 // |U|: rounds are enqueued speculatively, see capi.cu):
 //   mis_cluster_kernel : |U| <= 8192 -- one thread-block cluster of 8 x 1024 threads, one clause per
-//                        thread, phases separated by the hardware cluster barrier;
+//                        thread, phases separated by the hardware cluster barrier; |U| <= 512 is done by
+//                        CTA 0 alone with the claims in a shared-memory hash table (mis_small_body);
 //   mis_grid_kernel    : larger |U| -- cooperative launch, phases separated by grid-wide barriers.
 #include <cooperative_groups.h>
 
@@ -42,6 +43,9 @@ constexpr uint32_t CLUSTER_U = MIS_CLUSTER_MAX_U;        // violated sets up to 
 static_assert(CLUSTER_U == CL_THREADS * CL_SIZE, "one clause per cluster thread");
 constexpr uint32_t GRID_SMEM_WORDS_PER_THREAD = 48;     // 48 KB per 256-thread CTA: 4 CTAs per SM
 constexpr uint32_t EXTRA = 3;                           // cached per clause besides its literals: priority, id, width
+constexpr uint32_t SMALL_U = 512;                       // violated sets up to this size: one CTA, claims in a shared-memory hash table
+constexpr uint32_t HSLOTS = 8192;                       // hash slots (power of two); load factor <= 0.5 => SMALL path needs |U| * k <= 4096
+constexpr uint32_t H_EMPTY = 0xFFFFFFFFu, C_FREE = 0xFFFFFFFFu, C_TAKEN = 0u;
 
 enum : uint8_t { UNDECIDED = 0, IN_SET = 1, DROPPED = 2 };
 
@@ -117,8 +121,16 @@ __device__ __forceinline__ Item open_item(const MisParams &p, const uint32_t *pr
             x.k = x.rec ? p.p2p->k : p.cv.width(x.slot);
             x.id = x.rec ? x.rec[0] : p.cv.id(x.slot);
             x.prio = clause_priority(p.seed, p.round, x.id);
-#pragma unroll 8
-            for (uint32_t j = 0; j < x.k; j++) mis_smem[x.base + j * blockDim.x] = x.source_lit(p, j);
+            // the literals sit in k different planes (k DRAM sectors): issue 8 loads before the first store,
+            // otherwise every shared-memory store waits for its own load and the k latencies add up
+            for (uint32_t j0 = 0; j0 < x.k; j0 += 8) {
+                uint32_t tmp[8];
+#pragma unroll
+                for (uint32_t u = 0; u < 8; u++) tmp[u] = (j0 + u < x.k) ? x.source_lit(p, j0 + u) : 0u;
+#pragma unroll
+                for (uint32_t u = 0; u < 8; u++)
+                    if (j0 + u < x.k) mis_smem[x.base + (j0 + u) * blockDim.x] = tmp[u];
+            }
             mis_smem[x.base + (p.kmax + 0) * blockDim.x] = x.prio;
             mis_smem[x.base + (p.kmax + 1) * blockDim.x] = x.id;
             mis_smem[x.base + (p.kmax + 2) * blockDim.x] = x.k;
@@ -275,6 +287,109 @@ __device__ void mis_resample_body(const MisParams &p, Barrier &bar, const uint32
     if (first == 0) atomicAdd(&p.ctr->n_luby_steps, (unsigned long long)step);
 }
 
+// ---- small violated sets: the whole independent-set computation in ONE CTA's shared memory ---------------------
+// (|U| <= SMALL_U and |U| * kmax <= HSLOTS / 2).  No global claim traffic, no memory fences between steps: a Luby
+// step is two __syncthreads().  Exactly the same set as the large paths: the 64-bit (priority, id) keys are replaced
+// by their ranks within U (ids are unique, so ranks are a strict order), claims are 32-bit (step tag | rank) words in
+// an open-addressing table keyed by variable.
+__device__ __forceinline__ uint32_t h_find(const uint32_t *hvar, uint32_t v)
+{
+    uint32_t s = (v * 2654435761u) & (HSLOTS - 1);
+    while (hvar[s] != v) s = (s + 1) & (HSLOTS - 1);
+    return s;
+}
+
+__device__ void mis_small_body(const MisParams &p, const uint32_t *prefix, uint32_t n_u)
+{
+    uint32_t *hvar = mis_smem + (size_t)CL_THREADS * (p.kmax + EXTRA);
+    uint32_t *hclaim = hvar + HSLOTS;
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(hclaim + HSLOTS);     // [SMALL_U]
+    __shared__ unsigned int s_cnt;
+    __shared__ unsigned long long s_sum;
+    const uint32_t t = threadIdx.x;
+    const bool mine = t < n_u;
+
+    for (uint32_t i = t; i < HSLOTS; i += CL_THREADS) { hvar[i] = H_EMPTY; hclaim[i] = C_FREE; }
+    if (t == 0) { s_cnt = 0; s_sum = 0; }
+    Item x{};
+    if (mine) {
+        x = open_item(p, prefix, 0, t, true);
+        keys[t] = ((unsigned long long)x.prio << 32) | x.id;
+    }
+    __syncthreads();
+    uint32_t rank = 0;
+    if (mine) {
+        const unsigned long long k0 = keys[t];
+        for (uint32_t j = 0; j < n_u; j++) rank += keys[j] < k0;
+        for (uint32_t j = 0; j < x.k; j++) {                   // register this clause's variables in the table
+            const uint32_t v = x.lit(p, j) >> 1;
+            uint32_t s = (v * 2654435761u) & (HSLOTS - 1);
+            for (;;) {
+                const uint32_t old = atomicCAS(&hvar[s], H_EMPTY, v);
+                if (old == H_EMPTY || old == v) break;
+                s = (s + 1) & (HSLOTS - 1);
+            }
+        }
+    }
+    __syncthreads();
+
+    uint32_t state = mine ? UNDECIDED : DROPPED;
+    uint32_t step = 0;
+    for (;;) {
+        const uint32_t key = ((TAGS - (step % TAGS)) << 16) | rank;
+        bool live = false;
+        if (state == UNDECIDED) {
+            bool taken = false;
+            for (uint32_t j = 0; j < x.k; j++) taken |= hclaim[h_find(hvar, x.lit(p, j) >> 1)] == C_TAKEN;
+            if (taken) state = DROPPED;
+            else {
+                for (uint32_t j = 0; j < x.k; j++) atomicMin(&hclaim[h_find(hvar, x.lit(p, j) >> 1)], key);
+                live = true;
+            }
+        }
+        if (__syncthreads_count(live) == 0) break;
+        bool win = false;
+        if (state == UNDECIDED) {
+            win = true;
+            for (uint32_t j = 0; j < x.k; j++) win &= hclaim[h_find(hvar, x.lit(p, j) >> 1)] == key;
+        }
+        __syncthreads();                                       // every win test has read before TAKEN marks land
+        if (win) {
+            state = IN_SET;
+            for (uint32_t j = 0; j < x.k; j++) hclaim[h_find(hvar, x.lit(p, j) >> 1)] = C_TAKEN;
+        }
+        step++;
+        if (step % TAGS == 0) {                                // tag wrap: survivors clear their stale claims
+            __syncthreads();
+            if (state == UNDECIDED)
+                for (uint32_t j = 0; j < x.k; j++) {
+                    const uint32_t s = h_find(hvar, x.lit(p, j) >> 1);
+                    if (hclaim[s] != C_TAKEN) hclaim[s] = C_FREE;
+                }
+        }
+        __syncthreads();
+    }
+
+    // ---- K4: winners redraw their variables (global bit-packed assignment) and report themselves
+    if (state == IN_SET) {
+        for (uint32_t j = 0; j < x.k; j++) {
+            const uint32_t v = x.lit(p, j) >> 1;
+            const uint32_t mask = 1u << (v & 31u);
+            if (random_bit(p.seed, STREAM_RESAMPLE, p.round, v)) atomicOr(&p.bits[v >> 5], mask);
+            else atomicAnd(&p.bits[v >> 5], ~mask);
+        }
+        p.s_slots[atomicAdd(&s_cnt, 1u)] = x.slot;
+        atomicAdd(&s_sum, (unsigned long long)x.k);            // SATInstance.h:363 counts literals->size()
+    }
+    __syncthreads();
+    if (t == 0) {
+        p.ctr->n_s = s_cnt;
+        p.ctr->n_resampled_round = s_sum;
+        atomicAdd(&p.ctr->n_luby_steps, (unsigned long long)step);
+        __threadfence();
+    }
+}
+
 // Round bookkeeping by one thread after the last barrier.  n_iterations counts every sweep (SATInstance.h:261).
 __device__ __forceinline__ void announce(const MisParams &p, unsigned int n_viol, unsigned int n_s)
 {
@@ -288,11 +403,11 @@ __device__ __forceinline__ void announce(const MisParams &p, unsigned int n_viol
 __device__ __forceinline__ void finish_round(const MisParams &p, uint32_t n_u)
 {
     Counters *c = p.ctr;
-    c->n_iterations += 1;
-    const unsigned int n_s = ld_u32(&c->n_s);
-    const unsigned long long n_r = __ldcg(&c->n_resampled_round);
-    c->sum_mis += n_s;                                     // SATInstance.h:291
-    c->n_resamples += n_r;                                 // SATInstance.h:313-315
+    const unsigned int n_s = ld_u32(&c->n_s);              // (both loads in flight together; the totals below are
+    const unsigned long long n_r = __ldcg(&c->n_resampled_round);   //  fire-and-forget atomics: no read-modify-write chain)
+    atomicAdd(&c->n_iterations, 1ull);
+    atomicAdd(&c->sum_mis, (unsigned long long)n_s);       // SATInstance.h:291
+    atomicAdd(&c->n_resamples, n_r);                       // SATInstance.h:313-315
     c->last_n_viol = n_u;
     c->last_n_s = n_s;
     c->last_resampled = n_r;
@@ -320,7 +435,7 @@ __global__ void __cluster_dims__(CL_SIZE, 1, 1) __launch_bounds__(CL_THREADS) mi
     }
     if (n_u == 0) {
         if (blockIdx.x == 0 && threadIdx.x == 0) {
-            p.ctr->n_iterations += 1;             // the terminal all-satisfied sweep counts (SATInstance.h:261,285-287)
+            atomicAdd(&p.ctr->n_iterations, 1ull);  // the terminal all-satisfied sweep counts (SATInstance.h:261,285-287)
             p.ctr->last_n_viol = 0;
             p.ctr->last_n_s = 0;
             p.ctr->last_resampled = 0;
@@ -332,6 +447,12 @@ __global__ void __cluster_dims__(CL_SIZE, 1, 1) __launch_bounds__(CL_THREADS) mi
         return;
     }
     if (n_u > CLUSTER_U && p.grid_follows) return;  // the grid kernel behind us takes it (else: strided, slower, still exact)
+    if (n_u <= SMALL_U && (uint64_t)n_u * p.kmax <= HSLOTS / 2 && p.cache_items) {
+        if (blockIdx.x != 0) return;              // uniform over the cluster: nobody waits on a cluster barrier below
+        mis_small_body(p, s_prefix, n_u);
+        if (threadIdx.x == 0) finish_round(p, n_u);
+        return;
+    }
     ClusterBarrier bar;
     mis_resample_body(p, bar, s_prefix, blockIdx.x * CL_THREADS + threadIdx.x, CLUSTER_U, n_u);
     bar.sync();
@@ -384,8 +505,12 @@ __global__ void map_ids_kernel(const uint32_t *slots, const uint32_t *orig_id, u
 static uint32_t grid_cache_items(uint32_t kmax) { return GRID_SMEM_WORDS_PER_THREAD / (kmax + EXTRA); }
 static size_t grid_smem_bytes(uint32_t kmax) { return (size_t)grid_cache_items(kmax) * (kmax + EXTRA) * GRID_THREADS * 4; }
 // the cluster kernel caches its one clause per thread whenever that fits the opt-in shared memory
-static uint32_t cluster_cache_items(uint32_t kmax) { return (size_t)(kmax + EXTRA) * CL_THREADS * 4 <= 200u * 1024u ? 1u : 0u; }
-static size_t cluster_smem_bytes(uint32_t kmax) { return (size_t)cluster_cache_items(kmax) * (kmax + EXTRA) * CL_THREADS * 4; }
+static uint32_t cluster_cache_items(uint32_t kmax) { return (size_t)(kmax + EXTRA) * CL_THREADS * 4 <= 128u * 1024u ? 1u : 0u; }
+static size_t cluster_smem_bytes(uint32_t kmax)
+{
+    if (!cluster_cache_items(kmax)) return 0;
+    return (size_t)(kmax + EXTRA) * CL_THREADS * 4 + (size_t)2 * HSLOTS * 4 + (size_t)SMALL_U * 8;   // literal cache | hash table | keys
+}
 
 // Called once per upload on the handle's device: shared-memory opt-in + cooperative grid size.
 cudaError_t mis_configure(int device, uint32_t kmax, uint32_t *grid_out)
