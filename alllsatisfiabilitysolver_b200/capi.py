@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "liballl_b200.so")
 OK, MAX_ROUNDS, EMPTY_CLAUSE, BAD_ARG, CUDA_ERROR, NCCL_ERROR, NO_INSTANCE, CAPACITY, PREEMPTED = range(9)
 STATUS_NAMES = ["OK", "MAX_ROUNDS", "EMPTY_CLAUSE", "BAD_ARG", "CUDA_ERROR", "NCCL_ERROR", "NO_INSTANCE", "CAPACITY", "PREEMPTED"]
 FLAG_NO_BUCKETING = 1
+FLAG_INCREMENTAL = 4
 
 #: every symbol include/alll_b200.h declares (tests check the library exports exactly these)
 SYMBOLS = [
@@ -51,7 +52,8 @@ class StatsC(C.Structure):
     _fields_ = [("n_iterations", C.c_uint64), ("n_resamples", C.c_uint64), ("avg_mis_size", C.c_uint64),
                 ("sum_mis_size", C.c_uint64), ("n_clause_evals", C.c_uint64), ("n_luby_steps", C.c_uint64),
                 ("n_kernel_launches", C.c_uint64), ("solve_ms", C.c_double), ("sweep_ms", C.c_double),
-                ("status", C.c_int32), ("reserved", C.c_int32), ("between_sweeps_ms", C.c_double)]
+                ("status", C.c_int32), ("reserved", C.c_int32), ("between_sweeps_ms", C.c_double),
+                ("n_incremental_rounds", C.c_uint64)]
 
 
 @dataclass
@@ -68,6 +70,7 @@ class Stats:
     sweep_ms: float
     status: int
     between_sweeps_ms: float = 0.0
+    n_incremental_rounds: int = 0
 
 
 _lib = None
@@ -215,7 +218,7 @@ class Solver:
         st = StatsC()
         self._check(self.lib.alll_solve(self.h, seed, max_rounds, C.byref(st)), allow=(OK, MAX_ROUNDS))
         return Stats(st.n_iterations, st.n_resamples, st.avg_mis_size, st.sum_mis_size, st.n_clause_evals,
-                     st.n_luby_steps, st.n_kernel_launches, st.solve_ms, st.sweep_ms, st.status, st.between_sweeps_ms)
+                     st.n_luby_steps, st.n_kernel_launches, st.solve_ms, st.sweep_ms, st.status, st.between_sweeps_ms, st.n_incremental_rounds)
 
     # -- clause-range sharded mode (device pointers; the all-gather between the two calls is the caller's) -------
     def set_id_base(self, id_base: int):
@@ -247,7 +250,7 @@ class Solver:
         st = StatsC()
         self._check(self.lib.alll_solve_p2p(self.h, seed, max_rounds, m_global, epoch, C.byref(st)), allow=(OK, MAX_ROUNDS))
         return Stats(st.n_iterations, st.n_resamples, st.avg_mis_size, st.sum_mis_size, st.n_clause_evals,
-                     st.n_luby_steps, st.n_kernel_launches, st.solve_ms, st.sweep_ms, st.status, st.between_sweeps_ms)
+                     st.n_luby_steps, st.n_kernel_launches, st.solve_ms, st.sweep_ms, st.status, st.between_sweeps_ms, st.n_incremental_rounds)
 
     def get_stats(self) -> Stats:
         st = StatsC()

@@ -137,6 +137,10 @@ struct Counters {
     unsigned int cta_done;      // sweep CTAs that have finished (sharded P2P mode: the last one publishes the round)
     unsigned int p2p_error;     // 1: capacity overflow, 2: a peer did not arrive in time
     unsigned int handled_tag;   // sharded P2P mode: tag of the last round an MIS kernel has completed
+    // incremental re-evaluation: decided by the MIS kernel at the end of a round for the NEXT round
+    unsigned int incr_next;     // 1: the next violated set comes from incr_eval_kernel, the sweep kernel returns at entry
+    unsigned int n_incr_rounds; // rounds evaluated incrementally so far
+    unsigned long long n_evals_incr;   // clauses actually evaluated by incremental rounds
 };
 
 // What the round loop on the host needs to know about a finished round.  Lives in pinned host memory; the MIS

@@ -20,7 +20,7 @@ cudaError_t launch_mis_resample_args(const ClauseView &cv, uint32_t kmax, const 
                                      uint32_t *s_slots, unsigned long long *claim, uint64_t n_vars, uint32_t *bits,
                                      Counters *ctr, uint64_t seed, uint32_t round, uint32_t grid, bool with_grid,
                                      RoundNote *note, unsigned long long seq, const P2PLink *p2p, uint32_t p2p_parity,
-                                     uint32_t p2p_tag, cudaStream_t s);
+                                     uint32_t p2p_tag, uint32_t incr_max_vars, cudaStream_t s);
 cudaError_t launch_reset_counters(Counters *c, int reset_totals, cudaStream_t s);
 cudaError_t launch_map_ids(const uint32_t *slots, const uint32_t *orig_id, uint32_t id_base, uint32_t n, uint32_t *out,
                            cudaStream_t s);
@@ -31,6 +31,14 @@ cudaError_t launch_export_records(const ClauseView &cv, const uint32_t *viol, co
 cudaError_t launch_repack_records(const uint32_t *records, uint64_t block_cap, uint32_t k, uint32_t n_blocks,
                                   const uint32_t *prefix, uint32_t *planes, uint64_t dense_cap, uint32_t *ids,
                                   uint32_t *iota, Counters *ctr, uint32_t grid, cudaStream_t s);
+
+// incremental.cu
+cudaError_t launch_incr_build(const uint32_t *planes, uint64_t m_pad, uint32_t k, uint32_t stride, const BucketSeg *segs,
+                              uint32_t n_buckets, uint64_t n_vars, uint32_t *occ_off, uint32_t *cursor, uint32_t *block_sums,
+                              uint32_t *rows, uint32_t *occ, uint32_t *d_total, cudaStream_t s);
+cudaError_t launch_incr_eval(const uint32_t *s_slots, const uint32_t *rows, uint32_t stride, uint32_t k,
+                             const uint32_t *occ_off, const uint32_t *occ, uint32_t *visited, uint64_t visited_words,
+                             const uint32_t *bits, uint32_t *viol, Counters *ctr, uint32_t grid, cudaStream_t s);
 
 // batch.cu
 size_t batch_smem_bytes(uint32_t n_vars, uint32_t n_words, uint32_t m_max);

@@ -68,6 +68,11 @@ struct alll_solver {
     // sharded mode: dense copy of the gathered violated records
     uint32_t *d_sh_planes = nullptr, *d_sh_ids = nullptr, *d_sh_iota = nullptr, *d_sh_s = nullptr;
     uint8_t *d_sh_state = nullptr;
+    // incremental re-evaluation (ALLL_FLAG_INCREMENTAL, fixed-width layout)
+    bool incr_ready = false;
+    uint32_t incr_stride = 0, incr_max_vars = 0;
+    uint32_t *d_occ_off = nullptr, *d_occ = nullptr, *d_rows = nullptr, *d_visited = nullptr, *d_incr_tmp = nullptr;
+    uint64_t visited_words = 0;
     // sharded P2P mode: our exchange region, the peers' mappings, the device-resident link table
     uint8_t *d_p2p_region = nullptr;
     size_t p2p_region_bytes = 0;
@@ -115,6 +120,7 @@ void free_instance(alll_handle h)
 {
     h->has_instance = false;
     h->use_orig_id = false;
+    h->incr_ready = false;
 }
 
 void release_buffers(alll_handle h)
@@ -129,6 +135,8 @@ void release_buffers(alll_handle h)
     for (uint32_t q = 0; q < MAX_SHARDS; q++)
         if (h->p2p_peer[q]) { cudaIpcCloseMemHandle(h->p2p_peer[q]); h->p2p_peer[q] = nullptr; }
     dfree(h->d_p2p_region); dfree(h->d_p2p_link);
+    dfree(h->d_occ_off); dfree(h->d_occ); dfree(h->d_rows); dfree(h->d_visited); dfree(h->d_incr_tmp);
+    h->incr_ready = false;
     h->p2p_ready = false;
     h->caps.clear();
     h->has_instance = false;
@@ -276,6 +284,29 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     sp.bucket_words = h->bucket_words; sp.k = k; sp.min_resident = h->min_resident; sp.eager = (h->flags >> 8) & 0xFFu; sp.prefetch_tiles = prefetch_distance(h->flags);
     CK(configure_sweep_planes(sp, h->resident_all));
     h->sweep_grid = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)h->sm_count, h->n_tiles));
+    if ((h->flags & ALLL_FLAG_INCREMENTAL) && m > 0) {
+        // occurrence lists + row-major copy for incremental re-evaluation (see incremental.cu)
+        const uint64_t n_lit = m * k;
+        if (n_lit >= 0xFFFFFFF0ull) return fail(h, ALLL_BAD_ARG, "incremental mode needs fewer than 2^32 literals");
+        h->incr_stride = (k + 3u) & ~3u;
+        const uint32_t nb = (uint32_t)((n_vars + 1023) / 1024);
+        POOL(h->d_occ_off, (n_vars + 1) * 4);
+        POOL(h->d_occ, n_lit * 4);
+        POOL(h->d_rows, h->m_pad * h->incr_stride * 4);
+        h->visited_words = (h->m_pad + 31) / 32;
+        POOL(h->d_visited, h->visited_words * 4);
+        POOL(h->d_incr_tmp, (n_vars + nb + 4) * 4);                 // cursors | block sums | total
+        CK(cudaMemsetAsync(h->d_visited, 0, h->visited_words * 4, h->stream));
+        CK(launch_incr_build(h->d_planes, h->m_pad, k, h->incr_stride, h->d_segs, h->n_buckets, n_vars, h->d_occ_off,
+                             h->d_incr_tmp, h->d_incr_tmp + n_vars, h->d_rows, h->d_occ, h->d_incr_tmp + n_vars + nb, h->stream));
+        h->launches += 5;
+        // next round is incremental when the resampled variables' occurrence lists cover <= m / divisor clauses
+        const uint32_t div_log2 = (h->flags >> 24) & 0xFu;
+        const uint64_t divisor = div_log2 ? (1ull << div_log2) : 8ull;
+        const double avg_occ = (double)n_lit / (double)n_vars;
+        h->incr_max_vars = (uint32_t)std::max<double>(1.0, (double)m / ((double)divisor * avg_occ));
+        h->incr_ready = true;
+    }
     CK(cudaStreamSynchronize(h->stream));
     h->has_instance = true;
     return ALLL_OK;
@@ -306,10 +337,11 @@ int enqueue_sweep(alll_handle h, uint32_t p2p_parity = 0, uint32_t p2p_tag = 0)
 }
 
 int enqueue_mis_resample(alll_handle h, uint64_t seed, uint32_t round, bool with_grid = true, RoundNote *note = nullptr,
-                         unsigned long long seq = 0)
+                         unsigned long long seq = 0, bool allow_incremental = false)
 {
     CK(launch_mis_resample_args(clause_view(h), h->kmax, h->d_viol, h->d_state, h->d_s, h->d_claim, h->n_vars,
-                                h->d_bits, h->d_ctr, seed, round, h->mis_grid, with_grid, note, seq, nullptr, 0u, 0u, h->stream));
+                                h->d_bits, h->d_ctr, seed, round, h->mis_grid, with_grid, note, seq, nullptr, 0u, 0u,
+                                (allow_incremental && h->incr_ready) ? h->incr_max_vars : 0u, h->stream));
     h->launches += with_grid ? 2 : 1;    // cluster kernel (+ cooperative grid kernel)
     return ALLL_OK;
 }
@@ -629,7 +661,8 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
     stats->n_resamples = c.n_resamples;
     stats->sum_mis_size = c.sum_mis;
     stats->avg_mis_size = c.n_iterations ? c.sum_mis / c.n_iterations : 0;     // SATInstance.h:317
-    stats->n_clause_evals = h->m * c.n_iterations;
+    stats->n_clause_evals = h->m * (c.n_iterations - c.n_incr_rounds) + c.n_evals_incr;   // clauses actually evaluated
+    stats->n_incremental_rounds = c.n_incr_rounds;
     stats->n_luby_steps = c.n_luby_steps;
     stats->n_kernel_launches = h->launches - launches0;
     stats->solve_ms = ms;
@@ -698,7 +731,7 @@ int alll_shard_round(alll_handle h, const uint32_t *d_records, const uint64_t *c
     ClauseView cv{};
     cv.planes = h->d_sh_planes; cv.m_pad = cap; cv.k = h->k; cv.orig_id = h->d_sh_ids; cv.id_base = 0;
     CK(launch_mis_resample_args(cv, h->k, h->d_sh_iota, h->d_sh_state, h->d_sh_s, h->d_claim, h->n_vars, h->d_bits,
-                                h->d_ctr, seed, round, h->mis_grid, total > MIS_CLUSTER_MAX_U, nullptr, 0ull, nullptr, 0u, 0u, h->stream));
+                                h->d_ctr, seed, round, h->mis_grid, total > MIS_CLUSTER_MAX_U, nullptr, 0ull, nullptr, 0u, 0u, 0u, h->stream));
     h->launches += total > MIS_CLUSTER_MAX_U ? 2 : 1;
     if (int rc = fetch_counters(h)) return rc;
     const Counters &c = *h->h_ctr;
@@ -821,7 +854,7 @@ int alll_solve_p2p(alll_handle h, uint64_t seed, uint64_t max_rounds, uint64_t m
             const bool with_grid = last_seen_u > MIS_CLUSTER_MAX_U;
             CK(launch_mis_resample_args(cv, h->k, nullptr, h->d_sh_state, h->d_sh_s, h->d_claim, h->n_vars, h->d_bits,
                                         h->d_ctr, seed, (uint32_t)issued, h->mis_grid, with_grid, &h->h_ring[slot],
-                                        seq0 + issued + 1, h->d_p2p_link, parity, tag, h->stream));
+                                        seq0 + issued + 1, h->d_p2p_link, parity, tag, 0u, h->stream));
             h->launches += with_grid ? 2 : 1;
             CK(cudaEventRecord(h->ev_round[slot], h->stream));
             issued++;

@@ -1,0 +1,233 @@
+// incremental.cu -- incremental re-evaluation (no reference counterpart: the reference
+// re-sweeps all m clauses every round, SATInstance.h:273-280).
+//
+// After a resample round only clauses containing a resampled variable can change status, and because the
+// independent set S is MAXIMAL every clause of the old violated set contains one too.  So the next violated set is
+//     U' = { c in occ(vars(S)) : c violated },
+// where occ(v) lists the clauses containing v.  The set is the same as the full sweep's, hence (the MIS being a
+// function of the set only) the whole trajectory, the statistics and the final assignment are bit-identical with
+// or without this mode.  It pays once |S| is small: a round then touches k*d*|S| clauses instead of m.
+//
+// Extra HBM state (built once per upload, only when the mode is enabled):
+//   occ_off[n+1], occ[L]   variable -> clause slots (CSR, any polarity)
+//   rows[m_pad][stride]    literals row-major by slot (stride = k rounded up to 4): one 16/32-byte fetch per clause
+//   visited[m_pad/32]      per-round "already evaluated" bits (cleared after every incremental round)
+#include "alll_device.cuh"
+
+namespace alll {
+
+// ---- build ------------------------------------------------------------------------------------------------
+
+// one thread per slot: count occurrences, write the row-major copy (padding literals repeat literal 0: neutral)
+__global__ void __launch_bounds__(256) incr_count_rows_kernel(const uint32_t *__restrict__ planes, uint64_t m_pad, uint32_t k,
+                                                               uint32_t stride, const BucketSeg *__restrict__ segs,
+                                                               uint32_t n_buckets, uint32_t *__restrict__ occ_cnt,
+                                                               uint32_t *__restrict__ rows)
+{
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= m_pad) return;
+    // valid slot?  (bucket segments are padded to tile boundaries)
+    uint32_t b = 0;
+    while (b + 1 < n_buckets && (uint64_t)segs[b + 1].tile_begin * TILE <= p) ++b;
+    const bool valid = p < segs[b].slot_end;
+    uint32_t first = 0;
+    for (uint32_t j = 0; j < stride; j++) {
+        uint32_t l = first;
+        if (j < k) {
+            l = planes[(uint64_t)j * m_pad + p];
+            if (j == 0) first = l;
+            if (valid) atomicAdd(&occ_cnt[l >> 1], 1u);
+        }
+        rows[p * stride + j] = valid ? l : 0u;
+    }
+}
+
+// exclusive scan of n counters, three passes (block sums -> scan of block sums -> add), 1024 items per block
+constexpr uint32_t SCAN_BLOCK = 1024;
+
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_block_kernel(const uint32_t *__restrict__ in, uint64_t n,
+                                                                uint32_t *__restrict__ out, uint32_t *__restrict__ block_sums)
+{
+    __shared__ uint32_t warp_sums[32];
+    const uint64_t i = (uint64_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const uint32_t v = i < n ? in[i] : 0u;
+    uint32_t x = v;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= (uint32_t)o) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_sums[lane];
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= (uint32_t)o) w += y;
+        }
+        warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t incl = x + (warp ? warp_sums[warp - 1] : 0u);
+    if (i < n) out[i] = incl - v;                                   // exclusive within the block
+    if (threadIdx.x == SCAN_BLOCK - 1) block_sums[blockIdx.x] = incl;
+}
+
+// single block: exclusive scan of the block sums in place (n_blocks <= a few 10^4: sequential chunks of 1024)
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_sums_kernel(uint32_t *sums, uint32_t n_blocks, uint32_t *total)
+{
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n_blocks; base += SCAN_BLOCK) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_blocks ? sums[i] : 0u;
+        uint32_t x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= (uint32_t)o) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_sums[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= (uint32_t)o) w += y;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t incl = x + (warp ? warp_sums[warp - 1] : 0u) + carry;
+        if (i < n_blocks) sums[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == SCAN_BLOCK - 1) carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_add_kernel(uint32_t *__restrict__ out, uint64_t n,
+                                                              const uint32_t *__restrict__ block_sums, uint32_t *__restrict__ cursor)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    if (i < n) {
+        const uint32_t v = out[i] + block_sums[blockIdx.x];
+        out[i] = v;
+        cursor[i] = v;                                              // fill cursors start at the list heads
+    }
+}
+
+__global__ void __launch_bounds__(256) incr_fill_kernel(const uint32_t *__restrict__ planes, uint64_t m_pad, uint32_t k,
+                                                         const BucketSeg *__restrict__ segs, uint32_t n_buckets,
+                                                         uint32_t *__restrict__ cursor, uint32_t *__restrict__ occ)
+{
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= m_pad) return;
+    uint32_t b = 0;
+    while (b + 1 < n_buckets && (uint64_t)segs[b + 1].tile_begin * TILE <= p) ++b;
+    if (p >= segs[b].slot_end) return;
+    for (uint32_t j = 0; j < k; j++) {
+        const uint32_t v = planes[(uint64_t)j * m_pad + p] >> 1;
+        occ[atomicAdd(&cursor[v], 1u)] = (uint32_t)p;
+    }
+}
+
+// ---- per round ----------------------------------------------------------------------------------------------
+
+struct IncrParams {
+    const uint32_t *s_slots;       // S of the round that just finished (clause slots)
+    const uint32_t *rows;          // [m_pad][stride]
+    uint32_t stride, k;
+    const uint32_t *occ_off, *occ;
+    uint32_t *visited;
+    const uint32_t *bits;
+    uint32_t *viol;
+    Counters *ctr;
+};
+
+// One warp per (clause of S, literal): walks the occurrence list of that variable, 32 clauses at a time.
+__global__ void __launch_bounds__(256) incr_eval_kernel(const IncrParams p)
+{
+    if (__ldcg(&p.ctr->done) || !__ldcg(&p.ctr->incr_next)) return;   // this round is a full sweep (or none at all)
+    const uint32_t n_s = __ldcg(&p.ctr->last_n_s);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+    const uint32_t n_items = n_s * p.k;
+    unsigned long long evals = 0;
+    for (uint32_t item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < n_items; item += warps_total) {
+        const uint32_t slot_s = p.s_slots[item / p.k];
+        const uint32_t v = p.rows[(uint64_t)slot_s * p.stride + item % p.k] >> 1;
+        const uint32_t lo = p.occ_off[v], hi = p.occ_off[v + 1];
+        for (uint32_t base = lo; base < hi; base += 32) {
+            const uint32_t e = base + lane;
+            bool violated = false;
+            uint32_t c = 0;
+            if (e < hi) {
+                c = p.occ[e];
+                const uint32_t bit = 1u << (c & 31u);
+                if (!(atomicOr(&p.visited[c >> 5], bit) & bit)) {       // first visit this round: evaluate
+                    evals++;
+                    const uint32_t *row = p.rows + (uint64_t)c * p.stride;
+                    violated = true;
+                    for (uint32_t j0 = 0; j0 < p.k && violated; j0 += 4) {
+                        const uint4 L = *reinterpret_cast<const uint4 *>(row + j0);
+                        const uint32_t l[4] = {L.x, L.y, L.z, L.w};
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            if (j0 + q < p.k && violated) {
+                                const uint32_t var = l[q] >> 1;
+                                if (((__ldcg(p.bits + (var >> 5)) >> (var & 31u)) ^ l[q]) & 1u) violated = false;
+                            }
+                        }
+                    }
+                }
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, violated);
+            if (bal) {
+                unsigned int g = 0;
+                if (lane == 0) g = atomicAdd(&p.ctr->n_viol, (unsigned int)__popc(bal));
+                g = __shfl_sync(0xffffffffu, g, 0);
+                if (violated) p.viol[g + __popc(bal & ((1u << lane) - 1u))] = c;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) evals += __shfl_down_sync(0xffffffffu, evals, o);
+    if (lane == 0 && evals) atomicAdd(&p.ctr->n_evals_incr, evals);
+}
+
+// ---- launchers ----------------------------------------------------------------------------------------------
+static inline uint32_t blocks_for(uint64_t n, uint32_t t) { return (uint32_t)((n + t - 1) / t); }
+
+cudaError_t launch_incr_build(const uint32_t *planes, uint64_t m_pad, uint32_t k, uint32_t stride, const BucketSeg *segs,
+                              uint32_t n_buckets, uint64_t n_vars, uint32_t *occ_off /*[n_vars+1]*/, uint32_t *cursor /*[n_vars]*/,
+                              uint32_t *block_sums, uint32_t *rows, uint32_t *occ, uint32_t *d_total, cudaStream_t s)
+{
+    cudaError_t e = cudaMemsetAsync(cursor, 0, n_vars * 4, s);       // cursor doubles as the occurrence counter
+    if (e != cudaSuccess) return e;
+    if (m_pad) incr_count_rows_kernel<<<blocks_for(m_pad, 256), 256, 0, s>>>(planes, m_pad, k, stride, segs, n_buckets, cursor, rows);
+    const uint32_t nb = blocks_for(n_vars, SCAN_BLOCK);
+    scan_block_kernel<<<nb, SCAN_BLOCK, 0, s>>>(cursor, n_vars, occ_off, block_sums);
+    scan_sums_kernel<<<1, SCAN_BLOCK, 0, s>>>(block_sums, nb, d_total);
+    scan_add_kernel<<<nb, SCAN_BLOCK, 0, s>>>(occ_off, n_vars, block_sums, cursor);
+    e = cudaMemcpyAsync(occ_off + n_vars, d_total, 4, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return e;
+    if (m_pad) incr_fill_kernel<<<blocks_for(m_pad, 256), 256, 0, s>>>(planes, m_pad, k, segs, n_buckets, cursor, occ);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_incr_eval(const uint32_t *s_slots, const uint32_t *rows, uint32_t stride, uint32_t k,
+                             const uint32_t *occ_off, const uint32_t *occ, uint32_t *visited, uint64_t visited_words,
+                             const uint32_t *bits, uint32_t *viol, Counters *ctr, uint32_t grid, cudaStream_t s)
+{
+    IncrParams p{s_slots, rows, stride, k, occ_off, occ, visited, bits, viol, ctr};
+    incr_eval_kernel<<<grid, 256, 0, s>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // the bitmap must be clean for the next incremental round; clearing it unconditionally costs ~1 us per 5 MB
+    return cudaMemsetAsync(visited, 0, visited_words * 4, s);
+}
+
+} // namespace alll

@@ -68,6 +68,7 @@ struct MisParams {
     // sharded P2P mode (NULL otherwise): U is the union of the record blocks all ranks stored into OUR exchange region
     const P2PLink *p2p;
     uint32_t p2p_parity, p2p_tag;
+    uint32_t incr_max_vars;     // incremental mode: next round is incremental iff this round resampled <= this many variables (0 = off)
 };
 
 extern __shared__ uint32_t mis_smem[];
@@ -403,6 +404,7 @@ __device__ __forceinline__ void announce(const MisParams &p, unsigned int n_viol
 __device__ __forceinline__ void finish_round(const MisParams &p, uint32_t n_u)
 {
     Counters *c = p.ctr;
+    if (ld_u32(&c->incr_next)) c->n_incr_rounds += 1;      // the round that just ended was evaluated incrementally
     const unsigned int n_s = ld_u32(&c->n_s);              // (both loads in flight together; the totals below are
     const unsigned long long n_r = __ldcg(&c->n_resampled_round);   //  fire-and-forget atomics: no read-modify-write chain)
     atomicAdd(&c->n_iterations, 1ull);
@@ -415,6 +417,7 @@ __device__ __forceinline__ void finish_round(const MisParams &p, uint32_t n_u)
     c->n_s = 0;
     c->n_resampled_round = 0;
     c->handled_tag = p.p2p_tag;
+    c->incr_next = (p.incr_max_vars != 0 && n_r <= p.incr_max_vars) ? 1u : 0u;
     announce(p, n_u, n_s);
 }
 
@@ -436,6 +439,7 @@ __global__ void __cluster_dims__(CL_SIZE, 1, 1) __launch_bounds__(CL_THREADS) mi
     if (n_u == 0) {
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             atomicAdd(&p.ctr->n_iterations, 1ull);  // the terminal all-satisfied sweep counts (SATInstance.h:261,285-287)
+            if (ld_u32(&p.ctr->incr_next)) p.ctr->n_incr_rounds += 1;
             p.ctr->last_n_viol = 0;
             p.ctr->last_n_s = 0;
             p.ctr->last_resampled = 0;
@@ -485,7 +489,10 @@ __global__ void reset_counters_kernel(Counters *c, int reset_totals)
     c->done = 0;
     c->cta_done = 0;
     c->p2p_error = 0;
+    c->incr_next = 0;
     if (reset_totals) {
+        c->n_incr_rounds = 0;
+        c->n_evals_incr = 0;
         c->n_iterations = 0;
         c->sum_mis = 0;
         c->n_resamples = 0;
@@ -537,10 +544,10 @@ cudaError_t launch_mis_resample_args(const ClauseView &cv, uint32_t kmax, const 
                                      uint32_t *s_slots, unsigned long long *claim, uint64_t n_vars, uint32_t *bits,
                                      Counters *ctr, uint64_t seed, uint32_t round, uint32_t grid, bool with_grid,
                                      RoundNote *note, unsigned long long seq, const P2PLink *p2p, uint32_t p2p_parity,
-                                     uint32_t p2p_tag, cudaStream_t s)
+                                     uint32_t p2p_tag, uint32_t incr_max_vars, cudaStream_t s)
 {
     MisParams p{cv, viol, state, s_slots, claim, n_vars, bits, ctr, seed, round, kmax, cluster_cache_items(kmax),
-                with_grid ? 1u : 0u, note, seq, p2p, p2p_parity, p2p_tag};
+                with_grid ? 1u : 0u, note, seq, p2p, p2p_parity, p2p_tag, incr_max_vars};
     mis_cluster_kernel<<<CL_SIZE, CL_THREADS, cluster_smem_bytes(kmax), s>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || !with_grid) return e;

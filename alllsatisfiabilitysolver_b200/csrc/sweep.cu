@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const Sw
 {
     constexpr bool RESIDENT_ALL = RB >= K;
     constexpr int RBE = RB < E ? RB : E;
-    if (__ldcg(&p.ctr->done)) return;         // speculatively enqueued behind the terminal round
+    if (__ldcg(&p.ctr->done) || __ldcg(&p.ctr->incr_next)) return;   // behind the terminal round / this round is incremental
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = threadIdx.x >> 5;
     WarpCompactor out{p.bucket_words + warp * WBUF, p.viol, p.ctr, 0u, lane, &p};
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const Sw
 template <bool RESIDENT_ALL>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_generic_kernel(const SweepParams p)
 {
-    if (__ldcg(&p.ctr->done)) return;
+    if (__ldcg(&p.ctr->done) || __ldcg(&p.ctr->incr_next)) return;
     const uint32_t lane = threadIdx.x & 31u;
     WarpCompactor comp{p.bucket_words + (threadIdx.x >> 5) * WBUF, p.viol, p.ctr, 0u, lane, nullptr};
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ALLL_ABI_VERSION 2
+#define ALLL_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define ALLL_API __attribute__((visibility("default")))
@@ -61,6 +61,12 @@ typedef struct {
 #define ALLL_FLAG_NO_BUCKETING 1u  /* keep clause order; gather non-resident assignment words from L2 (debug / comparison) */
 /* tuning knobs (0 = measured default): bits 8..15 literal planes streamed eagerly (4..8, default 5);
  * bits 16..23 L2 bulk-prefetch distance in tiles (default 2; 0xFF = off) */
+/* incremental re-evaluation: builds variable->clause occurrence lists and a row-major literal
+ * copy at upload (about 2x the literal bytes of extra HBM); once a round resamples few variables, the next violated set
+ * is computed from the clauses containing them instead of a full sweep.  Results are bit-identical to the default
+ * mode.  Bits 24..27: log2 of the switch-over divisor (default 3: incremental when <= m/8 clauses would be touched). */
+#define ALLL_FLAG_INCREMENTAL 4u
+#define ALLL_FLAG_INCR_DIVISOR_LOG2(x) ((uint32_t)(x) << 24)
 #define ALLL_FLAG_EAGER_PLANES(e)   ((uint32_t)(e) << 8)
 #define ALLL_FLAG_PREFETCH_TILES(d) ((uint32_t)(d) << 16)
 
@@ -73,7 +79,7 @@ typedef struct {
     uint64_t n_resamples;
     uint64_t avg_mis_size;
     uint64_t sum_mis_size;      /* sum |S| before the division                         */
-    uint64_t n_clause_evals;    /* m * n_iterations                                    */
+    uint64_t n_clause_evals;    /* m * n_iterations (clauses actually evaluated in incremental mode) */
     uint64_t n_luby_steps;      /* claim/win iterations summed over rounds             */
     uint64_t n_kernel_launches; /* kernels launched by this call                       */
     double   solve_ms;          /* device-timed: first sweep launched -> last kernel done (upload excluded) */
@@ -82,6 +88,8 @@ typedef struct {
     int32_t  reserved;
     double   between_sweeps_ms; /* device time from the end of a sweep to the start of the next: independent-set
                                    and resample kernels plus launch gaps                                       */
+    uint64_t n_incremental_rounds; /* rounds whose violated set came from incremental re-evaluation (0 by default);
+                                      n_clause_evals then counts the clauses actually evaluated                 */
 } alll_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------- */

@@ -303,3 +303,33 @@ def test_cfg3_beyond_lll_round_cap(capi, oracle):
         assert np.array_equal(s.get_assignment(), v)
         cnt, _ = s.eval(want_ids=False)
         assert cnt == len(oracle.sweep(off, lits.reshape(-1), v)) > 0
+
+
+@pytest.mark.parametrize("layout", [dict(flags=4), dict(flags=4 | (1 << 24)), dict(flags=4, sweep_smem_bytes=1024)],
+                         ids=["incremental", "incremental_div2", "incremental_bucketed"])
+@pytest.mark.parametrize("name", ["cfg1", "k7_small", "k8_small", "k3_uniform"])
+def test_incremental_mode_is_bit_identical(capi, oracle, golden, name, layout):
+    """ALLL_FLAG_INCREMENTAL: violated sets come from the occurrence lists of the resampled
+    variables once few variables are resampled; trajectory, Statistics and assignment must not change."""
+    n, off, lit, _ = golden_case(golden, name)
+    used = 0
+    for seed in (0, 1, 2, 3):
+        with capi.Solver(**layout) as s:
+            upload(s, n, off, lit)
+            s.randomize(seed)
+            st = s.solve(seed, 300)
+            v = oracle.randomize(n, seed)
+            so = oracle.solve(n, off, lit, v, seed, max_rounds=300)
+            assert st.status == so.status
+            assert (st.n_iterations, st.n_resamples, st.avg_mis_size, st.sum_mis_size) == \
+                   (so.n_iterations, so.n_resamples, so.avg_mis_size, so.sum_mis_size)
+            assert np.array_equal(s.get_assignment(), v)
+            m = len(off) - 1
+            assert st.n_clause_evals <= m * st.n_iterations
+            if st.n_incremental_rounds:
+                assert st.n_clause_evals < m * st.n_iterations
+            used += st.n_incremental_rounds
+            # the single-step calls keep working (always full sweeps) after an incremental solve
+            cnt, ids = s.eval()
+            assert np.array_equal(np.sort(ids), oracle.sweep(off, lit, v))
+    assert used > 0 or name == "k3_uniform"
