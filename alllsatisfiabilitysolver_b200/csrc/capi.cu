@@ -602,9 +602,17 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
             if (time_this) CK(cudaEventRecord(h->ev[2 * issued], h->stream));
             if (int rc = enqueue_sweep(h)) return rc;
             if (time_this) CK(cudaEventRecord(h->ev[2 * issued + 1], h->stream));
+            if (h->incr_ready && issued > 0) {
+                // incremental mode: the device decided at the end of the previous round which of the two kernels
+                // produces this round's violated set; the other one returns at entry
+                const uint32_t grid = (uint32_t)h->sm_count * 8;
+                CK(launch_incr_eval(h->d_s, h->d_rows, h->incr_stride, h->k, h->d_occ_off, h->d_occ, h->d_visited,
+                                    h->visited_words, h->d_bits, h->d_viol, h->d_ctr, grid, h->stream));
+                h->launches++;
+            }
             const int slot = (int)(issued % ROUNDS_IN_FLIGHT);
             if (int rc = enqueue_mis_resample(h, seed, (uint32_t)issued, last_seen_u > MIS_CLUSTER_MAX_U, &h->h_ring[slot],
-                                              seq0 + issued + 1))
+                                              seq0 + issued + 1, true))
                 return rc;
             CK(cudaEventRecord(h->ev_round[slot], h->stream));      // timing only: marks the end of this round on the device
             issued++;
