@@ -164,10 +164,13 @@ __device__ __forceinline__ uint32_t p2p_wait(const MisParams &p, uint32_t *s_pre
             }
         }
         __threadfence_system();                       // acquire: the records behind the flags are now visible
+        if (*(volatile unsigned int *)&me->abort) bad = true;     // a peer overflowed even though every flag arrived
         uint32_t run = 0;
         for (uint32_t q = 0; q < L.world; q++) {
             s_prefix[q] = run;
-            run += *(volatile unsigned int *)&me->count[p.p2p_parity][q];
+            const unsigned int cnt = *(volatile unsigned int *)&me->count[p.p2p_parity][q];
+            if (cnt > L.cap) bad = true;
+            run += cnt;
         }
         s_prefix[L.world] = bad ? 0xFFFFFFFFu : run;
     }
