@@ -18,7 +18,8 @@ constexpr uint32_t WBUF = 64;                     // per-warp violated-id stagin
 constexpr uint32_t QBUF = 160;                    // per-warp parked-clause queue entries (<= 31 kept + 128 max per push)
 constexpr uint32_t MAX_BUCKETS = 256;
 constexpr uint32_t EAGER_PLANES = 5;              // planes streamed by the sweep; the tail planes are fetched only for surviving clauses
-constexpr uint32_t RESIDENT_CAP = 4;              // at most this many literals of a clause are placed as bucket-resident
+constexpr uint32_t RESIDENT_CAP = 3;              // literals of a clause placed as bucket-resident by default (measured best of 2/3/4 at k=8)
+constexpr uint32_t RESIDENT_CAP_MAX = 4;
 constexpr uint32_t MAX_K = 32;
 constexpr uint32_t MIS_CLUSTER_MAX_U = 8192;       // violated sets up to this size are handled by one 8 x 1024-thread cluster
 constexpr uint32_t MAX_SHARDS = 64;                // clause-range shards (GPUs) of one instance
@@ -198,6 +199,7 @@ struct SweepParams {
     uint32_t k;
     uint32_t eager;             // tuning: planes streamed eagerly (0 = default EAGER_PLANES)
     uint32_t prefetch_tiles;    // tiles of L2 prefetch distance ahead of the register double buffer (0 = off)
+    uint32_t resident_cap;      // resident cap the layout was built with (0 = RESIDENT_CAP)
     uint32_t min_resident;      // min over clauses of the number of resident-placed literals (0 when unknown)
     // sharded P2P mode (p2p == NULL otherwise): records go to every peer instead of the local violated list
     const P2PLink *p2p;

@@ -59,7 +59,7 @@ cudaError_t launch_bucket_count(const uint32_t *lit, uint64_t m, uint32_t k, uin
                                 uint32_t n_buckets, uint8_t *bkt, uint32_t *cta_counts, uint32_t *err, cudaStream_t s);
 cudaError_t launch_bucket_scatter(const uint32_t *lit, uint64_t m, uint32_t k, uint32_t bucket_vars, uint32_t n_buckets,
                                   const uint8_t *bkt, const uint32_t *cta_base, uint32_t *planes, uint64_t m_pad,
-                                  uint32_t *orig_id, uint32_t *min_resident, cudaStream_t s);
+                                  uint32_t *orig_id, uint32_t *min_resident, uint32_t resident_cap, cudaStream_t s);
 cudaError_t launch_pack_bits(const uint8_t *bools, uint64_t n_vars, uint32_t *bits, uint32_t n_words_alloc, cudaStream_t s);
 cudaError_t launch_unpack_bits(const uint32_t *bits, uint64_t n_vars, uint8_t *bools, cudaStream_t s);
 cudaError_t launch_randomize(uint32_t *bits, uint64_t n_vars, uint32_t n_words_alloc, uint64_t seed, cudaStream_t s);

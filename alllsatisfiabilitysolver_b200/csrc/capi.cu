@@ -43,6 +43,7 @@ struct alll_solver {
     uint32_t n_words_alloc = 0, bucket_words = 0, n_buckets = 1, n_tiles = 0;
     bool resident_all = true;
     uint32_t min_resident = 0;           // measured by the bucketing pass; selects the sweep specialisation
+    uint32_t resident_cap = RESIDENT_CAP; // literals per clause placed as bucket-resident (flags bits 28..31, 0 = default)
     uint32_t *d_planes = nullptr, *d_orig_id = nullptr;
     BucketSeg *d_segs = nullptr;
     uint64_t *d_off = nullptr;
@@ -227,6 +228,10 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     CK(cudaMemcpyAsync(d_err, err_init, 8, cudaMemcpyHostToDevice, h->stream));
     std::vector<BucketSeg> segs(h->n_buckets);
     h->min_resident = 0;
+    {
+        const uint32_t rc = (h->flags >> 28) & 0xFu;
+        h->resident_cap = (rc >= 2 && rc <= RESIDENT_CAP_MAX && k >= 5) ? rc : RESIDENT_CAP;
+    }
 
     if (h->n_buckets == 1) {
         h->m_pad = align_up(m, TILE);
@@ -265,7 +270,7 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
         }
         h->use_orig_id = true;
         if (m) {
-            CK(launch_bucket_scatter(d_lit, m, k, bucket_vars, nb, d_bkt, d_cnt, h->d_planes, h->m_pad, h->d_orig_id, d_err + 1, h->stream));
+            CK(launch_bucket_scatter(d_lit, m, k, bucket_vars, nb, d_bkt, d_cnt, h->d_planes, h->m_pad, h->d_orig_id, d_err + 1, h->resident_cap, h->stream));
             h->launches++;
         }
     }
@@ -281,7 +286,7 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
 
     if (int rc = alloc_common(h)) return rc;
     SweepParams sp{};
-    sp.bucket_words = h->bucket_words; sp.k = k; sp.min_resident = h->min_resident; sp.eager = (h->flags >> 8) & 0xFFu; sp.prefetch_tiles = prefetch_distance(h->flags);
+    sp.bucket_words = h->bucket_words; sp.k = k; sp.min_resident = h->min_resident; sp.resident_cap = h->resident_cap; sp.eager = (h->flags >> 8) & 0xFFu; sp.prefetch_tiles = prefetch_distance(h->flags);
     CK(configure_sweep_planes(sp, h->resident_all));
     h->sweep_grid = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)h->sm_count, h->n_tiles));
     if ((h->flags & ALLL_FLAG_INCREMENTAL) && m > 0) {
@@ -321,7 +326,7 @@ int enqueue_sweep(alll_handle h, uint32_t p2p_parity = 0, uint32_t p2p_tag = 0)
         SweepParams sp{};
         sp.planes = h->d_planes; sp.m_pad = h->m_pad; sp.bits = h->d_bits; sp.n_words = h->n_words_alloc;
         sp.bucket_words = h->bucket_words; sp.n_buckets = h->n_buckets; sp.n_tiles = h->n_tiles;
-        sp.segs = h->d_segs; sp.viol = h->d_viol; sp.ctr = h->d_ctr; sp.k = h->k; sp.min_resident = h->min_resident; sp.eager = (h->flags >> 8) & 0xFFu; sp.prefetch_tiles = prefetch_distance(h->flags);
+        sp.segs = h->d_segs; sp.viol = h->d_viol; sp.ctr = h->d_ctr; sp.k = h->k; sp.min_resident = h->min_resident; sp.resident_cap = h->resident_cap; sp.eager = (h->flags >> 8) & 0xFFu; sp.prefetch_tiles = prefetch_distance(h->flags);
         if (p2p_tag) {
             sp.p2p = h->d_p2p_link; sp.p2p_parity = p2p_parity; sp.p2p_tag = p2p_tag;
             sp.orig_id = h->use_orig_id ? h->d_orig_id : nullptr; sp.id_base = h->id_base;

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) bucket_scatter_kernel(const ui
                                                                          const uint32_t *__restrict__ cta_base,
                                                                          uint32_t *__restrict__ planes, uint64_t m_pad,
                                                                          uint32_t *__restrict__ orig_id,
-                                                                         uint32_t *__restrict__ min_resident)
+                                                                         uint32_t *__restrict__ min_resident, uint32_t resident_cap)
 {
     __shared__ uint16_t warp_cnt[(LAYOUT_THREADS / 32) * MAX_BUCKETS];   // [warp][bucket], then exclusive over warps
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -113,11 +113,11 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) bucket_scatter_kernel(const ui
     const uint64_t dst = (uint64_t)cta_base[(uint64_t)b * gridDim.x + blockIdx.x] + warp_cnt[warp * n_buckets + b] + rank;
     orig_id[dst] = (uint32_t)c;
     const uint32_t lo = b * bucket_vars;
-    // the first (at most RESIDENT_CAP) bucket-resident literals go to the leading planes, original order kept;
+    // the first (at most resident_cap) bucket-resident literals go to the leading planes, original order kept;
     // everything else follows (a resident literal beyond the cap is simply looked up through L2 like the rest)
     uint32_t j_out = 0, placed = 0;
     uint32_t front_mask = 0;
-    for (uint32_t j = 0; j < k && placed < RESIDENT_CAP; j++) {
+    for (uint32_t j = 0; j < k && placed < resident_cap; j++) {
         const uint32_t l = lit[c * k + j];
         if ((l >> 1) - lo < bucket_vars) {
             planes[(uint64_t)(j_out++) * m_pad + dst] = l;
@@ -207,10 +207,10 @@ cudaError_t launch_bucket_count(const uint32_t *lit, uint64_t m, uint32_t k, uin
 
 cudaError_t launch_bucket_scatter(const uint32_t *lit, uint64_t m, uint32_t k, uint32_t bucket_vars, uint32_t n_buckets,
                                   const uint8_t *bkt, const uint32_t *cta_base, uint32_t *planes, uint64_t m_pad,
-                                  uint32_t *orig_id, uint32_t *min_resident, cudaStream_t s)
+                                  uint32_t *orig_id, uint32_t *min_resident, uint32_t resident_cap, cudaStream_t s)
 {
     bucket_scatter_kernel<<<bucket_pass_ctas(m), LAYOUT_THREADS, 0, s>>>(lit, m, k, bucket_vars, n_buckets, bkt, cta_base,
-                                                                           planes, m_pad, orig_id, min_resident);
+                                                                           planes, m_pad, orig_id, min_resident, resident_cap);
     return cudaGetLastError();
 }
 

@@ -506,15 +506,26 @@ static cudaError_t launch_generic(const SweepParams &p, uint32_t grid, size_t sm
 
 // resident_all: every plane is resident-only (RB = RC = K).  Otherwise RC = min(K, RESIDENT_CAP) and
 // RB = min(p.min_resident, 2, RC) as measured by the upload pass.
+template <int K, int RC>
+static cudaError_t dispatch_rb(const SweepParams &p, uint32_t grid, size_t smem, cudaStream_t s, bool cfg)
+{
+    const uint32_t rb = p.min_resident < 2u ? p.min_resident : 2u;
+    if (rb >= 2 && RC >= 2) return launch_planes<K, (RC < 2 ? RC : 2), RC>(p, grid, smem, s, cfg);
+    if (rb >= 1 && RC >= 1) return launch_planes<K, (RC < 1 ? RC : 1), RC>(p, grid, smem, s, cfg);
+    return launch_planes<K, 0, RC>(p, grid, smem, s, cfg);
+}
+
 template <int K>
 static cudaError_t dispatch_class(const SweepParams &p, bool resident_all, uint32_t grid, size_t smem, cudaStream_t s, bool cfg)
 {
-    constexpr int RC = K < (int)RESIDENT_CAP ? K : (int)RESIDENT_CAP;
     if (resident_all) return launch_planes<K, K, K>(p, grid, smem, s, cfg);
-    const uint32_t rb = p.min_resident < 2u ? p.min_resident : 2u;
-    if (rb >= 2 && RC >= 2) return launch_planes<K, (RC < 2 ? RC : 2), RC>(p, grid, smem, s, cfg);
-    if (rb >= 1) return launch_planes<K, 1, RC>(p, grid, smem, s, cfg);
-    return launch_planes<K, 0, RC>(p, grid, smem, s, cfg);
+    // RC = min(K, resident cap of the layout); wide clauses may be laid out with a smaller cap (tuning knob)
+    constexpr int RC_DEFAULT = K < (int)RESIDENT_CAP ? K : (int)RESIDENT_CAP;
+    if constexpr (K >= 5) {
+        if (p.resident_cap == 2) return dispatch_rb<K, 2>(p, grid, smem, s, cfg);
+        if (p.resident_cap == 4) return dispatch_rb<K, 4>(p, grid, smem, s, cfg);
+    }
+    return dispatch_rb<K, RC_DEFAULT>(p, grid, smem, s, cfg);
 }
 
 static cudaError_t dispatch_k(const SweepParams &p, bool resident_all, uint32_t grid, size_t smem, cudaStream_t s, bool cfg)
