@@ -13,7 +13,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liballl_b200.so")
+LIB_PATH = os.environ.get("ALLL_B200_LIB") or os.path.join(_HERE, "liballl_b200.so")   # env override: tuning builds
 
 OK, MAX_ROUNDS, EMPTY_CLAUSE, BAD_ARG, CUDA_ERROR, NCCL_ERROR, NO_INSTANCE, CAPACITY, PREEMPTED = range(9)
 STATUS_NAMES = ["OK", "MAX_ROUNDS", "EMPTY_CLAUSE", "BAD_ARG", "CUDA_ERROR", "NCCL_ERROR", "NO_INSTANCE", "CAPACITY", "PREEMPTED"]

@@ -11,7 +11,10 @@ constexpr uint32_t STREAM_INIT = 0u;
 constexpr uint32_t STREAM_RESAMPLE = 1u;
 constexpr uint32_t STREAM_PRIORITY = 2u;
 
-constexpr uint32_t SWEEP_THREADS = 512;           // one CTA per SM (the staged assignment owns the shared memory), <=128 regs/thread
+#ifndef ALLL_SWEEP_THREADS
+#define ALLL_SWEEP_THREADS 512
+#endif
+constexpr uint32_t SWEEP_THREADS = ALLL_SWEEP_THREADS;           // one CTA per SM (the staged assignment owns the shared memory), <=128 regs/thread
 constexpr uint32_t CLAUSES_PER_THREAD = 4;        // one 128-bit load per literal plane
 constexpr uint32_t TILE = SWEEP_THREADS * CLAUSES_PER_THREAD;   // clause slots per sweep tile
 constexpr uint32_t WBUF = 64;                     // per-warp violated-id staging entries (flushed at >= 32, +32 max per push)
