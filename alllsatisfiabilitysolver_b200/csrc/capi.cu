@@ -230,7 +230,8 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     h->min_resident = 0;
     {
         const uint32_t rc = (h->flags >> 28) & 0xFu;
-        h->resident_cap = (rc >= 2 && rc <= RESIDENT_CAP_MAX && k >= 5) ? rc : RESIDENT_CAP;
+        (void)rc;                                        // (the 2 / 4 variants were measured and removed: see profiles/)
+        h->resident_cap = RESIDENT_CAP;
     }
 
     if (h->n_buckets == 1) {

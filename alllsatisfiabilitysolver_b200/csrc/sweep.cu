@@ -482,16 +482,11 @@ static cudaError_t launch_planes_e(const SweepParams &p, uint32_t grid, size_t s
     return cudaGetLastError();
 }
 
-// p.eager (tuning knob, 0 = default) picks how many planes are streamed; only wide clauses have a choice.
+// E = min(K, EAGER_PLANES) planes are streamed (4 / 5 / 6 / 8 were measured at k = 8: 5 is fastest, profiles/).
 template <int K, int RB, int RC>
 static cudaError_t launch_planes(const SweepParams &p, uint32_t grid, size_t smem, cudaStream_t s, bool configure_only)
 {
     constexpr int E = K < (int)EAGER_PLANES ? K : (int)EAGER_PLANES;
-    if constexpr (K >= 7) {
-        if (p.eager == 4) return launch_planes_e<K, RB, RC, 4>(p, grid, smem, s, configure_only);
-        if (p.eager == 6) return launch_planes_e<K, RB, RC, 6>(p, grid, smem, s, configure_only);
-        if (p.eager == (uint32_t)K) return launch_planes_e<K, RB, RC, K>(p, grid, smem, s, configure_only);
-    }
     return launch_planes_e<K, RB, RC, E>(p, grid, smem, s, configure_only);
 }
 
@@ -519,12 +514,8 @@ template <int K>
 static cudaError_t dispatch_class(const SweepParams &p, bool resident_all, uint32_t grid, size_t smem, cudaStream_t s, bool cfg)
 {
     if (resident_all) return launch_planes<K, K, K>(p, grid, smem, s, cfg);
-    // RC = min(K, resident cap of the layout); wide clauses may be laid out with a smaller cap (tuning knob)
+    // RC = min(K, RESIDENT_CAP): 2 / 3 / 4 resident-placed literals were measured at k = 8, 3 is fastest (profiles/)
     constexpr int RC_DEFAULT = K < (int)RESIDENT_CAP ? K : (int)RESIDENT_CAP;
-    if constexpr (K >= 5) {
-        if (p.resident_cap == 2) return dispatch_rb<K, 2>(p, grid, smem, s, cfg);
-        if (p.resident_cap == 4) return dispatch_rb<K, 4>(p, grid, smem, s, cfg);
-    }
     return dispatch_rb<K, RC_DEFAULT>(p, grid, smem, s, cfg);
 }
 

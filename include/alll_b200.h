@@ -59,18 +59,16 @@ typedef struct {
 } alll_config;
 
 #define ALLL_FLAG_NO_BUCKETING 1u  /* keep clause order; gather non-resident assignment words from L2 (debug / comparison) */
-/* tuning knobs (0 = measured default): bits 8..15 literal planes streamed eagerly (4..8, default 5);
- * bits 16..23 L2 bulk-prefetch distance in tiles (default 2; 0xFF = off);
- * bits 28..31 literals per clause laid out as bucket-resident (2..4, default 3; clause width >= 5 only) */
+/* tuning knob: bits 16..23 = L2 bulk-prefetch distance in tiles (0 = measured default 2; 0xFF = off).  The number of
+ * planes streamed eagerly (5) and of resident-placed literals per clause (3) are compile-time choices; the measured
+ * alternatives are recorded in profiles/. */
+#define ALLL_FLAG_PREFETCH_TILES(d) ((uint32_t)(d) << 16)
 /* incremental re-evaluation: builds variable->clause occurrence lists and a row-major literal
  * copy at upload (about 2x the literal bytes of extra HBM); once a round resamples few variables, the next violated set
  * is computed from the clauses containing them instead of a full sweep.  Results are bit-identical to the default
  * mode.  Bits 24..27: log2 of the switch-over divisor (default 3: incremental when <= m/8 clauses would be touched). */
 #define ALLL_FLAG_INCREMENTAL 4u
 #define ALLL_FLAG_INCR_DIVISOR_LOG2(x) ((uint32_t)(x) << 24)
-#define ALLL_FLAG_EAGER_PLANES(e)   ((uint32_t)(e) << 8)
-#define ALLL_FLAG_PREFETCH_TILES(d) ((uint32_t)(d) << 16)
-#define ALLL_FLAG_RESIDENT_CAP(c)   ((uint32_t)(c) << 28)
 
 /* Statistics{} of SATInstance.h:25-32 plus device-side counters.
  * n_iterations = resample rounds + 1 (the terminal all-satisfied sweep counts, :261,:285-287);
