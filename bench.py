@@ -62,7 +62,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -241,7 +241,7 @@ def run_ours(args):
 
     # ---- same workload with incremental re-evaluation (opt-in mode; bit-identical results, fewer clause evaluations) ----
     incremental = None
-    if not args.no_extras:
+    if not args.no_extras and world == 1:
         inc = capi.Solver(device=local_rank, flags=capi.FLAG_INCREMENTAL)
         inc.upload_fixedk_device(n, m, k, lits_t.data_ptr())
         res = []
@@ -288,12 +288,18 @@ def run_ours(args):
     # ---- other BASELINE configs, briefly (parity-test cases, not bench lines): cfg2 single solve, cfg5 batch ----
     extras = None
     if world == 1 and not args.no_extras and args.workload == "cfg4" and args.scale == 1.0:
-        extras = other_workloads(local_rank)
+        try:
+            extras = other_workloads(local_rank)
+        except Exception as e:                       # never lose the main line to an extra
+            extras = {"error": repr(e)}
 
     # ---- clause-range sharded solve of the SAME workload over all ranks (strong scaling, NCCL all-gather) ----
     sharded = None
     if world > 1 and not args.no_sharded:
-        sharded = sharded_solves(args, shape, rank, world, local_rank)
+        try:
+            sharded = sharded_solves(args, shape, rank, world, local_rank)
+        except Exception as e:                       # e.g. CUDA IPC not permitted on this box: report, do not die
+            sharded = {"error": repr(e)}
 
     # ---- reduce over ranks: MAX time, SUM work ----
     red = torch.tensor([dev_ms, wall_ms, e2e_s], dtype=torch.float64, device="cuda")
@@ -473,7 +479,7 @@ def sharded_solves(args, shape, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(CONFIGS))
