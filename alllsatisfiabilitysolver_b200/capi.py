@@ -19,6 +19,7 @@ OK, MAX_ROUNDS, EMPTY_CLAUSE, BAD_ARG, CUDA_ERROR, NCCL_ERROR, NO_INSTANCE, CAPA
 STATUS_NAMES = ["OK", "MAX_ROUNDS", "EMPTY_CLAUSE", "BAD_ARG", "CUDA_ERROR", "NCCL_ERROR", "NO_INSTANCE", "CAPACITY", "PREEMPTED"]
 FLAG_NO_BUCKETING = 1
 FLAG_INCREMENTAL = 4
+FLAG_FORCE_CSR = 8
 
 #: every symbol include/alll_b200.h declares (tests check the library exports exactly these)
 SYMBOLS = [

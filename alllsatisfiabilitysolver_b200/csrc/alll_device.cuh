@@ -107,10 +107,12 @@ struct ClauseView {
     // slot -> caller clause id (NULL = identity), plus the first id of this clause range (sharded mode)
     const uint32_t *orig_id;
     uint32_t id_base;
+    // padded planes (ragged input laid out with k = widest clause): true width per slot, NULL when all equal k
+    const uint8_t *width_arr;
 
     __device__ __forceinline__ uint32_t width(uint32_t p) const
     {
-        return k ? k : (uint32_t)(off[p + 1] - off[p]);
+        return width_arr ? width_arr[p] : (k ? k : (uint32_t)(off[p + 1] - off[p]));
     }
     __device__ __forceinline__ uint32_t literal(uint32_t p, uint32_t j) const
     {

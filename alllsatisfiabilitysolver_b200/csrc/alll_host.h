@@ -35,7 +35,7 @@ cudaError_t launch_repack_records(const uint32_t *records, uint64_t block_cap, u
 // incremental.cu
 cudaError_t launch_incr_build(const uint32_t *planes, uint64_t m_pad, uint32_t k, uint32_t stride, const BucketSeg *segs,
                               uint32_t n_buckets, uint64_t n_vars, uint32_t *occ_off, uint32_t *cursor, uint32_t *block_sums,
-                              uint32_t *rows, uint32_t *occ, uint32_t *d_total, cudaStream_t s);
+                              uint32_t *rows, uint32_t *occ, uint32_t *d_total, const uint8_t *width, cudaStream_t s);
 cudaError_t launch_incr_eval(const uint32_t *s_slots, const uint32_t *rows, uint32_t stride, uint32_t k,
                              const uint32_t *occ_off, const uint32_t *occ, uint32_t *visited, uint64_t visited_words,
                              const uint32_t *bits, uint32_t *viol, Counters *ctr, uint32_t grid, cudaStream_t s);
@@ -59,7 +59,8 @@ cudaError_t launch_bucket_count(const uint32_t *lit, uint64_t m, uint32_t k, uin
                                 uint32_t n_buckets, uint8_t *bkt, uint32_t *cta_counts, uint32_t *err, cudaStream_t s);
 cudaError_t launch_bucket_scatter(const uint32_t *lit, uint64_t m, uint32_t k, uint32_t bucket_vars, uint32_t n_buckets,
                                   const uint8_t *bkt, const uint32_t *cta_base, uint32_t *planes, uint64_t m_pad,
-                                  uint32_t *orig_id, uint32_t *min_resident, uint32_t resident_cap, cudaStream_t s);
+                                  uint32_t *orig_id, uint32_t *min_resident, uint32_t resident_cap, const uint8_t *width_in,
+                                  uint8_t *width_out, cudaStream_t s);
 cudaError_t launch_pack_bits(const uint8_t *bools, uint64_t n_vars, uint32_t *bits, uint32_t n_words_alloc, cudaStream_t s);
 cudaError_t launch_unpack_bits(const uint32_t *bits, uint64_t n_vars, uint8_t *bools, cudaStream_t s);
 cudaError_t launch_randomize(uint32_t *bits, uint64_t n_vars, uint32_t n_words_alloc, uint64_t seed, cudaStream_t s);

@@ -53,6 +53,8 @@ struct alll_solver {
     unsigned long long *d_claim = nullptr;
     uint32_t *d_viol = nullptr, *d_s = nullptr, *d_ids_out = nullptr;
     uint8_t *d_state = nullptr, *d_bools = nullptr;
+    uint8_t *d_width = nullptr, *d_width_in = nullptr;   // padded planes: true clause widths by slot / by caller id
+    bool use_width = false;
     Counters *d_ctr = nullptr;
     Counters *h_ctr = nullptr;           // pinned
     RoundNote *h_ring = nullptr;         // pinned [ROUNDS_IN_FLIGHT]: written by the MIS kernels, polled by the round loop
@@ -121,6 +123,7 @@ void free_instance(alll_handle h)
 {
     h->has_instance = false;
     h->use_orig_id = false;
+    h->use_width = false;
     h->incr_ready = false;
 }
 
@@ -128,7 +131,7 @@ void release_buffers(alll_handle h)
 {
     dfree(h->d_planes); dfree(h->d_orig_id); dfree(h->d_segs); dfree(h->d_off); dfree(h->d_csr_lit);
     dfree(h->d_bits); dfree(h->d_claim); dfree(h->d_viol); dfree(h->d_s); dfree(h->d_ids_out);
-    dfree(h->d_state); dfree(h->d_bools); dfree(h->d_tmp_bkt); dfree(h->d_tmp_cnt); dfree(h->d_tmp_err); dfree(h->d_stage);
+    dfree(h->d_state); dfree(h->d_bools); dfree(h->d_width); dfree(h->d_width_in); dfree(h->d_tmp_bkt); dfree(h->d_tmp_cnt); dfree(h->d_tmp_err); dfree(h->d_stage);
     dfree(h->d_sh_planes); dfree(h->d_sh_ids); dfree(h->d_sh_iota); dfree(h->d_sh_s); dfree(h->d_sh_state);
     dfree(h->d_b_planes); dfree(h->d_b_off); dfree(h->d_b_m); dfree(h->d_b_bits); dfree(h->d_b_lit); dfree(h->d_b_src_off);
     dfree(h->d_b_seeds); dfree(h->d_b_stats); dfree(h->d_b_bytes); dfree(h->d_b_winner);
@@ -172,6 +175,7 @@ ClauseView clause_view(alll_handle h)
     cv.planes = h->d_planes; cv.m_pad = h->m_pad; cv.k = h->k;
     cv.off = h->d_off; cv.csr_lit = h->d_csr_lit; cv.orig_id = h->use_orig_id ? h->d_orig_id : nullptr;
     cv.id_base = h->id_base;
+    cv.width_arr = h->use_width ? h->d_width : nullptr;
     return cv;
 }
 
@@ -200,7 +204,10 @@ int check_sizes(alll_handle h, uint64_t n_vars, uint64_t m)
     return ALLL_OK;
 }
 
-int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *d_lit)
+// d_width_in (may be NULL): true width of every clause (by caller id) when the rows are padded to k literals with
+// copies of their first literal (ragged input on the plane layout; a repeated literal never changes a clause's value).
+int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *d_lit,
+                              const uint8_t *d_width_in = nullptr)
 {
     free_instance(h);
     if (int rc = check_sizes(h, n_vars, m)) return rc;
@@ -240,6 +247,10 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
         if (h->m_pad) POOL(h->d_planes, h->m_pad * k * 4);
         CK(launch_transpose(d_lit, m, k, n_vars, h->d_planes, h->m_pad, d_err, h->stream)); h->launches++;
         segs[0] = BucketSeg{0u, (uint32_t)m};
+        if (d_width_in && m) {
+            POOL(h->d_width, h->m_pad);
+            CK(cudaMemcpyAsync(h->d_width, d_width_in, m, cudaMemcpyDeviceToDevice, h->stream));
+        }
     } else {
         const uint32_t bucket_vars = h->bucket_words * 32u, nb = h->n_buckets;
         const uint32_t n_cta = bucket_pass_ctas(m);
@@ -268,10 +279,12 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
         if (h->m_pad) {
             POOL(h->d_planes, h->m_pad * k * 4);
             POOL(h->d_orig_id, h->m_pad * 4);
+            if (d_width_in) POOL(h->d_width, h->m_pad);
         }
         h->use_orig_id = true;
         if (m) {
-            CK(launch_bucket_scatter(d_lit, m, k, bucket_vars, nb, d_bkt, d_cnt, h->d_planes, h->m_pad, h->d_orig_id, d_err + 1, h->resident_cap, h->stream));
+            CK(launch_bucket_scatter(d_lit, m, k, bucket_vars, nb, d_bkt, d_cnt, h->d_planes, h->m_pad, h->d_orig_id, d_err + 1, h->resident_cap, d_width_in,
+                                     d_width_in ? h->d_width : nullptr, h->stream));
             h->launches++;
         }
     }
@@ -285,6 +298,7 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     if (err_out[0]) { free_instance(h); return fail(h, ALLL_BAD_ARG, "a literal references a variable >= n_vars"); }
     if (h->n_buckets > 1 && m > 0 && err_out[1] != 0xFFFFFFFFu) h->min_resident = err_out[1];
 
+    h->use_width = d_width_in != nullptr && m > 0;
     if (int rc = alloc_common(h)) return rc;
     SweepParams sp{};
     sp.bucket_words = h->bucket_words; sp.k = k; sp.min_resident = h->min_resident; sp.resident_cap = h->resident_cap; sp.eager = (h->flags >> 8) & 0xFFu; sp.prefetch_tiles = prefetch_distance(h->flags);
@@ -304,7 +318,8 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
         POOL(h->d_incr_tmp, (n_vars + nb + 4) * 4);                 // cursors | block sums | total
         CK(cudaMemsetAsync(h->d_visited, 0, h->visited_words * 4, h->stream));
         CK(launch_incr_build(h->d_planes, h->m_pad, k, h->incr_stride, h->d_segs, h->n_buckets, n_vars, h->d_occ_off,
-                             h->d_incr_tmp, h->d_incr_tmp + n_vars, h->d_rows, h->d_occ, h->d_incr_tmp + n_vars + nb, h->stream));
+                             h->d_incr_tmp, h->d_incr_tmp + n_vars, h->d_rows, h->d_occ, h->d_incr_tmp + n_vars + nb,
+                             h->use_width ? h->d_width : nullptr, h->stream));
         h->launches += 5;
         // next round is incremental when the resampled variables' occurrence lists cover <= m / divisor clauses
         const uint32_t div_log2 = (h->flags >> 24) & 0xFu;
@@ -487,6 +502,26 @@ int alll_upload_csr(alll_handle h, uint64_t n_vars, uint64_t m, const uint64_t *
         kmax = std::max(kmax, w);
     }
     if (uniform && k0 <= MAX_K) return alll_upload_fixedk(h, n_vars, m, (uint32_t)k0, lit + off[0]);
+    const uint64_t n_lit_in = m ? off[m] - off[0] : 0;
+    if (m > 0 && kmax <= MAX_K && m * kmax <= 2 * n_lit_in + 1024 && !(h->flags & ALLL_FLAG_FORCE_CSR)) {
+        // ragged input with modest spread: pad every clause to the widest one with copies of its first literal and
+        // use the plane layout (fast sweep); true widths are kept for the independent-set / resample accounting
+        std::vector<uint32_t> padded(m * kmax);
+        std::vector<uint8_t> widths(m);
+        for (uint64_t c = 0; c < m; c++) {
+            const uint64_t w = off[c + 1] - off[c];
+            widths[c] = (uint8_t)w;
+            for (uint64_t j = 0; j < kmax; j++) padded[c * kmax + j] = lit[off[c] + (j < w ? j : 0)];
+        }
+        free_instance(h);
+        POOL(h->d_stage, padded.size() * 4);
+        POOL(h->d_width_in, m);
+        CK(cudaMemcpyAsync(h->d_stage, padded.data(), padded.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_width_in, widths.data(), m, cudaMemcpyHostToDevice, h->stream));
+        const int rc = upload_fixedk_device_impl(h, n_vars, m, (uint32_t)kmax, h->d_stage, h->d_width_in);
+        cudaStreamSynchronize(h->stream);
+        return rc;
+    }
 
     free_instance(h);
     if (int rc = check_sizes(h, n_vars, m)) return rc;
@@ -699,7 +734,7 @@ int alll_set_id_base(alll_handle h, uint64_t id_base)
 int alll_shard_sweep(alll_handle h, uint32_t *d_records, uint64_t cap_records, uint64_t *n_local)
 {
     NEED_INSTANCE();
-    if (!h->k) return fail(h, ALLL_BAD_ARG, "sharded mode needs the fixed-width layout");
+    if (!h->k || h->use_width) return fail(h, ALLL_BAD_ARG, "sharded mode needs uniform clause width");
     if (!d_records && cap_records) return fail(h, ALLL_BAD_ARG, "d_records == NULL");
     if (int rc = enqueue_sweep(h)) return rc;
     if (cap_records) {
@@ -787,7 +822,7 @@ int alll_reset_stats(alll_handle h)
 int alll_p2p_create(alll_handle h, uint32_t world, uint32_t rank, uint64_t cap_records, uint8_t handle_out[64])
 {
     NEED_INSTANCE();
-    if (!h->k || h->k > 8) return fail(h, ALLL_BAD_ARG, "P2P sharding needs the fixed-width layout with k <= 8");
+    if (!h->k || h->k > 8 || h->use_width) return fail(h, ALLL_BAD_ARG, "P2P sharding needs uniform clause width k <= 8");
     if (world < 1 || world > MAX_SHARDS || rank >= world || !handle_out) return fail(h, ALLL_BAD_ARG, "bad world / rank");
     if (cap_records == 0) return fail(h, ALLL_BAD_ARG, "cap_records == 0");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");

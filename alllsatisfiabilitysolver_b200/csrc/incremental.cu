@@ -22,7 +22,7 @@ namespace alll {
 __global__ void __launch_bounds__(256) incr_count_rows_kernel(const uint32_t *__restrict__ planes, uint64_t m_pad, uint32_t k,
                                                                uint32_t stride, const BucketSeg *__restrict__ segs,
                                                                uint32_t n_buckets, uint32_t *__restrict__ occ_cnt,
-                                                               uint32_t *__restrict__ rows)
+                                                               uint32_t *__restrict__ rows, const uint8_t *__restrict__ width)
 {
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= m_pad) return;
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) incr_count_rows_kernel(const uint32_t *__
         if (j < k) {
             l = planes[(uint64_t)j * m_pad + p];
             if (j == 0) first = l;
-            if (valid) atomicAdd(&occ_cnt[l >> 1], 1u);
+            if (valid && (!width || j < width[p])) atomicAdd(&occ_cnt[l >> 1], 1u);      // padding literals are not occurrences
         }
         rows[p * stride + j] = valid ? l : 0u;
     }
@@ -122,14 +122,16 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_add_kernel(uint32_t *__restri
 
 __global__ void __launch_bounds__(256) incr_fill_kernel(const uint32_t *__restrict__ planes, uint64_t m_pad, uint32_t k,
                                                          const BucketSeg *__restrict__ segs, uint32_t n_buckets,
-                                                         uint32_t *__restrict__ cursor, uint32_t *__restrict__ occ)
+                                                         uint32_t *__restrict__ cursor, uint32_t *__restrict__ occ,
+                                                         const uint8_t *__restrict__ width)
 {
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= m_pad) return;
     uint32_t b = 0;
     while (b + 1 < n_buckets && (uint64_t)segs[b + 1].tile_begin * TILE <= p) ++b;
     if (p >= segs[b].slot_end) return;
-    for (uint32_t j = 0; j < k; j++) {
+    const uint32_t kw = width ? width[p] : k;
+    for (uint32_t j = 0; j < kw; j++) {
         const uint32_t v = planes[(uint64_t)j * m_pad + p] >> 1;
         occ[atomicAdd(&cursor[v], 1u)] = (uint32_t)p;
     }
@@ -203,18 +205,18 @@ static inline uint32_t blocks_for(uint64_t n, uint32_t t) { return (uint32_t)((n
 
 cudaError_t launch_incr_build(const uint32_t *planes, uint64_t m_pad, uint32_t k, uint32_t stride, const BucketSeg *segs,
                               uint32_t n_buckets, uint64_t n_vars, uint32_t *occ_off /*[n_vars+1]*/, uint32_t *cursor /*[n_vars]*/,
-                              uint32_t *block_sums, uint32_t *rows, uint32_t *occ, uint32_t *d_total, cudaStream_t s)
+                              uint32_t *block_sums, uint32_t *rows, uint32_t *occ, uint32_t *d_total, const uint8_t *width, cudaStream_t s)
 {
     cudaError_t e = cudaMemsetAsync(cursor, 0, n_vars * 4, s);       // cursor doubles as the occurrence counter
     if (e != cudaSuccess) return e;
-    if (m_pad) incr_count_rows_kernel<<<blocks_for(m_pad, 256), 256, 0, s>>>(planes, m_pad, k, stride, segs, n_buckets, cursor, rows);
+    if (m_pad) incr_count_rows_kernel<<<blocks_for(m_pad, 256), 256, 0, s>>>(planes, m_pad, k, stride, segs, n_buckets, cursor, rows, width);
     const uint32_t nb = blocks_for(n_vars, SCAN_BLOCK);
     scan_block_kernel<<<nb, SCAN_BLOCK, 0, s>>>(cursor, n_vars, occ_off, block_sums);
     scan_sums_kernel<<<1, SCAN_BLOCK, 0, s>>>(block_sums, nb, d_total);
     scan_add_kernel<<<nb, SCAN_BLOCK, 0, s>>>(occ_off, n_vars, block_sums, cursor);
     e = cudaMemcpyAsync(occ_off + n_vars, d_total, 4, cudaMemcpyDeviceToDevice, s);
     if (e != cudaSuccess) return e;
-    if (m_pad) incr_fill_kernel<<<blocks_for(m_pad, 256), 256, 0, s>>>(planes, m_pad, k, segs, n_buckets, cursor, occ);
+    if (m_pad) incr_fill_kernel<<<blocks_for(m_pad, 256), 256, 0, s>>>(planes, m_pad, k, segs, n_buckets, cursor, occ, width);
     return cudaGetLastError();
 }
 

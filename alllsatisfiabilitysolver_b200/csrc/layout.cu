@@ -83,7 +83,9 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) bucket_scatter_kernel(const ui
                                                                          const uint32_t *__restrict__ cta_base,
                                                                          uint32_t *__restrict__ planes, uint64_t m_pad,
                                                                          uint32_t *__restrict__ orig_id,
-                                                                         uint32_t *__restrict__ min_resident, uint32_t resident_cap)
+                                                                         uint32_t *__restrict__ min_resident, uint32_t resident_cap,
+                                                                         const uint8_t *__restrict__ width_in,
+                                                                         uint8_t *__restrict__ width_out)
 {
     __shared__ uint16_t warp_cnt[(LAYOUT_THREADS / 32) * MAX_BUCKETS];   // [warp][bucket], then exclusive over warps
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -112,6 +114,7 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) bucket_scatter_kernel(const ui
     if (!active) return;
     const uint64_t dst = (uint64_t)cta_base[(uint64_t)b * gridDim.x + blockIdx.x] + warp_cnt[warp * n_buckets + b] + rank;
     orig_id[dst] = (uint32_t)c;
+    if (width_in) width_out[dst] = width_in[c];
     const uint32_t lo = b * bucket_vars;
     // the first (at most resident_cap) bucket-resident literals go to the leading planes, original order kept;
     // everything else follows (a resident literal beyond the cap is simply looked up through L2 like the rest)
@@ -207,10 +210,11 @@ cudaError_t launch_bucket_count(const uint32_t *lit, uint64_t m, uint32_t k, uin
 
 cudaError_t launch_bucket_scatter(const uint32_t *lit, uint64_t m, uint32_t k, uint32_t bucket_vars, uint32_t n_buckets,
                                   const uint8_t *bkt, const uint32_t *cta_base, uint32_t *planes, uint64_t m_pad,
-                                  uint32_t *orig_id, uint32_t *min_resident, uint32_t resident_cap, cudaStream_t s)
+                                  uint32_t *orig_id, uint32_t *min_resident, uint32_t resident_cap, const uint8_t *width_in,
+                                  uint8_t *width_out, cudaStream_t s)
 {
     bucket_scatter_kernel<<<bucket_pass_ctas(m), LAYOUT_THREADS, 0, s>>>(lit, m, k, bucket_vars, n_buckets, bkt, cta_base,
-                                                                           planes, m_pad, orig_id, min_resident, resident_cap);
+                                                                           planes, m_pad, orig_id, min_resident, resident_cap, width_in, width_out);
     return cudaGetLastError();
 }
 

@@ -68,6 +68,7 @@ typedef struct {
  * is computed from the clauses containing them instead of a full sweep.  Results are bit-identical to the default
  * mode.  Bits 24..27: log2 of the switch-over divisor (default 3: incremental when <= m/8 clauses would be touched). */
 #define ALLL_FLAG_INCREMENTAL 4u
+#define ALLL_FLAG_FORCE_CSR 8u     /* keep ragged input on the CSR kernels instead of padding it onto the plane layout */
 #define ALLL_FLAG_INCR_DIVISOR_LOG2(x) ((uint32_t)(x) << 24)
 
 /* Statistics{} of SATInstance.h:25-32 plus device-side counters.
@@ -109,7 +110,9 @@ ALLL_API int alll_abi_version(void);
 ALLL_API int alll_upload_fixedk(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit);
 /* Same, literals already in device memory (row-major [m][k]); the buffer is only read during the call. */
 ALLL_API int alll_upload_fixedk_device(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *d_lit);
-/* Variable width: off[m+1] into lit[].  Uniform-width inputs are routed to the fixed-k layout. */
+/* Variable width: off[m+1] into lit[].  Uniform-width input is routed to the fixed-k layout; ragged input whose widest
+ * clause has <= 32 literals and whose padding at most doubles the literal count is padded onto the plane layout (a
+ * repeated literal never changes a clause's value; true widths are kept for the statistics); anything else uses CSR. */
 ALLL_API int alll_upload_csr(alll_handle h, uint64_t n_vars, uint64_t m, const uint64_t *off, const uint32_t *lit);
 
 /* ---- assignment (VariablesArray<T>::vars, VariablesArray.h:18-35; 1 byte per variable on the host) */

@@ -28,8 +28,9 @@ def upload(solver, n, off, lit):
 
 
 # a 1 KiB staging budget forces variable-range bucketing (8192 variables per bucket) at test sizes
-LAYOUTS = [dict(), dict(sweep_smem_bytes=1024), dict(sweep_smem_bytes=1024, flags=1)]
-LAYOUT_IDS = ["resident", "bucketed", "no_bucketing_gather"]
+# flags=8 keeps ragged input on the CSR kernels (by default it is padded onto the plane layout)
+LAYOUTS = [dict(), dict(sweep_smem_bytes=1024), dict(sweep_smem_bytes=1024, flags=1), dict(flags=8)]
+LAYOUT_IDS = ["resident", "bucketed", "no_bucketing_gather", "force_csr"]
 
 
 @pytest.mark.parametrize("layout", LAYOUTS, ids=LAYOUT_IDS)
@@ -307,7 +308,7 @@ def test_cfg3_beyond_lll_round_cap(capi, oracle):
 
 @pytest.mark.parametrize("layout", [dict(flags=4), dict(flags=4 | (1 << 24)), dict(flags=4, sweep_smem_bytes=1024)],
                          ids=["incremental", "incremental_div2", "incremental_bucketed"])
-@pytest.mark.parametrize("name", ["cfg1", "k7_small", "k8_small", "k3_uniform"])
+@pytest.mark.parametrize("name", ["cfg1", "k7_small", "k8_small", "k3_uniform", "ragged"])
 def test_incremental_mode_is_bit_identical(capi, oracle, golden, name, layout):
     """ALLL_FLAG_INCREMENTAL: violated sets come from the occurrence lists of the resampled
     variables once few variables are resampled; trajectory, Statistics and assignment must not change."""
@@ -332,4 +333,21 @@ def test_incremental_mode_is_bit_identical(capi, oracle, golden, name, layout):
             # the single-step calls keep working (always full sweeps) after an incremental solve
             cnt, ids = s.eval()
             assert np.array_equal(np.sort(ids), oracle.sweep(off, lit, v))
-    assert used > 0 or name == "k3_uniform"
+    assert used > 0 or name in ("k3_uniform", "ragged")
+
+
+def test_ragged_input_uses_padded_planes_by_default(capi, oracle, golden):
+    """Ragged DIMACS-style input (widths 1..8, duplicated and tautological literals) is padded onto the plane layout
+    (k = widest clause) unless ALLL_FLAG_FORCE_CSR is set; both routes give the oracle's trajectory."""
+    n, off, lit, assigns = golden_case(golden, "ragged")
+    for flags, want_k in ((0, 8), (8, 0)):
+        with capi.Solver(flags=flags) as s:
+            s.upload_csr(n, off, lit)
+            assert s.layout_info()["k"] == want_k
+            s.randomize(9)
+            v = oracle.randomize(n, 9)
+            for rnd in range(6):
+                u_o, s_o, r_o = oracle.round(n, off, lit, v, 9, rnd)
+                u_g, s_g, r_g = s.round(9, rnd)
+                assert np.array_equal(np.sort(u_g), u_o) and np.array_equal(np.sort(s_g), np.sort(s_o)) and r_g == r_o
+                assert np.array_equal(s.get_assignment(), v)
