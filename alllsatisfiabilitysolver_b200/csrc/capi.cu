@@ -53,6 +53,8 @@ struct alll_solver {
     unsigned long long *d_claim = nullptr;
     uint32_t *d_viol = nullptr, *d_s = nullptr, *d_ids_out = nullptr;
     uint8_t *d_state = nullptr, *d_bools = nullptr;
+    uint8_t *h_bools = nullptr;          // pinned staging for the 1-byte-per-variable boundary (grow-only)
+    size_t h_bools_cap = 0;
     uint8_t *d_width = nullptr, *d_width_in = nullptr;   // padded planes: true clause widths by slot / by caller id
     bool use_width = false;
     Counters *d_ctr = nullptr;
@@ -451,6 +453,7 @@ int alll_destroy(alll_handle h)
     if (h->d_ctr) cudaFree(h->d_ctr);
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
     if (h->h_ring) cudaFreeHost(h->h_ring);
+    if (h->h_bools) cudaFreeHost(h->h_bools);
     for (auto &ev : h->ev_round) if (ev) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -550,11 +553,24 @@ int alll_upload_csr(alll_handle h, uint64_t n_vars, uint64_t m, const uint64_t *
     return ALLL_OK;
 }
 
+// The caller's bool array is pageable memory: stage it through a pinned buffer (one fast memcpy + one DMA instead of
+// the driver's chunked pageable path).
+static int ensure_pinned_bools(alll_handle h)
+{
+    if (h->h_bools_cap >= h->n_vars) return ALLL_OK;
+    if (h->h_bools) { cudaFreeHost(h->h_bools); h->h_bools = nullptr; h->h_bools_cap = 0; }
+    CK(cudaMallocHost(&h->h_bools, h->n_vars));
+    h->h_bools_cap = h->n_vars;
+    return ALLL_OK;
+}
+
 int alll_set_assignment(alll_handle h, const uint8_t *bools)
 {
     NEED_INSTANCE();
     if (!bools) return fail(h, ALLL_BAD_ARG, "bools == NULL");
-    CK(cudaMemcpyAsync(h->d_bools, bools, h->n_vars, cudaMemcpyHostToDevice, h->stream));
+    if (int rc = ensure_pinned_bools(h)) return rc;
+    std::memcpy(h->h_bools, bools, h->n_vars);
+    CK(cudaMemcpyAsync(h->d_bools, h->h_bools, h->n_vars, cudaMemcpyHostToDevice, h->stream));
     CK(launch_pack_bits(h->d_bools, h->n_vars, h->d_bits, h->n_words_alloc, h->stream)); h->launches++;
     CK(cudaStreamSynchronize(h->stream));
     return ALLL_OK;
@@ -564,9 +580,11 @@ int alll_get_assignment(alll_handle h, uint8_t *bools)
 {
     NEED_INSTANCE();
     if (!bools) return fail(h, ALLL_BAD_ARG, "bools == NULL");
+    if (int rc = ensure_pinned_bools(h)) return rc;
     CK(launch_unpack_bits(h->d_bits, h->n_vars, h->d_bools, h->stream)); h->launches++;
-    CK(cudaMemcpyAsync(bools, h->d_bools, h->n_vars, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_bools, h->d_bools, h->n_vars, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    std::memcpy(bools, h->h_bools, h->n_vars);
     return ALLL_OK;
 }
 
