@@ -102,35 +102,17 @@ int main(int argc, char *argv[])
     output("Log " + now_string() + ": Reading CNF file\n", out_f, dump);
     auto start = chrono::high_resolution_clock::now();
 
-    int c_num = 0, v_num = 0, l_num = 0;
-    if (cnf_header_read(cnf_fpath, &v_num, &c_num, &l_num)) {
-        cout << "The header information could not be read. Exiting..." << endl;
+    // DIMACS -> CSR in one parallel pass (literal encoding x>0 -> 2x-2, -x -> 2x-1 as main.cpp:168); the reference
+    // builds n_threads batches of heap Clause objects here (main.cpp:133-178), which the device path would only
+    // flatten again.  The batch split has no effect on the result: global clause id = position in the file.
+    int v_num = 0, c_num = 0;
+    vector<uint64_t> off;
+    vector<uint32_t> lit;
+    if (cnf_read_csr(cnf_fpath, &v_num, &c_num, off, lit)) {
+        if (off.empty()) cout << "The header information could not be read. Exiting..." << endl;
+        else cout << "The clause data does not match the header. Exiting..." << endl;
         return 1;
     }
-    int *l_c_num = new int[c_num > 0 ? c_num : 1];
-    int *l_val = new int[l_num > 0 ? l_num : 1];
-    if (cnf_data_read(cnf_fpath, v_num, c_num, l_num, l_c_num, l_val)) {
-        cout << "The clause data does not match the header. Exiting..." << endl;
-        return 1;
-    }
-
-    // literal encoding x>0 -> 2x-2, -x -> 2x-1; n_threads batches of ceil(c/n_threads) clauses
-    const long long chunk = (c_num + (long long)n_threads - 1) / n_threads;
-    auto clauses = new vector<ClauseArray *>();
-    for (int t = 0; t < n_threads; t++) clauses->push_back(new ClauseArray());
-    long long l = 0;
-    for (int c = 0; c < c_num; c++) {
-        auto literals = new vector<UINT_T>;
-        literals->reserve((size_t)l_c_num[c]);
-        for (int j = 0; j < l_c_num[c]; j++, l++) {
-            const long long x = l_val[l];
-            literals->push_back((UINT_T)(x > 0 ? 2 * x - 2 : -2 * x - 1));
-        }
-        const unsigned short t = (unsigned short)std::min<long long>(chunk ? c / chunk : 0, n_threads - 1);
-        clauses->at(t)->push_back(new Clause<UINT_T>(literals, t));
-    }
-    delete[] l_c_num;
-    delete[] l_val;
 
     auto var_arr = have_seed ? new VariablesArray<UINT_T>((UINT_T)v_num, (unsigned long)seed) : new VariablesArray<UINT_T>((UINT_T)v_num);
     auto satInstance = new SATInstance<UINT_T>(var_arr, n_threads);
@@ -157,7 +139,7 @@ int main(int argc, char *argv[])
     start = chrono::high_resolution_clock::now();
     Statistics *statistics = nullptr;
     try {
-        statistics = satInstance->solve(clauses);
+        statistics = satInstance->solve_csr(off, lit);
     } catch (const std::exception &e) {
         output(string("ERROR: ") + e.what() + "\n", out_f, dump);
         return 1;
@@ -182,7 +164,7 @@ int main(int argc, char *argv[])
     int rc = 1;
     if (satInstance->last_status() == ALLL_MAX_ROUNDS) {
         output("UNKNOWN: round cap reached before all clauses were satisfied\n", out_f, dump);
-    } else if (satInstance->verify_validity(clauses)) {
+    } else if (satInstance->verify_validity_csr(off, lit)) {
         output("SATISFIABLE\n", out_f, dump);
         if (dump)
             for (ull i = 0; i < satInstance->n_vars; i++)

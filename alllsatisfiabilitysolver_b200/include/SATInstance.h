@@ -138,6 +138,26 @@ public:
     }
 
     // ---- extensions (not in the reference) --------------------------------------------------------------
+    // The same solve / verify on clauses that already are a CSR (off[m+1], lit[L], literal = 2*var+neg): no
+    // Clause object graph (Clause.h:17-28 costs ~120 B of heap per clause, main.cpp:157-178 builds it one `new`
+    // at a time).  cnf_read_csr (cli/cnf_io/cnf_io.h) produces this form straight from a DIMACS file.
+    Statistics *solve_csr(const vector<uint64_t> &off, const vector<uint32_t> &lit)
+    {
+        if (off.empty()) throw std::runtime_error("SATInstance::solve_csr: off must hold m+1 entries");
+        n_clauses = off.size() - 1;
+        upload_flat(off, lit);
+        return run_solve();
+    }
+    bool verify_validity_csr(const vector<uint64_t> &off, const vector<uint32_t> &lit) const
+    {
+        if (off.empty()) throw std::runtime_error("SATInstance::verify_validity_csr: off must hold m+1 entries");
+        auto *self = const_cast<SATInstance *>(this);
+        self->upload_flat(off, lit);
+        self->check(alll_set_assignment(handle, reinterpret_cast<const uint8_t *>(var_arr->vars)), "alll_set_assignment");
+        int valid = 0;
+        self->check(alll_verify(handle, &valid), "alll_verify");
+        return valid != 0;
+    }
     void set_seed(uint64_t s) { seed = s; have_seed = true; }          // reproducible rounds (Philox key)
     void set_max_rounds(uint64_t r) { max_rounds = r; }                // default: effectively unbounded
     void set_device(int ordinal) { device = ordinal; }                 // before the first solve/verify

@@ -81,6 +81,45 @@ def test_cnf_loader_fixes_the_reference_hazards(tmp_path):
     assert parse("p cnf 2 1\n1 3 0\n")["error"] is True                    # variable beyond V
 
 
+def test_cnf_loader_is_independent_of_how_the_file_is_cut_into_pieces(tmp_path):
+    """The loader cuts the body at line starts into one piece per thread; clauses that span lines, comment lines,
+    the '%' trailer and an unterminated tail must come out the same for every cut.  Also checks the cnf_read_csr
+    extension (CSR + 2*var+neg encoding, example/main.cpp:168) against the cnf_io API result."""
+    exe = build(str(tmp_path), "cnf_dump", [os.path.join(ROOT, "tests", "cpp", "cnf_dump.cpp"),
+                                            os.path.join(PKG, "cli", "cnf_io", "cnf_io.cpp")], extra=["-I" + os.path.join(PKG, "cli")])
+    rng = np.random.default_rng(5)
+    lines, clauses, cur = ["c head", "p cnf 50 400"], [], []
+    for _ in range(400):
+        width = int(rng.integers(1, 9))
+        cl = [int(v) * (1 if rng.random() < 0.5 else -1) for v in rng.integers(1, 51, size=width)]
+        clauses.append(cl)
+        toks = [str(x) for x in cl] + ["0"]
+        while toks:                                           # break clauses over lines at random places
+            take = int(rng.integers(1, len(toks) + 1))
+            cur += toks[:take]
+            toks = toks[take:]
+            if rng.random() < 0.6:
+                lines.append(("\t" if rng.random() < 0.2 else " ").join(cur))
+                cur = []
+                if rng.random() < 0.1:
+                    lines.append("c 1 2 3 0 not a clause")
+    lines.append(" ".join(cur + ["7", "-9"]))                  # unterminated tail: dropped
+    lines += ["%", "0", "1 2 0"]                               # trailer: ignored
+    path = tmp_path / "cut.cnf"
+    path.write_text("\n".join(lines))                          # and no final newline
+    exp_val = [x for cl in clauses for x in cl]
+    exp_cnt = [len(cl) for cl in clauses]
+    exp_lit = [2 * x - 2 if x > 0 else -2 * x - 1 for x in exp_val]
+    exp_off = [0] + list(np.cumsum(exp_cnt))
+    for threads, piece in ((1, 1 << 20), (3, 64), (8, 16), (64, 1)):
+        env = dict(os.environ, ALLL_CNF_THREADS=str(threads), ALLL_CNF_PIECE_BYTES=str(piece))
+        got = json.loads(subprocess.run([exe, str(path)], capture_output=True, text=True, check=True, env=env).stdout)
+        assert got["error"] is False and got["l_c_num"] == exp_cnt and got["l_val"] == exp_val, (threads, piece)
+        got = json.loads(subprocess.run([exe, str(path), "csr"], capture_output=True, text=True, check=True, env=env).stdout)
+        assert got["error"] is False and got["off"] == exp_off and got["lit"] == exp_lit, (threads, piece)
+        assert (got["v_num"], got["c_num"]) == (50, 400)
+
+
 def test_user_program_and_cli_build(cli, lib, tmp_path):
     """Compile-and-link check of the reference-style user program (it runs in the GPU suite)."""
     build(str(tmp_path), "dropin_user", [os.path.join(ROOT, "tests", "cpp", "dropin_user.cpp")],
