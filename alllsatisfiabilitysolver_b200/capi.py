@@ -31,7 +31,10 @@ SYMBOLS = [
     "alll_set_id_base", "alll_shard_sweep", "alll_shard_round", "alll_get_stats", "alll_reset_stats",
     "alll_batch_upload", "alll_batch_solve",
     "alll_p2p_create", "alll_p2p_connect", "alll_solve_p2p",
+    "alll_upload_generator", "alll_upload_builtin_generator", "alll_builtin_generator_clause",
 ]
+
+GEN_UNIFORM, GEN_BOUNDED = 0, 1
 
 
 class AlllError(RuntimeError):
@@ -96,6 +99,9 @@ def load() -> C.CDLL:
     L.alll_upload_fixedk.argtypes = [vp, u64, u64, u32, vp]
     L.alll_upload_fixedk_device.argtypes = [vp, u64, u64, u32, vp]
     L.alll_upload_csr.argtypes = [vp, u64, u64, vp, vp]
+    L.alll_upload_generator.argtypes = [vp, u64, u64, u32, vp, vp, u64]
+    L.alll_upload_builtin_generator.argtypes = [vp, u32, u64, u64, u32, u64, u32, u64]
+    L.alll_builtin_generator_clause.argtypes = [u32, u64, u64, u32, u64, u32, u64, vp]
     L.alll_set_assignment.argtypes = [vp, vp]
     L.alll_get_assignment.argtypes = [vp, vp]
     L.alll_randomize.argtypes = [vp, u64]
@@ -175,6 +181,16 @@ class Solver:
         lit = np.ascontiguousarray(lit, np.uint32)
         m = len(off) - 1
         self._check(self.lib.alll_upload_csr(self.h, n_vars, m, off.ctypes.data, lit.ctypes.data if len(lit) else None))
+        self.n_vars, self.m = n_vars, m
+
+    def upload_builtin_generator(self, kind: int, n_vars: int, m: int, k: int, seed: int, d: int = 0, cap_records: int = 0):
+        """Enumerated clauses (SATInstance.h:70-153): clause i is a pure function of i, nothing is stored."""
+        self._check(self.lib.alll_upload_builtin_generator(self.h, kind, n_vars, m, k, seed, d, cap_records))
+        self.n_vars, self.m = n_vars, m
+
+    def upload_generator(self, n_vars: int, m: int, k: int, launch_fn: int, user: int = 0, cap_records: int = 0):
+        """``launch_fn``: address of an ``alll_gen_launch_fn`` exported by a user-built CUDA library."""
+        self._check(self.lib.alll_upload_generator(self.h, n_vars, m, k, launch_fn, user, cap_records))
         self.n_vars, self.m = n_vars, m
 
     # -- assignment ---------------------------------------------------------------------
@@ -300,3 +316,17 @@ class Solver:
         info = (C.c_uint64 * 6)()
         self._check(self.lib.alll_layout_info(self.h, info))
         return dict(m=info[0], k=info[1], n_buckets=info[2], m_padded=info[3], literal_bytes=info[4], sweep_smem_bytes=info[5])
+
+
+def builtin_generator_clauses(kind: int, n_vars: int, m: int, k: int, seed: int, d: int = 0, indices=None) -> np.ndarray:
+    """Host evaluation of a built-in generator (no GPU needed): the (len(indices), k) literal matrix."""
+    lib = load()
+    idx = np.arange(m, dtype=np.uint64) if indices is None else np.asarray(indices, np.uint64)
+    out = np.empty((len(idx), k), np.uint32)
+    row = np.empty(k, np.uint32)
+    for r, i in enumerate(idx):
+        rc = lib.alll_builtin_generator_clause(kind, n_vars, m, k, seed, d, int(i), row.ctypes.data)
+        if rc != OK:
+            raise AlllError(rc, "alll_builtin_generator_clause")
+        out[r] = row
+    return out

@@ -109,6 +109,9 @@ struct ClauseView {
     uint32_t id_base;
     // padded planes (ragged input laid out with k = widest clause): true width per slot, NULL when all equal k
     const uint8_t *width_arr;
+    // enumerated clauses (rec != NULL; k = width): only the violated ones exist, as records {index, k literals} that the
+    // generator sweep of this round wrote; "slot" p is the record number
+    const uint32_t *rec;
 
     __device__ __forceinline__ uint32_t width(uint32_t p) const
     {
@@ -116,9 +119,14 @@ struct ClauseView {
     }
     __device__ __forceinline__ uint32_t literal(uint32_t p, uint32_t j) const
     {
+        if (rec) return rec[(uint64_t)p * (k + 1) + 1 + j];
         return k ? planes[(uint64_t)j * m_pad + p] : csr_lit[off[p] + j];
     }
-    __device__ __forceinline__ uint32_t id(uint32_t p) const { return (orig_id ? orig_id[p] : p) + id_base; }
+    __device__ __forceinline__ uint32_t id(uint32_t p) const
+    {
+        if (rec) return rec[(uint64_t)p * (k + 1)];
+        return (orig_id ? orig_id[p] : p) + id_base;
+    }
 };
 
 // Device-side counters of one handle.
@@ -141,7 +149,7 @@ struct Counters {
     // behind it return immediately, so the round loop never has to wait for the host between rounds
     unsigned int done;
     unsigned int cta_done;      // sweep CTAs that have finished (sharded P2P mode: the last one publishes the round)
-    unsigned int p2p_error;     // 1: capacity overflow, 2: a peer did not arrive in time
+    unsigned int p2p_error;     // 1: capacity overflow (P2P exchange region / enumerated-clause record buffer), 2: a peer did not arrive in time
     unsigned int handled_tag;   // sharded P2P mode: tag of the last round an MIS kernel has completed
     // incremental re-evaluation: decided by the MIS kernel at the end of a round for the NEXT round
     unsigned int incr_next;     // 1: the next violated set comes from incr_eval_kernel, the sweep kernel returns at entry

@@ -1,6 +1,7 @@
 // alll_host.h -- launcher prototypes shared between the kernel translation units and the C ABI.
 #pragma once
 
+#include "../../include/alll_b200.h"
 #include "alll_device.cuh"
 
 namespace alll {
@@ -20,10 +21,18 @@ cudaError_t launch_mis_resample_args(const ClauseView &cv, uint32_t kmax, const 
                                      uint32_t *s_slots, unsigned long long *claim, uint64_t n_vars, uint32_t *bits,
                                      Counters *ctr, uint64_t seed, uint32_t round, uint32_t grid, bool with_grid,
                                      RoundNote *note, unsigned long long seq, const P2PLink *p2p, uint32_t p2p_parity,
-                                     uint32_t p2p_tag, uint32_t incr_max_vars, cudaStream_t s);
+                                     uint32_t p2p_tag, uint32_t incr_max_vars, uint32_t u_cap, cudaStream_t s);
 cudaError_t launch_reset_counters(Counters *c, int reset_totals, cudaStream_t s);
-cudaError_t launch_map_ids(const uint32_t *slots, const uint32_t *orig_id, uint32_t id_base, uint32_t n, uint32_t *out,
-                           cudaStream_t s);
+cudaError_t launch_map_ids(const ClauseView &cv, const uint32_t *slots, uint32_t n, uint32_t *out, cudaStream_t s);   // slots == NULL: identity
+
+// generator.cu (built-in clause generators of the enumerated-clause mode)
+struct BuiltinGenerator;
+const char *builtin_generator_create(uint32_t kind, uint64_t n_vars, uint64_t m, uint32_t k, uint64_t seed, uint32_t d,
+                                     BuiltinGenerator **out);       // NULL on success, else the error text
+void builtin_generator_destroy(BuiltinGenerator *g);
+int builtin_generator_launch(void *user, const alll_gen_sweep_args *a, void *stream);
+const char *builtin_generator_clause(uint32_t kind, uint64_t n_vars, uint64_t m, uint32_t k, uint64_t seed, uint32_t d,
+                                     uint64_t index, uint32_t *lits);
 
 // shard.cu
 cudaError_t launch_export_records(const ClauseView &cv, const uint32_t *viol, const Counters *ctr, uint32_t *records,

@@ -97,6 +97,13 @@ struct alll_solver {
     int *d_b_winner = nullptr;
     uint8_t *d_tmp_bkt = nullptr;
     uint32_t *d_tmp_cnt = nullptr, *d_tmp_err = nullptr, *d_stage = nullptr;
+    // enumerated clauses (alll_upload_generator): nothing stored but the violated records of the current round
+    bool gen_mode = false;
+    alll_gen_launch_fn gen_launch = nullptr;
+    void *gen_user = nullptr;
+    BuiltinGenerator *gen_builtin = nullptr;   // owned (alll_upload_builtin_generator)
+    uint32_t *d_gen_rec = nullptr;
+    uint64_t gen_cap = 0;
 };
 
 namespace {
@@ -127,6 +134,10 @@ void free_instance(alll_handle h)
     h->use_orig_id = false;
     h->use_width = false;
     h->incr_ready = false;
+    h->gen_mode = false;
+    h->gen_launch = nullptr;
+    h->gen_user = nullptr;
+    if (h->gen_builtin) { builtin_generator_destroy(h->gen_builtin); h->gen_builtin = nullptr; }
 }
 
 void release_buffers(alll_handle h)
@@ -142,6 +153,8 @@ void release_buffers(alll_handle h)
         if (h->p2p_peer[q]) { cudaIpcCloseMemHandle(h->p2p_peer[q]); h->p2p_peer[q] = nullptr; }
     dfree(h->d_p2p_region); dfree(h->d_p2p_link);
     dfree(h->d_occ_off); dfree(h->d_occ); dfree(h->d_rows); dfree(h->d_visited); dfree(h->d_incr_tmp);
+    dfree(h->d_gen_rec);
+    free_instance(h);
     h->incr_ready = false;
     h->p2p_ready = false;
     h->caps.clear();
@@ -178,13 +191,15 @@ ClauseView clause_view(alll_handle h)
     cv.off = h->d_off; cv.csr_lit = h->d_csr_lit; cv.orig_id = h->use_orig_id ? h->d_orig_id : nullptr;
     cv.id_base = h->id_base;
     cv.width_arr = h->use_width ? h->d_width : nullptr;
+    cv.rec = h->gen_mode ? h->d_gen_rec : nullptr;
     return cv;
 }
 
 // Buffers every instance needs regardless of the clause layout.
-int alloc_common(alll_handle h)
+// list_cap: the largest violated set the per-round lists must hold (m for stored clauses).
+int alloc_common(alll_handle h, uint64_t list_cap)
 {
-    const uint64_t m1 = std::max<uint64_t>(h->m, 1), n1 = std::max<uint64_t>(h->n_vars, 1);
+    const uint64_t m1 = std::max<uint64_t>(list_cap, 1), n1 = std::max<uint64_t>(h->n_vars, 1);
     POOL(h->d_bits, (size_t)std::max<uint32_t>(h->n_words_alloc, 4) * 4);
     CK(cudaMemsetAsync(h->d_bits, 0, (size_t)std::max<uint32_t>(h->n_words_alloc, 4) * 4, h->stream));
     POOL(h->d_claim, 2 * n1 * 8);                          // two claim arrays: even / odd Luby steps
@@ -301,7 +316,7 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     if (h->n_buckets > 1 && m > 0 && err_out[1] != 0xFFFFFFFFu) h->min_resident = err_out[1];
 
     h->use_width = d_width_in != nullptr && m > 0;
-    if (int rc = alloc_common(h)) return rc;
+    if (int rc = alloc_common(h, h->m)) return rc;
     SweepParams sp{};
     sp.bucket_words = h->bucket_words; sp.k = k; sp.min_resident = h->min_resident; sp.resident_cap = h->resident_cap; sp.eager = (h->flags >> 8) & 0xFFu; sp.prefetch_tiles = prefetch_distance(h->flags);
     CK(configure_sweep_planes(sp, h->resident_all));
@@ -339,6 +354,17 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
 // p2p_tag != 0: sharded P2P mode -- violated records are stored into every GPU's exchange region.
 int enqueue_sweep(alll_handle h, uint32_t p2p_parity = 0, uint32_t p2p_tag = 0)
 {
+    if (h->gen_mode) {
+        if (h->m == 0) return ALLL_OK;
+        alll_gen_sweep_args a{};
+        a.bits = h->d_bits; a.m = h->m; a.k = h->k; a.grid_hint = (uint32_t)h->sm_count * 8u;
+        a.records = h->d_gen_rec; a.cap = h->gen_cap;
+        a.n_violated = &h->d_ctr->n_viol; a.skip = &h->d_ctr->done;
+        const int e = h->gen_launch(h->gen_user, &a, (void *)h->stream);
+        if (e != 0) return fail(h, ALLL_CUDA_ERROR, std::string("generator sweep launch: ") + cudaGetErrorString((cudaError_t)e));
+        h->launches++;
+        return ALLL_OK;
+    }
     if (h->k) {
         if (h->n_tiles == 0 && !p2p_tag) return ALLL_OK;      // (a P2P rank without clauses still has to publish its round)
         SweepParams sp{};
@@ -362,9 +388,10 @@ int enqueue_sweep(alll_handle h, uint32_t p2p_parity = 0, uint32_t p2p_tag = 0)
 int enqueue_mis_resample(alll_handle h, uint64_t seed, uint32_t round, bool with_grid = true, RoundNote *note = nullptr,
                          unsigned long long seq = 0, bool allow_incremental = false)
 {
-    CK(launch_mis_resample_args(clause_view(h), h->kmax, h->d_viol, h->d_state, h->d_s, h->d_claim, h->n_vars,
-                                h->d_bits, h->d_ctr, seed, round, h->mis_grid, with_grid, note, seq, nullptr, 0u, 0u,
-                                (allow_incremental && h->incr_ready) ? h->incr_max_vars : 0u, h->stream));
+    CK(launch_mis_resample_args(clause_view(h), h->kmax, h->gen_mode ? nullptr : h->d_viol, h->d_state, h->d_s, h->d_claim,
+                                h->n_vars, h->d_bits, h->d_ctr, seed, round, h->mis_grid, with_grid, note, seq, nullptr, 0u, 0u,
+                                (allow_incremental && h->incr_ready) ? h->incr_max_vars : 0u,
+                                h->gen_mode ? (uint32_t)h->gen_cap : 0u, h->stream));
     h->launches += with_grid ? 2 : 1;    // cluster kernel (+ cooperative grid kernel)
     return ALLL_OK;
 }
@@ -381,7 +408,7 @@ int copy_ids_out(alll_handle h, const uint32_t *d_slots, uint64_t n, uint32_t *o
 {
     const uint64_t n_copy = std::min(n, cap);
     if (!out || n_copy == 0) return ALLL_OK;
-    CK(launch_map_ids(d_slots, h->use_orig_id ? h->d_orig_id : nullptr, h->id_base, (uint32_t)n_copy, h->d_ids_out, h->stream)); h->launches++;
+    CK(launch_map_ids(clause_view(h), d_slots, (uint32_t)n_copy, h->d_ids_out, h->stream)); h->launches++;
     CK(cudaMemcpyAsync(out, h->d_ids_out, n_copy * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return ALLL_OK;
@@ -547,7 +574,7 @@ int alll_upload_csr(alll_handle h, uint64_t n_vars, uint64_t m, const uint64_t *
     CK(cudaMemcpyAsync(&err_flags, d_err, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (err_flags) { free_instance(h); return fail(h, ALLL_BAD_ARG, "a literal references a variable >= n_vars"); }
-    if (int rc = alloc_common(h)) return rc;
+    if (int rc = alloc_common(h, h->m)) return rc;
     CK(cudaStreamSynchronize(h->stream));
     h->has_instance = true;
     return ALLL_OK;
@@ -555,6 +582,57 @@ int alll_upload_csr(alll_handle h, uint64_t n_vars, uint64_t m, const uint64_t *
 
 // The caller's bool array is pageable memory: stage it through a pinned buffer (one fast memcpy + one DMA instead of
 // the driver's chunked pageable path).
+// ---- enumerated clauses (SATInstance.h:70-153): nothing is stored, the caller's kernel launcher is the instance ----
+
+static int upload_generator_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, alll_gen_launch_fn launch, void *user,
+                                 uint64_t cap_records)
+{
+    if (int rc = check_sizes(h, n_vars, m)) return rc;
+    if (k < 1 || k > MAX_K) return fail(h, ALLL_BAD_ARG, "k must be in [1, 32]");
+    if (!launch) return fail(h, ALLL_BAD_ARG, "launch == NULL");
+    h->n_vars = n_vars; h->m = m; h->k = k; h->kmax = k;
+    h->n_words_alloc = (uint32_t)align_up((n_vars + 31) / 32, 4);
+    h->n_buckets = 1; h->bucket_words = 0; h->resident_all = false; h->m_pad = 0; h->n_tiles = 0; h->min_resident = 0;
+    h->gen_cap = std::min<uint64_t>(cap_records ? cap_records : m, std::max<uint64_t>(m, 1));
+    h->gen_cap = std::min<uint64_t>(std::max<uint64_t>(h->gen_cap, 1), 0xFFFFFFF0ull);
+    POOL(h->d_gen_rec, h->gen_cap * (k + 1) * 4);
+    h->gen_mode = true; h->gen_launch = launch; h->gen_user = user;
+    if (int rc = alloc_common(h, h->gen_cap)) { free_instance(h); return rc; }
+    CK(cudaStreamSynchronize(h->stream));
+    h->has_instance = true;
+    return ALLL_OK;
+}
+
+int alll_upload_generator(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, alll_gen_launch_fn launch, void *user,
+                          uint64_t cap_records)
+{
+    if (!h) return ALLL_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    free_instance(h);
+    return upload_generator_impl(h, n_vars, m, k, launch, user, cap_records);
+}
+
+int alll_upload_builtin_generator(alll_handle h, uint32_t kind, uint64_t n_vars, uint64_t m, uint32_t k, uint64_t seed,
+                                  uint32_t d, uint64_t cap_records)
+{
+    if (!h) return ALLL_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    free_instance(h);
+    BuiltinGenerator *g = nullptr;
+    if (const char *e = builtin_generator_create(kind, n_vars, m, k, seed, d, &g)) return fail(h, ALLL_BAD_ARG, e);
+    const int rc = upload_generator_impl(h, n_vars, m, k, builtin_generator_launch, g, cap_records);
+    if (rc != ALLL_OK) { builtin_generator_destroy(g); return rc; }
+    h->gen_builtin = g;
+    return ALLL_OK;
+}
+
+int alll_builtin_generator_clause(uint32_t kind, uint64_t n_vars, uint64_t m, uint32_t k, uint64_t seed, uint32_t d,
+                                  uint64_t index, uint32_t *lits)
+{
+    if (!lits) return ALLL_BAD_ARG;
+    return builtin_generator_clause(kind, n_vars, m, k, seed, d, index, lits) ? ALLL_BAD_ARG : ALLL_OK;
+}
+
 static int ensure_pinned_bools(alll_handle h)
 {
     if (h->h_bools_cap >= h->n_vars) return ALLL_OK;
@@ -603,9 +681,12 @@ int alll_eval(alll_handle h, uint32_t *ids, uint64_t cap, uint64_t *n_violated)
     if (int rc = fetch_counters(h)) return rc;
     const uint64_t n = h->h_ctr->n_viol;
     if (n_violated) *n_violated = n;
-    if (int rc = copy_ids_out(h, h->d_viol, n, ids, cap)) return rc;
+    const bool overflow = h->gen_mode && n > h->gen_cap;
+    if (!overflow)
+        if (int rc = copy_ids_out(h, h->gen_mode ? nullptr : h->d_viol, n, ids, cap)) return rc;
     CK(launch_reset_counters(h->d_ctr, 0, h->stream)); h->launches++;
     CK(cudaStreamSynchronize(h->stream));
+    if (overflow) return fail(h, ALLL_CAPACITY, "violated set exceeds cap_records of the enumerated instance");
     return ALLL_OK;
 }
 
@@ -625,10 +706,15 @@ int alll_round(alll_handle h, uint64_t seed, uint32_t round, uint32_t *u_ids, ui
     if (int rc = enqueue_mis_resample(h, seed, round)) return rc;
     if (int rc = fetch_counters(h)) return rc;
     const Counters &c = *h->h_ctr;
+    if (c.p2p_error) {                                        // enumerated clauses: the records of this round did not fit
+        CK(launch_reset_counters(h->d_ctr, 0, h->stream)); h->launches++;
+        CK(cudaStreamSynchronize(h->stream));
+        return fail(h, ALLL_CAPACITY, "violated set exceeds cap_records of the enumerated instance");
+    }
     if (n_u) *n_u = c.last_n_viol;
     if (n_s) *n_s = c.last_n_s;
     if (n_resampled) *n_resampled = c.last_resampled;
-    if (int rc = copy_ids_out(h, h->d_viol, c.last_n_viol, u_ids, u_cap)) return rc;
+    if (int rc = copy_ids_out(h, h->gen_mode ? nullptr : h->d_viol, c.last_n_viol, u_ids, u_cap)) return rc;
     if (int rc = copy_ids_out(h, h->d_s, c.last_n_s, s_ids, s_cap)) return rc;
     return ALLL_OK;
 }
@@ -703,6 +789,7 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
         retired++;
         last_seen_u = h->h_ring[slot].n_viol;
         if (last_seen_u == 0) { status = ALLL_OK; break; }                    // SATInstance.h:285-287
+        if (last_seen_u == 0xFFFFFFFFu) { status = ALLL_CAPACITY; break; }    // enumerated clauses: records did not fit
     }
     const uint64_t useful_rounds = retired;              // rounds whose sweep actually ran (incl. the terminal one)
     h->seq = seq0 + issued;
@@ -736,6 +823,7 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
     stats->sweep_ms = timed ? sweep_ms * ((double)c.n_iterations / timed) : 0.0;
     stats->between_sweeps_ms = timed > 1 ? between_ms * ((double)(c.n_iterations - 1) / (timed - 1)) : 0.0;
     stats->status = status;
+    if (status == ALLL_CAPACITY) return fail(h, ALLL_CAPACITY, "violated set exceeds cap_records of the enumerated instance");
     return status;
 }
 
@@ -752,7 +840,7 @@ int alll_set_id_base(alll_handle h, uint64_t id_base)
 int alll_shard_sweep(alll_handle h, uint32_t *d_records, uint64_t cap_records, uint64_t *n_local)
 {
     NEED_INSTANCE();
-    if (!h->k || h->use_width) return fail(h, ALLL_BAD_ARG, "sharded mode needs uniform clause width");
+    if (!h->k || h->use_width || h->gen_mode) return fail(h, ALLL_BAD_ARG, "sharded mode needs stored clauses of uniform width");
     if (!d_records && cap_records) return fail(h, ALLL_BAD_ARG, "d_records == NULL");
     if (int rc = enqueue_sweep(h)) return rc;
     if (cap_records) {
@@ -773,7 +861,7 @@ int alll_shard_round(alll_handle h, const uint32_t *d_records, const uint64_t *c
                      uint64_t *n_resampled)
 {
     NEED_INSTANCE();
-    if (!h->k) return fail(h, ALLL_BAD_ARG, "sharded mode needs the fixed-width layout");
+    if (!h->k || h->gen_mode) return fail(h, ALLL_BAD_ARG, "sharded mode needs the fixed-width layout");
     if (!counts || n_blocks == 0 || n_blocks > MAX_SHARDS) return fail(h, ALLL_BAD_ARG, "bad shard count");
     uint32_t prefix[MAX_SHARDS + 1];
     uint64_t total = 0;
@@ -798,7 +886,7 @@ int alll_shard_round(alll_handle h, const uint32_t *d_records, const uint64_t *c
     ClauseView cv{};
     cv.planes = h->d_sh_planes; cv.m_pad = cap; cv.k = h->k; cv.orig_id = h->d_sh_ids; cv.id_base = 0;
     CK(launch_mis_resample_args(cv, h->k, h->d_sh_iota, h->d_sh_state, h->d_sh_s, h->d_claim, h->n_vars, h->d_bits,
-                                h->d_ctr, seed, round, h->mis_grid, total > MIS_CLUSTER_MAX_U, nullptr, 0ull, nullptr, 0u, 0u, 0u, h->stream));
+                                h->d_ctr, seed, round, h->mis_grid, total > MIS_CLUSTER_MAX_U, nullptr, 0ull, nullptr, 0u, 0u, 0u, 0u, h->stream));
     h->launches += total > MIS_CLUSTER_MAX_U ? 2 : 1;
     if (int rc = fetch_counters(h)) return rc;
     const Counters &c = *h->h_ctr;
@@ -840,7 +928,7 @@ int alll_reset_stats(alll_handle h)
 int alll_p2p_create(alll_handle h, uint32_t world, uint32_t rank, uint64_t cap_records, uint8_t handle_out[64])
 {
     NEED_INSTANCE();
-    if (!h->k || h->k > 8 || h->use_width) return fail(h, ALLL_BAD_ARG, "P2P sharding needs uniform clause width k <= 8");
+    if (!h->k || h->k > 8 || h->use_width || h->gen_mode) return fail(h, ALLL_BAD_ARG, "P2P sharding needs stored clauses of uniform width k <= 8");
     if (world < 1 || world > MAX_SHARDS || rank >= world || !handle_out) return fail(h, ALLL_BAD_ARG, "bad world / rank");
     if (cap_records == 0) return fail(h, ALLL_BAD_ARG, "cap_records == 0");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -921,7 +1009,7 @@ int alll_solve_p2p(alll_handle h, uint64_t seed, uint64_t max_rounds, uint64_t m
             const bool with_grid = last_seen_u > MIS_CLUSTER_MAX_U;
             CK(launch_mis_resample_args(cv, h->k, nullptr, h->d_sh_state, h->d_sh_s, h->d_claim, h->n_vars, h->d_bits,
                                         h->d_ctr, seed, (uint32_t)issued, h->mis_grid, with_grid, &h->h_ring[slot],
-                                        seq0 + issued + 1, h->d_p2p_link, parity, tag, 0u, h->stream));
+                                        seq0 + issued + 1, h->d_p2p_link, parity, tag, 0u, 0u, h->stream));
             h->launches += with_grid ? 2 : 1;
             CK(cudaEventRecord(h->ev_round[slot], h->stream));
             issued++;

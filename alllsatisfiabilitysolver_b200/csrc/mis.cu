@@ -69,6 +69,7 @@ struct MisParams {
     const P2PLink *p2p;
     uint32_t p2p_parity, p2p_tag;
     uint32_t incr_max_vars;     // incremental mode: next round is incremental iff this round resampled <= this many variables (0 = off)
+    uint32_t u_cap;             // enumerated clauses: records the sweep could store (0 = no limit); a larger |U| aborts the solve
 };
 
 extern __shared__ uint32_t mis_smem[];
@@ -114,7 +115,7 @@ __device__ __forceinline__ Item open_item(const MisParams &p, const uint32_t *pr
         x.slot = i;
     } else {
         x.rec = nullptr;
-        x.slot = p.viol[i];
+        x.slot = p.viol ? p.viol[i] : i;          // (enumerated clauses: U is the record buffer itself)
     }
     if (it < p.cache_items) {
         x.base = it * slotw * blockDim.x + threadIdx.x;
@@ -431,9 +432,10 @@ __global__ void __cluster_dims__(CL_SIZE, 1, 1) __launch_bounds__(CL_THREADS) mi
     if (ld_u32(&p.ctr->done)) return;             // speculative round behind the terminal one
     // |U|: left by the sweep kernel that ran before us, or (sharded P2P mode) the sum over all ranks' record blocks
     const uint32_t n_u = p.p2p ? p2p_wait(p, s_prefix) : ld_u32(&p.ctr->n_viol);
-    if (n_u == 0xFFFFFFFFu) {                     // a peer overflowed or never arrived: stop the solve
+    if (n_u == 0xFFFFFFFFu || (p.u_cap && n_u > p.u_cap)) {   // a peer overflowed or never arrived / records did not fit: stop the solve
         if (blockIdx.x == 0 && threadIdx.x == 0) {
-            p.ctr->p2p_error = p.ctr->p2p_error ? p.ctr->p2p_error : 2;
+            p.ctr->p2p_error = p.ctr->p2p_error ? p.ctr->p2p_error : (n_u == 0xFFFFFFFFu ? 2 : 1);
+            p.ctr->n_viol = 0;
             p.ctr->done = 1;
             announce(p, 0xFFFFFFFFu, 0u);
         }
@@ -504,10 +506,10 @@ __global__ void reset_counters_kernel(Counters *c, int reset_totals)
 }
 
 // slots -> caller clause ids (for alll_eval / alll_round outputs)
-__global__ void map_ids_kernel(const uint32_t *slots, const uint32_t *orig_id, uint32_t id_base, uint32_t n, uint32_t *out)
+__global__ void map_ids_kernel(const ClauseView cv, const uint32_t *slots, uint32_t n, uint32_t *out)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (orig_id ? orig_id[slots[i]] : slots[i]) + id_base;
+    if (i < n) out[i] = cv.id(slots ? slots[i] : i);
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -547,10 +549,10 @@ cudaError_t launch_mis_resample_args(const ClauseView &cv, uint32_t kmax, const 
                                      uint32_t *s_slots, unsigned long long *claim, uint64_t n_vars, uint32_t *bits,
                                      Counters *ctr, uint64_t seed, uint32_t round, uint32_t grid, bool with_grid,
                                      RoundNote *note, unsigned long long seq, const P2PLink *p2p, uint32_t p2p_parity,
-                                     uint32_t p2p_tag, uint32_t incr_max_vars, cudaStream_t s)
+                                     uint32_t p2p_tag, uint32_t incr_max_vars, uint32_t u_cap, cudaStream_t s)
 {
     MisParams p{cv, viol, state, s_slots, claim, n_vars, bits, ctr, seed, round, kmax, cluster_cache_items(kmax),
-                with_grid ? 1u : 0u, note, seq, p2p, p2p_parity, p2p_tag, incr_max_vars};
+                with_grid ? 1u : 0u, note, seq, p2p, p2p_parity, p2p_tag, incr_max_vars, u_cap};
     mis_cluster_kernel<<<CL_SIZE, CL_THREADS, cluster_smem_bytes(kmax), s>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || !with_grid) return e;
@@ -566,11 +568,10 @@ cudaError_t launch_reset_counters(Counters *c, int reset_totals, cudaStream_t s)
     return cudaGetLastError();
 }
 
-cudaError_t launch_map_ids(const uint32_t *slots, const uint32_t *orig_id, uint32_t id_base, uint32_t n, uint32_t *out,
-                           cudaStream_t s)
+cudaError_t launch_map_ids(const ClauseView &cv, const uint32_t *slots, uint32_t n, uint32_t *out, cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
-    map_ids_kernel<<<(n + 255) / 256, 256, 0, s>>>(slots, orig_id, id_base, n, out);
+    map_ids_kernel<<<(n + 255) / 256, 256, 0, s>>>(cv, slots, n, out);
     return cudaGetLastError();
 }
 

@@ -158,6 +158,30 @@ public:
         self->check(alll_verify(handle, &valid), "alll_verify");
         return valid != 0;
     }
+    // Enumerated clauses produced ON THE DEVICE.  The reference's callback form above hands out heap Clause objects
+    // from host code, which cannot run inside a kernel; its device-side equivalent is a functor compiled into the
+    // sweep kernel of include/alll_generator.cuh, passed here by its launcher (see tests/cpp/user_generator.cu).
+    // Nothing is stored or materialised: n_clauses may exceed what fits in memory as a literal array.
+    Statistics *solve_generator(alll_gen_launch_fn launch, void *user, ull n_clauses, unsigned k, ull cap_records = 0)
+    {
+        this->n_clauses = n_clauses;
+        ensure_handle();
+        check(alll_upload_generator(handle, (uint64_t)n_vars, n_clauses, k, launch, user, cap_records), "alll_upload_generator");
+        have_upload = false;
+        return run_solve();
+    }
+    bool verify_validity_generator(alll_gen_launch_fn launch, void *user, ull n_clauses, unsigned k, ull cap_records = 0) const
+    {
+        auto *self = const_cast<SATInstance *>(this);
+        self->ensure_handle();
+        self->check(alll_upload_generator(handle, (uint64_t)n_vars, n_clauses, k, launch, user, cap_records), "alll_upload_generator");
+        self->have_upload = false;
+        self->check(alll_set_assignment(handle, reinterpret_cast<const uint8_t *>(var_arr->vars)), "alll_set_assignment");
+        int valid = 0;
+        self->check(alll_verify(handle, &valid), "alll_verify");
+        return valid != 0;
+    }
+
     void set_seed(uint64_t s) { seed = s; have_seed = true; }          // reproducible rounds (Philox key)
     void set_max_rounds(uint64_t r) { max_rounds = r; }                // default: effectively unbounded
     void set_device(int ordinal) { device = ordinal; }                 // before the first solve/verify

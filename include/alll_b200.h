@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ALLL_ABI_VERSION 3
+#define ALLL_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define ALLL_API __attribute__((visibility("default")))
@@ -114,6 +114,53 @@ ALLL_API int alll_upload_fixedk_device(alll_handle h, uint64_t n_vars, uint64_t 
  * clause has <= 32 literals and whose padding at most doubles the literal count is padded onto the plane layout (a
  * repeated literal never changes a clause's value; true widths are kept for the statistics); anything else uses CSR. */
 ALLL_API int alll_upload_csr(alll_handle h, uint64_t n_vars, uint64_t m, const uint64_t *off, const uint32_t *lit);
+
+/* ---- enumerated clauses -------------------------------------------------------------------
+ * Replaces SATInstance::solve(Clause<T>* (*)(T, unsigned short), ull n_clauses, T batch_size), SATInstance.h:70-153,
+ * and the ClauseGenerator that feeds it (ClauseGenerator.h:16-114): the clauses are a pure function of their index and
+ * are never stored.  A host callback cannot run on the device, so the device-side form of that callback is a functor
+ * the user compiles into a sweep kernel with include/alll_generator.cuh (templates in a header: no device linking
+ * across shared libraries); the library is handed the LAUNCHER of that kernel.  Every round the launcher is asked to
+ * evaluate all m clauses against the bit-packed assignment and to append {index, k literals} of the violated ones to
+ * `records`; the independent-set and resample kernels then work on those records.  Everything else (alll_randomize,
+ * alll_set/get_assignment, alll_eval, alll_verify, alll_round, alll_solve, statistics) behaves as for stored clauses. */
+typedef struct alll_gen_sweep_args {
+    const uint32_t *bits;        /* device: bit-packed assignment, bit v&31 of word v>>5                             */
+    uint64_t m;                  /* clause indices are [0, m)                                                        */
+    uint32_t k;                  /* literals per clause                                                              */
+    uint32_t grid_hint;          /* CTAs the library suggests (a multiple of the SM count)                           */
+    uint32_t *records;           /* device out: [cap][k+1] = {clause index, literals} of the violated clauses        */
+    uint64_t cap;                /* records that fit; count beyond it, store nothing there (the solve then fails      */
+                                 /* with ALLL_CAPACITY)                                                              */
+    unsigned int *n_violated;    /* device counter, 0 on entry                                                       */
+    const unsigned int *skip;    /* device flag: non-zero => return at once (round enqueued behind the terminal one) */
+} alll_gen_sweep_args;
+/* Enqueues the sweep kernel on `cuda_stream` (a cudaStream_t) and returns the cudaError_t of the launch (0 = ok). */
+typedef int (*alll_gen_launch_fn)(void *user, const alll_gen_sweep_args *args, void *cuda_stream);
+
+/* cap_records: capacity of the violated-record buffer; 0 = m (always enough).  A random assignment violates about
+ * m / 2^k clauses.  `user` must stay valid while the instance is loaded. */
+ALLL_API int alll_upload_generator(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, alll_gen_launch_fn launch,
+                                   void *user, uint64_t cap_records);
+
+/* Generators that ship with the library (tests, bench; csrc/generator.cu is also the worked example of a user TU):
+ *   ALLL_GEN_UNIFORM : clause i = k variables drawn uniformly: with w = word (j & 3) of
+ *                      Philox4x32-10(ctr = {lo32(i), hi32(i), 0x47454E31, j >> 2}, key = seed):
+ *                      var = (w * n_vars) >> 32, neg = w & 1;
+ *   ALLL_GEN_BOUNDED : every variable occurs at most d times: literal j of clause i sits at position p = i*k + j,
+ *                      var = ((a*p + b) mod (n_vars*d)) mod n_vars, neg = bit j of
+ *                      Philox4x32-10(ctr = {lo32(i), hi32(i), 0x47454E32, 0}, key = seed).x.  With
+ *                      (x, y, z, w) = Philox4x32-10(ctr = {0, 0, 0x47454E33, 0}, key = seed): a = the first value coprime
+ *                      to n_vars*d at or after ((((y << 32 | x) mod 2^26) | 2^20 | 1) mod (n_vars*d)) (0 counts as 1),
+ *                      b = (w << 32 | z) mod (n_vars*d).  Needs m*k <= n_vars*d < 2^36.
+ * Both take 1 <= k <= 16. */
+#define ALLL_GEN_UNIFORM 0u
+#define ALLL_GEN_BOUNDED 1u
+ALLL_API int alll_upload_builtin_generator(alll_handle h, uint32_t kind, uint64_t n_vars, uint64_t m, uint32_t k,
+                                           uint64_t seed, uint32_t d, uint64_t cap_records);
+/* The same generators on the host (used to cross-check a device generator; writes k literals of clause `index`). */
+ALLL_API int alll_builtin_generator_clause(uint32_t kind, uint64_t n_vars, uint64_t m, uint32_t k, uint64_t seed, uint32_t d,
+                                           uint64_t index, uint32_t *lits);
 
 /* ---- assignment (VariablesArray<T>::vars, VariablesArray.h:18-35; 1 byte per variable on the host) */
 

@@ -204,6 +204,49 @@ void alll_oracle_randomize(uint64_t n_vars, uint64_t seed, uint8_t *vars)
     }
 }
 
+static uint64_t gcd_u64(uint64_t a, uint64_t b)
+{
+    while (b) { uint64_t t = a % b; a = b; b = t; }
+    return a;
+}
+
+int alll_oracle_gen_materialize(uint32_t kind, uint64_t n_vars, uint64_t m, uint32_t k, uint64_t seed, uint32_t d,
+                                uint32_t *lits)
+{
+    const uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    uint32_t out[4];
+    if (k < 1 || k > 16 || n_vars == 0 || n_vars > (1ull << 31)) return -1;
+    if (kind == 0) {                                   /* uniform: var = (w * n) >> 32, neg = w & 1 */
+        for (uint64_t i = 0; i < m; i++)
+            for (uint32_t j = 0; j < k; j++) {
+                const uint32_t ctr[4] = { (uint32_t)i, (uint32_t)(i >> 32), 0x47454E31u, j >> 2 };
+                alll_oracle_philox4x32_10(ctr, key, out);
+                const uint32_t w = out[j & 3u];
+                lits[i * k + j] = 2u * (uint32_t)(((uint64_t)w * n_vars) >> 32) + (w & 1u);
+            }
+        return 0;
+    }
+    if (kind != 1 || d == 0) return -1;
+    const uint64_t span = n_vars * (uint64_t)d;        /* bounded: every variable at most d times */
+    if (span >= (1ull << 36) || m > span / k) return -1;
+    const uint32_t setup[4] = { 0u, 0u, 0x47454E33u, 0u };
+    alll_oracle_philox4x32_10(setup, key, out);
+    uint64_t a = ((((((uint64_t)out[1] << 32) | out[0]) % (1ull << 26)) | (1ull << 20) | 1ull)) % span;
+    if (a == 0) a = 1;
+    while (gcd_u64(a, span) != 1) a = (a + 1 < span) ? a + 1 : 1;
+    const uint64_t b = (((uint64_t)out[3] << 32) | out[2]) % span;
+    for (uint64_t i = 0; i < m; i++) {
+        const uint32_t ctr[4] = { (uint32_t)i, (uint32_t)(i >> 32), 0x47454E32u, 0u };
+        alll_oracle_philox4x32_10(ctr, key, out);
+        for (uint32_t j = 0; j < k; j++) {
+            const uint64_t p = i * k + j;
+            const uint64_t var = ((a * p + b) % span) % n_vars;
+            lits[i * k + j] = 2u * (uint32_t)var + ((out[0] >> j) & 1u);
+        }
+    }
+    return 0;
+}
+
 static int cmp_u64(const void *a, const void *b)
 {
     uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;

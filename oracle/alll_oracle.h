@@ -96,6 +96,13 @@ uint32_t alll_oracle_priority(uint64_t seed, uint32_t round, uint32_t c);
 /* vars[v] = random_bit(seed, INIT, 0, v) for all v (replaces VariablesArray.h:24-33). */
 void alll_oracle_randomize(uint64_t n_vars, uint64_t seed, uint8_t *vars);
 
+/* Enumerated-clause instances (SATInstance.h:70-153 takes the clauses as a callback of the index): the two index ->
+ * clause functions the CUDA library ships (include/alll_b200.h, ALLL_GEN_UNIFORM = 0 / ALLL_GEN_BOUNDED = 1), restated
+ * from that specification with plain 64-bit % arithmetic.  Writes all m clauses, row-major [m][k].
+ * Returns 0, or -1 on parameters outside the specification. */
+int alll_oracle_gen_materialize(uint32_t kind, uint64_t n_vars, uint64_t m, uint32_t k, uint64_t seed, uint32_t d,
+                                uint32_t *lits);
+
 /* Maximal independent set of U = greedy in ascending (priority, id) order;
  * identical to iterating fixed-priority Luby steps to a fixed point.
  * Writes S ascending by (priority,id); returns |S|.  scratch: n_vars bytes, zeroed on entry and exit. */

@@ -93,6 +93,8 @@ class Oracle:
         L.alll_oracle_priority.restype = C.c_uint32
         L.alll_oracle_priority.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
         L.alll_oracle_randomize.argtypes = [C.c_uint64, C.c_uint64, _u8p]
+        L.alll_oracle_gen_materialize.restype = C.c_int
+        L.alll_oracle_gen_materialize.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, _u32p]
         L.alll_oracle_priority_mis.restype = C.c_uint64
         L.alll_oracle_priority_mis.argtypes = [C.c_uint64, _u64p, _u32p, _u32p, C.c_uint64,
                                                C.c_uint64, C.c_uint32, _u8p, _u32p]
@@ -157,6 +159,13 @@ class Oracle:
         out = np.zeros(max(n_vars, 1), np.uint8)
         self.lib.alll_oracle_randomize(n_vars, seed, out)
         return out[:n_vars]
+
+    def gen_materialize(self, kind: int, n_vars: int, m: int, k: int, seed: int, d: int = 0) -> np.ndarray:
+        """All clauses of a built-in enumerated instance as an (m, k) literal matrix."""
+        out = np.zeros((max(m, 1), k), np.uint32)
+        if self.lib.alll_oracle_gen_materialize(kind, n_vars, m, k, seed, d, out.reshape(-1)) != 0:
+            raise ValueError("generator parameters outside the specification")
+        return out[:m]
 
     def priority_mis(self, n_vars, off, lit, u_ids, seed, rnd) -> np.ndarray:
         u_ids = np.ascontiguousarray(u_ids, np.uint32)
