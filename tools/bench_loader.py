@@ -14,7 +14,7 @@ ap.add_argument("--config", default="cfg2")
 ap.add_argument("--scale", type=float, default=0.25)
 args = ap.parse_args()
 
-work = os.path.join(ROOT, "gpurun_out", "loader")
+work = os.path.join(ROOT, ".scratch", "loader")      # git- and gpurun-ignored
 os.makedirs(work, exist_ok=True)
 import numpy as np  # noqa: E402
 cfg = instances.CONFIGS[args.config]
@@ -65,4 +65,5 @@ for t in (1, 2, 4, 8, 16, 32):
     r = json.loads(subprocess.check_output([ours, path], env=dict(os.environ, ALLL_CNF_THREADS=str(t))))
     res.setdefault("ours_ms_by_threads", {})[t] = r["ms"]
 res["host_cpus"] = os.cpu_count()
+os.remove(path)
 print(json.dumps(res))
