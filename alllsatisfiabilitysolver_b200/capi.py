@@ -32,6 +32,7 @@ SYMBOLS = [
     "alll_batch_upload", "alll_batch_solve",
     "alll_p2p_create", "alll_p2p_connect", "alll_solve_p2p",
     "alll_upload_generator", "alll_upload_builtin_generator", "alll_builtin_generator_clause",
+    "alll_flag_create", "alll_flag_open", "alll_flag_reset", "alll_flag_read", "alll_batch_set_job_base",
 ]
 
 GEN_UNIFORM, GEN_BOUNDED = 0, 1
@@ -102,6 +103,11 @@ def load() -> C.CDLL:
     L.alll_upload_generator.argtypes = [vp, u64, u64, u32, vp, vp, u64]
     L.alll_upload_builtin_generator.argtypes = [vp, u32, u64, u64, u32, u64, u32, u64]
     L.alll_builtin_generator_clause.argtypes = [u32, u64, u64, u32, u64, u32, u64, vp]
+    L.alll_flag_create.argtypes = [vp, vp]
+    L.alll_flag_open.argtypes = [vp, vp]
+    L.alll_flag_reset.argtypes = [vp]
+    L.alll_flag_read.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.alll_batch_set_job_base.argtypes = [vp, u32]
     L.alll_set_assignment.argtypes = [vp, vp]
     L.alll_get_assignment.argtypes = [vp, vp]
     L.alll_randomize.argtypes = [vp, u64]
@@ -295,10 +301,31 @@ class Solver:
                                                  ("status", "<i4"), ("reserved", "<i4")]))
         assign = np.zeros((n_jobs, n_vars), np.uint8) if want_assignments else None
         winner, ms = C.c_int32(-1), C.c_double(0.0)
-        self._check(self.lib.alll_batch_solve(self.h, n_jobs, seeds.ctypes.data, max_rounds, 1 if portfolio else 0,
+        self._check(self.lib.alll_batch_solve(self.h, n_jobs, seeds.ctypes.data, max_rounds, int(portfolio),      # 2: shared flag
                                               assign.ctypes.data if want_assignments else None, stats.ctypes.data,
                                               C.byref(winner), C.byref(ms)))
         return stats, assign, int(winner.value), float(ms.value)
+
+    # -- multi-GPU portfolio: one first-SAT word for all ranks --------------------------------
+    def flag_create(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        self._check(self.lib.alll_flag_create(self.h, buf))
+        return bytes(buf)
+
+    def flag_open(self, handle: bytes):
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        self._check(self.lib.alll_flag_open(self.h, buf))
+
+    def flag_reset(self):
+        self._check(self.lib.alll_flag_reset(self.h))
+
+    def flag_read(self) -> int:
+        v = C.c_int64(-1)
+        self._check(self.lib.alll_flag_read(self.h, C.byref(v)))
+        return int(v.value)
+
+    def batch_set_job_base(self, base: int):
+        self._check(self.lib.alll_batch_set_job_base(self.h, base))
 
     # -- measurement ----------------------------------------------------------------------
     def time_sweep(self, reps: int):

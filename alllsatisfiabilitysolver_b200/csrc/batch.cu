@@ -30,7 +30,9 @@ struct BatchParams {
     uint32_t *bits_out;            // [n_jobs][n_words]
     BatchJobStats *stats;          // [n_jobs]
     int portfolio;                 // 1: all jobs solve instance 0, first to finish wins
-    int *winner;                   // portfolio: job index of the winner, -1 while open
+    int *winner;                   // portfolio: job id of the winner, -1 while open
+    int job_base;                  // id written to *winner = job_base + job (distinct per GPU in a multi-GPU portfolio)
+    int shared;                    // *winner is one word shared by several GPUs (peer-mapped): system-scope atomics
 };
 
 extern __shared__ __align__(16) uint32_t b_smem[];
@@ -167,7 +169,10 @@ __global__ void __launch_bounds__(BATCH_THREADS) batch_solve_kernel(const BatchP
     bool publish = true;
     if (p.portfolio) {
         __shared__ int s_won;
-        if (tid == 0) s_won = (status == 0) ? (atomicCAS(p.winner, -1, (int)job) == -1) : 0;
+        if (tid == 0) {
+            const int id = p.job_base + (int)job;
+            s_won = (status == 0) ? ((p.shared ? atomicCAS_system(p.winner, -1, id) : atomicCAS(p.winner, -1, id)) == -1) : 0;
+        }
         __syncthreads();
         publish = s_won != 0;
         if (status == 0 && !publish) status = BATCH_PREEMPTED; // finished, but somebody else was first
@@ -223,13 +228,13 @@ size_t batch_smem_bytes(uint32_t n_vars, uint32_t n_words, uint32_t m_max)
 cudaError_t launch_batch_solve(const uint32_t *planes, uint64_t m_pad, const uint32_t *inst_off, const uint32_t *inst_m,
                                uint32_t n_instances, uint32_t n_vars, uint32_t n_words, uint32_t k, uint32_t m_max,
                                const uint64_t *seeds, uint64_t max_rounds, uint32_t *bits_out, BatchJobStats *stats,
-                               int portfolio, int *winner, uint32_t n_jobs, cudaStream_t s)
+                               int portfolio, int *winner, int job_base, int shared, uint32_t n_jobs, cudaStream_t s)
 {
     const size_t smem = batch_smem_bytes(n_vars, n_words, m_max);
     cudaError_t e = cudaFuncSetAttribute(batch_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     BatchParams p{planes, m_pad, inst_off, inst_m, n_instances, n_vars, n_words, k, m_max, seeds, max_rounds, bits_out, stats,
-                  portfolio, winner};
+                  portfolio, winner, job_base, shared};
     batch_solve_kernel<<<n_jobs, BATCH_THREADS, smem, s>>>(p);
     return cudaGetLastError();
 }

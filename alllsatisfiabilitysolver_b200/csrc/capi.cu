@@ -95,6 +95,10 @@ struct alll_solver {
     BatchJobStats *d_b_stats = nullptr;
     uint8_t *d_b_bytes = nullptr;
     int *d_b_winner = nullptr;
+    // multi-GPU portfolio: one winner word for all ranks, owned by one GPU and peer-mapped (CUDA IPC) by the others
+    int *d_flag = nullptr;               // the word as this process addresses it
+    bool flag_owner = false;
+    uint32_t b_job_base = 0;
     uint8_t *d_tmp_bkt = nullptr;
     uint32_t *d_tmp_cnt = nullptr, *d_tmp_err = nullptr, *d_stage = nullptr;
     // enumerated clauses (alll_upload_generator): nothing stored but the violated records of the current round
@@ -154,6 +158,7 @@ void release_buffers(alll_handle h)
     dfree(h->d_p2p_region); dfree(h->d_p2p_link);
     dfree(h->d_occ_off); dfree(h->d_occ); dfree(h->d_rows); dfree(h->d_visited); dfree(h->d_incr_tmp);
     dfree(h->d_gen_rec);
+    if (h->d_flag) { if (h->flag_owner) cudaFree(h->d_flag); else cudaIpcCloseMemHandle(h->d_flag); h->d_flag = nullptr; }
     free_instance(h);
     h->incr_ready = false;
     h->p2p_ready = false;
@@ -1135,6 +1140,10 @@ int alll_batch_solve(alll_handle h, uint32_t n_jobs, const uint64_t *seeds, uint
     if (!h->has_batch) return fail(h, ALLL_NO_INSTANCE, "no batch uploaded");
     CK(cudaSetDevice(h->device));
     if (n_jobs == 0 || !seeds || !stats) return fail(h, ALLL_BAD_ARG, "n_jobs / seeds / stats");
+    const bool shared = portfolio == 2;
+    if (shared && !h->d_flag) return fail(h, ALLL_BAD_ARG, "portfolio == 2 needs alll_flag_create / alll_flag_open first");
+    if ((uint64_t)h->b_job_base + n_jobs > 0x7FFFFFFFull) return fail(h, ALLL_BAD_ARG, "job ids must fit 31 bits");
+    int *d_winner_word = nullptr;
     if (!portfolio && n_jobs != h->b_n_inst) return fail(h, ALLL_BAD_ARG, "n_jobs must equal the number of uploaded instances");
     static_assert(sizeof(alll_batch_stats) == sizeof(BatchJobStats), "ABI mirror");
     POOL(h->d_b_seeds, (size_t)n_jobs * 8);
@@ -1144,17 +1153,18 @@ int alll_batch_solve(alll_handle h, uint32_t n_jobs, const uint64_t *seeds, uint
     const int minus1 = -1;
     CK(cudaMemcpyAsync(h->d_b_seeds, seeds, (size_t)n_jobs * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_b_winner, &minus1, 4, cudaMemcpyHostToDevice, h->stream));
+    d_winner_word = shared ? h->d_flag : h->d_b_winner;      // (the shared word is reset by its owner between portfolios)
     CK(cudaMemsetAsync(h->d_b_bits, 0, (size_t)n_jobs * h->b_n_words * 4, h->stream));
     cudaEvent_t e0 = h->ev[0], e1 = h->ev[1];
     CK(cudaEventRecord(e0, h->stream));
     CK(launch_batch_solve(h->d_b_planes, h->b_m_pad, h->d_b_off, h->d_b_m, h->b_n_inst, h->b_n_vars, h->b_n_words, h->b_k,
-                          h->b_m_max, h->d_b_seeds, max_rounds, h->d_b_bits, h->d_b_stats, portfolio ? 1 : 0, h->d_b_winner,
-                          n_jobs, h->stream));
+                          h->b_m_max, h->d_b_seeds, max_rounds, h->d_b_bits, h->d_b_stats, portfolio ? 1 : 0, d_winner_word,
+                          (int)h->b_job_base, shared ? 1 : 0, n_jobs, h->stream));
     h->launches++;
     CK(cudaEventRecord(e1, h->stream));
     CK(cudaMemcpyAsync(stats, h->d_b_stats, (size_t)n_jobs * sizeof(BatchJobStats), cudaMemcpyDeviceToHost, h->stream));
     int w = -1;
-    CK(cudaMemcpyAsync(&w, h->d_b_winner, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&w, d_winner_word, 4, cudaMemcpyDeviceToHost, h->stream));
     if (assignments) {
         const uint64_t total = (uint64_t)n_jobs * h->b_n_vars;
         POOL(h->d_b_bytes, total);
@@ -1166,6 +1176,66 @@ int alll_batch_solve(alll_handle h, uint32_t n_jobs, const uint64_t *seeds, uint
     CK(cudaEventElapsedTime(&ms, e0, e1));
     if (device_ms) *device_ms = ms;
     if (winner) *winner = w;
+    return ALLL_OK;
+}
+
+// ---- multi-GPU portfolio: the first-SAT word shared by all ranks ------------------------------
+
+int alll_flag_create(alll_handle h, uint8_t handle_out[64])
+{
+    if (!h || !handle_out) return ALLL_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (h->d_flag) { if (h->flag_owner) cudaFree(h->d_flag); else cudaIpcCloseMemHandle(h->d_flag); h->d_flag = nullptr; }
+    CK(cudaMalloc(&h->d_flag, 256));
+    h->flag_owner = true;
+    CK(cudaMemset(h->d_flag, 0xFF, 256));                    // -1: open
+    cudaIpcMemHandle_t ipc;
+    CK(cudaIpcGetMemHandle(&ipc, h->d_flag));
+    std::memcpy(handle_out, &ipc, 64);
+    return ALLL_OK;
+}
+
+int alll_flag_open(alll_handle h, const uint8_t *handle)
+{
+    if (!h || !handle) return ALLL_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    if (h->d_flag) { if (h->flag_owner) cudaFree(h->d_flag); else cudaIpcCloseMemHandle(h->d_flag); h->d_flag = nullptr; }
+    cudaIpcMemHandle_t ipc;
+    std::memcpy(&ipc, handle, 64);
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+    h->d_flag = static_cast<int *>(p);
+    h->flag_owner = false;
+    return ALLL_OK;
+}
+
+int alll_flag_reset(alll_handle h)
+{
+    if (!h) return ALLL_BAD_ARG;
+    if (!h->d_flag || !h->flag_owner) return fail(h, ALLL_BAD_ARG, "only the rank that created the flag resets it");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync(h->d_flag, 0xFF, 4, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return ALLL_OK;
+}
+
+int alll_flag_read(alll_handle h, int64_t *value)
+{
+    if (!h || !value) return ALLL_BAD_ARG;
+    if (!h->d_flag) return fail(h, ALLL_BAD_ARG, "no flag");
+    CK(cudaSetDevice(h->device));
+    int w = -1;
+    CK(cudaMemcpyAsync(&w, h->d_flag, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *value = w;
+    return ALLL_OK;
+}
+
+int alll_batch_set_job_base(alll_handle h, uint32_t job_base)
+{
+    if (!h) return ALLL_BAD_ARG;
+    h->b_job_base = job_base;
     return ALLL_OK;
 }
 

@@ -240,3 +240,93 @@ class P2PShardedSolver:
             ms = float(t.item())
         return ShardedStats(st.n_iterations, st.n_resamples, st.avg_mis_size, st.sum_mis_size, st.n_clause_evals,
                             st.status, ms, [], [])
+
+
+# ---- portfolio and batched instances over the GPUs of one box (BASELINE config 5) -----------
+
+def partition_round_robin(n_items: int, world: int, rank: int) -> np.ndarray:
+    """Seed (or instance) s runs on GPU s mod world."""
+    return np.arange(rank, n_items, world, dtype=np.int64)
+
+
+class CudaPortfolioBackend:
+    """Per-rank compute of the multi-GPU portfolio on the C ABI: one CTA per seed, one winner word for ALL ranks
+    (device memory of rank 0, peer-mapped through CUDA IPC, claimed with a system-scope atomicCAS)."""
+
+    def __init__(self, device: int):
+        from . import capi
+
+        self.solver = capi.Solver(device=device)
+        self.comm_device = torch.device("cuda", device)
+
+    def upload(self, n_vars: int, lits: np.ndarray):
+        lits = np.ascontiguousarray(lits, np.uint32)
+        self.solver.batch_upload(n_vars, lits.shape[1], np.array([0, lits.shape[0]], np.uint64), lits)
+
+    def flag_create(self) -> bytes:
+        return self.solver.flag_create()
+
+    def flag_open(self, handle: bytes):
+        self.solver.flag_open(handle)
+
+    def flag_reset(self):
+        self.solver.flag_reset()
+
+    def run(self, seeds: np.ndarray, job_base: int, max_rounds: int):
+        """-> (status per local job, assignment of the local winner or None, device ms)"""
+        self.solver.batch_set_job_base(job_base)
+        stats, assign, winner, ms = self.solver.batch_solve(seeds, max_rounds=max_rounds, portfolio=2, want_assignments=True)
+        won = np.flatnonzero(stats["status"] == 0)
+        return stats["status"].copy(), (assign[won[0]] if len(won) else None), ms
+
+
+class MultiGpuPortfolio:
+    """One instance, ``n_seeds`` solver seeds spread over all ranks (seed s -> rank s mod world); the first job
+    anywhere to satisfy every clause claims the shared winner word and every other job stops at its next round.
+
+    ``torch.distributed`` only moves the 64-byte flag handle once, acts as the barrier around a portfolio and
+    collects who won; during the solve the ranks interact through the flag word alone."""
+
+    def __init__(self, backend, rank: int = 0, world: int = 1, group=None):
+        self.be, self.rank, self.world, self.group = backend, rank, world, group
+        handle = [self.be.flag_create() if rank == 0 else None]
+        if world > 1:
+            dist.broadcast_object_list(handle, src=0, group=group)
+            if rank != 0:
+                self.be.flag_open(handle[0])
+            dist.barrier(group=group)
+
+    def upload(self, n_vars: int, lits):
+        self.n_vars = n_vars
+        self.be.upload(n_vars, lits)
+
+    def solve(self, seeds, max_rounds: int = 1 << 20):
+        """-> dict(winner_seed_index, winner_rank, assignment (on every rank), ms (max over ranks), n_finished)"""
+        seeds = np.ascontiguousarray(seeds, np.uint64)
+        mine = partition_round_robin(len(seeds), self.world, self.rank)
+        if self.world > 1:
+            dist.barrier(group=self.group)               # nobody is still polling the previous portfolio's word
+        if self.rank == 0:
+            self.be.flag_reset()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        status, assign, ms = self.be.run(seeds[mine], job_base=self.rank * len(seeds), max_rounds=max_rounds)
+        won = np.flatnonzero(status == 0)
+        # exactly one job in the world may hold status OK: the one whose compare-and-swap found the word open
+        info = torch.tensor([int(mine[won[0]]) if len(won) else -1, len(won), ms], dtype=torch.float64, device=self.be.comm_device)
+        if self.world > 1:
+            allinfo = [torch.zeros_like(info) for _ in range(self.world)]
+            dist.all_gather(allinfo, info, group=self.group)
+        else:
+            allinfo = [info]
+        allinfo = [t.cpu().numpy() for t in allinfo]
+        n_finished = int(sum(t[1] for t in allinfo))
+        winner_rank = next((r for r, t in enumerate(allinfo) if t[1] > 0), -1)
+        winner_seed = int(allinfo[winner_rank][0]) if winner_rank >= 0 else -1
+        buf = torch.zeros(self.n_vars, dtype=torch.uint8, device=self.be.comm_device)
+        if winner_rank == self.rank and assign is not None:
+            buf = torch.from_numpy(np.ascontiguousarray(assign)).to(self.be.comm_device)
+        if self.world > 1 and winner_rank >= 0:
+            dist.broadcast(buf, src=winner_rank, group=self.group)
+        return dict(winner_seed_index=winner_seed, winner_rank=winner_rank, n_finished=n_finished,
+                    assignment=buf.cpu().numpy() if winner_rank >= 0 else None, ms=float(max(t[2] for t in allinfo)))

@@ -301,6 +301,14 @@ def run_ours(args):
         except Exception as e:                       # e.g. CUDA IPC not permitted on this box: report, do not die
             sharded = {"error": repr(e)}
 
+    # ---- BASELINE config 5 over all ranks: seed portfolio with ONE first-SAT word for all GPUs, batched instances ----
+    cfg5_multi = None
+    if world > 1 and not args.no_sharded:
+        try:
+            cfg5_multi = cfg5_over_ranks(rank, world, local_rank)
+        except Exception as e:
+            cfg5_multi = {"error": repr(e)}
+
     # ---- reduce over ranks: MAX time, SUM work ----
     red = torch.tensor([dev_ms, wall_ms, e2e_s], dtype=torch.float64, device="cuda")
     tot = torch.tensor([evals, sweeps, rounds, e2e_evals, launches, int(all_sat and verified)], dtype=torch.float64, device="cuda")
@@ -356,6 +364,7 @@ def run_ours(args):
             "incremental_mode": incremental,
             "other_workloads": extras,
             "sharded": sharded,
+            "cfg5_multi_gpu": cfg5_multi,
         }
         print(json.dumps(line))
     solver.close()
@@ -429,6 +438,51 @@ def other_workloads(device: int):
     s.close()
     torch.cuda.empty_cache()
     return out
+
+
+def cfg5_over_ranks(rank, world, local_rank, n_seeds=8192, n_inst=8192, reps=3):
+    """Seed s / instance i on GPU s mod N.  Portfolio: one winner word in rank 0's memory, peer-mapped by every rank and
+    claimed with a system-scope atomicCAS.  Batch: no exchange.  Device-timed, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from alllsatisfiabilitysolver_b200 import capi
+    from alllsatisfiabilitysolver_b200.instances import bounded_degree_batch_torch, bounded_degree_ksat
+    from alllsatisfiabilitysolver_b200.sharded import CudaPortfolioBackend, MultiGpuPortfolio, partition_round_robin
+
+    c5 = CONFIGS["cfg5"]
+    lits = bounded_degree_ksat(c5["n"], c5["k"], c5["d"], seed=INSTANCE_SEED_BASE + 5)
+    pf = MultiGpuPortfolio(CudaPortfolioBackend(local_rank), rank, world)
+    pf.upload(c5["n"], lits)
+    runs = []
+    for r in range(reps):
+        res = pf.solve(np.arange(r * n_seeds, (r + 1) * n_seeds, dtype=np.uint64))
+        ok = res["n_finished"] == 1 and res["assignment"] is not None
+        if ok:
+            v = res["assignment"].astype(bool)
+            ok = bool((v[lits >> 1] ^ (lits & 1).astype(bool)).any(axis=1).all())
+        runs.append((res["ms"], res["winner_rank"], ok))
+    mine = partition_round_robin(n_inst, world, rank)
+    off, blits = bounded_degree_batch_torch(len(mine), c5["n"], c5["k"], c5["d"], INSTANCE_SEED_BASE + 5 + 1000 * rank)
+    s = capi.Solver(device=local_rank)
+    s.batch_upload(c5["n"], c5["k"], off.numpy().astype(np.uint64), blits.cpu().numpy().view(np.uint32))
+    best, solved = None, 0
+    for r in range(reps):
+        dist.barrier()
+        st, _, _, ms = s.batch_solve(mine.astype(np.uint64) + np.uint64(r * n_inst), want_assignments=False)
+        tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        tsum = torch.tensor([float((st["status"] == 0).sum())], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        best = float(tmax) if best is None else min(best, float(tmax))
+        solved = int(tsum)
+    s.close()
+    pf.be.solver.close()
+    return {"portfolio": {"seeds": n_seeds, "first_sat_ms": min(x[0] for x in runs), "winner_ranks": [x[1] for x in runs],
+                          "all_verified": all(x[2] for x in runs),
+                          "flag": "one word in rank 0's HBM, CUDA-IPC mapped by all ranks, system-scope atomicCAS"},
+            "batch": {"instances": n_inst, "batch_ms": best, "instances_per_sec": n_inst / (best * 1e-3), "solved": solved,
+                      "parallelism": "instance i on GPU i mod N, no exchange"}}
 
 
 def sharded_solves(args, shape, rank, world, local_rank):

@@ -250,9 +250,22 @@ ALLL_API int alll_batch_upload(alll_handle h, uint32_t n_instances, uint64_t n_v
 /* n_jobs == n_instances (portfolio == 0: job i solves instance i with seeds[i], starting from the Philox
  * assignment of that seed), or any n_jobs with portfolio != 0 (every job solves instance 0).
  * assignments (host, [n_jobs][n_vars] bytes, may be NULL): rows of finished jobs; in portfolio mode only the
- * winner's row is written.  *winner: portfolio winner job or -1.  *device_ms: kernel time from CUDA events. */
+ * winner's row is written.  *winner: portfolio winner id (job_base + job) or -1.  portfolio == 2: the winner word is
+ * the one shared between GPUs (alll_flag_*).  *device_ms: kernel time from CUDA events. */
 ALLL_API int alll_batch_solve(alll_handle h, uint32_t n_jobs, const uint64_t *seeds, uint64_t max_rounds, int portfolio,
                      uint8_t *assignments, alll_batch_stats *stats, int32_t *winner, double *device_ms);
+
+/* Multi-GPU portfolio (BASELINE config 5: seeds spread over the GPUs of a box, "the first GPU to find SAT wins via a
+ * device flag"): ONE winner word for all ranks.  One rank creates it (device memory, -1 = open) and passes the 64-byte
+ * CUDA IPC handle to the other processes, which map it over NVLink; alll_batch_solve(portfolio = 2) then claims and
+ * polls that word with system-scope atomics instead of the per-handle one, writing job_base + job (give every rank a
+ * distinct job_base).  A job that finishes after another rank's claim reports ALLL_PREEMPTED like a local loser.  The
+ * owner resets the word between portfolios (host barrier before and after, the caller's). */
+ALLL_API int alll_flag_create(alll_handle h, uint8_t handle_out[64]);
+ALLL_API int alll_flag_open(alll_handle h, const uint8_t *handle);
+ALLL_API int alll_flag_reset(alll_handle h);
+ALLL_API int alll_flag_read(alll_handle h, int64_t *value);
+ALLL_API int alll_batch_set_job_base(alll_handle h, uint32_t job_base);
 
 /* ---- measurement hooks -------------------------------------------------------------- */
 
