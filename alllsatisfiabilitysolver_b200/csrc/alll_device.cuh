@@ -155,7 +155,19 @@ struct Counters {
     unsigned int incr_next;     // 1: the next violated set comes from incr_eval_kernel, the sweep kernel returns at entry
     unsigned int n_incr_rounds; // rounds evaluated incrementally so far
     unsigned long long n_evals_incr;   // clauses actually evaluated by incremental rounds
+    // ALLL_TRACE: %globaltimer stamps of the first DBG_ROUNDS rounds (one thread writes them; a few stores per round)
+    // [0] sweep entry  [1] MIS kernel entry  [2] |U| known  [3] gather + first claims done  [4] Luby steps done
+    // [5] resample done  [6] round finished  [7] (steps << 8) | path (0 small, 1 cluster, 2 grid)
+    unsigned long long dbg[32][8];
 };
+constexpr uint32_t DBG_ROUNDS = 32;
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // What the round loop on the host needs to know about a finished round.  Lives in pinned host memory; the MIS
 // kernel's last thread stores it directly over PCIe (no copy-engine hop between the kernels of consecutive rounds)
@@ -193,6 +205,16 @@ struct P2PLink {                         // device-resident, one per handle
     uint32_t *rec[MAX_SHARDS];           // every GPU's record area
 };
 
+// Claim storage of a handle (+ the records the sweep of this round wrote next to the violated list, if any).
+struct MisScratch {
+    unsigned long long *claim;  // [2][claim_stride], CLAIM_FREE between rounds
+    uint64_t claim_stride;      // >= max(n_vars, tcap)
+    uint32_t *hvar;             // [tcap] compact-table keys, 0xFFFFFFFF between rounds (NULL: claims always indexed by variable)
+    uint32_t tcap;
+    const uint32_t *urec;       // [urec_cap][k+1] records {id, literals} parallel to viol[] (NULL: none)
+    uint32_t urec_cap;
+};
+
 struct BucketSeg {
     uint32_t tile_begin;        // first sweep tile of this bucket
     uint32_t slot_end;          // one past the last valid clause slot of this bucket
@@ -219,6 +241,10 @@ struct SweepParams {
     uint32_t p2p_parity, p2p_tag;
     const uint32_t *orig_id;
     uint32_t id_base;
+    uint32_t round;             // solve round this sweep belongs to (trace stamps only)
+    // records {caller id, k literals} of the first urec_cap violated clauses, parallel to viol[] (NULL = not written)
+    uint32_t *urec;
+    uint32_t urec_cap;
 };
 
 } // namespace alll

@@ -18,7 +18,7 @@ cudaError_t launch_sweep_csr(const uint64_t *off, const uint32_t *lit, uint64_t 
 // mis.cu
 cudaError_t mis_configure(int device, uint32_t kmax, uint32_t *grid_out);
 cudaError_t launch_mis_resample_args(const ClauseView &cv, uint32_t kmax, const uint32_t *viol, uint8_t *state,
-                                     uint32_t *s_slots, unsigned long long *claim, uint64_t n_vars, uint32_t *bits,
+                                     uint32_t *s_slots, const MisScratch &sc, uint64_t n_vars, uint32_t *bits,
                                      Counters *ctr, uint64_t seed, uint32_t round, uint32_t grid, bool with_grid,
                                      RoundNote *note, unsigned long long seq, const P2PLink *p2p, uint32_t p2p_parity,
                                      uint32_t p2p_tag, uint32_t incr_max_vars, uint32_t u_cap, cudaStream_t s);

@@ -51,6 +51,10 @@ struct alll_solver {
     uint64_t n_lit = 0;
     uint32_t *d_bits = nullptr;
     unsigned long long *d_claim = nullptr;
+    uint32_t *d_hvar = nullptr;          // compact claim table keys (mis.cu)
+    uint32_t tcap = 0;
+    uint32_t *d_urec = nullptr;          // records of the violated clauses of the current round, written by the sweep
+    uint32_t urec_cap = 0;
     uint32_t *d_viol = nullptr, *d_s = nullptr, *d_ids_out = nullptr;
     uint8_t *d_state = nullptr, *d_bools = nullptr;
     uint8_t *h_bools = nullptr;          // pinned staging for the 1-byte-per-variable boundary (grow-only)
@@ -147,7 +151,7 @@ void free_instance(alll_handle h)
 void release_buffers(alll_handle h)
 {
     dfree(h->d_planes); dfree(h->d_orig_id); dfree(h->d_segs); dfree(h->d_off); dfree(h->d_csr_lit);
-    dfree(h->d_bits); dfree(h->d_claim); dfree(h->d_viol); dfree(h->d_s); dfree(h->d_ids_out);
+    dfree(h->d_bits); dfree(h->d_claim); dfree(h->d_hvar); dfree(h->d_urec); dfree(h->d_viol); dfree(h->d_s); dfree(h->d_ids_out);
     dfree(h->d_state); dfree(h->d_bools); dfree(h->d_width); dfree(h->d_width_in); dfree(h->d_tmp_bkt); dfree(h->d_tmp_cnt); dfree(h->d_tmp_err); dfree(h->d_stage);
     dfree(h->d_sh_planes); dfree(h->d_sh_ids); dfree(h->d_sh_iota); dfree(h->d_sh_s); dfree(h->d_sh_state);
     dfree(h->d_b_planes); dfree(h->d_b_off); dfree(h->d_b_m); dfree(h->d_b_bits); dfree(h->d_b_lit); dfree(h->d_b_src_off);
@@ -189,6 +193,17 @@ inline uint32_t prefetch_distance(uint32_t flags)
     return d == 0 ? 2u : (d == 0xFFu ? 0u : d);
 }
 
+MisScratch mis_scratch(alll_handle h, bool with_records)
+{
+    MisScratch sc{};
+    sc.claim = h->d_claim; sc.claim_stride = std::max<uint64_t>(h->n_vars, 1);
+    sc.hvar = h->tcap ? h->d_hvar : nullptr; sc.tcap = h->tcap;
+    // (incremental rounds produce the violated list without records)
+    const bool rec = with_records && h->urec_cap != 0 && !h->incr_ready;
+    sc.urec = rec ? h->d_urec : nullptr; sc.urec_cap = rec ? h->urec_cap : 0u;
+    return sc;
+}
+
 ClauseView clause_view(alll_handle h)
 {
     ClauseView cv;
@@ -205,10 +220,18 @@ ClauseView clause_view(alll_handle h)
 int alloc_common(alll_handle h, uint64_t list_cap)
 {
     const uint64_t m1 = std::max<uint64_t>(list_cap, 1), n1 = std::max<uint64_t>(h->n_vars, 1);
+    h->urec_cap = 0;                                       // (set by the layouts whose sweep writes records)
     POOL(h->d_bits, (size_t)std::max<uint32_t>(h->n_words_alloc, 4) * 4);
     CK(cudaMemsetAsync(h->d_bits, 0, (size_t)std::max<uint32_t>(h->n_words_alloc, 4) * 4, h->stream));
     POOL(h->d_claim, 2 * n1 * 8);                          // two claim arrays: even / odd Luby steps
     CK(launch_fill_u64(h->d_claim, 2 * n1, CLAIM_FREE, h->stream)); h->launches++;
+    // compact claim table (mis.cu): used by rounds whose violated set touches at most n/4 variables
+    h->tcap = (uint32_t)std::min<uint64_t>(n1 / 2, 1ull << 23);
+    if (h->tcap < 256) h->tcap = 0;
+    if (h->tcap) {
+        POOL(h->d_hvar, (size_t)h->tcap * 4);
+        CK(cudaMemsetAsync(h->d_hvar, 0xFF, (size_t)h->tcap * 4, h->stream));
+    }
     POOL(h->d_viol, m1 * 4);
     POOL(h->d_s, m1 * 4);
     POOL(h->d_ids_out, m1 * 4);
@@ -322,6 +345,13 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
 
     h->use_width = d_width_in != nullptr && m > 0;
     if (int rc = alloc_common(h, h->m)) return rc;
+    if (k >= 1 && k <= 8 && !h->use_width && m > 0) {
+        // violated-clause records for the independent-set kernel (sweep.cu:write_records): room for twice the violated
+        // set of a uniformly random assignment (m / 2^k); larger sets fall back to reading the literal planes
+        const uint64_t cap = std::min<uint64_t>(m, std::max<uint64_t>(m >> (k - 1), 8192));
+        POOL(h->d_urec, cap * (k + 1) * 4);
+        h->urec_cap = (uint32_t)cap;
+    }
     SweepParams sp{};
     sp.bucket_words = h->bucket_words; sp.k = k; sp.min_resident = h->min_resident; sp.resident_cap = h->resident_cap; sp.eager = (h->flags >> 8) & 0xFFu; sp.prefetch_tiles = prefetch_distance(h->flags);
     CK(configure_sweep_planes(sp, h->resident_all));
@@ -357,7 +387,7 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
 
 // Enqueues one sweep.  Invariant: ctr->n_viol == 0 on entry (kept by the MIS kernel / reset kernel).
 // p2p_tag != 0: sharded P2P mode -- violated records are stored into every GPU's exchange region.
-int enqueue_sweep(alll_handle h, uint32_t p2p_parity = 0, uint32_t p2p_tag = 0)
+int enqueue_sweep(alll_handle h, uint32_t p2p_parity = 0, uint32_t p2p_tag = 0, uint32_t round = 0xFFFFFFFFu)
 {
     if (h->gen_mode) {
         if (h->m == 0) return ALLL_OK;
@@ -376,9 +406,12 @@ int enqueue_sweep(alll_handle h, uint32_t p2p_parity = 0, uint32_t p2p_tag = 0)
         sp.planes = h->d_planes; sp.m_pad = h->m_pad; sp.bits = h->d_bits; sp.n_words = h->n_words_alloc;
         sp.bucket_words = h->bucket_words; sp.n_buckets = h->n_buckets; sp.n_tiles = h->n_tiles;
         sp.segs = h->d_segs; sp.viol = h->d_viol; sp.ctr = h->d_ctr; sp.k = h->k; sp.min_resident = h->min_resident; sp.resident_cap = h->resident_cap; sp.eager = (h->flags >> 8) & 0xFFu; sp.prefetch_tiles = prefetch_distance(h->flags);
+        sp.round = round;
+        sp.orig_id = h->use_orig_id ? h->d_orig_id : nullptr; sp.id_base = h->id_base;
         if (p2p_tag) {
             sp.p2p = h->d_p2p_link; sp.p2p_parity = p2p_parity; sp.p2p_tag = p2p_tag;
-            sp.orig_id = h->use_orig_id ? h->d_orig_id : nullptr; sp.id_base = h->id_base;
+        } else if (h->urec_cap) {
+            sp.urec = h->d_urec; sp.urec_cap = h->urec_cap;
         }
         CK(launch_sweep_planes(sp, h->resident_all, h->sweep_grid, h->stream));
     } else {
@@ -393,7 +426,7 @@ int enqueue_sweep(alll_handle h, uint32_t p2p_parity = 0, uint32_t p2p_tag = 0)
 int enqueue_mis_resample(alll_handle h, uint64_t seed, uint32_t round, bool with_grid = true, RoundNote *note = nullptr,
                          unsigned long long seq = 0, bool allow_incremental = false)
 {
-    CK(launch_mis_resample_args(clause_view(h), h->kmax, h->gen_mode ? nullptr : h->d_viol, h->d_state, h->d_s, h->d_claim,
+    CK(launch_mis_resample_args(clause_view(h), h->kmax, h->gen_mode ? nullptr : h->d_viol, h->d_state, h->d_s, mis_scratch(h, true),
                                 h->n_vars, h->d_bits, h->d_ctr, seed, round, h->mis_grid, with_grid, note, seq, nullptr, 0u, 0u,
                                 (allow_incremental && h->incr_ready) ? h->incr_max_vars : 0u,
                                 h->gen_mode ? (uint32_t)h->gen_cap : 0u, h->stream));
@@ -750,7 +783,7 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
         while (issued < max_rounds && issued - retired < (uint64_t)ROUNDS_IN_FLIGHT) {
             const bool time_this = issued < (uint64_t)MAX_TIMED_ROUNDS;
             if (time_this) CK(cudaEventRecord(h->ev[2 * issued], h->stream));
-            if (int rc = enqueue_sweep(h)) return rc;
+            if (int rc = enqueue_sweep(h, 0u, 0u, (uint32_t)issued)) return rc;
             if (time_this) CK(cudaEventRecord(h->ev[2 * issued + 1], h->stream));
             if (h->incr_ready && issued > 0) {
                 // incremental mode: the device decided at the end of the previous round which of the two kernels
@@ -816,6 +849,18 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
     CK(launch_reset_counters(h->d_ctr, 0, h->stream)); h->launches++;      // clears `done` for the single-step calls
     CK(cudaStreamSynchronize(h->stream));
     const Counters &c = *h->h_ctr;
+    if (trace) {
+        // %globaltimer stamps written by the kernels (us relative to the sweep entry of each round)
+        const uint64_t nr = std::min<uint64_t>(useful_rounds, DBG_ROUNDS);
+        for (uint64_t r = 0; r < nr; r++) {
+            const unsigned long long *d = c.dbg[r];
+            auto us = [&](int i) { return d[i] >= d[0] ? (double)(d[i] - d[0]) * 1e-3 : -1.0; };
+            const double gap = r ? (double)(d[0] - c.dbg[r - 1][6]) * 1e-3 : 0.0;
+            fprintf(stderr, "[alll phases] round %llu: path=%llu steps=%llu | prev round end -> sweep entry %.1f | mis entry %.1f "
+                            "|U| known %.1f gather %.1f steps %.1f resample %.1f finished %.1f (us after sweep entry)\n",
+                    (unsigned long long)r, d[7] & 0xFF, d[7] >> 8, gap, us(1), us(2), us(3), us(4), us(5), us(6));
+        }
+    }
     stats->n_iterations = c.n_iterations;
     stats->n_resamples = c.n_resamples;
     stats->sum_mis_size = c.sum_mis;
@@ -890,7 +935,7 @@ int alll_shard_round(alll_handle h, const uint32_t *d_records, const uint64_t *c
     h->launches++;
     ClauseView cv{};
     cv.planes = h->d_sh_planes; cv.m_pad = cap; cv.k = h->k; cv.orig_id = h->d_sh_ids; cv.id_base = 0;
-    CK(launch_mis_resample_args(cv, h->k, h->d_sh_iota, h->d_sh_state, h->d_sh_s, h->d_claim, h->n_vars, h->d_bits,
+    CK(launch_mis_resample_args(cv, h->k, h->d_sh_iota, h->d_sh_state, h->d_sh_s, mis_scratch(h, false), h->n_vars, h->d_bits,
                                 h->d_ctr, seed, round, h->mis_grid, total > MIS_CLUSTER_MAX_U, nullptr, 0ull, nullptr, 0u, 0u, 0u, 0u, h->stream));
     h->launches += total > MIS_CLUSTER_MAX_U ? 2 : 1;
     if (int rc = fetch_counters(h)) return rc;
@@ -1012,7 +1057,7 @@ int alll_solve_p2p(alll_handle h, uint64_t seed, uint64_t max_rounds, uint64_t m
             if (time_this) CK(cudaEventRecord(h->ev[2 * issued + 1], h->stream));
             const int slot = (int)(issued % ROUNDS_IN_FLIGHT);
             const bool with_grid = last_seen_u > MIS_CLUSTER_MAX_U;
-            CK(launch_mis_resample_args(cv, h->k, nullptr, h->d_sh_state, h->d_sh_s, h->d_claim, h->n_vars, h->d_bits,
+            CK(launch_mis_resample_args(cv, h->k, nullptr, h->d_sh_state, h->d_sh_s, mis_scratch(h, false), h->n_vars, h->d_bits,
                                         h->d_ctr, seed, (uint32_t)issued, h->mis_grid, with_grid, &h->h_ring[slot],
                                         seq0 + issued + 1, h->d_p2p_link, parity, tag, 0u, 0u, h->stream));
             h->launches += with_grid ? 2 : 1;

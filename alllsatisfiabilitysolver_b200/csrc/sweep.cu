@@ -29,6 +29,22 @@ extern __shared__ __align__(16) uint32_t g_smem[];
 
 namespace {
 
+// Next to the violated list the sweep leaves one record {caller id, k literals} per violated clause (for the first
+// urec_cap of them): the independent-set kernel that runs next then reads each clause with one contiguous access
+// instead of chasing k literal planes through cold DRAM on its critical path.  Here the k + 1 scattered reads overlap
+// with the streaming of the other warps.  Out of line: it runs once per >= 32 violated clauses and must not cost the
+// streaming loop registers.
+__device__ __noinline__ void write_records(const SweepParams *sp, uint32_t wbuf, uint32_t g, uint32_t count, uint32_t lane)
+{
+    const uint32_t w = sp->k + 1;
+    for (uint32_t i = lane; i < count; i += 32) {
+        const uint32_t slot = g_smem[wbuf + i];
+        uint32_t *rec = sp->urec + (uint64_t)(g + i) * w;
+        rec[0] = (sp->orig_id ? sp->orig_id[slot] : slot) + sp->id_base;
+        for (uint32_t j = 1; j < w; j++) rec[j] = sp->planes[(uint64_t)(j - 1) * sp->m_pad + slot];
+    }
+}
+
 struct WarpCompactor {
     uint32_t wbuf;       // index in g_smem of this warp's staging buffer (WBUF entries)
     uint32_t *viol;
@@ -63,6 +79,7 @@ struct WarpCompactor {
             }
         } else {
             for (uint32_t i = lane; i < count; i += 32) viol[g + i] = g_smem[wbuf + i];
+            if (sp != nullptr && sp->urec != nullptr && (uint64_t)g + count <= sp->urec_cap) write_records(sp, wbuf, g, count, lane);
         }
         __syncwarp();
         count = 0;
@@ -335,6 +352,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const Sw
     constexpr bool RESIDENT_ALL = RB >= K;
     constexpr int RBE = RB < E ? RB : E;
     if (__ldcg(&p.ctr->done) || __ldcg(&p.ctr->incr_next)) return;   // behind the terminal round / this round is incremental
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.round < DBG_ROUNDS) p.ctr->dbg[p.round][0] = global_ns();
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = threadIdx.x >> 5;
     WarpCompactor out{p.bucket_words + warp * WBUF, p.viol, p.ctr, 0u, lane, &p};
