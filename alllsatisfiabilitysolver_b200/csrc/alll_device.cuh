@@ -155,6 +155,9 @@ struct Counters {
     unsigned int incr_next;     // 1: the next violated set comes from incr_eval_kernel, the sweep kernel returns at entry
     unsigned int n_incr_rounds; // rounds evaluated incrementally so far
     unsigned long long n_evals_incr;   // clauses actually evaluated by incremental rounds
+    // persistent solve kernel: |U| by round parity; time spent in sweeps / between sweeps as block 0 saw it
+    unsigned int n_viol_pp[2];
+    unsigned long long t_sweep_ns, t_mis_ns;
     // ALLL_TRACE: %globaltimer stamps of the first DBG_ROUNDS rounds (one thread writes them; a few stores per round)
     // [0] sweep entry  [1] MIS kernel entry  [2] |U| known  [3] gather + first claims done  [4] Luby steps done
     // [5] resample done  [6] round finished  [7] (steps << 8) | path (0 small, 1 cluster, 2 grid)
@@ -207,10 +210,7 @@ struct P2PLink {                         // device-resident, one per handle
 
 // Claim storage of a handle (+ the records the sweep of this round wrote next to the violated list, if any).
 struct MisScratch {
-    unsigned long long *claim;  // [2][claim_stride], CLAIM_FREE between rounds
-    uint64_t claim_stride;      // >= max(n_vars, tcap)
-    uint32_t *hvar;             // [tcap] compact-table keys, 0xFFFFFFFF between rounds (NULL: claims always indexed by variable)
-    uint32_t tcap;
+    unsigned long long *claim;  // [n_vars][2] claim words (even / odd Luby steps), CLAIM_FREE between rounds
     const uint32_t *urec;       // [urec_cap][k+1] records {id, literals} parallel to viol[] (NULL: none)
     uint32_t urec_cap;
 };

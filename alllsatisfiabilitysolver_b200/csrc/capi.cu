@@ -22,6 +22,7 @@ thread_local std::string g_create_error = "";
 
 constexpr uint32_t DEFAULT_SWEEP_SMEM = 192u * 1024u;
 constexpr int MAX_TIMED_ROUNDS = 256;
+constexpr uint64_t URECORD_CAP = 16384;  // violated-clause records are written for violated sets up to this size
 constexpr int ROUNDS_IN_FLIGHT = 3;      // rounds the host enqueues ahead of the last one it has seen retire
 
 } // namespace
@@ -51,8 +52,7 @@ struct alll_solver {
     uint64_t n_lit = 0;
     uint32_t *d_bits = nullptr;
     unsigned long long *d_claim = nullptr;
-    uint32_t *d_hvar = nullptr;          // compact claim table keys (mis.cu)
-    uint32_t tcap = 0;
+    bool persistent_ok = false;          // the persistent solve kernel fits this instance and device
     uint32_t *d_urec = nullptr;          // records of the violated clauses of the current round, written by the sweep
     uint32_t urec_cap = 0;
     uint32_t *d_viol = nullptr, *d_s = nullptr, *d_ids_out = nullptr;
@@ -151,7 +151,7 @@ void free_instance(alll_handle h)
 void release_buffers(alll_handle h)
 {
     dfree(h->d_planes); dfree(h->d_orig_id); dfree(h->d_segs); dfree(h->d_off); dfree(h->d_csr_lit);
-    dfree(h->d_bits); dfree(h->d_claim); dfree(h->d_hvar); dfree(h->d_urec); dfree(h->d_viol); dfree(h->d_s); dfree(h->d_ids_out);
+    dfree(h->d_bits); dfree(h->d_claim); dfree(h->d_urec); dfree(h->d_viol); dfree(h->d_s); dfree(h->d_ids_out);
     dfree(h->d_state); dfree(h->d_bools); dfree(h->d_width); dfree(h->d_width_in); dfree(h->d_tmp_bkt); dfree(h->d_tmp_cnt); dfree(h->d_tmp_err); dfree(h->d_stage);
     dfree(h->d_sh_planes); dfree(h->d_sh_ids); dfree(h->d_sh_iota); dfree(h->d_sh_s); dfree(h->d_sh_state);
     dfree(h->d_b_planes); dfree(h->d_b_off); dfree(h->d_b_m); dfree(h->d_b_bits); dfree(h->d_b_lit); dfree(h->d_b_src_off);
@@ -196,8 +196,7 @@ inline uint32_t prefetch_distance(uint32_t flags)
 MisScratch mis_scratch(alll_handle h, bool with_records)
 {
     MisScratch sc{};
-    sc.claim = h->d_claim; sc.claim_stride = std::max<uint64_t>(h->n_vars, 1);
-    sc.hvar = h->tcap ? h->d_hvar : nullptr; sc.tcap = h->tcap;
+    sc.claim = h->d_claim;
     // (incremental rounds produce the violated list without records)
     const bool rec = with_records && h->urec_cap != 0 && !h->incr_ready;
     sc.urec = rec ? h->d_urec : nullptr; sc.urec_cap = rec ? h->urec_cap : 0u;
@@ -221,17 +220,11 @@ int alloc_common(alll_handle h, uint64_t list_cap)
 {
     const uint64_t m1 = std::max<uint64_t>(list_cap, 1), n1 = std::max<uint64_t>(h->n_vars, 1);
     h->urec_cap = 0;                                       // (set by the layouts whose sweep writes records)
+    h->persistent_ok = false;
     POOL(h->d_bits, (size_t)std::max<uint32_t>(h->n_words_alloc, 4) * 4);
     CK(cudaMemsetAsync(h->d_bits, 0, (size_t)std::max<uint32_t>(h->n_words_alloc, 4) * 4, h->stream));
     POOL(h->d_claim, 2 * n1 * 8);                          // two claim arrays: even / odd Luby steps
     CK(launch_fill_u64(h->d_claim, 2 * n1, CLAIM_FREE, h->stream)); h->launches++;
-    // compact claim table (mis.cu): used by rounds whose violated set touches at most n/4 variables
-    h->tcap = (uint32_t)std::min<uint64_t>(n1 / 2, 1ull << 23);
-    if (h->tcap < 256) h->tcap = 0;
-    if (h->tcap) {
-        POOL(h->d_hvar, (size_t)h->tcap * 4);
-        CK(cudaMemsetAsync(h->d_hvar, 0xFF, (size_t)h->tcap * 4, h->stream));
-    }
     POOL(h->d_viol, m1 * 4);
     POOL(h->d_s, m1 * 4);
     POOL(h->d_ids_out, m1 * 4);
@@ -346,9 +339,10 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     h->use_width = d_width_in != nullptr && m > 0;
     if (int rc = alloc_common(h, h->m)) return rc;
     if (k >= 1 && k <= 8 && !h->use_width && m > 0) {
-        // violated-clause records for the independent-set kernel (sweep.cu:write_records): room for twice the violated
-        // set of a uniformly random assignment (m / 2^k); larger sets fall back to reading the literal planes
-        const uint64_t cap = std::min<uint64_t>(m, std::max<uint64_t>(m >> (k - 1), 8192));
+        // violated-clause records for the independent-set kernels (sweep.cu:write_records), for violated sets of up to
+        // URECORD_CAP clauses.  Larger sets read the literal planes instead: writing their records costs the sweep more
+        // (scattered reads at the tail of the kernel: +54 us at |U| = 156 k) than it saves the gather (31 us there).
+        const uint64_t cap = std::min<uint64_t>(m, URECORD_CAP);
         POOL(h->d_urec, cap * (k + 1) * 4);
         h->urec_cap = (uint32_t)cap;
     }
@@ -356,6 +350,12 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     sp.bucket_words = h->bucket_words; sp.k = k; sp.min_resident = h->min_resident; sp.resident_cap = h->resident_cap; sp.eager = (h->flags >> 8) & 0xFFu; sp.prefetch_tiles = prefetch_distance(h->flags);
     CK(configure_sweep_planes(sp, h->resident_all));
     h->sweep_grid = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)h->sm_count, h->n_tiles));
+    {
+        int ok = 0, coop = 0;
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+        if (coop && m > 0 && !h->use_width) CK(configure_solve_persistent(sp, h->resident_all, h->kmax, &ok));
+        h->persistent_ok = ok != 0;
+    }
     if ((h->flags & ALLL_FLAG_INCREMENTAL) && m > 0) {
         // occurrence lists + row-major copy for incremental re-evaluation (see incremental.cu)
         const uint64_t n_lit = m * k;
@@ -385,6 +385,23 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     return ALLL_OK;
 }
 
+SweepParams sweep_params(alll_handle h, uint32_t p2p_parity, uint32_t p2p_tag, uint32_t round)
+{
+    SweepParams sp{};
+    sp.planes = h->d_planes; sp.m_pad = h->m_pad; sp.bits = h->d_bits; sp.n_words = h->n_words_alloc;
+    sp.bucket_words = h->bucket_words; sp.n_buckets = h->n_buckets; sp.n_tiles = h->n_tiles;
+    sp.segs = h->d_segs; sp.viol = h->d_viol; sp.ctr = h->d_ctr; sp.k = h->k; sp.min_resident = h->min_resident;
+    sp.resident_cap = h->resident_cap; sp.eager = (h->flags >> 8) & 0xFFu; sp.prefetch_tiles = prefetch_distance(h->flags);
+    sp.round = round;
+    sp.orig_id = h->use_orig_id ? h->d_orig_id : nullptr; sp.id_base = h->id_base;
+    if (p2p_tag) {
+        sp.p2p = h->d_p2p_link; sp.p2p_parity = p2p_parity; sp.p2p_tag = p2p_tag;
+    } else if (h->urec_cap) {
+        sp.urec = h->d_urec; sp.urec_cap = h->urec_cap;
+    }
+    return sp;
+}
+
 // Enqueues one sweep.  Invariant: ctr->n_viol == 0 on entry (kept by the MIS kernel / reset kernel).
 // p2p_tag != 0: sharded P2P mode -- violated records are stored into every GPU's exchange region.
 int enqueue_sweep(alll_handle h, uint32_t p2p_parity = 0, uint32_t p2p_tag = 0, uint32_t round = 0xFFFFFFFFu)
@@ -402,17 +419,7 @@ int enqueue_sweep(alll_handle h, uint32_t p2p_parity = 0, uint32_t p2p_tag = 0, 
     }
     if (h->k) {
         if (h->n_tiles == 0 && !p2p_tag) return ALLL_OK;      // (a P2P rank without clauses still has to publish its round)
-        SweepParams sp{};
-        sp.planes = h->d_planes; sp.m_pad = h->m_pad; sp.bits = h->d_bits; sp.n_words = h->n_words_alloc;
-        sp.bucket_words = h->bucket_words; sp.n_buckets = h->n_buckets; sp.n_tiles = h->n_tiles;
-        sp.segs = h->d_segs; sp.viol = h->d_viol; sp.ctr = h->d_ctr; sp.k = h->k; sp.min_resident = h->min_resident; sp.resident_cap = h->resident_cap; sp.eager = (h->flags >> 8) & 0xFFu; sp.prefetch_tiles = prefetch_distance(h->flags);
-        sp.round = round;
-        sp.orig_id = h->use_orig_id ? h->d_orig_id : nullptr; sp.id_base = h->id_base;
-        if (p2p_tag) {
-            sp.p2p = h->d_p2p_link; sp.p2p_parity = p2p_parity; sp.p2p_tag = p2p_tag;
-        } else if (h->urec_cap) {
-            sp.urec = h->d_urec; sp.urec_cap = h->urec_cap;
-        }
+        const SweepParams sp = sweep_params(h, p2p_parity, p2p_tag, round);
         CK(launch_sweep_planes(sp, h->resident_all, h->sweep_grid, h->stream));
     } else {
         if (h->m == 0) return ALLL_OK;
@@ -432,6 +439,20 @@ int enqueue_mis_resample(alll_handle h, uint64_t seed, uint32_t round, bool with
                                 h->gen_mode ? (uint32_t)h->gen_cap : 0u, h->stream));
     h->launches += with_grid ? 2 : 1;    // cluster kernel (+ cooperative grid kernel)
     return ALLL_OK;
+}
+
+// ALLL_TRACE: %globaltimer stamps written by the kernels (us relative to the sweep entry of each round)
+void print_phases(const Counters &c, uint64_t rounds)
+{
+    const uint64_t nr = std::min<uint64_t>(rounds, DBG_ROUNDS);
+    for (uint64_t r = 0; r < nr; r++) {
+        const unsigned long long *d = c.dbg[r];
+        auto us = [&](int i) { return d[i] >= d[0] ? (double)(d[i] - d[0]) * 1e-3 : -1.0; };
+        const double gap = r ? (double)(d[0] - c.dbg[r - 1][6]) * 1e-3 : 0.0;
+        fprintf(stderr, "[alll phases] round %llu: path=%llu steps=%llu | prev round end -> sweep entry %.1f | mis entry %.1f "
+                        "|U| known %.1f gather %.1f steps %.1f resample %.1f finished %.1f (us after sweep entry)\n",
+                (unsigned long long)r, d[7] & 0xFF, d[7] >> 8, gap, us(1), us(2), us(3), us(4), us(5), us(6));
+    }
 }
 
 int fetch_counters(alll_handle h)
@@ -766,6 +787,39 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
     CK(launch_reset_counters(h->d_ctr, 1, h->stream)); h->launches++;
     cudaEvent_t ev_begin = h->ev[2 * MAX_TIMED_ROUNDS];
     CK(cudaEventRecord(ev_begin, h->stream));
+    const bool trace = getenv("ALLL_TRACE") != nullptr;
+
+    if (h->persistent_ok && h->k && h->n_tiles && !h->gen_mode && !h->incr_ready && !(h->flags & ALLL_FLAG_HOST_ROUND_LOOP)) {
+        // The whole round loop in one cooperative launch (sweep.cu: solve_persistent_kernel).
+        if (max_rounds == 0) max_rounds = 1;
+        const uint32_t cap = (uint32_t)std::min<uint64_t>(max_rounds, 0xFFFFFFFFull);
+        const SweepParams sp = sweep_params(h, 0u, 0u, 0u);
+        CK(launch_solve_persistent(sp, h->resident_all, h->sweep_grid, clause_view(h), h->kmax, h->d_state, h->d_s,
+                                   mis_scratch(h, true), h->n_vars, seed, cap, h->stream));
+        h->launches++;
+        cudaEvent_t ev_end = h->ev[2 * MAX_TIMED_ROUNDS + 1];
+        CK(cudaEventRecord(ev_end, h->stream));
+        if (int rc = fetch_counters(h)) return rc;
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+        CK(launch_reset_counters(h->d_ctr, 0, h->stream)); h->launches++;      // clears `done` for the single-step calls
+        CK(cudaStreamSynchronize(h->stream));
+        const Counters &c = *h->h_ctr;
+        if (trace) print_phases(c, c.n_iterations);
+        const int status = c.done ? ALLL_OK : ALLL_MAX_ROUNDS;
+        stats->n_iterations = c.n_iterations;
+        stats->n_resamples = c.n_resamples;
+        stats->sum_mis_size = c.sum_mis;
+        stats->avg_mis_size = c.n_iterations ? c.sum_mis / c.n_iterations : 0;     // SATInstance.h:317
+        stats->n_clause_evals = h->m * c.n_iterations;
+        stats->n_luby_steps = c.n_luby_steps;
+        stats->n_kernel_launches = h->launches - launches0;
+        stats->solve_ms = ms;
+        stats->sweep_ms = (double)c.t_sweep_ns * 1e-6;            // as block 0 saw it (%globaltimer): sweep + its grid barrier
+        stats->between_sweeps_ms = (double)c.t_mis_ns * 1e-6;
+        stats->status = status;
+        return status;
+    }
 
     // Pipelined round loop (replaces the per-round host control of SATInstance.h:260-311): up to
     // ROUNDS_IN_FLIGHT rounds are enqueued ahead of the last round whose counters the host has seen.  The
@@ -774,7 +828,6 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
     int status = ALLL_MAX_ROUNDS;
     uint64_t issued = 0, retired = 0;
     const unsigned long long seq0 = h->seq;
-    const bool trace = getenv("ALLL_TRACE") != nullptr;
     uint64_t last_seen_u = h->m;          // |U| of the newest retired round: violated sets shrink, so once it fits one
                                           // cluster the cooperative grid kernel is no longer enqueued
     cudaEvent_t ev_last = ev_begin;
@@ -849,18 +902,7 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
     CK(launch_reset_counters(h->d_ctr, 0, h->stream)); h->launches++;      // clears `done` for the single-step calls
     CK(cudaStreamSynchronize(h->stream));
     const Counters &c = *h->h_ctr;
-    if (trace) {
-        // %globaltimer stamps written by the kernels (us relative to the sweep entry of each round)
-        const uint64_t nr = std::min<uint64_t>(useful_rounds, DBG_ROUNDS);
-        for (uint64_t r = 0; r < nr; r++) {
-            const unsigned long long *d = c.dbg[r];
-            auto us = [&](int i) { return d[i] >= d[0] ? (double)(d[i] - d[0]) * 1e-3 : -1.0; };
-            const double gap = r ? (double)(d[0] - c.dbg[r - 1][6]) * 1e-3 : 0.0;
-            fprintf(stderr, "[alll phases] round %llu: path=%llu steps=%llu | prev round end -> sweep entry %.1f | mis entry %.1f "
-                            "|U| known %.1f gather %.1f steps %.1f resample %.1f finished %.1f (us after sweep entry)\n",
-                    (unsigned long long)r, d[7] & 0xFF, d[7] >> 8, gap, us(1), us(2), us(3), us(4), us(5), us(6));
-        }
-    }
+    if (trace) print_phases(c, useful_rounds);
     stats->n_iterations = c.n_iterations;
     stats->n_resamples = c.n_resamples;
     stats->sum_mis_size = c.sum_mis;

@@ -20,6 +20,7 @@
 //   * violated slots are compacted per warp with __ballot_sync/__popc into a shared-memory staging
 //     buffer and flushed with one global atomicAdd per >= 32 entries.
 #include "alll_device.cuh"
+#include "mis_body.cuh"
 
 namespace alll {
 
@@ -34,14 +35,33 @@ namespace {
 // instead of chasing k literal planes through cold DRAM on its critical path.  Here the k + 1 scattered reads overlap
 // with the streaming of the other warps.  Out of line: it runs once per >= 32 violated clauses and must not cost the
 // streaming loop registers.
-__device__ __noinline__ void write_records(const SweepParams *sp, uint32_t wbuf, uint32_t g, uint32_t count, uint32_t lane)
+// (Arguments by value: taking the address of the kernel's parameter block would move it to local memory, and the
+// streaming loop would then read its parameters through L1/L2 instead of the constant bank -- measured 0.22 -> 0.30 ms.)
+__device__ __noinline__ void write_records(uint32_t *__restrict__ urec, const uint32_t *__restrict__ planes, uint64_t m_pad,
+                                           const uint32_t *__restrict__ orig_id, uint32_t id_base, uint32_t k, uint32_t wbuf,
+                                           uint32_t g, uint32_t count, uint32_t lane)
 {
-    const uint32_t w = sp->k + 1;
-    for (uint32_t i = lane; i < count; i += 32) {
-        const uint32_t slot = g_smem[wbuf + i];
-        uint32_t *rec = sp->urec + (uint64_t)(g + i) * w;
-        rec[0] = (sp->orig_id ? sp->orig_id[slot] : slot) + sp->id_base;
-        for (uint32_t j = 1; j < w; j++) rec[j] = sp->planes[(uint64_t)(j - 1) * sp->m_pad + slot];
+    // One (clause, word) pair per lane and pass; k <= 8, count <= 63 => at most 18 passes.  All scattered reads are issued
+    // before the first store (one DRAM round trip per flush instead of one per pass), the stores of a pass are consecutive.
+    const uint32_t w = k + 1, total = count * w;
+    uint32_t *out = urec + (uint64_t)g * w;
+    for (uint32_t t0 = 0; t0 < total; t0 += 32 * 9) {
+        uint32_t val[9];
+#pragma unroll
+        for (int q = 0; q < 9; q++) {
+            const uint32_t t = t0 + q * 32 + lane;
+            val[q] = 0;
+            if (t < total) {
+                const uint32_t i = t / w, j = t - i * w;
+                const uint32_t slot = g_smem[wbuf + i];
+                val[q] = j == 0 ? (orig_id ? __ldg(orig_id + slot) : slot) + id_base : __ldg(planes + (uint64_t)(j - 1) * m_pad + slot);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 9; q++) {
+            const uint32_t t = t0 + q * 32 + lane;
+            if (t < total) out[t] = val[q];
+        }
     }
 }
 
@@ -49,6 +69,7 @@ struct WarpCompactor {
     uint32_t wbuf;       // index in g_smem of this warp's staging buffer (WBUF entries)
     uint32_t *viol;
     Counters *ctr;
+    unsigned int *n_viol;   // where |U| is accumulated (ctr->n_viol, or the round-parity counter of the persistent solve kernel)
     uint32_t count;      // warp-uniform
     uint32_t lane;
     const SweepParams *sp;   // non-NULL with sp->p2p set: sharded P2P mode
@@ -57,7 +78,7 @@ struct WarpCompactor {
     {
         __syncwarp();
         unsigned int g = 0;
-        if (lane == 0) g = atomicAdd(&ctr->n_viol, count);
+        if (lane == 0) g = atomicAdd(n_viol, count);
         g = __shfl_sync(0xffffffffu, g, 0);
         if (sp != nullptr && sp->p2p != nullptr) {
             // fused compute + collective: the violated clauses go straight into every GPU's receive slot for this
@@ -79,7 +100,8 @@ struct WarpCompactor {
             }
         } else {
             for (uint32_t i = lane; i < count; i += 32) viol[g + i] = g_smem[wbuf + i];
-            if (sp != nullptr && sp->urec != nullptr && (uint64_t)g + count <= sp->urec_cap) write_records(sp, wbuf, g, count, lane);
+            if (sp != nullptr && sp->urec != nullptr && (uint64_t)g + count <= sp->urec_cap)
+                write_records(sp->urec, sp->planes, sp->m_pad, sp->orig_id, sp->id_base, sp->k, wbuf, g, count, lane);
         }
         __syncwarp();
         count = 0;
@@ -347,15 +369,13 @@ struct SurvivorQueue {
 // consecutive clause slots of a tile and keeps TWO tiles of literals in registers: the next tile's E x 128-bit
 // loads are in flight while the current tile is evaluated (register double buffering).
 template <int K, int RB, int RC, int E>
-__global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const SweepParams p)
+__device__ __forceinline__ void sweep_planes_body(const SweepParams &p, unsigned int *n_viol_ctr)
 {
     constexpr bool RESIDENT_ALL = RB >= K;
     constexpr int RBE = RB < E ? RB : E;
-    if (__ldcg(&p.ctr->done) || __ldcg(&p.ctr->incr_next)) return;   // behind the terminal round / this round is incremental
-    if (blockIdx.x == 0 && threadIdx.x == 0 && p.round < DBG_ROUNDS) p.ctr->dbg[p.round][0] = global_ns();
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = threadIdx.x >> 5;
-    WarpCompactor out{p.bucket_words + warp * WBUF, p.viol, p.ctr, 0u, lane, &p};
+    WarpCompactor out{p.bucket_words + warp * WBUF, p.viol, p.ctr, n_viol_ctr, 0u, lane, &p};
     SurvivorQueue<K, E, RESIDENT_ALL> parked{p.bucket_words + (SWEEP_THREADS / 32) * WBUF + warp * QBUF, 0u, lane};
 
     const uint32_t t0 = (uint32_t)(((uint64_t)blockIdx.x * p.n_tiles) / gridDim.x);
@@ -422,13 +442,91 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const Sw
     p2p_publish(p);
 }
 
+template <int K, int RB, int RC, int E>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const SweepParams p)
+{
+    if (__ldcg(&p.ctr->done) || __ldcg(&p.ctr->incr_next)) return;   // behind the terminal round / this round is incremental
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.round < DBG_ROUNDS) p.ctr->dbg[p.round][0] = global_ns();
+    sweep_planes_body<K, RB, RC, E>(p, &p.ctr->n_viol);
+}
+
+// ---- the whole solve in one launch ------------------------------------------------------------------------
+// Replaces the round loop of parallel_solve (SATInstance.h:260-311) for the plane layout: sweep -> grid barrier ->
+// independent set + resample -> grid barrier, repeated on the device until a sweep finds no violated clause.
+// Why one kernel: the independent-set phases are a few microseconds of work but, launched as kernels of their own
+// behind a sweep that has just streamed > 1 GB through L2, they spend 20-100 us per round fetching their code cold
+// from DRAM (every phase cost about 0.6 us per 128-byte line of instructions it touched, whatever the size of U --
+// profiles/r01_mis_phases.md).  A persistent kernel keeps that code in the SMs' instruction caches from the second
+// round on, and launch gaps, event records and the host round trip disappear as well.
+// One CTA per SM (cooperative launch).  |U| is accumulated in one of two counters selected by round parity: the
+// one for round r+1 is cleared during the independent-set phase of round r, when nobody adds to it.
+template <int K, int RB, int RC, int E>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(const SweepParams sp, const MisParams mp_arg,
+                                                                           const uint32_t max_rounds)
+{
+    // The independent-set bodies are out-of-line functions: they get the parameter block through a pointer, and a
+    // pointer to kernel parameters would force a per-thread local-memory copy.  One copy per CTA in shared memory.
+    __shared__ MisParams s_mp;
+    if (threadIdx.x == 0) s_mp = mp_arg;
+    __syncthreads();
+    const MisParams &mp = s_mp;
+    GridBarrier bar{cg::this_grid()};
+    Counters *const c = sp.ctr;
+    const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
+    const uint32_t first = blockIdx.x * SWEEP_THREADS + threadIdx.x, stride = gridDim.x * SWEEP_THREADS;
+    unsigned long long t_sweep = 0, t_mis = 0;
+    for (uint32_t round = 0; round < max_rounds; ++round) {
+        unsigned long long t0 = 0, t1 = 0;
+        if (lead) {
+            t0 = global_ns();
+            if (round < DBG_ROUNDS) c->dbg[round][0] = t0;
+        }
+        sweep_planes_body<K, RB, RC, E>(sp, &c->n_viol_pp[round & 1u]);
+        bar.sync();
+        const uint32_t n_u = gm::ld_cg(&c->n_viol_pp[round & 1u]);
+        if (lead) {
+            t1 = global_ns();
+            t_sweep += t1 - t0;
+            if (round < DBG_ROUNDS) { c->dbg[round][1] = t1; c->dbg[round][2] = t1; }
+            c->n_viol_pp[(round + 1u) & 1u] = 0;
+        }
+        if (n_u == 0) {                                  // SATInstance.h:285-287; the terminal sweep counts (:261)
+            if (lead) {
+                gm::red_add(&c->n_iterations, 1ull);
+                c->last_n_viol = 0;
+                c->last_n_s = 0;
+                c->last_resampled = 0;
+                c->done = 1;
+            }
+            break;
+        }
+        if (n_u <= SMALL_U && (uint64_t)n_u * mp.kmax <= HSLOTS / 2 && mp.small_ok) {
+            if (blockIdx.x == 0) {
+                mis_small_body(mp, round, nullptr, n_u);
+                if (threadIdx.x == 0) finish_round(mp, round, n_u, 0u);
+            }
+        } else {
+            if ((uint64_t)n_u <= (uint64_t)stride * mp.cache_items) mis_resample_body<GridBarrier, true>(mp, round, bar, nullptr, first, stride, n_u);
+            else mis_resample_body<GridBarrier, false>(mp, round, bar, nullptr, first, stride, n_u);
+            bar.sync();
+            if (lead) finish_round(mp, round, n_u, 2u);
+        }
+        bar.sync();                                      // new assignment visible to every SM before it is staged again
+        if (lead) t_mis += global_ns() - t1;
+    }
+    if (lead) {
+        c->t_sweep_ns = t_sweep;
+        c->t_mis_ns = t_mis;
+    }
+}
+
 // Run-time clause width (k > 8): planes are loaded lazily level by level; no prefetch.
 template <bool RESIDENT_ALL>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_generic_kernel(const SweepParams p)
 {
     if (__ldcg(&p.ctr->done) || __ldcg(&p.ctr->incr_next)) return;
     const uint32_t lane = threadIdx.x & 31u;
-    WarpCompactor comp{p.bucket_words + (threadIdx.x >> 5) * WBUF, p.viol, p.ctr, 0u, lane, nullptr};
+    WarpCompactor comp{p.bucket_words + (threadIdx.x >> 5) * WBUF, p.viol, p.ctr, &p.ctr->n_viol, 0u, lane, nullptr};
 
     const uint32_t t0 = (uint32_t)(((uint64_t)blockIdx.x * p.n_tiles) / gridDim.x);
     const uint32_t t1 = (uint32_t)(((uint64_t)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
@@ -465,7 +563,7 @@ __global__ void __launch_bounds__(256) sweep_csr_kernel(const uint64_t *__restri
 {
     if (__ldcg(&ctr->done)) return;
     const uint32_t lane = threadIdx.x & 31u;                       // launched with 8 * WBUF words of dynamic smem
-    WarpCompactor comp{(threadIdx.x >> 5) * WBUF, viol, ctr, 0u, lane, nullptr};
+    WarpCompactor comp{(threadIdx.x >> 5) * WBUF, viol, ctr, &ctr->n_viol, 0u, lane, nullptr};
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t m_round = (m + 31) / 32 * 32;
     for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < m_round; c += stride) {
@@ -491,28 +589,54 @@ __global__ void __launch_bounds__(256) sweep_csr_kernel(const uint64_t *__restri
 
 // ---- launchers ------------------------------------------------------------------------
 
+namespace {
+enum Op { OP_LAUNCH, OP_CONFIGURE, OP_PERSIST_LAUNCH, OP_PERSIST_CONFIGURE };
+struct PersistArgs {
+    const MisParams *mp;
+    uint32_t max_rounds;
+    int *max_ctas_per_sm;     // OP_PERSIST_CONFIGURE: occupancy of the persistent kernel with the requested shared memory
+};
+} // namespace
+
 template <int K, int RB, int RC, int E>
-static cudaError_t launch_planes_e(const SweepParams &p, uint32_t grid, size_t smem, cudaStream_t s, bool configure_only)
+static cudaError_t launch_planes_e(const SweepParams &p, uint32_t grid, size_t smem, cudaStream_t s, Op op, const PersistArgs *pa)
 {
-    if (configure_only)   // function attributes are per device: the handle configures its kernel once at upload
+    switch (op) {
+    case OP_CONFIGURE:   // function attributes are per device: the handle configures its kernel once at upload
         return cudaFuncSetAttribute(sweep_planes_kernel<K, RB, RC, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    sweep_planes_kernel<K, RB, RC, E><<<grid, SWEEP_THREADS, smem, s>>>(p);
-    return cudaGetLastError();
+    case OP_LAUNCH:
+        sweep_planes_kernel<K, RB, RC, E><<<grid, SWEEP_THREADS, smem, s>>>(p);
+        return cudaGetLastError();
+    case OP_PERSIST_CONFIGURE: {
+        cudaError_t e = cudaFuncSetAttribute(solve_persistent_kernel<K, RB, RC, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(pa->max_ctas_per_sm, solve_persistent_kernel<K, RB, RC, E>,
+                                                             SWEEP_THREADS, smem);
+    }
+    case OP_PERSIST_LAUNCH: {
+        uint32_t max_rounds = pa->max_rounds;
+        void *args[] = {(void *)&p, (void *)pa->mp, (void *)&max_rounds};
+        return cudaLaunchCooperativeKernel((const void *)solve_persistent_kernel<K, RB, RC, E>, dim3(grid), dim3(SWEEP_THREADS),
+                                           args, smem, s);
+    }
+    }
+    return cudaErrorInvalidValue;
 }
 
 // E = min(K, EAGER_PLANES) planes are streamed (4 / 5 / 6 / 8 were measured at k = 8: 5 is fastest, profiles/).
 template <int K, int RB, int RC>
-static cudaError_t launch_planes(const SweepParams &p, uint32_t grid, size_t smem, cudaStream_t s, bool configure_only)
+static cudaError_t launch_planes(const SweepParams &p, uint32_t grid, size_t smem, cudaStream_t s, Op op, const PersistArgs *pa)
 {
     constexpr int E = K < (int)EAGER_PLANES ? K : (int)EAGER_PLANES;
-    return launch_planes_e<K, RB, RC, E>(p, grid, smem, s, configure_only);
+    return launch_planes_e<K, RB, RC, E>(p, grid, smem, s, op, pa);
 }
 
 template <bool R>
-static cudaError_t launch_generic(const SweepParams &p, uint32_t grid, size_t smem, cudaStream_t s, bool configure_only)
+static cudaError_t launch_generic(const SweepParams &p, uint32_t grid, size_t smem, cudaStream_t s, Op op)
 {
-    if (configure_only)
+    if (op == OP_CONFIGURE)
         return cudaFuncSetAttribute(sweep_planes_generic_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (op != OP_LAUNCH) return cudaErrorNotSupported;      // no persistent kernel for k > 8
     sweep_planes_generic_kernel<R><<<grid, SWEEP_THREADS, smem, s>>>(p);
     return cudaGetLastError();
 }
@@ -520,35 +644,37 @@ static cudaError_t launch_generic(const SweepParams &p, uint32_t grid, size_t sm
 // resident_all: every plane is resident-only (RB = RC = K).  Otherwise RC = min(K, RESIDENT_CAP) and
 // RB = min(p.min_resident, 2, RC) as measured by the upload pass.
 template <int K, int RC>
-static cudaError_t dispatch_rb(const SweepParams &p, uint32_t grid, size_t smem, cudaStream_t s, bool cfg)
+static cudaError_t dispatch_rb(const SweepParams &p, uint32_t grid, size_t smem, cudaStream_t s, Op op, const PersistArgs *pa)
 {
     const uint32_t rb = p.min_resident < 2u ? p.min_resident : 2u;
-    if (rb >= 2 && RC >= 2) return launch_planes<K, (RC < 2 ? RC : 2), RC>(p, grid, smem, s, cfg);
-    if (rb >= 1 && RC >= 1) return launch_planes<K, (RC < 1 ? RC : 1), RC>(p, grid, smem, s, cfg);
-    return launch_planes<K, 0, RC>(p, grid, smem, s, cfg);
+    if (rb >= 2 && RC >= 2) return launch_planes<K, (RC < 2 ? RC : 2), RC>(p, grid, smem, s, op, pa);
+    if (rb >= 1 && RC >= 1) return launch_planes<K, (RC < 1 ? RC : 1), RC>(p, grid, smem, s, op, pa);
+    return launch_planes<K, 0, RC>(p, grid, smem, s, op, pa);
 }
 
 template <int K>
-static cudaError_t dispatch_class(const SweepParams &p, bool resident_all, uint32_t grid, size_t smem, cudaStream_t s, bool cfg)
+static cudaError_t dispatch_class(const SweepParams &p, bool resident_all, uint32_t grid, size_t smem, cudaStream_t s, Op op,
+                                  const PersistArgs *pa)
 {
-    if (resident_all) return launch_planes<K, K, K>(p, grid, smem, s, cfg);
+    if (resident_all) return launch_planes<K, K, K>(p, grid, smem, s, op, pa);
     // RC = min(K, RESIDENT_CAP): 2 / 3 / 4 resident-placed literals were measured at k = 8, 3 is fastest (profiles/)
     constexpr int RC_DEFAULT = K < (int)RESIDENT_CAP ? K : (int)RESIDENT_CAP;
-    return dispatch_rb<K, RC_DEFAULT>(p, grid, smem, s, cfg);
+    return dispatch_rb<K, RC_DEFAULT>(p, grid, smem, s, op, pa);
 }
 
-static cudaError_t dispatch_k(const SweepParams &p, bool resident_all, uint32_t grid, size_t smem, cudaStream_t s, bool cfg)
+static cudaError_t dispatch_k(const SweepParams &p, bool resident_all, uint32_t grid, size_t smem, cudaStream_t s, Op op,
+                              const PersistArgs *pa = nullptr)
 {
     switch (p.k) {
-    case 1: return dispatch_class<1>(p, resident_all, grid, smem, s, cfg);
-    case 2: return dispatch_class<2>(p, resident_all, grid, smem, s, cfg);
-    case 3: return dispatch_class<3>(p, resident_all, grid, smem, s, cfg);
-    case 4: return dispatch_class<4>(p, resident_all, grid, smem, s, cfg);
-    case 5: return dispatch_class<5>(p, resident_all, grid, smem, s, cfg);
-    case 6: return dispatch_class<6>(p, resident_all, grid, smem, s, cfg);
-    case 7: return dispatch_class<7>(p, resident_all, grid, smem, s, cfg);
-    case 8: return dispatch_class<8>(p, resident_all, grid, smem, s, cfg);
-    default: return resident_all ? launch_generic<true>(p, grid, smem, s, cfg) : launch_generic<false>(p, grid, smem, s, cfg);
+    case 1: return dispatch_class<1>(p, resident_all, grid, smem, s, op, pa);
+    case 2: return dispatch_class<2>(p, resident_all, grid, smem, s, op, pa);
+    case 3: return dispatch_class<3>(p, resident_all, grid, smem, s, op, pa);
+    case 4: return dispatch_class<4>(p, resident_all, grid, smem, s, op, pa);
+    case 5: return dispatch_class<5>(p, resident_all, grid, smem, s, op, pa);
+    case 6: return dispatch_class<6>(p, resident_all, grid, smem, s, op, pa);
+    case 7: return dispatch_class<7>(p, resident_all, grid, smem, s, op, pa);
+    case 8: return dispatch_class<8>(p, resident_all, grid, smem, s, op, pa);
+    default: return resident_all ? launch_generic<true>(p, grid, smem, s, op) : launch_generic<false>(p, grid, smem, s, op);
     }
 }
 
@@ -560,13 +686,59 @@ size_t sweep_planes_smem_bytes(uint32_t bucket_words)
 cudaError_t configure_sweep_planes(const SweepParams &p, bool resident_all)
 {
     const size_t smem = sweep_planes_smem_bytes(p.bucket_words);
-    return dispatch_k(p, resident_all, 0, smem, 0, true);
+    return dispatch_k(p, resident_all, 0, smem, 0, OP_CONFIGURE);
 }
 
 cudaError_t launch_sweep_planes(const SweepParams &p, bool resident_all, uint32_t grid, cudaStream_t s)
 {
     const size_t smem = sweep_planes_smem_bytes(p.bucket_words);
-    return dispatch_k(p, resident_all, grid, smem, s, false);
+    return dispatch_k(p, resident_all, grid, smem, s, OP_LAUNCH);
+}
+
+// ---- persistent solve kernel: shared memory = the sweep's, or what the independent-set phases need if that is more
+static size_t persistent_smem_bytes(uint32_t bucket_words, uint32_t kmax)
+{
+    const size_t small_words = mis_small_words(SWEEP_THREADS, kmax);
+    const size_t one_item = (size_t)SWEEP_THREADS * mis_cache_words(kmax);
+    size_t b = sweep_planes_smem_bytes(bucket_words);
+    if (small_words * 4 <= 200u * 1024u) b = b > small_words * 4 ? b : small_words * 4;
+    else if (one_item * 4 <= 200u * 1024u) b = b > one_item * 4 ? b : one_item * 4;
+    return b;
+}
+
+static void persistent_fill(const SweepParams &p, MisParams &mp, size_t smem)
+{
+    mp.cache_items = (uint32_t)((smem / 4 / SWEEP_THREADS) / mis_cache_words(mp.kmax));
+    mp.small_ok = mis_small_words(SWEEP_THREADS, mp.kmax) * 4 <= smem ? 1u : 0u;
+    (void)p;
+}
+
+// ok_out: 1 when the instance can be solved by the persistent kernel on this device (k <= 8, one CTA per SM fits)
+cudaError_t configure_solve_persistent(const SweepParams &p, bool resident_all, uint32_t kmax, int *ok_out)
+{
+    *ok_out = 0;
+    if (p.k == 0 || p.k > 8) return cudaSuccess;
+    int per_sm = 0;
+    PersistArgs pa{nullptr, 0u, &per_sm};
+    const cudaError_t e = dispatch_k(p, resident_all, 0, persistent_smem_bytes(p.bucket_words, kmax), 0, OP_PERSIST_CONFIGURE, &pa);
+    if (e != cudaSuccess) return e;
+    *ok_out = per_sm >= 1;
+    return cudaSuccess;
+}
+
+cudaError_t launch_solve_persistent(const SweepParams &p, bool resident_all, uint32_t grid, const ClauseView &cv, uint32_t kmax,
+                                    uint8_t *state, uint32_t *s_slots, const MisScratch &sc, uint64_t n_vars, uint64_t seed,
+                                    uint32_t max_rounds, cudaStream_t s)
+{
+    const size_t smem = persistent_smem_bytes(p.bucket_words, kmax);
+    MisParams mp{};
+    mp.cv = cv; mp.viol = p.viol; mp.state = state; mp.s_slots = s_slots;
+    mp.claim = sc.claim;
+    mp.n_vars = n_vars; mp.bits = const_cast<uint32_t *>(p.bits); mp.ctr = p.ctr; mp.seed = seed; mp.kmax = kmax;
+    mp.urec = sc.urec; mp.urec_cap = sc.urec_cap;
+    persistent_fill(p, mp, smem);
+    PersistArgs pa{&mp, max_rounds, nullptr};
+    return dispatch_k(p, resident_all, grid, smem, s, OP_PERSIST_LAUNCH, &pa);
 }
 
 cudaError_t launch_sweep_csr(const uint64_t *off, const uint32_t *lit, uint64_t m, const uint32_t *bits,

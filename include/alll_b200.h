@@ -70,6 +70,11 @@ typedef struct {
 #define ALLL_FLAG_INCREMENTAL 4u
 #define ALLL_FLAG_FORCE_CSR 8u     /* keep ragged input on the CSR kernels instead of padding it onto the plane layout */
 #define ALLL_FLAG_INCR_DIVISOR_LOG2(x) ((uint32_t)(x) << 24)
+/* alll_solve runs the whole round loop of a plane-layout instance (k <= 8) as ONE cooperative kernel (sweep -> grid
+ * barrier -> independent set + resample -> grid barrier, all rounds on the device).  This flag keeps the round loop on
+ * the host instead, one kernel per phase with per-round CUDA events -- same trajectory, slower between sweeps; it is
+ * what incremental, enumerated, CSR and sharded solves use anyway. */
+#define ALLL_FLAG_HOST_ROUND_LOOP 16u
 
 /* Statistics{} of SATInstance.h:25-32 plus device-side counters.
  * n_iterations = resample rounds + 1 (the terminal all-satisfied sweep counts, :261,:285-287);

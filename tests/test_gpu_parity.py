@@ -29,8 +29,10 @@ def upload(solver, n, off, lit):
 
 # a 1 KiB staging budget forces variable-range bucketing (8192 variables per bucket) at test sizes
 # flags=8 keeps ragged input on the CSR kernels (by default it is padded onto the plane layout)
-LAYOUTS = [dict(), dict(sweep_smem_bytes=1024), dict(sweep_smem_bytes=1024, flags=1), dict(flags=8)]
-LAYOUT_IDS = ["resident", "bucketed", "no_bucketing_gather", "force_csr"]
+# flags=16 keeps alll_solve's round loop on the host (one kernel per phase) instead of the persistent solve kernel
+LAYOUTS = [dict(), dict(sweep_smem_bytes=1024), dict(sweep_smem_bytes=1024, flags=1), dict(flags=8), dict(flags=16),
+           dict(sweep_smem_bytes=1024, flags=16)]
+LAYOUT_IDS = ["resident", "bucketed", "no_bucketing_gather", "force_csr", "host_round_loop", "bucketed_host_round_loop"]
 
 
 @pytest.mark.parametrize("layout", LAYOUTS, ids=LAYOUT_IDS)
@@ -227,6 +229,58 @@ def test_cfg2_scale_trajectory(capi, oracle):
         so = oracle.solve(n, off, flat, v, 3)
         assert (st.n_iterations, st.n_resamples, st.sum_mis_size) == (so.n_iterations, so.n_resamples, so.sum_mis_size)
         assert np.array_equal(s.get_assignment(), v) and oracle.verify(off, flat, v)
+
+
+def test_persistent_kernel_and_host_round_loop_agree(capi, oracle):
+    """alll_solve as one cooperative kernel (default) and as a host-driven round loop (flags=16): same statistics, same
+    assignment, same per-round sets as the oracle -- on an instance large enough for the grid-wide independent-set
+    path (|U| > 8192 in the first rounds), the cluster path and the single-CTA path."""
+    from alllsatisfiabilitysolver_b200.instances import bounded_degree_ksat
+
+    n = 500_000
+    lits = bounded_degree_ksat(n, 7, 28, seed=0xA115)
+    m = lits.shape[0]
+    off = np.arange(m + 1, dtype=np.uint64) * np.uint64(7)
+    flat = lits.reshape(-1)
+    v = oracle.randomize(n, 11)
+    so = oracle.solve(n, off, flat, v, 11)
+    assert so.status == 0
+    results = []
+    for flags in (0, 16):
+        with capi.Solver(flags=flags) as s:
+            s.upload_fixedk(n, lits)
+            s.randomize(11)
+            cnt, _ = s.eval()
+            assert cnt > 8192
+            st = s.solve(11)
+            assert st.status == 0
+            assert (st.n_iterations, st.n_resamples, st.sum_mis_size) == (so.n_iterations, so.n_resamples, so.sum_mis_size)
+            assert np.array_equal(s.get_assignment(), v) and s.verify()
+            results.append((st.n_iterations, st.n_luby_steps, st.n_kernel_launches))
+            # a second solve on the same handle starts from clean claim tables and counters
+            s.randomize(12)
+            st2 = s.solve(12)
+            v2 = oracle.randomize(n, 12)
+            so2 = oracle.solve(n, off, flat, v2, 12)
+            assert (st2.n_iterations, st2.n_resamples) == (so2.n_iterations, so2.n_resamples)
+            assert np.array_equal(s.get_assignment(), v2)
+    assert results[0][:2] == results[1][:2]
+    assert results[0][2] <= 3 < results[1][2]          # one solve kernel (+ counter resets) vs one kernel per phase
+
+
+def test_persistent_kernel_round_cap(capi, oracle, golden):
+    """max_rounds ends the persistent kernel with ALLL_MAX_ROUNDS after exactly that many sweeps; the state equals
+    the oracle's after the same number of rounds and a later solve continues from it."""
+    n, off, lit, _ = golden_case(golden, "k7_small")
+    with capi.Solver() as s:
+        upload(s, n, off, lit)
+        s.randomize(4)
+        st = s.solve(4, max_rounds=2)
+        v = oracle.randomize(n, 4)
+        for r in range(2):
+            oracle.round(n, off, lit, v, 4, r)
+        assert st.status == 1 and st.n_iterations == 2
+        assert np.array_equal(s.get_assignment(), v)
 
 
 def test_cfg4_shape_bucketed_full_path(capi, oracle):
