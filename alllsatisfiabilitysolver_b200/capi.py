@@ -20,6 +20,7 @@ STATUS_NAMES = ["OK", "MAX_ROUNDS", "EMPTY_CLAUSE", "BAD_ARG", "CUDA_ERROR", "NC
 FLAG_NO_BUCKETING = 1
 FLAG_INCREMENTAL = 4
 FLAG_FORCE_CSR = 8
+FLAG_P2P_PERSISTENT = 32    # alll_solve_p2p: one persistent kernel per rank (every rank needs its own GPU)
 FLAG_HOST_ROUND_LOOP = 16   # alll_solve: one kernel per phase driven by the host instead of the persistent solve kernel
 
 #: every symbol include/alll_b200.h declares (tests check the library exports exactly these)

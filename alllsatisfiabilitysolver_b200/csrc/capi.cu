@@ -795,7 +795,7 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
         const uint32_t cap = (uint32_t)std::min<uint64_t>(max_rounds, 0xFFFFFFFFull);
         const SweepParams sp = sweep_params(h, 0u, 0u, 0u);
         CK(launch_solve_persistent(sp, h->resident_all, h->sweep_grid, clause_view(h), h->kmax, h->d_state, h->d_s,
-                                   mis_scratch(h, true), h->n_vars, seed, cap, h->stream));
+                                   mis_scratch(h, true), h->n_vars, seed, cap, 0u, h->stream));
         h->launches++;
         cudaEvent_t ev_end = h->ev[2 * MAX_TIMED_ROUNDS + 1];
         CK(cudaEventRecord(ev_end, h->stream));
@@ -1081,6 +1081,40 @@ int alll_solve_p2p(alll_handle h, uint64_t seed, uint64_t max_rounds, uint64_t m
     CK(cudaEventRecord(ev_begin, h->stream));
     if (max_rounds == 0) max_rounds = 1;
     max_rounds = std::min<uint64_t>(max_rounds, (1u << 20) - 2);       // the round lives in 20 bits of the tag
+    if ((h->flags & ALLL_FLAG_P2P_PERSISTENT) && h->persistent_ok && h->k && h->n_tiles) {
+        // every rank: the whole sharded solve in one cooperative launch (sweep.cu: solve_persistent_kernel, p2p branch)
+        const SweepParams sp = sweep_params(h, 0u, 1u, 0u);              // (tag != 0 selects the P2P form; the kernel derives parity / tag per round)
+        ClauseView pcv{};
+        pcv.k = h->k;
+        CK(launch_solve_persistent(sp, h->resident_all, h->sweep_grid, pcv, h->k, h->d_sh_state, h->d_sh_s, mis_scratch(h, false),
+                                   h->n_vars, seed, (uint32_t)max_rounds, epoch, h->stream));
+        h->launches++;
+        cudaEvent_t ev_end = h->ev[2 * MAX_TIMED_ROUNDS + 1];
+        CK(cudaEventRecord(ev_end, h->stream));
+        if (int rc = fetch_counters(h)) return rc;
+        float pms = 0.f;
+        CK(cudaEventElapsedTime(&pms, ev_begin, ev_end));
+        const Counters c = *h->h_ctr;
+        CK(launch_reset_counters(h->d_ctr, 0, h->stream)); h->launches++;
+        CK(cudaStreamSynchronize(h->stream));
+        if (getenv("ALLL_TRACE")) print_phases(c, c.n_iterations);
+        if (c.p2p_error || c.done == 2)
+            return fail(h, c.p2p_error == 1 ? ALLL_CAPACITY : ALLL_CUDA_ERROR,
+                        c.p2p_error == 1 ? "P2P exchange region too small for a round's violated records"
+                                         : "P2P exchange: a peer did not publish its round in time");
+        stats->n_iterations = c.n_iterations;
+        stats->n_resamples = c.n_resamples;
+        stats->sum_mis_size = c.sum_mis;
+        stats->avg_mis_size = c.n_iterations ? c.sum_mis / c.n_iterations : 0;
+        stats->n_clause_evals = m_global * c.n_iterations;
+        stats->n_luby_steps = c.n_luby_steps;
+        stats->n_kernel_launches = h->launches - launches0;
+        stats->solve_ms = pms;
+        stats->sweep_ms = (double)c.t_sweep_ns * 1e-6;
+        stats->between_sweeps_ms = (double)c.t_mis_ns * 1e-6;
+        stats->status = c.done == 1 ? ALLL_OK : ALLL_MAX_ROUNDS;
+        return stats->status;
+    }
     int status = ALLL_MAX_ROUNDS;
     uint64_t issued = 0, retired = 0;
     const unsigned long long seq0 = h->seq;

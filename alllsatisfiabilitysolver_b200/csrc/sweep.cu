@@ -70,6 +70,7 @@ struct WarpCompactor {
     uint32_t *viol;
     Counters *ctr;
     unsigned int *n_viol;   // where |U| is accumulated (ctr->n_viol, or the round-parity counter of the persistent solve kernel)
+    uint32_t p2p_parity; // sharded P2P mode: which of the two record areas this round uses
     uint32_t count;      // warp-uniform
     uint32_t lane;
     const SweepParams *sp;   // non-NULL with sp->p2p set: sharded P2P mode
@@ -88,7 +89,7 @@ struct WarpCompactor {
                 if (lane == 0) { ctr->p2p_error = 1; for (uint32_t q = 0; q < L.world; q++) L.hdr[q]->abort = 1; }
             } else {
                 const uint32_t w = L.k + 1;
-                const uint64_t base = (((uint64_t)sp->p2p_parity * L.world + L.rank) * L.cap + g) * w;
+                const uint64_t base = (((uint64_t)p2p_parity * L.world + L.rank) * L.cap + g) * w;
                 for (uint32_t i = lane; i < count; i += 32) {
                     const uint32_t slot = g_smem[wbuf + i];
                     for (uint32_t j = 0; j < w; j++) {
@@ -368,19 +369,24 @@ struct SurvivorQueue {
 // Compile-time clause width K, of which the first E planes are streamed.  One CTA per SM; each thread owns 4
 // consecutive clause slots of a tile and keeps TWO tiles of literals in registers: the next tile's E x 128-bit
 // loads are in flight while the current tile is evaluated (register double buffering).
-template <int K, int RB, int RC, int E>
-__device__ __forceinline__ void sweep_planes_body(const SweepParams &p, unsigned int *n_viol_ctr)
+// TICKET: (sharded P2P mode) the CTA that finishes last publishes this rank's round to the peers; the persistent solve
+// kernel publishes after its grid barrier instead.
+template <int K, int RB, int RC, int E, bool TICKET>
+__device__ __forceinline__ void sweep_planes_body(const SweepParams &p, unsigned int *n_viol_ctr, uint32_t p2p_parity)
 {
     constexpr bool RESIDENT_ALL = RB >= K;
     constexpr int RBE = RB < E ? RB : E;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = threadIdx.x >> 5;
-    WarpCompactor out{p.bucket_words + warp * WBUF, p.viol, p.ctr, n_viol_ctr, 0u, lane, &p};
+    WarpCompactor out{p.bucket_words + warp * WBUF, p.viol, p.ctr, n_viol_ctr, p2p_parity, 0u, lane, &p};
     SurvivorQueue<K, E, RESIDENT_ALL> parked{p.bucket_words + (SWEEP_THREADS / 32) * WBUF + warp * QBUF, 0u, lane};
 
     const uint32_t t0 = (uint32_t)(((uint64_t)blockIdx.x * p.n_tiles) / gridDim.x);
     const uint32_t t1 = (uint32_t)(((uint64_t)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
-    if (t0 >= t1) { p2p_publish(p); return; }
+    if (t0 >= t1) {
+        if (TICKET) p2p_publish(p);
+        return;
+    }
 
     TileCursor cur;
     cur.init(p, t0);
@@ -439,7 +445,7 @@ __device__ __forceinline__ void sweep_planes_body(const SweepParams &p, unsigned
     }
     if constexpr (E < K) parked.drain(0u, out, p, cur.b * bucket_vars, bucket_vars);
     if (out.count) out.flush();
-    p2p_publish(p);
+    if (TICKET) p2p_publish(p);
 }
 
 template <int K, int RB, int RC, int E>
@@ -447,7 +453,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const Sw
 {
     if (__ldcg(&p.ctr->done) || __ldcg(&p.ctr->incr_next)) return;   // behind the terminal round / this round is incremental
     if (blockIdx.x == 0 && threadIdx.x == 0 && p.round < DBG_ROUNDS) p.ctr->dbg[p.round][0] = global_ns();
-    sweep_planes_body<K, RB, RC, E>(p, &p.ctr->n_viol);
+    sweep_planes_body<K, RB, RC, E, true>(p, &p.ctr->n_viol, p.p2p_parity);
 }
 
 // ---- the whole solve in one launch ------------------------------------------------------------------------
@@ -462,33 +468,63 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const Sw
 // one for round r+1 is cleared during the independent-set phase of round r, when nobody adds to it.
 template <int K, int RB, int RC, int E>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(const SweepParams sp, const MisParams mp_arg,
-                                                                           const uint32_t max_rounds)
+                                                                           const uint32_t max_rounds, const uint32_t epoch)
 {
     // The independent-set bodies are out-of-line functions: they get the parameter block through a pointer, and a
-    // pointer to kernel parameters would force a per-thread local-memory copy.  One copy per CTA in shared memory.
+    // pointer to kernel parameters would force a per-thread local-memory copy.  One copy per CTA in shared memory
+    // (thread 0 also keeps the per-round exchange parity / tag of the sharded mode up to date in it).
     __shared__ MisParams s_mp;
+    __shared__ uint32_t s_prefix[MAX_SHARDS + 1];
     if (threadIdx.x == 0) s_mp = mp_arg;
     __syncthreads();
     const MisParams &mp = s_mp;
     GridBarrier bar{cg::this_grid()};
     Counters *const c = sp.ctr;
     const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
+    const bool p2p = sp.p2p != nullptr;      // clause-range sharded solve: every GPU runs this kernel on its range
     const uint32_t first = blockIdx.x * SWEEP_THREADS + threadIdx.x, stride = gridDim.x * SWEEP_THREADS;
     unsigned long long t_sweep = 0, t_mis = 0;
     for (uint32_t round = 0; round < max_rounds; ++round) {
+        const uint32_t par = round & 1u, tag = ((epoch & 0xFFFu) << 20) | (round + 1u);
         unsigned long long t0 = 0, t1 = 0;
         if (lead) {
             t0 = global_ns();
             if (round < DBG_ROUNDS) c->dbg[round][0] = t0;
         }
-        sweep_planes_body<K, RB, RC, E>(sp, &c->n_viol_pp[round & 1u]);
+        if (threadIdx.x == 0) { s_mp.p2p_parity = par; s_mp.p2p_tag = tag; }
+        sweep_planes_body<K, RB, RC, E, false>(sp, &c->n_viol_pp[par], par);
+        if (p2p) {                                       // this CTA's record stores (NVLink) are ordered before the barrier
+            __syncthreads();
+            if (threadIdx.x == 0) __threadfence_system();
+        }
         bar.sync();
-        const uint32_t n_u = gm::ld_cg(&c->n_viol_pp[round & 1u]);
+        uint32_t n_u;
+        if (p2p) {
+            // fused exchange: the violated records went straight into every GPU's region during the sweep; publish our
+            // count + arrival flag everywhere, then wait for every peer's flag of this round
+            if (lead) {
+                const P2PLink &L = *sp.p2p;
+                const unsigned int total = gm::ld_cg(&c->n_viol_pp[par]);
+                for (uint32_t q = 0; q < L.world; q++) L.hdr[q]->count[par][L.rank] = total;
+                __threadfence_system();
+                for (uint32_t q = 0; q < L.world; q++) *(volatile unsigned int *)&L.hdr[q]->flag[par][L.rank] = tag;
+            }
+            n_u = p2p_wait(mp, s_prefix);
+        } else {
+            n_u = gm::ld_cg(&c->n_viol_pp[par]);
+        }
         if (lead) {
             t1 = global_ns();
             t_sweep += t1 - t0;
             if (round < DBG_ROUNDS) { c->dbg[round][1] = t1; c->dbg[round][2] = t1; }
-            c->n_viol_pp[(round + 1u) & 1u] = 0;
+            c->n_viol_pp[par ^ 1u] = 0;
+        }
+        if (n_u == 0xFFFFFFFFu) {                        // a peer overflowed its exchange area or never arrived: stop
+            if (lead) {
+                c->p2p_error = c->p2p_error ? c->p2p_error : 2;
+                c->done = 2;
+            }
+            break;
         }
         if (n_u == 0) {                                  // SATInstance.h:285-287; the terminal sweep counts (:261)
             if (lead) {
@@ -502,12 +538,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(cons
         }
         if (n_u <= SMALL_U && (uint64_t)n_u * mp.kmax <= HSLOTS / 2 && mp.small_ok) {
             if (blockIdx.x == 0) {
-                mis_small_body(mp, round, nullptr, n_u);
+                mis_small_body(mp, round, s_prefix, n_u);
                 if (threadIdx.x == 0) finish_round(mp, round, n_u, 0u);
             }
         } else {
-            if ((uint64_t)n_u <= (uint64_t)stride * mp.cache_items) mis_resample_body<GridBarrier, true>(mp, round, bar, nullptr, first, stride, n_u);
-            else mis_resample_body<GridBarrier, false>(mp, round, bar, nullptr, first, stride, n_u);
+            if ((uint64_t)n_u <= (uint64_t)stride * mp.cache_items) mis_resample_body<GridBarrier, true>(mp, round, bar, s_prefix, first, stride, n_u);
+            else mis_resample_body<GridBarrier, false>(mp, round, bar, s_prefix, first, stride, n_u);
             bar.sync();
             if (lead) finish_round(mp, round, n_u, 2u);
         }
@@ -526,7 +562,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_generic_kernel(
 {
     if (__ldcg(&p.ctr->done) || __ldcg(&p.ctr->incr_next)) return;
     const uint32_t lane = threadIdx.x & 31u;
-    WarpCompactor comp{p.bucket_words + (threadIdx.x >> 5) * WBUF, p.viol, p.ctr, &p.ctr->n_viol, 0u, lane, nullptr};
+    WarpCompactor comp{p.bucket_words + (threadIdx.x >> 5) * WBUF, p.viol, p.ctr, &p.ctr->n_viol, 0u, 0u, lane, nullptr};
 
     const uint32_t t0 = (uint32_t)(((uint64_t)blockIdx.x * p.n_tiles) / gridDim.x);
     const uint32_t t1 = (uint32_t)(((uint64_t)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
@@ -563,7 +599,7 @@ __global__ void __launch_bounds__(256) sweep_csr_kernel(const uint64_t *__restri
 {
     if (__ldcg(&ctr->done)) return;
     const uint32_t lane = threadIdx.x & 31u;                       // launched with 8 * WBUF words of dynamic smem
-    WarpCompactor comp{(threadIdx.x >> 5) * WBUF, viol, ctr, &ctr->n_viol, 0u, lane, nullptr};
+    WarpCompactor comp{(threadIdx.x >> 5) * WBUF, viol, ctr, &ctr->n_viol, 0u, 0u, lane, nullptr};
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t m_round = (m + 31) / 32 * 32;
     for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < m_round; c += stride) {
@@ -593,7 +629,7 @@ namespace {
 enum Op { OP_LAUNCH, OP_CONFIGURE, OP_PERSIST_LAUNCH, OP_PERSIST_CONFIGURE };
 struct PersistArgs {
     const MisParams *mp;
-    uint32_t max_rounds;
+    uint32_t max_rounds, epoch;
     int *max_ctas_per_sm;     // OP_PERSIST_CONFIGURE: occupancy of the persistent kernel with the requested shared memory
 };
 } // namespace
@@ -614,8 +650,8 @@ static cudaError_t launch_planes_e(const SweepParams &p, uint32_t grid, size_t s
                                                              SWEEP_THREADS, smem);
     }
     case OP_PERSIST_LAUNCH: {
-        uint32_t max_rounds = pa->max_rounds;
-        void *args[] = {(void *)&p, (void *)pa->mp, (void *)&max_rounds};
+        uint32_t max_rounds = pa->max_rounds, epoch = pa->epoch;
+        void *args[] = {(void *)&p, (void *)pa->mp, (void *)&max_rounds, (void *)&epoch};
         return cudaLaunchCooperativeKernel((const void *)solve_persistent_kernel<K, RB, RC, E>, dim3(grid), dim3(SWEEP_THREADS),
                                            args, smem, s);
     }
@@ -719,7 +755,7 @@ cudaError_t configure_solve_persistent(const SweepParams &p, bool resident_all, 
     *ok_out = 0;
     if (p.k == 0 || p.k > 8) return cudaSuccess;
     int per_sm = 0;
-    PersistArgs pa{nullptr, 0u, &per_sm};
+    PersistArgs pa{nullptr, 0u, 0u, &per_sm};
     const cudaError_t e = dispatch_k(p, resident_all, 0, persistent_smem_bytes(p.bucket_words, kmax), 0, OP_PERSIST_CONFIGURE, &pa);
     if (e != cudaSuccess) return e;
     *ok_out = per_sm >= 1;
@@ -728,16 +764,17 @@ cudaError_t configure_solve_persistent(const SweepParams &p, bool resident_all, 
 
 cudaError_t launch_solve_persistent(const SweepParams &p, bool resident_all, uint32_t grid, const ClauseView &cv, uint32_t kmax,
                                     uint8_t *state, uint32_t *s_slots, const MisScratch &sc, uint64_t n_vars, uint64_t seed,
-                                    uint32_t max_rounds, cudaStream_t s)
+                                    uint32_t max_rounds, uint32_t epoch, cudaStream_t s)
 {
     const size_t smem = persistent_smem_bytes(p.bucket_words, kmax);
     MisParams mp{};
-    mp.cv = cv; mp.viol = p.viol; mp.state = state; mp.s_slots = s_slots;
+    mp.cv = cv; mp.viol = p.p2p ? nullptr : p.viol; mp.state = state; mp.s_slots = s_slots;
+    mp.p2p = p.p2p;                                    // sharded: U = the record blocks in our exchange region
     mp.claim = sc.claim;
     mp.n_vars = n_vars; mp.bits = const_cast<uint32_t *>(p.bits); mp.ctr = p.ctr; mp.seed = seed; mp.kmax = kmax;
     mp.urec = sc.urec; mp.urec_cap = sc.urec_cap;
     persistent_fill(p, mp, smem);
-    PersistArgs pa{&mp, max_rounds, nullptr};
+    PersistArgs pa{&mp, max_rounds, epoch, nullptr};
     return dispatch_k(p, resident_all, grid, smem, s, OP_PERSIST_LAUNCH, &pa);
 }
 

@@ -191,11 +191,13 @@ class P2PShardedSolver:
     ``torch.distributed`` is only used once to exchange the 64-byte IPC handles and as a barrier between solves.
     Needs one process per GPU on one node (peer access between all GPUs)."""
 
-    def __init__(self, device: int, rank: int, world: int, group=None):
+    def __init__(self, device: int, rank: int, world: int, group=None, persistent: bool = False):
         from . import capi
 
         self.capi = capi
-        self.solver = capi.Solver(device=device)
+        # persistent: every rank runs its whole solve as ONE cooperative kernel (ALLL_FLAG_P2P_PERSISTENT); only valid
+        # when every rank has a GPU of its own -- the kernels of all ranks must be resident at the same time
+        self.solver = capi.Solver(device=device, flags=capi.FLAG_P2P_PERSISTENT if persistent else 0)
         self.device = torch.device("cuda", device)
         self.rank, self.world, self.group = rank, world, group
         self.epoch = 0

@@ -75,6 +75,11 @@ typedef struct {
  * the host instead, one kernel per phase with per-round CUDA events -- same trajectory, slower between sweeps; it is
  * what incremental, enumerated, CSR and sharded solves use anyway. */
 #define ALLL_FLAG_HOST_ROUND_LOOP 16u
+/* alll_solve_p2p as one persistent kernel per GPU as well (the exchange stays fused: records stored into the peers
+ * during the sweep, count + flag published after the grid barrier, every GPU waits for all flags of the round).
+ * Opt-in because the kernels of all ranks must be resident at the same time: set it only when every rank of the
+ * sharded solve has a GPU of its own (several ranks on ONE device would wait for each other until the 3 s time-out). */
+#define ALLL_FLAG_P2P_PERSISTENT 32u
 
 /* Statistics{} of SATInstance.h:25-32 plus device-side counters.
  * n_iterations = resample rounds + 1 (the terminal all-satisfied sweep counts, :261,:285-287);

@@ -149,7 +149,23 @@ def test_sharded_p2p_fused_exchange_two_gpus():
 
 
 @pytest.mark.gpu
-def test_p2p_mode_single_rank_matches_plain_solve(oracle):
+def test_sharded_p2p_persistent_kernels_two_gpus():
+    """Same, with every rank's solve as one persistent kernel (exchange published after the grid barrier)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29657",
+                        os.path.join(ROOT, "tools", "run_sharded.py"), "--p2p", "--persistent", "--scale", "0.05", "--solves", "3",
+                        "--check"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"ok": true' in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("persistent", [False, True], ids=["kernel_per_phase", "persistent_kernel"])
+def test_p2p_mode_single_rank_matches_plain_solve(oracle, persistent):
     """world = 1 exercises the whole P2P code path (record export, flags, MIS over records) on one GPU."""
     from alllsatisfiabilitysolver_b200.instances import bounded_degree_ksat
     from alllsatisfiabilitysolver_b200.sharded import P2PShardedSolver
@@ -158,7 +174,7 @@ def test_p2p_mode_single_rank_matches_plain_solve(oracle):
     lits = bounded_degree_ksat(n, k, 32, seed=6)
     m = lits.shape[0]
     off = np.arange(m + 1, dtype=np.uint64) * np.uint64(k)
-    ss = P2PShardedSolver(0, 0, 1)
+    ss = P2PShardedSolver(0, 0, 1, persistent=persistent)
     ss.upload_range(n, lits, m, 0)
     for sd in (seed, seed + 1):
         ss.randomize(sd)
@@ -168,7 +184,7 @@ def test_p2p_mode_single_rank_matches_plain_solve(oracle):
         assert (st.n_iterations, st.n_resamples, st.sum_mis_size, st.status) == (so.n_iterations, so.n_resamples, so.sum_mis_size, 0)
         assert np.array_equal(ss.get_assignment(), v)
     # capacity overflow is reported, not hidden: 16 records cannot hold round 0
-    tiny = P2PShardedSolver(0, 0, 1)
+    tiny = P2PShardedSolver(0, 0, 1, persistent=persistent)
     tiny.upload_range(n, lits, m, 0, cap_records=16)
     tiny.randomize(1)
     with pytest.raises(tiny.capi.AlllError) as e:

@@ -28,6 +28,7 @@ ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--solves", type=int, default=3)
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--p2p", action="store_true", help="exchange fused into the kernels (NVLink P2P) instead of NCCL all-gather")
+ap.add_argument("--persistent", action="store_true", help="with --p2p: one persistent solve kernel per rank")
 a = ap.parse_args()
 
 rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -41,13 +42,13 @@ lits = (bounded_degree_ksat_torch(n, cfg["k"], cfg["d"], 0xA115) if cfg["kind"] 
 m, k = int(lits.shape[0]), int(lits.shape[1])
 lo, hi = partition(m, world)[rank]
 if a.p2p:
-    ss = P2PShardedSolver(local, rank, world)
+    ss = P2PShardedSolver(local, rank, world, persistent=a.persistent)
     be = ss
 else:
     be = CudaShardBackend(local)
     ss = ShardedSolver(be, rank, world)
 ss.upload_range(n, lits[lo:hi].contiguous(), m, lo)
-out = dict(world=world, n=n, m=m, k=k, mode="p2p" if a.p2p else "nccl", solves=[])
+out = dict(world=world, n=n, m=m, k=k, mode=("p2p-persistent" if a.persistent else "p2p") if a.p2p else "nccl", solves=[])
 for i in range(a.solves):
     if not a.p2p:
         be.solver.reset_stats()
