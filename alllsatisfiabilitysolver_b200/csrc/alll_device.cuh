@@ -112,6 +112,10 @@ struct ClauseView {
     // enumerated clauses (rec != NULL; k = width): only the violated ones exist, as records {index, k literals} that the
     // generator sweep of this round wrote; "slot" p is the record number
     const uint32_t *rec;
+    // incremental mode: row-major copy of the literals, rows[slot][row_stride] (NULL otherwise) -- the sparse kernels then
+    // fetch a clause with one or two sectors instead of one per literal plane
+    const uint32_t *rows;
+    uint32_t row_stride;
 
     __device__ __forceinline__ uint32_t width(uint32_t p) const
     {
@@ -120,6 +124,7 @@ struct ClauseView {
     __device__ __forceinline__ uint32_t literal(uint32_t p, uint32_t j) const
     {
         if (rec) return rec[(uint64_t)p * (k + 1) + 1 + j];
+        if (rows) return rows[(uint64_t)p * row_stride + j];
         return k ? planes[(uint64_t)j * m_pad + p] : csr_lit[off[p] + j];
     }
     __device__ __forceinline__ uint32_t id(uint32_t p) const

@@ -3,6 +3,7 @@
 
 #include "../../include/alll_b200.h"
 #include "alll_device.cuh"
+#include "incr_body.cuh"
 
 namespace alll {
 
@@ -16,7 +17,8 @@ cudaError_t launch_sweep_planes(const SweepParams &p, bool resident_all, uint32_
 cudaError_t configure_solve_persistent(const SweepParams &p, bool resident_all, uint32_t kmax, int *ok_out);
 cudaError_t launch_solve_persistent(const SweepParams &p, bool resident_all, uint32_t grid, const ClauseView &cv, uint32_t kmax,
                                     uint8_t *state, uint32_t *s_slots, const MisScratch &sc, uint64_t n_vars, uint64_t seed,
-                                    uint32_t max_rounds, uint32_t epoch, cudaStream_t s);   // p.p2p != NULL: sharded solve
+                                    uint32_t max_rounds, uint32_t epoch, const IncrParams *incr, uint32_t visited_words,
+                                    uint32_t incr_max_vars, cudaStream_t s);   // p.p2p != NULL: sharded solve; incr != NULL: incremental mode
 cudaError_t launch_sweep_csr(const uint64_t *off, const uint32_t *lit, uint64_t m, const uint32_t *bits,
                              uint32_t *viol, Counters *ctr, uint32_t grid, cudaStream_t s);
 

@@ -211,6 +211,8 @@ ClauseView clause_view(alll_handle h)
     cv.id_base = h->id_base;
     cv.width_arr = h->use_width ? h->d_width : nullptr;
     cv.rec = h->gen_mode ? h->d_gen_rec : nullptr;
+    cv.rows = h->incr_ready ? h->d_rows : nullptr;
+    cv.row_stride = h->incr_stride;
     return cv;
 }
 
@@ -223,7 +225,7 @@ int alloc_common(alll_handle h, uint64_t list_cap)
     h->persistent_ok = false;
     POOL(h->d_bits, (size_t)std::max<uint32_t>(h->n_words_alloc, 4) * 4);
     CK(cudaMemsetAsync(h->d_bits, 0, (size_t)std::max<uint32_t>(h->n_words_alloc, 4) * 4, h->stream));
-    POOL(h->d_claim, 2 * n1 * 8);                          // two claim arrays: even / odd Luby steps
+    POOL(h->d_claim, 2 * n1 * 8);                          // claim[v][2]: even / odd Luby steps of variable v side by side
     CK(launch_fill_u64(h->d_claim, 2 * n1, CLAIM_FREE, h->stream)); h->launches++;
     POOL(h->d_viol, m1 * 4);
     POOL(h->d_s, m1 * 4);
@@ -396,7 +398,7 @@ SweepParams sweep_params(alll_handle h, uint32_t p2p_parity, uint32_t p2p_tag, u
     sp.orig_id = h->use_orig_id ? h->d_orig_id : nullptr; sp.id_base = h->id_base;
     if (p2p_tag) {
         sp.p2p = h->d_p2p_link; sp.p2p_parity = p2p_parity; sp.p2p_tag = p2p_tag;
-    } else if (h->urec_cap) {
+    } else if (h->urec_cap && !h->incr_ready) {      // (incremental rounds produce no records, so the independent set reads rows[] instead)
         sp.urec = h->d_urec; sp.urec_cap = h->urec_cap;
     }
     return sp;
@@ -789,13 +791,17 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
     CK(cudaEventRecord(ev_begin, h->stream));
     const bool trace = getenv("ALLL_TRACE") != nullptr;
 
-    if (h->persistent_ok && h->k && h->n_tiles && !h->gen_mode && !h->incr_ready && !(h->flags & ALLL_FLAG_HOST_ROUND_LOOP)) {
+    if (h->persistent_ok && h->k && h->n_tiles && !h->gen_mode && !(h->flags & ALLL_FLAG_HOST_ROUND_LOOP)) {
         // The whole round loop in one cooperative launch (sweep.cu: solve_persistent_kernel).
         if (max_rounds == 0) max_rounds = 1;
         const uint32_t cap = (uint32_t)std::min<uint64_t>(max_rounds, 0xFFFFFFFFull);
         const SweepParams sp = sweep_params(h, 0u, 0u, 0u);
+        IncrParams ip{};
+        if (h->incr_ready)
+            ip = IncrParams{h->d_s, h->d_rows, h->incr_stride, h->k, h->d_occ_off, h->d_occ, h->d_visited, h->d_bits, h->d_viol, h->d_ctr};
         CK(launch_solve_persistent(sp, h->resident_all, h->sweep_grid, clause_view(h), h->kmax, h->d_state, h->d_s,
-                                   mis_scratch(h, true), h->n_vars, seed, cap, 0u, h->stream));
+                                   mis_scratch(h, true), h->n_vars, seed, cap, 0u, h->incr_ready ? &ip : nullptr,
+                                   (uint32_t)h->visited_words, h->incr_max_vars, h->stream));
         h->launches++;
         cudaEvent_t ev_end = h->ev[2 * MAX_TIMED_ROUNDS + 1];
         CK(cudaEventRecord(ev_end, h->stream));
@@ -811,7 +817,8 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
         stats->n_resamples = c.n_resamples;
         stats->sum_mis_size = c.sum_mis;
         stats->avg_mis_size = c.n_iterations ? c.sum_mis / c.n_iterations : 0;     // SATInstance.h:317
-        stats->n_clause_evals = h->m * c.n_iterations;
+        stats->n_clause_evals = h->m * (c.n_iterations - c.n_incr_rounds) + c.n_evals_incr;   // clauses actually evaluated
+        stats->n_incremental_rounds = c.n_incr_rounds;
         stats->n_luby_steps = c.n_luby_steps;
         stats->n_kernel_launches = h->launches - launches0;
         stats->solve_ms = ms;
@@ -1087,7 +1094,7 @@ int alll_solve_p2p(alll_handle h, uint64_t seed, uint64_t max_rounds, uint64_t m
         ClauseView pcv{};
         pcv.k = h->k;
         CK(launch_solve_persistent(sp, h->resident_all, h->sweep_grid, pcv, h->k, h->d_sh_state, h->d_sh_s, mis_scratch(h, false),
-                                   h->n_vars, seed, (uint32_t)max_rounds, epoch, h->stream));
+                                   h->n_vars, seed, (uint32_t)max_rounds, epoch, nullptr, 0u, 0u, h->stream));
         h->launches++;
         cudaEvent_t ev_end = h->ev[2 * MAX_TIMED_ROUNDS + 1];
         CK(cudaEventRecord(ev_end, h->stream));

@@ -20,6 +20,7 @@
 //   * violated slots are compacted per warp with __ballot_sync/__popc into a shared-memory staging
 //     buffer and flushed with one global atomicAdd per >= 32 entries.
 #include "alll_device.cuh"
+#include "incr_body.cuh"
 #include "mis_body.cuh"
 
 namespace alll {
@@ -468,7 +469,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const Sw
 // one for round r+1 is cleared during the independent-set phase of round r, when nobody adds to it.
 template <int K, int RB, int RC, int E>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(const SweepParams sp, const MisParams mp_arg,
-                                                                           const uint32_t max_rounds, const uint32_t epoch)
+                                                                           const uint32_t max_rounds, const uint32_t epoch,
+                                                                           const IncrParams ip, const uint32_t visited_words)
 {
     // The independent-set bodies are out-of-line functions: they get the parameter block through a pointer, and a
     // pointer to kernel parameters would force a per-thread local-memory copy.  One copy per CTA in shared memory
@@ -492,7 +494,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(cons
             if (round < DBG_ROUNDS) c->dbg[round][0] = t0;
         }
         if (threadIdx.x == 0) { s_mp.p2p_parity = par; s_mp.p2p_tag = tag; }
-        sweep_planes_body<K, RB, RC, E, false>(sp, &c->n_viol_pp[par], par);
+        // incremental mode (ip.rows != NULL): the round that just ended decided whether this round's violated set comes
+        // from the occurrence lists of the variables it resampled (same set as the sweep's, incremental.cu) or from a sweep
+        const bool incremental = ip.rows != nullptr && round > 0 && gm::ld_cg(&c->incr_next) != 0;
+        if (incremental) incr_eval_body(ip, gm::ld_cg(&c->last_n_s), &c->n_viol_pp[par]);
+        else sweep_planes_body<K, RB, RC, E, false>(sp, &c->n_viol_pp[par], par);
         if (p2p) {                                       // this CTA's record stores (NVLink) are ordered before the barrier
             __syncthreads();
             if (threadIdx.x == 0) __threadfence_system();
@@ -519,6 +525,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(cons
             if (round < DBG_ROUNDS) { c->dbg[round][1] = t1; c->dbg[round][2] = t1; }
             c->n_viol_pp[par ^ 1u] = 0;
         }
+        if (incremental)                                 // the first-visit bits of this round: nobody reads them before the next one
+            for (uint32_t i = first; i < visited_words; i += stride) ip.visited[i] = 0u;
         if (n_u == 0xFFFFFFFFu) {                        // a peer overflowed its exchange area or never arrived: stop
             if (lead) {
                 c->p2p_error = c->p2p_error ? c->p2p_error : 2;
@@ -529,6 +537,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(cons
         if (n_u == 0) {                                  // SATInstance.h:285-287; the terminal sweep counts (:261)
             if (lead) {
                 gm::red_add(&c->n_iterations, 1ull);
+                if (incremental) c->n_incr_rounds += 1;
                 c->last_n_viol = 0;
                 c->last_n_s = 0;
                 c->last_resampled = 0;
@@ -630,6 +639,8 @@ enum Op { OP_LAUNCH, OP_CONFIGURE, OP_PERSIST_LAUNCH, OP_PERSIST_CONFIGURE };
 struct PersistArgs {
     const MisParams *mp;
     uint32_t max_rounds, epoch;
+    const IncrParams *ip;
+    uint32_t visited_words;
     int *max_ctas_per_sm;     // OP_PERSIST_CONFIGURE: occupancy of the persistent kernel with the requested shared memory
 };
 } // namespace
@@ -650,8 +661,8 @@ static cudaError_t launch_planes_e(const SweepParams &p, uint32_t grid, size_t s
                                                              SWEEP_THREADS, smem);
     }
     case OP_PERSIST_LAUNCH: {
-        uint32_t max_rounds = pa->max_rounds, epoch = pa->epoch;
-        void *args[] = {(void *)&p, (void *)pa->mp, (void *)&max_rounds, (void *)&epoch};
+        uint32_t max_rounds = pa->max_rounds, epoch = pa->epoch, visited_words = pa->visited_words;
+        void *args[] = {(void *)&p, (void *)pa->mp, (void *)&max_rounds, (void *)&epoch, (void *)pa->ip, (void *)&visited_words};
         return cudaLaunchCooperativeKernel((const void *)solve_persistent_kernel<K, RB, RC, E>, dim3(grid), dim3(SWEEP_THREADS),
                                            args, smem, s);
     }
@@ -755,7 +766,7 @@ cudaError_t configure_solve_persistent(const SweepParams &p, bool resident_all, 
     *ok_out = 0;
     if (p.k == 0 || p.k > 8) return cudaSuccess;
     int per_sm = 0;
-    PersistArgs pa{nullptr, 0u, 0u, &per_sm};
+    PersistArgs pa{nullptr, 0u, 0u, nullptr, 0u, &per_sm};
     const cudaError_t e = dispatch_k(p, resident_all, 0, persistent_smem_bytes(p.bucket_words, kmax), 0, OP_PERSIST_CONFIGURE, &pa);
     if (e != cudaSuccess) return e;
     *ok_out = per_sm >= 1;
@@ -764,7 +775,8 @@ cudaError_t configure_solve_persistent(const SweepParams &p, bool resident_all, 
 
 cudaError_t launch_solve_persistent(const SweepParams &p, bool resident_all, uint32_t grid, const ClauseView &cv, uint32_t kmax,
                                     uint8_t *state, uint32_t *s_slots, const MisScratch &sc, uint64_t n_vars, uint64_t seed,
-                                    uint32_t max_rounds, uint32_t epoch, cudaStream_t s)
+                                    uint32_t max_rounds, uint32_t epoch, const IncrParams *incr, uint32_t visited_words,
+                                    uint32_t incr_max_vars, cudaStream_t s)
 {
     const size_t smem = persistent_smem_bytes(p.bucket_words, kmax);
     MisParams mp{};
@@ -774,7 +786,9 @@ cudaError_t launch_solve_persistent(const SweepParams &p, bool resident_all, uin
     mp.n_vars = n_vars; mp.bits = const_cast<uint32_t *>(p.bits); mp.ctr = p.ctr; mp.seed = seed; mp.kmax = kmax;
     mp.urec = sc.urec; mp.urec_cap = sc.urec_cap;
     persistent_fill(p, mp, smem);
-    PersistArgs pa{&mp, max_rounds, epoch, nullptr};
+    mp.incr_max_vars = incr ? incr_max_vars : 0u;
+    const IncrParams no_incr{};
+    PersistArgs pa{&mp, max_rounds, epoch, incr ? incr : &no_incr, incr ? visited_words : 0u, nullptr};
     return dispatch_k(p, resident_all, grid, smem, s, OP_PERSIST_LAUNCH, &pa);
 }
 

@@ -360,8 +360,10 @@ def test_cfg3_beyond_lll_round_cap(capi, oracle):
         assert cnt == len(oracle.sweep(off, lits.reshape(-1), v)) > 0
 
 
-@pytest.mark.parametrize("layout", [dict(flags=4), dict(flags=4 | (1 << 24)), dict(flags=4, sweep_smem_bytes=1024)],
-                         ids=["incremental", "incremental_div2", "incremental_bucketed"])
+@pytest.mark.parametrize("layout", [dict(flags=4), dict(flags=4 | (1 << 24)), dict(flags=4, sweep_smem_bytes=1024),
+                                    dict(flags=4 | 16), dict(flags=4 | 16, sweep_smem_bytes=1024)],
+                         ids=["incremental", "incremental_div2", "incremental_bucketed", "incremental_host_round_loop",
+                              "incremental_bucketed_host_round_loop"])
 @pytest.mark.parametrize("name", ["cfg1", "k7_small", "k8_small", "k3_uniform", "ragged"])
 def test_incremental_mode_is_bit_identical(capi, oracle, golden, name, layout):
     """ALLL_FLAG_INCREMENTAL: violated sets come from the occurrence lists of the resampled
