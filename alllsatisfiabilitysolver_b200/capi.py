@@ -207,8 +207,13 @@ class Solver:
         assert bools.shape == (self.n_vars,)
         self._check(self.lib.alll_set_assignment(self.h, bools.ctypes.data))
 
-    def get_assignment(self) -> np.ndarray:
-        out = np.empty(self.n_vars, np.uint8)
+    def get_assignment(self, out: np.ndarray | None = None) -> np.ndarray:
+        """1 byte per variable, like the reference's ``var_arr->vars``.  ``out``: a caller-owned uint8 buffer of n_vars
+        bytes to fill (the reference's array is long-lived too; a fresh 10 MB array costs more in page faults than the copy)."""
+        if out is None:
+            out = np.empty(self.n_vars, np.uint8)
+        elif out.dtype != np.uint8 or out.size != self.n_vars or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a contiguous uint8 array of n_vars elements")
         self._check(self.lib.alll_get_assignment(self.h, out.ctypes.data))
         return out
 

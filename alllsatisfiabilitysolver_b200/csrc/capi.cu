@@ -30,6 +30,8 @@ constexpr int ROUNDS_IN_FLIGHT = 3;      // rounds the host enqueues ahead of th
 struct alll_solver {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D of a host-buffer upload, chunk by chunk ahead of the layout kernels
+    cudaEvent_t ev_chunk[33] = {};       // [i]: chunk i has arrived; [32]: the layout stream is done with the staging buffer
     int sm_count = 0;
     uint32_t smem_budget = DEFAULT_SWEEP_SMEM;
     uint32_t flags = 0;
@@ -246,8 +248,11 @@ int check_sizes(alll_handle h, uint64_t n_vars, uint64_t m)
 
 // d_width_in (may be NULL): true width of every clause (by caller id) when the rows are padded to k literals with
 // copies of their first literal (ragged input on the plane layout; a repeated literal never changes a clause's value).
+// host_lit != NULL: d_lit is the staging buffer of a host-buffer upload that has NOT been filled yet -- the copy is issued
+// here, in chunks on the copy stream, and the first layout pass (transpose, or bucket count) runs chunk by chunk behind it,
+// so that pass hides under the PCIe transfer instead of following it.
 int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *d_lit,
-                              const uint8_t *d_width_in = nullptr)
+                              const uint8_t *d_width_in = nullptr, const uint32_t *host_lit = nullptr)
 {
     free_instance(h);
     if (int rc = check_sizes(h, n_vars, m)) return rc;
@@ -281,11 +286,35 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
         h->resident_cap = RESIDENT_CAP;
     }
 
+    // clause ranges of the first pass: one, or (host-buffer upload) one per H2D chunk of about 64 MB
+    std::vector<uint64_t> cut{0, m};
+    if (host_lit && m) {
+        const uint64_t per = bucket_pass_clauses_per_cta();
+        uint64_t chunk = std::max<uint64_t>(per, ((64ull << 20) / (4ull * k)) / per * per);
+        if ((m + chunk - 1) / chunk > 32) chunk = align_up((m + 31) / 32, per);
+        cut.clear();
+        for (uint64_t c0 = 0; c0 < m; c0 += chunk) cut.push_back(c0);
+        cut.push_back(m);
+        CK(cudaEventRecord(h->ev_chunk[32], h->stream));                // the staging buffer may still be read by earlier work
+        CK(cudaStreamWaitEvent(h->copy_stream, h->ev_chunk[32], 0));
+        for (size_t i = 0; i + 1 < cut.size(); i++) {
+            CK(cudaMemcpyAsync(const_cast<uint32_t *>(d_lit) + cut[i] * k, host_lit + cut[i] * k, (cut[i + 1] - cut[i]) * k * 4,
+                               cudaMemcpyHostToDevice, h->copy_stream));
+            CK(cudaEventRecord(h->ev_chunk[i], h->copy_stream));
+        }
+    }
+    auto chunk_ready = [&](size_t i) -> cudaError_t {               // the layout stream waits for chunk i of the copy
+        return host_lit && m ? cudaStreamWaitEvent(h->stream, h->ev_chunk[i], 0) : cudaSuccess;
+    };
+
     if (h->n_buckets == 1) {
         h->m_pad = align_up(m, TILE);
         // padding slots are never evaluated (masked by slot_end), so the planes need no clearing
         if (h->m_pad) POOL(h->d_planes, h->m_pad * k * 4);
-        CK(launch_transpose(d_lit, m, k, n_vars, h->d_planes, h->m_pad, d_err, h->stream)); h->launches++;
+        for (size_t i = 0; i + 1 < cut.size(); i++) {
+            CK(chunk_ready(i));
+            CK(launch_transpose(d_lit, cut[i], cut[i + 1], k, n_vars, h->d_planes, h->m_pad, d_err, h->stream)); h->launches++;
+        }
         segs[0] = BucketSeg{0u, (uint32_t)m};
         if (d_width_in && m) {
             POOL(h->d_width, h->m_pad);
@@ -298,7 +327,11 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
         POOL(h->d_tmp_cnt, (size_t)nb * std::max<uint32_t>(n_cta, 1) * 4);
         uint8_t *d_bkt = h->d_tmp_bkt;
         uint32_t *d_cnt = h->d_tmp_cnt;
-        if (m) { CK(launch_bucket_count(d_lit, m, k, n_vars, bucket_vars, nb, d_bkt, d_cnt, d_err, h->stream)); h->launches++; }
+        for (size_t i = 0; i + 1 < cut.size() && m; i++) {
+            CK(chunk_ready(i));
+            CK(launch_bucket_count(d_lit, m, cut[i], cut[i + 1], k, n_vars, bucket_vars, nb, d_bkt, d_cnt, d_err, h->stream));
+            h->launches++;
+        }
         std::vector<uint32_t> cnt((size_t)nb * n_cta);
         CK(cudaMemcpyAsync(cnt.data(), d_cnt, cnt.size() * 4, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -387,7 +420,8 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     return ALLL_OK;
 }
 
-SweepParams sweep_params(alll_handle h, uint32_t p2p_parity, uint32_t p2p_tag, uint32_t round)
+// records: leave {id, literals} records next to the violated list (an independent-set phase follows and will read them)
+SweepParams sweep_params(alll_handle h, uint32_t p2p_parity, uint32_t p2p_tag, uint32_t round, bool records)
 {
     SweepParams sp{};
     sp.planes = h->d_planes; sp.m_pad = h->m_pad; sp.bits = h->d_bits; sp.n_words = h->n_words_alloc;
@@ -398,7 +432,7 @@ SweepParams sweep_params(alll_handle h, uint32_t p2p_parity, uint32_t p2p_tag, u
     sp.orig_id = h->use_orig_id ? h->d_orig_id : nullptr; sp.id_base = h->id_base;
     if (p2p_tag) {
         sp.p2p = h->d_p2p_link; sp.p2p_parity = p2p_parity; sp.p2p_tag = p2p_tag;
-    } else if (h->urec_cap && !h->incr_ready) {      // (incremental rounds produce no records, so the independent set reads rows[] instead)
+    } else if (records && h->urec_cap && !h->incr_ready) {      // (incremental rounds produce no records, so the independent set reads rows[] instead)
         sp.urec = h->d_urec; sp.urec_cap = h->urec_cap;
     }
     return sp;
@@ -406,7 +440,7 @@ SweepParams sweep_params(alll_handle h, uint32_t p2p_parity, uint32_t p2p_tag, u
 
 // Enqueues one sweep.  Invariant: ctr->n_viol == 0 on entry (kept by the MIS kernel / reset kernel).
 // p2p_tag != 0: sharded P2P mode -- violated records are stored into every GPU's exchange region.
-int enqueue_sweep(alll_handle h, uint32_t p2p_parity = 0, uint32_t p2p_tag = 0, uint32_t round = 0xFFFFFFFFu)
+int enqueue_sweep(alll_handle h, uint32_t p2p_parity = 0, uint32_t p2p_tag = 0, uint32_t round = 0xFFFFFFFFu, bool records = false)
 {
     if (h->gen_mode) {
         if (h->m == 0) return ALLL_OK;
@@ -421,7 +455,7 @@ int enqueue_sweep(alll_handle h, uint32_t p2p_parity = 0, uint32_t p2p_tag = 0, 
     }
     if (h->k) {
         if (h->n_tiles == 0 && !p2p_tag) return ALLL_OK;      // (a P2P rank without clauses still has to publish its round)
-        const SweepParams sp = sweep_params(h, p2p_parity, p2p_tag, round);
+        const SweepParams sp = sweep_params(h, p2p_parity, p2p_tag, round, records);
         CK(launch_sweep_planes(sp, h->resident_all, h->sweep_grid, h->stream));
     } else {
         if (h->m == 0) return ALLL_OK;
@@ -433,9 +467,9 @@ int enqueue_sweep(alll_handle h, uint32_t p2p_parity = 0, uint32_t p2p_tag = 0, 
 }
 
 int enqueue_mis_resample(alll_handle h, uint64_t seed, uint32_t round, bool with_grid = true, RoundNote *note = nullptr,
-                         unsigned long long seq = 0, bool allow_incremental = false)
+                         unsigned long long seq = 0, bool allow_incremental = false, bool records = true)
 {
-    CK(launch_mis_resample_args(clause_view(h), h->kmax, h->gen_mode ? nullptr : h->d_viol, h->d_state, h->d_s, mis_scratch(h, true),
+    CK(launch_mis_resample_args(clause_view(h), h->kmax, h->gen_mode ? nullptr : h->d_viol, h->d_state, h->d_s, mis_scratch(h, records),
                                 h->n_vars, h->d_bits, h->d_ctr, seed, round, h->mis_grid, with_grid, note, seq, nullptr, 0u, 0u,
                                 (allow_incremental && h->incr_ready) ? h->incr_max_vars : 0u,
                                 h->gen_mode ? (uint32_t)h->gen_cap : 0u, h->stream));
@@ -519,6 +553,9 @@ int alll_create(const alll_config *cfg, alll_handle *out)
     h = s;
     auto bail = [&](int rc) { std::string m = h->err; alll_destroy(h); g_create_error = m; return rc; };
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaStreamCreate failed"));
+    if (cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaStreamCreate failed"));
+    for (auto &ev : s->ev_chunk)
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaEventCreate failed"));
     if (cudaMalloc(&s->d_ctr, sizeof(Counters)) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaMalloc(counters) failed"));
     if (cudaMallocHost(&s->h_ctr, sizeof(Counters)) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaMallocHost failed"));
     if (cudaMallocHost(&s->h_ring, sizeof(RoundNote) * ROUNDS_IN_FLIGHT) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaMallocHost failed"));
@@ -544,6 +581,8 @@ int alll_destroy(alll_handle h)
     if (h->h_bools) cudaFreeHost(h->h_bools);
     for (auto &ev : h->ev_round) if (ev) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (cudaEvent_t e : h->ev_chunk) if (e) cudaEventDestroy(e);
     delete h;
     return ALLL_OK;
 }
@@ -566,8 +605,8 @@ int alll_upload_fixedk(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, c
     free_instance(h);
     const size_t bytes = (size_t)std::max<uint64_t>(m * k, 1) * 4;
     POOL(h->d_stage, bytes);
-    if (m) CK(cudaMemcpyAsync(h->d_stage, lit, (size_t)m * k * 4, cudaMemcpyHostToDevice, h->stream));
-    const int rc = upload_fixedk_device_impl(h, n_vars, m, k, h->d_stage);
+    const int rc = upload_fixedk_device_impl(h, n_vars, m, k, h->d_stage, nullptr, lit);      // (issues the H2D copy itself, in chunks)
+    cudaStreamSynchronize(h->copy_stream);            // `lit` is the caller's again when we return, on every path
     cudaStreamSynchronize(h->stream);
     if (bytes > (4ull << 30)) {          // do not sit on a very large staging buffer
         dfree(h->d_stage);
@@ -694,6 +733,15 @@ int alll_builtin_generator_clause(uint32_t kind, uint64_t n_vars, uint64_t m, ui
     return builtin_generator_clause(kind, n_vars, m, k, seed, d, index, lits) ? ALLL_BAD_ARG : ALLL_OK;
 }
 
+// true when the caller's buffer is page-locked (cudaMallocHost / cudaHostRegister): the copy engine can then use it
+// directly and the pinned staging hop (a 10 MB memcpy at n = 10 M) is skipped
+static bool caller_buffer_is_pinned(const void *p)
+{
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 static int ensure_pinned_bools(alll_handle h)
 {
     if (h->h_bools_cap >= h->n_vars) return ALLL_OK;
@@ -707,9 +755,13 @@ int alll_set_assignment(alll_handle h, const uint8_t *bools)
 {
     NEED_INSTANCE();
     if (!bools) return fail(h, ALLL_BAD_ARG, "bools == NULL");
-    if (int rc = ensure_pinned_bools(h)) return rc;
-    std::memcpy(h->h_bools, bools, h->n_vars);
-    CK(cudaMemcpyAsync(h->d_bools, h->h_bools, h->n_vars, cudaMemcpyHostToDevice, h->stream));
+    const uint8_t *src = bools;
+    if (!caller_buffer_is_pinned(bools)) {
+        if (int rc = ensure_pinned_bools(h)) return rc;
+        std::memcpy(h->h_bools, bools, h->n_vars);
+        src = h->h_bools;
+    }
+    CK(cudaMemcpyAsync(h->d_bools, src, h->n_vars, cudaMemcpyHostToDevice, h->stream));
     CK(launch_pack_bits(h->d_bools, h->n_vars, h->d_bits, h->n_words_alloc, h->stream)); h->launches++;
     CK(cudaStreamSynchronize(h->stream));
     return ALLL_OK;
@@ -719,11 +771,13 @@ int alll_get_assignment(alll_handle h, uint8_t *bools)
 {
     NEED_INSTANCE();
     if (!bools) return fail(h, ALLL_BAD_ARG, "bools == NULL");
-    if (int rc = ensure_pinned_bools(h)) return rc;
+    const bool direct = caller_buffer_is_pinned(bools);
+    if (!direct)
+        if (int rc = ensure_pinned_bools(h)) return rc;
     CK(launch_unpack_bits(h->d_bits, h->n_vars, h->d_bools, h->stream)); h->launches++;
-    CK(cudaMemcpyAsync(h->h_bools, h->d_bools, h->n_vars, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(direct ? bools : h->h_bools, h->d_bools, h->n_vars, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    std::memcpy(bools, h->h_bools, h->n_vars);
+    if (!direct) std::memcpy(bools, h->h_bools, h->n_vars);
     return ALLL_OK;
 }
 
@@ -763,7 +817,7 @@ int alll_round(alll_handle h, uint64_t seed, uint32_t round, uint32_t *u_ids, ui
                uint32_t *s_ids, uint64_t s_cap, uint64_t *n_s, uint64_t *n_resampled)
 {
     NEED_INSTANCE();
-    if (int rc = enqueue_sweep(h)) return rc;
+    if (int rc = enqueue_sweep(h, 0u, 0u, 0xFFFFFFFFu, true)) return rc;
     if (int rc = enqueue_mis_resample(h, seed, round)) return rc;
     if (int rc = fetch_counters(h)) return rc;
     const Counters &c = *h->h_ctr;
@@ -795,7 +849,7 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
         // The whole round loop in one cooperative launch (sweep.cu: solve_persistent_kernel).
         if (max_rounds == 0) max_rounds = 1;
         const uint32_t cap = (uint32_t)std::min<uint64_t>(max_rounds, 0xFFFFFFFFull);
-        const SweepParams sp = sweep_params(h, 0u, 0u, 0u);
+        const SweepParams sp = sweep_params(h, 0u, 0u, 0u, true);
         IncrParams ip{};
         if (h->incr_ready)
             ip = IncrParams{h->d_s, h->d_rows, h->incr_stride, h->k, h->d_occ_off, h->d_occ, h->d_visited, h->d_bits, h->d_viol, h->d_ctr};
@@ -843,7 +897,9 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
         while (issued < max_rounds && issued - retired < (uint64_t)ROUNDS_IN_FLIGHT) {
             const bool time_this = issued < (uint64_t)MAX_TIMED_ROUNDS;
             if (time_this) CK(cudaEventRecord(h->ev[2 * issued], h->stream));
-            if (int rc = enqueue_sweep(h, 0u, 0u, (uint32_t)issued)) return rc;
+            // records for the independent set only while the violated set is expected to fit them (see sweep.cu)
+            const bool records = last_seen_u <= 2ull * h->urec_cap;
+            if (int rc = enqueue_sweep(h, 0u, 0u, (uint32_t)issued, records)) return rc;
             if (time_this) CK(cudaEventRecord(h->ev[2 * issued + 1], h->stream));
             if (h->incr_ready && issued > 0) {
                 // incremental mode: the device decided at the end of the previous round which of the two kernels
@@ -855,7 +911,7 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
             }
             const int slot = (int)(issued % ROUNDS_IN_FLIGHT);
             if (int rc = enqueue_mis_resample(h, seed, (uint32_t)issued, last_seen_u > MIS_CLUSTER_MAX_U, &h->h_ring[slot],
-                                              seq0 + issued + 1, true))
+                                              seq0 + issued + 1, true, records))
                 return rc;
             CK(cudaEventRecord(h->ev_round[slot], h->stream));      // timing only: marks the end of this round on the device
             issued++;
@@ -1090,7 +1146,7 @@ int alll_solve_p2p(alll_handle h, uint64_t seed, uint64_t max_rounds, uint64_t m
     max_rounds = std::min<uint64_t>(max_rounds, (1u << 20) - 2);       // the round lives in 20 bits of the tag
     if ((h->flags & ALLL_FLAG_P2P_PERSISTENT) && h->persistent_ok && h->k && h->n_tiles) {
         // every rank: the whole sharded solve in one cooperative launch (sweep.cu: solve_persistent_kernel, p2p branch)
-        const SweepParams sp = sweep_params(h, 0u, 1u, 0u);              // (tag != 0 selects the P2P form; the kernel derives parity / tag per round)
+        const SweepParams sp = sweep_params(h, 0u, 1u, 0u, false);              // (tag != 0 selects the P2P form; the kernel derives parity / tag per round)
         ClauseView pcv{};
         pcv.k = h->k;
         CK(launch_solve_persistent(sp, h->resident_all, h->sweep_grid, pcv, h->k, h->d_sh_state, h->d_sh_s, mis_scratch(h, false),

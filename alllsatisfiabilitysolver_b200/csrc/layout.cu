@@ -16,12 +16,13 @@ constexpr uint32_t LAYOUT_THREADS = 1024;   // clauses per CTA in the bucketing 
 constexpr uint32_t ERR_LITERAL_RANGE = 1u;
 
 // ---- no bucketing: transpose row-major [m][k] into planes, validating literals -------------------
-__global__ void __launch_bounds__(256) transpose_kernel(const uint32_t *__restrict__ lit, uint64_t m, uint32_t k,
+// clauses [c0, c1): the host-buffer upload runs this chunk by chunk behind the H2D copy of each chunk
+__global__ void __launch_bounds__(256) transpose_kernel(const uint32_t *__restrict__ lit, uint64_t c0, uint64_t c1, uint32_t k,
                                                          uint64_t n_vars, uint32_t *__restrict__ planes,
                                                          uint64_t m_pad, uint32_t *err)
 {
-    const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= m) return;
+    const uint64_t c = c0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
     uint32_t bad = 0;
     for (uint32_t j = 0; j < k; j++) {
         const uint32_t l = lit[c * k + j];
@@ -40,16 +41,19 @@ __global__ void __launch_bounds__(256) validate_csr_kernel(const uint32_t *__res
 
 // ---- bucketing pass 1: bucket of every clause + per-CTA histogram --------------------------------
 // bucket(c) = the variable-range bucket that holds most of c's variables (ties: lowest bucket).
+// This launch covers the logical CTAs [cta0, cta0 + gridDim.x) of the n_cta the whole pass has (chunked behind the H2D copy).
 __global__ void __launch_bounds__(LAYOUT_THREADS) bucket_count_kernel(const uint32_t *__restrict__ lit, uint64_t m,
                                                                        uint32_t k, uint64_t n_vars,
                                                                        uint32_t bucket_vars, uint32_t n_buckets,
                                                                        uint8_t *__restrict__ bkt,
-                                                                       uint32_t *__restrict__ cta_counts, uint32_t *err)
+                                                                       uint32_t *__restrict__ cta_counts, uint32_t *err,
+                                                                       uint32_t cta0, uint32_t n_cta)
 {
     __shared__ uint32_t hist[MAX_BUCKETS];
     for (uint32_t i = threadIdx.x; i < n_buckets; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    const uint64_t c = (uint64_t)blockIdx.x * LAYOUT_THREADS + threadIdx.x;
+    const uint32_t cta = cta0 + blockIdx.x;
+    const uint64_t c = (uint64_t)cta * LAYOUT_THREADS + threadIdx.x;
     if (c < m) {
         uint32_t b_of[MAX_K];
         uint32_t bad = 0;
@@ -71,7 +75,7 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) bucket_count_kernel(const uint
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < n_buckets; i += blockDim.x)
-        cta_counts[(uint64_t)i * gridDim.x + blockIdx.x] = hist[i];
+        cta_counts[(uint64_t)i * n_cta + cta] = hist[i];
 }
 
 // ---- bucketing pass 2: stable scatter into planes, bucket-resident literals first -----------------
@@ -183,11 +187,12 @@ __global__ void __launch_bounds__(256) fill_u64_kernel(unsigned long long *p, ui
 // ---- launchers ---------------------------------------------------------------------------------
 static inline uint32_t blocks_for(uint64_t n, uint32_t threads) { return (uint32_t)((n + threads - 1) / threads); }
 
-cudaError_t launch_transpose(const uint32_t *lit, uint64_t m, uint32_t k, uint64_t n_vars, uint32_t *planes,
+// clauses [c0, c1) of the instance
+cudaError_t launch_transpose(const uint32_t *lit, uint64_t c0, uint64_t c1, uint32_t k, uint64_t n_vars, uint32_t *planes,
                              uint64_t m_pad, uint32_t *err, cudaStream_t s)
 {
-    if (m == 0) return cudaSuccess;
-    transpose_kernel<<<blocks_for(m, 256), 256, 0, s>>>(lit, m, k, n_vars, planes, m_pad, err);
+    if (c1 <= c0) return cudaSuccess;
+    transpose_kernel<<<blocks_for(c1 - c0, 256), 256, 0, s>>>(lit, c0, c1, k, n_vars, planes, m_pad, err);
     return cudaGetLastError();
 }
 
@@ -200,12 +205,95 @@ cudaError_t launch_validate_csr(const uint32_t *lit, uint64_t n_lit, uint64_t n_
 
 uint32_t bucket_pass_ctas(uint64_t m) { return blocks_for(m, LAYOUT_THREADS); }
 
-cudaError_t launch_bucket_count(const uint32_t *lit, uint64_t m, uint32_t k, uint64_t n_vars, uint32_t bucket_vars,
-                                uint32_t n_buckets, uint8_t *bkt, uint32_t *cta_counts, uint32_t *err, cudaStream_t s)
+// clauses [c0, c1) of the m the whole pass covers; c0 must be a multiple of bucket_pass_clauses_per_cta()
+uint32_t bucket_pass_clauses_per_cta() { return LAYOUT_THREADS; }
+cudaError_t launch_bucket_count(const uint32_t *lit, uint64_t m, uint64_t c0, uint64_t c1, uint32_t k, uint64_t n_vars,
+                                uint32_t bucket_vars, uint32_t n_buckets, uint8_t *bkt, uint32_t *cta_counts, uint32_t *err,
+                                cudaStream_t s)
 {
-    bucket_count_kernel<<<bucket_pass_ctas(m), LAYOUT_THREADS, 0, s>>>(lit, m, k, n_vars, bucket_vars, n_buckets, bkt,
-                                                                         cta_counts, err);
+    if (c1 <= c0) return cudaSuccess;
+    bucket_count_kernel<<<blocks_for(c1 - c0, LAYOUT_THREADS), LAYOUT_THREADS, 0, s>>>(
+        lit, m, k, n_vars, bucket_vars, n_buckets, bkt, cta_counts, err, (uint32_t)(c0 / LAYOUT_THREADS), bucket_pass_ctas(m));
     return cudaGetLastError();
+}
+
+// Same result as bucket_scatter_kernel for k <= 8 without per-clause widths, with the CTA's 1024 clauses staged in shared
+// memory in destination order first: thread t of the write phase owns the t-th clause of that order, so consecutive threads
+// write consecutive slots of a bucket segment (whole sectors) instead of each warp scattering 4-5 word fragments over all
+// segments.  Dynamic shared memory: (k + 1) * 1024 words.
+extern __shared__ uint32_t stage_smem[];
+__global__ void __launch_bounds__(LAYOUT_THREADS) bucket_scatter_staged_kernel(const uint32_t *__restrict__ lit, uint64_t m,
+                                                                                uint32_t k, uint32_t bucket_vars,
+                                                                                uint32_t n_buckets,
+                                                                                const uint8_t *__restrict__ bkt,
+                                                                                const uint32_t *__restrict__ cta_base,
+                                                                                uint32_t *__restrict__ planes, uint64_t m_pad,
+                                                                                uint32_t *__restrict__ orig_id,
+                                                                                uint32_t *__restrict__ min_resident, uint32_t resident_cap)
+{
+    __shared__ uint16_t warp_cnt[(LAYOUT_THREADS / 32) * MAX_BUCKETS];   // [warp][bucket], then exclusive over warps
+    __shared__ uint32_t bucket_off[MAX_BUCKETS + 1];                     // CTA-local start of every bucket's run
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    for (uint32_t i = threadIdx.x; i < (LAYOUT_THREADS / 32) * n_buckets; i += blockDim.x) warp_cnt[i] = 0;
+    __syncthreads();
+    const uint64_t c = (uint64_t)blockIdx.x * LAYOUT_THREADS + threadIdx.x;
+    const bool active = c < m;
+    const uint32_t act = __ballot_sync(0xffffffffu, active);
+    uint32_t b = 0, rank = 0;
+    uint32_t l[8];
+    if (active) {
+        b = bkt[c];
+        const uint32_t peers = __match_any_sync(act, b);
+        rank = __popc(peers & ((1u << lane) - 1u));
+        if (rank == 0) warp_cnt[warp * n_buckets + b] = (uint16_t)__popc(peers);
+#pragma unroll
+        for (uint32_t j = 0; j < 8; j++) l[j] = j < k ? lit[c * k + j] : 0u;
+    }
+    __syncthreads();
+    for (uint32_t bb = threadIdx.x; bb < n_buckets; bb += blockDim.x) {
+        uint32_t run = 0;
+        for (uint32_t w = 0; w < LAYOUT_THREADS / 32; w++) {
+            const uint32_t t = warp_cnt[w * n_buckets + bb];
+            warp_cnt[w * n_buckets + bb] = (uint16_t)run;
+            run += t;
+        }
+        bucket_off[bb + 1] = run;                       // totals for now
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        bucket_off[0] = 0;
+        for (uint32_t bb = 0; bb < n_buckets; bb++) { run += bucket_off[bb + 1]; bucket_off[bb + 1] = run; }
+    }
+    __syncthreads();
+    uint32_t placed = 0;
+    if (active) {
+        const uint32_t loc = bucket_off[b] + warp_cnt[warp * n_buckets + b] + rank;
+        const uint32_t lo = b * bucket_vars;
+        // the first (at most resident_cap) bucket-resident literals go to the leading planes, original order kept
+        uint32_t j_out = 0, front_mask = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 8; j++)
+            if (j < k && placed < resident_cap && (l[j] >> 1) - lo < bucket_vars) {
+                stage_smem[(j_out++) * LAYOUT_THREADS + loc] = l[j];
+                front_mask |= 1u << j;
+                placed++;
+            }
+#pragma unroll
+        for (uint32_t j = 0; j < 8; j++)
+            if (j < k && !((front_mask >> j) & 1u)) stage_smem[(j_out++) * LAYOUT_THREADS + loc] = l[j];
+        stage_smem[k * LAYOUT_THREADS + loc] = (uint32_t)c;
+        const uint32_t wmin = __reduce_min_sync(act, placed);           // one atomicMin per warp
+        if (__popc(act & ((1u << lane) - 1u)) == 0) atomicMin(min_resident, wmin);
+    }
+    __syncthreads();
+    const uint32_t t = threadIdx.x;
+    if (t >= bucket_off[n_buckets]) return;
+    uint32_t bb = 0;
+    while (bucket_off[bb + 1] <= t) ++bb;
+    const uint64_t dst = (uint64_t)cta_base[(uint64_t)bb * gridDim.x + blockIdx.x] + (t - bucket_off[bb]);
+    for (uint32_t j = 0; j < k; j++) planes[(uint64_t)j * m_pad + dst] = stage_smem[j * LAYOUT_THREADS + t];
+    orig_id[dst] = stage_smem[k * LAYOUT_THREADS + t];
 }
 
 cudaError_t launch_bucket_scatter(const uint32_t *lit, uint64_t m, uint32_t k, uint32_t bucket_vars, uint32_t n_buckets,
@@ -213,8 +301,16 @@ cudaError_t launch_bucket_scatter(const uint32_t *lit, uint64_t m, uint32_t k, u
                                   uint32_t *orig_id, uint32_t *min_resident, uint32_t resident_cap, const uint8_t *width_in,
                                   uint8_t *width_out, cudaStream_t s)
 {
-    bucket_scatter_kernel<<<bucket_pass_ctas(m), LAYOUT_THREADS, 0, s>>>(lit, m, k, bucket_vars, n_buckets, bkt, cta_base,
-                                                                           planes, m_pad, orig_id, min_resident, resident_cap, width_in, width_out);
+    if (k <= 8 && width_in == nullptr) {
+        // static (17 KB) + dynamic shared memory exceed the 48 KB default: opt in (per device, cheap, idempotent)
+        const cudaError_t e = cudaFuncSetAttribute(bucket_scatter_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)((k + 1) * LAYOUT_THREADS * 4));
+        if (e != cudaSuccess) return e;
+        bucket_scatter_staged_kernel<<<bucket_pass_ctas(m), LAYOUT_THREADS, (size_t)(k + 1) * LAYOUT_THREADS * 4, s>>>(
+            lit, m, k, bucket_vars, n_buckets, bkt, cta_base, planes, m_pad, orig_id, min_resident, resident_cap);
+    } else
+        bucket_scatter_kernel<<<bucket_pass_ctas(m), LAYOUT_THREADS, 0, s>>>(lit, m, k, bucket_vars, n_buckets, bkt, cta_base,
+                                                                               planes, m_pad, orig_id, min_resident, resident_cap, width_in, width_out);
     return cudaGetLastError();
 }
 

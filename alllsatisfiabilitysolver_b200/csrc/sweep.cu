@@ -72,6 +72,7 @@ struct WarpCompactor {
     Counters *ctr;
     unsigned int *n_viol;   // where |U| is accumulated (ctr->n_viol, or the round-parity counter of the persistent solve kernel)
     uint32_t p2p_parity; // sharded P2P mode: which of the two record areas this round uses
+    bool rec_on;         // write records next to the violated list this round
     uint32_t count;      // warp-uniform
     uint32_t lane;
     const SweepParams *sp;   // non-NULL with sp->p2p set: sharded P2P mode
@@ -102,7 +103,7 @@ struct WarpCompactor {
             }
         } else {
             for (uint32_t i = lane; i < count; i += 32) viol[g + i] = g_smem[wbuf + i];
-            if (sp != nullptr && sp->urec != nullptr && (uint64_t)g + count <= sp->urec_cap)
+            if (rec_on && sp != nullptr && sp->urec != nullptr && (uint64_t)g + count <= sp->urec_cap)
                 write_records(sp->urec, sp->planes, sp->m_pad, sp->orig_id, sp->id_base, sp->k, wbuf, g, count, lane);
         }
         __syncwarp();
@@ -373,13 +374,13 @@ struct SurvivorQueue {
 // TICKET: (sharded P2P mode) the CTA that finishes last publishes this rank's round to the peers; the persistent solve
 // kernel publishes after its grid barrier instead.
 template <int K, int RB, int RC, int E, bool TICKET>
-__device__ __forceinline__ void sweep_planes_body(const SweepParams &p, unsigned int *n_viol_ctr, uint32_t p2p_parity)
+__device__ __forceinline__ void sweep_planes_body(const SweepParams &p, unsigned int *n_viol_ctr, uint32_t p2p_parity, bool rec_on)
 {
     constexpr bool RESIDENT_ALL = RB >= K;
     constexpr int RBE = RB < E ? RB : E;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = threadIdx.x >> 5;
-    WarpCompactor out{p.bucket_words + warp * WBUF, p.viol, p.ctr, n_viol_ctr, p2p_parity, 0u, lane, &p};
+    WarpCompactor out{p.bucket_words + warp * WBUF, p.viol, p.ctr, n_viol_ctr, p2p_parity, rec_on, 0u, lane, &p};
     SurvivorQueue<K, E, RESIDENT_ALL> parked{p.bucket_words + (SWEEP_THREADS / 32) * WBUF + warp * QBUF, 0u, lane};
 
     const uint32_t t0 = (uint32_t)(((uint64_t)blockIdx.x * p.n_tiles) / gridDim.x);
@@ -454,7 +455,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const Sw
 {
     if (__ldcg(&p.ctr->done) || __ldcg(&p.ctr->incr_next)) return;   // behind the terminal round / this round is incremental
     if (blockIdx.x == 0 && threadIdx.x == 0 && p.round < DBG_ROUNDS) p.ctr->dbg[p.round][0] = global_ns();
-    sweep_planes_body<K, RB, RC, E, true>(p, &p.ctr->n_viol, p.p2p_parity);
+    sweep_planes_body<K, RB, RC, E, true>(p, &p.ctr->n_viol, p.p2p_parity, true);
 }
 
 // ---- the whole solve in one launch ------------------------------------------------------------------------
@@ -486,6 +487,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(cons
     const bool p2p = sp.p2p != nullptr;      // clause-range sharded solve: every GPU runs this kernel on its range
     const uint32_t first = blockIdx.x * SWEEP_THREADS + threadIdx.x, stride = gridDim.x * SWEEP_THREADS;
     unsigned long long t_sweep = 0, t_mis = 0;
+    uint32_t prev_n_u = (uint32_t)min((uint64_t)0xFFFFFFFFu, ((uint64_t)sp.n_tiles * TILE) >> K);
     for (uint32_t round = 0; round < max_rounds; ++round) {
         const uint32_t par = round & 1u, tag = ((epoch & 0xFFFu) << 20) | (round + 1u);
         unsigned long long t0 = 0, t1 = 0;
@@ -493,12 +495,15 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(cons
             t0 = global_ns();
             if (round < DBG_ROUNDS) c->dbg[round][0] = t0;
         }
-        if (threadIdx.x == 0) { s_mp.p2p_parity = par; s_mp.p2p_tag = tag; }
+        // records next to the violated list only while the violated set is expected to fit them (the previous round's
+        // |U|, or m / 2^K before the first round): writing the first urec_cap records of a larger set is wasted work
+        const bool rec_on = (uint64_t)prev_n_u <= 2ull * sp.urec_cap;
+        if (threadIdx.x == 0) { s_mp.p2p_parity = par; s_mp.p2p_tag = tag; s_mp.urec_cap = rec_on ? sp.urec_cap : 0u; }
         // incremental mode (ip.rows != NULL): the round that just ended decided whether this round's violated set comes
         // from the occurrence lists of the variables it resampled (same set as the sweep's, incremental.cu) or from a sweep
         const bool incremental = ip.rows != nullptr && round > 0 && gm::ld_cg(&c->incr_next) != 0;
         if (incremental) incr_eval_body(ip, gm::ld_cg(&c->last_n_s), &c->n_viol_pp[par]);
-        else sweep_planes_body<K, RB, RC, E, false>(sp, &c->n_viol_pp[par], par);
+        else sweep_planes_body<K, RB, RC, E, false>(sp, &c->n_viol_pp[par], par, rec_on);
         if (p2p) {                                       // this CTA's record stores (NVLink) are ordered before the barrier
             __syncthreads();
             if (threadIdx.x == 0) __threadfence_system();
@@ -557,6 +562,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(cons
             if (lead) finish_round(mp, round, n_u, 2u);
         }
         bar.sync();                                      // new assignment visible to every SM before it is staged again
+        prev_n_u = n_u;
         if (lead) t_mis += global_ns() - t1;
     }
     if (lead) {
@@ -571,7 +577,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_generic_kernel(
 {
     if (__ldcg(&p.ctr->done) || __ldcg(&p.ctr->incr_next)) return;
     const uint32_t lane = threadIdx.x & 31u;
-    WarpCompactor comp{p.bucket_words + (threadIdx.x >> 5) * WBUF, p.viol, p.ctr, &p.ctr->n_viol, 0u, 0u, lane, nullptr};
+    WarpCompactor comp{p.bucket_words + (threadIdx.x >> 5) * WBUF, p.viol, p.ctr, &p.ctr->n_viol, 0u, false, 0u, lane, nullptr};
 
     const uint32_t t0 = (uint32_t)(((uint64_t)blockIdx.x * p.n_tiles) / gridDim.x);
     const uint32_t t1 = (uint32_t)(((uint64_t)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
@@ -608,7 +614,7 @@ __global__ void __launch_bounds__(256) sweep_csr_kernel(const uint64_t *__restri
 {
     if (__ldcg(&ctr->done)) return;
     const uint32_t lane = threadIdx.x & 31u;                       // launched with 8 * WBUF words of dynamic smem
-    WarpCompactor comp{(threadIdx.x >> 5) * WBUF, viol, ctr, &ctr->n_viol, 0u, 0u, lane, nullptr};
+    WarpCompactor comp{(threadIdx.x >> 5) * WBUF, viol, ctr, &ctr->n_viol, 0u, false, 0u, lane, nullptr};
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t m_round = (m + 31) / 32 * 32;
     for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < m_round; c += stride) {
