@@ -2,7 +2,7 @@
 //
 // Host control flow replaces SATInstance::solve -> parallel_solve (SATInstance.h:60-66, :217-320).  There is
 // no CPU compute path in this file: every clause evaluation, independent-set decision and resample happens
-// in the kernels of sweep.cu / mis.cu / layout.cu.
+// in the kernels of persist.cu / sweep.cu / mis.cu / layout.cu.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -374,7 +374,7 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     h->use_width = d_width_in != nullptr && m > 0;
     if (int rc = alloc_common(h, h->m)) return rc;
     if (k >= 1 && k <= 8 && !h->use_width && m > 0) {
-        // violated-clause records for the independent-set kernels (sweep.cu:write_records), for violated sets of up to
+        // violated-clause records for the independent-set kernels (sweep_body.cuh:write_records), for violated sets of up to
         // URECORD_CAP clauses.  Larger sets read the literal planes instead: writing their records costs the sweep more
         // (scattered reads at the tail of the kernel: +54 us at |U| = 156 k) than it saves the gather (31 us there).
         const uint64_t cap = std::min<uint64_t>(m, URECORD_CAP);
@@ -846,7 +846,7 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
     const bool trace = getenv("ALLL_TRACE") != nullptr;
 
     if (h->persistent_ok && h->k && h->n_tiles && !h->gen_mode && !(h->flags & ALLL_FLAG_HOST_ROUND_LOOP)) {
-        // The whole round loop in one cooperative launch (sweep.cu: solve_persistent_kernel).
+        // The whole round loop in one cooperative launch (persist.cu: solve_persistent_kernel).
         if (max_rounds == 0) max_rounds = 1;
         const uint32_t cap = (uint32_t)std::min<uint64_t>(max_rounds, 0xFFFFFFFFull);
         const SweepParams sp = sweep_params(h, 0u, 0u, 0u, true);
@@ -897,7 +897,7 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
         while (issued < max_rounds && issued - retired < (uint64_t)ROUNDS_IN_FLIGHT) {
             const bool time_this = issued < (uint64_t)MAX_TIMED_ROUNDS;
             if (time_this) CK(cudaEventRecord(h->ev[2 * issued], h->stream));
-            // records for the independent set only while the violated set is expected to fit them (see sweep.cu)
+            // records for the independent set only while the violated set is expected to fit them (see persist.cu)
             const bool records = last_seen_u <= 2ull * h->urec_cap;
             if (int rc = enqueue_sweep(h, 0u, 0u, (uint32_t)issued, records)) return rc;
             if (time_this) CK(cudaEventRecord(h->ev[2 * issued + 1], h->stream));
@@ -1145,7 +1145,7 @@ int alll_solve_p2p(alll_handle h, uint64_t seed, uint64_t max_rounds, uint64_t m
     if (max_rounds == 0) max_rounds = 1;
     max_rounds = std::min<uint64_t>(max_rounds, (1u << 20) - 2);       // the round lives in 20 bits of the tag
     if ((h->flags & ALLL_FLAG_P2P_PERSISTENT) && h->persistent_ok && h->k && h->n_tiles) {
-        // every rank: the whole sharded solve in one cooperative launch (sweep.cu: solve_persistent_kernel, p2p branch)
+        // every rank: the whole sharded solve in one cooperative launch (persist.cu: solve_persistent_kernel, p2p branch)
         const SweepParams sp = sweep_params(h, 0u, 1u, 0u, false);              // (tag != 0 selects the P2P form; the kernel derives parity / tag per round)
         ClauseView pcv{};
         pcv.k = h->k;

@@ -1,5 +1,5 @@
 // incr_body.cuh -- per-round device code of the incremental re-evaluation (see incremental.cu), shared by
-// incr_eval_kernel and the persistent solve kernel of sweep.cu.
+// incr_eval_kernel and the persistent solve kernel of persist.cu.
 #pragma once
 
 #include "alll_device.cuh"

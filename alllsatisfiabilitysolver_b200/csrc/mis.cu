@@ -27,7 +27,7 @@
 // Latency structure: literals, priority, id and state of every violated clause are held in shared memory; all claim
 // reads of a step are issued together, and deciding step s is fused with claiming for step s+1: one barrier and one
 // memory round trip per Luby step however wide the clauses are.  The bodies are out-of-line functions with explicit
-// global-space memory operations (mis_body.cuh) shared with the persistent solve kernel of sweep.cu, where they run
+// global-space memory operations (mis_body.cuh) shared with the persistent solve kernel of persist.cu, where they run
 // between sweeps without kernel boundaries; Philox is one out-of-line function and literal loops are only unrolled
 // where loads must overlap (the first version compiled to 160 KB per kernel, all of it fetched cold after a sweep).
 //

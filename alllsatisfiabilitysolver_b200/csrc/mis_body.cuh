@@ -1,5 +1,5 @@
 // mis_body.cuh -- device code of K3 + K4 (see mis.cu for the algorithm), shared by the per-round kernels of mis.cu and
-// the persistent solve kernel of sweep.cu.
+// the persistent solve kernel of persist.cu.
 #pragma once
 
 #include <cooperative_groups.h>

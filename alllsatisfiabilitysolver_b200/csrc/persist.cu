@@ -1,0 +1,199 @@
+// persist.cu -- the whole solve in one cooperative launch: solve_persistent_kernel and its launchers.
+// Device code of the phases: sweep_body.cuh (clause evaluation + compaction), mis_body.cuh (independent set + resample),
+// incr_body.cuh (incremental re-evaluation).
+#include "incr_body.cuh"
+#include "mis_body.cuh"
+#include "sweep_body.cuh"
+
+namespace alll {
+
+// ---- the whole solve in one launch ------------------------------------------------------------------------
+// Replaces the round loop of parallel_solve (SATInstance.h:260-311) for the plane layout: sweep -> grid barrier ->
+// independent set + resample -> grid barrier, repeated on the device until a sweep finds no violated clause.
+// Why one kernel: the independent-set phases are a few microseconds of work but, launched as kernels of their own
+// behind a sweep that has just streamed > 1 GB through L2, they spend 20-100 us per round fetching their code cold
+// from DRAM (every phase cost about 0.6 us per 128-byte line of instructions it touched, whatever the size of U --
+// profiles/r01_mis_phases.md).  A persistent kernel keeps that code in the SMs' instruction caches from the second
+// round on, and launch gaps, event records and the host round trip disappear as well.
+// One CTA per SM (cooperative launch).  |U| is accumulated in one of two counters selected by round parity: the
+// one for round r+1 is cleared during the independent-set phase of round r, when nobody adds to it.
+template <int K, int RB, int RC, int E>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(const SweepParams sp, const MisParams mp_arg,
+                                                                           const uint32_t max_rounds, const uint32_t epoch,
+                                                                           const IncrParams ip, const uint32_t visited_words)
+{
+    // The independent-set bodies are out-of-line functions: they get the parameter block through a pointer, and a
+    // pointer to kernel parameters would force a per-thread local-memory copy.  One copy per CTA in shared memory
+    // (thread 0 also keeps the per-round exchange parity / tag of the sharded mode up to date in it).
+    __shared__ MisParams s_mp;
+    __shared__ uint32_t s_prefix[MAX_SHARDS + 1];
+    if (threadIdx.x == 0) s_mp = mp_arg;
+    __syncthreads();
+    const MisParams &mp = s_mp;
+    GridBarrier bar{cg::this_grid()};
+    Counters *const c = sp.ctr;
+    const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
+    const bool p2p = sp.p2p != nullptr;      // clause-range sharded solve: every GPU runs this kernel on its range
+    const uint32_t first = blockIdx.x * SWEEP_THREADS + threadIdx.x, stride = gridDim.x * SWEEP_THREADS;
+    unsigned long long t_sweep = 0, t_mis = 0;
+    uint32_t prev_n_u = (uint32_t)min((uint64_t)0xFFFFFFFFu, ((uint64_t)sp.n_tiles * TILE) >> K);
+    for (uint32_t round = 0; round < max_rounds; ++round) {
+        const uint32_t par = round & 1u, tag = ((epoch & 0xFFFu) << 20) | (round + 1u);
+        unsigned long long t0 = 0, t1 = 0;
+        if (lead) {
+            t0 = global_ns();
+            if (round < DBG_ROUNDS) c->dbg[round][0] = t0;
+        }
+        // records next to the violated list only while the violated set is expected to fit them (the previous round's
+        // |U|, or m / 2^K before the first round): writing the first urec_cap records of a larger set is wasted work
+        const bool rec_on = (uint64_t)prev_n_u <= 2ull * sp.urec_cap;
+        if (threadIdx.x == 0) { s_mp.p2p_parity = par; s_mp.p2p_tag = tag; s_mp.urec_cap = rec_on ? sp.urec_cap : 0u; }
+        // incremental mode (ip.rows != NULL): the round that just ended decided whether this round's violated set comes
+        // from the occurrence lists of the variables it resampled (same set as the sweep's, incremental.cu) or from a sweep
+        const bool incremental = ip.rows != nullptr && round > 0 && gm::ld_cg(&c->incr_next) != 0;
+        if (incremental) incr_eval_body(ip, gm::ld_cg(&c->last_n_s), &c->n_viol_pp[par]);
+        else sweep_planes_body<K, RB, RC, E, false>(sp, &c->n_viol_pp[par], par, rec_on);
+        if (p2p) {                                       // this CTA's record stores (NVLink) are ordered before the barrier
+            __syncthreads();
+            if (threadIdx.x == 0) __threadfence_system();
+        }
+        bar.sync();
+        uint32_t n_u;
+        if (p2p) {
+            // fused exchange: the violated records went straight into every GPU's region during the sweep; publish our
+            // count + arrival flag everywhere, then wait for every peer's flag of this round
+            if (lead) {
+                const P2PLink &L = *sp.p2p;
+                const unsigned int total = gm::ld_cg(&c->n_viol_pp[par]);
+                for (uint32_t q = 0; q < L.world; q++) L.hdr[q]->count[par][L.rank] = total;
+                __threadfence_system();
+                for (uint32_t q = 0; q < L.world; q++) *(volatile unsigned int *)&L.hdr[q]->flag[par][L.rank] = tag;
+            }
+            n_u = p2p_wait(mp, s_prefix);
+        } else {
+            n_u = gm::ld_cg(&c->n_viol_pp[par]);
+        }
+        if (lead) {
+            t1 = global_ns();
+            t_sweep += t1 - t0;
+            if (round < DBG_ROUNDS) { c->dbg[round][1] = t1; c->dbg[round][2] = t1; }
+            c->n_viol_pp[par ^ 1u] = 0;
+        }
+        if (incremental)                                 // the first-visit bits of this round: nobody reads them before the next one
+            for (uint32_t i = first; i < visited_words; i += stride) ip.visited[i] = 0u;
+        if (n_u == 0xFFFFFFFFu) {                        // a peer overflowed its exchange area or never arrived: stop
+            if (lead) {
+                c->p2p_error = c->p2p_error ? c->p2p_error : 2;
+                c->done = 2;
+            }
+            break;
+        }
+        if (n_u == 0) {                                  // SATInstance.h:285-287; the terminal sweep counts (:261)
+            if (lead) {
+                gm::red_add(&c->n_iterations, 1ull);
+                if (incremental) c->n_incr_rounds += 1;
+                c->last_n_viol = 0;
+                c->last_n_s = 0;
+                c->last_resampled = 0;
+                c->done = 1;
+            }
+            break;
+        }
+        if (n_u <= SMALL_U && (uint64_t)n_u * mp.kmax <= HSLOTS / 2 && mp.small_ok) {
+            if (blockIdx.x == 0) {
+                mis_small_body(mp, round, s_prefix, n_u);
+                if (threadIdx.x == 0) finish_round(mp, round, n_u, 0u);
+            }
+        } else {
+            if ((uint64_t)n_u <= (uint64_t)stride * mp.cache_items) mis_resample_body<GridBarrier, true>(mp, round, bar, s_prefix, first, stride, n_u);
+            else mis_resample_body<GridBarrier, false>(mp, round, bar, s_prefix, first, stride, n_u);
+            bar.sync();
+            if (lead) finish_round(mp, round, n_u, 2u);
+        }
+        bar.sync();                                      // new assignment visible to every SM before it is staged again
+        prev_n_u = n_u;
+        if (lead) t_mis += global_ns() - t1;
+    }
+    if (lead) {
+        c->t_sweep_ns = t_sweep;
+        c->t_mis_ns = t_mis;
+    }
+}
+
+// ---- launchers ------------------------------------------------------------------------
+
+namespace {
+struct PersistOp {
+    const SweepParams &p;
+    uint32_t grid;
+    size_t smem;
+    cudaStream_t s;
+    const MisParams *mp;          // NULL: configure (shared-memory opt-in + occupancy) instead of launching
+    uint32_t max_rounds, epoch;
+    const IncrParams *ip;
+    uint32_t visited_words;
+    int *max_ctas_per_sm;
+    template <int K, int RB, int RC, int E> cudaError_t run()
+    {
+        if (mp == nullptr) {
+            cudaError_t e = cudaFuncSetAttribute(solve_persistent_kernel<K, RB, RC, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_ctas_per_sm, solve_persistent_kernel<K, RB, RC, E>, SWEEP_THREADS, smem);
+        }
+        void *args[] = {(void *)&p, (void *)mp, (void *)&max_rounds, (void *)&epoch, (void *)ip, (void *)&visited_words};
+        return cudaLaunchCooperativeKernel((const void *)solve_persistent_kernel<K, RB, RC, E>, dim3(grid), dim3(SWEEP_THREADS), args, smem, s);
+    }
+};
+} // namespace
+
+// ---- persistent solve kernel: shared memory = the sweep's, or what the independent-set phases need if that is more
+static size_t persistent_smem_bytes(uint32_t bucket_words, uint32_t kmax)
+{
+    const size_t small_words = mis_small_words(SWEEP_THREADS, kmax);
+    const size_t one_item = (size_t)SWEEP_THREADS * mis_cache_words(kmax);
+    size_t b = sweep_smem_bytes_for(bucket_words);
+    if (small_words * 4 <= 200u * 1024u) b = b > small_words * 4 ? b : small_words * 4;
+    else if (one_item * 4 <= 200u * 1024u) b = b > one_item * 4 ? b : one_item * 4;
+    return b;
+}
+
+static void persistent_fill(const SweepParams &p, MisParams &mp, size_t smem)
+{
+    mp.cache_items = (uint32_t)((smem / 4 / SWEEP_THREADS) / mis_cache_words(mp.kmax));
+    mp.small_ok = mis_small_words(SWEEP_THREADS, mp.kmax) * 4 <= smem ? 1u : 0u;
+    (void)p;
+}
+
+// ok_out: 1 when the instance can be solved by the persistent kernel on this device (k <= 8, one CTA per SM fits)
+cudaError_t configure_solve_persistent(const SweepParams &p, bool resident_all, uint32_t kmax, int *ok_out)
+{
+    *ok_out = 0;
+    if (p.k == 0 || p.k > 8) return cudaSuccess;
+    int per_sm = 0;
+    PersistOp op{p, 0u, persistent_smem_bytes(p.bucket_words, kmax), 0, nullptr, 0u, 0u, nullptr, 0u, &per_sm};
+    const cudaError_t e = dispatch_variant(p, resident_all, op);
+    if (e != cudaSuccess) return e;
+    *ok_out = per_sm >= 1;
+    return cudaSuccess;
+}
+
+cudaError_t launch_solve_persistent(const SweepParams &p, bool resident_all, uint32_t grid, const ClauseView &cv, uint32_t kmax,
+                                    uint8_t *state, uint32_t *s_slots, const MisScratch &sc, uint64_t n_vars, uint64_t seed,
+                                    uint32_t max_rounds, uint32_t epoch, const IncrParams *incr, uint32_t visited_words,
+                                    uint32_t incr_max_vars, cudaStream_t s)
+{
+    const size_t smem = persistent_smem_bytes(p.bucket_words, kmax);
+    MisParams mp{};
+    mp.cv = cv; mp.viol = p.p2p ? nullptr : p.viol; mp.state = state; mp.s_slots = s_slots;
+    mp.p2p = p.p2p;                                    // sharded: U = the record blocks in our exchange region
+    mp.claim = sc.claim;
+    mp.n_vars = n_vars; mp.bits = const_cast<uint32_t *>(p.bits); mp.ctr = p.ctr; mp.seed = seed; mp.kmax = kmax;
+    mp.urec = sc.urec; mp.urec_cap = sc.urec_cap;
+    persistent_fill(p, mp, smem);
+    mp.incr_max_vars = incr ? incr_max_vars : 0u;
+    const IncrParams no_incr{};
+    PersistOp op{p, grid, smem, s, &mp, max_rounds, epoch, incr ? incr : &no_incr, incr ? visited_words : 0u, nullptr};
+    return dispatch_variant(p, resident_all, op);
+}
+
+} // namespace alll
