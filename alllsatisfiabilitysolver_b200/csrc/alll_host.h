@@ -61,7 +61,8 @@ size_t batch_smem_bytes(uint32_t n_vars, uint32_t n_words, uint32_t m_max);
 cudaError_t launch_batch_solve(const uint32_t *planes, uint64_t m_pad, const uint32_t *inst_off, const uint32_t *inst_m,
                                uint32_t n_instances, uint32_t n_vars, uint32_t n_words, uint32_t k, uint32_t m_max,
                                const uint64_t *seeds, uint64_t max_rounds, uint32_t *bits_out, BatchJobStats *stats,
-                               int portfolio, int *winner, int job_base, int shared, uint32_t n_jobs, cudaStream_t s);
+                               int portfolio, int *winner, int job_base, int shared, uint32_t n_jobs, uint32_t *retry,
+                               int *n_launches, cudaStream_t s);
 cudaError_t launch_batch_transpose(const uint32_t *lit, const uint64_t *src_off, const uint32_t *inst_off, uint32_t n_instances,
                                    uint32_t k, uint32_t n_vars, uint32_t *planes, uint64_t m_pad, uint32_t *err, cudaStream_t s);
 cudaError_t launch_batch_unpack(const uint32_t *bits, uint32_t n_words, uint32_t n_vars, uint64_t total, uint8_t *out, cudaStream_t s);

@@ -101,6 +101,7 @@ struct alll_solver {
     BatchJobStats *d_b_stats = nullptr;
     uint8_t *d_b_bytes = nullptr;
     int *d_b_winner = nullptr;
+    uint32_t *d_b_retry = nullptr;      // small batch kernel -> large batch kernel: count + job ids
     // multi-GPU portfolio: one winner word for all ranks, owned by one GPU and peer-mapped (CUDA IPC) by the others
     int *d_flag = nullptr;               // the word as this process addresses it
     bool flag_owner = false;
@@ -157,7 +158,7 @@ void release_buffers(alll_handle h)
     dfree(h->d_state); dfree(h->d_bools); dfree(h->d_width); dfree(h->d_width_in); dfree(h->d_tmp_bkt); dfree(h->d_tmp_cnt); dfree(h->d_tmp_err); dfree(h->d_stage);
     dfree(h->d_sh_planes); dfree(h->d_sh_ids); dfree(h->d_sh_iota); dfree(h->d_sh_s); dfree(h->d_sh_state);
     dfree(h->d_b_planes); dfree(h->d_b_off); dfree(h->d_b_m); dfree(h->d_b_bits); dfree(h->d_b_lit); dfree(h->d_b_src_off);
-    dfree(h->d_b_seeds); dfree(h->d_b_stats); dfree(h->d_b_bytes); dfree(h->d_b_winner);
+    dfree(h->d_b_seeds); dfree(h->d_b_stats); dfree(h->d_b_bytes); dfree(h->d_b_winner); dfree(h->d_b_retry);
     h->has_batch = false;
     for (uint32_t q = 0; q < MAX_SHARDS; q++)
         if (h->p2p_peer[q]) { cudaIpcCloseMemHandle(h->p2p_peer[q]); h->p2p_peer[q] = nullptr; }
@@ -1334,6 +1335,7 @@ int alll_batch_solve(alll_handle h, uint32_t n_jobs, const uint64_t *seeds, uint
     POOL(h->d_b_stats, (size_t)n_jobs * sizeof(BatchJobStats));
     POOL(h->d_b_bits, (size_t)n_jobs * h->b_n_words * 4);
     POOL(h->d_b_winner, 4);
+    POOL(h->d_b_retry, ((size_t)n_jobs + 1) * 4);
     const int minus1 = -1;
     CK(cudaMemcpyAsync(h->d_b_seeds, seeds, (size_t)n_jobs * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_b_winner, &minus1, 4, cudaMemcpyHostToDevice, h->stream));
@@ -1341,10 +1343,11 @@ int alll_batch_solve(alll_handle h, uint32_t n_jobs, const uint64_t *seeds, uint
     CK(cudaMemsetAsync(h->d_b_bits, 0, (size_t)n_jobs * h->b_n_words * 4, h->stream));
     cudaEvent_t e0 = h->ev[0], e1 = h->ev[1];
     CK(cudaEventRecord(e0, h->stream));
+    int n_launched = 1;
     CK(launch_batch_solve(h->d_b_planes, h->b_m_pad, h->d_b_off, h->d_b_m, h->b_n_inst, h->b_n_vars, h->b_n_words, h->b_k,
                           h->b_m_max, h->d_b_seeds, max_rounds, h->d_b_bits, h->d_b_stats, portfolio ? 1 : 0, d_winner_word,
-                          (int)h->b_job_base, shared ? 1 : 0, n_jobs, h->stream));
-    h->launches++;
+                          (int)h->b_job_base, shared ? 1 : 0, n_jobs, h->d_b_retry, &n_launched, h->stream));
+    h->launches += n_launched;
     CK(cudaEventRecord(e1, h->stream));
     CK(cudaMemcpyAsync(stats, h->d_b_stats, (size_t)n_jobs * sizeof(BatchJobStats), cudaMemcpyDeviceToHost, h->stream));
     int w = -1;

@@ -22,7 +22,10 @@ def make_batch(n_inst, n, k, d, seed0):
     return insts, off, np.concatenate(insts, axis=0)
 
 
-@pytest.mark.parametrize("shape", [(48, 2000, 5, 3), (24, 10_000, 5, 3), (16, 3000, 7, 20), (8, 1500, 3, 4)])
+@pytest.mark.parametrize("shape", [(48, 2000, 5, 3), (24, 10_000, 5, 3), (16, 3000, 7, 20), (8, 1500, 3, 4),
+                                   (6, 9000, 3, 3),       # |U| ~ 1,100 in round 0: every job outgrows the small kernel's records
+                                   (4, 2000, 9, 40),      # k = 9: large kernel only
+                                   (5, 4000, 8, 30), (5, 3000, 4, 3), (5, 3000, 6, 8)])
 def test_batch_matches_oracle_per_instance(capi, oracle, shape):
     """Every instance of the batch ends with the oracle's assignment and Statistics for its seed
     (same round specification as alll_solve), and the assignment satisfies the instance."""
@@ -43,6 +46,32 @@ def test_batch_matches_oracle_per_instance(capi, oracle, shape):
         assert (int(stats["n_iterations"][i]), int(stats["n_resamples"][i]), int(stats["sum_mis_size"][i])) == \
                (so.n_iterations, so.n_resamples, so.sum_mis_size)
         assert np.array_equal(assign[i], v) and oracle.verify(coff, flat, assign[i])
+
+
+def test_batch_mixed_small_and_retried_jobs(capi, oracle):
+    """One batch whose instances differ in size: the small ones finish in the small kernel, the ones whose violated set
+    outgrows its records are redone by the large kernel behind it -- every job must still equal the oracle."""
+    from alllsatisfiabilitysolver_b200.instances import bounded_degree_ksat
+
+    n, k = 9000, 3
+    insts = [bounded_degree_ksat(n, k, d, seed=4000 + i) for i, d in enumerate([1, 3, 1, 2, 3, 1, 3])]
+    sizes = [x.shape[0] for x in insts]
+    assert min(sizes) * 2 ** -k < 400 and max(sizes) * 2 ** -k > 700      # both sides of the 512-record limit
+    off = np.zeros(len(insts) + 1, np.uint64)
+    off[1:] = np.cumsum(sizes)
+    seeds = np.arange(77, 77 + len(insts), dtype=np.uint64)
+    with capi.Solver() as s:
+        s.batch_upload(n, k, off, np.concatenate(insts, axis=0))
+        for _ in range(2):                                                   # the retry list is reset per call
+            stats, assign, _, _ = s.batch_solve(seeds)
+            for i, lits in enumerate(insts):
+                coff = np.arange(lits.shape[0] + 1, dtype=np.uint64) * np.uint64(k)
+                v = oracle.randomize(n, int(seeds[i]))
+                so = oracle.solve(n, coff, lits.reshape(-1), v, int(seeds[i]))
+                assert stats["status"][i] == 0 and so.status == 0
+                assert (int(stats["n_iterations"][i]), int(stats["n_resamples"][i]), int(stats["sum_mis_size"][i])) == \
+                       (so.n_iterations, so.n_resamples, so.sum_mis_size)
+                assert np.array_equal(assign[i], v)
 
 
 def test_batch_agrees_with_single_instance_path(capi):
