@@ -234,11 +234,22 @@ size_t batch_small_smem_bytes(uint32_t n_vars, uint32_t n_words, uint32_t k)
 {
     return (size_t)bs_align4(n_words) * 4 + (size_t)BS_UCAP * 8 + (size_t)k * BS_UCAP * 4 + BS_UCAP + (size_t)bs_align4((n_vars + 1) / 2) * 4;
 }
+// The small kernel takes the batch when this holds.
+static bool batch_small_eligible(uint32_t n_vars, uint32_t n_words, uint32_t k)
+{
+    return k >= 3 && k <= 8 && batch_small_smem_bytes(n_vars, n_words, k) <= 100u * 1024u;      // >= 2 CTAs per SM
+}
 
+__device__ __forceinline__ uint32_t bs_lds32(uint32_t byte_addr)
+{
+    uint32_t w;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(byte_addr));
+    return w;
+}
 __device__ __forceinline__ uint32_t lane_of(const uint4 &v, int q) { return q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w; }
 
-template <uint32_t K>
-__global__ void __launch_bounds__(BS_THREADS, 4) batch_solve_small_kernel(const BatchParams p)
+template <uint32_t K, int MINB, bool PIPE>
+__global__ void __launch_bounds__(BS_THREADS, MINB) batch_solve_small_kernel(const BatchParams p)
 {
     const uint32_t job = blockIdx.x;
     const uint32_t inst = p.portfolio ? 0u : job;
@@ -271,33 +282,36 @@ __global__ void __launch_bounds__(BS_THREADS, 4) batch_solve_small_kernel(const 
     int status = 1;                       // ALLL_MAX_ROUNDS until proven otherwise
     const uint64_t max_rounds = p.max_rounds ? p.max_rounds : 1;
     const uint32_t *lit0 = p.planes + off;
+    const uint32_t sbits = (uint32_t)__cvta_generic_to_shared(bits);
 
     for (uint64_t round = 0; round < max_rounds; round++) {
         if (tid == 0) { s_nu = 0; s_ns = 0; s_stop = p.portfolio && *(volatile int *)p.winner >= 0; }
         __syncthreads();
         if (s_stop) { status = BATCH_PREEMPTED; break; }
+        uint32_t sb = sbits;
+        asm volatile("" : "+r"(sb));      // opaque register copy of the window address: nvcc otherwise rebuilds it (S2R, MOV, LEA) per
+                                          // lookup; re-made after the barrier so that no lookup is hoisted above the resample of the last round
 
-        // ---- K1+K2: four clauses per thread and step; all K plane loads of the step are in flight together
-        for (uint32_t c0 = tid * 4; c0 < m; c0 += BS_THREADS * 4) {
-            uint4 L[K];
+        // ---- K1+K2: four clauses per thread and group; all K plane loads of a step (one or two groups) are in flight together
+        // Lookups are predicated on the clause still being unsatisfied (a dead lane touches no bank) and branch-free:
+        // shift, mask, ld.shared through a 32-bit window address, funnel shift, one LOP3, predicate -- 8 instructions per literal (17 with `if`s and bits[] indexing).
+        auto eval_group = [&](const uint4 (&L)[K], uint32_t c0) {
+            uint32_t a[4];                                     // bit 0: clause q has seen no true literal yet
 #pragma unroll
-            for (uint32_t j = 0; j < K; j++) L[j] = ld_stream_v4(lit0 + (uint64_t)j * p.m_pad + c0);
-            uint32_t alive = m - c0 >= 4 ? 15u : (1u << (m - c0)) - 1u;
+            for (int q = 0; q < 4; q++) a[q] = c0 + q < m ? 1u : 0u;
 #pragma unroll
             for (uint32_t j = 0; j < K; j++) {
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const uint32_t l = lane_of(L[j], q);
-                    if ((alive >> q) & 1u) {
-                        const uint32_t v = l >> 1;
-                        if (((bits[v >> 5] >> (v & 31u)) ^ l) & 1u) alive &= ~(1u << q);
-                    }
+                    const uint32_t w = a[q] ? bs_lds32(sb + ((l >> 6) << 2)) : 0u;
+                    a[q] &= ~(__funnelshift_r(w, 0u, l >> 1) ^ l);            // bit (v & 31) of the word, xor the negation flag
                 }
             }
-            if (alive) {
+            if (a[0] | a[1] | a[2] | a[3]) {
 #pragma unroll
                 for (int q = 0; q < 4; q++)
-                    if ((alive >> q) & 1u) {
+                    if (a[q]) {
                         const uint32_t idx = atomicAdd(&s_nu, 1u);
                         if (idx < BS_UCAP) {
                             key[idx] = c0 + q;
@@ -305,6 +319,27 @@ __global__ void __launch_bounds__(BS_THREADS, 4) batch_solve_small_kernel(const 
                             for (uint32_t j = 0; j < K; j++) rec[j * BS_UCAP + idx] = lane_of(L[j], q);
                         }
                     }
+            }
+        };
+        if (PIPE) {
+            for (uint32_t c0 = tid * 4; c0 < m; c0 += BS_THREADS * 8) {
+                const uint32_t c1 = c0 + BS_THREADS * 4;
+                uint4 A[K], B[K];
+#pragma unroll
+                for (uint32_t j = 0; j < K; j++) A[j] = ld_stream_v4(lit0 + (uint64_t)j * p.m_pad + c0);
+                if (c1 < m) {
+#pragma unroll
+                    for (uint32_t j = 0; j < K; j++) B[j] = ld_stream_v4(lit0 + (uint64_t)j * p.m_pad + c1);
+                }
+                eval_group(A, c0);
+                if (c1 < m) eval_group(B, c1);
+            }
+        } else {
+            for (uint32_t c0 = tid * 4; c0 < m; c0 += BS_THREADS * 4) {
+                uint4 L[K];
+#pragma unroll
+                for (uint32_t j = 0; j < K; j++) L[j] = ld_stream_v4(lit0 + (uint64_t)j * p.m_pad + c0);
+                eval_group(L, c0);
             }
         }
         __syncthreads();
@@ -421,13 +456,24 @@ size_t batch_smem_bytes(uint32_t n_vars, uint32_t n_words, uint32_t m_max)
     return (size_t)n_vars * 8 + (size_t)((n_words + 3u) & ~3u) * 4 + (size_t)m_max * 4 + (((size_t)m_max + 15) & ~(size_t)15);
 }
 
+template <uint32_t K, int MINB, bool PIPE>
+static cudaError_t launch_small_v(const BatchParams &p, size_t smem, uint32_t n_jobs, cudaStream_t s)
+{
+    cudaError_t e = cudaFuncSetAttribute(batch_solve_small_kernel<K, MINB, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    batch_solve_small_kernel<K, MINB, PIPE><<<n_jobs, BS_THREADS, smem, s>>>(p);
+    return cudaGetLastError();
+}
 template <uint32_t K>
 static cudaError_t launch_small(const BatchParams &p, size_t smem, uint32_t n_jobs, cudaStream_t s)
 {
-    cudaError_t e = cudaFuncSetAttribute(batch_solve_small_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    batch_solve_small_kernel<K><<<n_jobs, BS_THREADS, smem, s>>>(p);
-    return cudaGetLastError();
+    static const int variant = getenv("ALLL_BATCH_VARIANT") ? atoi(getenv("ALLL_BATCH_VARIANT")) : 0;
+    switch (variant) {                                          // measured on B200, cfg5 (profiles/r01_batch_small.md)
+    case 1: return launch_small_v<K, 6, false>(p, smem, n_jobs, s);    // 40 registers, 6 CTAs per SM: 1.04 ms
+    case 2: return launch_small_v<K, 4, true>(p, smem, n_jobs, s);     // two groups in flight, 4 CTAs per SM: 0.92 ms
+    case 3: return launch_small_v<K, 4, false>(p, smem, n_jobs, s);    // 64 registers, 4 CTAs per SM: 0.94 ms
+    default: return launch_small_v<K, 5, false>(p, smem, n_jobs, s);   // 47 registers, 5 CTAs per SM: 0.84 ms
+    }
 }
 
 // retry: n_jobs + 1 words of device scratch (NULL: large kernel only).  *n_launches: kernels enqueued.
@@ -444,7 +490,7 @@ cudaError_t launch_batch_solve(const uint32_t *planes, uint64_t m_pad, const uin
     BatchParams p{planes, m_pad, inst_off, inst_m, n_instances, n_vars, n_words, k, m_max, seeds, max_rounds, bits_out, stats,
                   portfolio, winner, job_base, shared, retry, 0};
     const size_t small = batch_small_smem_bytes(n_vars, n_words, k);
-    const bool use_small = retry && !large_only && k >= 3 && k <= 8 && small <= 100u * 1024u;   // >= 2 CTAs per SM
+    const bool use_small = retry && !large_only && batch_small_eligible(n_vars, n_words, k);
     if (n_launches) *n_launches = use_small ? 2 : 1;
     if (!use_small) {
         batch_solve_kernel<<<n_jobs, BATCH_THREADS, smem, s>>>(p);

@@ -52,51 +52,92 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).
+
+    Samples come from NVML (nvidia_ml_py, one query every ~4 ms in a thread) or, without it, from an `nvidia-smi -lms 20`
+    child.  The sampler is started before the warm-up so that it is already running when the timed region begins; every
+    sample carries its arrival time and stop(t0, t1) keeps the ones that fell inside the region.
+    """
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
-        self.samples = []
+        self.samples = []          # (t, sm_mhz, sm_max_mhz, [reason names])
         self.proc = None
+        self.source = None
+        self._stop = threading.Event()
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.bits = [(getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8), "hw_slowdown"),
+                         (getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40), "hw_thermal_slowdown"),
+                         (getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), "sw_thermal_slowdown"),
+                         (getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4), "sw_power_cap")]
+            self._sample_nvml()                                  # fails here rather than in the thread
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._loop_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.samples = []
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def _sample_nvml(self):
+        nv = self.nv
+        mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        self.samples.append((time.perf_counter(), mhz, self.max_mhz, [nm for bit, nm in self.bits if mask & bit]))
+
+    def _loop_nvml(self):
+        while not self._stop.is_set():
+            try:
+                self._sample_nvml()
+            except Exception:
+                return
+            time.sleep(0.004)
+
     def _read(self):
         for line in self.proc.stdout:
             parts = [x.strip() for x in line.split(",")]
             if len(parts) >= 6:
-                self.samples.append(parts)
+                try:
+                    self.samples.append((time.perf_counter(), float(parts[0]), float(parts[1]),
+                                         [nm for nm, val in zip(self.NAMES, parts[2:6]) if val.lower().startswith("active")]))
+                except ValueError:
+                    continue
 
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+    def stop(self, t0: float | None = None, t1: float | None = None):
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
+        if self.source == "nvidia-smi":
+            time.sleep(0.05)
+            self.proc.terminate()
             try:
-                sm.append(float(s[0]))
-                mx.append(float(s[1]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, s[2:6]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        else:
+            self._stop.set()
+            self.t.join(timeout=1)
+        inside = [s for s in self.samples if t0 is not None and t0 <= s[0] <= t1]
+        use = inside if inside else self.samples
+        sm = [s[1] for s in use]
+        reasons = sorted({r for s in use for r in s[3]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max((s[2] for s in use), default=None),
+                "reasons": reasons, "samples": len(sm), "source": self.source,
+                "window": "timed region" if inside else "whole run (no sample fell inside the timed region)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -220,19 +261,20 @@ def run_ours(args):
         solver.randomize(1000 + i)
         return solver.solve(1000 + i, max_rounds)
 
+    clocks = ClockSampler(local_rank) if rank == 0 else None   # already sampling when the timed region starts
     for i in range(args.warmup):
         one_step(-1 - i)
 
     # ---- timed region: exactly K steps, inputs resident in HBM ----
     barrier()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
     launches0 = solver.launch_count()
     t0 = time.perf_counter()
     stats = [one_step(i) for i in range(args.steps)]
     barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
+    t1 = time.perf_counter()
+    wall_ms = (t1 - t0) * 1e3
     launches = solver.launch_count() - launches0
-    clk = clocks.stop() if clocks else None
+    clk = clocks.stop(t0, t1) if clocks else None
 
     dev_ms = sum(s.solve_ms for s in stats)                 # CUDA events on the solver's stream
     evals = sum(s.n_clause_evals for s in stats)
