@@ -160,9 +160,6 @@ struct Counters {
     unsigned int incr_next;     // 1: the next violated set comes from incr_eval_kernel, the sweep kernel returns at entry
     unsigned int n_incr_rounds; // rounds evaluated incrementally so far
     unsigned long long n_evals_incr;   // clauses actually evaluated by incremental rounds
-    // tail of a large independent-set round: the clauses still undecided when one CTA takes over (mis_body.cuh)
-    unsigned int tail_n;
-    unsigned int tail_list[512];
     // persistent solve kernel: |U| by round parity; time spent in sweeps / between sweeps as block 0 saw it
     unsigned int n_viol_pp[2];
     unsigned long long t_sweep_ns, t_mis_ns;

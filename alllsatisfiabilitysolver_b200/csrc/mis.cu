@@ -85,7 +85,7 @@ __global__ void __cluster_dims__(CL_SIZE, 1, 1) __launch_bounds__(CL_THREADS) mi
     if (n_u > CLUSTER_U && p.grid_follows) return;  // the grid kernel behind us takes it (else: strided, slower, still exact)
     if (n_u <= SMALL_U && (uint64_t)n_u * p.kmax <= HSLOTS / 2 && p.cache_items) {
         if (blockIdx.x != 0) return;              // uniform over the cluster: nobody waits on a cluster barrier below
-        mis_small_body(p, round, s_prefix, n_u, nullptr, 0u);
+        mis_small_body(p, round, s_prefix, n_u);
         if (threadIdx.x == 0) finish_round(p, round, n_u, 0u);
         return;
     }
@@ -134,7 +134,6 @@ __global__ void reset_counters_kernel(Counters *c, int reset_totals)
     c->cta_done = 0;
     c->p2p_error = 0;
     c->incr_next = 0;
-    c->tail_n = 0;
     c->n_viol_pp[0] = 0;
     c->n_viol_pp[1] = 0;
     c->t_sweep_ns = 0;
@@ -197,14 +196,12 @@ cudaError_t launch_mis_resample_args(const ClauseView &cv, uint32_t kmax, const 
                                      uint32_t p2p_tag, uint32_t incr_max_vars, uint32_t u_cap, cudaStream_t s)
 {
     MisParams p{cv, viol, state, s_slots, sc.claim, n_vars, bits, ctr, seed, kmax,
-                cluster_cache_items(kmax), cluster_cache_items(kmax), cluster_cache_items(kmax) ? mis_tail_max(kmax) : 0u,
-                with_grid ? 1u : 0u, note, seq, sc.urec, sc.urec_cap, p2p, p2p_parity, p2p_tag,
+                cluster_cache_items(kmax), cluster_cache_items(kmax), with_grid ? 1u : 0u, note, seq, sc.urec, sc.urec_cap, p2p, p2p_parity, p2p_tag,
                 incr_max_vars, u_cap};
     mis_cluster_kernel<<<CL_SIZE, CL_THREADS, cluster_smem_bytes(kmax), s>>>(p, round);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || !with_grid) return e;
     p.cache_items = grid_cache_items(kmax);
-    p.tail_max = 0;                     // (256-thread CTAs with 48 KB: no room for the one-CTA tail)
     void *args[] = {(void *)&p, (void *)&round};
     return cudaLaunchCooperativeKernel((const void *)mis_grid_kernel, dim3(grid), dim3(GRID_THREADS), args,
                                        grid_smem_bytes(kmax), s);

@@ -2,8 +2,6 @@
 // the persistent solve kernel of persist.cu.
 #pragma once
 
-#include <cstdlib>
-
 #include <cooperative_groups.h>
 
 #include "alll_device.cuh"
@@ -27,14 +25,6 @@ enum : uint32_t { UNDECIDED = 0, IN_SET = 1, DROPPED = 2 };
 
 // shared-memory words: per cached clause of mis_resample_body / all of mis_small_body in a CTA of `threads` threads
 __host__ __device__ constexpr uint32_t mis_cache_words(uint32_t kmax) { return kmax + EXTRA; }
-// largest undecided set the one-CTA tail takes over (mis_small_body's limits: SMALL_U clauses, HSLOTS / 2 variables);
-// env ALLL_NO_TAIL=1 switches the hand-off off (measurement knob)
-inline uint32_t mis_tail_max(uint32_t kmax)
-{
-    static const bool off = getenv("ALLL_NO_TAIL") != nullptr;
-    const uint32_t by_table = (HSLOTS / 2) / (kmax ? kmax : 1);
-    return off ? 0u : (by_table < SMALL_U ? by_table : SMALL_U);
-}
 __host__ __device__ constexpr size_t mis_small_words(uint32_t threads, uint32_t kmax)
 {
     return (size_t)threads * (2 * kmax + EXTRA) + 2 * (size_t)HSLOTS + 2 * (size_t)SMALL_U;   // literals + table slots | table | keys
@@ -53,7 +43,6 @@ struct MisParams {
     uint32_t kmax;              // widest clause
     uint32_t cache_items;       // clauses per thread that fit the shared-memory cache
     uint32_t small_ok;          // the shared memory of the launch holds mis_small_body's tables (persistent solve kernel)
-    uint32_t tail_max;          // once at most this many clauses are undecided, one CTA finishes the Luby steps in shared memory (0 = never)
     uint32_t grid_follows;      // cluster kernel only: a grid kernel is enqueued behind it and takes large sets
     RoundNote *note;            // pinned host memory (may be NULL): where the finished round is announced
     unsigned long long seq;     // value to publish in note->seq
@@ -248,9 +237,6 @@ __device__ __forceinline__ uint32_t p2p_wait(const MisParams &p, uint32_t *s_pre
     return s_prefix[L.world];
 }
 
-static __device__ __noinline__ void mis_small_body(const MisParams &p, uint32_t round, const uint32_t *prefix, uint32_t n_u,
-                                                   const unsigned int *list, uint32_t n_total);
-
 // Threads `first`, `first + stride`, ... of the participating group own the same U entries in every phase.
 //
 // One barrier and one memory round trip per Luby step: step s decides on the claims standing in array s&1 and,
@@ -303,7 +289,6 @@ __device__ __noinline__ void mis_resample_body(const MisParams &p, uint32_t roun
     if (first == 0) stamp(p, round, 3);
 
     uint32_t step = 0;
-    bool tail = false;
     for (;;) {
         const uint32_t cur = step & 1u, nxt = cur ^ 1u;
         const bool wrap = (step + 1) % TAGS == 0;
@@ -376,32 +361,7 @@ __device__ __noinline__ void mis_resample_body(const MisParams &p, uint32_t roun
         if (first == 0) p.ctr->step_live[(step + 3) & 63u] = 0;
         bar.sync();
         step++;
-        const uint32_t live_next = ld_u32(&p.ctr->step_live[step & 63u]);
-        if (live_next == 0) break;                                   // nobody claimed for this step: all decided
-        if (ALL_CACHED && live_next <= p.tail_max) { tail = true; break; }
-    }
-
-    // ---- tail: few clauses are still undecided, but every further step would cost everybody a barrier and a memory
-    // round trip.  Each of them checks its variables for TAKEN marks one last time (what the next step would have done
-    // first) and, if none, puts itself on a list; after one more barrier the first CTA finishes the Luby steps on that
-    // list in shared memory (mis_small_body: same fixed-priority process on the conflict graph of the listed clauses,
-    // hence the same set) while everybody else goes straight to K4.  Nobody reads a global claim word after this barrier.
-    if (tail) {
-        const uint32_t cur = step & 1u;
-        uint32_t it = 0;
-        for (uint32_t i = first; i < n_u; i += stride, ++it) {
-            const uint32_t base = it * slotw * bd + threadIdx.x;
-            const uint32_t w = mis_smem[base + META * bd];
-            if ((w >> 8) != UNDECIDED) continue;
-            const uint32_t k = w & 0xFFu;
-            bool taken = false;
-#pragma unroll 4
-            for (uint32_t j = 0; j < k; j++)
-                taken |= ld_claim(claim + 2 * (uint64_t)(mis_smem[base + j * bd] >> 1) + cur) == CLAIM_TAKEN;
-            if (taken) mis_smem[base + META * bd] = k | (DROPPED << 8);
-            else p.ctr->tail_list[gm::add_ret(&p.ctr->tail_n, 1u)] = i;     // (stays UNDECIDED here: K4 below only resets its claims)
-        }
-        bar.sync();
+        if (ld_u32(&p.ctr->step_live[step & 63u]) == 0) break;      // nobody claimed for this step: all decided
     }
 
     if (first == 0) stamp(p, round, 4);
@@ -435,11 +395,7 @@ __device__ __noinline__ void mis_resample_body(const MisParams &p, uint32_t roun
     if ((threadIdx.x & 31u) == 0 && resampled) gm::red_add(&p.ctr->n_resampled_round, resampled);
     if (first == 0) {
         gm::red_add(&p.ctr->n_luby_steps, (unsigned long long)step);
-        if (round < DBG_ROUNDS) p.ctr->dbg[round][7] = ((unsigned long long)step << 8) | (tail ? 0x40u : 0u);
-    }
-    if (tail && first == threadIdx.x) {                        // the first CTA of the group: finish the listed clauses
-        __syncthreads();                                           // (its own K4 above is done with the clause cache)
-        mis_small_body(p, round, prefix, ld_u32(&p.ctr->tail_n), p.ctr->tail_list, n_u);
+        if (round < DBG_ROUNDS) p.ctr->dbg[round][7] = (unsigned long long)step << 8;
     }
 }
 
@@ -449,27 +405,22 @@ __device__ __noinline__ void mis_resample_body(const MisParams &p, uint32_t roun
 // by their ranks within U (ids are unique, so ranks are a strict order), claims are 32-bit (step tag | rank) words in
 // an open-addressing table keyed by variable; each literal's table slot is found once and cached.
 // Runs in one CTA of >= SMALL_U threads (1024 in the cluster kernel, 512 in the persistent solve kernel).
-// list != NULL (tail of a large round, see mis_resample_body): the clauses are entries list[0..n_u) of U, the sizes of S
-// and of the resampled set are ADDED to what the large phase left, and the trace stamps are not touched.
-static __device__ __noinline__ void mis_small_body(const MisParams &p, uint32_t round, const uint32_t *prefix, uint32_t n_u,
-                                                   const unsigned int *list, uint32_t n_total)
+static __device__ __noinline__ void mis_small_body(const MisParams &p, uint32_t round, const uint32_t *prefix, uint32_t n_u)
 {
     const uint32_t km = p.kmax, bd = blockDim.x;
     uint32_t *hvar = mis_smem + (size_t)bd * (2 * km + EXTRA);
     uint32_t *hclaim = hvar + HSLOTS;
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(hclaim + HSLOTS);     // [SMALL_U]
-    __shared__ unsigned int s_cnt, s_sum, s_base;
+    __shared__ unsigned int s_cnt, s_sum;
     const uint32_t t = threadIdx.x;
     const bool mine = t < n_u;
-    if (!list) n_total = n_u;
-    const bool use_urec = p.urec != nullptr && n_total <= p.urec_cap;
-    const uint32_t u_index = mine ? (list ? gm::ld_cg(list + t) : t) : 0u;      // which entry of U this thread owns
+    const bool use_urec = p.urec != nullptr && n_u <= p.urec_cap;
 
     for (uint32_t i = t; i < HSLOTS; i += bd) { hvar[i] = H_EMPTY; hclaim[i] = C_FREE; }
     if (t == 0) { s_cnt = 0; s_sum = 0; }
     uint32_t k = 0;
     if (mine) {
-        const Src s = locate(p, prefix, u_index, use_urec);
+        const Src s = locate(p, prefix, t, use_urec);
         const uint32_t id = src_id(p, s);
         k = s.k;
 #pragma unroll 4
@@ -493,7 +444,7 @@ static __device__ __noinline__ void mis_small_body(const MisParams &p, uint32_t 
         }
     }
     __syncthreads();
-    if (t == 0 && !list) stamp(p, round, 3);
+    if (t == 0) stamp(p, round, 3);
 
     uint32_t state = mine ? UNDECIDED : DROPPED;
     uint32_t step = 0;
@@ -532,27 +483,24 @@ static __device__ __noinline__ void mis_small_body(const MisParams &p, uint32_t 
         __syncthreads();
     }
 
-    if (t == 0 && !list) stamp(p, round, 4);
+    if (t == 0) stamp(p, round, 4);
     // ---- K4: winners redraw their variables (global bit-packed assignment) and report themselves
     const bool in_s = state == IN_SET;
-    uint32_t my_pos = 0;
     if (in_s) {
         for (uint32_t j = 0; j < k; j++) resample_var(p, round, mis_smem[t + j * bd] >> 1);
-        my_pos = atomicAdd(&s_cnt, 1u);
+        p.s_slots[atomicAdd(&s_cnt, 1u)] = slot_of(p, t);
     }
     uint32_t resampled = in_s ? k : 0u;                        // SATInstance.h:363 counts literals->size()
     for (int o = 16; o > 0; o >>= 1) resampled += __shfl_down_sync(0xffffffffu, resampled, o);
     if ((t & 31u) == 0 && resampled) atomicAdd(&s_sum, resampled);
     __syncthreads();
     if (t == 0) {
-        s_base = gm::add_ret(&p.ctr->n_s, s_cnt);             // 0 unless a large phase has already put winners into S
-        if (s_sum) gm::red_add(&p.ctr->n_resampled_round, (unsigned long long)s_sum);
+        p.ctr->n_s = s_cnt;
+        p.ctr->n_resampled_round = s_sum;
         gm::red_add(&p.ctr->n_luby_steps, (unsigned long long)step);
-        if (round < DBG_ROUNDS && !list) p.ctr->dbg[round][7] = (unsigned long long)step << 8;
+        if (round < DBG_ROUNDS) p.ctr->dbg[round][7] = (unsigned long long)step << 8;
+        __threadfence();
     }
-    __syncthreads();
-    if (in_s) p.s_slots[s_base + my_pos] = slot_of(p, u_index);
-    if (t == 0) __threadfence();
 }
 
 // Round bookkeeping by one thread after the last barrier.  n_iterations counts every sweep (SATInstance.h:261).
@@ -581,7 +529,6 @@ __device__ __forceinline__ void finish_round(const MisParams &p, uint32_t round,
     c->n_viol = 0;                                         // clean slate for the next sweep
     c->n_s = 0;
     c->n_resampled_round = 0;
-    c->tail_n = 0;
     c->handled_tag = p.p2p_tag;
     c->incr_next = (p.incr_max_vars != 0 && n_r <= p.incr_max_vars) ? 1u : 0u;
     announce(p, n_u, n_s);

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(cons
         }
         if (n_u <= SMALL_U && (uint64_t)n_u * mp.kmax <= HSLOTS / 2 && mp.small_ok) {
             if (blockIdx.x == 0) {
-                mis_small_body(mp, round, s_prefix, n_u, nullptr, 0u);
+                mis_small_body(mp, round, s_prefix, n_u);
                 if (threadIdx.x == 0) finish_round(mp, round, n_u, 0u);
             }
         } else {
@@ -161,7 +161,6 @@ static void persistent_fill(const SweepParams &p, MisParams &mp, size_t smem)
 {
     mp.cache_items = (uint32_t)((smem / 4 / SWEEP_THREADS) / mis_cache_words(mp.kmax));
     mp.small_ok = mis_small_words(SWEEP_THREADS, mp.kmax) * 4 <= smem ? 1u : 0u;
-    mp.tail_max = mp.small_ok ? mis_tail_max(mp.kmax) : 0u;
     (void)p;
 }
 

@@ -264,7 +264,7 @@ def test_persistent_kernel_and_host_round_loop_agree(capi, oracle):
             so2 = oracle.solve(n, off, flat, v2, 12)
             assert (st2.n_iterations, st2.n_resamples) == (so2.n_iterations, so2.n_resamples)
             assert np.array_equal(s.get_assignment(), v2)
-    assert results[0][0] == results[1][0]              # (Luby step counts may differ by timing and by where the tail steps run)
+    assert results[0][:2] == results[1][:2]
     assert results[0][2] <= 3 < results[1][2]          # one solve kernel (+ counter resets) vs one kernel per phase
 
 
