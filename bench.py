@@ -193,7 +193,7 @@ def run_reference(args):
     shape = workload_shape(args.workload, args.scale)
     r = reference_sample(shape, args.steps, args.warmup)
     if r is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/liballl_ref.so not built"}))
+        emit_line({"impl": "reference", "unavailable": "oracle/_ref/liballl_ref.so not built"})
         return 0
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
@@ -202,7 +202,7 @@ def run_reference(args):
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit_line(line)
     return 0
 
 
@@ -443,7 +443,7 @@ def run_ours(args):
             "sharded": sharded,
             "cfg5_multi_gpu": cfg5_multi,
         }
-        print(json.dumps(line))
+        emit_line(line)
     solver.close()
     if world > 1:
         dist.destroy_process_group()
@@ -629,7 +629,31 @@ def sharded_solves(args, shape, rank, world, local_rank):
     return out
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON result: fd 1 is pointed at stderr for everything else (NCCL prints its
+    version banner to stdout at NCCL_DEBUG=VERSION and WARN; libraries and child processes inherit fd 1), and emit_line
+    writes to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
