@@ -54,6 +54,30 @@ struct BatchParams {
 
 extern __shared__ __align__(16) uint32_t b_smem[];
 
+// ---- clause evaluation against the bit-packed assignment in shared memory (both kernels)
+// sb = 32-bit shared-window address of the assignment words, held in a register that nvcc cannot see through (callers
+// re-make it with an empty asm volatile after the barrier that ends a resample): the lookup is shift, mask, LDS, funnel
+// shift, one LOP3 -- predicated on the clause having seen no true literal yet (a dead lane touches no bank), no branch.
+// With `if`s around bits[v >> 5] nvcc emits BSSY/BRA/BSYNC per lookup and rebuilds the window base (S2UR SR_CgaCtaId, UMOV,
+// ULEA) every time: 17 instead of 8 instructions per literal (profiles/r01_batch_small.md).
+__device__ __forceinline__ uint32_t bs_lds32(uint32_t byte_addr)
+{
+    uint32_t w;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(byte_addr));
+    return w;
+}
+__device__ __forceinline__ uint32_t lane_of(const uint4 &v, int q) { return q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w; }
+// a[q] bit 0: clause q of the group is still unsatisfied; one literal plane vector L
+__device__ __forceinline__ void bs_eval4(const uint4 &L, uint32_t (&a)[4], uint32_t sb)
+{
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint32_t l = lane_of(L, q);
+        const uint32_t w = a[q] ? bs_lds32(sb + ((l >> 6) << 2)) : 0u;
+        a[q] &= ~(__funnelshift_r(w, 0u, l >> 1) ^ l);            // bit (v & 31) of the word, xor the negation flag
+    }
+}
+
 // End of a job: portfolio winner claim, assignment and statistics out.  Called by every thread of the CTA.
 __device__ __forceinline__ void batch_finish(const BatchParams &p, uint32_t job, int status, const uint32_t *bits,
                                              uint64_t n_iter, uint64_t n_res, uint64_t sum_mis)
@@ -114,28 +138,32 @@ static __device__ __forceinline__ void batch_job_large(const BatchParams &p, con
     uint64_t n_iter = 0, n_res = 0, sum_mis = 0;
     int status = 1;                       // ALLL_MAX_ROUNDS until proven otherwise
     const uint64_t max_rounds = p.max_rounds ? p.max_rounds : 1;
+    const uint32_t sbits = (uint32_t)__cvta_generic_to_shared(bits);
 
     for (uint64_t round = 0; round < max_rounds; round++) {
         if (tid == 0) { s_nu = 0; s_ns = 0; s_res = 0; s_stop = p.portfolio && *(volatile int *)p.winner >= 0; }
         __syncthreads();
         if (s_stop) { status = BATCH_PREEMPTED; break; }        // somebody else finished: give up (decided by one thread: uniform)
 
-        // ---- K1+K2: sweep this instance's clauses, 4 per thread and plane
+        // ---- K1+K2: sweep this instance's clauses, 4 per thread and plane, two planes in flight; stops at the first pair of
+        // planes after which none of the four clauses is still unsatisfied
+        uint32_t sb = sbits;
+        asm volatile("" : "+r"(sb));
         for (uint32_t c0 = tid * 4; c0 < m; c0 += BATCH_THREADS * 4) {
-            uint32_t alive = (c0 + 0 < m ? 1u : 0u) | (c0 + 1 < m ? 2u : 0u) | (c0 + 2 < m ? 4u : 0u) | (c0 + 3 < m ? 8u : 0u);
-            for (uint32_t j = 0; j < p.k && alive; j++) {
-                const uint4 L = *reinterpret_cast<const uint4 *>(p.planes + (uint64_t)j * p.m_pad + off + c0);
-                const uint32_t l[4] = {L.x, L.y, L.z, L.w};
+            const uint32_t *src = p.planes + off + c0;
+            uint32_t a[4];
 #pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if ((alive >> q) & 1u) {
-                        const uint32_t v = l[q] >> 1;
-                        if (((bits[v >> 5] >> (v & 31u)) ^ l[q]) & 1u) alive &= ~(1u << q);
-                    }
+            for (int q = 0; q < 4; q++) a[q] = c0 + q < m ? 1u : 0u;
+            for (uint32_t j = 0; j < p.k && (a[0] | a[1] | a[2] | a[3]); j += 2) {
+                const bool two = j + 1 < p.k;
+                const uint4 L0 = ld_stream_v4(src + (uint64_t)j * p.m_pad);
+                const uint4 L1 = two ? ld_stream_v4(src + (uint64_t)(j + 1) * p.m_pad) : make_uint4(0u, 0u, 0u, 0u);
+                bs_eval4(L0, a, sb);
+                if (two) bs_eval4(L1, a, sb);
             }
 #pragma unroll
             for (int q = 0; q < 4; q++)
-                if ((alive >> q) & 1u) ulist[atomicAdd(&s_nu, 1u)] = c0 + q;
+                if (a[q]) ulist[atomicAdd(&s_nu, 1u)] = c0 + q;
         }
         __syncthreads();
         const uint32_t n_u = s_nu;
@@ -240,13 +268,6 @@ static bool batch_small_eligible(uint32_t n_vars, uint32_t n_words, uint32_t k)
     return k >= 3 && k <= 8 && batch_small_smem_bytes(n_vars, n_words, k) <= 100u * 1024u;      // >= 2 CTAs per SM
 }
 
-__device__ __forceinline__ uint32_t bs_lds32(uint32_t byte_addr)
-{
-    uint32_t w;
-    asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(byte_addr));
-    return w;
-}
-__device__ __forceinline__ uint32_t lane_of(const uint4 &v, int q) { return q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w; }
 
 template <uint32_t K, int MINB, bool PIPE>
 __global__ void __launch_bounds__(BS_THREADS, MINB) batch_solve_small_kernel(const BatchParams p)
@@ -293,21 +314,12 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) batch_solve_small_kernel(con
                                           // lookup; re-made after the barrier so that no lookup is hoisted above the resample of the last round
 
         // ---- K1+K2: four clauses per thread and group; all K plane loads of a step (one or two groups) are in flight together
-        // Lookups are predicated on the clause still being unsatisfied (a dead lane touches no bank) and branch-free:
-        // shift, mask, ld.shared through a 32-bit window address, funnel shift, one LOP3, predicate -- 8 instructions per literal (17 with `if`s and bits[] indexing).
         auto eval_group = [&](const uint4 (&L)[K], uint32_t c0) {
             uint32_t a[4];                                     // bit 0: clause q has seen no true literal yet
 #pragma unroll
             for (int q = 0; q < 4; q++) a[q] = c0 + q < m ? 1u : 0u;
 #pragma unroll
-            for (uint32_t j = 0; j < K; j++) {
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t l = lane_of(L[j], q);
-                    const uint32_t w = a[q] ? bs_lds32(sb + ((l >> 6) << 2)) : 0u;
-                    a[q] &= ~(__funnelshift_r(w, 0u, l >> 1) ^ l);            // bit (v & 31) of the word, xor the negation flag
-                }
-            }
+            for (uint32_t j = 0; j < K; j++) bs_eval4(L[j], a, sb);
             if (a[0] | a[1] | a[2] | a[3]) {
 #pragma unroll
                 for (int q = 0; q < 4; q++)
