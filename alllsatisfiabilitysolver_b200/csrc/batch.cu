@@ -269,8 +269,11 @@ static bool batch_small_eligible(uint32_t n_vars, uint32_t n_words, uint32_t k)
 }
 
 
-template <uint32_t K, int MINB, bool PIPE>
-__global__ void __launch_bounds__(BS_THREADS, MINB) batch_solve_small_kernel(const BatchParams p)
+// 5 CTAs per SM (47 registers at K = 5): measured best on B200 -- 4 per SM with 64 registers 0.94 ms, 6 per SM with 40
+// registers 1.04 ms (the literals of 6 x 148 resident jobs no longer stay in L2), two groups of four clauses in flight per
+// thread 0.92 ms at 4 per SM; this shape 0.84 ms (profiles/r01_batch_small.md).
+template <uint32_t K>
+__global__ void __launch_bounds__(BS_THREADS, 5) batch_solve_small_kernel(const BatchParams p)
 {
     const uint32_t job = blockIdx.x;
     const uint32_t inst = p.portfolio ? 0u : job;
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) batch_solve_small_kernel(con
         asm volatile("" : "+r"(sb));      // opaque register copy of the window address: nvcc otherwise rebuilds it (S2R, MOV, LEA) per
                                           // lookup; re-made after the barrier so that no lookup is hoisted above the resample of the last round
 
-        // ---- K1+K2: four clauses per thread and group; all K plane loads of a step (one or two groups) are in flight together
+        // ---- K1+K2: four clauses per thread and step; all K plane loads of the step are in flight together
         auto eval_group = [&](const uint4 (&L)[K], uint32_t c0) {
             uint32_t a[4];                                     // bit 0: clause q has seen no true literal yet
 #pragma unroll
@@ -333,26 +336,11 @@ __global__ void __launch_bounds__(BS_THREADS, MINB) batch_solve_small_kernel(con
                     }
             }
         };
-        if (PIPE) {
-            for (uint32_t c0 = tid * 4; c0 < m; c0 += BS_THREADS * 8) {
-                const uint32_t c1 = c0 + BS_THREADS * 4;
-                uint4 A[K], B[K];
+        for (uint32_t c0 = tid * 4; c0 < m; c0 += BS_THREADS * 4) {
+            uint4 L[K];
 #pragma unroll
-                for (uint32_t j = 0; j < K; j++) A[j] = ld_stream_v4(lit0 + (uint64_t)j * p.m_pad + c0);
-                if (c1 < m) {
-#pragma unroll
-                    for (uint32_t j = 0; j < K; j++) B[j] = ld_stream_v4(lit0 + (uint64_t)j * p.m_pad + c1);
-                }
-                eval_group(A, c0);
-                if (c1 < m) eval_group(B, c1);
-            }
-        } else {
-            for (uint32_t c0 = tid * 4; c0 < m; c0 += BS_THREADS * 4) {
-                uint4 L[K];
-#pragma unroll
-                for (uint32_t j = 0; j < K; j++) L[j] = ld_stream_v4(lit0 + (uint64_t)j * p.m_pad + c0);
-                eval_group(L, c0);
-            }
+            for (uint32_t j = 0; j < K; j++) L[j] = ld_stream_v4(lit0 + (uint64_t)j * p.m_pad + c0);
+            eval_group(L, c0);
         }
         __syncthreads();
         const uint32_t n_u = s_nu;
@@ -468,24 +456,13 @@ size_t batch_smem_bytes(uint32_t n_vars, uint32_t n_words, uint32_t m_max)
     return (size_t)n_vars * 8 + (size_t)((n_words + 3u) & ~3u) * 4 + (size_t)m_max * 4 + (((size_t)m_max + 15) & ~(size_t)15);
 }
 
-template <uint32_t K, int MINB, bool PIPE>
-static cudaError_t launch_small_v(const BatchParams &p, size_t smem, uint32_t n_jobs, cudaStream_t s)
-{
-    cudaError_t e = cudaFuncSetAttribute(batch_solve_small_kernel<K, MINB, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    batch_solve_small_kernel<K, MINB, PIPE><<<n_jobs, BS_THREADS, smem, s>>>(p);
-    return cudaGetLastError();
-}
 template <uint32_t K>
 static cudaError_t launch_small(const BatchParams &p, size_t smem, uint32_t n_jobs, cudaStream_t s)
 {
-    static const int variant = getenv("ALLL_BATCH_VARIANT") ? atoi(getenv("ALLL_BATCH_VARIANT")) : 0;
-    switch (variant) {                                          // measured on B200, cfg5 (profiles/r01_batch_small.md)
-    case 1: return launch_small_v<K, 6, false>(p, smem, n_jobs, s);    // 40 registers, 6 CTAs per SM: 1.04 ms
-    case 2: return launch_small_v<K, 4, true>(p, smem, n_jobs, s);     // two groups in flight, 4 CTAs per SM: 0.92 ms
-    case 3: return launch_small_v<K, 4, false>(p, smem, n_jobs, s);    // 64 registers, 4 CTAs per SM: 0.94 ms
-    default: return launch_small_v<K, 5, false>(p, smem, n_jobs, s);   // 47 registers, 5 CTAs per SM: 0.84 ms
-    }
+    cudaError_t e = cudaFuncSetAttribute(batch_solve_small_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    batch_solve_small_kernel<K><<<n_jobs, BS_THREADS, smem, s>>>(p);
+    return cudaGetLastError();
 }
 
 // retry: n_jobs + 1 words of device scratch (NULL: large kernel only).  *n_launches: kernels enqueued.
