@@ -74,6 +74,37 @@ def test_batch_mixed_small_and_retried_jobs(capi, oracle):
                 assert np.array_equal(assign[i], v)
 
 
+def test_batch_edge_cases_small_kernel(capi, oracle):
+    """Ragged instance sizes (0, 1, not a multiple of 4 clauses), repeated variables and tautologies inside a clause,
+    variables nobody uses, an odd variable count: every job equals the oracle (k = 3 and k = 8: the 256-thread kernel)."""
+    rng = np.random.default_rng(99)
+    for k, n in ((3, 41), (8, 77)):
+        sizes = [0, 1, 3, 5, 4, 7, 64, 129, 2, 0, 33]
+        insts = []
+        for m in sizes:
+            v = rng.integers(0, n - 5, size=(m, k), dtype=np.int64)          # the last 5 variables never occur
+            if m:
+                v[0, 1] = v[0, 0]                                            # a repeated variable ...
+            lits = (v * 2 + rng.integers(0, 2, size=(m, k), dtype=np.int64)).astype(np.uint32)
+            if m > 2:
+                lits[2, 1] = lits[2, 0] ^ np.uint32(1)                       # ... and a tautology (x or not-x)
+            insts.append(lits)
+        off = np.zeros(len(insts) + 1, np.uint64)
+        off[1:] = np.cumsum(sizes)
+        seeds = np.arange(5, 5 + len(insts), dtype=np.uint64)
+        with capi.Solver() as s:
+            s.batch_upload(n, k, off, np.concatenate(insts, axis=0))
+            stats, assign, _, _ = s.batch_solve(seeds, max_rounds=500)
+        for i, lits in enumerate(insts):
+            coff = np.arange(lits.shape[0] + 1, dtype=np.uint64) * np.uint64(k)
+            vv = oracle.randomize(n, int(seeds[i]))
+            so = oracle.solve(n, coff, lits.reshape(-1), vv, int(seeds[i]), 500)
+            assert int(stats["status"][i]) == so.status, (k, i)
+            assert (int(stats["n_iterations"][i]), int(stats["n_resamples"][i]), int(stats["sum_mis_size"][i])) == \
+                   (so.n_iterations, so.n_resamples, so.sum_mis_size), (k, i)
+            assert np.array_equal(assign[i], vv), (k, i)
+
+
 def test_batch_agrees_with_single_instance_path(capi):
     """The one-CTA kernel and the large-instance kernels implement one specification."""
     insts, off, lits = make_batch(6, 4000, 5, 3, 900)
