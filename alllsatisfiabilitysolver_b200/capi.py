@@ -22,6 +22,7 @@ FLAG_INCREMENTAL = 4
 FLAG_FORCE_CSR = 8
 FLAG_P2P_PERSISTENT = 32    # alll_solve_p2p: one persistent kernel per rank (every rank needs its own GPU)
 FLAG_HOST_ROUND_LOOP = 16   # alll_solve: one kernel per phase driven by the host instead of the persistent solve kernel
+FLAG_FORCE_SHARDING = 64    # alll_multi_*: shard small instances too (tests)
 
 #: every symbol include/alll_b200.h declares (tests check the library exports exactly these)
 SYMBOLS = [
@@ -35,6 +36,9 @@ SYMBOLS = [
     "alll_p2p_create", "alll_p2p_connect", "alll_solve_p2p",
     "alll_upload_generator", "alll_upload_builtin_generator", "alll_builtin_generator_clause",
     "alll_flag_create", "alll_flag_open", "alll_flag_reset", "alll_flag_read", "alll_batch_set_job_base",
+    "alll_multi_create", "alll_multi_destroy", "alll_multi_last_error", "alll_multi_upload_fixedk", "alll_multi_upload_csr",
+    "alll_multi_set_assignment", "alll_multi_get_assignment", "alll_multi_randomize", "alll_multi_verify", "alll_multi_solve",
+    "alll_multi_info", "alll_multi_device_handle", "alll_multi_batch_upload", "alll_multi_batch_solve",
 ]
 
 GEN_UNIFORM, GEN_BOUNDED = 0, 1
@@ -130,6 +134,21 @@ def load() -> C.CDLL:
     L.alll_solve_p2p.argtypes = [vp, u64, u64, u64, u32, C.POINTER(StatsC)]
     L.alll_batch_upload.argtypes = [vp, u32, u64, u32, vp, vp]
     L.alll_batch_solve.argtypes = [vp, u32, vp, u64, C.c_int, vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+    L.alll_multi_create.argtypes = [vp, u32, C.POINTER(Config), C.POINTER(vp)]
+    L.alll_multi_destroy.argtypes = [vp]
+    L.alll_multi_last_error.restype = C.c_char_p
+    L.alll_multi_last_error.argtypes = [vp]
+    L.alll_multi_upload_fixedk.argtypes = [vp, u64, u64, u32, vp]
+    L.alll_multi_upload_csr.argtypes = [vp, u64, u64, vp, vp]
+    L.alll_multi_set_assignment.argtypes = [vp, vp]
+    L.alll_multi_get_assignment.argtypes = [vp, vp]
+    L.alll_multi_randomize.argtypes = [vp, u64]
+    L.alll_multi_verify.argtypes = [vp, C.POINTER(C.c_int)]
+    L.alll_multi_solve.argtypes = [vp, u64, u64, C.POINTER(StatsC)]
+    L.alll_multi_info.argtypes = [vp, C.POINTER(u64)]
+    L.alll_multi_device_handle.argtypes = [vp, u32, C.POINTER(vp)]
+    L.alll_multi_batch_upload.argtypes = [vp, u32, u64, u32, vp, vp]
+    L.alll_multi_batch_solve.argtypes = [vp, u32, vp, u64, C.c_int, vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     for name in SYMBOLS:
         getattr(L, name)            # raises AttributeError if the library misses a declared entry point
     _lib = L
@@ -148,6 +167,16 @@ class Solver:
             raise AlllError(rc, self.lib.alll_last_error(None).decode())
         self.n_vars = 0
         self.m = 0
+        self._owned = True
+
+    @classmethod
+    def borrowed(cls, handle: int, n_vars: int, m: int) -> "Solver":
+        """View of an ``alll_handle`` owned by someone else (a device slot of a ``MultiSolver``); ``close`` is a no-op."""
+        self = cls.__new__(cls)
+        self.lib = load()
+        self.h = C.c_void_p(handle)
+        self.n_vars, self.m, self._owned = n_vars, m, False
+        return self
 
     # -- plumbing ---------------------------------------------------------------------
     def _check(self, rc: int, allow=(OK,)):
@@ -156,9 +185,9 @@ class Solver:
         return rc
 
     def close(self):
-        if self.h:
+        if self.h and self._owned:
             self.lib.alll_destroy(self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def __enter__(self):
         return self
@@ -350,6 +379,115 @@ class Solver:
         info = (C.c_uint64 * 6)()
         self._check(self.lib.alll_layout_info(self.h, info))
         return dict(m=info[0], k=info[1], n_buckets=info[2], m_padded=info[3], literal_bytes=info[4], sweep_smem_bytes=info[5])
+
+
+class MultiSolver:
+    """Several GPUs behind one call from ONE process (``alll_multi_*``): clause-range sharded solve of one large
+    instance (every device uploads only its own range from the host buffer; fused NVLink exchange, peer access instead
+    of CUDA IPC), or batched small instances / a seed portfolio spread over the devices.  The same device may be listed
+    several times (simulated ranks on one GPU)."""
+
+    def __init__(self, devices, sweep_smem_bytes: int = 0, flags: int = 0):
+        self.lib = load()
+        self.h = C.c_void_p()
+        devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        cfg = Config(-1, sweep_smem_bytes, flags, 0)
+        rc = self.lib.alll_multi_create(devs, len(devices), C.byref(cfg), C.byref(self.h))
+        if rc != OK:
+            raise AlllError(rc, self.lib.alll_multi_last_error(None).decode())
+        self.n_devices = len(devices)
+        self.n_vars = 0
+        self.m = 0
+
+    def _check(self, rc: int, allow=(OK,)):
+        if rc not in allow:
+            raise AlllError(rc, self.lib.alll_multi_last_error(self.h).decode())
+        return rc
+
+    def close(self):
+        if self.h:
+            self.lib.alll_multi_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload_fixedk(self, n_vars: int, lits: np.ndarray):
+        lits = np.ascontiguousarray(lits, np.uint32)
+        m, k = lits.shape
+        self._check(self.lib.alll_multi_upload_fixedk(self.h, n_vars, m, k, lits.ctypes.data))
+        self.n_vars, self.m = n_vars, m
+
+    def upload_csr(self, n_vars: int, off: np.ndarray, lit: np.ndarray):
+        off = np.ascontiguousarray(off, np.uint64)
+        lit = np.ascontiguousarray(lit, np.uint32)
+        self._check(self.lib.alll_multi_upload_csr(self.h, n_vars, len(off) - 1, off.ctypes.data, lit.ctypes.data if len(lit) else None))
+        self.n_vars, self.m = n_vars, len(off) - 1
+
+    def set_assignment(self, bools: np.ndarray):
+        bools = np.ascontiguousarray(bools, np.uint8)
+        assert bools.shape == (self.n_vars,)
+        self._check(self.lib.alll_multi_set_assignment(self.h, bools.ctypes.data))
+
+    def get_assignment(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.n_vars, np.uint8)
+        self._check(self.lib.alll_multi_get_assignment(self.h, out.ctypes.data))
+        return out
+
+    def randomize(self, seed: int):
+        self._check(self.lib.alll_multi_randomize(self.h, seed))
+
+    def verify(self) -> bool:
+        v = C.c_int(0)
+        self._check(self.lib.alll_multi_verify(self.h, C.byref(v)))
+        return bool(v.value)
+
+    def solve(self, seed: int, max_rounds: int = 1 << 19) -> Stats:
+        st = StatsC()
+        self._check(self.lib.alll_multi_solve(self.h, seed, max_rounds, C.byref(st)), allow=(OK, MAX_ROUNDS))
+        return Stats(st.n_iterations, st.n_resamples, st.avg_mis_size, st.sum_mis_size, st.n_clause_evals,
+                     st.n_luby_steps, st.n_kernel_launches, st.solve_ms, st.sweep_ms, st.status, st.between_sweeps_ms, st.n_incremental_rounds)
+
+    def device_solver(self, i: int) -> Solver:
+        """Device slot ``i`` as a (borrowed) ``Solver``: its clause range only."""
+        h = C.c_void_p()
+        self._check(self.lib.alll_multi_device_handle(self.h, i, C.byref(h)))
+        return Solver.borrowed(h.value, self.n_vars, self.m)
+
+    def info(self) -> dict:
+        info = (C.c_uint64 * 4)()
+        self._check(self.lib.alll_multi_info(self.h, info))
+        return dict(devices_in_use=info[0], sharded=bool(info[1]), widest_range=info[2], cap_records=info[3])
+
+    def batch_upload(self, n_vars: int, k: int, clause_off: np.ndarray, lits: np.ndarray):
+        clause_off = np.ascontiguousarray(clause_off, np.uint64)
+        lits = np.ascontiguousarray(lits, np.uint32)
+        self._check(self.lib.alll_multi_batch_upload(self.h, len(clause_off) - 1, n_vars, k, clause_off.ctypes.data,
+                                                     lits.ctypes.data if lits.size else None))
+        self._batch = (len(clause_off) - 1, n_vars)
+
+    def batch_solve(self, seeds, max_rounds: int = 1 << 20, portfolio: bool = False, want_assignments: bool = True):
+        """Returns (stats structured array, assignments [n_jobs, n_vars] or None, winner, device_ms max over devices)."""
+        seeds = np.ascontiguousarray(seeds, np.uint64)
+        n_jobs, n_vars = len(seeds), self._batch[1]
+        stats = np.zeros(n_jobs, dtype=np.dtype([("n_iterations", "<u8"), ("n_resamples", "<u8"), ("sum_mis_size", "<u8"),
+                                                 ("status", "<i4"), ("reserved", "<i4")]))
+        assign = np.zeros((n_jobs, n_vars), np.uint8) if want_assignments else None
+        winner, ms = C.c_int32(-1), C.c_double(0.0)
+        self._check(self.lib.alll_multi_batch_solve(self.h, n_jobs, seeds.ctypes.data, max_rounds, int(portfolio),
+                                                    assign.ctypes.data if want_assignments else None, stats.ctypes.data,
+                                                    C.byref(winner), C.byref(ms)))
+        return stats, assign, int(winner.value), float(ms.value)
 
 
 def builtin_generator_clauses(kind: int, n_vars: int, m: int, k: int, seed: int, d: int = 0, indices=None) -> np.ndarray:

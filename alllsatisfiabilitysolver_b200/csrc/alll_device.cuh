@@ -154,7 +154,7 @@ struct Counters {
     // behind it return immediately, so the round loop never has to wait for the host between rounds
     unsigned int done;
     unsigned int cta_done;      // sweep CTAs that have finished (sharded P2P mode: the last one publishes the round)
-    unsigned int p2p_error;     // 1: capacity overflow (P2P exchange region / enumerated-clause record buffer), 2: a peer did not arrive in time
+    unsigned int p2p_error;     // 1: capacity overflow (P2P exchange region / enumerated-clause record buffer), 2: a peer did not arrive in time, 3: a peer aborted the solve
     unsigned int handled_tag;   // sharded P2P mode: tag of the last round an MIS kernel has completed
     // incremental re-evaluation: decided by the MIS kernel at the end of a round for the NEXT round
     unsigned int incr_next;     // 1: the next violated set comes from incr_eval_kernel, the sweep kernel returns at entry
@@ -201,7 +201,8 @@ constexpr int BATCH_PREEMPTED = 8;      // == ALLL_PREEMPTED: portfolio job stop
 struct P2PHeader {
     unsigned int flag[2][MAX_SHARDS];    // written by peers: tag of the round whose records are complete
     unsigned int count[2][MAX_SHARDS];   // written by peers: number of records of that round
-    unsigned int abort;                  // set when a peer overflowed its capacity or a wait timed out
+    unsigned int abort;                  // == (epoch & 0xFFF) + 1 of the solve in which a peer overflowed its capacity or a wait timed out
+                                         // (tagged by solve, so that a failed solve does not poison the next one on the same link)
 };
 constexpr uint32_t P2P_HEADER_BYTES = 4096;
 static_assert(sizeof(P2PHeader) <= P2P_HEADER_BYTES, "header must fit its page");
@@ -209,6 +210,7 @@ static_assert(sizeof(P2PHeader) <= P2P_HEADER_BYTES, "header must fit its page")
 struct P2PLink {                         // device-resident, one per handle
     uint32_t world, rank, k;
     uint64_t cap;                        // records per (parity, source rank)
+    long long timeout_cycles;            // bounded wait for a peer's round (clock64 ticks; ALLL_P2P_TIMEOUT_MS, default 20 s)
     P2PHeader *hdr[MAX_SHARDS];          // every GPU's header (own one included), peer-mapped
     uint32_t *rec[MAX_SHARDS];           // every GPU's record area
 };
@@ -244,6 +246,7 @@ struct SweepParams {
     // sharded P2P mode (p2p == NULL otherwise): records go to every peer instead of the local violated list
     const P2PLink *p2p;
     uint32_t p2p_parity, p2p_tag;
+    uint32_t p2p_epoch;         // epoch & 0xFFF of this solve (the abort word of the exchange headers is tagged with it)
     const uint32_t *orig_id;
     uint32_t id_base;
     uint32_t round;             // solve round this sweep belongs to (trace stamps only)

@@ -85,4 +85,14 @@ cudaError_t launch_unpack_bits(const uint32_t *bits, uint64_t n_vars, uint8_t *b
 cudaError_t launch_randomize(uint32_t *bits, uint64_t n_vars, uint32_t n_words_alloc, uint64_t seed, cudaStream_t s);
 cudaError_t launch_fill_u64(unsigned long long *p, uint64_t n, unsigned long long value, cudaStream_t s);
 
+// capi.cu: what the single-process multi-GPU layer (multi.cu) needs beyond the C ABI
+void *internal_p2p_region(alll_handle h);
+int internal_p2p_connect_ptrs(alll_handle h, void *const *regions);         // regions[rank]: exchange-region base of every rank
+bool internal_p2p_persistent_possible(alll_handle h);
+int internal_solve_p2p_begin(alll_handle h, uint64_t seed, uint64_t max_rounds, uint32_t epoch, uint64_t *launches0);   // enqueue only
+int internal_solve_p2p_end(alll_handle h, uint64_t m_global, uint64_t launches0, alll_stats *stats);                    // wait + statistics
+int *internal_flag_ptr(alll_handle h);
+int internal_flag_attach(alll_handle h, int *word);
+int internal_device(alll_handle h);
+
 } // namespace alll

@@ -105,6 +105,7 @@ struct alll_solver {
     // multi-GPU portfolio: one winner word for all ranks, owned by one GPU and peer-mapped (CUDA IPC) by the others
     int *d_flag = nullptr;               // the word as this process addresses it
     bool flag_owner = false;
+    bool flag_borrowed = false;          // the word belongs to another handle of this process (multi.cu): never freed / closed here
     uint32_t b_job_base = 0;
     uint8_t *d_tmp_bkt = nullptr;
     uint32_t *d_tmp_cnt = nullptr, *d_tmp_err = nullptr, *d_stage = nullptr;
@@ -163,9 +164,10 @@ void release_buffers(alll_handle h)
     for (uint32_t q = 0; q < MAX_SHARDS; q++)
         if (h->p2p_peer[q]) { cudaIpcCloseMemHandle(h->p2p_peer[q]); h->p2p_peer[q] = nullptr; }
     dfree(h->d_p2p_region); dfree(h->d_p2p_link);
+    h->p2p_region_bytes = 0;
     dfree(h->d_occ_off); dfree(h->d_occ); dfree(h->d_rows); dfree(h->d_visited); dfree(h->d_incr_tmp);
     dfree(h->d_gen_rec);
-    if (h->d_flag) { if (h->flag_owner) cudaFree(h->d_flag); else cudaIpcCloseMemHandle(h->d_flag); h->d_flag = nullptr; }
+    if (h->d_flag) { if (h->flag_owner) cudaFree(h->d_flag); else if (!h->flag_borrowed) cudaIpcCloseMemHandle(h->d_flag); h->d_flag = nullptr; h->flag_borrowed = false; }
     free_instance(h);
     h->incr_ready = false;
     h->p2p_ready = false;
@@ -432,7 +434,7 @@ SweepParams sweep_params(alll_handle h, uint32_t p2p_parity, uint32_t p2p_tag, u
     sp.round = round;
     sp.orig_id = h->use_orig_id ? h->d_orig_id : nullptr; sp.id_base = h->id_base;
     if (p2p_tag) {
-        sp.p2p = h->d_p2p_link; sp.p2p_parity = p2p_parity; sp.p2p_tag = p2p_tag;
+        sp.p2p = h->d_p2p_link; sp.p2p_parity = p2p_parity; sp.p2p_tag = p2p_tag; sp.p2p_epoch = p2p_tag >> 20;
     } else if (records && h->urec_cap && !h->incr_ready) {      // (incremental rounds produce no records, so the independent set reads rows[] instead)
         sp.urec = h->d_urec; sp.urec_cap = h->urec_cap;
     }
@@ -508,6 +510,94 @@ int copy_ids_out(alll_handle h, const uint32_t *d_slots, uint64_t n, uint32_t *o
     CK(cudaMemcpyAsync(out, h->d_ids_out, n_copy * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return ALLL_OK;
+}
+
+// Builds the device-resident link table of the sharded P2P mode from every rank's exchange-region base address (as THIS
+// process addresses it: CUDA IPC mappings for peers in other processes, plain device pointers for peers in this one).
+int p2p_link_up(alll_handle h, void *const *bases)
+{
+    P2PLink link{};
+    link.world = h->p2p_world; link.rank = h->p2p_rank; link.k = h->k; link.cap = h->p2p_cap;
+    {   // bounded wait for a peer's round: long enough for a peer that starts late (module load, a busy host), short
+        // enough to turn a dead peer into an error instead of a hang
+        double ms = 20000.0;
+        if (const char *e = getenv("ALLL_P2P_TIMEOUT_MS")) { const double v = atof(e); if (v > 0.0) ms = v; }
+        int khz = 0;
+        if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device) != cudaSuccess || khz <= 0) khz = 2000000;
+        link.timeout_cycles = (long long)(ms * (double)khz);
+    }
+    for (uint32_t q = 0; q < h->p2p_world; q++) {
+        uint8_t *base = static_cast<uint8_t *>(bases[q]);
+        if (!base) return fail(h, ALLL_BAD_ARG, "missing exchange region of a peer");
+        link.hdr[q] = reinterpret_cast<P2PHeader *>(base);
+        link.rec[q] = reinterpret_cast<uint32_t *>(base + P2P_HEADER_BYTES);
+    }
+    POOL(h->d_p2p_link, sizeof(P2PLink));
+    CK(cudaMemcpy(h->d_p2p_link, &link, sizeof(P2PLink), cudaMemcpyHostToDevice));
+    const uint64_t total_cap = (uint64_t)h->p2p_world * h->p2p_cap;
+    POOL(h->d_sh_s, total_cap * 4);
+    POOL(h->d_sh_state, total_cap);
+    h->p2p_ready = true;
+    return ALLL_OK;
+}
+
+// ---- sharded P2P solve as one persistent kernel per rank, split into enqueue / collect so that ONE host thread can start
+// the kernels of all ranks of a single-process multi-GPU solve (multi.cu) before it waits for any of them ----
+bool p2p_persistent_possible(alll_handle h)
+{
+    return (h->flags & ALLL_FLAG_P2P_PERSISTENT) && h->persistent_ok && h->k && h->n_tiles && h->p2p_ready;
+}
+
+int p2p_persistent_begin(alll_handle h, uint64_t seed, uint64_t max_rounds, uint32_t epoch)
+{
+    CK(cudaSetDevice(h->device));
+    if (max_rounds == 0) max_rounds = 1;
+    max_rounds = std::min<uint64_t>(max_rounds, (1u << 20) - 2);       // the round lives in 20 bits of the tag
+    CK(launch_reset_counters(h->d_ctr, 1, h->stream)); h->launches++;
+    CK(cudaEventRecord(h->ev[2 * MAX_TIMED_ROUNDS], h->stream));
+    SweepParams sp = sweep_params(h, 0u, 1u, 0u, false);                    // (tag != 0 selects the P2P form; the kernel derives parity / tag per round)
+    sp.p2p_epoch = epoch & 0xFFFu;
+    ClauseView pcv{};
+    pcv.k = h->k;
+    IncrParams ip{};
+    if (h->incr_ready)
+        ip = IncrParams{h->d_sh_s, h->d_rows, h->incr_stride, h->k, h->d_occ_off, h->d_occ, h->d_visited, h->d_bits, h->d_viol, h->d_ctr};
+    CK(launch_solve_persistent(sp, h->resident_all, h->sweep_grid, pcv, h->k, h->d_sh_state, h->d_sh_s, mis_scratch(h, false),
+                               h->n_vars, seed, (uint32_t)max_rounds, epoch, h->incr_ready ? &ip : nullptr,
+                               (uint32_t)h->visited_words, h->incr_ready ? h->incr_max_vars : 0u, h->stream));
+    h->launches++;
+    CK(cudaEventRecord(h->ev[2 * MAX_TIMED_ROUNDS + 1], h->stream));
+    return ALLL_OK;
+}
+
+int p2p_persistent_end(alll_handle h, uint64_t m_global, uint64_t launches0, alll_stats *stats)
+{
+    CK(cudaSetDevice(h->device));
+    if (int rc = fetch_counters(h)) return rc;
+    float pms = 0.f;
+    CK(cudaEventElapsedTime(&pms, h->ev[2 * MAX_TIMED_ROUNDS], h->ev[2 * MAX_TIMED_ROUNDS + 1]));
+    const Counters c = *h->h_ctr;
+    CK(launch_reset_counters(h->d_ctr, 0, h->stream)); h->launches++;
+    CK(cudaStreamSynchronize(h->stream));
+    if (getenv("ALLL_TRACE")) print_phases(c, c.n_iterations);
+    if (c.p2p_error || c.done == 2)
+        return fail(h, c.p2p_error == 1 ? ALLL_CAPACITY : ALLL_CUDA_ERROR,
+                    c.p2p_error == 1 ? "P2P exchange region too small for a round's violated records"
+                                     : c.p2p_error == 3 ? "P2P exchange: a peer aborted the solve"
+                                                        : "P2P exchange: a peer did not publish its round in time");
+    stats->n_iterations = c.n_iterations;
+    stats->n_resamples = c.n_resamples;
+    stats->sum_mis_size = c.sum_mis;
+    stats->avg_mis_size = c.n_iterations ? c.sum_mis / c.n_iterations : 0;
+    stats->n_clause_evals = m_global * (c.n_iterations - c.n_incr_rounds) + c.n_evals_incr;   // (n_evals_incr: this rank's share)
+    stats->n_incremental_rounds = c.n_incr_rounds;
+    stats->n_luby_steps = c.n_luby_steps;
+    stats->n_kernel_launches = h->launches - launches0;
+    stats->solve_ms = pms;
+    stats->sweep_ms = (double)c.t_sweep_ns * 1e-6;
+    stats->between_sweeps_ms = (double)c.t_mis_ns * 1e-6;
+    stats->status = c.done == 1 ? ALLL_OK : ALLL_MAX_ROUNDS;
+    return stats->status;
 }
 
 #define NEED_INSTANCE()                                                                   \
@@ -1092,11 +1182,15 @@ int alll_p2p_create(alll_handle h, uint32_t world, uint32_t rank, uint64_t cap_r
     for (uint32_t q = 0; q < MAX_SHARDS; q++)
         if (h->p2p_peer[q]) { cudaIpcCloseMemHandle(h->p2p_peer[q]); h->p2p_peer[q] = nullptr; }
     const size_t bytes = P2P_HEADER_BYTES + (size_t)2 * world * cap_records * (h->k + 1) * 4;
-    // IPC-exported memory must be its own allocation and must not move: not pooled
-    if (h->d_p2p_region) { cudaFree(h->d_p2p_region); h->d_p2p_region = nullptr; }
-    CK(cudaMalloc(&h->d_p2p_region, bytes));
-    CK(cudaMemset(h->d_p2p_region, 0, bytes));
-    h->p2p_region_bytes = bytes;
+    // IPC-exported memory must be its own allocation (not pooled with other buffers); it is kept across uploads of the
+    // same shape and only grows (a 1.28 GB / 8-GPU exchange region is 0.7 GB: cudaMalloc + a full clear per upload would
+    // cost more than the upload).  Only the header carries state between solves.
+    if (h->d_p2p_region && h->p2p_region_bytes < bytes) { cudaFree(h->d_p2p_region); h->d_p2p_region = nullptr; h->p2p_region_bytes = 0; }
+    if (!h->d_p2p_region) {
+        CK(cudaMalloc(&h->d_p2p_region, bytes));
+        h->p2p_region_bytes = bytes;
+    }
+    CK(cudaMemset(h->d_p2p_region, 0, P2P_HEADER_BYTES));
     h->p2p_world = world; h->p2p_rank = rank; h->p2p_cap = cap_records;
     cudaIpcMemHandle_t ipc;
     CK(cudaIpcGetMemHandle(&ipc, h->d_p2p_region));
@@ -1108,29 +1202,19 @@ int alll_p2p_connect(alll_handle h, const uint8_t *handles)
 {
     NEED_INSTANCE();
     if (!h->d_p2p_region || !handles) return fail(h, ALLL_BAD_ARG, "call alll_p2p_create first");
-    P2PLink link{};
-    link.world = h->p2p_world; link.rank = h->p2p_rank; link.k = h->k; link.cap = h->p2p_cap;
+    void *bases[MAX_SHARDS] = {};
     for (uint32_t q = 0; q < h->p2p_world; q++) {
-        uint8_t *base = nullptr;
-        if (q == h->p2p_rank) base = h->d_p2p_region;
+        if (q == h->p2p_rank) bases[q] = h->d_p2p_region;
         else {
             cudaIpcMemHandle_t ipc;
             std::memcpy(&ipc, handles + (size_t)q * 64, 64);
             void *ptr = nullptr;
             CK(cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess));
             h->p2p_peer[q] = ptr;
-            base = static_cast<uint8_t *>(ptr);
+            bases[q] = ptr;
         }
-        link.hdr[q] = reinterpret_cast<P2PHeader *>(base);
-        link.rec[q] = reinterpret_cast<uint32_t *>(base + P2P_HEADER_BYTES);
     }
-    POOL(h->d_p2p_link, sizeof(P2PLink));
-    CK(cudaMemcpy(h->d_p2p_link, &link, sizeof(P2PLink), cudaMemcpyHostToDevice));
-    const uint64_t total_cap = (uint64_t)h->p2p_world * h->p2p_cap;
-    POOL(h->d_sh_s, total_cap * 4);
-    POOL(h->d_sh_state, total_cap);
-    h->p2p_ready = true;
-    return ALLL_OK;
+    return p2p_link_up(h, bases);
 }
 
 int alll_solve_p2p(alll_handle h, uint64_t seed, uint64_t max_rounds, uint64_t m_global, uint32_t epoch, alll_stats *stats)
@@ -1140,45 +1224,16 @@ int alll_solve_p2p(alll_handle h, uint64_t seed, uint64_t max_rounds, uint64_t m
     if (!h->p2p_ready) return fail(h, ALLL_BAD_ARG, "call alll_p2p_create / alll_p2p_connect first");
     std::memset(stats, 0, sizeof(*stats));
     const uint64_t launches0 = h->launches;
+    if (max_rounds == 0) max_rounds = 1;
+    max_rounds = std::min<uint64_t>(max_rounds, (1u << 20) - 2);       // the round lives in 20 bits of the tag
+    if (p2p_persistent_possible(h)) {
+        // every rank: the whole sharded solve in one cooperative launch (persist.cu: solve_persistent_kernel, p2p branch)
+        if (int rc = p2p_persistent_begin(h, seed, max_rounds, epoch)) return rc;
+        return p2p_persistent_end(h, m_global, launches0, stats);
+    }
     CK(launch_reset_counters(h->d_ctr, 1, h->stream)); h->launches++;
     cudaEvent_t ev_begin = h->ev[2 * MAX_TIMED_ROUNDS];
     CK(cudaEventRecord(ev_begin, h->stream));
-    if (max_rounds == 0) max_rounds = 1;
-    max_rounds = std::min<uint64_t>(max_rounds, (1u << 20) - 2);       // the round lives in 20 bits of the tag
-    if ((h->flags & ALLL_FLAG_P2P_PERSISTENT) && h->persistent_ok && h->k && h->n_tiles) {
-        // every rank: the whole sharded solve in one cooperative launch (persist.cu: solve_persistent_kernel, p2p branch)
-        const SweepParams sp = sweep_params(h, 0u, 1u, 0u, false);              // (tag != 0 selects the P2P form; the kernel derives parity / tag per round)
-        ClauseView pcv{};
-        pcv.k = h->k;
-        CK(launch_solve_persistent(sp, h->resident_all, h->sweep_grid, pcv, h->k, h->d_sh_state, h->d_sh_s, mis_scratch(h, false),
-                                   h->n_vars, seed, (uint32_t)max_rounds, epoch, nullptr, 0u, 0u, h->stream));
-        h->launches++;
-        cudaEvent_t ev_end = h->ev[2 * MAX_TIMED_ROUNDS + 1];
-        CK(cudaEventRecord(ev_end, h->stream));
-        if (int rc = fetch_counters(h)) return rc;
-        float pms = 0.f;
-        CK(cudaEventElapsedTime(&pms, ev_begin, ev_end));
-        const Counters c = *h->h_ctr;
-        CK(launch_reset_counters(h->d_ctr, 0, h->stream)); h->launches++;
-        CK(cudaStreamSynchronize(h->stream));
-        if (getenv("ALLL_TRACE")) print_phases(c, c.n_iterations);
-        if (c.p2p_error || c.done == 2)
-            return fail(h, c.p2p_error == 1 ? ALLL_CAPACITY : ALLL_CUDA_ERROR,
-                        c.p2p_error == 1 ? "P2P exchange region too small for a round's violated records"
-                                         : "P2P exchange: a peer did not publish its round in time");
-        stats->n_iterations = c.n_iterations;
-        stats->n_resamples = c.n_resamples;
-        stats->sum_mis_size = c.sum_mis;
-        stats->avg_mis_size = c.n_iterations ? c.sum_mis / c.n_iterations : 0;
-        stats->n_clause_evals = m_global * c.n_iterations;
-        stats->n_luby_steps = c.n_luby_steps;
-        stats->n_kernel_launches = h->launches - launches0;
-        stats->solve_ms = pms;
-        stats->sweep_ms = (double)c.t_sweep_ns * 1e-6;
-        stats->between_sweeps_ms = (double)c.t_mis_ns * 1e-6;
-        stats->status = c.done == 1 ? ALLL_OK : ALLL_MAX_ROUNDS;
-        return stats->status;
-    }
     int status = ALLL_MAX_ROUNDS;
     uint64_t issued = 0, retired = 0;
     const unsigned long long seq0 = h->seq;
@@ -1233,7 +1288,8 @@ int alll_solve_p2p(alll_handle h, uint64_t seed, uint64_t max_rounds, uint64_t m
     if (failed || c.p2p_error)
         return fail(h, c.p2p_error == 1 ? ALLL_CAPACITY : ALLL_CUDA_ERROR,
                     c.p2p_error == 1 ? "P2P exchange region too small for a round's violated records"
-                                     : "P2P exchange: a peer did not publish its round in time");
+                                     : c.p2p_error == 3 ? "P2P exchange: a peer aborted the solve"
+                                                        : "P2P exchange: a peer did not publish its round in time");
     float ms = 0.f;
     if (retired) CK(cudaEventElapsedTime(&ms, ev_begin, ev_last));
     double sweep_ms = 0.0, between_ms = 0.0;
@@ -1373,7 +1429,7 @@ int alll_flag_create(alll_handle h, uint8_t handle_out[64])
     if (!h || !handle_out) return ALLL_BAD_ARG;
     CK(cudaSetDevice(h->device));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    if (h->d_flag) { if (h->flag_owner) cudaFree(h->d_flag); else cudaIpcCloseMemHandle(h->d_flag); h->d_flag = nullptr; }
+    if (h->d_flag) { if (h->flag_owner) cudaFree(h->d_flag); else if (!h->flag_borrowed) cudaIpcCloseMemHandle(h->d_flag); h->d_flag = nullptr; h->flag_borrowed = false; }
     CK(cudaMalloc(&h->d_flag, 256));
     h->flag_owner = true;
     CK(cudaMemset(h->d_flag, 0xFF, 256));                    // -1: open
@@ -1387,7 +1443,7 @@ int alll_flag_open(alll_handle h, const uint8_t *handle)
 {
     if (!h || !handle) return ALLL_BAD_ARG;
     CK(cudaSetDevice(h->device));
-    if (h->d_flag) { if (h->flag_owner) cudaFree(h->d_flag); else cudaIpcCloseMemHandle(h->d_flag); h->d_flag = nullptr; }
+    if (h->d_flag) { if (h->flag_owner) cudaFree(h->d_flag); else if (!h->flag_borrowed) cudaIpcCloseMemHandle(h->d_flag); h->d_flag = nullptr; h->flag_borrowed = false; }
     cudaIpcMemHandle_t ipc;
     std::memcpy(&ipc, handle, 64);
     void *p = nullptr;
@@ -1477,3 +1533,51 @@ int alll_layout_info(alll_handle h, uint64_t info[6])
 }
 
 } // extern "C"
+
+// ---- internal entry points for the single-process multi-GPU layer (multi.cu); not part of the C ABI -----------------
+namespace alll {
+
+void *internal_p2p_region(alll_handle h) { return h ? h->d_p2p_region : nullptr; }
+
+int internal_p2p_connect_ptrs(alll_handle h, void *const *regions)
+{
+    if (!h) return ALLL_BAD_ARG;
+    if (!h->has_instance) return fail(h, ALLL_NO_INSTANCE, "no instance uploaded");
+    if (!h->d_p2p_region || !regions) return fail(h, ALLL_BAD_ARG, "call alll_p2p_create first");
+    CK(cudaSetDevice(h->device));
+    return p2p_link_up(h, regions);
+}
+
+bool internal_p2p_persistent_possible(alll_handle h) { return h && p2p_persistent_possible(h); }
+
+int internal_solve_p2p_begin(alll_handle h, uint64_t seed, uint64_t max_rounds, uint32_t epoch, uint64_t *launches0)
+{
+    if (!h) return ALLL_BAD_ARG;
+    if (!h->has_instance || !h->p2p_ready) return fail(h, ALLL_NO_INSTANCE, "no sharded instance");
+    *launches0 = h->launches;
+    return p2p_persistent_begin(h, seed, max_rounds, epoch);
+}
+
+int internal_solve_p2p_end(alll_handle h, uint64_t m_global, uint64_t launches0, alll_stats *stats)
+{
+    std::memset(stats, 0, sizeof(*stats));
+    return p2p_persistent_end(h, m_global, launches0, stats);
+}
+
+int *internal_flag_ptr(alll_handle h) { return h ? h->d_flag : nullptr; }
+
+// Same-process peer: use the winner word another handle of this process created (plain device pointer, peer access on).
+int internal_flag_attach(alll_handle h, int *word)
+{
+    if (!h || !word) return ALLL_BAD_ARG;
+    if (h->d_flag) { if (h->flag_owner) cudaFree(h->d_flag); else if (!h->flag_borrowed) cudaIpcCloseMemHandle(h->d_flag); h->d_flag = nullptr; }
+    h->d_flag = word;
+    h->flag_owner = false;
+    h->flag_borrowed = true;
+    return ALLL_OK;
+}
+
+int internal_device(alll_handle h) { return h ? h->device : -1; }
+
+} // namespace alll
+

@@ -7,7 +7,7 @@
 namespace alll {
 
 struct IncrParams {
-    const uint32_t *s_slots;       // S of the round that just finished (clause slots)
+    const uint32_t *s_slots;       // S of the round that just finished (clause slots; sharded P2P mode: indices into that round's gathered U)
     const uint32_t *rows;          // [m_pad][stride]
     uint32_t stride, k;
     const uint32_t *occ_off, *occ;
@@ -17,17 +17,39 @@ struct IncrParams {
     Counters *ctr;
 };
 
+// Sharded P2P mode of the persistent solve kernel: where S's literals come from (the records of the PREVIOUS round in
+// our own exchange region) and where the new violated clauses go (records in every GPU's region, like the sweep's).
+struct IncrP2P {
+    const P2PLink *link;           // NULL: single-GPU form (S as slots, violated slots into IncrParams::viol)
+    const uint32_t *prev_prefix;   // exclusive prefix sums of the previous round's per-rank record counts
+    uint32_t par;                  // parity of THIS round (previous round's records: par ^ 1)
+    const uint32_t *orig_id;       // slot -> caller id (NULL = identity), + id_base = global clause id
+    uint32_t id_base;
+    Counters *ctr;
+    uint32_t abort_val;            // what to write into the peers' abort words on a capacity overflow ((epoch & 0xFFF) + 1)
+};
+
 // One warp per (clause of S, literal): walks the occurrence list of that variable, 32 clauses at a time.
 // n_s: |S| of the round that just ended; n_viol: where |U| of the new round is accumulated.
-__device__ __forceinline__ void incr_eval_body(const IncrParams &p, uint32_t n_s, unsigned int *n_viol)
+__device__ __forceinline__ void incr_eval_body(const IncrParams &p, uint32_t n_s, unsigned int *n_viol, const IncrP2P &x)
 {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
     const uint32_t n_items = n_s * p.k;
+    const uint32_t w = p.k + 1;
     unsigned long long evals = 0;
     for (uint32_t item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < n_items; item += warps_total) {
-        const uint32_t slot_s = p.s_slots[item / p.k];
-        const uint32_t v = p.rows[(uint64_t)slot_s * p.stride + item % p.k] >> 1;
+        const uint32_t s_entry = p.s_slots[item / p.k];
+        uint32_t v;
+        if (x.link) {                                   // entry i of the previous round's gathered U: a record in our region
+            const P2PLink &L = *x.link;
+            uint32_t q = 0;
+            while (x.prev_prefix[q + 1] <= s_entry) ++q;
+            const uint32_t *rec = L.rec[L.rank] + (((uint64_t)(x.par ^ 1u) * L.world + q) * L.cap + (s_entry - x.prev_prefix[q])) * w;
+            v = __ldcg(rec + 1 + item % p.k) >> 1;
+        } else {
+            v = p.rows[(uint64_t)s_entry * p.stride + item % p.k] >> 1;
+        }
         const uint32_t lo = p.occ_off[v], hi = p.occ_off[v + 1];
         for (uint32_t base = lo; base < hi; base += 32) {
             const uint32_t e = base + lane;
@@ -53,12 +75,37 @@ __device__ __forceinline__ void incr_eval_body(const IncrParams &p, uint32_t n_s
                     }
                 }
             }
-            const uint32_t bal = __ballot_sync(0xffffffffu, violated);
+            uint32_t bal = __ballot_sync(0xffffffffu, violated);
             if (bal) {
                 unsigned int g = 0;
                 if (lane == 0) g = atomicAdd(n_viol, (unsigned int)__popc(bal));
                 g = __shfl_sync(0xffffffffu, g, 0);
-                if (violated) p.viol[g + __popc(bal & ((1u << lane) - 1u))] = c;
+                if (!x.link) {
+                    if (violated) p.viol[g + __popc(bal & ((1u << lane) - 1u))] = c;
+                } else {
+                    // fused exchange, as in the sweep's flush: the record {global id, k literals} of every violated clause
+                    // goes into this rank's receive slot in every GPU's region; lanes 0..k write one record (36 bytes,
+                    // contiguous) per peer
+                    const P2PLink &L = *x.link;
+                    const uint32_t n_new = __popc(bal);
+                    if ((uint64_t)g + n_new > L.cap) {
+                        if (lane == 0) { x.ctr->p2p_error = 1; for (uint32_t q = 0; q < L.world; q++) L.hdr[q]->abort = x.abort_val; }
+                    } else {
+                        uint32_t at = g;
+                        while (bal) {
+                            const int src = __ffs(bal) - 1;
+                            bal &= bal - 1;
+                            const uint32_t cs = __shfl_sync(0xffffffffu, c, src);
+                            if (lane < w) {
+                                const uint32_t word = lane == 0 ? (x.orig_id ? __ldg(x.orig_id + cs) : cs) + x.id_base
+                                                                : p.rows[(uint64_t)cs * p.stride + lane - 1];
+                                const uint64_t off = (((uint64_t)x.par * L.world + L.rank) * L.cap + at) * w + lane;
+                                for (uint32_t q = 0; q < L.world; q++) L.rec[q][off] = word;
+                            }
+                            ++at;
+                        }
+                    }
+                }
             }
         }
     }

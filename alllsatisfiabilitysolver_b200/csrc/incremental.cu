@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) incr_fill_kernel(const uint32_t *__restri
 __global__ void __launch_bounds__(256) incr_eval_kernel(const IncrParams p)
 {
     if (__ldcg(&p.ctr->done) || !__ldcg(&p.ctr->incr_next)) return;   // this round is a full sweep (or none at all)
-    incr_eval_body(p, __ldcg(&p.ctr->last_n_s), &p.ctr->n_viol);
+    incr_eval_body(p, __ldcg(&p.ctr->last_n_s), &p.ctr->n_viol, IncrP2P{});
 }
 
 // ---- launchers ----------------------------------------------------------------------------------------------

@@ -121,10 +121,14 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) bucket_scatter_kernel(const ui
     if (width_in) width_out[dst] = width_in[c];
     const uint32_t lo = b * bucket_vars;
     // the first (at most resident_cap) bucket-resident literals go to the leading planes, original order kept;
-    // everything else follows (a resident literal beyond the cap is simply looked up through L2 like the rest)
+    // everything else follows (a resident literal beyond the cap is simply looked up through L2 like the rest).
+    // Padded rows (width_in): only the TRUE literals [0, w) are reordered; the pad copies of literal 0 stay in planes
+    // [w, k), because the independent set, the resample and the incremental row build read exactly the first w planes
+    // of a slot and must see every variable of the clause there (never a pad copy in place of a true literal).
+    const uint32_t w = width_in ? width_in[c] : k;
     uint32_t j_out = 0, placed = 0;
     uint32_t front_mask = 0;
-    for (uint32_t j = 0; j < k && placed < resident_cap; j++) {
+    for (uint32_t j = 0; j < w && placed < resident_cap; j++) {
         const uint32_t l = lit[c * k + j];
         if ((l >> 1) - lo < bucket_vars) {
             planes[(uint64_t)(j_out++) * m_pad + dst] = l;

@@ -217,13 +217,22 @@ __device__ __forceinline__ uint32_t p2p_wait(const MisParams &p, uint32_t *s_pre
         P2PHeader *me = L.hdr[L.rank];
         const long long t_start = clock64();
         bool bad = false;
+        unsigned int why = 0;                         // 2: a peer never published this round in time, 3: a peer aborted
+        const unsigned int aval = (p.p2p_tag >> 20) + 1u;     // abort words are tagged with the solve's epoch
         for (uint32_t q = 0; q < L.world && !bad; q++) {
             while (*(volatile unsigned int *)&me->flag[p.p2p_parity][q] != p.p2p_tag) {
-                if (*(volatile unsigned int *)&me->abort || clock64() - t_start > 6000000000ll) { bad = true; break; }
+                if (*(volatile unsigned int *)&me->abort == aval) { bad = true; why = 3; break; }
+                if (clock64() - t_start > L.timeout_cycles) {
+                    // tell the peers as well: they would otherwise wait for OUR next round until their own time-out
+                    bad = true; why = 2;
+                    for (uint32_t r = 0; r < L.world; r++) *(volatile unsigned int *)&L.hdr[r]->abort = aval;
+                    break;
+                }
             }
         }
         __threadfence_system();                       // acquire: the records behind the flags are now visible
-        if (*(volatile unsigned int *)&me->abort) bad = true;     // a peer overflowed even though every flag arrived
+        if (!bad && *(volatile unsigned int *)&me->abort == aval) { bad = true; why = 3; }   // a peer overflowed even though every flag arrived
+        if (bad && blockIdx.x == 0 && p.ctr->p2p_error == 0) p.ctr->p2p_error = why;
         uint32_t run = 0;
         for (uint32_t q = 0; q < L.world; q++) {
             s_prefix[q] = run;

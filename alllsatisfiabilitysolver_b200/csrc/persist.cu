@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(cons
         // incremental mode (ip.rows != NULL): the round that just ended decided whether this round's violated set comes
         // from the occurrence lists of the variables it resampled (same set as the sweep's, incremental.cu) or from a sweep
         const bool incremental = ip.rows != nullptr && round > 0 && gm::ld_cg(&c->incr_next) != 0;
-        if (incremental) incr_eval_body(ip, gm::ld_cg(&c->last_n_s), &c->n_viol_pp[par]);
+        if (incremental) incr_eval_body(ip, gm::ld_cg(&c->last_n_s), &c->n_viol_pp[par], IncrP2P{sp.p2p, s_prefix, par, sp.orig_id, sp.id_base, c, sp.p2p_epoch + 1u});
         else sweep_planes_body<K, RB, RC, E, false>(sp, &c->n_viol_pp[par], par, rec_on);
         if (p2p) {                                       // this CTA's record stores (NVLink) are ordered before the barrier
             __syncthreads();
@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(cons
         }
         if (incremental)                                 // the first-visit bits of this round: nobody reads them before the next one
             for (uint32_t i = first; i < visited_words; i += stride) ip.visited[i] = 0u;
-        if (n_u == 0xFFFFFFFFu) {                        // a peer overflowed its exchange area or never arrived: stop
-            if (lead) {
+        if (n_u == 0xFFFFFFFFu) {                        // a peer overflowed its exchange area, aborted or never arrived: stop
+            if (lead) {                                  // (p2p_wait left the reason: 2 = time-out, 3 = a peer aborted)
                 c->p2p_error = c->p2p_error ? c->p2p_error : 2;
                 c->done = 2;
             }

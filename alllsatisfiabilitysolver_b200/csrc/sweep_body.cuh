@@ -21,14 +21,18 @@ namespace {
 // streaming loop registers.
 // (Arguments by value: taking the address of the kernel's parameter block would move it to local memory, and the
 // streaming loop would then read its parameters through L1/L2 instead of the constant bank -- measured 0.22 -> 0.30 ms.)
+// link != NULL (sharded P2P mode): the same records go into the receive slot of this rank and round in EVERY GPU's
+// exchange region (urec is then the offset of that slot in words): consecutive lanes store consecutive words, so each
+// peer gets whole 128-byte NVLink writes instead of one 4-byte packet per word.
 __device__ __noinline__ void write_records(uint32_t *__restrict__ urec, const uint32_t *__restrict__ planes, uint64_t m_pad,
                                            const uint32_t *__restrict__ orig_id, uint32_t id_base, uint32_t k, uint32_t wbuf,
-                                           uint32_t g, uint32_t count, uint32_t lane)
+                                           uint32_t g, uint32_t count, uint32_t lane, const P2PLink *link = nullptr, uint64_t slot_base = 0)
 {
     // One (clause, word) pair per lane and pass; k <= 8, count <= 63 => at most 18 passes.  All scattered reads are issued
     // before the first store (one DRAM round trip per flush instead of one per pass), the stores of a pass are consecutive.
     const uint32_t w = k + 1, total = count * w;
-    uint32_t *out = urec + (uint64_t)g * w;
+    uint32_t *out = link ? nullptr : urec + (uint64_t)g * w;
+    const uint32_t n_dst = link ? link->world : 1u;
     for (uint32_t t0 = 0; t0 < total; t0 += 32 * 9) {
         uint32_t val[9];
 #pragma unroll
@@ -41,10 +45,13 @@ __device__ __noinline__ void write_records(uint32_t *__restrict__ urec, const ui
                 val[q] = j == 0 ? (orig_id ? __ldg(orig_id + slot) : slot) + id_base : __ldg(planes + (uint64_t)(j - 1) * m_pad + slot);
             }
         }
+        for (uint32_t d = 0; d < n_dst; d++) {
+            if (link) out = link->rec[d] + slot_base + (uint64_t)g * w;
 #pragma unroll
-        for (int q = 0; q < 9; q++) {
-            const uint32_t t = t0 + q * 32 + lane;
-            if (t < total) out[t] = val[q];
+            for (int q = 0; q < 9; q++) {
+                const uint32_t t = t0 + q * 32 + lane;
+                if (t < total) out[t] = val[q];
+            }
         }
     }
 }
@@ -71,18 +78,10 @@ struct WarpCompactor {
             // rank and round (NVLink P2P stores), as records {global id, k literals}
             const P2PLink &L = *sp->p2p;
             if ((uint64_t)g + count > L.cap) {
-                if (lane == 0) { ctr->p2p_error = 1; for (uint32_t q = 0; q < L.world; q++) L.hdr[q]->abort = 1; }
+                if (lane == 0) { ctr->p2p_error = 1; for (uint32_t q = 0; q < L.world; q++) L.hdr[q]->abort = sp->p2p_epoch + 1u; }
             } else {
-                const uint32_t w = L.k + 1;
-                const uint64_t base = (((uint64_t)p2p_parity * L.world + L.rank) * L.cap + g) * w;
-                for (uint32_t i = lane; i < count; i += 32) {
-                    const uint32_t slot = g_smem[wbuf + i];
-                    for (uint32_t j = 0; j < w; j++) {
-                        const uint32_t word = j == 0 ? (sp->orig_id ? sp->orig_id[slot] : slot) + sp->id_base
-                                                     : sp->planes[(uint64_t)(j - 1) * sp->m_pad + slot];
-                        for (uint32_t q = 0; q < L.world; q++) L.rec[q][base + (uint64_t)i * w + j] = word;
-                    }
-                }
+                const uint64_t slot_base = ((uint64_t)p2p_parity * L.world + L.rank) * L.cap * (L.k + 1);
+                write_records(nullptr, sp->planes, sp->m_pad, sp->orig_id, sp->id_base, sp->k, wbuf, g, count, lane, sp->p2p, slot_base);
             }
         } else {
             for (uint32_t i = lane; i < count; i += 32) viol[g + i] = g_smem[wbuf + i];
@@ -140,6 +139,13 @@ __device__ __forceinline__ void p2p_publish(const SweepParams &p)
     for (uint32_t q = 0; q < L.world; q++) *(volatile unsigned int *)&L.hdr[q]->flag[p.p2p_parity][L.rank] = p.p2p_tag;
 }
 
+// Assignment words are read with ld.global.cg (L2, coherent), never through the non-coherent path (__ldg / ld.global.nc):
+// inside solve_persistent_kernel the same launch rewrites `bits` every round (resample_var: red.or / red.and), and .nc
+// is only defined for data that is read-only for the whole kernel -- a stale line would silently drop a violated clause.
+// The immutable literal planes, orig_id and segs keep the .nc path.  (L1 would not help these lookups anyway: the
+// staged assignment leaves ~30 KB of L1 against a 1.25 MB array.)
+__device__ __forceinline__ uint32_t ld_bits(const uint32_t *p) { return __ldcg(p); }
+
 // true iff literal l is TRUE under the assignment
 template <bool RESIDENT_ALL>
 __device__ __forceinline__ uint32_t literal_true(uint32_t l, const uint32_t *gbits, uint32_t vbase, uint32_t bucket_vars)
@@ -150,7 +156,7 @@ __device__ __forceinline__ uint32_t literal_true(uint32_t l, const uint32_t *gbi
         w = g_smem[v >> 5];
     } else {
         const uint32_t rel = v - vbase;                 // wraps to a huge value when v < vbase
-        w = (rel < bucket_vars) ? g_smem[rel >> 5] : __ldg(gbits + (v >> 5));
+        w = (rel < bucket_vars) ? g_smem[rel >> 5] : ld_bits(gbits + (v >> 5));
     }
     return ((w >> (v & 31u)) ^ l) & 1u;
 }
@@ -185,7 +191,7 @@ struct TileCursor {
         __syncthreads();                      // everyone is done with the previous bucket's bits
         const uint4 *src = reinterpret_cast<const uint4 *>(p.bits + (uint64_t)b * p.bucket_words);
         for (uint32_t i = threadIdx.x; i < p.bucket_words / 4; i += SWEEP_THREADS)
-            reinterpret_cast<uint4 *>(g_smem)[i] = __ldg(src + i);
+            reinterpret_cast<uint4 *>(g_smem)[i] = __ldcg(src + i);      // coherent (L2) read: see ld_bits
         __syncthreads();
         loaded = b;
     }
@@ -243,7 +249,7 @@ __device__ __forceinline__ void gather_issue(uint32_t l, uint32_t alive, const u
 {
     const uint32_t v = l >> 1;
     go = TEST_RANGE ? (alive != 0 && (v - vbase) >= bucket_vars) : (alive != 0);
-    w = go ? __ldg(gbits + (v >> 5)) : 0u;
+    w = go ? ld_bits(gbits + (v >> 5)) : 0u;
 }
 __device__ __forceinline__ void gather_apply(uint32_t l, uint32_t &alive, uint32_t w, bool go)
 {
@@ -338,7 +344,7 @@ struct SurvivorQueue {
                 if (RESIDENT_ALL) w[j] = act ? g_smem[v >> 5] : 0u;
                 else {
                     const uint32_t rel = v - vbase;
-                    w[j] = !act ? 0u : (rel < bucket_vars) ? g_smem[rel >> 5] : __ldg(p.bits + (v >> 5));
+                    w[j] = !act ? 0u : (rel < bucket_vars) ? g_smem[rel >> 5] : ld_bits(p.bits + (v >> 5));
                 }
             }
             bool violated = act;

@@ -45,6 +45,7 @@ class ShardedStats:
     solve_ms: float              # device-clock interval of the round loop, max over ranks
     trace_u: list
     trace_s: list
+    n_incremental_rounds: int = 0
 
 
 class CudaShardBackend:
@@ -191,13 +192,14 @@ class P2PShardedSolver:
     ``torch.distributed`` is only used once to exchange the 64-byte IPC handles and as a barrier between solves.
     Needs one process per GPU on one node (peer access between all GPUs)."""
 
-    def __init__(self, device: int, rank: int, world: int, group=None, persistent: bool = False):
+    def __init__(self, device: int, rank: int, world: int, group=None, persistent: bool = False, flags: int = 0):
         from . import capi
 
         self.capi = capi
         # persistent: every rank runs its whole solve as ONE cooperative kernel (ALLL_FLAG_P2P_PERSISTENT); only valid
-        # when every rank has a GPU of its own -- the kernels of all ranks must be resident at the same time
-        self.solver = capi.Solver(device=device, flags=capi.FLAG_P2P_PERSISTENT if persistent else 0)
+        # when every rank has a GPU of its own -- the kernels of all ranks must be resident at the same time.
+        # flags: e.g. capi.FLAG_INCREMENTAL (each rank then walks the occurrence lists of its own clause range)
+        self.solver = capi.Solver(device=device, flags=(capi.FLAG_P2P_PERSISTENT if persistent else 0) | flags)
         self.device = torch.device("cuda", device)
         self.rank, self.world, self.group = rank, world, group
         self.epoch = 0
@@ -236,12 +238,19 @@ class P2PShardedSolver:
         self.epoch += 1
         st = self.solver.solve_p2p(seed, self.m_global, self.epoch, max_rounds)
         ms = st.solve_ms
+        # incremental rounds evaluate only the clauses next to resampled variables: every rank counted its own range
+        full = self.m_global * (st.n_iterations - st.n_incremental_rounds)
+        evals = st.n_clause_evals
         if self.world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=self.device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
             ms = float(t.item())
-        return ShardedStats(st.n_iterations, st.n_resamples, st.avg_mis_size, st.sum_mis_size, st.n_clause_evals,
-                            st.status, ms, [], [])
+            if st.n_incremental_rounds:
+                e = torch.tensor([st.n_clause_evals - full], dtype=torch.int64, device=self.device)
+                dist.all_reduce(e, op=dist.ReduceOp.SUM, group=self.group)
+                evals = full + int(e.item())
+        return ShardedStats(st.n_iterations, st.n_resamples, st.avg_mis_size, st.sum_mis_size, evals,
+                            st.status, ms, [], [], st.n_incremental_rounds)
 
 
 # ---- portfolio and batched instances over the GPUs of one box (BASELINE config 5) -----------

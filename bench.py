@@ -144,18 +144,17 @@ class ClockSampler:
 # reference arm / cpu_baseline: the unmodified reference headers on host cores (oracle/_ref)
 # ------------------------------------------------------------------------------------------------
 
-def reference_sample(shape: dict, steps: int, warmup: int, budget_s: float = 150.0):
-    """Times SATInstance::solve (the -p OpenMP path) on a bounded sample of the workload shape."""
-    from alllsatisfiabilitysolver_b200.instances import bounded_degree_ksat, uniform_ksat
-    from oracle.oracle import Reference, have_reference, to_csr
+SAMPLE_N = 1_000_000      # variables of the bounded sample both arms can solve (see sample_instance)
 
-    if not have_reference():
-        return None
-    ref = Reference()
-    cores = ref.num_procs()
-    # bounded sample: same (k, d) shape at n = 1M variables at most (cfg4 itself would need ~5 GB of Clause
-    # objects and minutes per solve in the reference's quadratic greedy independent set)
-    n = min(shape["n"], 1_000_000)
+
+def sample_instance(shape: dict):
+    """The bounded sample of the workload: same (k, d) shape at n = 1M variables at most, numpy generator, fixed seed --
+    the EXACT instance the reference arm solves and the `same_instance` record of our arm solves on the GPU.
+    (Full cfg4 needs ~5 GB of Clause objects and ~10 minutes per solve in the reference's quadratic greedy independent
+    set: 601.6 s measured with 8 threads, profiles/r02_reference_full_cfg4.md.)"""
+    from alllsatisfiabilitysolver_b200.instances import bounded_degree_ksat, uniform_ksat
+
+    n = min(shape["n"], SAMPLE_N)
     if shape["kind"] == "bounded":
         lits = bounded_degree_ksat(n, shape["k"], shape["d"], seed=INSTANCE_SEED_BASE)
         desc = f"bounded-degree {shape['k']}-SAT d={shape['d']} n={n} m={lits.shape[0]}"
@@ -163,6 +162,18 @@ def reference_sample(shape: dict, steps: int, warmup: int, budget_s: float = 150
         m = int(shape["m"] * n / shape["n"])
         lits = uniform_ksat(n, shape["k"], m, seed=INSTANCE_SEED_BASE)
         desc = f"uniform {shape['k']}-SAT n={n} m={m}"
+    return n, lits, desc
+
+
+def reference_sample(shape: dict, steps: int, warmup: int, budget_s: float = 150.0):
+    """Times SATInstance::solve (the -p OpenMP path) on a bounded sample of the workload shape."""
+    from oracle.oracle import Reference, have_reference, to_csr
+
+    if not have_reference():
+        return None
+    ref = Reference()
+    cores = ref.num_procs()
+    n, lits, desc = sample_instance(shape)
     off, lit = to_csr(lits)
     m = lits.shape[0]
     evals, secs, its = 0, 0.0, []
@@ -183,7 +194,61 @@ def reference_sample(shape: dict, steps: int, warmup: int, budget_s: float = 150
     return dict(value=evals / secs, unit=UNIT, cores=cores, kind="reference",
                 sample=f"{desc}; {done} full SATInstance::solve runs with n_threads={cores} (unmodified reference headers, "
                        f"-Ofast -fopenmp), mean {np.mean(its):.1f} iterations, {secs / done * 1e3:.1f} ms per solve",
-                ms_per_step=secs / done * 1e3, steps=done)
+                ms_per_step=secs / done * 1e3, steps=done, n=n, m=m, desc=desc)
+
+
+_FULL_REF_CHILD = r"""
+import sys, time, json
+sys.path.insert(0, {root!r})
+import numpy as np
+from alllsatisfiabilitysolver_b200.instances import bounded_degree_ksat, uniform_ksat, INSTANCE_SEED_BASE
+from oracle.oracle import Reference, to_csr
+shape = {shape!r}
+t0 = time.time()
+lits = (bounded_degree_ksat(shape["n"], shape["k"], shape["d"], seed=INSTANCE_SEED_BASE) if shape["kind"] == "bounded"
+        else uniform_ksat(shape["n"], shape["k"], shape["m"], seed=INSTANCE_SEED_BASE))
+off, lit = to_csr(lits)
+ref = Reference()
+with ref.instance(shape["n"], off, lit, ref.num_procs()) as ri:
+    print(json.dumps({{"built_s": time.time() - t0, "m": int(lits.shape[0])}}), flush=True)
+    st = ri.solve()
+    print(json.dumps({{"solve_s": st.seconds, "n_iterations": st.n_iterations, "verified": bool(ri.verify())}}), flush=True)
+"""
+
+
+def reference_full_instance(shape: dict, timebox_s: float):
+    """The reference ONCE on the full workload instance, in a child process that is stopped at the time box (the solve
+    is one blocking C++ call).  Returns what happened -- a result, or 'no result in T s' (SURVEY 8d expected minutes)."""
+    import tempfile
+
+    if timebox_s <= 0:
+        return {"skipped": "time box 0"}
+    with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
+        f.write(_FULL_REF_CHILD.format(root=ROOT, shape=dict(shape)))
+        path = f.name
+    t0 = time.time()
+    out = ""
+    try:
+        proc = subprocess.Popen([sys.executable, path], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, start_new_session=True)
+        try:
+            out, _ = proc.communicate(timeout=timebox_s)
+        except subprocess.TimeoutExpired:
+            import signal
+            os.killpg(proc.pid, signal.SIGKILL)              # the exact process group we started
+            out, _ = proc.communicate()
+    finally:
+        os.unlink(path)
+    info = {}
+    for line in (out or "").splitlines():
+        try:
+            info.update(json.loads(line))
+        except Exception:
+            pass
+    if "solve_s" in info:
+        return {"workload": describe(shape, "full"), "result": info, "clause_evals_per_sec": info["m"] * info["n_iterations"] / info["solve_s"]}
+    return {"workload": describe(shape, "full"), "result": f"no result in {timebox_s:.0f} s (time box; instance built: {'built_s' in info})",
+            "elapsed_s": time.time() - t0,
+            "measured_elsewhere": "601.6 s per solve (17 iterations, verified) with 8 threads in the build container: profiles/r02_reference_full_cfg4.md"}
 
 
 def run_reference(args):
@@ -195,12 +260,21 @@ def run_reference(args):
     if r is None:
         emit_line({"impl": "reference", "unavailable": "oracle/_ref/liballl_ref.so not built"})
         return 0
+    sampled = r["n"] != shape["n"]
+    full = None
+    if sampled and args.full_ref_timebox > 0:
+        full = reference_full_instance(shape, args.full_ref_timebox)
+    # config.workload says what THIS arm solved: the bounded sample, not the full instance of our arm's `value`; the
+    # like-for-like comparison is our arm's `same_instance` record (the GPU on exactly this sample instance)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": describe(shape, args.workload), "sample": r["sample"]},
+            "config": {"workload": (f"{args.workload} SHAPE, bounded sample: {r['desc']} (the full instance is n={shape['n']})" if sampled
+                                    else describe(shape, args.workload)),
+                       "sample": r["sample"], "same_instance_as": "our arm's `same_instance` record"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "full_instance": full,
             "gpu_launches": 0}
     emit_line(line)
     return 0
@@ -215,6 +289,87 @@ def describe(shape, name):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+
+def independent_check(lits, assignment: np.ndarray) -> bool:
+    """north_star: 'an independent checker verifies every returned assignment'.  NOT the GPU's own sweep: the caller's
+    literals are turned into signed DIMACS literals and evaluated on the host by the oracle's restatement of the
+    reference's cnf_evaluate (cnf_io.cpp:392-484) -- checker use of oracle/, outside every timed region.
+    ``lits``: (m, k) torch tensor on the device (int32 view of uint32 2*var+neg) or numpy uint32 matrix."""
+    from oracle.oracle import Oracle
+
+    if isinstance(lits, np.ndarray):
+        flat = lits.reshape(-1)
+        var1 = (flat >> 1).astype(np.int64) + 1
+        l_val = np.where(flat & 1, -var1, var1).astype(np.int32)
+        m, k = lits.shape
+    else:
+        import torch
+
+        m, k = int(lits.shape[0]), int(lits.shape[1])
+        var1 = (lits >> 1) + 1
+        l_val = torch.where((lits & 1) != 0, -var1, var1).to(torch.int32).reshape(-1).cpu().numpy()
+        del var1
+    return bool(Oracle().check_signed(np.full(m, k, np.int32), l_val, np.ascontiguousarray(assignment, np.uint8)))
+
+
+def same_instance_record(shape: dict, device: int, cpu: dict | None, max_rounds: int):
+    """Like-for-like: the GPU arm on the EXACT instance the reference arm / cpu_baseline solves (sample_instance), device
+    timed and end to end from host buffers, each result checked by the independent checker."""
+    import torch
+
+    from alllsatisfiabilitysolver_b200 import capi
+
+    n, lits, desc = sample_instance(shape)
+    m, k = lits.shape
+    host_t = torch.from_numpy(lits.view(np.int32)).pin_memory()
+    host = host_t.numpy().view(np.uint32)
+    out_t = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    out = out_t.numpy()
+    ok = True
+    with capi.Solver(device=device) as s:
+        s.upload_fixedk(n, host)
+        dev = []
+        for i in range(-3, 10):
+            s.randomize(4000 + i)
+            st = s.solve(4000 + i, max_rounds)
+            if i >= 0:
+                dev.append(st)
+        ok &= all(x.status == 0 for x in dev) and independent_check(lits, s.get_assignment())
+        e2e_ms, e2e_evals = [], 0
+
+        def step(i):
+            s.upload_fixedk(n, host)
+            s.randomize(5000 + i)
+            st = s.solve(5000 + i, max_rounds)
+            s.get_assignment(out)
+            return st
+
+        step(-1)
+        for i in range(5):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            st = step(i)
+            e2e_ms.append((time.perf_counter() - t0) * 1e3)
+            e2e_evals += st.n_clause_evals
+        ok &= independent_check(lits, out)
+    gpu_value = sum(x.n_clause_evals for x in dev) / (sum(x.solve_ms for x in dev) * 1e-3)
+    gpu_e2e = e2e_evals / (sum(e2e_ms) * 1e-3)
+    rec = {"workload": desc, "instance": "numpy generator, seed INSTANCE_SEED_BASE: identical literals in both arms",
+           "gpu": {"value": gpu_value, "unit": UNIT, "time_to_sat_ms": float(np.mean([x.solve_ms for x in dev])),
+                   "sweeps_per_solve": float(np.mean([x.n_iterations for x in dev])), "solves": len(dev)},
+           "gpu_e2e": {"value": gpu_e2e, "unit": UNIT, "ms_per_step": float(np.mean(e2e_ms)), "steps": len(e2e_ms),
+                       "h2d_bytes_per_step": 4 * k * m, "d2h_bytes_per_step": n,
+                       "call": "alll_upload_fixedk(host) + alll_randomize + alll_solve + alll_get_assignment(host)"},
+           "all_verified_by_independent_checker": bool(ok)}
+    if cpu:
+        rec["reference"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "ms_per_solve": cpu.get("ms_per_step"),
+                            "note": "measured in this same run on this box's host cores (cpu_baseline)"}
+        rec["ratio_device_timed"] = gpu_value / cpu["value"]
+        rec["ratio_e2e"] = gpu_e2e / cpu["value"]
+        if cpu.get("ms_per_step"):
+            rec["time_to_sat_ratio"] = cpu["ms_per_step"] / rec["gpu"]["time_to_sat_ms"]
+    return rec
+
 
 def run_ours(args):
     import torch
@@ -234,6 +389,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    host_group = dist.new_group(backend="gloo") if world > 1 else None     # barriers that keep the waiting ranks' GPUs idle
 
     shape = workload_shape(args.workload, args.scale)
     k, n = shape["k"], shape["n"]
@@ -282,7 +438,10 @@ def run_ours(args):
     sweep_ms = sum(s.sweep_ms for s in stats)
     rounds = sum(s.n_iterations - 1 for s in stats)
     all_sat = all(s.status == 0 for s in stats)
-    verified = solver.verify() if all_sat else False
+    # the last timed step's assignment, checked OUTSIDE the timed region by the independent signed-literal checker
+    # (cnf_io.cpp:392-484 semantics, restated in oracle/) -- not by the GPU's own sweep
+    verified = bool(all_sat and independent_check(lits_t, solver.get_assignment()))
+    verified_gpu_sweep = bool(solver.verify())
 
     # ---- same workload with incremental re-evaluation (opt-in mode; bit-identical results, fewer clause evaluations) ----
     incremental = None
@@ -344,7 +503,7 @@ def run_ours(args):
     sharded = None
     if world > 1 and not args.no_sharded:
         try:
-            sharded = sharded_solves(args, shape, rank, world, local_rank)
+            sharded = sharded_solves(args, shape, rank, world, local_rank, host_group)
         except Exception as e:                       # e.g. CUDA IPC not permitted on this box: report, do not die
             sharded = {"error": repr(e)}
 
@@ -385,7 +544,7 @@ def run_ours(args):
         sweep_avg_ms = sweep_ms / max(sweeps, 1)
         sweep_phase = alg_bytes / (sweep_avg_ms * 1e-3) / 1e9 if sweep_avg_ms > 0 else 0.0
         standalone = alg_bytes / (standalone_ms * 1e-3) / 1e9 if standalone_ms > 0 else 0.0
-        traffic = None
+        traffic, traffic_source = None, None
         tp = os.path.join(ROOT, "profiles", "sweep_traffic.json")
         if os.path.exists(tp):
             try:
@@ -394,15 +553,24 @@ def run_ours(args):
                 # `sweeps` sweeps); falls back to the per-sweep figure of the standalone kernel x sweeps of this run
                 if persistent and tj.get(args.workload + "_solve_launch"):
                     traffic = tj[args.workload + "_solve_launch"] / tj[args.workload + "_solve_launch_sweeps"] * (sweeps / args.steps)
+                    traffic_source = (f"NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one solve_persistent_kernel launch "
+                                      f"({tj[args.workload + '_solve_launch_sweeps']} sweeps) from the committed ncu --set full capture "
+                                      f"{tj.get('source', 'profiles/sweep_traffic.json')}, rescaled to this run's {sweeps / args.steps:.1f} sweeps per launch")
                 elif tj.get(args.workload):
                     traffic = tj[args.workload] * (sweeps / args.steps if persistent else 1)
+                    traffic_source = "NOT measured in this run: per-sweep DRAM bytes of the committed ncu capture (profiles/sweep_traffic.json)"
             except Exception:
                 traffic = None
-        cpu = None
+        cpu, same = None, None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = reference_sample(shape, steps=3, warmup=1, budget_s=60.0)
-            if cpu:
-                cpu = {kk: cpu[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+            cpu_full = reference_sample(shape, steps=3, warmup=1, budget_s=60.0)
+            if cpu_full:
+                cpu = {kk: cpu_full[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+            if args.scale == 1.0 and not args.no_extras:
+                try:
+                    same = same_instance_record(shape, local_rank, cpu_full, max_rounds)
+                except Exception as e:               # never lose the main line to an extra
+                    same = {"error": repr(e)}
         line = {
             "metric": METRIC, "value": evals_all / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
@@ -417,10 +585,14 @@ def run_ours(args):
             "rounds_per_sec": rounds_all / (dev_ms_max * 1e-3),
             "sweeps_per_solve": sweeps / args.steps,
             "all_runs_sat_and_verified": bool(n_ok == world),
+            "verification": {"checker": "independent: signed DIMACS literals evaluated on the host (oracle restatement of the reference's "
+                                        "cnf_evaluate, cnf_io.cpp:392-484), last timed step's assignment of every rank, outside the timed region",
+                             "gpu_sweep_agrees": verified_gpu_sweep},
+            "same_instance": same,
             "wall_ms_per_step": wall_ms_max / args.steps,
             "roofline": {"bound": "hbm", "kernel": "solve_persistent_kernel" if persistent else "sweep_planes_kernel",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes_launch, "avg_launch_ms": launch_ms,
                          "launch": "one launch = one whole solve (all sweeps + independent-set phases); CUDA events on the solver's stream",
                          "frac_of_nominal_8TBps": achieved / 8000.0,
@@ -562,13 +734,21 @@ def cfg5_over_ranks(rank, world, local_rank, n_seeds=8192, n_inst=8192, reps=3):
                       "parallelism": "instance i on GPU i mod N, no exchange"}}
 
 
-def sharded_solves(args, shape, rank, world, local_rank):
-    """Strong scaling: the workload instance split into contiguous clause ranges over all ranks.  Primary: exchange
-    fused into the kernels (NVLink P2P stores + arrival flags, no NCCL in the loop); also timed: the host-driven
-    variant with an NCCL all-gather of the violated records per round."""
+def sharded_solves(args, shape, rank, world, local_rank, host_group):
+    """Strong scaling: the workload instance split into contiguous clause ranges over all GPUs, fused NVLink exchange
+    (records stored into every peer by the sweep, arrival flags, no NCCL call in the loop).  Measured three ways:
+      (a) one process per GPU (CUDA IPC mappings; torch.distributed only moves the handles and is the barrier), full sweeps
+          every round and with incremental re-evaluation; device-timed, max over ranks;
+      (b) the same END TO END from host buffers: every rank uploads only ITS 1/N of the literals from pinned host memory
+          (N PCIe links side by side), solves, rank 0 reads the assignment back; wall clock, max over ranks;
+      (c) ONE process, ONE call (alll_multi_*: what SATInstance(..., n_threads) / the CLI's --gpus reach): rank 0 drives all
+          N GPUs over peer access while the other ranks wait on a host (gloo) barrier with idle GPUs; device-timed and
+          end to end from ONE host buffer;
+    plus the round-1 NCCL all-gather variant for the record.  Every result is checked by the independent checker."""
     import torch
     import torch.distributed as dist
 
+    from alllsatisfiabilitysolver_b200 import capi
     from alllsatisfiabilitysolver_b200.instances import bounded_degree_ksat_torch, uniform_ksat_torch
     from alllsatisfiabilitysolver_b200.sharded import CudaShardBackend, P2PShardedSolver, ShardedSolver, partition
 
@@ -579,53 +759,155 @@ def sharded_solves(args, shape, rank, world, local_rank):
     m = int(lits.shape[0])
     lo, hi = partition(m, world)[rank]
     local = lits[lo:hi].contiguous()
-    del lits
-    torch.cuda.empty_cache()
+    local_host_t = torch.empty(local.shape, dtype=local.dtype, pin_memory=True)
+    local_host_t.copy_(local)
+    full_host_t = None
+    if rank == 0:                                                       # (c) needs the whole instance in ONE host buffer
+        full_host_t = torch.empty(lits.shape, dtype=lits.dtype, pin_memory=True)
+        full_host_t.copy_(lits)
+    torch.cuda.synchronize()
+    max_rounds = min(args.max_rounds, 1 << 19)
+
+    def hbarrier():
+        torch.cuda.synchronize()
+        dist.barrier(group=host_group)
 
     def run(solver, randomize, reset):
         res = []
         for i in range(args.warmup + args.steps):
             reset()
             randomize(3000 + i)
-            st = solver.solve(3000 + i, min(args.max_rounds, 1 << 19))
+            st = solver.solve(3000 + i, max_rounds)
             if i >= args.warmup:
                 res.append(st)
         return res
 
-    out = {"scaling": "strong", "m_clauses_total": m,
-           "parallelism": f"{world} contiguous clause ranges, replicated bit-packed assignment"}
-    # primary: every rank runs its whole solve as ONE persistent kernel (one GPU per rank here, so all are resident)
-    p2p = P2PShardedSolver(local_rank, rank, world, persistent=True)
-    p2p.upload_range(n, local, m, lo)
-    res = run(p2p, p2p.randomize, lambda: None)
-    mine = torch.from_numpy(p2p.get_assignment()).cuda()
-    ref = mine.clone()
-    dist.broadcast(ref, 0)
-    flags = torch.tensor([int(bool((ref == mine).all())), int(p2p.solver.verify())], device="cuda")
-    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
-    p2p.solver.close()
-    out.update({"exchange": "fused into ONE persistent kernel per GPU: the sweep stores violated records into every peer over "
-                            "NVLink (CUDA IPC), count + arrival flag after the grid barrier, every GPU waits for all flags and "
-                            "runs the identical independent set; no NCCL call, kernel boundary or host round trip per round",
-                "time_to_sat_ms": float(np.mean([r.solve_ms for r in res])),
+    def summarize(res):
+        return {"time_to_sat_ms": float(np.mean([r.solve_ms for r in res])),
                 "sweeps_per_solve": float(np.mean([r.n_iterations for r in res])),
                 "clause_evals_per_sec": float(np.sum([r.n_clause_evals for r in res]) / (np.sum([r.solve_ms for r in res]) * 1e-3)),
-                "replicas_bit_identical": bool(flags[0].item()), "all_ranges_verified": bool(flags[1].item()),
-                "all_sat": all(r.status == 0 for r in res)})
-    try:                                             # same exchange, one kernel per phase driven by the host
-        p2k = P2PShardedSolver(local_rank, rank, world)
-        p2k.upload_range(n, local, m, lo)
-        res = run(p2k, p2k.randomize, lambda: None)
-        p2k.solver.close()
-        out["kernel_per_phase_variant_time_to_sat_ms"] = float(np.mean([r.solve_ms for r in res]))
+                "all_sat": all(r.status == 0 for r in res)}
+
+    out = {"scaling": "strong", "m_clauses_total": m,
+           "parallelism": f"{world} contiguous clause ranges, replicated bit-packed assignment"}
+
+    # ---- (a) one process per GPU, persistent kernel per rank ----
+    for key, flags in (("full_sweeps", 0), ("incremental", capi.FLAG_INCREMENTAL)):
+        p2p = P2PShardedSolver(local_rank, rank, world, persistent=True, flags=flags)
+        p2p.upload_range(n, local, m, lo)
+        res = run(p2p, p2p.randomize, lambda: None)
+        mine_np = p2p.get_assignment()
+        mine = torch.from_numpy(mine_np).cuda()
+        ref = mine.clone()
+        dist.broadcast(ref, 0)
+        checked = independent_check(lits, mine_np) if rank == 0 else True      # the full instance against rank 0's replica
+        flags_t = torch.tensor([int(bool((ref == mine).all())), int(p2p.solver.verify()), int(checked)], device="cuda")
+        dist.all_reduce(flags_t, op=dist.ReduceOp.MIN)
+        rec = summarize(res)
+        rec.update({"replicas_bit_identical": bool(flags_t[0].item()), "all_ranges_verified_on_gpu": bool(flags_t[1].item()),
+                    "verified_by_independent_checker": bool(flags_t[2].item())})
+        if flags:
+            rec["incremental_rounds_per_solve"] = float(np.mean([r.n_incremental_rounds for r in res])) if hasattr(res[0], "n_incremental_rounds") else None
+        out[key] = rec
+        if key == "full_sweeps":
+            # ---- (b) end to end from host buffers, every rank uploads only its own range ----
+            e2e_out_t = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+            host_np = local_host_t.numpy().view(np.uint32)
+
+            def e2e_step(i):
+                p2p.upload_range(n, host_np, m, lo)
+                p2p.randomize(6000 + i)
+                st = p2p.solve(6000 + i, max_rounds)
+                if rank == 0:
+                    p2p.solver.get_assignment(e2e_out_t.numpy())
+                return st
+
+            e2e_step(-1)
+            steps = max(1, min(args.steps, args.e2e_steps))
+            hbarrier()
+            t0 = time.perf_counter()
+            ev = 0
+            for i in range(steps):
+                ev += e2e_step(i).n_clause_evals
+            hbarrier()
+            dt = time.perf_counter() - t0
+            tmax = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            out["e2e_sharded"] = {"value": ev / float(tmax), "unit": UNIT, "ms_per_step": float(tmax) / steps * 1e3, "steps": steps,
+                                  "h2d_bytes_per_step_per_gpu": 4 * k * (hi - lo), "d2h_bytes_per_step": n,
+                                  "call": "per rank: alll_upload_fixedk(host, own 1/N range) + alll_p2p_create/connect + alll_randomize + "
+                                          "alll_solve_p2p; rank 0: alll_get_assignment(host)"}
+        p2p.solver.close()
+    out.update({"exchange": "fused into ONE persistent kernel per GPU: the sweep stores violated records into every peer over "
+                            "NVLink (one coalesced block per warp flush per peer), count + arrival flag after the grid barrier, "
+                            "every GPU waits for all flags and runs the identical independent set; no NCCL call, kernel boundary or "
+                            "host round trip per round",
+                "time_to_sat_ms": out["full_sweeps"]["time_to_sat_ms"], "sweeps_per_solve": out["full_sweeps"]["sweeps_per_solve"],
+                "clause_evals_per_sec": out["full_sweeps"]["clause_evals_per_sec"],
+                "replicas_bit_identical": out["full_sweeps"]["replicas_bit_identical"] and out["incremental"]["replicas_bit_identical"],
+                "all_verified_by_independent_checker": out["full_sweeps"]["verified_by_independent_checker"] and out["incremental"]["verified_by_independent_checker"],
+                "all_sat": out["full_sweeps"]["all_sat"] and out["incremental"]["all_sat"]})
+
+    # ---- round-1 variant for the record: host-driven, NCCL all-gather of the records per round ----
+    try:
+        be = CudaShardBackend(local_rank)
+        ss = ShardedSolver(be, rank, world)
+        ss.upload_range(n, local, m, lo)
+        res = run(ss, be.randomize, be.solver.reset_stats)
+        be.solver.close()
+        out["nccl_allgather_variant_time_to_sat_ms"] = float(np.mean([r.solve_ms for r in res]))
     except Exception as e:
-        out["kernel_per_phase_variant_time_to_sat_ms"] = repr(e)
-    be = CudaShardBackend(local_rank)
-    ss = ShardedSolver(be, rank, world)
-    ss.upload_range(n, local, m, lo)
-    res = run(ss, be.randomize, be.solver.reset_stats)
-    be.solver.close()
-    out["nccl_allgather_variant_time_to_sat_ms"] = float(np.mean([r.solve_ms for r in res]))
+        out["nccl_allgather_variant_time_to_sat_ms"] = repr(e)
+    del local, lits
+    torch.cuda.empty_cache()
+
+    # ---- (c) ONE process, ONE call: rank 0 drives every GPU; the other ranks wait on the host with idle GPUs ----
+    hbarrier()
+    if rank == 0:
+        try:
+            one = {}
+            full_np = full_host_t.numpy().view(np.uint32)
+            out_np = torch.empty(n, dtype=torch.uint8, pin_memory=True).numpy()
+            for key, flags in (("full_sweeps", 0), ("incremental", capi.FLAG_INCREMENTAL)):
+                with capi.MultiSolver(list(range(world)), flags=flags) as ms:
+                    ms.upload_fixedk(n, full_np)
+                    info = ms.info()
+                    res = []
+                    for i in range(args.warmup + args.steps):
+                        ms.randomize(3000 + i)
+                        st = ms.solve(3000 + i, max_rounds)
+                        if i >= args.warmup:
+                            res.append(st)
+                    rec = summarize(res)
+                    rec["verified_by_independent_checker"] = independent_check(full_np.reshape(m, k), ms.get_assignment())
+                    if flags:
+                        rec["incremental_rounds_per_solve"] = float(np.mean([r.n_incremental_rounds for r in res]))
+                    one[key] = rec
+                    if key == "full_sweeps":
+                        one["layout"] = info
+
+                        def step(i):
+                            ms.upload_fixedk(n, full_np)
+                            ms.randomize(7000 + i)
+                            st = ms.solve(7000 + i, max_rounds)
+                            ms.get_assignment(out_np)
+                            return st
+
+                        step(-1)
+                        steps = max(1, min(args.steps, args.e2e_steps))
+                        t0 = time.perf_counter()
+                        ev = sum(step(i).n_clause_evals for i in range(steps))
+                        dt = time.perf_counter() - t0
+                        one["e2e"] = {"value": ev / dt, "unit": UNIT, "ms_per_step": dt / steps * 1e3, "steps": steps,
+                                      "h2d_bytes_per_step": 4 * k * m, "d2h_bytes_per_step": n,
+                                      "call": "alll_multi_upload_fixedk(ONE host buffer; every GPU copies its own 1/N) + alll_multi_randomize + "
+                                              "alll_multi_solve + alll_multi_get_assignment(host)"}
+            one["how"] = ("alll_multi_* from rank 0's process alone: peer access instead of CUDA IPC, one host thread starts every GPU's "
+                          "persistent solve kernel; the other ranks' processes wait on a gloo barrier")
+            out["single_process"] = one
+        except Exception as e:
+            out["single_process"] = {"error": repr(e)}
+    hbarrier()
     return out
 
 
@@ -666,6 +948,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the brief cfg2 / cfg5 runs at N=1")
     ap.add_argument("--no-sharded", action="store_true", help="skip the clause-range sharded solves at N>1")
+    ap.add_argument("--full-ref-timebox", type=float, default=120.0,
+                    help="--impl reference: seconds allowed for ONE reference solve of the full workload instance (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print(f"note: warmup {args.warmup} < 3; timing rules ask for >= 3", file=sys.stderr)

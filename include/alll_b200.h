@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ALLL_ABI_VERSION 4
+#define ALLL_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define ALLL_API __attribute__((visibility("default")))
@@ -80,6 +80,9 @@ typedef struct {
  * Opt-in because the kernels of all ranks must be resident at the same time: set it only when every rank of the
  * sharded solve has a GPU of its own (several ranks on ONE device would wait for each other until the 3 s time-out). */
 #define ALLL_FLAG_P2P_PERSISTENT 32u
+/* alll_multi_*: shard every stored instance of uniform width k <= 8 with at least one clause per device (default: only
+ * instances with >= 4096 clauses per device; smaller ones are solved on the first device alone).  For tests. */
+#define ALLL_FLAG_FORCE_SHARDING 64u
 
 /* Statistics{} of SATInstance.h:25-32 plus device-side counters.
  * n_iterations = resample rounds + 1 (the terminal all-satisfied sweep counts, :261,:285-287);
@@ -281,6 +284,50 @@ ALLL_API int alll_flag_open(alll_handle h, const uint8_t *handle);
 ALLL_API int alll_flag_reset(alll_handle h);
 ALLL_API int alll_flag_read(alll_handle h, int64_t *value);
 ALLL_API int alll_batch_set_job_base(alll_handle h, uint32_t job_base);
+
+/* ---- several GPUs behind ONE call from ONE process (alll_solve_sharded / alll_solve_batch) -----
+ * The reference's parallel-resource knob is the constructor argument / CLI flag -p (SATInstance.h:51-56,259;
+ * example/main.cpp:56-61,76-84): a single process, a single blocking call.  This group gives a C or C++ caller of the
+ * drop-in headers the same shape over a list of GPUs -- no torch.distributed, no process per GPU: peer access
+ * (cudaDeviceEnablePeerAccess) instead of CUDA IPC, one host thread starts every GPU's persistent solve kernel.
+ *   - one large instance: contiguous clause ranges, one per device, replicated bit-packed assignment; every device
+ *     uploads ONLY its own 1/N of the caller's host literals (N PCIe links in parallel); the round loop is the fused
+ *     P2P exchange of alll_solve_p2p.  Needs stored clauses of uniform width k <= 8; anything else (and n_devices == 1)
+ *     is solved on the first device alone -- same results, alll_multi_info tells which.
+ *   - batched small instances / seed portfolio: instance (or seed) blocks per device, one first-SAT word for all devices.
+ * The same device may be listed several times (simulated ranks sharing one GPU: one kernel per phase instead of
+ * persistent kernels, host threads instead of one launcher) -- that is how single-GPU machines test the exchange.
+ * Results are bit-identical to the single-GPU calls for the same seed, whatever the device list. */
+typedef struct alll_multi *alll_multi_handle;
+
+/* cfg (may be NULL): sweep_smem_bytes and flags apply to every device; cfg->device is ignored.
+ * ALLL_FLAG_INCREMENTAL is honoured by the sharded solve as well (each device walks the occurrence lists of its own range). */
+ALLL_API int alll_multi_create(const int32_t *devices, uint32_t n_devices, const alll_config *cfg, alll_multi_handle *out);
+ALLL_API int alll_multi_destroy(alll_multi_handle mh);
+ALLL_API const char *alll_multi_last_error(alll_multi_handle mh);      /* mh == NULL: error of the failed alll_multi_create */
+/* Replaces the flattening + ownership of SATInstance::solve's vector<ClauseArray*> (SATInstance.h:60-66) for N GPUs. */
+ALLL_API int alll_multi_upload_fixedk(alll_multi_handle mh, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit);
+ALLL_API int alll_multi_upload_csr(alll_multi_handle mh, uint64_t n_vars, uint64_t m, const uint64_t *off, const uint32_t *lit);
+ALLL_API int alll_multi_set_assignment(alll_multi_handle mh, const uint8_t *bools);
+ALLL_API int alll_multi_get_assignment(alll_multi_handle mh, uint8_t *bools);
+ALLL_API int alll_multi_randomize(alll_multi_handle mh, uint64_t seed);
+/* verify_validity (SATInstance.h:156-173) over all clause ranges. */
+ALLL_API int alll_multi_verify(alll_multi_handle mh, int *valid);
+/* SATInstance::solve -> parallel_solve (SATInstance.h:60-66, :217-320) over all devices.  stats->solve_ms is the
+ * device-timed span (CUDA events), max over the devices; n_kernel_launches sums over them. */
+ALLL_API int alll_multi_solve(alll_multi_handle mh, uint64_t seed, uint64_t max_rounds, alll_stats *stats);
+/* {devices in use, 1 if the instance is clause-range sharded (0: first device alone), clauses of the widest range,
+ *  records one rank may publish per round} */
+ALLL_API int alll_multi_info(alll_multi_handle mh, uint64_t info[4]);
+/* Handle of device slot i (for alll_layout_info, alll_eval, ... on one range); owned by mh. */
+ALLL_API int alll_multi_device_handle(alll_multi_handle mh, uint32_t i, alll_handle *out);
+/* Batched small instances / seed portfolio over the device list: instance blocks [i*n/N, (i+1)*n/N) per device (seed
+ * blocks in portfolio mode, every device then holds instance 0); arguments as for alll_batch_upload / alll_batch_solve,
+ * portfolio != 0 uses ONE winner word for all devices.  *device_ms: max over the devices. */
+ALLL_API int alll_multi_batch_upload(alll_multi_handle mh, uint32_t n_instances, uint64_t n_vars, uint32_t k,
+                                     const uint64_t *clause_off, const uint32_t *lit);
+ALLL_API int alll_multi_batch_solve(alll_multi_handle mh, uint32_t n_jobs, const uint64_t *seeds, uint64_t max_rounds, int portfolio,
+                                    uint8_t *assignments, alll_batch_stats *stats, int32_t *winner, double *device_ms);
 
 /* ---- measurement hooks -------------------------------------------------------------- */
 

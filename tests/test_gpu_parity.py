@@ -161,6 +161,41 @@ def test_round_count_distribution_vs_reference(capi, golden):
     assert abs(np.mean(rs) - ref_rs.mean()) <= 0.05 * ref_rs.mean()
 
 
+def test_round_count_distribution_vs_reference_medium_instance(capi, oracle, golden):
+    """Same check on the medium instance of the golden set (7-SAT, n=100k, m~400k, d=28; `k7_100k`): 30 self-seeded runs
+    of the unmodified reference with 8 threads (17.8 +- 2.4 iterations, 35.9 k +- 0.7 k resamples) against 32 GPU seeds.
+    Stated tolerance: mean n_iterations within +-15 %, mean n_resamples within +-5 %; in addition the
+    two samples must pass a two-sample Kolmogorov-Smirnov test on n_iterations at alpha = 0.001 (D < 1.95*sqrt((a+b)/ab)),
+    and every GPU run must end in an assignment the independent signed-literal checker accepts."""
+    from alllsatisfiabilitysolver_b200.instances import bounded_degree_ksat
+
+    n, k, d, inst_seed, m_want = (int(x) for x in golden["k7_100k/shape"])
+    lits = bounded_degree_ksat(n, k, d, inst_seed)
+    assert lits.shape[0] == m_want                   # the very instance the reference solved for the fixture
+    ref_it = golden["k7_100k/ref_solve_t8_iterations"].astype(float)
+    ref_rs = golden["k7_100k/ref_solve_t8_resamples"].astype(float)
+    flat = lits.reshape(-1)
+    signed = np.where(flat & 1, -((flat >> 1).astype(np.int64) + 1), (flat >> 1).astype(np.int64) + 1).astype(np.int32)
+    widths = np.full(lits.shape[0], k, np.int32)
+    its, rs = [], []
+    with capi.Solver() as s:
+        s.upload_fixedk(n, lits)
+        for seed in range(32):
+            s.randomize(seed)
+            st = s.solve(seed)
+            assert st.status == 0
+            assert oracle.check_signed(widths, signed, s.get_assignment())
+            its.append(st.n_iterations)
+            rs.append(st.n_resamples)
+    its, rs = np.array(its, float), np.array(rs, float)
+    assert abs(its.mean() - ref_it.mean()) <= 0.15 * ref_it.mean(), (its.mean(), ref_it.mean())
+    assert abs(rs.mean() - ref_rs.mean()) <= 0.05 * ref_rs.mean(), (rs.mean(), ref_rs.mean())
+    grid = np.union1d(its, ref_it)
+    cdf = lambda x: np.searchsorted(np.sort(x), grid, side="right") / len(x)
+    dstat = np.abs(cdf(its) - cdf(ref_it)).max()
+    assert dstat < 1.95 * np.sqrt((len(its) + len(ref_it)) / (len(its) * len(ref_it))), dstat
+
+
 @pytest.mark.parametrize("k", [1, 2, 4, 6, 9, 12, 32])
 def test_all_clause_widths(capi, oracle, k):
     """k <= 8 uses the unrolled kernels, larger k the run-time-width kernel."""
@@ -406,4 +441,84 @@ def test_ragged_input_uses_padded_planes_by_default(capi, oracle, golden):
                 u_o, s_o, r_o = oracle.round(n, off, lit, v, 9, rnd)
                 u_g, s_g, r_g = s.round(9, rnd)
                 assert np.array_equal(np.sort(u_g), u_o) and np.array_equal(np.sort(s_g), np.sort(s_o)) and r_g == r_o
+                assert np.array_equal(s.get_assignment(), v)
+
+
+def _ragged_instance(n, m, seed, wmin=1, wmax=8):
+    """Mixed-width clauses over n variables (distinct variables inside a clause), CSR form."""
+    rng = np.random.default_rng(seed)
+    widths = rng.integers(wmin, wmax + 1, size=m)
+    off = np.zeros(m + 1, np.uint64)
+    off[1:] = np.cumsum(widths)
+    lit = np.empty(int(off[-1]), np.uint32)
+    for c in range(m):
+        vs = rng.choice(n, size=int(widths[c]), replace=False)
+        lit[int(off[c]):int(off[c + 1])] = (vs * 2 + rng.integers(0, 2, size=len(vs))).astype(np.uint32)
+    return off, lit
+
+
+@pytest.mark.parametrize("layout", [dict(sweep_smem_bytes=1024), dict(sweep_smem_bytes=1024, flags=16),
+                                    dict(sweep_smem_bytes=1024, flags=4), dict(sweep_smem_bytes=1024, flags=4 | 16),
+                                    dict(sweep_smem_bytes=1024, flags=8)],
+                         ids=["bucketed", "bucketed_host_round_loop", "bucketed_incremental",
+                              "bucketed_incremental_host_round_loop", "force_csr"])
+def test_ragged_input_on_several_buckets(capi, oracle, layout):
+    """Mixed-width input padded onto the plane layout WITH variable-range bucketing (n_buckets > 1; round-1 advisor
+    finding): the bucket pass reorders a clause's literals, and the independent set / resample / incremental row build
+    read only the first `width` planes -- they must still see every variable of the clause, never a pad copy.
+    Round by round and as a whole solve against the oracle."""
+    n, m = 40_000, 14_000                      # 8192 variables per bucket at the 1 KiB staging budget -> 5 buckets
+    off, lit = _ragged_instance(n, m, seed=77, wmin=2, wmax=8)
+    seed = 31
+    with capi.Solver(**layout) as s:
+        s.upload_csr(n, off, lit)
+        if not (layout.get("flags", 0) & 8):
+            info = s.layout_info()
+            assert info["n_buckets"] > 1 and info["k"] == 8
+        s.randomize(seed)
+        v = oracle.randomize(n, seed)
+        for rnd in range(10):
+            u_o, s_o, r_o = oracle.round(n, off, lit, v, seed, rnd)
+            u_g, s_g, r_g = s.round(seed, rnd)
+            assert np.array_equal(np.sort(u_g), u_o)
+            assert np.array_equal(np.sort(s_g), np.sort(s_o))
+            assert r_g == r_o
+            assert np.array_equal(s.get_assignment(), v)
+            if len(u_o) == 0:
+                break
+        for sd in (1, 2):
+            s.randomize(sd)
+            st = s.solve(sd, 500)
+            v = oracle.randomize(n, sd)
+            so = oracle.solve(n, off, lit, v, sd, max_rounds=500)
+            assert st.status == so.status == 0
+            assert (st.n_iterations, st.n_resamples, st.avg_mis_size, st.sum_mis_size) == \
+                   (so.n_iterations, so.n_resamples, so.avg_mis_size, so.sum_mis_size)
+            assert np.array_equal(s.get_assignment(), v) and oracle.verify(off, lit, v)
+
+
+def test_ragged_bucketed_private_variable_terminates(capi, oracle):
+    """(a or b) and (not a) with b occurring only there, a resident in the clause's bucket and b not: before the fix the
+    padded row became (a, a) and b was never resampled -- an endless loop on a satisfiable instance."""
+    n = 20_000
+    a, b = 5, 15_000                           # different 8192-variable buckets
+    rows = [[2 * a, 2 * b], [2 * a + 1]]
+    # filler so that bucket sizes are not degenerate; every filler clause is satisfied by the all-zero start
+    rows += [[2 * (100 + i) + 1, 2 * (9000 + i) + 1, 2 * (17000 + i) + 1] for i in range(500)]
+    off = np.zeros(len(rows) + 1, np.uint64)
+    off[1:] = np.cumsum([len(r) for r in rows])
+    lit = np.array([l for r in rows for l in r], np.uint32)
+    for flags in (0, 4, 16):
+        with capi.Solver(sweep_smem_bytes=1024, flags=flags) as s:
+            s.upload_csr(n, off, lit)
+            assert s.layout_info()["n_buckets"] > 1
+            v0 = np.zeros(n, np.uint8)
+            v0[a] = 1                           # (not a) violated; the fix needs b := 1 after a := 0
+            for seed in range(4):
+                s.set_assignment(v0)
+                st = s.solve(seed, 200)
+                v = v0.copy()
+                so = oracle.solve(n, off, lit, v, seed, max_rounds=200)
+                assert st.status == so.status == 0
+                assert (st.n_iterations, st.n_resamples) == (so.n_iterations, so.n_resamples)
                 assert np.array_equal(s.get_assignment(), v)

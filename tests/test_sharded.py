@@ -164,6 +164,51 @@ def test_sharded_p2p_persistent_kernels_two_gpus():
 
 
 @pytest.mark.gpu
+def test_sharded_p2p_persistent_incremental_two_gpus():
+    """Persistent kernels + incremental re-evaluation of each rank's own clause range (the violated records of an
+    incremental round go through the same fused exchange)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29658",
+                        os.path.join(ROOT, "tools", "run_sharded.py"), "--p2p", "--persistent", "--incremental", "--scale", "0.05",
+                        "--solves", "3", "--check"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"ok": true' in r.stdout
+
+
+@pytest.mark.gpu
+def test_p2p_persistent_incremental_single_rank_matches_oracle(oracle):
+    """world = 1 runs the incremental branch of the sharded persistent kernel on one GPU: S comes from the previous
+    round's records in the exchange region, the new violated clauses leave as records; trajectory == oracle."""
+    from alllsatisfiabilitysolver_b200 import capi
+    from alllsatisfiabilitysolver_b200.instances import bounded_degree_ksat
+    from alllsatisfiabilitysolver_b200.sharded import P2PShardedSolver
+
+    for n, k, d in ((300_000, 8, 32), (120_000, 7, 28), (2_000_000, 8, 32)):      # resident / resident / bucketed layout
+        lits = bounded_degree_ksat(n, k, d, seed=16)
+        m = lits.shape[0]
+        off = np.arange(m + 1, dtype=np.uint64) * np.uint64(k)
+        ss = P2PShardedSolver(0, 0, 1, persistent=True, flags=capi.FLAG_INCREMENTAL)
+        ss.upload_range(n, lits, m, 0)
+        used = 0
+        for sd in (7, 8):
+            ss.randomize(sd)
+            st = ss.solve(sd)
+            v = oracle.randomize(n, sd)
+            so = oracle.solve(n, off, lits.reshape(-1), v, sd)
+            assert (st.n_iterations, st.n_resamples, st.sum_mis_size, st.status) == (so.n_iterations, so.n_resamples, so.sum_mis_size, 0)
+            assert np.array_equal(ss.get_assignment(), v) and ss.solver.verify()
+            used += st.n_incremental_rounds
+            if st.n_incremental_rounds:
+                assert st.n_clause_evals < m * st.n_iterations
+        assert used > 0
+        ss.solver.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("persistent", [False, True], ids=["kernel_per_phase", "persistent_kernel"])
 def test_p2p_mode_single_rank_matches_plain_solve(oracle, persistent):
     """world = 1 exercises the whole P2P code path (record export, flags, MIS over records) on one GPU."""

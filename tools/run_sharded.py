@@ -29,6 +29,7 @@ ap.add_argument("--solves", type=int, default=3)
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--p2p", action="store_true", help="exchange fused into the kernels (NVLink P2P) instead of NCCL all-gather")
 ap.add_argument("--persistent", action="store_true", help="with --p2p: one persistent solve kernel per rank")
+ap.add_argument("--incremental", action="store_true", help="with --p2p --persistent: ALLL_FLAG_INCREMENTAL on every rank")
 a = ap.parse_args()
 
 rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -42,7 +43,7 @@ lits = (bounded_degree_ksat_torch(n, cfg["k"], cfg["d"], 0xA115) if cfg["kind"] 
 m, k = int(lits.shape[0]), int(lits.shape[1])
 lo, hi = partition(m, world)[rank]
 if a.p2p:
-    ss = P2PShardedSolver(local, rank, world, persistent=a.persistent)
+    ss = P2PShardedSolver(local, rank, world, persistent=a.persistent, flags=capi.FLAG_INCREMENTAL if a.incremental else 0)
     be = ss
 else:
     be = CudaShardBackend(local)
@@ -55,6 +56,7 @@ for i in range(a.solves):
     be.randomize(100 + i)
     st = ss.solve(100 + i)
     out["solves"].append(dict(ms=st.solve_ms, iters=st.n_iterations, resamples=st.n_resamples, status=st.status,
+                              incremental_rounds=getattr(st, "n_incremental_rounds", 0),
                               clause_evals_per_s=st.n_clause_evals / (st.solve_ms * 1e-3)))
 ok = True
 if a.check:
