@@ -84,9 +84,7 @@ def test_small_and_unshardable_instances_fall_back_to_the_first_device(capi, ora
     ALLL_FLAG_FORCE_SHARDING shards a small uniform instance anyway (one clause per device is enough)."""
     from conftest import golden_case
 
-    n, off, lit, _ = golden_case(golden, "k7_small")
-    m = len(off) - 1
-    lits = lit.reshape(m, 7)
+    n, off, lit, _ = golden_case(golden, "cfg1")              # m ~ 1,200 clauses: below the 4096-per-device threshold
     for flags, want_sharded in ((0, False), (capi.FLAG_FORCE_SHARDING, True)):
         with capi.MultiSolver([0, 0], flags=flags) as ms:
             ms.upload_csr(n, off, lit)                       # uniform width -> routed to the fixed-width upload
