@@ -4,12 +4,14 @@
 // "Variable i = b" dump :272-276, exit code :283,294), written without Boost and driving the B200 path
 // through the drop-in SATInstance.h.
 //
-//   alll_solve [-h] [-o] [-p n_threads] --sat <file.cnf> [--seed S] [--max-rounds R] [--gpu ORDINAL]
+//   alll_solve [-h] [-o] [-p n_threads] --sat <file.cnf> [--seed S] [--max-rounds R] [--gpu ORDINAL] [--gpus N]
 //
 // Deviations: the INFORMATION block and csv field 3 carry the true clause count
 // (Q1); a positional path is accepted as well as --sat (Q3); paths shorter than 4 characters get
 // ".out"/".csv" appended instead of overwriting (Q12); -p only sizes the per-thread statistics block --
-// the work runs on the GPU.
+// the work runs on the GPU(s): --gpus N (0 = all visible) is the parallel-resource knob of this build, what -p is to
+// the reference (main.cpp:56-61,76-84); one large instance is then clause-range sharded over N B200s behind the same
+// blocking solve call.
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -57,7 +59,8 @@ static void usage()
             "  --sat arg                  Path to SAT instance in DIMACS-CNF format\n"
             "  --seed arg                 Solver seed (default: random_device)\n"
             "  --max-rounds arg           Resample-round cap (default: unbounded)\n"
-            "  --gpu arg                  CUDA device ordinal (default: current device)\n";
+            "  --gpu arg                  CUDA device ordinal of the first GPU (default: 0)\n"
+            "  --gpus arg (=1)            Number of GPUs for the solve (0 = all visible; default: ALLL_GPUS or 1)\n";
 }
 
 int main(int argc, char *argv[])
@@ -66,7 +69,7 @@ int main(int argc, char *argv[])
     bool dump = false, have_seed = false;
     string cnf_fpath;
     uint64_t seed = 0, max_rounds = ~0ull;
-    int gpu = -1;
+    int gpu = -1, gpus = -1;
     const int n_procs = (int)std::max(1u, std::thread::hardware_concurrency());
 
     for (int i = 1; i < argc; i++) {
@@ -87,6 +90,7 @@ int main(int argc, char *argv[])
         else if (a == "--seed") { seed = strtoull(value("--seed").c_str(), nullptr, 0); have_seed = true; }
         else if (a == "--max-rounds") max_rounds = strtoull(value("--max-rounds").c_str(), nullptr, 0);
         else if (a == "--gpu") gpu = atoi(value("--gpu").c_str());
+        else if (a == "--gpus") gpus = atoi(value("--gpus").c_str());
         else if (!a.empty() && a[0] != '-' && cnf_fpath.empty()) cnf_fpath = a;
         else { cerr << "unrecognised option '" << a << "'" << endl; return 1; }
     }
@@ -120,6 +124,7 @@ int main(int argc, char *argv[])
     if (have_seed) satInstance->set_seed(seed);
     satInstance->set_max_rounds(max_rounds);
     satInstance->set_device(gpu);
+    if (gpus >= 0) satInstance->set_gpus(gpus);
 
     auto stop = chrono::high_resolution_clock::now();
     auto read_duration = chrono::duration_cast<chrono::milliseconds>(stop - start);
@@ -164,7 +169,7 @@ int main(int argc, char *argv[])
     int rc = 1;
     if (satInstance->last_status() == ALLL_MAX_ROUNDS) {
         output("UNKNOWN: round cap reached before all clauses were satisfied\n", out_f, dump);
-    } else if (satInstance->verify_validity_csr(off, lit)) {
+    } else if (satInstance->verify_last()) {             // the clauses of the solve are still on the device(s): no second upload
         output("SATISFIABLE\n", out_f, dump);
         if (dump)
             for (ull i = 0; i < satInstance->n_vars; i++)

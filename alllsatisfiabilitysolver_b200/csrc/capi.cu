@@ -9,6 +9,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/alll_b200.h"
@@ -61,6 +62,8 @@ struct alll_solver {
     uint8_t *d_state = nullptr, *d_bools = nullptr;
     uint8_t *h_bools = nullptr;          // pinned staging for the 1-byte-per-variable boundary (grow-only)
     size_t h_bools_cap = 0;
+    uint8_t *h_stage = nullptr;          // pinned staging for rows the library builds itself (padded ragged input; grow-only)
+    size_t h_stage_cap = 0;
     uint8_t *d_width = nullptr, *d_width_in = nullptr;   // padded planes: true clause widths by slot / by caller id
     bool use_width = false;
     Counters *d_ctr = nullptr;
@@ -190,6 +193,22 @@ template <typename T> int pool_alloc(alll_handle h, T **slot, size_t bytes)
 #define POOL(slot, bytes) do { if (int rc__ = pool_alloc(h, &(slot), (bytes))) return rc__; } while (0)
 
 inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+// Host-side passes over the caller's arrays (width scan, ragged padding) are split over the host's threads.
+inline uint32_t host_threads_for(uint64_t items, uint64_t min_per_thread)
+{
+    const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+    return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint32_t>(hw, 32u), items / std::max<uint64_t>(min_per_thread, 1)));
+}
+template <class F> void parallel_ranges(uint64_t items, uint32_t nt, F &&fn)     // fn(thread, begin, end)
+{
+    if (nt <= 1) { fn(0u, (uint64_t)0, items); return; }
+    std::vector<std::thread> th;
+    th.reserve(nt - 1);
+    for (uint32_t t = 1; t < nt; t++) th.emplace_back([&, t] { fn(t, items * t / nt, items * (t + 1) / nt); });
+    fn(0u, (uint64_t)0, items / nt);
+    for (auto &x : th) x.join();
+}
 
 // flags bits 16..23: L2 prefetch distance in tiles; 0 = default (2, measured best on B200), 0xFF = off
 inline uint32_t prefetch_distance(uint32_t flags)
@@ -613,6 +632,29 @@ extern "C" {
 
 int alll_abi_version(void) { return ALLL_ABI_VERSION; }
 
+int alll_device_count(int32_t *n)
+{
+    if (!n) return ALLL_BAD_ARG;
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); c = 0; }
+    *n = c;
+    return ALLL_OK;
+}
+
+int alll_host_alloc(uint64_t bytes, void **out)
+{
+    if (!out) return ALLL_BAD_ARG;
+    *out = nullptr;
+    if (cudaMallocHost(out, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return ALLL_CUDA_ERROR; }
+    return ALLL_OK;
+}
+
+int alll_host_free(void *p)
+{
+    if (p && cudaFreeHost(p) != cudaSuccess) { cudaGetLastError(); return ALLL_CUDA_ERROR; }
+    return ALLL_OK;
+}
+
 const char *alll_last_error(alll_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int alll_create(const alll_config *cfg, alll_handle *out)
@@ -670,6 +712,7 @@ int alll_destroy(alll_handle h)
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
     if (h->h_ring) cudaFreeHost(h->h_ring);
     if (h->h_bools) cudaFreeHost(h->h_bools);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
     for (auto &ev : h->ev_round) if (ev) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -711,35 +754,64 @@ int alll_upload_csr(alll_handle h, uint64_t n_vars, uint64_t m, const uint64_t *
     if (!h) return ALLL_BAD_ARG;
     if (!off || (m && off[m] > off[0] && !lit)) return fail(h, ALLL_BAD_ARG, "off/lit == NULL");
     CK(cudaSetDevice(h->device));
-    // width scan: refuse empty clauses (Clause.h:35-45 makes them unsatisfiable), route uniform width to planes
+    // width scan: refuse empty clauses (Clause.h:35-45 makes them unsatisfiable), route uniform width to planes.
+    // One pass over m+1 offsets, split over the host's threads (320 MB at m = 40 M: ~40 ms on one core).
     bool uniform = m > 0;
     const uint64_t k0 = m ? off[1] - off[0] : 0;
     uint64_t kmax = 0;
-    for (uint64_t c = 0; c < m; c++) {
-        if (off[c + 1] < off[c]) return fail(h, ALLL_BAD_ARG, "offsets must be non-decreasing");
-        const uint64_t w = off[c + 1] - off[c];
-        if (w == 0) return fail(h, ALLL_EMPTY_CLAUSE, "clause " + std::to_string(c) + " is empty and can never be satisfied");
-        uniform &= (w == k0);
-        kmax = std::max(kmax, w);
+    {
+        const uint32_t nt = host_threads_for(m, 1u << 18);
+        std::vector<uint64_t> t_kmax(nt, 0), t_bad(nt, ~0ull), t_empty(nt, ~0ull);
+        std::vector<uint8_t> t_uniform(nt, 1);
+        parallel_ranges(m, nt, [&](uint32_t t, uint64_t c0, uint64_t c1) {
+            uint64_t km = 0;
+            bool uni = true;
+            for (uint64_t c = c0; c < c1; c++) {
+                if (off[c + 1] < off[c]) { t_bad[t] = c; return; }
+                const uint64_t w = off[c + 1] - off[c];
+                if (w == 0) { t_empty[t] = c; return; }
+                uni &= (w == k0);
+                km = std::max(km, w);
+            }
+            t_kmax[t] = km; t_uniform[t] = uni;
+        });
+        for (uint32_t t = 0; t < nt; t++) {                  // first offender in clause order, like the serial scan
+            if (t_bad[t] != ~0ull) return fail(h, ALLL_BAD_ARG, "offsets must be non-decreasing");
+            if (t_empty[t] != ~0ull) return fail(h, ALLL_EMPTY_CLAUSE, "clause " + std::to_string(t_empty[t]) + " is empty and can never be satisfied");
+            uniform = uniform && t_uniform[t];
+            kmax = std::max(kmax, t_kmax[t]);
+        }
     }
     if (uniform && k0 <= MAX_K) return alll_upload_fixedk(h, n_vars, m, (uint32_t)k0, lit + off[0]);
     const uint64_t n_lit_in = m ? off[m] - off[0] : 0;
     if (m > 0 && kmax <= MAX_K && m * kmax <= 2 * n_lit_in + 1024 && !(h->flags & ALLL_FLAG_FORCE_CSR)) {
         // ragged input with modest spread: pad every clause to the widest one with copies of its first literal and
         // use the plane layout (fast sweep); true widths are kept for the independent-set / resample accounting
-        std::vector<uint32_t> padded(m * kmax);
-        std::vector<uint8_t> widths(m);
-        for (uint64_t c = 0; c < m; c++) {
-            const uint64_t w = off[c + 1] - off[c];
-            widths[c] = (uint8_t)w;
-            for (uint64_t j = 0; j < kmax; j++) padded[c * kmax + j] = lit[off[c] + (j < w ? j : 0)];
+        // (padded rows + widths are built by all host threads straight into a page-locked staging buffer of the handle:
+        // the copy then runs at the PCIe rate instead of the pageable path's fifth of it)
+        const size_t pad_bytes = (size_t)m * kmax * 4, need = pad_bytes + m;
+        if (h->h_stage_cap < need) {
+            if (h->h_stage) { cudaFreeHost(h->h_stage); h->h_stage = nullptr; h->h_stage_cap = 0; }
+            CK(cudaMallocHost(&h->h_stage, need));
+            h->h_stage_cap = need;
         }
+        uint32_t *padded = reinterpret_cast<uint32_t *>(h->h_stage);
+        uint8_t *widths = h->h_stage + pad_bytes;
+        parallel_ranges(m, host_threads_for(m, 1u << 16), [&](uint32_t, uint64_t c0, uint64_t c1) {
+            for (uint64_t c = c0; c < c1; c++) {
+                const uint64_t w = off[c + 1] - off[c];
+                widths[c] = (uint8_t)w;
+                const uint32_t *src = lit + off[c];
+                uint32_t *dst = padded + c * kmax;
+                for (uint64_t j = 0; j < kmax; j++) dst[j] = src[j < w ? j : 0];
+            }
+        });
         free_instance(h);
-        POOL(h->d_stage, padded.size() * 4);
+        POOL(h->d_stage, pad_bytes);
         POOL(h->d_width_in, m);
-        CK(cudaMemcpyAsync(h->d_stage, padded.data(), padded.size() * 4, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->d_width_in, widths.data(), m, cudaMemcpyHostToDevice, h->stream));
-        const int rc = upload_fixedk_device_impl(h, n_vars, m, (uint32_t)kmax, h->d_stage, h->d_width_in);
+        CK(cudaMemcpyAsync(h->d_width_in, widths, m, cudaMemcpyHostToDevice, h->stream));
+        const int rc = upload_fixedk_device_impl(h, n_vars, m, (uint32_t)kmax, h->d_stage, h->d_width_in, padded);   // chunked H2D behind the layout pass
+        cudaStreamSynchronize(h->copy_stream);
         cudaStreamSynchronize(h->stream);
         return rc;
     }

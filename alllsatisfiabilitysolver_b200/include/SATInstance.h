@@ -10,9 +10,15 @@
 // so example/main.cpp of the reference compiles unchanged against this directory.
 //
 // What is different underneath: there is no OpenMP loop here.  solve() flattens the caller's batches once
-// (global clause id = position in the concatenation), uploads them through the C ABI (include/alll_b200.h)
-// and the whole round loop -- sweep, independent set, resample -- runs on the B200.  There is no CPU
-// fallback: a missing device or library error throws std::runtime_error.
+// (global clause id = position in the concatenation; all host threads, straight into a page-locked staging buffer),
+// uploads them through the C ABI (include/alll_b200.h) and the whole round loop -- sweep, independent set, resample --
+// runs on the B200s.  There is no CPU fallback: a missing device or library error throws std::runtime_error.
+//
+// The reference's parallel-resource knob is this constructor's n_threads (SATInstance.h:51-56,259; -p of the CLI).  Here
+// the resource is GPUs: set_gpus(n) -- or the environment variable ALLL_GPUS=n|all for programs compiled unchanged --
+// solves one large instance over min(n, visible) devices behind this same blocking call (alll_multi_*: contiguous
+// clause ranges, every device uploads its own 1/N of the staging buffer, fused NVLink exchange per round).  n_threads
+// keeps its second role (number of input batches, size of n_thread_resamples) and is used for the host-side flatten.
 //
 // Deliberate deviations from the reference: n_clauses is assigned, not accumulated,
 // by solve() (Q6); an optional seed makes runs reproducible (Q8); a round cap turns the reference's
@@ -21,19 +27,22 @@
 #ifndef ALLL_B200_SATINSTANCE_H
 #define ALLL_B200_SATINSTANCE_H
 
+#include <chrono>
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <random>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
 #ifdef _OPENMP
 #include <omp.h>
 #else
-#include <thread>
 // The reference header pulls in <omp.h> (SATInstance.h:16) and its CLI calls omp_get_num_procs()
 // (example/main.cpp:77-78); keep that call compiling without OpenMP.
 static inline int omp_get_num_procs() { const unsigned n = std::thread::hardware_concurrency(); return n ? (int)n : 1; }
@@ -72,7 +81,9 @@ public:
 
     ~SATInstance()
     {
-        if (handle) alll_destroy(handle);
+        if (handle) alll_multi_destroy(handle);
+        if (stage_lit) alll_host_free(stage_lit);
+        if (stage_off) alll_host_free(stage_off);
     }
 
     // Parallel Moser-Tardos solve of the clauses in `clauses` (n_threads batches, any split); on return
@@ -92,29 +103,30 @@ public:
         (void)batch_size;
         this->n_clauses = n_clauses;
         ClauseGenerator<T> generator(getEnumeratedClause, 0, (T)n_clauses, 0, (T)n_clauses);
+        // (the caller's callback is host code handing out heap objects one at a time: inherently serial)
         vector<uint64_t> off(1, 0);
         vector<uint32_t> lit;
+        off.reserve(n_clauses + 1);
         for (ull i = 0; i < n_clauses; i++) {
             Clause<T> *cl = generator.yieldNextClause();
             if (cl == nullptr) throw std::runtime_error("SATInstance::solve: clause enumeration ended early");
+            if (i == 0) lit.reserve(cl->literals->size() * n_clauses);
             for (auto &l : *cl->literals) lit.push_back((uint32_t)l);
             off.push_back(lit.size());
             delete cl->literals;
             delete cl;
         }
-        upload_flat(off, lit);
+        upload_flat(off.data(), off.size() - 1, lit.data());
         return run_solve();
     }
 
     // true iff the assignment in var_arr satisfies every clause (SATInstance.h:156-173); evaluated on the device.
     bool verify_validity(vector<ClauseArray *> *clauses) const
     {
+        // (const in the reference's signature; the device handle is this object's cache, not its value)
         auto *self = const_cast<SATInstance *>(this);
         self->upload(clauses);
-        self->check(alll_set_assignment(handle, reinterpret_cast<const uint8_t *>(var_arr->vars)), "alll_set_assignment");
-        int valid = 0;
-        self->check(alll_verify(handle, &valid), "alll_verify");
-        return valid != 0;
+        return self->verify_uploaded();
     }
 
     // DIMACS dump of an enumerated instance (SATInstance.h:175-203): "p cnf V C", then " l1 l2 ... 0" per clause.
@@ -145,18 +157,23 @@ public:
     {
         if (off.empty()) throw std::runtime_error("SATInstance::solve_csr: off must hold m+1 entries");
         n_clauses = off.size() - 1;
-        upload_flat(off, lit);
+        upload_flat(off.data(), off.size() - 1, lit.data());
         return run_solve();
     }
     bool verify_validity_csr(const vector<uint64_t> &off, const vector<uint32_t> &lit) const
     {
         if (off.empty()) throw std::runtime_error("SATInstance::verify_validity_csr: off must hold m+1 entries");
         auto *self = const_cast<SATInstance *>(this);
-        self->upload_flat(off, lit);
-        self->check(alll_set_assignment(handle, reinterpret_cast<const uint8_t *>(var_arr->vars)), "alll_set_assignment");
-        int valid = 0;
-        self->check(alll_verify(handle, &valid), "alll_verify");
-        return valid != 0;
+        self->upload_flat(off.data(), off.size() - 1, lit.data());
+        return self->verify_uploaded();
+    }
+    // var_arr against the clauses of the most recent solve / verify call, which are still on the device: no flatten, no
+    // upload.  (verify_validity(clauses) itself always uploads what it is given -- it cannot know whether the caller
+    // changed a clause since; round 1 guessed with a fingerprint, which a collision would have turned into a wrong answer.)
+    bool verify_last() const
+    {
+        if (!have_upload) throw std::runtime_error("SATInstance::verify_last: nothing has been solved or verified yet");
+        return const_cast<SATInstance *>(this)->verify_uploaded();
     }
     // Enumerated clauses produced ON THE DEVICE.  The reference's callback form above hands out heap Clause objects
     // from host code, which cannot run inside a kernel; its device-side equivalent is a functor compiled into the
@@ -166,90 +183,177 @@ public:
     {
         this->n_clauses = n_clauses;
         ensure_handle();
-        check(alll_upload_generator(handle, (uint64_t)n_vars, n_clauses, k, launch, user, cap_records), "alll_upload_generator");
+        check1(alll_upload_generator(first(), (uint64_t)n_vars, n_clauses, k, launch, user, cap_records), "alll_upload_generator");
         have_upload = false;
-        return run_solve();
+        return run_solve_single();
     }
     bool verify_validity_generator(alll_gen_launch_fn launch, void *user, ull n_clauses, unsigned k, ull cap_records = 0) const
     {
         auto *self = const_cast<SATInstance *>(this);
         self->ensure_handle();
-        self->check(alll_upload_generator(handle, (uint64_t)n_vars, n_clauses, k, launch, user, cap_records), "alll_upload_generator");
+        alll_handle h = self->first();
+        self->check1(alll_upload_generator(h, (uint64_t)n_vars, n_clauses, k, launch, user, cap_records), "alll_upload_generator");
         self->have_upload = false;
-        self->check(alll_set_assignment(handle, reinterpret_cast<const uint8_t *>(var_arr->vars)), "alll_set_assignment");
+        self->check1(alll_set_assignment(h, reinterpret_cast<const uint8_t *>(var_arr->vars)), "alll_set_assignment");
         int valid = 0;
-        self->check(alll_verify(handle, &valid), "alll_verify");
+        self->check1(alll_verify(h, &valid), "alll_verify");
         return valid != 0;
     }
 
     void set_seed(uint64_t s) { seed = s; have_seed = true; }          // reproducible rounds (Philox key)
     void set_max_rounds(uint64_t r) { max_rounds = r; }                // default: effectively unbounded
-    void set_device(int ordinal) { device = ordinal; }                 // before the first solve/verify
+    void set_device(int ordinal) { device = ordinal; }                 // first (or only) GPU; before the first solve/verify
+    // GPUs for one large instance (0 = every visible device); before the first solve/verify.  Default: ALLL_GPUS, else 1.
+    void set_gpus(int n) { n_gpus = n; gpus_set = true; }
+    int gpus_in_use() const { uint64_t info[4] = {1, 0, 0, 0}; if (handle && have_upload) alll_multi_info(handle, info); return (int)info[0]; }
+    double last_flatten_ms() const { return flatten_ms; }              // host time of the last flatten of Clause objects
     int last_status() const { return status; }                         // alll_status of the last solve
     const alll_stats &last_device_stats() const { return dev_stats; }  // device-timed ms, launches, ...
 
 private:
     int n_threads{};
-    alll_handle handle = nullptr;
-    int device = -1;
+    alll_multi_handle handle = nullptr;
+    int device = -1, n_gpus = 1;
+    bool gpus_set = false;
     uint64_t seed = 0;
     bool have_seed = false;
     uint64_t max_rounds = ~0ull;
     int status = ALLL_OK;
     alll_stats dev_stats{};
-    uint64_t uploaded_fingerprint = 0;
     bool have_upload = false;
+    double flatten_ms = 0.0;
+    // page-locked staging of the flattened clauses (grow-only): the H2D copy runs at the PCIe rate from here
+    uint32_t *stage_lit = nullptr;
+    uint64_t *stage_off = nullptr;
+    size_t stage_lit_cap = 0, stage_off_cap = 0;
 
     void check(int rc, const char *what) const
     {
-        if (rc != ALLL_OK) throw std::runtime_error(string(what) + ": " + alll_last_error(handle));
+        if (rc != ALLL_OK) throw std::runtime_error(string(what) + ": " + alll_multi_last_error(handle));
+    }
+    void check1(int rc, const char *what) const          // calls on the first device's own handle
+    {
+        if (rc != ALLL_OK) throw std::runtime_error(string(what) + ": " + alll_last_error(first()));
+    }
+    alll_handle first() const
+    {
+        alll_handle h = nullptr;
+        if (!handle || alll_multi_device_handle(handle, 0, &h) != ALLL_OK) throw std::runtime_error("SATInstance: no device handle");
+        return h;
     }
 
     void ensure_handle()
     {
         if (handle) return;
+        int32_t visible = 0;
+        alll_device_count(&visible);
+        if (visible <= 0) throw std::runtime_error("alll_multi_create: no CUDA device: the solver has no CPU fallback");
+        int want = n_gpus;
+        if (!gpus_set) {
+            if (const char *e = std::getenv("ALLL_GPUS")) want = (std::strcmp(e, "all") == 0) ? 0 : std::atoi(e);
+        }
+        if (want <= 0 || want > visible) want = visible;
+        const int base = device < 0 ? 0 : device;
+        vector<int32_t> devs;
+        for (int i = 0; i < want; i++) devs.push_back((int32_t)((base + i) % visible));
         alll_config cfg{};
-        cfg.device = device;
-        if (alll_create(&cfg, &handle) != ALLL_OK)
-            throw std::runtime_error(string("alll_create: ") + alll_last_error(nullptr));
+        if (alll_multi_create(devs.data(), (uint32_t)devs.size(), &cfg, &handle) != ALLL_OK)
+            throw std::runtime_error(string("alll_multi_create: ") + alll_multi_last_error(nullptr));
     }
 
-    // Concatenate the batches in order -> CSR; identical content is not uploaded twice (solve then verify).
+    template <typename U> void ensure_stage(U *&buf, size_t &cap, size_t count)
+    {
+        if (cap >= count) return;
+        if (buf) { alll_host_free(buf); buf = nullptr; cap = 0; }
+        void *p = nullptr;
+        const size_t want = count + count / 8 + 64;
+        if (alll_host_alloc(want * sizeof(U), &p) != ALLL_OK) throw std::runtime_error("alll_host_alloc failed");
+        buf = static_cast<U *>(p);
+        cap = want;
+    }
+
+    static unsigned flatten_threads(size_t m)
+    {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        return (unsigned)std::max<size_t>(1, std::min<size_t>(std::min(hw, 64u), m / 16384));
+    }
+    template <class F> static void run_threads(unsigned nt, F &&fn)      // fn(t)
+    {
+        vector<std::thread> th;
+        for (unsigned t = 1; t < nt; t++) th.emplace_back([&, t] { fn(t); });
+        fn(0u);
+        for (auto &x : th) x.join();
+    }
+
+    // Concatenate the batches in order -> CSR in page-locked memory.  Two passes over the caller's object graph, both
+    // split over the host's threads by clause position: widths (-> offsets by a prefix sum), then literals.  The pointer
+    // chase Clause -> vector -> data is what the reference pays in EVERY sweep (Clause.h:34-46); here it is paid once.
     void upload(vector<ClauseArray *> *clauses)
     {
-        vector<uint64_t> off(1, 0);
-        vector<uint32_t> lit;
+        const auto t0 = std::chrono::steady_clock::now();
         size_t m = 0;
-        for (auto batch : *clauses) m += batch->size();
-        off.reserve(m + 1);
-        for (auto batch : *clauses) {
-            for (auto cl : *batch) {
-                for (auto &l : *cl->literals) lit.push_back((uint32_t)l);
-                off.push_back(lit.size());
+        vector<size_t> batch_first;
+        for (auto batch : *clauses) { batch_first.push_back(m); m += batch->size(); }
+        batch_first.push_back(m);
+        ensure_stage(stage_off, stage_off_cap, m + 1);
+        const unsigned nt = flatten_threads(m);
+        // clause position -> (batch, index): each thread walks its own contiguous position range
+        auto for_range = [&](size_t p0, size_t p1, auto &&fn) {
+            size_t b = 0;
+            while (b + 1 < batch_first.size() - 1 && batch_first[b + 1] <= p0) ++b;
+            for (size_t p = p0; p < p1;) {
+                while (batch_first[b + 1] <= p) ++b;
+                const ClauseArray &arr = *(*clauses)[b];
+                const size_t end = std::min(p1, batch_first[b + 1]);
+                for (; p < end; ++p) fn(p, arr[p - batch_first[b]]);
             }
-        }
-        upload_flat(off, lit);
+        };
+        vector<uint64_t> part(nt + 1, 0);
+        run_threads(nt, [&](unsigned t) {
+            uint64_t sum = 0;
+            for_range(m * t / nt, m * (t + 1) / nt, [&](size_t p, const Clause<T> *cl) {
+                const uint64_t w = cl->literals->size();
+                stage_off[p + 1] = w;                         // widths for now
+                sum += w;
+            });
+            part[t + 1] = sum;
+        });
+        for (unsigned t = 0; t < nt; t++) part[t + 1] += part[t];
+        const uint64_t n_lit = part[nt];
+        ensure_stage(stage_lit, stage_lit_cap, (size_t)std::max<uint64_t>(n_lit, 1));
+        stage_off[0] = 0;
+        run_threads(nt, [&](unsigned t) {
+            uint64_t at = part[t];
+            for_range(m * t / nt, m * (t + 1) / nt, [&](size_t p, const Clause<T> *cl) {
+                const vector<T> &ls = *cl->literals;
+                uint32_t *dst = stage_lit + at;
+                for (size_t j = 0; j < ls.size(); j++) dst[j] = (uint32_t)ls[j];
+                at += ls.size();
+                stage_off[p + 1] = at;
+            });
+        });
+        flatten_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        upload_flat(stage_off, m, stage_lit);
     }
 
-    void upload_flat(const vector<uint64_t> &off, const vector<uint32_t> &lit)
+    void upload_flat(const uint64_t *off, size_t m, const uint32_t *lit)
     {
         ensure_handle();
-        uint64_t fp = 1469598103934665603ull ^ off.size();                    // FNV-1a over widths and literals
-        for (size_t c = 1; c < off.size(); c++) fp = (fp ^ (off[c] - off[c - 1])) * 1099511628211ull;
-        for (uint32_t l : lit) fp = (fp ^ l) * 1099511628211ull;
-        if (have_upload && fp == uploaded_fingerprint) return;
-        check(alll_upload_csr(handle, (uint64_t)n_vars, off.size() - 1, off.data(), lit.data()), "alll_upload_csr");
-        uploaded_fingerprint = fp;
+        have_upload = false;
+        check(alll_multi_upload_csr(handle, (uint64_t)n_vars, m, off, lit), "alll_multi_upload_csr");
         have_upload = true;
     }
 
-    Statistics *run_solve()
+    bool verify_uploaded()
     {
-        check(alll_set_assignment(handle, reinterpret_cast<const uint8_t *>(var_arr->vars)), "alll_set_assignment");
-        const uint64_t s = have_seed ? seed : (((uint64_t)std::random_device{}() << 32) | std::random_device{}());
-        status = alll_solve(handle, s, max_rounds, &dev_stats);
-        if (status != ALLL_OK && status != ALLL_MAX_ROUNDS) check(status, "alll_solve");
-        check(alll_get_assignment(handle, reinterpret_cast<uint8_t *>(var_arr->vars)), "alll_get_assignment");
+        check(alll_multi_set_assignment(handle, reinterpret_cast<const uint8_t *>(var_arr->vars)), "alll_multi_set_assignment");
+        int valid = 0;
+        check(alll_multi_verify(handle, &valid), "alll_multi_verify");
+        return valid != 0;
+    }
+
+    Statistics *make_statistics()
+    {
         auto *st = new Statistics;
         st->n_iterations = dev_stats.n_iterations;
         st->n_resamples = dev_stats.n_resamples;
@@ -257,6 +361,27 @@ private:
         st->n_thread_resamples.assign((size_t)n_threads, 0);
         st->n_thread_resamples[0] = dev_stats.n_resamples;
         return st;
+    }
+    uint64_t next_seed() { return have_seed ? seed : (((uint64_t)std::random_device{}() << 32) | std::random_device{}()); }
+
+    Statistics *run_solve()
+    {
+        check(alll_multi_set_assignment(handle, reinterpret_cast<const uint8_t *>(var_arr->vars)), "alll_multi_set_assignment");
+        status = alll_multi_solve(handle, next_seed(), max_rounds, &dev_stats);
+        if (status != ALLL_OK && status != ALLL_MAX_ROUNDS) check(status, "alll_multi_solve");
+        check(alll_multi_get_assignment(handle, reinterpret_cast<uint8_t *>(var_arr->vars)), "alll_multi_get_assignment");
+        return make_statistics();
+    }
+
+    // enumerated clauses produced on the device: first device only (the generator launcher is bound to one device)
+    Statistics *run_solve_single()
+    {
+        alll_handle h = first();
+        check1(alll_set_assignment(h, reinterpret_cast<const uint8_t *>(var_arr->vars)), "alll_set_assignment");
+        status = alll_solve(h, next_seed(), max_rounds, &dev_stats);
+        if (status != ALLL_OK && status != ALLL_MAX_ROUNDS) check1(status, "alll_solve");
+        check1(alll_get_assignment(h, reinterpret_cast<uint8_t *>(var_arr->vars)), "alll_get_assignment");
+        return make_statistics();
     }
 };
 

@@ -114,6 +114,13 @@ ALLL_API int alll_destroy(alll_handle h);
 /* Last error text of this handle (or of the failed alll_create when h == NULL). Never NULL. */
 ALLL_API const char *alll_last_error(alll_handle h);
 ALLL_API int alll_abi_version(void);
+/* Number of CUDA devices this process sees (0 without a usable device -- every other call then fails: no CPU fallback). */
+ALLL_API int alll_device_count(int32_t *n);
+/* Page-locked host memory for upload buffers (cudaMallocHost / cudaFreeHost): literals copied from it reach the full
+ * PCIe rate (about 5x pageable memory).  For callers that do not link the CUDA runtime themselves -- the drop-in
+ * SATInstance.h flattens the caller's Clause objects straight into such a buffer. */
+ALLL_API int alll_host_alloc(uint64_t bytes, void **out);
+ALLL_API int alll_host_free(void *p);
 
 /* ---- instance upload (the flattening of vector<ClauseArray*> that solve() receives) - */
 

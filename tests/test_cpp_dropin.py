@@ -180,3 +180,37 @@ def test_reference_style_user_program(lib, tmp_path):
     assert got["resamples"] % 5 == 0 and got["iterations"] >= 1 and got["iterations2"] >= 1
     head = dimacs.read_text().splitlines()
     assert head[0] == f"p cnf 3000 {got['n_clauses']}" and head[1].startswith(" ") and head[1].endswith(" 0")
+
+
+@pytest.mark.gpu
+def test_dropin_solve_over_several_gpus_from_cpp(lib, cli, oracle, tmp_path):
+    """The reference's parallel-resource knob reaches more than one GPU from C++ (round-1 gap): SATInstance::set_gpus /
+    ALLL_GPUS and the CLI's --gpus.  With a single GPU in the box the request is clamped to what is visible; the
+    statistics and the assignment for a fixed seed do not depend on the number of GPUs."""
+    import torch
+
+    subprocess.run([os.path.join(ROOT, "tools", "build_dropin_bench.sh")], check=True, capture_output=True)
+    exe = os.path.join(ROOT, "tools", "dropin_bench")
+    visible = torch.cuda.device_count()
+    runs = {}
+    for gpus in sorted({1, min(2, visible), visible}):
+        r = subprocess.run([exe, "--n", "200000", "--k", "7", "--d", "28", "--threads", "4", "--gpus", str(gpus), "--steps", "2"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        got = json.loads(r.stdout.strip().splitlines()[-1])
+        assert got["all_ok"] and got["gpus_in_use"] == gpus, got
+        runs[gpus] = got
+    assert len({(g["m"], g["sweeps_per_solve"]) for g in runs.values()}) == 1     # same trajectory on 1..N GPUs
+    # ALLL_GPUS for programs compiled unchanged (here: the reference-style user program), and the CLI flag
+    exe2 = build(str(tmp_path), "dropin_user", [os.path.join(ROOT, "tests", "cpp", "dropin_user.cpp")],
+                 extra=["-I" + os.path.join(PKG, "include")], libs=LINK)
+    r = subprocess.run([exe2], capture_output=True, text=True, env=dict(os.environ, ALLL_GPUS="all"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert json.loads(r.stdout.strip().splitlines()[-1])["valid"]
+    cnf = tmp_path / "cfg1.cnf"
+    cnf.write_bytes(open(os.path.join(GOLDEN, "dimacs", "cfg1.cnf"), "rb").read())
+    a = subprocess.run([cli, "--sat", str(cnf), "--seed", "5", "--gpus", "0"], capture_output=True, text=True)
+    b = subprocess.run([cli, "--sat", str(cnf), "--seed", "5", "--gpus", "1"], capture_output=True, text=True)
+    assert a.returncode == 0 and b.returncode == 0, a.stdout + a.stderr
+    it = lambda t: re.search(r"# Iterations\t= (\d+)\n# Resamples\t= (\d+)", t).groups()
+    assert it(a.stdout) == it(b.stdout) and a.stdout.rstrip().endswith("SATISFIABLE")
