@@ -87,6 +87,8 @@ cudaError_t launch_fill_u64(unsigned long long *p, uint64_t n, unsigned long lon
 
 // capi.cu: what the single-process multi-GPU layer (multi.cu) needs beyond the C ABI
 void *internal_p2p_region(alll_handle h);
+int internal_p2p_create_local(alll_handle h, uint32_t world, uint32_t rank, uint64_t cap_records);   // exchange region, no IPC export
+bool internal_csr_is_uniform(const uint64_t *off, uint64_t m);
 int internal_p2p_connect_ptrs(alll_handle h, void *const *regions);         // regions[rank]: exchange-region base of every rank
 bool internal_p2p_persistent_possible(alll_handle h);
 int internal_solve_p2p_begin(alll_handle h, uint64_t seed, uint64_t max_rounds, uint32_t epoch, uint64_t *launches0);   // enqueue only

@@ -91,6 +91,9 @@ struct alll_solver {
     uint8_t *d_p2p_region = nullptr;
     size_t p2p_region_bytes = 0;
     void *p2p_peer[MAX_SHARDS] = {};
+    uint8_t p2p_peer_ipc[MAX_SHARDS][64] = {};   // the IPC handle each open peer mapping came from
+    uint8_t p2p_ipc[64] = {};                    // IPC handle of our own region (valid while the allocation lives)
+    bool p2p_ipc_valid = false;
     P2PLink *d_p2p_link = nullptr;
     uint32_t p2p_world = 0, p2p_rank = 0;
     uint64_t p2p_cap = 0;
@@ -167,7 +170,7 @@ void release_buffers(alll_handle h)
     for (uint32_t q = 0; q < MAX_SHARDS; q++)
         if (h->p2p_peer[q]) { cudaIpcCloseMemHandle(h->p2p_peer[q]); h->p2p_peer[q] = nullptr; }
     dfree(h->d_p2p_region); dfree(h->d_p2p_link);
-    h->p2p_region_bytes = 0;
+    h->p2p_region_bytes = 0; h->p2p_ipc_valid = false;
     dfree(h->d_occ_off); dfree(h->d_occ); dfree(h->d_rows); dfree(h->d_visited); dfree(h->d_incr_tmp);
     dfree(h->d_gen_rec);
     if (h->d_flag) { if (h->flag_owner) cudaFree(h->d_flag); else if (!h->flag_borrowed) cudaIpcCloseMemHandle(h->d_flag); h->d_flag = nullptr; h->flag_borrowed = false; }
@@ -528,6 +531,38 @@ int copy_ids_out(alll_handle h, const uint32_t *d_slots, uint64_t n, uint32_t *o
     CK(launch_map_ids(clause_view(h), d_slots, (uint32_t)n_copy, h->d_ids_out, h->stream)); h->launches++;
     CK(cudaMemcpyAsync(out, h->d_ids_out, n_copy * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return ALLL_OK;
+}
+
+// Exchange region of this rank (sharded P2P mode): header + records[2 parities][world][cap][k+1].  The allocation is
+// kept across uploads of the same shape and only grows (a 1.28 GB / 8-GPU exchange region is 0.7 GB: cudaMalloc and a
+// full clear per upload would cost more than the upload); it is its own allocation because it may be exported over CUDA
+// IPC.  A retained region keeps its header: round flags are tagged with the solve's epoch, which the caller never
+// reuses on a link, so stale flags cannot match -- and peers may already be storing into it while we are still here.
+int p2p_region_setup(alll_handle h, uint32_t world, uint32_t rank, uint64_t cap_records, bool *fresh)
+{
+    if (!h) return ALLL_BAD_ARG;
+    if (!h->has_instance) return fail(h, ALLL_NO_INSTANCE, "no instance uploaded");
+    CK(cudaSetDevice(h->device));
+    if (!h->k || h->k > 8 || h->use_width || h->gen_mode) return fail(h, ALLL_BAD_ARG, "P2P sharding needs stored clauses of uniform width k <= 8");
+    if (world < 1 || world > MAX_SHARDS || rank >= world) return fail(h, ALLL_BAD_ARG, "bad world / rank");
+    if (cap_records == 0) return fail(h, ALLL_BAD_ARG, "cap_records == 0");
+    h->p2p_ready = false;
+    const size_t bytes = P2P_HEADER_BYTES + (size_t)2 * world * cap_records * (h->k + 1) * 4;
+    *fresh = false;
+    if (h->d_p2p_region && h->p2p_region_bytes < bytes) {
+        // (peers' mappings of the old allocation die with it; they re-open on their next alll_p2p_connect)
+        cudaFree(h->d_p2p_region);
+        h->d_p2p_region = nullptr; h->p2p_region_bytes = 0; h->p2p_ipc_valid = false;
+    }
+    if (!h->d_p2p_region) {
+        CK(cudaMalloc(&h->d_p2p_region, bytes));
+        CK(cudaMemset(h->d_p2p_region, 0, P2P_HEADER_BYTES));
+        CK(cudaDeviceSynchronize());                       // (the clear is ordered on the default stream, our kernels are not)
+        h->p2p_region_bytes = bytes;
+        *fresh = true;
+    }
+    h->p2p_world = world; h->p2p_rank = rank; h->p2p_cap = cap_records;
     return ALLL_OK;
 }
 
@@ -1245,28 +1280,17 @@ int alll_reset_stats(alll_handle h)
 
 int alll_p2p_create(alll_handle h, uint32_t world, uint32_t rank, uint64_t cap_records, uint8_t handle_out[64])
 {
-    NEED_INSTANCE();
-    if (!h->k || h->k > 8 || h->use_width || h->gen_mode) return fail(h, ALLL_BAD_ARG, "P2P sharding needs stored clauses of uniform width k <= 8");
-    if (world < 1 || world > MAX_SHARDS || rank >= world || !handle_out) return fail(h, ALLL_BAD_ARG, "bad world / rank");
-    if (cap_records == 0) return fail(h, ALLL_BAD_ARG, "cap_records == 0");
+    if (!handle_out) return h ? fail(h, ALLL_BAD_ARG, "handle_out == NULL") : ALLL_BAD_ARG;
+    bool fresh = false;
+    if (int rc = p2p_region_setup(h, world, rank, cap_records, &fresh)) return rc;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    h->p2p_ready = false;
-    for (uint32_t q = 0; q < MAX_SHARDS; q++)
-        if (h->p2p_peer[q]) { cudaIpcCloseMemHandle(h->p2p_peer[q]); h->p2p_peer[q] = nullptr; }
-    const size_t bytes = P2P_HEADER_BYTES + (size_t)2 * world * cap_records * (h->k + 1) * 4;
-    // IPC-exported memory must be its own allocation (not pooled with other buffers); it is kept across uploads of the
-    // same shape and only grows (a 1.28 GB / 8-GPU exchange region is 0.7 GB: cudaMalloc + a full clear per upload would
-    // cost more than the upload).  Only the header carries state between solves.
-    if (h->d_p2p_region && h->p2p_region_bytes < bytes) { cudaFree(h->d_p2p_region); h->d_p2p_region = nullptr; h->p2p_region_bytes = 0; }
-    if (!h->d_p2p_region) {
-        CK(cudaMalloc(&h->d_p2p_region, bytes));
-        h->p2p_region_bytes = bytes;
+    if (fresh || !h->p2p_ipc_valid) {
+        cudaIpcMemHandle_t ipc;
+        CK(cudaIpcGetMemHandle(&ipc, h->d_p2p_region));
+        std::memcpy(h->p2p_ipc, &ipc, 64);
+        h->p2p_ipc_valid = true;
     }
-    CK(cudaMemset(h->d_p2p_region, 0, P2P_HEADER_BYTES));
-    h->p2p_world = world; h->p2p_rank = rank; h->p2p_cap = cap_records;
-    cudaIpcMemHandle_t ipc;
-    CK(cudaIpcGetMemHandle(&ipc, h->d_p2p_region));
-    std::memcpy(handle_out, &ipc, 64);
+    std::memcpy(handle_out, h->p2p_ipc, 64);
     return ALLL_OK;
 }
 
@@ -1276,16 +1300,21 @@ int alll_p2p_connect(alll_handle h, const uint8_t *handles)
     if (!h->d_p2p_region || !handles) return fail(h, ALLL_BAD_ARG, "call alll_p2p_create first");
     void *bases[MAX_SHARDS] = {};
     for (uint32_t q = 0; q < h->p2p_world; q++) {
-        if (q == h->p2p_rank) bases[q] = h->d_p2p_region;
-        else {
-            cudaIpcMemHandle_t ipc;
-            std::memcpy(&ipc, handles + (size_t)q * 64, 64);
-            void *ptr = nullptr;
-            CK(cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess));
-            h->p2p_peer[q] = ptr;
-            bases[q] = ptr;
-        }
+        if (q == h->p2p_rank) { bases[q] = h->d_p2p_region; continue; }
+        // a peer that kept its region (same allocation => same IPC handle) keeps our mapping of it: opening and closing
+        // IPC mappings costs milliseconds, which an end-to-end step that re-uploads the instance would pay every time
+        if (h->p2p_peer[q] && std::memcmp(h->p2p_peer_ipc[q], handles + (size_t)q * 64, 64) == 0) { bases[q] = h->p2p_peer[q]; continue; }
+        if (h->p2p_peer[q]) { cudaIpcCloseMemHandle(h->p2p_peer[q]); h->p2p_peer[q] = nullptr; }
+        cudaIpcMemHandle_t ipc;
+        std::memcpy(&ipc, handles + (size_t)q * 64, 64);
+        void *ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess));
+        h->p2p_peer[q] = ptr;
+        std::memcpy(h->p2p_peer_ipc[q], handles + (size_t)q * 64, 64);
+        bases[q] = ptr;
     }
+    for (uint32_t q = h->p2p_world; q < MAX_SHARDS; q++)
+        if (h->p2p_peer[q]) { cudaIpcCloseMemHandle(h->p2p_peer[q]); h->p2p_peer[q] = nullptr; }
     return p2p_link_up(h, bases);
 }
 
@@ -1610,6 +1639,28 @@ int alll_layout_info(alll_handle h, uint64_t info[6])
 namespace alll {
 
 void *internal_p2p_region(alll_handle h) { return h ? h->d_p2p_region : nullptr; }
+
+// alll_p2p_create without the CUDA IPC export: the peers live in this process and address the region directly
+int internal_p2p_create_local(alll_handle h, uint32_t world, uint32_t rank, uint64_t cap_records)
+{
+    bool fresh = false;
+    return p2p_region_setup(h, world, rank, cap_records, &fresh);
+}
+
+// true iff every clause of the CSR has the width of the first one (all host threads)
+bool internal_csr_is_uniform(const uint64_t *off, uint64_t m)
+{
+    if (m == 0) return false;
+    const uint64_t k0 = off[1] - off[0];
+    const uint32_t nt = host_threads_for(m, 1u << 18);
+    std::vector<uint8_t> ok(nt, 1);
+    parallel_ranges(m, nt, [&](uint32_t t, uint64_t c0, uint64_t c1) {
+        bool u = true;
+        for (uint64_t c = c0; c < c1 && u; c++) u = off[c + 1] - off[c] == k0;
+        ok[t] = u;
+    });
+    return std::all_of(ok.begin(), ok.end(), [](uint8_t v) { return v != 0; });
+}
 
 int internal_p2p_connect_ptrs(alll_handle h, void *const *regions)
 {

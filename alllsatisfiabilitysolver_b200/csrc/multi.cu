@@ -10,8 +10,14 @@
 // Host code only; every clause evaluation, independent-set decision and resample happens in the kernels behind the
 // per-device handles.  No CPU fallback.
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -21,7 +27,46 @@
 
 using namespace alll;
 
+namespace {
+// One long-lived host thread per device slot (slot 0 is the caller's thread): the per-slot calls of an upload or a
+// batch solve run side by side without creating threads per call -- a fresh thread pays the CUDA runtime's per-thread
+// set-up on its first call, milliseconds that would otherwise land inside every end-to-end step.
+struct SlotWorker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool has_job = false, quit = false;
+    void loop()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv.wait(lk, [&] { return has_job || quit; });
+            if (quit) return;
+            lk.unlock();
+            job();
+            lk.lock();
+            has_job = false;
+            cv.notify_all();
+        }
+    }
+    void submit(std::function<void()> f)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        job = std::move(f);
+        has_job = true;
+        cv.notify_all();
+    }
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return !has_job; });
+    }
+};
+} // namespace
+
 struct alll_multi {
+    std::vector<std::unique_ptr<SlotWorker>> workers;   // [slot - 1]
     std::vector<alll_handle> h;
     std::vector<int> dev;
     bool distinct = true;        // every slot has a GPU of its own -> persistent kernels, one launcher thread
@@ -56,11 +101,9 @@ int mfail(alll_multi_handle mh, int status, const std::string &msg)
 int for_all_slots(alll_multi_handle mh, uint32_t n, const std::function<int(uint32_t)> &fn, bool allow_max_rounds = false)
 {
     std::vector<int> rc(n, ALLL_OK);
-    std::vector<std::thread> th;
-    th.reserve(n);
-    for (uint32_t r = 1; r < n; r++) th.emplace_back([&, r] { rc[r] = fn(r); });
+    for (uint32_t r = 1; r < n; r++) mh->workers[r - 1]->submit([&rc, &fn, r] { rc[r] = fn(r); });
     rc[0] = fn(0);
-    for (auto &t : th) t.join();
+    for (uint32_t r = 1; r < n; r++) mh->workers[r - 1]->wait();
     for (uint32_t r = 0; r < n; r++)
         if (rc[r] != ALLL_OK && !(allow_max_rounds && rc[r] == ALLL_MAX_ROUNDS))
             return mfail(mh, rc[r], "device slot " + std::to_string(r) + ": " + alll_last_error(mh->h[r]));
@@ -81,6 +124,19 @@ void split(uint64_t total, uint32_t parts, std::vector<uint64_t> &lo, std::vecto
 }
 
 uint32_t slots_in_use(alll_multi_handle mh) { return mh->sharded ? (uint32_t)mh->h.size() : 1u; }
+
+// ALLL_TRACE_HOST=1: host wall time of the stages of an upload / solve on stderr
+struct HostTrace {
+    const bool on = getenv("ALLL_TRACE_HOST") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void mark(const char *what)
+    {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[alll host] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
 
 #define MNEED_INSTANCE()                                                                       \
     do {                                                                                       \
@@ -148,6 +204,11 @@ int alll_multi_create(const int32_t *devices, uint32_t n_devices, const alll_con
         }
         mh->h.push_back(h);
     }
+    for (uint32_t r = 1; r < n_devices; r++) {
+        mh->workers.emplace_back(new SlotWorker);
+        SlotWorker *w = mh->workers.back().get();
+        w->th = std::thread([w] { w->loop(); });
+    }
     *out = mh;
     return ALLL_OK;
 }
@@ -155,6 +216,10 @@ int alll_multi_create(const int32_t *devices, uint32_t n_devices, const alll_con
 int alll_multi_destroy(alll_multi_handle mh)
 {
     if (!mh) return ALLL_OK;
+    for (auto &w : mh->workers) {
+        { std::lock_guard<std::mutex> lk(w->mu); w->quit = true; w->cv.notify_all(); }
+        w->th.join();
+    }
     // borrowed winner words first (they point into slot 0's allocation)
     for (size_t r = mh->h.size(); r-- > 0;) alll_destroy(mh->h[r]);
     delete mh;
@@ -175,6 +240,7 @@ int alll_multi_upload_fixedk(alll_multi_handle mh, uint64_t n_vars, uint64_t m, 
         mh->has_instance = true;
         return ALLL_OK;
     }
+    HostTrace tr;
     split(m, n, mh->lo, mh->hi);
     // records one rank may publish per round: a random start violates about m_r / 2^k clauses; a quarter of the range
     // holds that for every k >= 3 with a wide margin (an adversarial start that violates more ends in ALLL_CAPACITY)
@@ -184,13 +250,14 @@ int alll_multi_upload_fixedk(alll_multi_handle mh, uint64_t n_vars, uint64_t m, 
     if (int rc = for_all_slots(mh, n, [&](uint32_t r) {
             if (int e = alll_upload_fixedk(mh->h[r], n_vars, mh->hi[r] - mh->lo[r], k, lit + mh->lo[r] * k)) return e;
             if (int e = alll_set_id_base(mh->h[r], mh->lo[r])) return e;
-            uint8_t ipc[64];
-            return alll_p2p_create(mh->h[r], n, r, mh->cap_records, ipc);
+            return internal_p2p_create_local(mh->h[r], n, r, mh->cap_records);
         }))
         return rc;
+    tr.mark("upload + region (all slots)");
     void *regions[MAX_SHARDS] = {};
     for (uint32_t r = 0; r < n; r++) regions[r] = internal_p2p_region(mh->h[r]);
     for (uint32_t r = 0; r < n; r++) MCALL(r, internal_p2p_connect_ptrs(mh->h[r], regions));
+    tr.mark("link");
     mh->has_instance = true;
     return ALLL_OK;
 }
@@ -200,10 +267,11 @@ int alll_multi_upload_csr(alll_multi_handle mh, uint64_t n_vars, uint64_t m, con
     if (!mh) return ALLL_BAD_ARG;
     if (!off) return mfail(mh, ALLL_BAD_ARG, "off == NULL");
     // uniform width k <= 8 is what the sharded exchange carries; everything else goes to the first device alone
-    bool uniform = m > 0;
-    const uint64_t k0 = m ? off[1] - off[0] : 0;
-    for (uint64_t c = 0; c < m && uniform; c++) uniform = off[c + 1] - off[c] == k0;
-    if (uniform && k0 >= 1 && k0 <= 8 && mh->h.size() > 1) return alll_multi_upload_fixedk(mh, n_vars, m, (uint32_t)k0, lit + off[0]);
+    if (mh->h.size() > 1) {
+        const uint64_t k0 = m ? off[1] - off[0] : 0;
+        if (k0 >= 1 && k0 <= 8 && internal_csr_is_uniform(off, m))       // (all host threads; one device: alll_upload_csr scans itself)
+            return alll_multi_upload_fixedk(mh, n_vars, m, (uint32_t)k0, lit + off[0]);
+    }
     mh->has_instance = false;
     mh->sharded = false;
     mh->n_vars = n_vars; mh->m = m; mh->k = 0;
@@ -252,6 +320,7 @@ int alll_multi_solve(alll_multi_handle mh, uint64_t seed, uint64_t max_rounds, a
         return rc;
     }
     const uint32_t n = (uint32_t)mh->h.size();
+    HostTrace tr;
     mh->epoch++;
     std::vector<alll_stats> st(n);
     bool persistent = mh->distinct;
@@ -261,12 +330,14 @@ int alll_multi_solve(alll_multi_handle mh, uint64_t seed, uint64_t max_rounds, a
         // round flags on the device; nothing here blocks until all of them are running.)
         std::vector<uint64_t> l0(n, 0);
         for (uint32_t r = 0; r < n; r++) MCALL(r, internal_solve_p2p_begin(mh->h[r], seed, max_rounds, mh->epoch, &l0[r]));
+        tr.mark("solve: kernels enqueued");
         int worst = ALLL_OK;
         std::string msg;
         for (uint32_t r = 0; r < n; r++) {
             const int rc = internal_solve_p2p_end(mh->h[r], mh->m, l0[r], &st[r]);
             if (rc != ALLL_OK && rc != ALLL_MAX_ROUNDS && worst == ALLL_OK) { worst = rc; msg = "device slot " + std::to_string(r) + ": " + alll_last_error(mh->h[r]); }
         }
+        tr.mark("solve: collected");
         if (worst != ALLL_OK) return mfail(mh, worst, msg);
     } else {
         // slots share GPUs (or the persistent kernel does not fit): one kernel per phase, one host thread per slot
