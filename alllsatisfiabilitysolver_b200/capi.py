@@ -26,7 +26,7 @@ FLAG_FORCE_SHARDING = 64    # alll_multi_*: shard small instances too (tests)
 
 #: every symbol include/alll_b200.h declares (tests check the library exports exactly these)
 SYMBOLS = [
-    "alll_abi_version", "alll_create", "alll_destroy", "alll_last_error",
+    "alll_abi_version", "alll_create", "alll_destroy", "alll_last_error", "alll_device_count", "alll_host_alloc", "alll_host_free",
     "alll_upload_fixedk", "alll_upload_fixedk_device", "alll_upload_csr",
     "alll_set_assignment", "alll_get_assignment", "alll_randomize",
     "alll_eval", "alll_verify", "alll_round", "alll_solve",
@@ -134,6 +134,9 @@ def load() -> C.CDLL:
     L.alll_solve_p2p.argtypes = [vp, u64, u64, u64, u32, C.POINTER(StatsC)]
     L.alll_batch_upload.argtypes = [vp, u32, u64, u32, vp, vp]
     L.alll_batch_solve.argtypes = [vp, u32, vp, u64, C.c_int, vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+    L.alll_device_count.argtypes = [C.POINTER(C.c_int32)]
+    L.alll_host_alloc.argtypes = [u64, C.POINTER(vp)]
+    L.alll_host_free.argtypes = [vp]
     L.alll_multi_create.argtypes = [vp, u32, C.POINTER(Config), C.POINTER(vp)]
     L.alll_multi_destroy.argtypes = [vp]
     L.alll_multi_last_error.restype = C.c_char_p
