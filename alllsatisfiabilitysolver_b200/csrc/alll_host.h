@@ -19,8 +19,16 @@ cudaError_t launch_solve_persistent(const SweepParams &p, bool resident_all, uin
                                     uint8_t *state, uint32_t *s_slots, const MisScratch &sc, uint64_t n_vars, uint64_t seed,
                                     uint32_t max_rounds, uint32_t epoch, const IncrParams *incr, uint32_t visited_words,
                                     uint32_t incr_max_vars, cudaStream_t s);   // p.p2p != NULL: sharded solve; incr != NULL: incremental mode
-cudaError_t launch_sweep_csr(const uint64_t *off, const uint32_t *lit, uint64_t m, const uint32_t *bits,
-                             uint32_t *viol, Counters *ctr, uint32_t grid, cudaStream_t s);
+// csr.cu (variable-width clauses: layout build, warp-cooperative sweep, whole solve in one cooperative launch)
+struct CsrSweepParams;
+cudaError_t launch_csr_build(const uint64_t *off, uint64_t m, uint64_t n_lit, uint64_t l_pad, uint32_t *start, uint32_t *chunk_rank,
+                             cudaStream_t s);
+cudaError_t configure_sweep_csr(const CsrSweepParams &p);
+cudaError_t launch_sweep_csr(const CsrSweepParams &p, uint32_t grid, cudaStream_t s);
+cudaError_t configure_solve_persistent_csr(const CsrSweepParams &p, uint32_t kmax, int *ok_out);
+cudaError_t launch_solve_persistent_csr(const CsrSweepParams &p, uint32_t grid, const ClauseView &cv, uint32_t kmax, uint8_t *state,
+                                        uint32_t *s_slots, const MisScratch &sc, uint64_t n_vars, uint64_t seed, uint32_t max_rounds,
+                                        cudaStream_t s);
 
 // mis.cu
 cudaError_t mis_configure(int device, uint32_t kmax, uint32_t *grid_out);

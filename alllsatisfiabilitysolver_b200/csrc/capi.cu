@@ -14,6 +14,7 @@
 
 #include "../../include/alll_b200.h"
 #include "alll_host.h"
+#include "csr_body.cuh"
 
 using namespace alll;
 
@@ -51,8 +52,10 @@ struct alll_solver {
     uint32_t *d_planes = nullptr, *d_orig_id = nullptr;
     BucketSeg *d_segs = nullptr;
     uint64_t *d_off = nullptr;
-    uint32_t *d_csr_lit = nullptr;
-    uint64_t n_lit = 0;
+    uint32_t *d_csr_lit = nullptr;       // [csr_l_pad]: the literal array, padded to a multiple of 128 (>= 1 padding position)
+    uint64_t n_lit = 0, csr_l_pad = 0;
+    uint32_t *d_csr_start = nullptr, *d_csr_rank = nullptr;   // clause-start bits, clause rank of every 128-literal chunk (csr.cu)
+    uint32_t csr_staged_words = 0;       // assignment words staged in shared memory by the CSR sweep (0: lookups through L2)
     uint32_t *d_bits = nullptr;
     unsigned long long *d_claim = nullptr;
     bool persistent_ok = false;          // the persistent solve kernel fits this instance and device
@@ -160,7 +163,7 @@ void free_instance(alll_handle h)
 
 void release_buffers(alll_handle h)
 {
-    dfree(h->d_planes); dfree(h->d_orig_id); dfree(h->d_segs); dfree(h->d_off); dfree(h->d_csr_lit);
+    dfree(h->d_planes); dfree(h->d_orig_id); dfree(h->d_segs); dfree(h->d_off); dfree(h->d_csr_lit); dfree(h->d_csr_start); dfree(h->d_csr_rank);
     dfree(h->d_bits); dfree(h->d_claim); dfree(h->d_urec); dfree(h->d_viol); dfree(h->d_s); dfree(h->d_ids_out);
     dfree(h->d_state); dfree(h->d_bools); dfree(h->d_width); dfree(h->d_width_in); dfree(h->d_tmp_bkt); dfree(h->d_tmp_cnt); dfree(h->d_tmp_err); dfree(h->d_stage);
     dfree(h->d_sh_planes); dfree(h->d_sh_ids); dfree(h->d_sh_iota); dfree(h->d_sh_s); dfree(h->d_sh_state);
@@ -445,6 +448,16 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     return ALLL_OK;
 }
 
+CsrSweepParams csr_params(alll_handle h)
+{
+    CsrSweepParams cp{};
+    cp.lit = h->d_csr_lit; cp.start = h->d_csr_start; cp.chunk_rank = h->d_csr_rank;
+    cp.n_chunks = (uint32_t)(h->csr_l_pad / CSR_CHUNK); cp.m = (uint32_t)h->m;
+    cp.bits = h->d_bits; cp.n_words = h->n_words_alloc; cp.staged_words = h->csr_staged_words;
+    cp.viol = h->d_viol; cp.ctr = h->d_ctr;
+    return cp;
+}
+
 // records: leave {id, literals} records next to the violated list (an independent-set phase follows and will read them)
 SweepParams sweep_params(alll_handle h, uint32_t p2p_parity, uint32_t p2p_tag, uint32_t round, bool records)
 {
@@ -484,8 +497,7 @@ int enqueue_sweep(alll_handle h, uint32_t p2p_parity = 0, uint32_t p2p_tag = 0, 
         CK(launch_sweep_planes(sp, h->resident_all, h->sweep_grid, h->stream));
     } else {
         if (h->m == 0) return ALLL_OK;
-        const uint32_t grid = (uint32_t)std::min<uint64_t>((h->m + 255) / 256, (uint64_t)h->sm_count * 8);
-        CK(launch_sweep_csr(h->d_off, h->d_csr_lit, h->m, h->d_bits, h->d_viol, h->d_ctr, grid, h->stream));
+        CK(launch_sweep_csr(csr_params(h), h->sweep_grid, h->stream));
     }
     h->launches++;
     return ALLL_OK;
@@ -862,8 +874,16 @@ int alll_upload_csr(alll_handle h, uint64_t n_vars, uint64_t m, const uint64_t *
     for (uint64_t c = 0; c <= m; c++) off0[c] = off[c] - off[0];
     POOL(h->d_off, (m + 1) * 8);
     CK(cudaMemcpyAsync(h->d_off, off0.data(), (m + 1) * 8, cudaMemcpyHostToDevice, h->stream));
-    POOL(h->d_csr_lit, std::max<uint64_t>(h->n_lit, 1) * 4);
+    // device layout of the warp-cooperative sweep (csr_body.cuh): literals padded to whole 128-literal chunks with at
+    // least one padding position, one start bit per position, the clause rank of every chunk
+    h->csr_l_pad = align_up(h->n_lit + 1, CSR_CHUNK);
+    if (h->csr_l_pad / CSR_CHUNK > 0xFFFFFFF0ull) return fail(h, ALLL_BAD_ARG, "too many literals for the CSR layout");
+    POOL(h->d_csr_lit, h->csr_l_pad * 4);
     if (h->n_lit) CK(cudaMemcpyAsync(h->d_csr_lit, lit + off[0], h->n_lit * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->d_csr_lit + h->n_lit, 0, (h->csr_l_pad - h->n_lit) * 4, h->stream));
+    POOL(h->d_csr_start, h->csr_l_pad / 8);
+    POOL(h->d_csr_rank, (h->csr_l_pad / CSR_CHUNK + 1) * 4);
+    CK(launch_csr_build(h->d_off, m, h->n_lit, h->csr_l_pad, h->d_csr_start, h->d_csr_rank, h->stream)); h->launches += 2;
     POOL(h->d_tmp_err, 8);
     uint32_t *d_err = h->d_tmp_err;
     CK(cudaMemsetAsync(d_err, 0, 4, h->stream));
@@ -873,6 +893,17 @@ int alll_upload_csr(alll_handle h, uint64_t n_vars, uint64_t m, const uint64_t *
     CK(cudaStreamSynchronize(h->stream));
     if (err_flags) { free_instance(h); return fail(h, ALLL_BAD_ARG, "a literal references a variable >= n_vars"); }
     if (int rc = alloc_common(h, h->m)) return rc;
+    {
+        // stage the whole assignment in shared memory when it fits next to what the independent-set phases need
+        h->csr_staged_words = (size_t)h->n_words_alloc * 4 <= h->smem_budget ? h->n_words_alloc : 0u;
+        const CsrSweepParams cp = csr_params(h);
+        CK(configure_sweep_csr(cp));
+        h->sweep_grid = (uint32_t)std::max(1, h->sm_count);
+        int ok = 0, coop = 0;
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+        if (coop && m > 0) CK(configure_solve_persistent_csr(cp, h->kmax, &ok));
+        h->persistent_ok = ok != 0;
+    }
     CK(cudaStreamSynchronize(h->stream));
     h->has_instance = true;
     return ALLL_OK;
@@ -1075,6 +1106,37 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
         stats->n_kernel_launches = h->launches - launches0;
         stats->solve_ms = ms;
         stats->sweep_ms = (double)c.t_sweep_ns * 1e-6;            // as block 0 saw it (%globaltimer): sweep + its grid barrier
+        stats->between_sweeps_ms = (double)c.t_mis_ns * 1e-6;
+        stats->status = status;
+        return status;
+    }
+
+    if (h->persistent_ok && !h->k && h->m && !h->gen_mode && !(h->flags & ALLL_FLAG_HOST_ROUND_LOOP)) {
+        // CSR instance: the whole round loop in one cooperative launch as well (csr.cu: solve_persistent_csr_kernel)
+        if (max_rounds == 0) max_rounds = 1;
+        const uint32_t cap = (uint32_t)std::min<uint64_t>(max_rounds, 0xFFFFFFFFull);
+        CK(launch_solve_persistent_csr(csr_params(h), h->sweep_grid, clause_view(h), h->kmax, h->d_state, h->d_s, mis_scratch(h, false),
+                                       h->n_vars, seed, cap, h->stream));
+        h->launches++;
+        cudaEvent_t ev_end = h->ev[2 * MAX_TIMED_ROUNDS + 1];
+        CK(cudaEventRecord(ev_end, h->stream));
+        if (int rc = fetch_counters(h)) return rc;
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+        CK(launch_reset_counters(h->d_ctr, 0, h->stream)); h->launches++;
+        CK(cudaStreamSynchronize(h->stream));
+        const Counters &c = *h->h_ctr;
+        if (trace) print_phases(c, c.n_iterations);
+        const int status = c.done ? ALLL_OK : ALLL_MAX_ROUNDS;
+        stats->n_iterations = c.n_iterations;
+        stats->n_resamples = c.n_resamples;
+        stats->sum_mis_size = c.sum_mis;
+        stats->avg_mis_size = c.n_iterations ? c.sum_mis / c.n_iterations : 0;     // SATInstance.h:317
+        stats->n_clause_evals = h->m * c.n_iterations;
+        stats->n_luby_steps = c.n_luby_steps;
+        stats->n_kernel_launches = h->launches - launches0;
+        stats->solve_ms = ms;
+        stats->sweep_ms = (double)c.t_sweep_ns * 1e-6;
         stats->between_sweeps_ms = (double)c.t_mis_ns * 1e-6;
         stats->status = status;
         return status;
@@ -1628,8 +1690,8 @@ int alll_layout_info(alll_handle h, uint64_t info[6])
     info[1] = h->k;
     info[2] = h->n_buckets;
     info[3] = h->m_pad;
-    info[4] = h->k ? h->m_pad * h->k * 4 : h->n_lit * 4 + (h->m + 1) * 8;
-    info[5] = h->k ? sweep_planes_smem_bytes(h->bucket_words) : 0;
+    info[4] = h->k ? h->m_pad * h->k * 4 : h->csr_l_pad * 4 + h->csr_l_pad / 8 + (h->csr_l_pad / CSR_CHUNK + 1) * 4;   // bytes one sweep reads
+    info[5] = h->k ? sweep_planes_smem_bytes(h->bucket_words) : sweep_csr_smem_bytes(h->csr_staged_words, SWEEP_THREADS);
     return ALLL_OK;
 }
 

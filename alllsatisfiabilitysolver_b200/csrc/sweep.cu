@@ -66,37 +66,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_generic_kernel(
     if (comp.count) comp.flush();
 }
 
-// Variable-width fallback (general DIMACS input): one clause per thread over CSR, assignment words
-// gathered through L1/L2.  Not the roofline-graded path.
-__global__ void __launch_bounds__(256) sweep_csr_kernel(const uint64_t *__restrict__ off, const uint32_t *__restrict__ lit,
-                                                         uint64_t m, const uint32_t *__restrict__ bits,
-                                                         uint32_t *viol, Counters *ctr)
-{
-    if (__ldcg(&ctr->done)) return;
-    const uint32_t lane = threadIdx.x & 31u;                       // launched with 8 * WBUF words of dynamic smem
-    WarpCompactor comp{(threadIdx.x >> 5) * WBUF, viol, ctr, &ctr->n_viol, 0u, false, 0u, lane, nullptr};
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t m_round = (m + 31) / 32 * 32;
-    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < m_round; c += stride) {
-        uint32_t violated = 0;
-        if (c < m) {
-            violated = 1;
-            const uint64_t e = off[c + 1];
-            for (uint64_t j = off[c]; j < e; j++) {
-                const uint32_t l = __ldg(lit + j);
-                const uint32_t v = l >> 1;
-                if (((__ldg(bits + (v >> 5)) >> (v & 31u)) ^ l) & 1u) { violated = 0; break; }
-            }
-        }
-        const uint32_t bal = __ballot_sync(0xffffffffu, violated);
-        if (bal) {
-            if (violated) g_smem[comp.wbuf + comp.count + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)c;
-            comp.count += __popc(bal);
-            if (comp.count >= 32) comp.flush();
-        }
-    }
-    if (comp.count) comp.flush();
-}
+// (Variable-width clauses that stay in CSR form: csr.cu / csr_body.cuh -- the warp-cooperative sweep.)
 
 // ---- launchers ------------------------------------------------------------------------
 
@@ -141,13 +111,6 @@ cudaError_t configure_sweep_planes(const SweepParams &p, bool resident_all) { re
 cudaError_t launch_sweep_planes(const SweepParams &p, bool resident_all, uint32_t grid, cudaStream_t s)
 {
     return sweep_op(p, resident_all, grid, s, false);
-}
-
-cudaError_t launch_sweep_csr(const uint64_t *off, const uint32_t *lit, uint64_t m, const uint32_t *bits,
-                             uint32_t *viol, Counters *ctr, uint32_t grid, cudaStream_t s)
-{
-    sweep_csr_kernel<<<grid, 256, 8 * WBUF * 4, s>>>(off, lit, m, bits, viol, ctr);
-    return cudaGetLastError();
 }
 
 } // namespace alll

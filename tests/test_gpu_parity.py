@@ -522,3 +522,45 @@ def test_ragged_bucketed_private_variable_terminates(capi, oracle):
                 assert st.status == so.status == 0
                 assert (st.n_iterations, st.n_resamples) == (so.n_iterations, so.n_resamples)
                 assert np.array_equal(s.get_assignment(), v)
+
+
+@pytest.mark.parametrize("layout", [dict(flags=8), dict(flags=8, sweep_smem_bytes=1024), dict(flags=8 | 16), dict(flags=8 | 16, sweep_smem_bytes=1024)],
+                         ids=["csr_staged", "csr_l2_lookups", "csr_staged_host_round_loop", "csr_l2_host_round_loop"])
+def test_warp_cooperative_csr_sweep(capi, oracle, layout):
+    """The CSR path (csr_body.cuh: a warp streams 128 literals per step with 128-bit loads, clause boundaries from start
+    bits): violated sets bit-exact vs the oracle on mixed widths -- narrow (1..12, many clauses per chunk), wide (up to
+    300 literals: clauses spanning lanes, chunks and warp ranges), a single clause, literal counts around multiples of
+    128 -- then whole solves (persistent CSR kernel / host round loop) with oracle-identical statistics."""
+    rng = np.random.default_rng(12)
+    n = 20_000
+    cases = [(_ragged_instance(n, 9000, seed=1, wmin=1, wmax=12), "narrow"),
+             (_ragged_instance(n, 700, seed=2, wmin=1, wmax=300), "wide"),
+             (_ragged_instance(n, 1, seed=3, wmin=5, wmax=5), "single"),
+             (_ragged_instance(n, 64, seed=4, wmin=2, wmax=2), "exactly_128_literals"),
+             (_ragged_instance(n, 43, seed=5, wmin=3, wmax=3), "129_literals")]
+    with capi.Solver(**layout) as s:
+        for (off, lit), name in cases:
+            s.upload_csr(n, off, lit)
+            assert s.layout_info()["k"] == 0, name
+            for density in (0.5, 0.1, 0.0):
+                v = (rng.random(n) < density).astype(np.uint8)
+                s.set_assignment(v)
+                cnt, ids = s.eval()
+                want = oracle.sweep(off, lit, v)
+                assert cnt == len(want) and np.array_equal(np.sort(ids), want), (name, density)
+        # whole solves on a satisfiable mixed-width instance (widths 3..9 at low density)
+        off, lit = _ragged_instance(n, 5000, seed=6, wmin=3, wmax=9)
+        s.upload_csr(n, off, lit)
+        for seed in (0, 1, 2):
+            s.randomize(seed)
+            st = s.solve(seed, 500)
+            v = oracle.randomize(n, seed)
+            so = oracle.solve(n, off, lit, v, seed, max_rounds=500)
+            assert st.status == so.status == 0
+            assert (st.n_iterations, st.n_resamples, st.avg_mis_size, st.sum_mis_size) == \
+                   (so.n_iterations, so.n_resamples, so.avg_mis_size, so.sum_mis_size)
+            assert np.array_equal(s.get_assignment(), v) and oracle.verify(off, lit, v)
+            if not (layout["flags"] & 16):
+                assert st.n_kernel_launches <= 3          # one cooperative launch (+ counter resets)
+        ms, nv = s.time_sweep(3)
+        assert ms > 0
