@@ -829,7 +829,7 @@ int alll_upload_csr(alll_handle h, uint64_t n_vars, uint64_t m, const uint64_t *
             kmax = std::max(kmax, t_kmax[t]);
         }
     }
-    if (uniform && k0 <= MAX_K) return alll_upload_fixedk(h, n_vars, m, (uint32_t)k0, lit + off[0]);
+    if (uniform && k0 <= MAX_K && !(h->flags & ALLL_FLAG_FORCE_CSR)) return alll_upload_fixedk(h, n_vars, m, (uint32_t)k0, lit + off[0]);
     const uint64_t n_lit_in = m ? off[m] - off[0] : 0;
     if (m > 0 && kmax <= MAX_K && m * kmax <= 2 * n_lit_in + 1024 && !(h->flags & ALLL_FLAG_FORCE_CSR)) {
         // ragged input with modest spread: pad every clause to the widest one with copies of its first literal and

@@ -68,7 +68,7 @@ typedef struct {
  * is computed from the clauses containing them instead of a full sweep.  Results are bit-identical to the default
  * mode.  Bits 24..27: log2 of the switch-over divisor (default 3: incremental when <= m/8 clauses would be touched). */
 #define ALLL_FLAG_INCREMENTAL 4u
-#define ALLL_FLAG_FORCE_CSR 8u     /* keep ragged input on the CSR kernels instead of padding it onto the plane layout */
+#define ALLL_FLAG_FORCE_CSR 8u     /* alll_upload_csr: keep the input on the CSR kernels (warp-cooperative sweep) instead of the plane layout */
 #define ALLL_FLAG_INCR_DIVISOR_LOG2(x) ((uint32_t)(x) << 24)
 /* alll_solve runs the whole round loop of a plane-layout instance (k <= 8) as ONE cooperative kernel (sweep -> grid
  * barrier -> independent set + resample -> grid barrier, all rounds on the device).  This flag keeps the round loop on
