@@ -167,6 +167,9 @@ struct Counters {
     // [0] sweep entry  [1] MIS kernel entry  [2] |U| known  [3] gather + first claims done  [4] Luby steps done
     // [5] resample done  [6] round finished  [7] (steps << 8) | path (0 small, 1 cluster, 2 grid)
     unsigned long long dbg[32][8];
+    // ALLL_TRACE: inside the Luby steps of round 0 (grid-wide path), as block 0 / thread 0 sees them:
+    // [s][0] step entry  [1] own clauses decided (claim reads + stores issued)  [2] CTA reduced + live count published  [3] grid barrier passed
+    unsigned long long dbg_step[16][4];
 };
 constexpr uint32_t DBG_ROUNDS = 32;
 
@@ -199,8 +202,10 @@ constexpr int BATCH_PREEMPTED = 8;      // == ALLL_PREEMPTED: portfolio job stop
 // publishes count and arrival flag; the MIS kernel of each GPU waits for all flags of the round and works on its
 // own region.  Two parities suffice: a rank cannot start sweep r+2 before every peer has finished MIS r.
 struct P2PHeader {
-    unsigned int flag[2][MAX_SHARDS];    // written by peers: tag of the round whose records are complete
-    unsigned int count[2][MAX_SHARDS];   // written by peers: number of records of that round
+    // written by peers, one 8-byte store per (parity, source rank): (tag of the round whose records are complete) << 32 |
+    // number of records of that round.  Count and arrival flag travel in ONE store, so the publisher needs no
+    // system-scope fence between them (a fence costs an NVLink round trip on the critical path of every round).
+    unsigned long long cf[2][MAX_SHARDS];
     unsigned int abort;                  // == (epoch & 0xFFF) + 1 of the solve in which a peer overflowed its capacity or a wait timed out
                                          // (tagged by solve, so that a failed solve does not poison the next one on the same link)
 };

@@ -517,6 +517,14 @@ int enqueue_mis_resample(alll_handle h, uint64_t seed, uint32_t round, bool with
 // ALLL_TRACE: %globaltimer stamps written by the kernels (us relative to the sweep entry of each round)
 void print_phases(const Counters &c, uint64_t rounds)
 {
+    if (c.dbg_step[0][0]) {
+        for (int s = 0; s < 16 && c.dbg_step[s][0]; s++) {
+            const unsigned long long *d = c.dbg_step[s];
+            fprintf(stderr, "[alll steps] round 0 step %d: decide %.2f | reduce+publish %.2f | barrier %.2f us%s\n", s,
+                    (double)(d[1] - d[0]) * 1e-3, (double)(d[2] - d[1]) * 1e-3, (double)(d[3] - d[2]) * 1e-3,
+                    s + 1 < 16 && c.dbg_step[s + 1][0] ? "" : "  (last)");
+        }
+    }
     const uint64_t nr = std::min<uint64_t>(rounds, DBG_ROUNDS);
     for (uint64_t r = 0; r < nr; r++) {
         const unsigned long long *d = c.dbg[r];

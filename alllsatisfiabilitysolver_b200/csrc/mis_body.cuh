@@ -220,7 +220,7 @@ __device__ __forceinline__ uint32_t p2p_wait(const MisParams &p, uint32_t *s_pre
         unsigned int why = 0;                         // 2: a peer never published this round in time, 3: a peer aborted
         const unsigned int aval = (p.p2p_tag >> 20) + 1u;     // abort words are tagged with the solve's epoch
         for (uint32_t q = 0; q < L.world && !bad; q++) {
-            while (*(volatile unsigned int *)&me->flag[p.p2p_parity][q] != p.p2p_tag) {
+            while ((uint32_t)(*(volatile unsigned long long *)&me->cf[p.p2p_parity][q] >> 32) != p.p2p_tag) {
                 if (*(volatile unsigned int *)&me->abort == aval) { bad = true; why = 3; break; }
                 if (clock64() - t_start > L.timeout_cycles) {
                     // tell the peers as well: they would otherwise wait for OUR next round until their own time-out
@@ -236,7 +236,7 @@ __device__ __forceinline__ uint32_t p2p_wait(const MisParams &p, uint32_t *s_pre
         uint32_t run = 0;
         for (uint32_t q = 0; q < L.world; q++) {
             s_prefix[q] = run;
-            const unsigned int cnt = *(volatile unsigned int *)&me->count[p.p2p_parity][q];
+            const unsigned int cnt = (unsigned int)*(volatile unsigned long long *)&me->cf[p.p2p_parity][q];
             if (cnt > L.cap) bad = true;
             run += cnt;
         }
@@ -298,9 +298,11 @@ __device__ __noinline__ void mis_resample_body(const MisParams &p, uint32_t roun
     if (first == 0) stamp(p, round, 3);
 
     uint32_t step = 0;
+    const bool trace_steps = first == 0 && round == 0;
     for (;;) {
         const uint32_t cur = step & 1u, nxt = cur ^ 1u;
         const bool wrap = (step + 1) % TAGS == 0;
+        if (trace_steps && step < 16) p.ctr->dbg_step[step][0] = global_ns();
         // wrap: the tag of step+1 wraps to the largest value, stale claims in `nxt` would undercut fresh ones, so
         // in a pass of its own the still-undecided clauses clear what they touch there (nobody reads `nxt` now)
         for (uint32_t pass = wrap ? 0u : 1u; pass < 2u; pass++) {
@@ -362,13 +364,16 @@ __device__ __noinline__ void mis_resample_body(const MisParams &p, uint32_t roun
                 else p.state[i] = (uint8_t)st;
             }
             if (pass == 0u) { bar.sync(); continue; }
+            if (trace_steps && step < 16) p.ctr->dbg_step[step][1] = global_ns();
             if (live) atomicAdd(&s_live, live);
         }
         __syncthreads();
         if (threadIdx.x == 0 && s_live) gm::red_add(&p.ctr->step_live[(step + 1) & 63u], s_live);
         // the slot of step+3 (mod 64) is next written two steps from now: clear it while nobody touches it
         if (first == 0) p.ctr->step_live[(step + 3) & 63u] = 0;
+        if (trace_steps && step < 16) p.ctr->dbg_step[step][2] = global_ns();
         bar.sync();
+        if (trace_steps && step < 16) p.ctr->dbg_step[step][3] = global_ns();
         step++;
         if (ld_u32(&p.ctr->step_live[step & 63u]) == 0) break;      // nobody claimed for this step: all decided
     }

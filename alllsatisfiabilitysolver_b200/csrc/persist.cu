@@ -64,10 +64,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(cons
             // count + arrival flag everywhere, then wait for every peer's flag of this round
             if (lead) {
                 const P2PLink &L = *sp.p2p;
-                const unsigned int total = gm::ld_cg(&c->n_viol_pp[par]);
-                for (uint32_t q = 0; q < L.world; q++) L.hdr[q]->count[par][L.rank] = total;
-                __threadfence_system();
-                for (uint32_t q = 0; q < L.world; q++) *(volatile unsigned int *)&L.hdr[q]->flag[par][L.rank] = tag;
+                // (every CTA's record stores were fenced at system scope before the grid barrier above)
+                const unsigned long long word = ((unsigned long long)tag << 32) | gm::ld_cg(&c->n_viol_pp[par]);
+                for (uint32_t q = 0; q < L.world; q++) *(volatile unsigned long long *)&L.hdr[q]->cf[par][L.rank] = word;
             }
             n_u = p2p_wait(mp, s_prefix);
         } else {

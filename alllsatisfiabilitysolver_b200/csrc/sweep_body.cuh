@@ -133,10 +133,8 @@ __device__ __forceinline__ void p2p_publish(const SweepParams &p)
     p.ctr->cta_done = 0;                                   // ready for the next launch (stream-ordered)
     __threadfence_system();
     const P2PLink &L = *p.p2p;
-    const unsigned int total = __ldcg(&p.ctr->n_viol);
-    for (uint32_t q = 0; q < L.world; q++) L.hdr[q]->count[p.p2p_parity][L.rank] = total;
-    __threadfence_system();
-    for (uint32_t q = 0; q < L.world; q++) *(volatile unsigned int *)&L.hdr[q]->flag[p.p2p_parity][L.rank] = p.p2p_tag;
+    const unsigned long long word = ((unsigned long long)p.p2p_tag << 32) | __ldcg(&p.ctr->n_viol);
+    for (uint32_t q = 0; q < L.world; q++) *(volatile unsigned long long *)&L.hdr[q]->cf[p.p2p_parity][L.rank] = word;
 }
 
 // Assignment words are read with ld.global.cg (L2, coherent), never through the non-coherent path (__ldg / ld.global.nc):
