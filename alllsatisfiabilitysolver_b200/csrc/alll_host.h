@@ -23,7 +23,7 @@ cudaError_t launch_solve_persistent(const SweepParams &p, bool resident_all, uin
 struct CsrSweepParams;
 cudaError_t launch_csr_build(const uint64_t *off, uint64_t m, uint64_t n_lit, uint64_t l_pad, uint32_t *start, uint32_t *chunk_rank,
                              cudaStream_t s);
-cudaError_t configure_sweep_csr(const CsrSweepParams &p);
+cudaError_t configure_sweep_csr(const CsrSweepParams &p, int *ctas_per_sm);
 cudaError_t launch_sweep_csr(const CsrSweepParams &p, uint32_t grid, cudaStream_t s);
 cudaError_t configure_solve_persistent_csr(const CsrSweepParams &p, uint32_t kmax, int *ok_out);
 cudaError_t launch_solve_persistent_csr(const CsrSweepParams &p, uint32_t grid, const ClauseView &cv, uint32_t kmax, uint8_t *state,

@@ -74,7 +74,7 @@ struct alll_solver {
     RoundNote *h_ring = nullptr;         // pinned [ROUNDS_IN_FLIGHT]: written by the MIS kernels, polled by the round loop
     unsigned long long seq = 0;          // last sequence number handed to a round
     cudaEvent_t ev_round[ROUNDS_IN_FLIGHT] = {};
-    uint32_t sweep_grid = 1, mis_grid = 1;
+    uint32_t sweep_grid = 1, mis_grid = 1, csr_grid = 1;
     std::vector<cudaEvent_t> ev;         // 2 * MAX_TIMED_ROUNDS + 2
 
     // Device buffers are kept across uploads and only grow: re-uploading an instance of the same shape (the
@@ -497,7 +497,7 @@ int enqueue_sweep(alll_handle h, uint32_t p2p_parity = 0, uint32_t p2p_tag = 0, 
         CK(launch_sweep_planes(sp, h->resident_all, h->sweep_grid, h->stream));
     } else {
         if (h->m == 0) return ALLL_OK;
-        CK(launch_sweep_csr(csr_params(h), h->sweep_grid, h->stream));
+        CK(launch_sweep_csr(csr_params(h), h->csr_grid, h->stream));
     }
     h->launches++;
     return ALLL_OK;
@@ -905,8 +905,10 @@ int alll_upload_csr(alll_handle h, uint64_t n_vars, uint64_t m, const uint64_t *
         // stage the whole assignment in shared memory when it fits next to what the independent-set phases need
         h->csr_staged_words = (size_t)h->n_words_alloc * 4 <= h->smem_budget ? h->n_words_alloc : 0u;
         const CsrSweepParams cp = csr_params(h);
-        CK(configure_sweep_csr(cp));
-        h->sweep_grid = (uint32_t)std::max(1, h->sm_count);
+        int per_sm = 1;
+        CK(configure_sweep_csr(cp, &per_sm));
+        h->sweep_grid = (uint32_t)std::max(1, h->sm_count);                       // persistent CSR solve: one CTA per SM
+        h->csr_grid = (uint32_t)std::max(1, h->sm_count * std::min(per_sm, 4));   // stand-alone sweep: as many as fit
         int ok = 0, coop = 0;
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
         if (coop && m > 0) CK(configure_solve_persistent_csr(cp, h->kmax, &ok));

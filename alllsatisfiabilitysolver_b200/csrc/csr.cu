@@ -59,17 +59,24 @@ cudaError_t launch_csr_build(const uint64_t *off, uint64_t m, uint64_t n_lit, ui
 
 // ---- the sweep as a kernel of its own (alll_eval / alll_round / host round loop / alll_time_sweep) ---------------
 template <bool STAGED>
-__global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_csr_warp_kernel(const CsrSweepParams p)
+__global__ void __launch_bounds__(SWEEP_THREADS, STAGED ? 1 : 2) sweep_csr_warp_kernel(const CsrSweepParams p)
 {
     if (__ldcg(&p.ctr->done)) return;
     sweep_csr_body<STAGED>(p, &p.ctr->n_viol);
 }
 
-cudaError_t configure_sweep_csr(const CsrSweepParams &p)
+// ctas_per_sm: how many CTAs of the stand-alone sweep fit one SM (the L2-lookup variant is latency-bound: more resident
+// warps hide more lookups; the staged variant owns the shared memory and runs one CTA per SM)
+cudaError_t configure_sweep_csr(const CsrSweepParams &p, int *ctas_per_sm)
 {
     const size_t smem = sweep_csr_smem_bytes(p.staged_words, SWEEP_THREADS);
-    return p.staged_words ? cudaFuncSetAttribute(sweep_csr_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                          : cudaFuncSetAttribute(sweep_csr_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = p.staged_words ? cudaFuncSetAttribute(sweep_csr_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                   : cudaFuncSetAttribute(sweep_csr_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = p.staged_words ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, sweep_csr_warp_kernel<true>, SWEEP_THREADS, smem)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, sweep_csr_warp_kernel<false>, SWEEP_THREADS, smem);
+    if (e == cudaSuccess && *ctas_per_sm < 1) *ctas_per_sm = 1;
+    return e;
 }
 
 cudaError_t launch_sweep_csr(const CsrSweepParams &p, uint32_t grid, cudaStream_t s)

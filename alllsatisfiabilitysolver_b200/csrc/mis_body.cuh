@@ -117,6 +117,12 @@ __device__ __forceinline__ void st(unsigned long long *p, unsigned long long v)
 {
     asm volatile("st.global.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "l"(v));
 }
+// both claim words of a variable (even / odd Luby steps, one aligned 16-byte pair) in ONE store: the independent-set
+// phases of large violated sets are bound by the number of L2 write / atomic operations, not by bytes
+__device__ __forceinline__ void st_pair(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.global.v2.u64 [%0], {%1, %1};" ::"l"(__cvta_generic_to_global(p)), "l"(v));
+}
 __device__ __forceinline__ void st(uint32_t *p, uint32_t v)
 {
     asm volatile("st.global.u32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(v));
@@ -347,11 +353,7 @@ __device__ __noinline__ void mis_resample_body(const MisParams &p, uint32_t roun
                     taken |= c == CLAIM_TAKEN;
                 }
                 if (win) {
-                    for (uint32_t j = 0; j < k; j++) {
-                        unsigned long long *c = pair(j);
-                        gm::st(c, CLAIM_TAKEN);
-                        gm::st(c + 1, CLAIM_TAKEN);
-                    }
+                    for (uint32_t j = 0; j < k; j++) gm::st_pair(pair(j), CLAIM_TAKEN);
                     append_s(p, slot_of(p, i));
                 } else if (!taken) {
                     const unsigned long long next_key = claim_key(step + 1, prio, id);
@@ -398,8 +400,7 @@ __device__ __noinline__ void mis_resample_body(const MisParams &p, uint32_t roun
         }
         for (uint32_t j = 0; j < k; j++) {
             const uint32_t v = (cached ? mis_smem[base + j * bd] : src_lit(p, s, j)) >> 1;
-            gm::st(&claim[2 * (uint64_t)v], CLAIM_FREE);
-            gm::st(&claim[2 * (uint64_t)v + 1], CLAIM_FREE);
+            gm::st_pair(&claim[2 * (uint64_t)v], CLAIM_FREE);
             if (st == IN_SET) resample_var(p, round, v);
         }
         if (st == IN_SET) resampled += k;                          // SATInstance.h:363 counts literals->size()

@@ -115,7 +115,10 @@ def test_small_and_unshardable_instances_fall_back_to_the_first_device(capi, ora
 def test_exchange_capacity_overflow_is_reported(capi):
     """A start that violates far more clauses than the exchange slots hold ends the solve with ALLL_CAPACITY on every
     rank (abort word), not with a hang or a wrong result."""
-    n, m, k = 600_000, 200_000, 3
+    # (k = 5: the random start of the second solve violates m / 32 = 6 k clauses in total -- simulated ranks sharing ONE
+    # GPU must stay on the cluster-sized independent-set path, |U| <= 8192: a grid-wide cooperative phase of one rank
+    # cannot become resident while the other rank's kernel spins on the same GPU waiting for it)
+    n, m, k = 1_000_000, 200_000, 5
     lits = (np.arange(m * k, dtype=np.uint32).reshape(m, k) * 2)          # all-positive, disjoint clauses
     with capi.MultiSolver([0, 0]) as ms:
         ms.upload_fixedk(n, lits)

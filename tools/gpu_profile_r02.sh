@@ -23,4 +23,11 @@ ncu --set full --clock-control none -k regex:solve_persistent_kernel -s 1 -c 1 -
     python tools/prof_sweep.py --workload cfg3 --reps 1 --solves 2 --max-rounds 40 > $O/r02_ncu_cfg3.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:sweep_csr_warp -s 2 -c 1 -f -o $O/r02_csr_sweep \
     python tools/prof_csr.py --reps 4 > $O/r02_ncu_csr.log 2>&1
-ls -la $O | tail -30
+# the reports stay on the box (gpurun_out is capped at 64 MiB): keep their text / csv pages
+for r in r02_cfg4_persistent r02_cfg2_persistent r02_cfg3_persistent r02_csr_sweep; do
+    ncu -i $O/$r.ncu-rep --page details > $O/${r}_details.txt 2>&1
+    ncu -i $O/$r.ncu-rep --page raw --csv > $O/${r}_raw.csv 2>&1
+done
+ncu -i $O/r02_csr_sweep.ncu-rep --page source --csv > $O/r02_csr_sweep_source.csv 2>&1
+rm -f $O/*.ncu-rep
+ls -la $O | tail -40
