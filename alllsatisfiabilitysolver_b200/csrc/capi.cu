@@ -745,8 +745,13 @@ int alll_create(const alll_config *cfg, alll_handle *out)
     for (auto &ev : s->ev_chunk)
         if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaEventCreate failed"));
     if (cudaMalloc(&s->d_ctr, sizeof(Counters)) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaMalloc(counters) failed"));
+    if (cudaMemset(s->d_ctr, 0, sizeof(Counters)) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaMemset(counters) failed"));
     if (cudaMallocHost(&s->h_ctr, sizeof(Counters)) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaMallocHost failed"));
     if (cudaMallocHost(&s->h_ring, sizeof(RoundNote) * ROUNDS_IN_FLIGHT) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaMallocHost failed"));
+    // page-locked memory is handed out uncleared and is recycled between handles: a stale sequence number left by an
+    // earlier handle's first round would look like OUR first round having retired (the host round loops poll `seq`)
+    std::memset(s->h_ring, 0, sizeof(RoundNote) * ROUNDS_IN_FLIGHT);
+    std::memset(s->h_ctr, 0, sizeof(Counters));
     for (auto &ev : s->ev_round)
         if (cudaEventCreate(&ev) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaEventCreate failed"));
     s->ev.resize(2 * MAX_TIMED_ROUNDS + 2);
