@@ -39,7 +39,8 @@ struct Mapped {                         // read-only view of the whole file
         void *p = mmap(nullptr, size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
         close(fd);
         if (p == MAP_FAILED) return;
-        madvise(p, size, MADV_SEQUENTIAL | MADV_WILLNEED);
+        madvise(p, size, MADV_SEQUENTIAL);       // (advice values are enumerators, not flags: one call each)
+        madvise(p, size, MADV_WILLNEED);
         data = static_cast<const char *>(p);
         ok = true;
     }

@@ -48,7 +48,7 @@ struct alll_solver {
     uint32_t n_words_alloc = 0, bucket_words = 0, n_buckets = 1, n_tiles = 0;
     bool resident_all = true;
     uint32_t min_resident = 0;           // measured by the bucketing pass; selects the sweep specialisation
-    uint32_t resident_cap = RESIDENT_CAP; // literals per clause placed as bucket-resident (flags bits 28..31, 0 = default)
+    uint32_t resident_cap = RESIDENT_CAP; // literals per clause placed as bucket-resident (compile-time choice: 2 / 3 / 4 were measured, profiles/)
     uint32_t *d_planes = nullptr, *d_orig_id = nullptr;
     BucketSeg *d_segs = nullptr;
     uint64_t *d_off = nullptr;
@@ -308,11 +308,7 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     CK(cudaMemcpyAsync(d_err, err_init, 8, cudaMemcpyHostToDevice, h->stream));
     std::vector<BucketSeg> segs(h->n_buckets);
     h->min_resident = 0;
-    {
-        const uint32_t rc = (h->flags >> 28) & 0xFu;
-        (void)rc;                                        // (the 2 / 4 variants were measured and removed: see profiles/)
-        h->resident_cap = RESIDENT_CAP;
-    }
+    h->resident_cap = RESIDENT_CAP;
 
     // clause ranges of the first pass: one, or (host-buffer upload) one per H2D chunk of about 64 MB
     std::vector<uint64_t> cut{0, m};

@@ -156,11 +156,10 @@ static size_t persistent_smem_bytes(uint32_t bucket_words, uint32_t kmax)
     return b;
 }
 
-static void persistent_fill(const SweepParams &p, MisParams &mp, size_t smem)
+static void persistent_fill(MisParams &mp, size_t smem)
 {
     mp.cache_items = (uint32_t)((smem / 4 / SWEEP_THREADS) / mis_cache_words(mp.kmax));
     mp.small_ok = mis_small_words(SWEEP_THREADS, mp.kmax) * 4 <= smem ? 1u : 0u;
-    (void)p;
 }
 
 // ok_out: 1 when the instance can be solved by the persistent kernel on this device (k <= 8, one CTA per SM fits)
@@ -188,7 +187,7 @@ cudaError_t launch_solve_persistent(const SweepParams &p, bool resident_all, uin
     mp.claim = sc.claim;
     mp.n_vars = n_vars; mp.bits = const_cast<uint32_t *>(p.bits); mp.ctr = p.ctr; mp.seed = seed; mp.kmax = kmax;
     mp.urec = sc.urec; mp.urec_cap = sc.urec_cap;
-    persistent_fill(p, mp, smem);
+    persistent_fill(mp, smem);
     mp.incr_max_vars = incr ? incr_max_vars : 0u;
     const IncrParams no_incr{};
     PersistOp op{p, grid, smem, s, &mp, max_rounds, epoch, incr ? incr : &no_incr, incr ? visited_words : 0u, nullptr};
