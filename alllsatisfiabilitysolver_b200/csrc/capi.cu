@@ -35,6 +35,7 @@ struct alll_solver {
     cudaStream_t copy_stream = nullptr;  // H2D of a host-buffer upload, chunk by chunk ahead of the layout kernels
     cudaEvent_t ev_chunk[33] = {};       // [i]: chunk i has arrived; [32]: the layout stream is done with the staging buffer
     int sm_count = 0;
+    int clock_khz = 0;                   // SM clock (kHz) for turning a time-out into clock64 ticks
     uint32_t smem_budget = DEFAULT_SWEEP_SMEM;
     uint32_t flags = 0;
     std::string err;
@@ -592,8 +593,7 @@ int p2p_link_up(alll_handle h, void *const *bases)
         // enough to turn a dead peer into an error instead of a hang
         double ms = 20000.0;
         if (const char *e = getenv("ALLL_P2P_TIMEOUT_MS")) { const double v = atof(e); if (v > 0.0) ms = v; }
-        int khz = 0;
-        if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device) != cudaSuccess || khz <= 0) khz = 2000000;
+        const int khz = h->clock_khz > 0 ? h->clock_khz : 2000000;     // (cached at alll_create: the attribute query costs milliseconds)
         link.timeout_cycles = (long long)(ms * (double)khz);
     }
     for (uint32_t q = 0; q < h->p2p_world; q++) {
@@ -729,6 +729,7 @@ int alll_create(const alll_config *cfg, alll_handle *out)
     alll_solver *s = new alll_solver;
     s->device = device;
     s->sm_count = prop.multiProcessorCount;
+    s->clock_khz = prop.clockRate;
     s->flags = cfg ? cfg->flags : 0;
     const uint32_t wbuf_bytes = (SWEEP_THREADS / 32) * (WBUF + QBUF) * 4;
     const uint32_t max_bits = (uint32_t)prop.sharedMemPerBlockOptin - wbuf_bytes - 1024;

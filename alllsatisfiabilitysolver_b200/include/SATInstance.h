@@ -285,9 +285,12 @@ private:
         for (auto &x : th) x.join();
     }
 
-    // Concatenate the batches in order -> CSR in page-locked memory.  Two passes over the caller's object graph, both
-    // split over the host's threads by clause position: widths (-> offsets by a prefix sum), then literals.  The pointer
-    // chase Clause -> vector -> data is what the reference pays in EVERY sweep (Clause.h:34-46); here it is paid once.
+    // Concatenate the batches in order -> CSR in page-locked memory, split over the host's threads by clause position.
+    // The pointer chase Clause -> vector -> data is what the reference pays in EVERY sweep (Clause.h:34-46); here it
+    // is paid once per solve, with the next clauses' three levels software-prefetched (the chase is latency-bound).
+    // Fast path: one pass that assumes every clause has the width of the first one and writes literals to their final
+    // place; the first clause of another width sends the whole flatten down the general two-pass path
+    // (widths -> offsets by a prefix sum -> literals).
     void upload(vector<ClauseArray *> *clauses)
     {
         const auto t0 = std::chrono::steady_clock::now();
@@ -304,34 +307,70 @@ private:
             for (size_t p = p0; p < p1;) {
                 while (batch_first[b + 1] <= p) ++b;
                 const ClauseArray &arr = *(*clauses)[b];
+                const size_t base = batch_first[b], n_in = arr.size();
                 const size_t end = std::min(p1, batch_first[b + 1]);
-                for (; p < end; ++p) fn(p, arr[p - batch_first[b]]);
+                for (; p < end; ++p) {
+                    const size_t i = p - base;
+                    // three-stage prefetch: Clause object, its vector header, the vector's storage
+                    if (i + 24 < n_in) __builtin_prefetch(arr[i + 24]);
+                    if (i + 16 < n_in) __builtin_prefetch(arr[i + 16]->literals);
+                    if (i + 8 < n_in) __builtin_prefetch(arr[i + 8]->literals->data());
+                    if (!fn(p, arr[i])) return false;
+                }
             }
+            return true;
         };
-        vector<uint64_t> part(nt + 1, 0);
-        run_threads(nt, [&](unsigned t) {
-            uint64_t sum = 0;
-            for_range(m * t / nt, m * (t + 1) / nt, [&](size_t p, const Clause<T> *cl) {
-                const uint64_t w = cl->literals->size();
-                stage_off[p + 1] = w;                         // widths for now
-                sum += w;
+        bool done = false;
+        if (m > 0) {
+            size_t b0 = 0;
+            while ((*clauses)[b0]->empty()) ++b0;
+            const uint64_t w0 = (*(*clauses)[b0])[0]->literals->size();
+            if (w0 > 0 && w0 <= 32) {
+                ensure_stage(stage_lit, stage_lit_cap, m * w0);
+                vector<char> uniform(nt, 1);
+                run_threads(nt, [&](unsigned t) {
+                    uniform[t] = for_range(m * t / nt, m * (t + 1) / nt, [&](size_t p, const Clause<T> *cl) {
+                        const vector<T> &ls = *cl->literals;
+                        if (ls.size() != w0) return false;
+                        uint32_t *dst = stage_lit + p * w0;
+                        for (size_t j = 0; j < w0; j++) dst[j] = (uint32_t)ls[j];
+                        stage_off[p + 1] = (p + 1) * w0;
+                        return true;
+                    });
+                });
+                done = true;
+                for (char u : uniform) done = done && u;
+                stage_off[0] = 0;
+            }
+        }
+        if (!done) {
+            vector<uint64_t> part(nt + 1, 0);
+            run_threads(nt, [&](unsigned t) {
+                uint64_t sum = 0;
+                for_range(m * t / nt, m * (t + 1) / nt, [&](size_t p, const Clause<T> *cl) {
+                    const uint64_t w = cl->literals->size();
+                    stage_off[p + 1] = w;                         // widths for now
+                    sum += w;
+                    return true;
+                });
+                part[t + 1] = sum;
             });
-            part[t + 1] = sum;
-        });
-        for (unsigned t = 0; t < nt; t++) part[t + 1] += part[t];
-        const uint64_t n_lit = part[nt];
-        ensure_stage(stage_lit, stage_lit_cap, (size_t)std::max<uint64_t>(n_lit, 1));
-        stage_off[0] = 0;
-        run_threads(nt, [&](unsigned t) {
-            uint64_t at = part[t];
-            for_range(m * t / nt, m * (t + 1) / nt, [&](size_t p, const Clause<T> *cl) {
-                const vector<T> &ls = *cl->literals;
-                uint32_t *dst = stage_lit + at;
-                for (size_t j = 0; j < ls.size(); j++) dst[j] = (uint32_t)ls[j];
-                at += ls.size();
-                stage_off[p + 1] = at;
+            for (unsigned t = 0; t < nt; t++) part[t + 1] += part[t];
+            const uint64_t n_lit = part[nt];
+            ensure_stage(stage_lit, stage_lit_cap, (size_t)std::max<uint64_t>(n_lit, 1));
+            stage_off[0] = 0;
+            run_threads(nt, [&](unsigned t) {
+                uint64_t at = part[t];
+                for_range(m * t / nt, m * (t + 1) / nt, [&](size_t p, const Clause<T> *cl) {
+                    const vector<T> &ls = *cl->literals;
+                    uint32_t *dst = stage_lit + at;
+                    for (size_t j = 0; j < ls.size(); j++) dst[j] = (uint32_t)ls[j];
+                    at += ls.size();
+                    stage_off[p + 1] = at;
+                    return true;
+                });
             });
-        });
+        }
         flatten_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         upload_flat(stage_off, m, stage_lit);
     }

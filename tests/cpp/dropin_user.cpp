@@ -55,6 +55,31 @@ int main(int argc, char **argv)
     for (auto &c : g_clauses) { Clause<UINT_T> cl(&c, 0); host_ok2 &= !cl.is_not_satisfied(inst2->var_arr->vars); }
     if (argc > 1) { std::ofstream f(argv[1]); inst2->writeDIMACS(enumerate, (ull)c_num, &f); }
 
+    // mixed clause widths (general DIMACS input, Clause.h:20-28): the flatten leaves its uniform-width fast path
+    bool host_ok3 = true;
+    {
+        auto ragged = new std::vector<ClauseArray *>();
+        for (int t = 0; t < 2; t++) ragged->push_back(new ClauseArray());
+        std::mt19937 r2(21);
+        for (int c = 0; c < 900; c++) {
+            const int w = 2 + (int)(r2() % 5);
+            auto *ls = new std::vector<UINT_T>();
+            while ((int)ls->size() < w) {
+                const UINT_T v = r2() % n;
+                bool dup = false;
+                for (auto l : *ls) dup |= (l >> 1) == v;
+                if (!dup) ls->push_back(2 * v + (r2() & 1));
+            }
+            ragged->at(c < 500 ? 0 : 1)->push_back(new Clause<UINT_T>(ls, (unsigned short)(c < 500 ? 0 : 1)));
+        }
+        auto inst3 = new SATInstance<UINT_T>(new VariablesArray<UINT_T>(n), 2);
+        inst3->set_seed(5);
+        Statistics *st3 = inst3->solve(ragged);
+        host_ok3 = inst3->last_status() == 0 && inst3->verify_validity(ragged) && inst3->verify_last() && st3->n_iterations >= 1;
+        for (auto b : *ragged) for (auto cl : *b) host_ok3 &= !cl->is_not_satisfied(inst3->var_arr->vars);
+    }
+    if (!host_ok3) { printf("{\"valid\": false, \"ragged\": false}\n"); return 1; }
+
     printf("{\"n_clauses\": %llu, \"iterations\": %llu, \"resamples\": %llu, \"avg_mis\": %llu, \"thread_entries\": %zu, "
            "\"thread0\": %llu, \"valid\": %s, \"host_ok\": %s, \"status\": %d, \"iterations2\": %llu, \"host_ok2\": %s}\n",
            inst->n_clauses, st->n_iterations, st->n_resamples, st->avg_mis_size, st->n_thread_resamples.size(),
