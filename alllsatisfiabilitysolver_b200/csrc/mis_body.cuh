@@ -219,34 +219,48 @@ __device__ __forceinline__ void append_s(const MisParams &p, uint32_t slot)
 __device__ __forceinline__ uint32_t p2p_wait(const MisParams &p, uint32_t *s_prefix)
 {
     const P2PLink &L = *p.p2p;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+        // One lane per source rank (two at world > 32): all arrival words are polled side by side -- one L2 round trip
+        // for the whole round instead of one per rank on the critical path of every round.  The word carries the count.
+        const uint32_t lane = threadIdx.x;
         P2PHeader *me = L.hdr[L.rank];
         const long long t_start = clock64();
-        bool bad = false;
-        unsigned int why = 0;                         // 2: a peer never published this round in time, 3: a peer aborted
         const unsigned int aval = (p.p2p_tag >> 20) + 1u;     // abort words are tagged with the solve's epoch
-        for (uint32_t q = 0; q < L.world && !bad; q++) {
-            while ((uint32_t)(*(volatile unsigned long long *)&me->cf[p.p2p_parity][q] >> 32) != p.p2p_tag) {
-                if (*(volatile unsigned int *)&me->abort == aval) { bad = true; why = 3; break; }
-                if (clock64() - t_start > L.timeout_cycles) {
-                    // tell the peers as well: they would otherwise wait for OUR next round until their own time-out
-                    bad = true; why = 2;
-                    for (uint32_t r = 0; r < L.world; r++) *(volatile unsigned int *)&L.hdr[r]->abort = aval;
-                    break;
+        unsigned int why = 0;                         // 2: a peer never published this round in time, 3: a peer aborted
+        uint32_t cnt[2] = {0u, 0u};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t q = lane + 32u * h;
+            if (q < L.world) {
+                for (;;) {
+                    const unsigned long long w = *(volatile unsigned long long *)&me->cf[p.p2p_parity][q];
+                    if ((uint32_t)(w >> 32) == p.p2p_tag) { cnt[h] = (uint32_t)w; break; }
+                    if (*(volatile unsigned int *)&me->abort == aval) { why = 3; break; }
+                    if (clock64() - t_start > L.timeout_cycles) { why = 2; break; }
                 }
             }
         }
         __threadfence_system();                       // acquire: the records behind the flags are now visible
-        if (!bad && *(volatile unsigned int *)&me->abort == aval) { bad = true; why = 3; }   // a peer overflowed even though every flag arrived
-        if (bad && blockIdx.x == 0 && p.ctr->p2p_error == 0) p.ctr->p2p_error = why;
-        uint32_t run = 0;
-        for (uint32_t q = 0; q < L.world; q++) {
-            s_prefix[q] = run;
-            const unsigned int cnt = (unsigned int)*(volatile unsigned long long *)&me->cf[p.p2p_parity][q];
-            if (cnt > L.cap) bad = true;
-            run += cnt;
+        if (why == 0 && lane == 0 && *(volatile unsigned int *)&me->abort == aval) why = 3;   // a peer overflowed even though every flag arrived
+        const bool over = cnt[0] > L.cap || cnt[1] > L.cap;
+        const unsigned int any_timeout = __ballot_sync(0xffffffffu, why == 2);
+        const unsigned int any_abort = __ballot_sync(0xffffffffu, why == 3);
+        const bool bad = any_timeout != 0u || any_abort != 0u || __any_sync(0xffffffffu, over);
+        if (any_timeout && lane < L.world)            // tell the peers as well: they would otherwise wait for OUR next round until their own time-out
+            *(volatile unsigned int *)&L.hdr[lane]->abort = aval;
+        if (any_timeout && lane + 32u < L.world) *(volatile unsigned int *)&L.hdr[lane + 32u]->abort = aval;
+        if (bad && lane == 0 && blockIdx.x == 0 && p.ctr->p2p_error == 0) p.ctr->p2p_error = any_timeout ? 2u : (any_abort ? 3u : 0u);
+        // exclusive prefix sums of the counts in rank order: ranks 0..31 by lane, then ranks 32..63
+        uint32_t inc0 = cnt[0], inc1 = cnt[1];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, inc0, o), b = __shfl_up_sync(0xffffffffu, inc1, o);
+            if ((int)lane >= o) { inc0 += a; inc1 += b; }
         }
-        s_prefix[L.world] = bad ? 0xFFFFFFFFu : run;
+        const uint32_t total0 = __shfl_sync(0xffffffffu, inc0, 31), total1 = __shfl_sync(0xffffffffu, inc1, 31);
+        if (lane < L.world) s_prefix[lane] = inc0 - cnt[0];
+        if (lane + 32u < L.world) s_prefix[lane + 32u] = total0 + inc1 - cnt[1];
+        if (lane == 0) s_prefix[L.world] = bad ? 0xFFFFFFFFu : total0 + total1;
     }
     __syncthreads();
     return s_prefix[L.world];

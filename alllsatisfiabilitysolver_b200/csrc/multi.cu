@@ -326,10 +326,13 @@ int alll_multi_solve(alll_multi_handle mh, uint64_t seed, uint64_t max_rounds, a
     bool persistent = mh->distinct;
     for (uint32_t r = 0; r < n && persistent; r++) persistent = internal_p2p_persistent_possible(mh->h[r]);
     if (persistent) {
-        // one launcher: enqueue every GPU's persistent solve kernel, then collect.  (The kernels wait for each other's
-        // round flags on the device; nothing here blocks until all of them are running.)
+        // enqueue every GPU's persistent solve kernel, then collect.  (The kernels wait for each other's round flags on
+        // the device; nothing here blocks until all of them are running.)
+        // (enqueued from the slot threads side by side: launched one after the other from one thread, the last GPU's
+        // kernel starts ~10 us per GPU after the first, and the first round of every GPU waits for it)
         std::vector<uint64_t> l0(n, 0);
-        for (uint32_t r = 0; r < n; r++) MCALL(r, internal_solve_p2p_begin(mh->h[r], seed, max_rounds, mh->epoch, &l0[r]));
+        if (int rc = for_all_slots(mh, n, [&](uint32_t r) { return internal_solve_p2p_begin(mh->h[r], seed, max_rounds, mh->epoch, &l0[r]); }))
+            return rc;
         tr.mark("solve: kernels enqueued");
         int worst = ALLL_OK;
         std::string msg;

@@ -170,16 +170,18 @@ def test_batch_and_portfolio_over_a_device_list(capi, oracle):
             ms.batch_upload(n, k, clause_off, lits)
             got, assign, _, ms_t = ms.batch_solve(seeds)
             for f in ("n_iterations", "n_resamples", "sum_mis_size", "status"):
-                assert np.array_equal(got[f], want[f]), (name, f)
-            assert np.array_equal(assign, want_assign) and ms_t > 0
+                assert np.array_equal(got[f], want[f]), (name, f, np.flatnonzero(got[f] != want[f])[:8])
+            assert np.array_equal(assign, want_assign), (name, np.flatnonzero((assign != want_assign).any(axis=1))[:8])
+            assert ms_t > 0, (name, ms_t)
             # seed portfolio on instance 0
             ms.batch_upload(n, k, clause_off[:2], lits)
             pseeds = np.arange(9000, 9000 + 300, dtype=np.uint64)
             stats, passign, winner, _ = ms.batch_solve(pseeds, portfolio=True)
             won = np.flatnonzero(stats["status"] == 0)
             assert len(won) == 1 and winner == int(won[0]), (name, won, winner)
-            assert (stats["status"][np.arange(300) != winner] == capi.PREEMPTED).all() or True   # late finishers are PREEMPTED
+            assert set(np.unique(stats["status"]).tolist()) <= {0, capi.PREEMPTED}, (name, np.unique(stats["status"]))
             off0, lit0 = to_csr(mats[0])
             v = oracle.randomize(n, int(pseeds[winner]))
             oracle.solve(n, off0, lit0, v, int(pseeds[winner]))
-            assert np.array_equal(passign[winner], v) and oracle.verify(off0, lit0, v)
+            assert oracle.verify(off0, lit0, v), name
+            assert np.array_equal(passign[winner], v), (name, winner, int((passign[winner] != v).sum()))
