@@ -95,6 +95,11 @@ __device__ __forceinline__ void tma_prefetch_l2(const void *p, uint32_t bytes)
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(bytes) : "memory");
 }
 
+// (Measured and rejected, profiles/r02_l2_policy.md: an explicit L2 evict_first policy on the stream -- loads and bulk
+// prefetches through createpolicy / .L2::cache_hint -- runs exactly like these hint-less forms, an evict_normal policy is
+// 10 % slower, and prefetch.global.L2 (SASS CCTL.E.PML2) of the claim sectors of violated clauses from inside the sweep
+// costs the stream far more than it saves the independent-set phase.)
+
 // ---- clause access for the sparse kernels (MIS / resample / id mapping) ----
 struct ClauseView {
     // fixed-k literal planes: lit j of slot p is planes[j * m_pad + p]
@@ -163,6 +168,9 @@ struct Counters {
     // persistent solve kernel: |U| by round parity; time spent in sweeps / between sweeps as block 0 saw it
     unsigned int n_viol_pp[2];
     unsigned long long t_sweep_ns, t_mis_ns;
+    // Luby step barrier of the grid-wide independent-set phase (mis_body.cuh: luby_barrier_fused), by step parity:
+    // CTAs arrived (low half) | clauses that claimed for the next step (high half); zero between rounds
+    unsigned long long luby_bar[2];
     // ALLL_TRACE: %globaltimer stamps of the first DBG_ROUNDS rounds (one thread writes them; a few stores per round)
     // [0] sweep entry  [1] MIS kernel entry  [2] |U| known  [3] gather + first claims done  [4] Luby steps done
     // [5] resample done  [6] round finished  [7] (steps << 8) | path (0 small, 1 cluster, 2 grid)
@@ -258,6 +266,9 @@ struct SweepParams {
     // records {caller id, k literals} of the first urec_cap violated clauses, parallel to viol[] (NULL = not written)
     uint32_t *urec;
     uint32_t urec_cap;
+    // measurement knobs (environment ALLL_TUNE, read at alll_create): TUNE_* bits
+    uint32_t tune;
 };
+constexpr uint32_t TUNE_CG_LUBY_BARRIER = 1u;      // Luby steps end with grid.sync() + a counter of their own instead of luby_barrier_fused
 
 } // namespace alll

@@ -38,6 +38,7 @@ struct alll_solver {
     int clock_khz = 0;                   // SM clock (kHz) for turning a time-out into clock64 ticks
     uint32_t smem_budget = DEFAULT_SWEEP_SMEM;
     uint32_t flags = 0;
+    uint32_t tune = 0;                   // TUNE_* measurement knobs (environment ALLL_TUNE, read at alll_create)
     std::string err;
     uint64_t launches = 0;
 
@@ -464,6 +465,7 @@ SweepParams sweep_params(alll_handle h, uint32_t p2p_parity, uint32_t p2p_tag, u
     sp.segs = h->d_segs; sp.viol = h->d_viol; sp.ctr = h->d_ctr; sp.k = h->k; sp.min_resident = h->min_resident;
     sp.resident_cap = h->resident_cap; sp.eager = (h->flags >> 8) & 0xFFu; sp.prefetch_tiles = prefetch_distance(h->flags);
     sp.round = round;
+    sp.tune = h->tune;
     sp.orig_id = h->use_orig_id ? h->d_orig_id : nullptr; sp.id_base = h->id_base;
     if (p2p_tag) {
         sp.p2p = h->d_p2p_link; sp.p2p_parity = p2p_parity; sp.p2p_tag = p2p_tag; sp.p2p_epoch = p2p_tag >> 20;
@@ -731,6 +733,7 @@ int alll_create(const alll_config *cfg, alll_handle *out)
     s->sm_count = prop.multiProcessorCount;
     s->clock_khz = prop.clockRate;
     s->flags = cfg ? cfg->flags : 0;
+    if (const char *e = getenv("ALLL_TUNE")) s->tune = (uint32_t)strtoul(e, nullptr, 0);
     const uint32_t wbuf_bytes = (SWEEP_THREADS / 32) * (WBUF + QBUF) * 4;
     const uint32_t max_bits = (uint32_t)prop.sharedMemPerBlockOptin - wbuf_bytes - 1024;
     s->smem_budget = (cfg && cfg->sweep_smem_bytes) ? cfg->sweep_smem_bytes : DEFAULT_SWEEP_SMEM;

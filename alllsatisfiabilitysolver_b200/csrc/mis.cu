@@ -136,6 +136,8 @@ __global__ void reset_counters_kernel(Counters *c, int reset_totals)
     c->incr_next = 0;
     c->n_viol_pp[0] = 0;
     c->n_viol_pp[1] = 0;
+    c->luby_bar[0] = 0;
+    c->luby_bar[1] = 0;
     c->t_sweep_ns = 0;
     c->t_mis_ns = 0;
     if (reset_totals) {

@@ -55,6 +55,7 @@ struct MisParams {
     uint32_t p2p_parity, p2p_tag;
     uint32_t incr_max_vars;     // incremental mode: next round is incremental iff this round resampled <= this many variables (0 = off)
     uint32_t u_cap;             // enumerated clauses: records the sweep could store (0 = no limit); a larger |U| aborts the solve
+    uint32_t tune;              // TUNE_* measurement knobs
 };
 
 extern __shared__ uint32_t mis_smem[];
@@ -160,11 +161,38 @@ __device__ __forceinline__ void resample_var(const MisParams &p, uint32_t round,
 
 struct GridBarrier {
     cg::grid_group g;
+    static constexpr bool GRID = true;
     __device__ __forceinline__ void sync() { g.sync(); }
 };
 struct ClusterBarrier {
+    static constexpr bool GRID = false;
     __device__ __forceinline__ void sync() { cg::this_cluster().sync(); }
 };
+
+// Grid-wide end of a Luby step with the live count riding on the arrival word: every CTA adds (its clauses that claimed
+// for the next step) << 32 | 1 to the word of the step's parity and polls it until all CTAs have arrived; the value that
+// ends the poll already carries the grid-wide count.  Against grid.sync() + a counter of its own this saves the separate
+// reduction atomic before the barrier and a dependent L2 round trip after it -- a Luby step of a few thousand clauses IS
+// these round trips.  Two words by step parity: a CTA that has passed step s may arrive for step s+1 while slower CTAs
+// still poll the word of step s, and nobody arrives for step s+2 before everyone has left that poll.  The words count up
+// over the steps of a round (`seen` = high half after this CTA's previous barrier of the same parity); the thread that
+// finishes the round clears them (finish_round), when no CTA is inside a Luby loop.
+// Called by thread 0 of every CTA of the grid, after a __syncthreads() that made the CTA's claims of this step complete.
+__device__ __forceinline__ uint32_t luby_barrier_fused(unsigned long long *words, uint32_t step, uint32_t cta_live, uint32_t n_ctas,
+                                                       uint32_t (&seen)[2])
+{
+    unsigned long long *w = words + (step & 1u);
+    const uint32_t target = (step / 2u + 1u) * n_ctas;
+    __threadfence();                                   // the CTA's claim stores / reductions are ordered before its arrival
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(w)), "l"(((unsigned long long)cta_live << 32) | 1ull) : "memory");
+    unsigned long long v;
+    do {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(__cvta_generic_to_global(w)) : "memory");
+    } while ((uint32_t)v < target);
+    const uint32_t hi = (uint32_t)(v >> 32), live = hi - seen[step & 1u];
+    seen[step & 1u] = hi;
+    return live;
+}
 
 // Where entry i of U comes from: a record {id, literals} (P2P exchange region, enumerated-clause records, or the
 // records the sweep wrote next to viol[]), or the stored clause in slot viol[i].
@@ -281,7 +309,9 @@ template <class Barrier, bool ALL_CACHED>
 __device__ __noinline__ void mis_resample_body(const MisParams &p, uint32_t round, Barrier &bar, const uint32_t *prefix,
                                                uint32_t first, uint32_t stride, uint32_t n_u)
 {
-    __shared__ unsigned int s_live;
+    __shared__ unsigned int s_live, s_total;
+    const bool fused = Barrier::GRID && (p.tune & TUNE_CG_LUBY_BARRIER) == 0;
+    uint32_t seen[2] = {0u, 0u};
     const uint32_t bd = blockDim.x, km = p.kmax, slotw = km + EXTRA;
     const bool use_urec = p.urec != nullptr && n_u <= p.urec_cap;
     // claim words of variable v: p.claim[2v] (even Luby steps) and p.claim[2v + 1] (odd steps) -- one 16-byte pair, so
@@ -384,6 +414,17 @@ __device__ __noinline__ void mis_resample_body(const MisParams &p, uint32_t roun
             if (live) atomicAdd(&s_live, live);
         }
         __syncthreads();
+        if (fused) {
+            if (threadIdx.x == 0) {
+                if (trace_steps && step < 16) p.ctr->dbg_step[step][2] = global_ns();
+                s_total = luby_barrier_fused(p.ctr->luby_bar, step, s_live, gridDim.x, seen);
+                if (trace_steps && step < 16) p.ctr->dbg_step[step][3] = global_ns();
+            }
+            __syncthreads();
+            step++;
+            if (s_total == 0) break;                                    // nobody claimed for this step: all decided
+            continue;
+        }
         if (threadIdx.x == 0 && s_live) gm::red_add(&p.ctr->step_live[(step + 1) & 63u], s_live);
         // the slot of step+3 (mod 64) is next written two steps from now: clear it while nobody touches it
         if (first == 0) p.ctr->step_live[(step + 3) & 63u] = 0;
@@ -559,6 +600,8 @@ __device__ __forceinline__ void finish_round(const MisParams &p, uint32_t round,
     c->n_s = 0;
     c->n_resampled_round = 0;
     c->handled_tag = p.p2p_tag;
+    c->luby_bar[0] = 0;                                    // (luby_barrier_fused: no CTA is inside a Luby loop here)
+    c->luby_bar[1] = 0;
     c->incr_next = (p.incr_max_vars != 0 && n_r <= p.incr_max_vars) ? 1u : 0u;
     announce(p, n_u, n_s);
     if (round < DBG_ROUNDS) { c->dbg[round][6] = global_ns(); c->dbg[round][7] |= path; }

@@ -187,6 +187,7 @@ cudaError_t launch_solve_persistent(const SweepParams &p, bool resident_all, uin
     mp.claim = sc.claim;
     mp.n_vars = n_vars; mp.bits = const_cast<uint32_t *>(p.bits); mp.ctr = p.ctr; mp.seed = seed; mp.kmax = kmax;
     mp.urec = sc.urec; mp.urec_cap = sc.urec_cap;
+    mp.tune = p.tune;
     persistent_fill(mp, smem);
     mp.incr_max_vars = incr ? incr_max_vars : 0u;
     const IncrParams no_incr{};
