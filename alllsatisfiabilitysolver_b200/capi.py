@@ -23,6 +23,7 @@ FLAG_FORCE_CSR = 8
 FLAG_P2P_PERSISTENT = 32    # alll_solve_p2p: one persistent kernel per rank (every rank needs its own GPU)
 FLAG_HOST_ROUND_LOOP = 16   # alll_solve: one kernel per phase driven by the host instead of the persistent solve kernel
 FLAG_FORCE_SHARDING = 64    # alll_multi_*: shard small instances too (tests)
+FLAG_NO_PACKING = 128       # sweep streams the plain planes 0..4 instead of the packed eager planes (comparison / tests)
 
 #: every symbol include/alll_b200.h declares (tests check the library exports exactly these)
 SYMBOLS = [
@@ -30,7 +31,7 @@ SYMBOLS = [
     "alll_upload_fixedk", "alll_upload_fixedk_device", "alll_upload_csr",
     "alll_set_assignment", "alll_get_assignment", "alll_randomize",
     "alll_eval", "alll_verify", "alll_round", "alll_solve",
-    "alll_time_sweep", "alll_launch_count", "alll_layout_info",
+    "alll_time_sweep", "alll_launch_count", "alll_layout_info", "alll_sweep_info",
     "alll_set_id_base", "alll_shard_sweep", "alll_shard_round", "alll_get_stats", "alll_reset_stats",
     "alll_batch_upload", "alll_batch_solve",
     "alll_p2p_create", "alll_p2p_connect", "alll_solve_p2p",
@@ -124,6 +125,7 @@ def load() -> C.CDLL:
     L.alll_time_sweep.argtypes = [vp, u32, C.POINTER(C.c_double), C.POINTER(u64)]
     L.alll_launch_count.argtypes = [vp, C.POINTER(u64)]
     L.alll_layout_info.argtypes = [vp, C.POINTER(u64)]
+    L.alll_sweep_info.argtypes = [vp, C.POINTER(u64)]
     L.alll_set_id_base.argtypes = [vp, u64]
     L.alll_shard_sweep.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.alll_shard_round.argtypes = [vp, vp, C.POINTER(u64), u32, u64, u64, u32, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
@@ -382,6 +384,11 @@ class Solver:
         info = (C.c_uint64 * 6)()
         self._check(self.lib.alll_layout_info(self.h, info))
         return dict(m=info[0], k=info[1], n_buckets=info[2], m_padded=info[3], literal_bytes=info[4], sweep_smem_bytes=info[5])
+
+    def sweep_info(self) -> dict:
+        info = (C.c_uint64 * 4)()
+        self._check(self.lib.alll_sweep_info(self.h, info))
+        return dict(packed=bool(info[0]), bucket_relative_literals=info[1], streamed_bytes_per_clause=info[2], min_resident=info[3])
 
 
 class MultiSolver:

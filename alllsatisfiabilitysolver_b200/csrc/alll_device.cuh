@@ -100,6 +100,50 @@ __device__ __forceinline__ void tma_prefetch_l2(const void *p, uint32_t bytes)
 // 10 % slower, and prefetch.global.L2 (SASS CCTL.E.PML2) of the claim sectors of violated clauses from inside the sweep
 // costs the stream far more than it saves the independent-set phase.)
 
+// ---- packed eager planes ---------------------------------------------------------------------------------------
+// The sweep streams the first five literals of every clause (planes 0..4) and is bound by those bytes.  On a bucketed
+// layout the leading RB literals of a clause lie in its bucket's variable range, so they are stored relative to the
+// bucket (2 * bucket_vars <= 2^22), and the others need 1 + log2(n_vars) bits: five literals fit ONE 128-bit word per
+// clause -- four packed planes instead of five, 16 streamed bytes per clause instead of 20.
+//   RB = 2: [l0' : 22][l1' : 22][l2 : 28][l3 : 28][l4 : 28]   (n_vars <= 2^27)
+//   RB = 1: [l0' : 22][l1 : 26][l2 : 26][l3 : 26][l4 : 26]    (n_vars <= 2^25), two spare bits
+// l' = l - 2 * vbase(bucket).  Word w of clause slot p is packed[w * m_pad + p].  The unpacked planes stay in HBM next to
+// them for everything that reads single clauses (records, independent set, tail literals, incremental rows).
+template <int RB>
+struct EagerPack {
+    static_assert(RB == 1 || RB == 2, "packed eager planes need one or two bucket-resident leading literals");
+    static constexpr int N = 5;                                   // == EAGER_PLANES
+    static constexpr int WORDS = 4;
+    static constexpr int REL_BITS = 22, GLOB_BITS = RB == 2 ? 28 : 26;
+    __host__ __device__ static constexpr int width(int j) { return j < RB ? REL_BITS : GLOB_BITS; }
+    __host__ __device__ static constexpr int offset(int j) { return j <= RB ? j * REL_BITS : RB * REL_BITS + (j - RB) * GLOB_BITS; }
+    static_assert(offset(4) + width(4) <= 128, "five literals must fit 128 bits");
+
+    // l[0 .. RB) already relative to the bucket
+    __host__ __device__ static void encode(const uint32_t (&l)[N], uint32_t (&w)[WORDS])
+    {
+        for (int i = 0; i < WORDS; i++) w[i] = 0u;
+        for (int j = 0; j < N; j++) {
+            const int o = offset(j), i = o >> 5, sh = o & 31;
+            w[i] |= l[j] << sh;
+            if (sh + width(j) > 32) w[i + 1] |= l[j] >> (32 - sh);
+        }
+    }
+    template <int J>
+    __device__ __forceinline__ static uint32_t field(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3)
+    {
+        constexpr int o = offset(J), i = o >> 5, sh = o & 31, wd = width(J);
+        constexpr uint32_t mask = (1u << wd) - 1u;
+        const uint32_t lo = i == 0 ? w0 : i == 1 ? w1 : i == 2 ? w2 : w3;
+        if constexpr (sh + wd == 32) return lo >> sh;
+        else if constexpr (sh + wd < 32) return (lo >> sh) & mask;
+        else {
+            const uint32_t hi = i == 0 ? w1 : i == 1 ? w2 : w3;
+            return __funnelshift_r(lo, hi, sh) & mask;
+        }
+    }
+};
+
 // ---- clause access for the sparse kernels (MIS / resample / id mapping) ----
 struct ClauseView {
     // fixed-k literal planes: lit j of slot p is planes[j * m_pad + p]
@@ -268,7 +312,14 @@ struct SweepParams {
     uint32_t urec_cap;
     // measurement knobs (environment ALLL_TUNE, read at alll_create): TUNE_* bits
     uint32_t tune;
+    // packed eager planes [4][m_pad] (EagerPack<min(min_resident, 2)>; NULL = the sweep streams planes 0..4)
+    const uint32_t *packed;
+    // tail rows [m_pad] (5 < k <= 8; NULL = none): literals 5 .. k-1 of a clause side by side in one 16-byte row, so a
+    // clause that survives its five eager literals costs ONE scattered sector instead of one per tail plane
+    const uint4 *tail_rows;
 };
+constexpr uint32_t TUNE_NO_TAIL_ROWS = 2u;         // survivors fetch their tail literals from the planes (one sector per literal)
+constexpr uint32_t TUNE_NO_PACKED_PLANES = 4u;     // the sweep streams planes 0..4 even where the packed eager planes apply
 constexpr uint32_t TUNE_CG_LUBY_BARRIER = 1u;      // Luby steps end with grid.sync() + a counter of their own instead of luby_barrier_fused
 
 } // namespace alll

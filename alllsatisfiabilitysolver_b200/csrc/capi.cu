@@ -52,6 +52,10 @@ struct alll_solver {
     uint32_t min_resident = 0;           // measured by the bucketing pass; selects the sweep specialisation
     uint32_t resident_cap = RESIDENT_CAP; // literals per clause placed as bucket-resident (compile-time choice: 2 / 3 / 4 were measured, profiles/)
     uint32_t *d_planes = nullptr, *d_orig_id = nullptr;
+    uint32_t *d_packed = nullptr;        // packed eager planes [4][m_pad] (alll_device.cuh: EagerPack), streamed by the sweep when packed_on
+    bool packed_on = false;
+    uint4 *d_tail_rows = nullptr;        // literals 5 .. k-1 of every slot in one 16-byte row (5 < k <= 8), read by the sweep for surviving clauses
+    bool tail_on = false;
     BucketSeg *d_segs = nullptr;
     uint64_t *d_off = nullptr;
     uint32_t *d_csr_lit = nullptr;       // [csr_l_pad]: the literal array, padded to a multiple of 128 (>= 1 padding position)
@@ -154,6 +158,8 @@ template <typename T> void dfree(T *&p)
 void free_instance(alll_handle h)
 {
     h->has_instance = false;
+    h->packed_on = false;
+    h->tail_on = false;
     h->use_orig_id = false;
     h->use_width = false;
     h->incr_ready = false;
@@ -165,7 +171,7 @@ void free_instance(alll_handle h)
 
 void release_buffers(alll_handle h)
 {
-    dfree(h->d_planes); dfree(h->d_orig_id); dfree(h->d_segs); dfree(h->d_off); dfree(h->d_csr_lit); dfree(h->d_csr_start); dfree(h->d_csr_rank);
+    dfree(h->d_planes); dfree(h->d_packed); dfree(h->d_tail_rows); dfree(h->d_orig_id); dfree(h->d_segs); dfree(h->d_off); dfree(h->d_csr_lit); dfree(h->d_csr_start); dfree(h->d_csr_rank);
     dfree(h->d_bits); dfree(h->d_claim); dfree(h->d_urec); dfree(h->d_viol); dfree(h->d_s); dfree(h->d_ids_out);
     dfree(h->d_state); dfree(h->d_bools); dfree(h->d_width); dfree(h->d_width_in); dfree(h->d_tmp_bkt); dfree(h->d_tmp_cnt); dfree(h->d_tmp_err); dfree(h->d_stage);
     dfree(h->d_sh_planes); dfree(h->d_sh_ids); dfree(h->d_sh_iota); dfree(h->d_sh_s); dfree(h->d_sh_state);
@@ -398,6 +404,24 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     if (h->n_buckets > 1 && m > 0 && err_out[1] != 0xFFFFFFFFu) h->min_resident = err_out[1];
 
     h->use_width = d_width_in != nullptr && m > 0;
+    {
+        // Packed eager planes: the five literals the sweep streams per clause in one 128-bit word (EagerPack).  Needs a
+        // bucketed layout whose clauses all have a bucket-resident leading literal (two for the wider global fields).
+        const uint32_t rb = std::min<uint32_t>(h->min_resident, 2u);
+        const uint64_t glob_limit = rb >= 2 ? (1ull << 27) : (1ull << 25);
+        h->packed_on = h->n_buckets > 1 && m > 0 && k >= EAGER_PLANES && k <= 8 && rb >= 1 && h->resident_cap == 3 &&
+                       2ull * h->bucket_words * 32u <= (1ull << 22) && n_vars <= glob_limit && !(h->flags & ALLL_FLAG_NO_PACKING) && !(h->tune & TUNE_NO_PACKED_PLANES);
+        if (h->packed_on) {
+            POOL(h->d_packed, h->m_pad * 4 * 4);
+            CK(launch_pack_eager(h->d_planes, h->m_pad, h->d_segs, h->n_buckets, h->bucket_words * 32u, rb, h->d_packed, h->stream));
+            h->launches++;
+        }
+    }
+    h->tail_on = m > 0 && k > EAGER_PLANES && k <= 8 && !(h->flags & ALLL_FLAG_NO_PACKING) && !(h->tune & TUNE_NO_TAIL_ROWS);
+    if (h->tail_on) {
+        POOL(h->d_tail_rows, h->m_pad * sizeof(uint4));
+        CK(launch_tail_rows(h->d_planes, h->m_pad, k, h->d_tail_rows, h->stream)); h->launches++;
+    }
     if (int rc = alloc_common(h, h->m)) return rc;
     if (k >= 1 && k <= 8 && !h->use_width && m > 0) {
         // violated-clause records for the independent-set kernels (sweep_body.cuh:write_records), for violated sets of up to
@@ -409,6 +433,8 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     }
     SweepParams sp{};
     sp.bucket_words = h->bucket_words; sp.k = k; sp.min_resident = h->min_resident; sp.resident_cap = h->resident_cap; sp.eager = (h->flags >> 8) & 0xFFu; sp.prefetch_tiles = prefetch_distance(h->flags);
+    sp.packed = h->packed_on ? h->d_packed : nullptr;
+    sp.tail_rows = h->tail_on ? h->d_tail_rows : nullptr;
     CK(configure_sweep_planes(sp, h->resident_all));
     h->sweep_grid = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)h->sm_count, h->n_tiles));
     {
@@ -466,6 +492,8 @@ SweepParams sweep_params(alll_handle h, uint32_t p2p_parity, uint32_t p2p_tag, u
     sp.resident_cap = h->resident_cap; sp.eager = (h->flags >> 8) & 0xFFu; sp.prefetch_tiles = prefetch_distance(h->flags);
     sp.round = round;
     sp.tune = h->tune;
+    sp.packed = h->packed_on ? h->d_packed : nullptr;
+    sp.tail_rows = h->tail_on ? h->d_tail_rows : nullptr;
     sp.orig_id = h->use_orig_id ? h->d_orig_id : nullptr; sp.id_base = h->id_base;
     if (p2p_tag) {
         sp.p2p = h->d_p2p_link; sp.p2p_parity = p2p_parity; sp.p2p_tag = p2p_tag; sp.p2p_epoch = p2p_tag >> 20;
@@ -1707,6 +1735,18 @@ int alll_layout_info(alll_handle h, uint64_t info[6])
     info[3] = h->m_pad;
     info[4] = h->k ? h->m_pad * h->k * 4 : h->csr_l_pad * 4 + h->csr_l_pad / 8 + (h->csr_l_pad / CSR_CHUNK + 1) * 4;   // bytes one sweep reads
     info[5] = h->k ? sweep_planes_smem_bytes(h->bucket_words) : sweep_csr_smem_bytes(h->csr_staged_words, SWEEP_THREADS);
+    return ALLL_OK;
+}
+
+int alll_sweep_info(alll_handle h, uint64_t info[4])
+{
+    if (!h || !info) return ALLL_BAD_ARG;
+    if (!h->has_instance) return fail(h, ALLL_NO_INSTANCE, "no instance uploaded");
+    const uint32_t eager = h->k ? std::min<uint32_t>(h->k, EAGER_PLANES) : 0u;
+    info[0] = h->packed_on ? 1 : 0;
+    info[1] = h->packed_on ? std::min<uint32_t>(h->min_resident, 2u) : 0u;
+    info[2] = h->packed_on ? 16u : 4u * eager;
+    info[3] = h->min_resident;
     return ALLL_OK;
 }
 

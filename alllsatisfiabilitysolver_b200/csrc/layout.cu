@@ -300,6 +300,58 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) bucket_scatter_staged_kernel(c
     orig_id[dst] = stage_smem[k * LAYOUT_THREADS + t];
 }
 
+// ---- packed eager planes (alll_device.cuh: EagerPack) -- one pass over the finished planes ------------------------
+template <int RB>
+__global__ void __launch_bounds__(256) pack_eager_kernel(const uint32_t *__restrict__ planes, uint64_t m_pad,
+                                                          const BucketSeg *__restrict__ segs, uint32_t n_buckets,
+                                                          uint32_t bucket_vars, uint32_t *__restrict__ packed)
+{
+    const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= m_pad) return;
+    const uint32_t tile = (uint32_t)(slot / TILE);
+    uint32_t b = 0;
+    while (b + 1 < n_buckets && segs[b + 1].tile_begin <= tile) ++b;
+    uint32_t w[EagerPack<RB>::WORDS] = {0u, 0u, 0u, 0u};
+    if (slot < segs[b].slot_end) {                       // (padding slots are never evaluated: all-zero words)
+        uint32_t l[EagerPack<RB>::N];
+#pragma unroll
+        for (int j = 0; j < EagerPack<RB>::N; j++) l[j] = planes[(uint64_t)j * m_pad + slot];
+#pragma unroll
+        for (int j = 0; j < RB; j++) l[j] -= 2u * b * bucket_vars;
+        EagerPack<RB>::encode(l, w);
+    }
+#pragma unroll
+    for (int i = 0; i < EagerPack<RB>::WORDS; i++) packed[(uint64_t)i * m_pad + slot] = w[i];
+}
+
+// ---- tail rows: literals EAGER_PLANES .. k-1 of every slot side by side (k <= 8: at most three) ----------------------
+__global__ void __launch_bounds__(256) tail_rows_kernel(const uint32_t *__restrict__ planes, uint64_t m_pad, uint32_t k,
+                                                         uint4 *__restrict__ rows)
+{
+    const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= m_pad) return;
+    uint32_t l[4] = {0u, 0u, 0u, 0u};
+    for (uint32_t j = EAGER_PLANES; j < k; j++) l[j - EAGER_PLANES] = planes[(uint64_t)j * m_pad + slot];
+    rows[slot] = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+cudaError_t launch_tail_rows(const uint32_t *planes, uint64_t m_pad, uint32_t k, uint4 *rows, cudaStream_t s)
+{
+    if (m_pad == 0) return cudaSuccess;
+    tail_rows_kernel<<<(uint32_t)((m_pad + 255) / 256), 256, 0, s>>>(planes, m_pad, k, rows);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_eager(const uint32_t *planes, uint64_t m_pad, const BucketSeg *segs, uint32_t n_buckets,
+                              uint32_t bucket_vars, uint32_t rb, uint32_t *packed, cudaStream_t s)
+{
+    if (m_pad == 0) return cudaSuccess;
+    const uint32_t grid = (uint32_t)((m_pad + 255) / 256);
+    if (rb >= 2) pack_eager_kernel<2><<<grid, 256, 0, s>>>(planes, m_pad, segs, n_buckets, bucket_vars, packed);
+    else pack_eager_kernel<1><<<grid, 256, 0, s>>>(planes, m_pad, segs, n_buckets, bucket_vars, packed);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_bucket_scatter(const uint32_t *lit, uint64_t m, uint32_t k, uint32_t bucket_vars, uint32_t n_buckets,
                                   const uint8_t *bkt, const uint32_t *cta_base, uint32_t *planes, uint64_t m_pad,
                                   uint32_t *orig_id, uint32_t *min_resident, uint32_t resident_cap, const uint8_t *width_in,

@@ -17,7 +17,7 @@ namespace alll {
 // round on, and launch gaps, event records and the host round trip disappear as well.
 // One CTA per SM (cooperative launch).  |U| is accumulated in one of two counters selected by round parity: the
 // one for round r+1 is cleared during the independent-set phase of round r, when nobody adds to it.
-template <int K, int RB, int RC, int E>
+template <int K, int RB, int RC, int E, bool PK>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(const SweepParams sp, const MisParams mp_arg,
                                                                            const uint32_t max_rounds, const uint32_t epoch,
                                                                            const IncrParams ip, const uint32_t visited_words)
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(cons
         // from the occurrence lists of the variables it resampled (same set as the sweep's, incremental.cu) or from a sweep
         const bool incremental = ip.rows != nullptr && round > 0 && gm::ld_cg(&c->incr_next) != 0;
         if (incremental) incr_eval_body(ip, gm::ld_cg(&c->last_n_s), &c->n_viol_pp[par], IncrP2P{sp.p2p, s_prefix, par, sp.orig_id, sp.id_base, c, sp.p2p_epoch + 1u});
-        else sweep_planes_body<K, RB, RC, E, false>(sp, &c->n_viol_pp[par], par, rec_on);
+        else sweep_planes_body<K, RB, RC, E, false, PK>(sp, &c->n_viol_pp[par], par, rec_on);
         if (p2p) {                                       // this CTA's record stores (NVLink) are ordered before the barrier
             __syncthreads();
             if (threadIdx.x == 0) __threadfence_system();
@@ -132,15 +132,15 @@ struct PersistOp {
     const IncrParams *ip;
     uint32_t visited_words;
     int *max_ctas_per_sm;
-    template <int K, int RB, int RC, int E> cudaError_t run()
+    template <int K, int RB, int RC, int E, bool PK> cudaError_t run()
     {
         if (mp == nullptr) {
-            cudaError_t e = cudaFuncSetAttribute(solve_persistent_kernel<K, RB, RC, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(solve_persistent_kernel<K, RB, RC, E, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_ctas_per_sm, solve_persistent_kernel<K, RB, RC, E>, SWEEP_THREADS, smem);
+            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_ctas_per_sm, solve_persistent_kernel<K, RB, RC, E, PK>, SWEEP_THREADS, smem);
         }
         void *args[] = {(void *)&p, (void *)mp, (void *)&max_rounds, (void *)&epoch, (void *)ip, (void *)&visited_words};
-        return cudaLaunchCooperativeKernel((const void *)solve_persistent_kernel<K, RB, RC, E>, dim3(grid), dim3(SWEEP_THREADS), args, smem, s);
+        return cudaLaunchCooperativeKernel((const void *)solve_persistent_kernel<K, RB, RC, E, PK>, dim3(grid), dim3(SWEEP_THREADS), args, smem, s);
     }
 };
 } // namespace

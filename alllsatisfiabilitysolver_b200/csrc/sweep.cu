@@ -23,12 +23,12 @@
 
 namespace alll {
 
-template <int K, int RB, int RC, int E>
+template <int K, int RB, int RC, int E, bool PK>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_kernel(const SweepParams p)
 {
     if (__ldcg(&p.ctr->done) || __ldcg(&p.ctr->incr_next)) return;   // behind the terminal round / this round is incremental
     if (blockIdx.x == 0 && threadIdx.x == 0 && p.round < DBG_ROUNDS) p.ctr->dbg[p.round][0] = global_ns();
-    sweep_planes_body<K, RB, RC, E, true>(p, &p.ctr->n_viol, p.p2p_parity, true);
+    sweep_planes_body<K, RB, RC, E, true, PK>(p, &p.ctr->n_viol, p.p2p_parity, true);
 }
 
 // Run-time clause width (k > 8): planes are loaded lazily level by level; no prefetch.
@@ -77,11 +77,11 @@ struct SweepOp {                 // launch or (configure) opt in to the shared m
     size_t smem;
     cudaStream_t s;
     bool configure;
-    template <int K, int RB, int RC, int E> cudaError_t run()
+    template <int K, int RB, int RC, int E, bool PK> cudaError_t run()
     {
         if (configure)   // function attributes are per device: the handle configures its kernel once at upload
-            return cudaFuncSetAttribute(sweep_planes_kernel<K, RB, RC, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        sweep_planes_kernel<K, RB, RC, E><<<grid, SWEEP_THREADS, smem, s>>>(p);
+            return cudaFuncSetAttribute(sweep_planes_kernel<K, RB, RC, E, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        sweep_planes_kernel<K, RB, RC, E, PK><<<grid, SWEEP_THREADS, smem, s>>>(p);
         return cudaGetLastError();
     }
 };

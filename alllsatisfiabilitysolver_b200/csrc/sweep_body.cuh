@@ -282,8 +282,10 @@ __device__ __forceinline__ void gather_round(const uint4 (&L)[K], uint32_t (&a)[
 // Evaluates the first E literals (the planes held in registers) of 4 clauses; component q of every plane is
 // clause slot0+q.  Returns the still-unsatisfied mask (bit q).  Phase R: shared memory.  Phase G: the
 // non-resident literals of planes [RB, E), all issued at once -- one L2 round trip.
+// sadj_rb: base for planes [0, RB) -- the same as sadj, or (packed eager planes: those literals are stored relative to
+// the bucket) the shared byte address of staged word 0 itself.
 template <int E, int RB, int RC>
-__device__ __forceinline__ uint32_t eval4(const uint4 (&L)[E], uint32_t valid_mask, uint32_t sadj,
+__device__ __forceinline__ uint32_t eval4(const uint4 (&L)[E], uint32_t valid_mask, uint32_t sadj_rb, uint32_t sadj,
                                           const uint32_t *gbits, uint32_t vbase, uint32_t bucket_vars)
 {
     constexpr int R_END = RC < E ? RC : E;
@@ -292,7 +294,7 @@ __device__ __forceinline__ uint32_t eval4(const uint4 (&L)[E], uint32_t valid_ma
     for (int j = 0; j < R_END; j++)
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            if (j < RB) resident_only_step(comp(L[j], q), a[q], sadj);
+            if (j < RB) resident_only_step(comp(L[j], q), a[q], sadj_rb);
             else resident_mixed_step(comp(L[j], q), a[q], sadj, vbase, bucket_vars);
         }
     gather_round<E, RB, RC, (RB < E ? RB : E), E>(L, a, gbits, vbase, bucket_vars);
@@ -333,8 +335,14 @@ struct SurvivorQueue {
             const uint32_t slot = act ? g_smem[qbuf + count - n + lane] : 0u;
             constexpr int T = K > E ? K - E : 1;     // tail planes (T = 1 only keeps the arrays legal when E == K)
             uint32_t l[T];
+            if (K - E <= 4 && p.tail_rows != nullptr) {       // one 16-byte row instead of K - E scattered plane words
+                const uint4 t = act ? __ldg(p.tail_rows + slot) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-            for (int j = 0; j < K - E; j++) l[j] = act ? __ldg(p.planes + (uint64_t)(E + j) * p.m_pad + slot) : 0u;
+                for (int j = 0; j < K - E; j++) l[j] = comp(t, j);
+            } else {
+#pragma unroll
+                for (int j = 0; j < K - E; j++) l[j] = act ? __ldg(p.planes + (uint64_t)(E + j) * p.m_pad + slot) : 0u;
+            }
             uint32_t w[T];
 #pragma unroll
             for (int j = 0; j < K - E; j++) {                 // all lookups at once: this path is rare and dense
@@ -360,11 +368,14 @@ struct SurvivorQueue {
 // loads are in flight while the current tile is evaluated (register double buffering).
 // TICKET: (sharded P2P mode) the CTA that finishes last publishes this rank's round to the peers; the persistent solve
 // kernel publishes after its grid barrier instead.
-template <int K, int RB, int RC, int E, bool TICKET>
+// PK: the E = 5 eager literals come from the four packed planes (EagerPack<RB>) instead of planes 0..4.
+template <int K, int RB, int RC, int E, bool TICKET, bool PK>
 __device__ __forceinline__ void sweep_planes_body(const SweepParams &p, unsigned int *n_viol_ctr, uint32_t p2p_parity, bool rec_on)
 {
     constexpr bool RESIDENT_ALL = RB >= K;
     constexpr int RBE = RB < E ? RB : E;
+    constexpr int NS = PK ? 4 : E;               // planes streamed per tile
+    static_assert(!PK || (E == 5 && K >= 5 && (RB == 1 || RB == 2)), "packed eager planes: five literals, one or two of them bucket-relative");
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = threadIdx.x >> 5;
     WarpCompactor out{p.bucket_words + warp * WBUF, p.viol, p.ctr, n_viol_ctr, p2p_parity, rec_on, 0u, lane, &p};
@@ -380,15 +391,16 @@ __device__ __forceinline__ void sweep_planes_body(const SweepParams &p, unsigned
     TileCursor cur;
     cur.init(p, t0);
     const uint32_t bucket_vars = p.bucket_words * 32u;
-    const uint32_t *base = p.planes + threadIdx.x * CLAUSES_PER_THREAD;
+    const uint32_t *const stream = PK ? p.packed : p.planes;
+    const uint32_t *base = stream + threadIdx.x * CLAUSES_PER_THREAD;
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(g_smem);
 
-    auto load = [&](uint4 (&L)[E], uint32_t tile) {
+    auto load = [&](uint4 (&L)[NS], uint32_t tile) {
         const uint32_t *src = base + (uint64_t)tile * TILE;
 #pragma unroll
-        for (int j = 0; j < E; j++) L[j] = ld_stream_v4(src + (uint64_t)j * p.m_pad);
+        for (int j = 0; j < NS; j++) L[j] = ld_stream_v4(src + (uint64_t)j * p.m_pad);
     };
-    auto process = [&](const uint4 (&L)[E], uint32_t tile) {
+    auto process = [&](const uint4 (&S)[NS], uint32_t tile) {
         const uint32_t prev_vbase = cur.b * bucket_vars;
         if (cur.advance(p, tile)) {
             if constexpr (E < K) parked.drain(0u, out, p, prev_vbase, bucket_vars);   // parked clauses belong to the old bucket
@@ -401,7 +413,19 @@ __device__ __forceinline__ void sweep_planes_body(const SweepParams &p, unsigned
         const uint32_t vbase = cur.b * bucket_vars;
         uint32_t sb = smem_base;
         asm volatile("" : "+r"(sb));          // opaque: lookups below cannot be hoisted above the staging barrier
-        const uint32_t alive = eval4<E, RBE, RC>(L, valid, sb - ((vbase >> 5) << 2), p.bits, vbase, bucket_vars);
+        const uint32_t sadj = sb - ((vbase >> 5) << 2);
+        uint32_t alive;
+        if constexpr (PK) {
+            using P = EagerPack<(RB < 2 ? 1 : 2)>;
+            uint4 L[E];
+#define ALLL_UNPACK(J) L[J] = make_uint4(P::template field<J>(S[0].x, S[1].x, S[2].x, S[3].x), P::template field<J>(S[0].y, S[1].y, S[2].y, S[3].y), \
+                                         P::template field<J>(S[0].z, S[1].z, S[2].z, S[3].z), P::template field<J>(S[0].w, S[1].w, S[2].w, S[3].w))
+            ALLL_UNPACK(0); ALLL_UNPACK(1); ALLL_UNPACK(2); ALLL_UNPACK(3); ALLL_UNPACK(4);
+#undef ALLL_UNPACK
+            alive = eval4<E, RBE, RC>(L, valid, sb, sadj, p.bits, vbase, bucket_vars);
+        } else {
+            alive = eval4<E, RBE, RC>(S, valid, sadj, sadj, p.bits, vbase, bucket_vars);
+        }
         if constexpr (E < K) {
             parked.push4(alive, slot0);
             parked.drain(31u, out, p, vbase, bucket_vars);
@@ -416,21 +440,25 @@ __device__ __forceinline__ void sweep_planes_body(const SweepParams &p, unsigned
     auto prefetch = [&](uint32_t tile) {
         if (threadIdx.x == 0 && dist != 0 && tile < t1) {
 #pragma unroll
-            for (int j = 0; j < E; j++) tma_prefetch_l2(p.planes + (uint64_t)j * p.m_pad + (uint64_t)tile * TILE, TILE * 4);
+            for (int j = 0; j < NS; j++) tma_prefetch_l2(stream + (uint64_t)j * p.m_pad + (uint64_t)tile * TILE, TILE * 4);
         }
     };
-    for (uint32_t d = 2; d < 2 + dist; d++) prefetch(t0 + d);
-
-    uint4 A[E], B[E];
-    load(A, t0);
-    for (uint32_t tile = t0; tile < t1; tile += 2) {
-        if (tile + 1 < t1) load(B, tile + 1);
-        prefetch(tile + 2 + dist);
-        process(A, tile);
-        if (tile + 1 >= t1) break;
-        if (tile + 2 < t1) load(A, tile + 2);
-        prefetch(tile + 3 + dist);
-        process(B, tile + 1);
+    // (Measured and rejected for the packed planes, profiles/r02_packed_planes.md: a third register buffer -- loads issued
+    // two tiles ahead -- is slower, 0.2075 vs 0.2029 ms stand-alone and 0.220 vs 0.204 ms inside the solve kernel, where it
+    // spills: the wait at a tile's first use is arrival rate, not latency.)
+    {
+        for (uint32_t d = 2; d < 2 + dist; d++) prefetch(t0 + d);
+        uint4 A[NS], B[NS];
+        load(A, t0);
+        for (uint32_t tile = t0; tile < t1; tile += 2) {
+            if (tile + 1 < t1) load(B, tile + 1);
+            prefetch(tile + 2 + dist);
+            process(A, tile);
+            if (tile + 1 >= t1) break;
+            if (tile + 2 < t1) load(A, tile + 2);
+            prefetch(tile + 3 + dist);
+            process(B, tile + 1);
+        }
     }
     if constexpr (E < K) parked.drain(0u, out, p, cur.b * bucket_vars, bucket_vars);
     if (out.count) out.flush();
@@ -438,7 +466,7 @@ __device__ __forceinline__ void sweep_planes_body(const SweepParams &p, unsigned
 }
 
 // ---- dispatch over the compile-time variants ---------------------------------------------------------------------
-// f.template run<K, RB, RC, E>() for the variant that fits p.k / the bucket classes measured at upload; returns
+// f.template run<K, RB, RC, E, PK>() for the variant that fits p.k / the bucket classes measured at upload; returns
 // cudaErrorNotSupported for k > 8 (only sweep.cu has a run-time-width kernel).
 // E = min(K, EAGER_PLANES) planes are streamed (4 / 5 / 6 / 8 were measured at k = 8: 5 is fastest, profiles/).
 // resident_all: every plane is resident-only (RB = RC = K).  Otherwise RC = min(K, RESIDENT_CAP) (2 / 3 / 4 measured at
@@ -447,7 +475,7 @@ template <int K, int RB, int RC, class F>
 static cudaError_t dispatch_e(F &f)
 {
     constexpr int E = K < (int)EAGER_PLANES ? K : (int)EAGER_PLANES;
-    return f.template run<K, RB, RC, E>();
+    return f.template run<K, RB, RC, E, false>();
 }
 
 template <int K, class F>
@@ -456,6 +484,13 @@ static cudaError_t dispatch_class(const SweepParams &p, bool resident_all, F &f)
     if (resident_all) return dispatch_e<K, K, K>(f);
     constexpr int RC = K < (int)RESIDENT_CAP ? K : (int)RESIDENT_CAP;
     const uint32_t rb = p.min_resident < 2u ? p.min_resident : 2u;
+    if (p.packed != nullptr) {                           // packed eager planes (capi.cu decides eligibility at upload)
+        if constexpr (K >= (int)EAGER_PLANES && RC == 3) {
+            if (rb >= 2) return f.template run<K, 2, RC, (int)EAGER_PLANES, true>();
+            if (rb == 1) return f.template run<K, 1, RC, (int)EAGER_PLANES, true>();
+        }
+        return cudaErrorNotSupported;
+    }
     if (rb >= 2 && RC >= 2) return dispatch_e<K, (RC < 2 ? RC : 2), RC>(f);
     if (rb >= 1 && RC >= 1) return dispatch_e<K, (RC < 1 ? RC : 1), RC>(f);
     return dispatch_e<K, 0, RC>(f);

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ALLL_ABI_VERSION 5
+#define ALLL_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define ALLL_API __attribute__((visibility("default")))
@@ -83,6 +83,11 @@ typedef struct {
 /* alll_multi_*: shard every stored instance of uniform width k <= 8 with at least one clause per device (default: only
  * instances with >= 4096 clauses per device; smaller ones are solved on the first device alone).  For tests. */
 #define ALLL_FLAG_FORCE_SHARDING 64u
+/* The sweep of a bucketed instance with 5 <= k <= 8 streams its five eager literals per clause from four packed planes
+ * (one 128-bit word per clause: leading literals relative to the clause's bucket, the others in 26 / 28 bits; 16 bytes
+ * per clause instead of 20, built at upload next to the plain planes).  This flag keeps the sweep on the plain planes
+ * (comparison / tests); results are identical either way. */
+#define ALLL_FLAG_NO_PACKING 128u
 
 /* Statistics{} of SATInstance.h:25-32 plus device-side counters.
  * n_iterations = resample rounds + 1 (the terminal all-satisfied sweep counts, :261,:285-287);
@@ -345,6 +350,11 @@ ALLL_API int alll_time_sweep(alll_handle h, uint32_t reps, double *ms_per_sweep,
 ALLL_API int alll_launch_count(alll_handle h, uint64_t *n);
 /* Layout facts: {m, k (0 = CSR), n_buckets, m_padded, bytes of literal planes, smem bytes of the sweep}. */
 ALLL_API int alll_layout_info(alll_handle h, uint64_t info[6]);
+
+/* What the sweep of the uploaded instance streams: {1 if it reads the packed eager planes (see ALLL_FLAG_NO_PACKING),
+ *  leading literals stored relative to their bucket (0 when unpacked), bytes streamed per clause (the remaining literals
+ *  are fetched only for clauses that survive the streamed ones), minimum number of bucket-resident leading literals}. */
+ALLL_API int alll_sweep_info(alll_handle h, uint64_t info[4]);
 
 #ifdef __cplusplus
 }

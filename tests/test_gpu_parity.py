@@ -564,3 +564,45 @@ def test_warp_cooperative_csr_sweep(capi, oracle, layout):
                 assert st.n_kernel_launches <= 3          # one cooperative launch (+ counter resets)
         ms, nv = s.time_sweep(3)
         assert ms > 0
+
+
+@pytest.mark.parametrize("k,d", [(5, 10), (6, 16), (7, 28), (8, 32)])
+def test_packed_eager_planes_match_plain_planes_and_oracle(capi, oracle, k, d):
+    """Bucketed instances with 5 <= k <= 8 stream their five eager literals from four packed planes (EagerPack: leading
+    literals relative to the bucket, 16 bytes per clause).  Same violated sets, trajectory and statistics as the plain
+    planes (ALLL_FLAG_NO_PACKING) and as the oracle -- with one and with two bucket-relative leading literals."""
+    from alllsatisfiabilitysolver_b200.instances import bounded_degree_ksat
+
+    n, seed = 60_000, 77
+    lits = bounded_degree_ksat(n, k, d, seed=0xBEEF + k)
+    m = lits.shape[0]
+    off = np.arange(m + 1, dtype=np.uint64) * np.uint64(k)
+    seen_rb = set()
+    for smem in (1024, 4096):                     # 8 / 2 buckets: few buckets => two resident leading literals for every clause
+        with capi.Solver(sweep_smem_bytes=smem) as sp, capi.Solver(sweep_smem_bytes=smem, flags=capi.FLAG_NO_PACKING) as su:
+            sp.upload_fixedk(n, lits)
+            su.upload_fixedk(n, lits)
+            ip, iu = sp.sweep_info(), su.sweep_info()
+            assert ip["packed"] and ip["streamed_bytes_per_clause"] == 16 and not iu["packed"] and iu["streamed_bytes_per_clause"] == 20
+            assert sp.layout_info()["n_buckets"] > 1
+            seen_rb.add(ip["bucket_relative_literals"])
+            sp.randomize(seed)
+            su.randomize(seed)
+            v = oracle.randomize(n, seed)
+            want = oracle.sweep(off, lits.reshape(-1), v)
+            for s in (sp, su):
+                cnt, ids = s.eval()
+                assert cnt == len(want) and np.array_equal(np.sort(ids), want)
+            for rnd in range(3):                  # round by round: U, S, assignment
+                u_o, s_o, r_o = oracle.round(n, off, lits.reshape(-1), v, seed, rnd)
+                for s in (sp, su):
+                    u_g, s_g, r_g = s.round(seed, rnd)
+                    assert np.array_equal(np.sort(u_g), u_o) and np.array_equal(np.sort(s_g), np.sort(s_o)) and r_g == r_o
+                    assert np.array_equal(s.get_assignment(), v)
+            stp, stu = sp.solve(seed), su.solve(seed)     # the rest of the solve in the persistent kernel
+            so = oracle.solve(n, off, lits.reshape(-1), v, seed)
+            for st in (stp, stu):
+                assert st.status == 0 and (st.n_iterations, st.n_resamples, st.sum_mis_size) == (so.n_iterations, so.n_resamples, so.sum_mis_size)
+            assert np.array_equal(sp.get_assignment(), v) and np.array_equal(su.get_assignment(), v)
+            assert oracle.verify(off, lits.reshape(-1), v) and sp.verify()
+    assert seen_rb <= {1, 2} and len(seen_rb) >= 1
