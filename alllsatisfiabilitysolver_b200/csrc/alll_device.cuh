@@ -222,6 +222,9 @@ struct Counters {
     // ALLL_TRACE: inside the Luby steps of round 0 (grid-wide path), as block 0 / thread 0 sees them:
     // [s][0] step entry  [1] own clauses decided (claim reads + stores issued)  [2] CTA reduced + live count published  [3] grid barrier passed
     unsigned long long dbg_step[16][4];
+    // ALLL_TRACE, sharded persistent solve, block 0 / thread 0: [r][0] own sweep body done  [1] record stores fenced (system
+    // scope) + ticket drawn  [2] (the CTA with the last ticket) count + flag stored into every GPU  [3] every rank's flag seen
+    unsigned long long dbg_x[32][4];
 };
 constexpr uint32_t DBG_ROUNDS = 32;
 
@@ -279,10 +282,41 @@ struct MisScratch {
     uint32_t urec_cap;
 };
 
+// One run of clause slots that all belong to the same variable-range bucket.  The bucketing pass lays the clauses out
+// upload chunk by upload chunk (so that it runs behind the H2D copy of each chunk), bucket by bucket inside a chunk, every
+// (chunk, bucket) segment starting on a sweep-tile boundary.  The sweep walks the segments bucket by bucket instead (all
+// chunks' segments of bucket 0, then bucket 1, ...): a CTA's contiguous range of that order stays inside one bucket almost
+// always and stages its slice of the assignment once.  Two tables: in slot order (layout passes) and in sweep order
+// (SweepParams::segs; empty segments dropped), where tile_begin counts tiles of the sweep order.
 struct BucketSeg {
-    uint32_t tile_begin;        // first sweep tile of this bucket
-    uint32_t slot_end;          // one past the last valid clause slot of this bucket
+    uint32_t tile_begin;        // first tile of this segment in the table's own order
+    uint32_t slot_end;          // one past its last valid clause slot
+    uint32_t bucket;            // variable-range bucket its clauses are resident in
+    uint32_t phys_tile;         // first tile in slot space (== tile_begin in the slot-order table)
 };
+
+// What one CTA of the sweep streams: runs of consecutive tiles (slot space), each inside one bucket segment.  The host cuts
+// the sweep order (bucket-major over the segments) into sweep_grid equal ranges and every range into its runs at upload, so
+// the streaming loop works on plain tile numbers -- the loop is latency-bound and has neither registers nor dependent loads
+// to spare for a per-tile mapping (profiles/r02_pipelined_layout.md).
+struct SweepRun {
+    uint32_t tile_begin, tile_end;   // tiles [begin, end) in slot space
+    uint32_t slot_end;               // one past the last valid clause slot of the run's segment
+    uint32_t bucket;                 // variable-range bucket the run's clauses are resident in
+};
+
+// The segment a sweep tile belongs to: the last one that starts at or before it (empty segments share their successor's
+// first tile; segs[0].tile_begin == 0).
+__device__ __forceinline__ uint32_t find_segment(const BucketSeg *__restrict__ segs, uint32_t n_segs, uint32_t tile)
+{
+    uint32_t lo = 0, hi = n_segs;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (segs[mid].tile_begin <= tile) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
 
 struct SweepParams {
     const uint32_t *planes;     // [k][m_pad]
@@ -290,9 +324,12 @@ struct SweepParams {
     const uint32_t *bits;       // bit-packed assignment, n_words (padded to a multiple of 4) words
     uint32_t n_words;
     uint32_t bucket_words;      // words of assignment staged per bucket (multiple of 4)
-    uint32_t n_buckets;
+    uint32_t n_segs;            // bucket segments (BucketSeg)
     uint32_t n_tiles;
-    const BucketSeg *segs;      // [n_buckets]
+    const BucketSeg *segs;      // [n_segs], sweep order
+    const SweepRun *runs;       // the runs of CTA c are runs[run_begin[c] .. run_begin[c + 1]) (sweep_planes kernels, k <= 8)
+    const uint32_t *run_begin;  // [run_grid + 1]
+    uint32_t run_grid;          // grid size the run lists were cut for
     uint32_t *viol;             // out: violated slots
     Counters *ctr;
     uint32_t k;

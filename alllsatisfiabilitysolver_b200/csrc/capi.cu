@@ -48,6 +48,7 @@ struct alll_solver {
     uint32_t k = 0;                      // 0 = CSR
     uint32_t kmax = 0;                   // widest clause
     uint32_t n_words_alloc = 0, bucket_words = 0, n_buckets = 1, n_tiles = 0;
+    uint32_t n_segs = 1;                 // bucket segments of the slot order: upload chunks x buckets (BucketSeg)
     bool resident_all = true;
     uint32_t min_resident = 0;           // measured by the bucketing pass; selects the sweep specialisation
     uint32_t resident_cap = RESIDENT_CAP; // literals per clause placed as bucket-resident (compile-time choice: 2 / 3 / 4 were measured, profiles/)
@@ -57,6 +58,10 @@ struct alll_solver {
     uint4 *d_tail_rows = nullptr;        // literals 5 .. k-1 of every slot in one 16-byte row (5 < k <= 8), read by the sweep for surviving clauses
     bool tail_on = false;
     BucketSeg *d_segs = nullptr;
+    BucketSeg *d_sweep_segs = nullptr;   // the non-empty segments in sweep order (bucket-major over the chunk-major slot order)
+    uint32_t n_sweep_segs = 1;
+    SweepRun *d_runs = nullptr;          // per-CTA run lists of the sweep (SweepRun), cut for sweep_grid CTAs
+    uint32_t *d_run_begin = nullptr;
     uint64_t *d_off = nullptr;
     uint32_t *d_csr_lit = nullptr;       // [csr_l_pad]: the literal array, padded to a multiple of 128 (>= 1 padding position)
     uint64_t n_lit = 0, csr_l_pad = 0;
@@ -171,7 +176,7 @@ void free_instance(alll_handle h)
 
 void release_buffers(alll_handle h)
 {
-    dfree(h->d_planes); dfree(h->d_packed); dfree(h->d_tail_rows); dfree(h->d_orig_id); dfree(h->d_segs); dfree(h->d_off); dfree(h->d_csr_lit); dfree(h->d_csr_start); dfree(h->d_csr_rank);
+    dfree(h->d_planes); dfree(h->d_packed); dfree(h->d_tail_rows); dfree(h->d_orig_id); dfree(h->d_segs); dfree(h->d_sweep_segs); dfree(h->d_runs); dfree(h->d_run_begin); dfree(h->d_off); dfree(h->d_csr_lit); dfree(h->d_csr_start); dfree(h->d_csr_rank);
     dfree(h->d_bits); dfree(h->d_claim); dfree(h->d_urec); dfree(h->d_viol); dfree(h->d_s); dfree(h->d_ids_out);
     dfree(h->d_state); dfree(h->d_bools); dfree(h->d_width); dfree(h->d_width_in); dfree(h->d_tmp_bkt); dfree(h->d_tmp_cnt); dfree(h->d_tmp_err); dfree(h->d_stage);
     dfree(h->d_sh_planes); dfree(h->d_sh_ids); dfree(h->d_sh_iota); dfree(h->d_sh_s); dfree(h->d_sh_state);
@@ -310,11 +315,14 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     }
     h->n_words_alloc = std::max<uint32_t>(n_words4, h->n_buckets * h->bucket_words);
 
-    POOL(h->d_tmp_err, 8);
-    uint32_t *d_err = h->d_tmp_err;                  // [0] error flags, [1] min resident-placed literals per clause
-    const uint32_t err_init[2] = {0u, 0xFFFFFFFFu};
-    CK(cudaMemcpyAsync(d_err, err_init, 8, cudaMemcpyHostToDevice, h->stream));
+    POOL(h->d_tmp_err, 16);
+    uint32_t *d_err = h->d_tmp_err;                  // [0] error flags, [1] min resident-placed literals per clause, [2] tile cursor of the bucketing pass
+    const uint32_t err_init[4] = {0u, 0xFFFFFFFFu, 0u, 0u};
+    CK(cudaMemcpyAsync(d_err, err_init, 16, cudaMemcpyHostToDevice, h->stream));
     std::vector<BucketSeg> segs(h->n_buckets);
+    h->n_segs = h->n_buckets;
+    uint32_t tiles_used = 0;
+    bool fused_pack = false, fused_tail = false;     // written by the bucket scatter already
     h->min_resident = 0;
     h->resident_cap = RESIDENT_CAP;
 
@@ -347,59 +355,94 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
             CK(chunk_ready(i));
             CK(launch_transpose(d_lit, cut[i], cut[i + 1], k, n_vars, h->d_planes, h->m_pad, d_err, h->stream)); h->launches++;
         }
-        segs[0] = BucketSeg{0u, (uint32_t)m};
+        segs[0] = BucketSeg{0u, (uint32_t)m, 0u, 0u};
         if (d_width_in && m) {
             POOL(h->d_width, h->m_pad);
             CK(cudaMemcpyAsync(h->d_width, d_width_in, m, cudaMemcpyDeviceToDevice, h->stream));
         }
     } else {
+        // Bucketing, chunk by chunk behind the H2D copy: count -> scan (device) -> scatter per chunk, no host round trip
+        // in between.  Slot order: chunk-major, bucket by bucket inside a chunk, every (chunk, bucket) segment starting on
+        // a sweep-tile boundary -- so the planes are allocated for the worst-case padding up front and m_pad is their stride.
         const uint32_t bucket_vars = h->bucket_words * 32u, nb = h->n_buckets;
         const uint32_t n_cta = bucket_pass_ctas(m);
+        const uint32_t n_chunks = (uint32_t)cut.size() - 1;
+        h->n_segs = nb * n_chunks;
+        const uint64_t m_pad_max = align_up(m, TILE) + (uint64_t)h->n_segs * TILE;
+        if (m_pad_max >= 0xFFFFFFFFull) return fail(h, ALLL_BAD_ARG, "m too large for the bucketed layout (slot numbers are uint32)");
+        h->m_pad = m_pad_max;
         POOL(h->d_tmp_bkt, std::max<uint64_t>(m, 1));
         POOL(h->d_tmp_cnt, (size_t)nb * std::max<uint32_t>(n_cta, 1) * 4);
+        POOL(h->d_segs, sizeof(BucketSeg) * h->n_segs);
+        POOL(h->d_planes, h->m_pad * k * 4);
+        POOL(h->d_orig_id, h->m_pad * 4);
+        if (d_width_in) POOL(h->d_width, h->m_pad);
+        h->use_orig_id = true;
         uint8_t *d_bkt = h->d_tmp_bkt;
         uint32_t *d_cnt = h->d_tmp_cnt;
+        // The sweep's packed eager planes and tail rows are written by the scatter itself where it can (k > buckets: every
+        // clause has two literals in the bucket that holds most of its variables -- pigeonhole); otherwise by passes below.
+        const bool want_pack = !(h->flags & ALLL_FLAG_NO_PACKING) && !(h->tune & TUNE_NO_PACKED_PLANES) && h->resident_cap == 3 &&
+                               2ull * bucket_vars <= (1ull << 22) && m > 0 && k >= EAGER_PLANES && k <= 8;
+        const bool want_tail = !(h->flags & ALLL_FLAG_NO_PACKING) && !(h->tune & TUNE_NO_TAIL_ROWS) && m > 0 && k > EAGER_PLANES && k <= 8;
+        const bool fuses = bucket_scatter_fuses(k, d_width_in != nullptr);
+        fused_pack = fuses && want_pack && k > nb && n_vars <= (1ull << 27);
+        fused_tail = fuses && want_tail;
+        if (fused_pack) POOL(h->d_packed, h->m_pad * 4 * 4);
+        if (fused_tail) POOL(h->d_tail_rows, h->m_pad * sizeof(uint4));
         for (size_t i = 0; i + 1 < cut.size() && m; i++) {
             CK(chunk_ready(i));
             CK(launch_bucket_count(d_lit, m, cut[i], cut[i + 1], k, n_vars, bucket_vars, nb, d_bkt, d_cnt, d_err, h->stream));
-            h->launches++;
+            CK(launch_bucket_scan(d_cnt, m, cut[i], cut[i + 1], nb, h->d_segs + i * nb, d_err + 2, h->stream));
+            CK(launch_bucket_scatter(d_lit, m, cut[i], cut[i + 1], k, bucket_vars, nb, d_bkt, d_cnt, h->d_planes, h->m_pad, h->d_orig_id,
+                                     d_err + 1, h->resident_cap, d_width_in, d_width_in ? h->d_width : nullptr,
+                                     fused_pack ? h->d_packed : nullptr, fused_tail ? h->d_tail_rows : nullptr, h->stream));
+            h->launches += 3;
         }
-        std::vector<uint32_t> cnt((size_t)nb * n_cta);
-        CK(cudaMemcpyAsync(cnt.data(), d_cnt, cnt.size() * 4, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        // exclusive scan: bucket segments start on a sweep-tile boundary, CTAs keep their order inside a segment
-        uint64_t pos = 0;
-        for (uint32_t b = 0; b < nb; b++) {
-            pos = align_up(pos, TILE);
-            segs[b].tile_begin = (uint32_t)(pos / TILE);
-            for (uint32_t c = 0; c < n_cta; c++) {
-                const uint32_t t = cnt[(size_t)b * n_cta + c];
-                cnt[(size_t)b * n_cta + c] = (uint32_t)pos;
-                pos += t;
-            }
-            segs[b].slot_end = (uint32_t)pos;
-        }
-        h->m_pad = align_up(pos, TILE);
-        CK(cudaMemcpyAsync(d_cnt, cnt.data(), cnt.size() * 4, cudaMemcpyHostToDevice, h->stream));
-        if (h->m_pad) {
-            POOL(h->d_planes, h->m_pad * k * 4);
-            POOL(h->d_orig_id, h->m_pad * 4);
-            if (d_width_in) POOL(h->d_width, h->m_pad);
-        }
-        h->use_orig_id = true;
-        if (m) {
-            CK(launch_bucket_scatter(d_lit, m, k, bucket_vars, nb, d_bkt, d_cnt, h->d_planes, h->m_pad, h->d_orig_id, d_err + 1, h->resident_cap, d_width_in,
-                                     d_width_in ? h->d_width : nullptr, h->stream));
-            h->launches++;
+        if (m == 0) {                                    // no chunk ran: empty segments
+            segs.assign(h->n_segs, BucketSeg{0u, 0u, 0u, 0u});
+            for (uint32_t i = 0; i < h->n_segs; i++) segs[i].bucket = i % nb;
+            CK(cudaMemcpyAsync(h->d_segs, segs.data(), sizeof(BucketSeg) * h->n_segs, cudaMemcpyHostToDevice, h->stream));
         }
     }
-    h->n_tiles = (uint32_t)(h->m_pad / TILE);
-    POOL(h->d_segs, sizeof(BucketSeg) * h->n_buckets);
-    CK(cudaMemcpyAsync(h->d_segs, segs.data(), sizeof(BucketSeg) * h->n_buckets, cudaMemcpyHostToDevice, h->stream));
+    if (h->n_buckets == 1) {
+        tiles_used = (uint32_t)(h->m_pad / TILE);
+        POOL(h->d_segs, sizeof(BucketSeg));
+        CK(cudaMemcpyAsync(h->d_segs, segs.data(), sizeof(BucketSeg), cudaMemcpyHostToDevice, h->stream));
+    }
 
-    uint32_t err_out[2] = {0, 0};
-    CK(cudaMemcpyAsync(err_out, d_err, 8, cudaMemcpyDeviceToHost, h->stream));
+    uint32_t err_out[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(err_out, d_err, 16, cudaMemcpyDeviceToHost, h->stream));
+    if (h->n_buckets > 1 && m) {
+        segs.resize(h->n_segs);
+        CK(cudaMemcpyAsync(segs.data(), h->d_segs, sizeof(BucketSeg) * h->n_segs, cudaMemcpyDeviceToHost, h->stream));
+    }
     CK(cudaStreamSynchronize(h->stream));
+    if (h->n_buckets > 1) tiles_used = err_out[2];
+    h->n_tiles = tiles_used;
+    std::vector<BucketSeg> sw;                            // sweep order: bucket by bucket over the chunk-major slot order, empty segments dropped
+    {
+        if (h->n_buckets > 1 && m) {
+            const uint32_t nb = h->n_buckets, n_chunks = h->n_segs / nb;
+            uint32_t at = 0;
+            for (uint32_t bkt = 0; bkt < nb; bkt++)
+                for (uint32_t c = 0; c < n_chunks; c++) {
+                    const BucketSeg &g = segs[c * nb + bkt];
+                    const uint32_t t_end = (uint32_t)(((uint64_t)g.slot_end + TILE - 1) / TILE);
+                    if (t_end <= g.tile_begin) continue;
+                    sw.push_back(BucketSeg{at, g.slot_end, bkt, g.tile_begin});
+                    at += t_end - g.tile_begin;
+                }
+            if (at != tiles_used) return fail(h, ALLL_CUDA_ERROR, "internal: bucket segments do not cover the tiles the scatter used");
+        } else if (h->n_buckets == 1) {
+            sw.push_back(segs[0]);
+        }
+        if (sw.empty()) sw.push_back(BucketSeg{0u, 0u, 0u, 0u});
+        h->n_sweep_segs = (uint32_t)sw.size();
+        POOL(h->d_sweep_segs, sizeof(BucketSeg) * sw.size());
+        CK(cudaMemcpyAsync(h->d_sweep_segs, sw.data(), sizeof(BucketSeg) * sw.size(), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));             // (`sw` is pageable and goes out of scope)
+    }
     if (err_out[0]) { free_instance(h); return fail(h, ALLL_BAD_ARG, "a literal references a variable >= n_vars"); }
     if (h->n_buckets > 1 && m > 0 && err_out[1] != 0xFFFFFFFFu) h->min_resident = err_out[1];
 
@@ -411,14 +454,15 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
         const uint64_t glob_limit = rb >= 2 ? (1ull << 27) : (1ull << 25);
         h->packed_on = h->n_buckets > 1 && m > 0 && k >= EAGER_PLANES && k <= 8 && rb >= 1 && h->resident_cap == 3 &&
                        2ull * h->bucket_words * 32u <= (1ull << 22) && n_vars <= glob_limit && !(h->flags & ALLL_FLAG_NO_PACKING) && !(h->tune & TUNE_NO_PACKED_PLANES);
-        if (h->packed_on) {
+        if (fused_pack && rb < 2) return fail(h, ALLL_CUDA_ERROR, "internal: packed planes written for two resident literals, but a clause has fewer");
+        if (h->packed_on && !fused_pack) {
             POOL(h->d_packed, h->m_pad * 4 * 4);
-            CK(launch_pack_eager(h->d_planes, h->m_pad, h->d_segs, h->n_buckets, h->bucket_words * 32u, rb, h->d_packed, h->stream));
+            CK(launch_pack_eager(h->d_planes, h->m_pad, h->d_segs, h->n_segs, h->bucket_words * 32u, rb, h->d_packed, h->stream));
             h->launches++;
         }
     }
     h->tail_on = m > 0 && k > EAGER_PLANES && k <= 8 && !(h->flags & ALLL_FLAG_NO_PACKING) && !(h->tune & TUNE_NO_TAIL_ROWS);
-    if (h->tail_on) {
+    if (h->tail_on && !fused_tail) {
         POOL(h->d_tail_rows, h->m_pad * sizeof(uint4));
         CK(launch_tail_rows(h->d_planes, h->m_pad, k, h->d_tail_rows, h->stream)); h->launches++;
     }
@@ -438,6 +482,30 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     CK(configure_sweep_planes(sp, h->resident_all));
     h->sweep_grid = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)h->sm_count, h->n_tiles));
     {
+        // per-CTA run lists: CTA c sweeps tiles [c * n_tiles / grid, (c + 1) * n_tiles / grid) of the sweep order, cut at segment ends
+        std::vector<SweepRun> runs;
+        std::vector<uint32_t> run_begin(h->sweep_grid + 1, 0u);
+        size_t sg = 0;
+        for (uint32_t c = 0; c < h->sweep_grid; c++) {
+            run_begin[c] = (uint32_t)runs.size();
+            uint32_t t = (uint32_t)(((uint64_t)c * h->n_tiles) / h->sweep_grid);
+            const uint32_t t1 = (uint32_t)(((uint64_t)(c + 1) * h->n_tiles) / h->sweep_grid);
+            while (t < t1) {
+                while (sg + 1 < sw.size() && sw[sg + 1].tile_begin <= t) ++sg;
+                const uint32_t seg_end = sg + 1 < sw.size() ? sw[sg + 1].tile_begin : h->n_tiles;
+                const uint32_t e = std::min(t1, seg_end), delta = sw[sg].phys_tile - sw[sg].tile_begin;
+                runs.push_back(SweepRun{t + delta, e + delta, sw[sg].slot_end, sw[sg].bucket});
+                t = e;
+            }
+        }
+        run_begin[h->sweep_grid] = (uint32_t)runs.size();
+        POOL(h->d_runs, sizeof(SweepRun) * std::max<size_t>(runs.size(), 1));
+        POOL(h->d_run_begin, sizeof(uint32_t) * run_begin.size());
+        if (!runs.empty()) CK(cudaMemcpyAsync(h->d_runs, runs.data(), sizeof(SweepRun) * runs.size(), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_run_begin, run_begin.data(), sizeof(uint32_t) * run_begin.size(), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));             // (pageable sources going out of scope)
+    }
+    {
         int ok = 0, coop = 0;
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
         if (coop && m > 0 && !h->use_width) CK(configure_solve_persistent(sp, h->resident_all, h->kmax, &ok));
@@ -456,7 +524,7 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
         POOL(h->d_visited, h->visited_words * 4);
         POOL(h->d_incr_tmp, (n_vars + nb + 4) * 4);                 // cursors | block sums | total
         CK(cudaMemsetAsync(h->d_visited, 0, h->visited_words * 4, h->stream));
-        CK(launch_incr_build(h->d_planes, h->m_pad, k, h->incr_stride, h->d_segs, h->n_buckets, n_vars, h->d_occ_off,
+        CK(launch_incr_build(h->d_planes, h->m_pad, k, h->incr_stride, h->d_segs, h->n_segs, n_vars, h->d_occ_off,
                              h->d_incr_tmp, h->d_incr_tmp + n_vars, h->d_rows, h->d_occ, h->d_incr_tmp + n_vars + nb,
                              h->use_width ? h->d_width : nullptr, h->stream));
         h->launches += 5;
@@ -487,8 +555,9 @@ SweepParams sweep_params(alll_handle h, uint32_t p2p_parity, uint32_t p2p_tag, u
 {
     SweepParams sp{};
     sp.planes = h->d_planes; sp.m_pad = h->m_pad; sp.bits = h->d_bits; sp.n_words = h->n_words_alloc;
-    sp.bucket_words = h->bucket_words; sp.n_buckets = h->n_buckets; sp.n_tiles = h->n_tiles;
-    sp.segs = h->d_segs; sp.viol = h->d_viol; sp.ctr = h->d_ctr; sp.k = h->k; sp.min_resident = h->min_resident;
+    sp.bucket_words = h->bucket_words; sp.n_segs = h->n_sweep_segs; sp.n_tiles = h->n_tiles;
+    sp.runs = h->d_runs; sp.run_begin = h->d_run_begin; sp.run_grid = h->sweep_grid;
+    sp.segs = h->d_sweep_segs; sp.viol = h->d_viol; sp.ctr = h->d_ctr; sp.k = h->k; sp.min_resident = h->min_resident;
     sp.resident_cap = h->resident_cap; sp.eager = (h->flags >> 8) & 0xFFu; sp.prefetch_tiles = prefetch_distance(h->flags);
     sp.round = round;
     sp.tune = h->tune;
@@ -560,6 +629,12 @@ void print_phases(const Counters &c, uint64_t rounds)
         fprintf(stderr, "[alll phases] round %llu: path=%llu steps=%llu | prev round end -> sweep entry %.1f | mis entry %.1f "
                         "|U| known %.1f gather %.1f steps %.1f resample %.1f finished %.1f (us after sweep entry)\n",
                 (unsigned long long)r, d[7] & 0xFF, d[7] >> 8, gap, us(1), us(2), us(3), us(4), us(5), us(6));
+        const unsigned long long *x = c.dbg_x[r];
+        if (x[0] >= d[0] && x[3] >= x[0])        // sharded persistent solve: the exchange between sweep and independent set
+            fprintf(stderr, "[alll exchange] round %llu: own sweep done %.1f | fenced + ticket %.1f | last CTA stored the flags %.1f | all ranks seen %.1f "
+                            "(us after sweep entry; epoch ns of sweep entry %llu)\n",
+                    (unsigned long long)r, (double)(x[0] - d[0]) * 1e-3, (double)(x[1] - d[0]) * 1e-3, (double)(x[2] - d[0]) * 1e-3,
+                    (double)(x[3] - d[0]) * 1e-3, d[0]);
     }
 }
 

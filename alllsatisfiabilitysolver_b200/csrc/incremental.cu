@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256) incr_count_rows_kernel(const uint32_t *__
     if (p >= m_pad) return;
     // valid slot?  (bucket segments are padded to tile boundaries)
     uint32_t b = 0;
-    while (b + 1 < n_buckets && (uint64_t)segs[b + 1].tile_begin * TILE <= p) ++b;
+    b = find_segment(segs, n_buckets, (uint32_t)(p / TILE));
     const bool valid = p < segs[b].slot_end;
     uint32_t first = 0;
     for (uint32_t j = 0; j < stride; j++) {
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) incr_fill_kernel(const uint32_t *__restri
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= m_pad) return;
     uint32_t b = 0;
-    while (b + 1 < n_buckets && (uint64_t)segs[b + 1].tile_begin * TILE <= p) ++b;
+    b = find_segment(segs, n_buckets, (uint32_t)(p / TILE));
     if (p >= segs[b].slot_end) return;
     const uint32_t kw = width ? width[p] : k;
     for (uint32_t j = 0; j < kw; j++) {

@@ -89,13 +89,14 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) bucket_scatter_kernel(const ui
                                                                          uint32_t *__restrict__ orig_id,
                                                                          uint32_t *__restrict__ min_resident, uint32_t resident_cap,
                                                                          const uint8_t *__restrict__ width_in,
-                                                                         uint8_t *__restrict__ width_out)
+                                                                         uint8_t *__restrict__ width_out, uint32_t cta0, uint32_t n_cta)
 {
     __shared__ uint16_t warp_cnt[(LAYOUT_THREADS / 32) * MAX_BUCKETS];   // [warp][bucket], then exclusive over warps
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     for (uint32_t i = threadIdx.x; i < (LAYOUT_THREADS / 32) * n_buckets; i += blockDim.x) warp_cnt[i] = 0;
     __syncthreads();
-    const uint64_t c = (uint64_t)blockIdx.x * LAYOUT_THREADS + threadIdx.x;
+    const uint32_t cta = cta0 + blockIdx.x;              // logical CTA of the whole pass (this launch covers one upload chunk)
+    const uint64_t c = (uint64_t)cta * LAYOUT_THREADS + threadIdx.x;
     const bool active = c < m;
     const uint32_t act = __ballot_sync(0xffffffffu, active);
     uint32_t b = 0, rank = 0;
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) bucket_scatter_kernel(const ui
     }
     __syncthreads();
     if (!active) return;
-    const uint64_t dst = (uint64_t)cta_base[(uint64_t)b * gridDim.x + blockIdx.x] + warp_cnt[warp * n_buckets + b] + rank;
+    const uint64_t dst = (uint64_t)cta_base[(uint64_t)b * n_cta + cta] + warp_cnt[warp * n_buckets + b] + rank;
     orig_id[dst] = (uint32_t)c;
     if (width_in) width_out[dst] = width_in[c];
     const uint32_t lo = b * bucket_vars;
@@ -233,14 +234,17 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) bucket_scatter_staged_kernel(c
                                                                                 const uint32_t *__restrict__ cta_base,
                                                                                 uint32_t *__restrict__ planes, uint64_t m_pad,
                                                                                 uint32_t *__restrict__ orig_id,
-                                                                                uint32_t *__restrict__ min_resident, uint32_t resident_cap)
+                                                                                uint32_t *__restrict__ min_resident, uint32_t resident_cap,
+                                                                                uint32_t cta0, uint32_t n_cta,
+                                                                                uint32_t *__restrict__ packed, uint4 *__restrict__ tail_rows)
 {
     __shared__ uint16_t warp_cnt[(LAYOUT_THREADS / 32) * MAX_BUCKETS];   // [warp][bucket], then exclusive over warps
     __shared__ uint32_t bucket_off[MAX_BUCKETS + 1];                     // CTA-local start of every bucket's run
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     for (uint32_t i = threadIdx.x; i < (LAYOUT_THREADS / 32) * n_buckets; i += blockDim.x) warp_cnt[i] = 0;
     __syncthreads();
-    const uint64_t c = (uint64_t)blockIdx.x * LAYOUT_THREADS + threadIdx.x;
+    const uint32_t cta = cta0 + blockIdx.x;              // logical CTA of the whole pass (this launch covers one upload chunk)
+    const uint64_t c = (uint64_t)cta * LAYOUT_THREADS + threadIdx.x;
     const bool active = c < m;
     const uint32_t act = __ballot_sync(0xffffffffu, active);
     uint32_t b = 0, rank = 0;
@@ -295,29 +299,44 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) bucket_scatter_staged_kernel(c
     if (t >= bucket_off[n_buckets]) return;
     uint32_t bb = 0;
     while (bucket_off[bb + 1] <= t) ++bb;
-    const uint64_t dst = (uint64_t)cta_base[(uint64_t)bb * gridDim.x + blockIdx.x] + (t - bucket_off[bb]);
+    const uint64_t dst = (uint64_t)cta_base[(uint64_t)bb * n_cta + cta] + (t - bucket_off[bb]);
     for (uint32_t j = 0; j < k; j++) planes[(uint64_t)j * m_pad + dst] = stage_smem[j * LAYOUT_THREADS + t];
     orig_id[dst] = stage_smem[k * LAYOUT_THREADS + t];
+    // The sweep's own copies of the clause, written while its literals are at hand instead of in passes of their own:
+    // packed eager planes (caller guarantees two bucket-resident leading literals for every clause: k > n_buckets) ...
+    if (packed != nullptr) {
+        uint32_t l[EagerPack<2>::N], w[EagerPack<2>::WORDS];
+#pragma unroll
+        for (int j = 0; j < EagerPack<2>::N; j++) l[j] = stage_smem[j * LAYOUT_THREADS + t];
+        l[0] -= 2u * bb * bucket_vars;
+        l[1] -= 2u * bb * bucket_vars;
+        EagerPack<2>::encode(l, w);
+#pragma unroll
+        for (int i = 0; i < EagerPack<2>::WORDS; i++) packed[(uint64_t)i * m_pad + dst] = w[i];
+    }
+    // ... and the tail row (literals 5 .. k-1 side by side)
+    if (tail_rows != nullptr)
+        tail_rows[dst] = make_uint4(k > 5 ? stage_smem[5 * LAYOUT_THREADS + t] : 0u, k > 6 ? stage_smem[6 * LAYOUT_THREADS + t] : 0u,
+                                    k > 7 ? stage_smem[7 * LAYOUT_THREADS + t] : 0u, 0u);
 }
 
 // ---- packed eager planes (alll_device.cuh: EagerPack) -- one pass over the finished planes ------------------------
 template <int RB>
 __global__ void __launch_bounds__(256) pack_eager_kernel(const uint32_t *__restrict__ planes, uint64_t m_pad,
-                                                          const BucketSeg *__restrict__ segs, uint32_t n_buckets,
+                                                          const BucketSeg *__restrict__ segs, uint32_t n_buckets /* segments */,
                                                           uint32_t bucket_vars, uint32_t *__restrict__ packed)
 {
     const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= m_pad) return;
     const uint32_t tile = (uint32_t)(slot / TILE);
-    uint32_t b = 0;
-    while (b + 1 < n_buckets && segs[b + 1].tile_begin <= tile) ++b;
+    const uint32_t b = find_segment(segs, n_buckets, tile);
     uint32_t w[EagerPack<RB>::WORDS] = {0u, 0u, 0u, 0u};
     if (slot < segs[b].slot_end) {                       // (padding slots are never evaluated: all-zero words)
         uint32_t l[EagerPack<RB>::N];
 #pragma unroll
         for (int j = 0; j < EagerPack<RB>::N; j++) l[j] = planes[(uint64_t)j * m_pad + slot];
 #pragma unroll
-        for (int j = 0; j < RB; j++) l[j] -= 2u * b * bucket_vars;
+        for (int j = 0; j < RB; j++) l[j] -= 2u * segs[b].bucket * bucket_vars;
         EagerPack<RB>::encode(l, w);
     }
 #pragma unroll
@@ -352,21 +371,81 @@ cudaError_t launch_pack_eager(const uint32_t *planes, uint64_t m_pad, const Buck
     return cudaGetLastError();
 }
 
-cudaError_t launch_bucket_scatter(const uint32_t *lit, uint64_t m, uint32_t k, uint32_t bucket_vars, uint32_t n_buckets,
-                                  const uint8_t *bkt, const uint32_t *cta_base, uint32_t *planes, uint64_t m_pad,
-                                  uint32_t *orig_id, uint32_t *min_resident, uint32_t resident_cap, const uint8_t *width_in,
-                                  uint8_t *width_out, cudaStream_t s)
+// ---- between the two bucketing passes of one upload chunk: exclusive scan on the device ----------------------------
+// cta_counts[b * n_cta + cta] for the chunk's CTAs [cta0, cta1) -> first slot of that CTA's clauses of bucket b; the chunk's
+// n_buckets segments (each starting on a sweep-tile boundary at *tile_cursor, which moves on) -> segs_out[0 .. n_buckets).
+// One CTA: warp w scans buckets w, w + 32, ...  No host round trip, so the scatter of a chunk follows its count directly
+// and both run behind the H2D copy of the next chunk.
+__global__ void __launch_bounds__(1024) bucket_scan_kernel(uint32_t *__restrict__ cta_counts, uint32_t n_cta, uint32_t cta0,
+                                                            uint32_t cta1, uint32_t n_buckets, BucketSeg *__restrict__ segs_out,
+                                                            uint32_t *__restrict__ tile_cursor)
 {
+    __shared__ uint32_t tot[MAX_BUCKETS], base[MAX_BUCKETS];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    for (uint32_t b = warp; b < n_buckets; b += 32) {
+        uint32_t run = 0;
+        for (uint32_t i0 = cta0; i0 < cta1; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            const uint32_t t = i < cta1 ? cta_counts[(uint64_t)b * n_cta + i] : 0u;
+            uint32_t inc = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((int)lane >= o) inc += x;
+            }
+            if (i < cta1) cta_counts[(uint64_t)b * n_cta + i] = run + inc - t;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) tot[b] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t pos = (uint64_t)*tile_cursor * TILE;
+        for (uint32_t b = 0; b < n_buckets; b++) {
+            base[b] = (uint32_t)pos;
+            segs_out[b] = BucketSeg{(uint32_t)(pos / TILE), (uint32_t)(pos + tot[b]), b, (uint32_t)(pos / TILE)};
+            pos = (pos + tot[b] + TILE - 1) / TILE * TILE;
+        }
+        *tile_cursor = (uint32_t)(pos / TILE);
+    }
+    __syncthreads();
+    const uint32_t span = cta1 - cta0;
+    for (uint64_t x = threadIdx.x; x < (uint64_t)n_buckets * span; x += blockDim.x) {
+        const uint32_t b = (uint32_t)(x / span), i = cta0 + (uint32_t)(x % span);
+        cta_counts[(uint64_t)b * n_cta + i] += base[b];
+    }
+}
+
+cudaError_t launch_bucket_scan(uint32_t *cta_counts, uint64_t m, uint64_t c0, uint64_t c1, uint32_t n_buckets, BucketSeg *segs_out,
+                               uint32_t *tile_cursor, cudaStream_t s)
+{
+    bucket_scan_kernel<<<1, 1024, 0, s>>>(cta_counts, bucket_pass_ctas(m), (uint32_t)(c0 / LAYOUT_THREADS),
+                                          (uint32_t)((c1 + LAYOUT_THREADS - 1) / LAYOUT_THREADS), n_buckets, segs_out, tile_cursor);
+    return cudaGetLastError();
+}
+
+// true when launch_bucket_scatter can write the packed eager planes / tail rows itself (the shared-memory staged kernel)
+bool bucket_scatter_fuses(uint32_t k, bool with_widths) { return k >= EAGER_PLANES && k <= 8 && !with_widths; }
+
+// clauses [c0, c1) of the m the whole pass covers (c0 a multiple of bucket_pass_clauses_per_cta())
+cudaError_t launch_bucket_scatter(const uint32_t *lit, uint64_t m, uint64_t c0, uint64_t c1, uint32_t k, uint32_t bucket_vars,
+                                  uint32_t n_buckets, const uint8_t *bkt, const uint32_t *cta_base, uint32_t *planes, uint64_t m_pad,
+                                  uint32_t *orig_id, uint32_t *min_resident, uint32_t resident_cap, const uint8_t *width_in,
+                                  uint8_t *width_out, uint32_t *packed, uint4 *tail_rows, cudaStream_t s)
+{
+    if (c1 <= c0) return cudaSuccess;
+    if ((packed || tail_rows) && !bucket_scatter_fuses(k, width_in != nullptr)) return cudaErrorInvalidValue;
+    const uint32_t grid = blocks_for(c1 - c0, LAYOUT_THREADS), cta0 = (uint32_t)(c0 / LAYOUT_THREADS), n_cta = bucket_pass_ctas(m);
     if (k <= 8 && width_in == nullptr) {
         // static (17 KB) + dynamic shared memory exceed the 48 KB default: opt in (per device, cheap, idempotent)
         const cudaError_t e = cudaFuncSetAttribute(bucket_scatter_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    (int)((k + 1) * LAYOUT_THREADS * 4));
         if (e != cudaSuccess) return e;
-        bucket_scatter_staged_kernel<<<bucket_pass_ctas(m), LAYOUT_THREADS, (size_t)(k + 1) * LAYOUT_THREADS * 4, s>>>(
-            lit, m, k, bucket_vars, n_buckets, bkt, cta_base, planes, m_pad, orig_id, min_resident, resident_cap);
+        bucket_scatter_staged_kernel<<<grid, LAYOUT_THREADS, (size_t)(k + 1) * LAYOUT_THREADS * 4, s>>>(
+            lit, m, k, bucket_vars, n_buckets, bkt, cta_base, planes, m_pad, orig_id, min_resident, resident_cap, cta0, n_cta, packed, tail_rows);
     } else
-        bucket_scatter_kernel<<<bucket_pass_ctas(m), LAYOUT_THREADS, 0, s>>>(lit, m, k, bucket_vars, n_buckets, bkt, cta_base,
-                                                                               planes, m_pad, orig_id, min_resident, resident_cap, width_in, width_out);
+        bucket_scatter_kernel<<<grid, LAYOUT_THREADS, 0, s>>>(lit, m, k, bucket_vars, n_buckets, bkt, cta_base, planes, m_pad, orig_id,
+                                                               min_resident, resident_cap, width_in, width_out, cta0, n_cta);
     return cudaGetLastError();
 }
 

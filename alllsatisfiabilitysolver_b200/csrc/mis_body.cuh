@@ -130,6 +130,9 @@ __device__ __forceinline__ void st(uint32_t *p, uint32_t v)
 }
 } // namespace gm
 
+// acquire / release at system scope without the sequential-consistency part of __threadfence_system() (membar.sys)
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
 __device__ __forceinline__ unsigned long long ld_claim(const unsigned long long *p) { return gm::ld_cg(p); }
 __device__ __forceinline__ unsigned int ld_u32(const unsigned int *p) { return gm::ld_cg(p); }
 
@@ -268,7 +271,7 @@ __device__ __forceinline__ uint32_t p2p_wait(const MisParams &p, uint32_t *s_pre
                 }
             }
         }
-        __threadfence_system();                       // acquire: the records behind the flags are now visible
+        fence_acq_rel_sys();                          // acquire: the records behind the flags are now visible
         if (why == 0 && lane == 0 && *(volatile unsigned int *)&me->abort == aval) why = 3;   // a peer overflowed even though every flag arrived
         const bool over = cnt[0] > L.cap || cnt[1] > L.cap;
         const unsigned int any_timeout = __ballot_sync(0xffffffffu, why == 2);

@@ -53,23 +53,31 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(cons
         const bool incremental = ip.rows != nullptr && round > 0 && gm::ld_cg(&c->incr_next) != 0;
         if (incremental) incr_eval_body(ip, gm::ld_cg(&c->last_n_s), &c->n_viol_pp[par], IncrP2P{sp.p2p, s_prefix, par, sp.orig_id, sp.id_base, c, sp.p2p_epoch + 1u});
         else sweep_planes_body<K, RB, RC, E, false, PK>(sp, &c->n_viol_pp[par], par, rec_on);
-        if (p2p) {                                       // this CTA's record stores (NVLink) are ordered before the barrier
-            __syncthreads();
-            if (threadIdx.x == 0) __threadfence_system();
-        }
-        bar.sync();
         uint32_t n_u;
         if (p2p) {
-            // fused exchange: the violated records went straight into every GPU's region during the sweep; publish our
-            // count + arrival flag everywhere, then wait for every peer's flag of this round
-            if (lead) {
-                const P2PLink &L = *sp.p2p;
-                // (every CTA's record stores were fenced at system scope before the grid barrier above)
-                const unsigned long long word = ((unsigned long long)tag << 32) | gm::ld_cg(&c->n_viol_pp[par]);
-                for (uint32_t q = 0; q < L.world; q++) *(volatile unsigned long long *)&L.hdr[q]->cf[par][L.rank] = word;
+            // Fused exchange: the violated records went straight into every GPU's region during the sweep.  Every CTA orders
+            // its record stores (NVLink) before its ticket; the CTA that draws the last ticket stores this rank's count +
+            // arrival flag into every GPU, our own included -- so the wait for all flags of the round below is also the
+            // grid barrier of this GPU (no grid.sync() on the exchange's critical path).
+            if (lead && round < DBG_ROUNDS) c->dbg_x[round][0] = global_ns();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                fence_acq_rel_sys();
+                const unsigned int t = atomicAdd(&c->cta_done, 1u);
+                if (lead && round < DBG_ROUNDS) c->dbg_x[round][1] = global_ns();
+                if (t == gridDim.x - 1) {
+                    c->cta_done = 0;                     // next round's tickets are drawn behind two grid barriers
+                    fence_acq_rel_sys();                 // the other CTAs' tickets (and what they fenced) happen before our flag
+                    const P2PLink &L = *sp.p2p;
+                    const unsigned long long word = ((unsigned long long)tag << 32) | gm::ld_cg(&c->n_viol_pp[par]);
+                    for (uint32_t q = 0; q < L.world; q++) *(volatile unsigned long long *)&L.hdr[q]->cf[par][L.rank] = word;
+                    if (round < DBG_ROUNDS) c->dbg_x[round][2] = global_ns();
+                }
             }
             n_u = p2p_wait(mp, s_prefix);
+            if (lead && round < DBG_ROUNDS) c->dbg_x[round][3] = global_ns();
         } else {
+            bar.sync();
             n_u = gm::ld_cg(&c->n_viol_pp[par]);
         }
         if (lead) {
@@ -180,6 +188,7 @@ cudaError_t launch_solve_persistent(const SweepParams &p, bool resident_all, uin
                                     uint32_t max_rounds, uint32_t epoch, const IncrParams *incr, uint32_t visited_words,
                                     uint32_t incr_max_vars, cudaStream_t s)
 {
+    if (p.runs == nullptr || grid != p.run_grid) return cudaErrorInvalidValue;      // the run lists are cut for one grid size
     const size_t smem = persistent_smem_bytes(p.bucket_words, kmax);
     MisParams mp{};
     mp.cv = cv; mp.viol = p.p2p ? nullptr : p.viol; mp.state = state; mp.s_slots = s_slots;

@@ -48,8 +48,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_planes_generic_kernel(
 
     for (uint32_t tile = t0; tile < t1; ++tile) {
         cur.enter(p, tile);
-        const uint32_t vbase = cur.b * bucket_vars;
-        const uint32_t slot0 = tile * TILE + threadIdx.x * CLAUSES_PER_THREAD;
+        const uint32_t vbase = cur.bucket * bucket_vars;
+        const uint32_t slot0 = cur.phys * TILE + threadIdx.x * CLAUSES_PER_THREAD;
         const uint32_t *src = p.planes + slot0;
         uint32_t alive = 0;
 #pragma unroll
@@ -100,6 +100,7 @@ static cudaError_t sweep_op(const SweepParams &p, bool resident_all, uint32_t gr
 {
     const size_t smem = sweep_smem_bytes_for(p.bucket_words);
     if (p.k > 8) return resident_all ? launch_generic<true>(p, grid, smem, s, configure) : launch_generic<false>(p, grid, smem, s, configure);
+    if (!configure && (p.runs == nullptr || grid != p.run_grid)) return cudaErrorInvalidValue;   // the run lists are cut for one grid size
     SweepOp op{p, grid, smem, s, configure};
     return dispatch_variant(p, resident_all, op);
 }

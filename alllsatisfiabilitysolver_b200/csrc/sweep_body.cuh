@@ -162,36 +162,49 @@ __device__ __forceinline__ uint32_t literal_true(uint32_t l, const uint32_t *gbi
 } // namespace
 
 // ---- per-tile bookkeeping shared by both plane kernels ---------------------------------------------
-struct TileCursor {
-    uint32_t b, bucket_tile_end, slot_end, loaded;
+// Stages a bucket's slice of the assignment into shared memory (whole CTA).
+__device__ __forceinline__ void stage_bucket(const SweepParams &p, uint32_t bucket)
+{
+    __syncthreads();                      // everyone is done with the previous bucket's bits
+    const uint4 *src = reinterpret_cast<const uint4 *>(p.bits + (uint64_t)bucket * p.bucket_words);
+    for (uint32_t i = threadIdx.x; i < p.bucket_words / 4; i += SWEEP_THREADS)
+        reinterpret_cast<uint4 *>(g_smem)[i] = __ldcg(src + i);      // coherent (L2) read: see ld_bits
+    __syncthreads();
+}
 
+// Tile-by-tile walk over the sweep order (the run-time-width kernel; the k <= 8 kernels work on SweepRun lists instead).
+struct TileCursor {
+    uint32_t b, bucket, bucket_tile_end, slot_end, loaded;    // b: segment index (sweep order); bucket / loaded: variable-range bucket ids
+    uint32_t phys, delta;                                     // the current tile's number in slot space; slot space - sweep order within the segment
+
+    __device__ __forceinline__ void read(const SweepParams &p)
+    {
+        bucket_tile_end = (b + 1 < p.n_segs) ? p.segs[b + 1].tile_begin : p.n_tiles;
+        slot_end = p.segs[b].slot_end;
+        bucket = p.segs[b].bucket;
+        delta = p.segs[b].phys_tile - p.segs[b].tile_begin;
+    }
     __device__ __forceinline__ void init(const SweepParams &p, uint32_t t0)
     {
-        b = 0;
-        while (b + 1 < p.n_buckets && p.segs[b + 1].tile_begin <= t0) ++b;
-        bucket_tile_end = (b + 1 < p.n_buckets) ? p.segs[b + 1].tile_begin : p.n_tiles;
-        slot_end = p.segs[b].slot_end;
         loaded = 0xFFFFFFFFu;
+        phys = t0;
+        b = find_segment(p.segs, p.n_segs, t0);
+        read(p);
     }
-    // Moves to `tile`; returns true when its bucket differs from the staged one (caller must then stage()).
+    // Moves to `tile` of the sweep order; returns true when its bucket differs from the staged one (caller must then stage()).
     __device__ __forceinline__ bool advance(const SweepParams &p, uint32_t tile)
     {
         while (tile >= bucket_tile_end) {
             ++b;
-            bucket_tile_end = (b + 1 < p.n_buckets) ? p.segs[b + 1].tile_begin : p.n_tiles;
-            slot_end = p.segs[b].slot_end;
+            read(p);
         }
-        return b != loaded;
+        phys = tile + delta;
+        return bucket != loaded;
     }
-    // Stages bucket b's slice of the assignment into shared memory (whole CTA).
     __device__ __forceinline__ void stage(const SweepParams &p)
     {
-        __syncthreads();                      // everyone is done with the previous bucket's bits
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.bits + (uint64_t)b * p.bucket_words);
-        for (uint32_t i = threadIdx.x; i < p.bucket_words / 4; i += SWEEP_THREADS)
-            reinterpret_cast<uint4 *>(g_smem)[i] = __ldcg(src + i);      // coherent (L2) read: see ld_bits
-        __syncthreads();
-        loaded = b;
+        stage_bucket(p, bucket);
+        loaded = bucket;
     }
     __device__ __forceinline__ void enter(const SweepParams &p, uint32_t tile)
     {
@@ -381,72 +394,68 @@ __device__ __forceinline__ void sweep_planes_body(const SweepParams &p, unsigned
     WarpCompactor out{p.bucket_words + warp * WBUF, p.viol, p.ctr, n_viol_ctr, p2p_parity, rec_on, 0u, lane, &p};
     SurvivorQueue<K, E, RESIDENT_ALL> parked{p.bucket_words + (SWEEP_THREADS / 32) * WBUF + warp * QBUF, 0u, lane};
 
-    const uint32_t t0 = (uint32_t)(((uint64_t)blockIdx.x * p.n_tiles) / gridDim.x);
-    const uint32_t t1 = (uint32_t)(((uint64_t)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
-    if (t0 >= t1) {
-        if (TICKET) p2p_publish(p);
-        return;
-    }
-
-    TileCursor cur;
-    cur.init(p, t0);
+    // this CTA's runs (SweepRun): consecutive tiles of one bucket segment each
+    const uint32_t r0 = __ldg(p.run_begin + blockIdx.x), r1 = __ldg(p.run_begin + blockIdx.x + 1);
     const uint32_t bucket_vars = p.bucket_words * 32u;
     const uint32_t *const stream = PK ? p.packed : p.planes;
     const uint32_t *base = stream + threadIdx.x * CLAUSES_PER_THREAD;
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(g_smem);
+    const uint32_t dist = p.prefetch_tiles;
+    uint32_t loaded = 0xFFFFFFFFu;               // bucket whose slice of the assignment is staged
+    uint32_t vbase = 0;
 
-    auto load = [&](uint4 (&L)[NS], uint32_t tile) {
-        const uint32_t *src = base + (uint64_t)tile * TILE;
-#pragma unroll
-        for (int j = 0; j < NS; j++) L[j] = ld_stream_v4(src + (uint64_t)j * p.m_pad);
-    };
-    auto process = [&](const uint4 (&S)[NS], uint32_t tile) {
-        const uint32_t prev_vbase = cur.b * bucket_vars;
-        if (cur.advance(p, tile)) {
-            if constexpr (E < K) parked.drain(0u, out, p, prev_vbase, bucket_vars);   // parked clauses belong to the old bucket
-            cur.stage(p);
+    for (uint32_t r = r0; r < r1; r++) {
+        const uint4 run = __ldg(reinterpret_cast<const uint4 *>(p.runs) + r);     // {tile_begin, tile_end, slot_end, bucket}
+        const uint32_t t0 = run.x, t1 = run.y, slot_end = run.z;
+        if (run.w != loaded) {
+            if constexpr (E < K) parked.drain(0u, out, p, vbase, bucket_vars);    // parked clauses belong to the old bucket
+            stage_bucket(p, run.w);
+            loaded = run.w;
+            vbase = run.w * bucket_vars;
         }
-        const uint32_t slot0 = tile * TILE + threadIdx.x * CLAUSES_PER_THREAD;
-        uint32_t valid = 0;
+
+        auto load = [&](uint4 (&L)[NS], uint32_t tile) {
+            const uint32_t *src = base + (uint64_t)tile * TILE;
 #pragma unroll
-        for (int q = 0; q < 4; q++) valid |= (slot0 + q < cur.slot_end) ? (1u << q) : 0u;
-        const uint32_t vbase = cur.b * bucket_vars;
-        uint32_t sb = smem_base;
-        asm volatile("" : "+r"(sb));          // opaque: lookups below cannot be hoisted above the staging barrier
-        const uint32_t sadj = sb - ((vbase >> 5) << 2);
-        uint32_t alive;
-        if constexpr (PK) {
-            using P = EagerPack<(RB < 2 ? 1 : 2)>;
-            uint4 L[E];
+            for (int j = 0; j < NS; j++) L[j] = ld_stream_v4(src + (uint64_t)j * p.m_pad);
+        };
+        auto process = [&](const uint4 (&S)[NS], uint32_t tile) {
+            const uint32_t slot0 = tile * TILE + threadIdx.x * CLAUSES_PER_THREAD;
+            uint32_t valid = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) valid |= (slot0 + q < slot_end) ? (1u << q) : 0u;
+            uint32_t sb = smem_base;
+            asm volatile("" : "+r"(sb));          // opaque: lookups below cannot be hoisted above the staging barrier
+            const uint32_t sadj = sb - ((vbase >> 5) << 2);
+            uint32_t alive;
+            if constexpr (PK) {
+                using P = EagerPack<(RB < 2 ? 1 : 2)>;
+                uint4 L[E];
 #define ALLL_UNPACK(J) L[J] = make_uint4(P::template field<J>(S[0].x, S[1].x, S[2].x, S[3].x), P::template field<J>(S[0].y, S[1].y, S[2].y, S[3].y), \
                                          P::template field<J>(S[0].z, S[1].z, S[2].z, S[3].z), P::template field<J>(S[0].w, S[1].w, S[2].w, S[3].w))
-            ALLL_UNPACK(0); ALLL_UNPACK(1); ALLL_UNPACK(2); ALLL_UNPACK(3); ALLL_UNPACK(4);
+                ALLL_UNPACK(0); ALLL_UNPACK(1); ALLL_UNPACK(2); ALLL_UNPACK(3); ALLL_UNPACK(4);
 #undef ALLL_UNPACK
-            alive = eval4<E, RBE, RC>(L, valid, sb, sadj, p.bits, vbase, bucket_vars);
-        } else {
-            alive = eval4<E, RBE, RC>(S, valid, sadj, sadj, p.bits, vbase, bucket_vars);
-        }
-        if constexpr (E < K) {
-            parked.push4(alive, slot0);
-            parked.drain(31u, out, p, vbase, bucket_vars);
-        } else {
-            out.push4(alive, slot0);
-        }
-    };
-
-    // HBM -> L2: one thread per CTA bulk-prefetches the E plane segments of the tile `dist` ahead of the register
-    // double buffer, so enough bytes are in flight to cover the loaded DRAM latency without spending registers.
-    const uint32_t dist = p.prefetch_tiles;
-    auto prefetch = [&](uint32_t tile) {
-        if (threadIdx.x == 0 && dist != 0 && tile < t1) {
+                alive = eval4<E, RBE, RC>(L, valid, sb, sadj, p.bits, vbase, bucket_vars);
+            } else {
+                alive = eval4<E, RBE, RC>(S, valid, sadj, sadj, p.bits, vbase, bucket_vars);
+            }
+            if constexpr (E < K) {
+                parked.push4(alive, slot0);
+                parked.drain(31u, out, p, vbase, bucket_vars);
+            } else {
+                out.push4(alive, slot0);
+            }
+        };
+        // HBM -> L2: one thread per CTA bulk-prefetches the plane segments of the tile `dist` ahead of the register
+        // double buffer, so enough bytes are in flight to cover the loaded DRAM latency without spending registers.
+        auto prefetch = [&](uint32_t tile) {
+            if (threadIdx.x == 0 && dist != 0 && tile < t1) {
 #pragma unroll
-            for (int j = 0; j < NS; j++) tma_prefetch_l2(stream + (uint64_t)j * p.m_pad + (uint64_t)tile * TILE, TILE * 4);
-        }
-    };
-    // (Measured and rejected for the packed planes, profiles/r02_packed_planes.md: a third register buffer -- loads issued
-    // two tiles ahead -- is slower, 0.2075 vs 0.2029 ms stand-alone and 0.220 vs 0.204 ms inside the solve kernel, where it
-    // spills: the wait at a tile's first use is arrival rate, not latency.)
-    {
+                for (int j = 0; j < NS; j++) tma_prefetch_l2(stream + (uint64_t)j * p.m_pad + (uint64_t)tile * TILE, TILE * 4);
+            }
+        };
+        // (Measured and rejected for the packed planes, profiles/r02_packed_planes.md: a third register buffer -- loads
+        // issued two tiles ahead -- is slower: the wait at a tile's first use is arrival rate, not latency.)
         for (uint32_t d = 2; d < 2 + dist; d++) prefetch(t0 + d);
         uint4 A[NS], B[NS];
         load(A, t0);
@@ -460,7 +469,7 @@ __device__ __forceinline__ void sweep_planes_body(const SweepParams &p, unsigned
             process(B, tile + 1);
         }
     }
-    if constexpr (E < K) parked.drain(0u, out, p, cur.b * bucket_vars, bucket_vars);
+    if constexpr (E < K) parked.drain(0u, out, p, vbase, bucket_vars);
     if (out.count) out.flush();
     if (TICKET) p2p_publish(p);
 }
