@@ -30,29 +30,36 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(cons
     if (threadIdx.x == 0) s_mp = mp_arg;
     __syncthreads();
     const MisParams &mp = s_mp;
-    GridBarrier bar{cg::this_grid()};
+    // Nothing but `round` stays in registers across the sweep body: the streaming loop is latency-bound at the register
+    // limit of a 512-thread CTA, and every value kept live around it (timers, barrier handle, thread indices) costs it
+    // scheduling freedom -- the same body ran 0.185 ms as a kernel of its own and 0.203 ms in here before this was moved
+    // to shared memory / recomputed (profiles/r02_pipelined_layout.md).
+    __shared__ unsigned long long s_t0;      // block 0: %globaltimer at sweep entry
+    __shared__ uint32_t s_prev_n_u;          // |U| of the previous round (m / 2^K before the first)
     Counters *const c = sp.ctr;
-    const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
-    const bool p2p = sp.p2p != nullptr;      // clause-range sharded solve: every GPU runs this kernel on its range
-    const uint32_t first = blockIdx.x * SWEEP_THREADS + threadIdx.x, stride = gridDim.x * SWEEP_THREADS;
-    unsigned long long t_sweep = 0, t_mis = 0;
-    uint32_t prev_n_u = (uint32_t)min((uint64_t)0xFFFFFFFFu, ((uint64_t)sp.n_tiles * TILE) >> K);
+#define ALLL_LEAD (blockIdx.x == 0 && threadIdx.x == 0)
+    if (threadIdx.x == 0) s_prev_n_u = (uint32_t)min((uint64_t)0xFFFFFFFFu, ((uint64_t)sp.n_tiles * TILE) >> K);
+    __syncthreads();
     for (uint32_t round = 0; round < max_rounds; ++round) {
         const uint32_t par = round & 1u, tag = ((epoch & 0xFFFu) << 20) | (round + 1u);
-        unsigned long long t0 = 0, t1 = 0;
-        if (lead) {
-            t0 = global_ns();
-            if (round < DBG_ROUNDS) c->dbg[round][0] = t0;
+        if (ALLL_LEAD) {
+            s_t0 = global_ns();
+            if (round < DBG_ROUNDS) c->dbg[round][0] = s_t0;
         }
         // records next to the violated list only while the violated set is expected to fit them (the previous round's
         // |U|, or m / 2^K before the first round): writing the first urec_cap records of a larger set is wasted work
-        const bool rec_on = (uint64_t)prev_n_u <= 2ull * sp.urec_cap;
+        const bool rec_on = (uint64_t)s_prev_n_u <= 2ull * sp.urec_cap;
         if (threadIdx.x == 0) { s_mp.p2p_parity = par; s_mp.p2p_tag = tag; s_mp.urec_cap = rec_on ? sp.urec_cap : 0u; }
         // incremental mode (ip.rows != NULL): the round that just ended decided whether this round's violated set comes
         // from the occurrence lists of the variables it resampled (same set as the sweep's, incremental.cu) or from a sweep
         const bool incremental = ip.rows != nullptr && round > 0 && gm::ld_cg(&c->incr_next) != 0;
         if (incremental) incr_eval_body(ip, gm::ld_cg(&c->last_n_s), &c->n_viol_pp[par], IncrP2P{sp.p2p, s_prefix, par, sp.orig_id, sp.id_base, c, sp.p2p_epoch + 1u});
         else sweep_planes_body<K, RB, RC, E, false, PK>(sp, &c->n_viol_pp[par], par, rec_on);
+        GridBarrier bar{cg::this_grid()};
+        const bool lead = ALLL_LEAD;
+        const bool p2p = sp.p2p != nullptr;  // clause-range sharded solve: every GPU runs this kernel on its range
+        const uint32_t first = blockIdx.x * SWEEP_THREADS + threadIdx.x, stride = gridDim.x * SWEEP_THREADS;
+        unsigned long long t1 = 0;
         uint32_t n_u;
         if (p2p) {
             // Fused exchange: the violated records went straight into every GPU's region during the sweep.  Every CTA orders
@@ -82,7 +89,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(cons
         }
         if (lead) {
             t1 = global_ns();
-            t_sweep += t1 - t0;
+            c->t_sweep_ns += t1 - s_t0;
             if (round < DBG_ROUNDS) { c->dbg[round][1] = t1; c->dbg[round][2] = t1; }
             c->n_viol_pp[par ^ 1u] = 0;
         }
@@ -118,13 +125,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(cons
             if (lead) finish_round(mp, round, n_u, 2u);
         }
         bar.sync();                                      // new assignment visible to every SM before it is staged again
-        prev_n_u = n_u;
-        if (lead) t_mis += global_ns() - t1;
+        if (threadIdx.x == 0) s_prev_n_u = n_u;          // (read again after the __syncthreads() inside the next sweep's staging... and here:)
+        __syncthreads();
+        if (lead) c->t_mis_ns += global_ns() - t1;
     }
-    if (lead) {
-        c->t_sweep_ns = t_sweep;
-        c->t_mis_ns = t_mis;
-    }
+#undef ALLL_LEAD
 }
 
 // ---- launchers ------------------------------------------------------------------------

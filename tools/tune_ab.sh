@@ -5,7 +5,7 @@ W=$1; TAG=$2; shift 2
 O=gpurun_out
 mkdir -p $O
 for T in "$@"; do
-    ALLL_TUNE=$T ${TRACE:+ALLL_TRACE=1} python tools/prof_sweep.py --workload $W --reps 10 --solves 4 ${MAXR:+--max-rounds $MAXR} > $O/${TAG}_${W}_t$T.json 2> $O/${TAG}_${W}_t$T.txt
+    env ALLL_TUNE=$T ${TRACE:+ALLL_TRACE=1} python tools/prof_sweep.py --workload $W --reps 10 --solves 4 ${MAXR:+--max-rounds $MAXR} > $O/${TAG}_${W}_t$T.json 2> $O/${TAG}_${W}_t$T.txt
     python - $O/${TAG}_${W}_t$T.json $T <<'PY'
 import json, sys
 d = json.load(open(sys.argv[1]))
