@@ -25,6 +25,8 @@
 // set claims the device-wide `winner` word (atomicCAS) and the others stop at their next round boundary.
 #include <cstdlib>
 
+#include <mutex>
+
 #include "alll_device.cuh"
 
 namespace alll {
@@ -473,6 +475,11 @@ cudaError_t launch_batch_solve(const uint32_t *planes, uint64_t m_pad, const uin
                                int *n_launches, cudaStream_t s)
 {
     static const bool large_only = getenv("ALLL_BATCH_LARGE_ONLY") != nullptr;        // measurement / test knob
+    // alll_multi_batch_solve enqueues the device slots from one host thread each: the function attributes and the
+    // (first: module-loading) launches of the same kernels are serialised here -- microseconds of enqueue, not the solve
+    static std::mutex enqueue_mu;
+    std::lock_guard<std::mutex> lock(enqueue_mu);
+    (void)cudaGetLastError();                       // a stale non-sticky error of this thread must not be taken for the launch's
     const size_t smem = batch_smem_bytes(n_vars, n_words, m_max);
     cudaError_t e = cudaFuncSetAttribute(batch_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
