@@ -606,3 +606,44 @@ def test_packed_eager_planes_match_plain_planes_and_oracle(capi, oracle, k, d):
             assert np.array_equal(sp.get_assignment(), v) and np.array_equal(su.get_assignment(), v)
             assert oracle.verify(off, lits.reshape(-1), v) and sp.verify()
     assert seen_rb <= {1, 2} and len(seen_rb) >= 1
+
+
+@pytest.mark.parametrize("smem", [0, 16384], ids=["resident", "bucketed"])
+def test_host_upload_in_several_chunks_matches_device_upload_and_oracle(capi, oracle, smem):
+    """A host buffer above 64 MB is copied in chunks with the bucketing passes (count -> device-side scan -> scatter, which
+    also writes the packed eager planes and tail rows) running chunk by chunk behind the copy: slots lie chunk-major, the
+    sweep walks its per-CTA run lists bucket-major.  Violated sets, trajectory and statistics must not depend on it: same as
+    the single-chunk device upload of the same literals and as the oracle."""
+    import torch
+
+    from alllsatisfiabilitysolver_b200.instances import bounded_degree_ksat
+
+    n, k, d, seed = 640_000, 8, 32, 31
+    lits = bounded_degree_ksat(n, k, d, seed=0xC4C4)
+    m = lits.shape[0]
+    assert m * k * 4 > (64 << 20) * 1.1, "instance must span more than one 64 MB upload chunk"
+    off = np.arange(m + 1, dtype=np.uint64) * np.uint64(k)
+    flat = lits.reshape(-1)
+    d_lits = torch.from_numpy(lits.astype(np.int32)).cuda()
+    with capi.Solver(sweep_smem_bytes=smem) as sh, capi.Solver(sweep_smem_bytes=smem) as sd:
+        sh.upload_fixedk(n, lits)                                   # host buffer: several chunks
+        sd.upload_fixedk_device(n, m, k, d_lits.data_ptr())         # device buffer: one chunk
+        if smem:
+            assert sh.layout_info()["n_buckets"] > 1 and sh.sweep_info()["packed"] and sd.sweep_info()["packed"]
+        v = oracle.randomize(n, seed)
+        want = oracle.sweep(off, flat, v)
+        for s in (sh, sd):
+            s.randomize(seed)
+            cnt, ids = s.eval()
+            assert cnt == len(want) and np.array_equal(np.sort(ids), want)
+        u_o, s_o, r_o = oracle.round(n, off, flat, v, seed, 0)
+        for s in (sh, sd):
+            u_g, s_g, r_g = s.round(seed, 0)
+            assert np.array_equal(np.sort(u_g), u_o) and np.array_equal(np.sort(s_g), np.sort(s_o)) and r_g == r_o
+            assert np.array_equal(s.get_assignment(), v)
+        so = oracle.solve(n, off, flat, v, seed)
+        for s in (sh, sd):
+            st = s.solve(seed)
+            assert st.status == 0 and (st.n_iterations, st.n_resamples, st.sum_mis_size) == (so.n_iterations, so.n_resamples, so.sum_mis_size)
+            assert np.array_equal(s.get_assignment(), v) and s.verify()
+        assert oracle.verify(off, flat, v)
