@@ -70,3 +70,28 @@ def test_product_never_touches_the_oracle():
                         if re.search(r"(from|import)\s+oracle|#include.*oracle|liballl_ref|liballl_oracle", line):
                             bad.append((f, line.strip()))
     assert not bad, bad
+
+
+def test_headline_kernels_do_not_spill(built):
+    """The sweep body runs at the register limit of a 512-thread CTA, and inside `solve_persistent_kernel` that limit covers
+    the whole call tree: code added to an out-of-line independent-set function has pushed the sweep loop into local memory
+    before (cfg4 solve 3.2 -> 5.7 ms, profiles/r02_l2_policy.md).  The built library must keep the headline variants free
+    of spills: a stack frame beyond the 8 bytes the out-of-line calls need means the streaming loop lost registers."""
+    import shutil
+
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([exe, "-res-usage", built], capture_output=True, text=True, check=True).stdout
+    usage = {m.group(1): (int(m.group(2)), int(m.group(3))) for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", out)}
+    checked = 0
+    for name, (reg, stack) in usage.items():
+        # cfg4 (packed, two resident leading literals), cfg2 (7-SAT, assignment fully staged), cfg3 (3-SAT)
+        headline = any(v in name for v in ("ILi8ELi2ELi3ELi5ELb1E", "ILi7ELi7ELi7ELi5ELb0E", "ILi3ELi3ELi3ELi3ELb0E"))
+        if "solve_persistent_kernel" in name and headline:
+            assert reg <= 128 and stack <= 8, f"{name}: REG {reg} STACK {stack}"
+            checked += 1
+        if "sweep_planes_kernel" in name and headline:
+            assert reg <= 128 and stack == 0, f"{name}: REG {reg} STACK {stack}"
+            checked += 1
+    assert checked >= 6
