@@ -371,6 +371,32 @@ def same_instance_record(shape: dict, device: int, cpu: dict | None, max_rounds:
     return rec
 
 
+_FULL_AFFINITY = None      # this process's CPU set before bind_to_gpu_numa_node narrowed it (the CPU baseline gets it back)
+
+
+def bind_to_gpu_numa_node(index):
+    """Pins this process to the host CPUs NVML names as local to GPU `index`, before any page-locked buffer exists: the
+    end-to-end steps copy 1.28 GB per step and rank from pinned host memory, and with one rank per GPU all of them pull at
+    once -- buffers first-touched on the far socket would cross the inter-socket link.  Returns a small record for the line
+    (None when NVML or the affinity call is unavailable: nothing changes then)."""
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        mask = nv.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        global _FULL_AFFINITY
+        _FULL_AFFINITY = set(os.sched_getaffinity(0))
+        cpus = {i for i in range(n_cpu) if (int(mask[i // 64]) >> (i % 64)) & 1} & _FULL_AFFINITY
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"cpus": len(cpus), "first": min(cpus), "last": max(cpus), "source": "nvmlDeviceGetCpuAffinity"}
+    except Exception as e:                                  # noqa: BLE001 -- a missing NVML must not cost the bench line
+        return {"error": repr(e)[:80]}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -386,6 +412,7 @@ def run_ours(args):
         os.environ["NCCL_DEBUG"] = "WARN"
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the solver has no CPU fallback")
+    host_affinity = None if os.environ.get("ALLL_BENCH_NO_AFFINITY") else bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -563,6 +590,8 @@ def run_ours(args):
                 traffic = None
         cpu, same = None, None
         if world == 1 and not args.no_cpu_baseline:
+            if _FULL_AFFINITY:                                  # the reference runs on ALL host cores, as in its own arm
+                os.sched_setaffinity(0, _FULL_AFFINITY)
             cpu_full = reference_sample(shape, steps=3, warmup=1, budget_s=60.0)
             if cpu_full:
                 cpu = {kk: cpu_full[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
@@ -581,6 +610,7 @@ def run_ours(args):
                        "l2": "literal stream (4*k*m bytes) is larger than L2; no flush needed" if 4 * k * m > 126e6 else
                              "literal stream fits L2 (126 MB): sweeps after the first are L2-resident",
                        "layout": layout},
+            "host_affinity": host_affinity,
             "time_to_sat_ms": dev_ms_max / args.steps,
             "rounds_per_sec": rounds_all / (dev_ms_max * 1e-3),
             "sweeps_per_solve": sweeps / args.steps,
