@@ -550,6 +550,16 @@ def run_ours(args):
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     dev_ms_max, wall_ms_max, e2e_s_max = [float(x) for x in red.tolist()]
     evals_all, sweeps_all, rounds_all, e2e_evals_all, launches_all, n_ok = [float(x) for x in tot.tolist()]
+    # per rank: every rank solves its OWN random instance, whose solves need different numbers of sweeps -- the MAX over
+    # ranks above therefore contains the spread of the workload itself, next to any contention between the GPUs
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([dev_ms / args.steps, sweeps / args.steps, sweep_ms / max(sweeps, 1)], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [round(float(x[0]), 4) for x in allr], "sweeps_per_solve": [round(float(x[1]), 2) for x in allr],
+                    "sweep_phase_ms": [round(float(x[2]), 4) for x in allr],
+                    "note": "one independent random instance per rank: the slowest rank is the one whose solves needed most sweeps"}
 
     # ---- the sweep as a kernel of its own, back to back on the same resident data (CUDA events, alll_time_sweep):
     # the cross-check for the roofline figure below, whose kernel runs every sweep of a solve in one launch ----
@@ -611,6 +621,7 @@ def run_ours(args):
                              "literal stream fits L2 (126 MB): sweeps after the first are L2-resident",
                        "layout": layout},
             "host_affinity": host_affinity,
+            "per_rank": per_rank,
             "time_to_sat_ms": dev_ms_max / args.steps,
             "rounds_per_sec": rounds_all / (dev_ms_max * 1e-3),
             "sweeps_per_solve": sweeps / args.steps,
