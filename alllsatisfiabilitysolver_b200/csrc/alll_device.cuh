@@ -351,9 +351,9 @@ struct SweepParams {
     uint32_t tune;
     // packed eager planes [4][m_pad] (EagerPack<min(min_resident, 2)>; NULL = the sweep streams planes 0..4)
     const uint32_t *packed;
-    // tail rows [m_pad] (5 < k <= 8; NULL = none): literals 5 .. k-1 of a clause side by side in one 16-byte row, so a
-    // clause that survives its five eager literals costs ONE scattered sector instead of one per tail plane
-    const uint4 *tail_rows;
+    // row-major copy [m_pad][8] (5 < k <= 8; NULL = none), 32 bytes per clause: a clause that survives its five eager
+    // literals gets literals 5 .. k-1 with ONE 16-byte fetch of the row's second half instead of one sector per tail plane
+    const uint4 *rows8;
 };
 constexpr uint32_t TUNE_NO_TAIL_ROWS = 2u;         // survivors fetch their tail literals from the planes (one sector per literal)
 constexpr uint32_t TUNE_NO_PACKED_PLANES = 4u;     // the sweep streams planes 0..4 even where the packed eager planes apply

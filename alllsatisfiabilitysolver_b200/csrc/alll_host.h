@@ -84,7 +84,7 @@ uint32_t bucket_pass_clauses_per_cta();
 cudaError_t launch_bucket_count(const uint32_t *lit, uint64_t m, uint64_t c0, uint64_t c1, uint32_t k, uint64_t n_vars,
                                 uint32_t bucket_vars, uint32_t n_buckets, uint8_t *bkt, uint32_t *cta_counts, uint32_t *err,
                                 cudaStream_t s);                                            // clauses [c0, c1) of m
-cudaError_t launch_tail_rows(const uint32_t *planes, uint64_t m_pad, uint32_t k, uint4 *rows, cudaStream_t s);
+cudaError_t launch_rows8(const uint32_t *planes, uint64_t m_pad, uint32_t k, uint4 *rows, cudaStream_t s);
 cudaError_t launch_pack_eager(const uint32_t *planes, uint64_t m_pad, const BucketSeg *segs, uint32_t n_buckets,
                               uint32_t bucket_vars, uint32_t rb, uint32_t *packed, cudaStream_t s);
 cudaError_t launch_bucket_scan(uint32_t *cta_counts, uint64_t m, uint64_t c0, uint64_t c1, uint32_t n_buckets, BucketSeg *segs_out,
@@ -92,7 +92,7 @@ cudaError_t launch_bucket_scan(uint32_t *cta_counts, uint64_t m, uint64_t c0, ui
 cudaError_t launch_bucket_scatter(const uint32_t *lit, uint64_t m, uint64_t c0, uint64_t c1, uint32_t k, uint32_t bucket_vars,
                                   uint32_t n_buckets, const uint8_t *bkt, const uint32_t *cta_base, uint32_t *planes, uint64_t m_pad,
                                   uint32_t *orig_id, uint32_t *min_resident, uint32_t resident_cap, const uint8_t *width_in,
-                                  uint8_t *width_out, uint32_t *packed, uint4 *tail_rows, cudaStream_t s);
+                                  uint8_t *width_out, uint32_t *packed, uint4 *rows, cudaStream_t s);
 bool bucket_scatter_fuses(uint32_t k, bool with_widths);
 cudaError_t launch_pack_bits(const uint8_t *bools, uint64_t n_vars, uint32_t *bits, uint32_t n_words_alloc, cudaStream_t s);
 cudaError_t launch_unpack_bits(const uint32_t *bits, uint64_t n_vars, uint8_t *bools, cudaStream_t s);

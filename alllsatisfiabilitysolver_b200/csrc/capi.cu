@@ -55,8 +55,7 @@ struct alll_solver {
     uint32_t *d_planes = nullptr, *d_orig_id = nullptr;
     uint32_t *d_packed = nullptr;        // packed eager planes [4][m_pad] (alll_device.cuh: EagerPack), streamed by the sweep when packed_on
     bool packed_on = false;
-    uint4 *d_tail_rows = nullptr;        // literals 5 .. k-1 of every slot in one 16-byte row (5 < k <= 8), read by the sweep for surviving clauses
-    bool tail_on = false;
+    bool rows8_on = false;               // d_rows holds the row-major copy [m_pad][8] (5 <= k <= 8): the sweep's tail fetch and the independent-set gather read it
     BucketSeg *d_segs = nullptr;
     BucketSeg *d_sweep_segs = nullptr;   // the non-empty segments in sweep order (bucket-major over the chunk-major slot order)
     uint32_t n_sweep_segs = 1;
@@ -164,7 +163,7 @@ void free_instance(alll_handle h)
 {
     h->has_instance = false;
     h->packed_on = false;
-    h->tail_on = false;
+    h->rows8_on = false;
     h->use_orig_id = false;
     h->use_width = false;
     h->incr_ready = false;
@@ -176,7 +175,7 @@ void free_instance(alll_handle h)
 
 void release_buffers(alll_handle h)
 {
-    dfree(h->d_planes); dfree(h->d_packed); dfree(h->d_tail_rows); dfree(h->d_orig_id); dfree(h->d_segs); dfree(h->d_sweep_segs); dfree(h->d_runs); dfree(h->d_run_begin); dfree(h->d_off); dfree(h->d_csr_lit); dfree(h->d_csr_start); dfree(h->d_csr_rank);
+    dfree(h->d_planes); dfree(h->d_packed); dfree(h->d_orig_id); dfree(h->d_segs); dfree(h->d_sweep_segs); dfree(h->d_runs); dfree(h->d_run_begin); dfree(h->d_off); dfree(h->d_csr_lit); dfree(h->d_csr_start); dfree(h->d_csr_rank);
     dfree(h->d_bits); dfree(h->d_claim); dfree(h->d_urec); dfree(h->d_viol); dfree(h->d_s); dfree(h->d_ids_out);
     dfree(h->d_state); dfree(h->d_bools); dfree(h->d_width); dfree(h->d_width_in); dfree(h->d_tmp_bkt); dfree(h->d_tmp_cnt); dfree(h->d_tmp_err); dfree(h->d_stage);
     dfree(h->d_sh_planes); dfree(h->d_sh_ids); dfree(h->d_sh_iota); dfree(h->d_sh_s); dfree(h->d_sh_state);
@@ -254,8 +253,8 @@ ClauseView clause_view(alll_handle h)
     cv.id_base = h->id_base;
     cv.width_arr = h->use_width ? h->d_width : nullptr;
     cv.rec = h->gen_mode ? h->d_gen_rec : nullptr;
-    cv.rows = h->incr_ready ? h->d_rows : nullptr;
-    cv.row_stride = h->incr_stride;
+    cv.rows = (h->incr_ready || h->rows8_on) ? h->d_rows : nullptr;          // (incremental mode builds the same rows for any k)
+    cv.row_stride = h->incr_ready ? h->incr_stride : 8u;
     return cv;
 }
 
@@ -322,7 +321,7 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     std::vector<BucketSeg> segs(h->n_buckets);
     h->n_segs = h->n_buckets;
     uint32_t tiles_used = 0;
-    bool fused_pack = false, fused_tail = false;     // written by the bucket scatter already
+    bool fused_pack = false, fused_rows = false;     // written by the bucket scatter already
     h->min_resident = 0;
     h->resident_cap = RESIDENT_CAP;
 
@@ -384,19 +383,19 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
         // clause has two literals in the bucket that holds most of its variables -- pigeonhole); otherwise by passes below.
         const bool want_pack = !(h->flags & ALLL_FLAG_NO_PACKING) && !(h->tune & TUNE_NO_PACKED_PLANES) && h->resident_cap == 3 &&
                                2ull * bucket_vars <= (1ull << 22) && m > 0 && k >= EAGER_PLANES && k <= 8;
-        const bool want_tail = !(h->flags & ALLL_FLAG_NO_PACKING) && !(h->tune & TUNE_NO_TAIL_ROWS) && m > 0 && k > EAGER_PLANES && k <= 8;
+        const bool want_rows = !(h->flags & ALLL_FLAG_NO_PACKING) && !(h->tune & TUNE_NO_TAIL_ROWS) && m > 0 && k >= EAGER_PLANES && k <= 8;
         const bool fuses = bucket_scatter_fuses(k, d_width_in != nullptr);
         fused_pack = fuses && want_pack && k > nb && n_vars <= (1ull << 27);
-        fused_tail = fuses && want_tail;
+        fused_rows = fuses && want_rows;
         if (fused_pack) POOL(h->d_packed, h->m_pad * 4 * 4);
-        if (fused_tail) POOL(h->d_tail_rows, h->m_pad * sizeof(uint4));
+        if (fused_rows) POOL(h->d_rows, h->m_pad * 8 * 4);
         for (size_t i = 0; i + 1 < cut.size() && m; i++) {
             CK(chunk_ready(i));
             CK(launch_bucket_count(d_lit, m, cut[i], cut[i + 1], k, n_vars, bucket_vars, nb, d_bkt, d_cnt, d_err, h->stream));
             CK(launch_bucket_scan(d_cnt, m, cut[i], cut[i + 1], nb, h->d_segs + i * nb, d_err + 2, h->stream));
             CK(launch_bucket_scatter(d_lit, m, cut[i], cut[i + 1], k, bucket_vars, nb, d_bkt, d_cnt, h->d_planes, h->m_pad, h->d_orig_id,
                                      d_err + 1, h->resident_cap, d_width_in, d_width_in ? h->d_width : nullptr,
-                                     fused_pack ? h->d_packed : nullptr, fused_tail ? h->d_tail_rows : nullptr, h->stream));
+                                     fused_pack ? h->d_packed : nullptr, fused_rows ? reinterpret_cast<uint4 *>(h->d_rows) : nullptr, h->stream));
             h->launches += 3;
         }
         if (m == 0) {                                    // no chunk ran: empty segments
@@ -461,10 +460,10 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
             h->launches++;
         }
     }
-    h->tail_on = m > 0 && k > EAGER_PLANES && k <= 8 && !(h->flags & ALLL_FLAG_NO_PACKING) && !(h->tune & TUNE_NO_TAIL_ROWS);
-    if (h->tail_on && !fused_tail) {
-        POOL(h->d_tail_rows, h->m_pad * sizeof(uint4));
-        CK(launch_tail_rows(h->d_planes, h->m_pad, k, h->d_tail_rows, h->stream)); h->launches++;
+    h->rows8_on = m > 0 && k >= EAGER_PLANES && k <= 8 && !(h->flags & ALLL_FLAG_NO_PACKING) && !(h->tune & TUNE_NO_TAIL_ROWS);
+    if (h->rows8_on && !fused_rows) {
+        POOL(h->d_rows, h->m_pad * 8 * 4);
+        CK(launch_rows8(h->d_planes, h->m_pad, k, reinterpret_cast<uint4 *>(h->d_rows), h->stream)); h->launches++;
     }
     if (int rc = alloc_common(h, h->m)) return rc;
     if (k >= 1 && k <= 8 && !h->use_width && m > 0) {
@@ -478,7 +477,7 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     SweepParams sp{};
     sp.bucket_words = h->bucket_words; sp.k = k; sp.min_resident = h->min_resident; sp.resident_cap = h->resident_cap; sp.eager = (h->flags >> 8) & 0xFFu; sp.prefetch_tiles = prefetch_distance(h->flags);
     sp.packed = h->packed_on ? h->d_packed : nullptr;
-    sp.tail_rows = h->tail_on ? h->d_tail_rows : nullptr;
+    sp.rows8 = (h->rows8_on && h->k > EAGER_PLANES) ? reinterpret_cast<const uint4 *>(h->d_rows) : nullptr;
     CK(configure_sweep_planes(sp, h->resident_all));
     h->sweep_grid = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)h->sm_count, h->n_tiles));
     {
@@ -562,7 +561,7 @@ SweepParams sweep_params(alll_handle h, uint32_t p2p_parity, uint32_t p2p_tag, u
     sp.round = round;
     sp.tune = h->tune;
     sp.packed = h->packed_on ? h->d_packed : nullptr;
-    sp.tail_rows = h->tail_on ? h->d_tail_rows : nullptr;
+    sp.rows8 = (h->rows8_on && h->k > EAGER_PLANES) ? reinterpret_cast<const uint4 *>(h->d_rows) : nullptr;
     sp.orig_id = h->use_orig_id ? h->d_orig_id : nullptr; sp.id_base = h->id_base;
     if (p2p_tag) {
         sp.p2p = h->d_p2p_link; sp.p2p_parity = p2p_parity; sp.p2p_tag = p2p_tag; sp.p2p_epoch = p2p_tag >> 20;

@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) bucket_scatter_staged_kernel(c
                                                                                 uint32_t *__restrict__ orig_id,
                                                                                 uint32_t *__restrict__ min_resident, uint32_t resident_cap,
                                                                                 uint32_t cta0, uint32_t n_cta,
-                                                                                uint32_t *__restrict__ packed, uint4 *__restrict__ tail_rows)
+                                                                                uint32_t *__restrict__ packed, uint4 *__restrict__ rows)
 {
     __shared__ uint16_t warp_cnt[(LAYOUT_THREADS / 32) * MAX_BUCKETS];   // [warp][bucket], then exclusive over warps
     __shared__ uint32_t bucket_off[MAX_BUCKETS + 1];                     // CTA-local start of every bucket's run
@@ -314,10 +314,15 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) bucket_scatter_staged_kernel(c
 #pragma unroll
         for (int i = 0; i < EagerPack<2>::WORDS; i++) packed[(uint64_t)i * m_pad + dst] = w[i];
     }
-    // ... and the tail row (literals 5 .. k-1 side by side)
-    if (tail_rows != nullptr)
-        tail_rows[dst] = make_uint4(k > 5 ? stage_smem[5 * LAYOUT_THREADS + t] : 0u, k > 6 ? stage_smem[6 * LAYOUT_THREADS + t] : 0u,
-                                    k > 7 ? stage_smem[7 * LAYOUT_THREADS + t] : 0u, 0u);
+    // ... and the row-major copy (32 bytes per clause, literals beyond k zero): its second half is the sweep's tail row, the
+    // whole row is what the independent-set gather reads -- one sector per violated clause instead of one per literal plane
+    if (rows != nullptr) {
+        uint32_t l[8];
+#pragma unroll
+        for (uint32_t j = 0; j < 8; j++) l[j] = j < k ? stage_smem[j * LAYOUT_THREADS + t] : 0u;
+        rows[2 * dst] = make_uint4(l[0], l[1], l[2], l[3]);
+        rows[2 * dst + 1] = make_uint4(l[4], l[5], l[6], l[7]);
+    }
 }
 
 // ---- packed eager planes (alll_device.cuh: EagerPack) -- one pass over the finished planes ------------------------
@@ -343,21 +348,23 @@ __global__ void __launch_bounds__(256) pack_eager_kernel(const uint32_t *__restr
     for (int i = 0; i < EagerPack<RB>::WORDS; i++) packed[(uint64_t)i * m_pad + slot] = w[i];
 }
 
-// ---- tail rows: literals EAGER_PLANES .. k-1 of every slot side by side (k <= 8: at most three) ----------------------
-__global__ void __launch_bounds__(256) tail_rows_kernel(const uint32_t *__restrict__ planes, uint64_t m_pad, uint32_t k,
-                                                         uint4 *__restrict__ rows)
+// ---- row-major copy for 5 <= k <= 8: rows[slot] = literals 0..7 (zero beyond k), 32 bytes -- as a pass of its own where
+// the bucket scatter does not write it
+__global__ void __launch_bounds__(256) rows8_kernel(const uint32_t *__restrict__ planes, uint64_t m_pad, uint32_t k,
+                                                     uint4 *__restrict__ rows)
 {
     const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= m_pad) return;
-    uint32_t l[4] = {0u, 0u, 0u, 0u};
-    for (uint32_t j = EAGER_PLANES; j < k; j++) l[j - EAGER_PLANES] = planes[(uint64_t)j * m_pad + slot];
-    rows[slot] = make_uint4(l[0], l[1], l[2], l[3]);
+    uint32_t l[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    for (uint32_t j = 0; j < k && j < 8; j++) l[j] = planes[(uint64_t)j * m_pad + slot];
+    rows[2 * slot] = make_uint4(l[0], l[1], l[2], l[3]);
+    rows[2 * slot + 1] = make_uint4(l[4], l[5], l[6], l[7]);
 }
 
-cudaError_t launch_tail_rows(const uint32_t *planes, uint64_t m_pad, uint32_t k, uint4 *rows, cudaStream_t s)
+cudaError_t launch_rows8(const uint32_t *planes, uint64_t m_pad, uint32_t k, uint4 *rows, cudaStream_t s)
 {
     if (m_pad == 0) return cudaSuccess;
-    tail_rows_kernel<<<(uint32_t)((m_pad + 255) / 256), 256, 0, s>>>(planes, m_pad, k, rows);
+    rows8_kernel<<<(uint32_t)((m_pad + 255) / 256), 256, 0, s>>>(planes, m_pad, k, rows);
     return cudaGetLastError();
 }
 
@@ -431,10 +438,10 @@ bool bucket_scatter_fuses(uint32_t k, bool with_widths) { return k >= EAGER_PLAN
 cudaError_t launch_bucket_scatter(const uint32_t *lit, uint64_t m, uint64_t c0, uint64_t c1, uint32_t k, uint32_t bucket_vars,
                                   uint32_t n_buckets, const uint8_t *bkt, const uint32_t *cta_base, uint32_t *planes, uint64_t m_pad,
                                   uint32_t *orig_id, uint32_t *min_resident, uint32_t resident_cap, const uint8_t *width_in,
-                                  uint8_t *width_out, uint32_t *packed, uint4 *tail_rows, cudaStream_t s)
+                                  uint8_t *width_out, uint32_t *packed, uint4 *rows, cudaStream_t s)
 {
     if (c1 <= c0) return cudaSuccess;
-    if ((packed || tail_rows) && !bucket_scatter_fuses(k, width_in != nullptr)) return cudaErrorInvalidValue;
+    if ((packed || rows) && !bucket_scatter_fuses(k, width_in != nullptr)) return cudaErrorInvalidValue;
     const uint32_t grid = blocks_for(c1 - c0, LAYOUT_THREADS), cta0 = (uint32_t)(c0 / LAYOUT_THREADS), n_cta = bucket_pass_ctas(m);
     if (k <= 8 && width_in == nullptr) {
         // static (17 KB) + dynamic shared memory exceed the 48 KB default: opt in (per device, cheap, idempotent)
@@ -442,7 +449,7 @@ cudaError_t launch_bucket_scatter(const uint32_t *lit, uint64_t m, uint64_t c0, 
                                                    (int)((k + 1) * LAYOUT_THREADS * 4));
         if (e != cudaSuccess) return e;
         bucket_scatter_staged_kernel<<<grid, LAYOUT_THREADS, (size_t)(k + 1) * LAYOUT_THREADS * 4, s>>>(
-            lit, m, k, bucket_vars, n_buckets, bkt, cta_base, planes, m_pad, orig_id, min_resident, resident_cap, cta0, n_cta, packed, tail_rows);
+            lit, m, k, bucket_vars, n_buckets, bkt, cta_base, planes, m_pad, orig_id, min_resident, resident_cap, cta0, n_cta, packed, rows);
     } else
         bucket_scatter_kernel<<<grid, LAYOUT_THREADS, 0, s>>>(lit, m, k, bucket_vars, n_buckets, bkt, cta_base, planes, m_pad, orig_id,
                                                                min_resident, resident_cap, width_in, width_out, cta0, n_cta);

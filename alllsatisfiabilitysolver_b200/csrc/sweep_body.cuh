@@ -348,10 +348,10 @@ struct SurvivorQueue {
             const uint32_t slot = act ? g_smem[qbuf + count - n + lane] : 0u;
             constexpr int T = K > E ? K - E : 1;     // tail planes (T = 1 only keeps the arrays legal when E == K)
             uint32_t l[T];
-            if (K - E <= 4 && p.tail_rows != nullptr) {       // one 16-byte row instead of K - E scattered plane words
-                const uint4 t = act ? __ldg(p.tail_rows + slot) : make_uint4(0u, 0u, 0u, 0u);
+            if (E >= 4 && K <= 8 && p.rows8 != nullptr) {     // the second half of the clause's row (literals 4..7) instead of K - E scattered plane words
+                const uint4 t = act ? __ldg(p.rows8 + 2 * (uint64_t)slot + 1) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                for (int j = 0; j < K - E; j++) l[j] = comp(t, j);
+                for (int j = 0; j < K - E; j++) l[j] = comp(t, E - 4 + j);
             } else {
 #pragma unroll
                 for (int j = 0; j < K - E; j++) l[j] = act ? __ldg(p.planes + (uint64_t)(E + j) * p.m_pad + slot) : 0u;
