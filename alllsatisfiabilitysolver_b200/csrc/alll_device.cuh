@@ -276,6 +276,11 @@ struct P2PLink {                         // device-resident, one per handle
 };
 
 // Claim storage of a handle (+ the records the sweep of this round wrote next to the violated list, if any).
+// Sharded persistent solve: set by any thread of the CTA that stored into a peer's exchange region this round.  A CTA that
+// stored nothing draws its ticket without the system-scope fence (~3 us on the critical path of every round; in the late
+// rounds of a solve most CTAs find no violated clause at all).
+__shared__ uint32_t g_remote_dirty;
+
 struct MisScratch {
     unsigned long long *claim;  // [n_vars][2] claim words (even / odd Luby steps), CLAIM_FREE between rounds
     const uint32_t *urec;       // [urec_cap][k+1] records {id, literals} parallel to viol[] (NULL: none)

@@ -88,6 +88,7 @@ __device__ __forceinline__ void incr_eval_body(const IncrParams &p, uint32_t n_s
                     // contiguous) per peer
                     const P2PLink &L = *x.link;
                     const uint32_t n_new = __popc(bal);
+                    if (lane == 0) g_remote_dirty = 1u;
                     if ((uint64_t)g + n_new > L.cap) {
                         if (lane == 0) { x.ctr->p2p_error = 1; for (uint32_t q = 0; q < L.world; q++) L.hdr[q]->abort = x.abort_val; }
                     } else {

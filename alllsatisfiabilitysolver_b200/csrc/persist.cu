@@ -38,7 +38,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(cons
     __shared__ uint32_t s_prev_n_u;          // |U| of the previous round (m / 2^K before the first)
     Counters *const c = sp.ctr;
 #define ALLL_LEAD (blockIdx.x == 0 && threadIdx.x == 0)
-    if (threadIdx.x == 0) s_prev_n_u = (uint32_t)min((uint64_t)0xFFFFFFFFu, ((uint64_t)sp.n_tiles * TILE) >> K);
+    if (threadIdx.x == 0) {
+        s_prev_n_u = (uint32_t)min((uint64_t)0xFFFFFFFFu, ((uint64_t)sp.n_tiles * TILE) >> K);
+        g_remote_dirty = 0u;
+    }
     __syncthreads();
     for (uint32_t round = 0; round < max_rounds; ++round) {
         const uint32_t par = round & 1u, tag = ((epoch & 0xFFFu) << 20) | (round + 1u);
@@ -69,7 +72,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(cons
             if (lead && round < DBG_ROUNDS) c->dbg_x[round][0] = global_ns();
             __syncthreads();
             if (threadIdx.x == 0) {
-                fence_acq_rel_sys();
+                if (g_remote_dirty) {                    // (only CTAs that stored records this round pay the system-scope fence)
+                    fence_acq_rel_sys();
+                    g_remote_dirty = 0u;
+                }
                 const unsigned int t = atomicAdd(&c->cta_done, 1u);
                 if (lead && round < DBG_ROUNDS) c->dbg_x[round][1] = global_ns();
                 if (t == gridDim.x - 1) {

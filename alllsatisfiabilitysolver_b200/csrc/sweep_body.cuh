@@ -77,6 +77,7 @@ struct WarpCompactor {
             // fused compute + collective: the violated clauses go straight into every GPU's receive slot for this
             // rank and round (NVLink P2P stores), as records {global id, k literals}
             const P2PLink &L = *sp->p2p;
+            if (lane == 0) g_remote_dirty = 1u;
             if ((uint64_t)g + count > L.cap) {
                 if (lane == 0) { ctr->p2p_error = 1; for (uint32_t q = 0; q < L.world; q++) L.hdr[q]->abort = sp->p2p_epoch + 1u; }
             } else {
