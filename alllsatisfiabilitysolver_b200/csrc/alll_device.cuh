@@ -225,6 +225,8 @@ struct Counters {
     // ALLL_TRACE, sharded persistent solve, block 0 / thread 0: [r][0] own sweep body done  [1] record stores fenced (system
     // scope) + ticket drawn  [2] (the CTA with the last ticket) count + flag stored into every GPU  [3] every rank's flag seen
     unsigned long long dbg_x[32][4];
+    // ALLL_TRACE: %globaltimer at the end of every CTA's sweep body in round 1 of a persistent solve (tail / imbalance study)
+    unsigned long long dbg_cta[256];
 };
 constexpr uint32_t DBG_ROUNDS = 32;
 

@@ -621,6 +621,17 @@ void print_phases(const Counters &c, uint64_t rounds)
         }
     }
     const uint64_t nr = std::min<uint64_t>(rounds, DBG_ROUNDS);
+    if (nr > 1 && c.dbg_cta[0] >= c.dbg[1][0]) {        // when every CTA left the sweep body of round 1 (us after block 0 entered it)
+        std::vector<std::pair<double, int>> t;
+        for (int b = 0; b < 256 && c.dbg_cta[b] >= c.dbg[1][0]; b++) t.emplace_back((double)(c.dbg_cta[b] - c.dbg[1][0]) * 1e-3, b);
+        std::sort(t.begin(), t.end());
+        fprintf(stderr, "[alll tail] round 1, %zu CTAs: sweep body done min %.1f | median %.1f | p90 %.1f | max %.1f us; slowest:", t.size(), t.front().first,
+                t[t.size() / 2].first, t[t.size() * 9 / 10].first, t.back().first);
+        for (size_t i = t.size() > 8 ? t.size() - 8 : 0; i < t.size(); i++) fprintf(stderr, " cta %d %.1f", t[i].second, t[i].first);
+        fprintf(stderr, "; fastest:");
+        for (size_t i = 0; i < 4 && i < t.size(); i++) fprintf(stderr, " cta %d %.1f", t[i].second, t[i].first);
+        fprintf(stderr, "\n");
+    }
     for (uint64_t r = 0; r < nr; r++) {
         const unsigned long long *d = c.dbg[r];
         auto us = [&](int i) { return d[i] >= d[0] ? (double)(d[i] - d[0]) * 1e-3 : -1.0; };

@@ -143,6 +143,7 @@ __global__ void reset_counters_kernel(Counters *c, int reset_totals)
     if (reset_totals) {
         for (int s = 0; s < 16; s++) c->dbg_step[s][0] = 0;
         for (int r = 0; r < 32; r++) c->dbg_x[r][0] = c->dbg_x[r][3] = 0;
+        c->dbg_cta[0] = 0;
         c->n_incr_rounds = 0;
         c->n_evals_incr = 0;
         c->n_iterations = 0;

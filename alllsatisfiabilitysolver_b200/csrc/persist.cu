@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(cons
         const bool incremental = ip.rows != nullptr && round > 0 && gm::ld_cg(&c->incr_next) != 0;
         if (incremental) incr_eval_body(ip, gm::ld_cg(&c->last_n_s), &c->n_viol_pp[par], IncrP2P{sp.p2p, s_prefix, par, sp.orig_id, sp.id_base, c, sp.p2p_epoch + 1u});
         else sweep_planes_body<K, RB, RC, E, false, PK>(sp, &c->n_viol_pp[par], par, rec_on);
+        if (threadIdx.x == 0 && round == 1u && blockIdx.x < 256u) c->dbg_cta[blockIdx.x] = global_ns();
         GridBarrier bar{cg::this_grid()};
         const bool lead = ALLL_LEAD;
         const bool p2p = sp.p2p != nullptr;  // clause-range sharded solve: every GPU runs this kernel on its range
