@@ -31,7 +31,8 @@ SYMBOLS = [
     "alll_upload_fixedk", "alll_upload_fixedk_device", "alll_upload_csr",
     "alll_set_assignment", "alll_get_assignment", "alll_randomize",
     "alll_eval", "alll_verify", "alll_round", "alll_solve",
-    "alll_time_sweep", "alll_launch_count", "alll_layout_info", "alll_sweep_info",
+    "alll_time_sweep", "alll_launch_count", "alll_layout_info", "alll_sweep_info", "alll_upload_fixedk_streamed",
+    "alll_multi_upload_fixedk_streamed",
     "alll_set_id_base", "alll_shard_sweep", "alll_shard_round", "alll_get_stats", "alll_reset_stats",
     "alll_batch_upload", "alll_batch_solve",
     "alll_p2p_create", "alll_p2p_connect", "alll_solve_p2p",

@@ -100,6 +100,8 @@ cudaError_t launch_randomize(uint32_t *bits, uint64_t n_vars, uint32_t n_words_a
 cudaError_t launch_fill_u64(unsigned long long *p, uint64_t n, unsigned long long value, cudaStream_t s);
 
 // capi.cu: what the single-process multi-GPU layer (multi.cu) needs beyond the C ABI
+int internal_upload_fixedk_streamed(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit, alll_filled_fn filled,
+                                    void *user, uint64_t filled_base);
 void *internal_p2p_region(alll_handle h);
 int internal_p2p_create_local(alll_handle h, uint32_t world, uint32_t rank, uint64_t cap_records);   // exchange region, no IPC export
 bool internal_csr_is_uniform(const uint64_t *off, uint64_t m);

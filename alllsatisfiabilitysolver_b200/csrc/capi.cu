@@ -291,8 +291,11 @@ int check_sizes(alll_handle h, uint64_t n_vars, uint64_t m)
 // host_lit != NULL: d_lit is the staging buffer of a host-buffer upload that has NOT been filled yet -- the copy is issued
 // here, in chunks on the copy stream, and the first layout pass (transpose, or bucket count) runs chunk by chunk behind it,
 // so that pass hides under the PCIe transfer instead of following it.
+// filled != NULL (host-buffer upload only): the producer is still filling host_lit; filled(user, filled_base + c) blocks
+// until rows [0, c) of host_lit are there (non-zero return: the producer gave up -> ALLL_BAD_ARG).
 int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *d_lit,
-                              const uint8_t *d_width_in = nullptr, const uint32_t *host_lit = nullptr)
+                              const uint8_t *d_width_in = nullptr, const uint32_t *host_lit = nullptr,
+                              alll_filled_fn filled = nullptr, void *filled_user = nullptr, uint64_t filled_base = 0)
 {
     free_instance(h);
     if (int rc = check_sizes(h, n_vars, m)) return rc;
@@ -336,22 +339,33 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
         cut.push_back(m);
         CK(cudaEventRecord(h->ev_chunk[32], h->stream));                // the staging buffer may still be read by earlier work
         CK(cudaStreamWaitEvent(h->copy_stream, h->ev_chunk[32], 0));
-        for (size_t i = 0; i + 1 < cut.size(); i++) {
-            CK(cudaMemcpyAsync(const_cast<uint32_t *>(d_lit) + cut[i] * k, host_lit + cut[i] * k, (cut[i + 1] - cut[i]) * k * 4,
-                               cudaMemcpyHostToDevice, h->copy_stream));
-            CK(cudaEventRecord(h->ev_chunk[i], h->copy_stream));
-        }
     }
-    auto chunk_ready = [&](size_t i) -> cudaError_t {               // the layout stream waits for chunk i of the copy
-        return host_lit && m ? cudaStreamWaitEvent(h->stream, h->ev_chunk[i], 0) : cudaSuccess;
+    bool producer_gave_up = false;
+    // chunk i: (streamed upload: wait until the producer has filled it,) enqueue its copy, make the layout stream wait for it
+    auto chunk_ready = [&](size_t i) -> cudaError_t {
+        if (!(host_lit && m)) return cudaSuccess;
+        if (filled && filled(filled_user, filled_base + cut[i + 1]) != 0) { producer_gave_up = true; return cudaErrorUnknown; }
+        cudaError_t e = cudaMemcpyAsync(const_cast<uint32_t *>(d_lit) + cut[i] * k, host_lit + cut[i] * k, (cut[i + 1] - cut[i]) * k * 4,
+                                        cudaMemcpyHostToDevice, h->copy_stream);
+        if (e != cudaSuccess) return e;
+        e = cudaEventRecord(h->ev_chunk[i], h->copy_stream);
+        if (e != cudaSuccess) return e;
+        return cudaStreamWaitEvent(h->stream, h->ev_chunk[i], 0);
     };
+#define CK_CHUNK(i)                                                                                     \
+    do {                                                                                                \
+        const cudaError_t e_ = chunk_ready(i);                                                          \
+        if (producer_gave_up) { cudaStreamSynchronize(h->copy_stream); cudaStreamSynchronize(h->stream); free_instance(h);  \
+                                return fail(h, ALLL_BAD_ARG, "streamed upload: the producer of the host buffer gave up"); } \
+        CK(e_);                                                                                         \
+    } while (0)
 
     if (h->n_buckets == 1) {
         h->m_pad = align_up(m, TILE);
         // padding slots are never evaluated (masked by slot_end), so the planes need no clearing
         if (h->m_pad) POOL(h->d_planes, h->m_pad * k * 4);
         for (size_t i = 0; i + 1 < cut.size(); i++) {
-            CK(chunk_ready(i));
+            CK_CHUNK(i);
             CK(launch_transpose(d_lit, cut[i], cut[i + 1], k, n_vars, h->d_planes, h->m_pad, d_err, h->stream)); h->launches++;
         }
         segs[0] = BucketSeg{0u, (uint32_t)m, 0u, 0u};
@@ -390,7 +404,7 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
         if (fused_pack) POOL(h->d_packed, h->m_pad * 4 * 4);
         if (fused_rows) POOL(h->d_rows, h->m_pad * 8 * 4);
         for (size_t i = 0; i + 1 < cut.size() && m; i++) {
-            CK(chunk_ready(i));
+            CK_CHUNK(i);
             CK(launch_bucket_count(d_lit, m, cut[i], cut[i + 1], k, n_vars, bucket_vars, nb, d_bkt, d_cnt, d_err, h->stream));
             CK(launch_bucket_scan(d_cnt, m, cut[i], cut[i + 1], nb, h->d_segs + i * nb, d_err + 2, h->stream));
             CK(launch_bucket_scatter(d_lit, m, cut[i], cut[i + 1], k, bucket_vars, nb, d_bkt, d_cnt, h->d_planes, h->m_pad, h->d_orig_id,
@@ -903,7 +917,18 @@ int alll_upload_fixedk_device(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     return upload_fixedk_device_impl(h, n_vars, m, k, d_lit);
 }
 
+static int upload_fixedk_host(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit, alll_filled_fn filled,
+                              void *user, uint64_t filled_base);
+
 int alll_upload_fixedk(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit)
+{
+    return upload_fixedk_host(h, n_vars, m, k, lit, nullptr, nullptr, 0);
+}
+
+// alll_upload_fixedk with the host buffer still being produced: see include/alll_b200.h.  filled_base: position of lit's row 0
+// in the producer's numbering (multi.cu hands every device its own clause range of one buffer).
+static int upload_fixedk_host(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit, alll_filled_fn filled,
+                              void *user, uint64_t filled_base)
 {
     if (!h) return ALLL_BAD_ARG;
     if (m && !lit) return fail(h, ALLL_BAD_ARG, "lit == NULL");
@@ -912,7 +937,7 @@ int alll_upload_fixedk(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, c
     free_instance(h);
     const size_t bytes = (size_t)std::max<uint64_t>(m * k, 1) * 4;
     POOL(h->d_stage, bytes);
-    const int rc = upload_fixedk_device_impl(h, n_vars, m, k, h->d_stage, nullptr, lit);      // (issues the H2D copy itself, in chunks)
+    const int rc = upload_fixedk_device_impl(h, n_vars, m, k, h->d_stage, nullptr, lit, filled, user, filled_base);
     cudaStreamSynchronize(h->copy_stream);            // `lit` is the caller's again when we return, on every path
     cudaStreamSynchronize(h->stream);
     if (bytes > (4ull << 30)) {          // do not sit on a very large staging buffer
@@ -920,6 +945,11 @@ int alll_upload_fixedk(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, c
         h->caps.erase(reinterpret_cast<void **>(&h->d_stage));
     }
     return rc;
+}
+
+int alll_upload_fixedk_streamed(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit, alll_filled_fn filled, void *user)
+{
+    return upload_fixedk_host(h, n_vars, m, k, lit, filled, user, 0);
 }
 
 int alll_upload_csr(alll_handle h, uint64_t n_vars, uint64_t m, const uint64_t *off, const uint32_t *lit)
@@ -1841,6 +1871,12 @@ int alll_sweep_info(alll_handle h, uint64_t info[4])
 namespace alll {
 
 void *internal_p2p_region(alll_handle h) { return h ? h->d_p2p_region : nullptr; }
+
+int internal_upload_fixedk_streamed(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit, alll_filled_fn filled,
+                                    void *user, uint64_t filled_base)
+{
+    return upload_fixedk_host(h, n_vars, m, k, lit, filled, user, filled_base);
+}
 
 // alll_p2p_create without the CUDA IPC export: the peers live in this process and address the region directly
 int internal_p2p_create_local(alll_handle h, uint32_t world, uint32_t rank, uint64_t cap_records)

@@ -228,6 +228,12 @@ int alll_multi_destroy(alll_multi_handle mh)
 
 int alll_multi_upload_fixedk(alll_multi_handle mh, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit)
 {
+    return alll_multi_upload_fixedk_streamed(mh, n_vars, m, k, lit, nullptr, nullptr);
+}
+
+int alll_multi_upload_fixedk_streamed(alll_multi_handle mh, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit,
+                                      alll_filled_fn filled, void *user)
+{
     if (!mh) return ALLL_BAD_ARG;
     mh->has_instance = false;
     const uint32_t n = (uint32_t)mh->h.size();
@@ -235,7 +241,7 @@ int alll_multi_upload_fixedk(alll_multi_handle mh, uint64_t n_vars, uint64_t m, 
     // the fused exchange carries fixed-size records {id, k literals}, k <= 8; tiny instances gain nothing from sharding
     mh->sharded = n > 1 && k >= 1 && k <= 8 && (m >= (uint64_t)n * 4096 || ((mh->flags & ALLL_FLAG_FORCE_SHARDING) && m >= n));
     if (!mh->sharded) {
-        MCALL(0, alll_upload_fixedk(mh->h[0], n_vars, m, k, lit));
+        MCALL(0, internal_upload_fixedk_streamed(mh->h[0], n_vars, m, k, lit, filled, user, 0));
         MCALL(0, alll_set_id_base(mh->h[0], 0));
         mh->has_instance = true;
         return ALLL_OK;
@@ -248,7 +254,9 @@ int alll_multi_upload_fixedk(alll_multi_handle mh, uint64_t n_vars, uint64_t m, 
     mh->cap_records = (k >= 3 ? widest / 4 : widest) + 8192;
     // every device uploads ONLY its own clause range from the caller's buffer: N host->device copies side by side
     if (int rc = for_all_slots(mh, n, [&](uint32_t r) {
-            if (int e = alll_upload_fixedk(mh->h[r], n_vars, mh->hi[r] - mh->lo[r], k, lit + mh->lo[r] * k)) return e;
+            // (streamed: device r's chunks become ready as the producer's fill position passes them; `filled` is called from
+            // every slot thread)
+            if (int e = internal_upload_fixedk_streamed(mh->h[r], n_vars, mh->hi[r] - mh->lo[r], k, lit + mh->lo[r] * k, filled, user, mh->lo[r])) return e;
             if (int e = alll_set_id_base(mh->h[r], mh->lo[r])) return e;
             return internal_p2p_create_local(mh->h[r], n, r, mh->cap_records);
         }))

@@ -27,12 +27,14 @@
 #ifndef ALLL_B200_SATINSTANCE_H
 #define ALLL_B200_SATINSTANCE_H
 
+#include <atomic>
 #include <chrono>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <mutex>
 #include <random>
 #include <stdexcept>
 #include <string>
@@ -272,6 +274,36 @@ private:
         cap = want;
     }
 
+    // progress of a streamed flatten: units of clauses are filled by the flatten threads (any order), `filled_rows` is the
+    // contiguous prefix -- what alll_multi_upload_fixedk_streamed waits on
+    struct Streamed {
+        size_t unit = 0, n_units = 0, m = 0;
+        std::atomic<size_t> next{0}, filled_rows{0};
+        std::atomic<int> abort{0};
+        vector<char> done;
+        size_t prefix = 0;
+        std::mutex mu;
+        std::chrono::steady_clock::time_point t_last;
+        void finish(size_t u)
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            done[u] = 1;
+            while (prefix < n_units && done[prefix]) ++prefix;
+            filled_rows.store(std::min(m, prefix * unit), std::memory_order_release);
+            t_last = std::chrono::steady_clock::now();
+        }
+        double flatten_ms(std::chrono::steady_clock::time_point t0) const { return std::chrono::duration<double, std::milli>(t_last - t0).count(); }
+        static int filled(void *user, uint64_t rows_needed)       // alll_filled_fn
+        {
+            Streamed *s = static_cast<Streamed *>(user);
+            while (s->filled_rows.load(std::memory_order_acquire) < rows_needed) {
+                if (s->abort.load()) return 1;
+                std::this_thread::yield();
+            }
+            return s->abort.load();
+        }
+    };
+
     static unsigned flatten_threads(size_t m)
     {
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
@@ -325,7 +357,42 @@ private:
             size_t b0 = 0;
             while ((*clauses)[b0]->empty()) ++b0;
             const uint64_t w0 = (*(*clauses)[b0])[0]->literals->size();
-            if (w0 > 0 && w0 <= 32) {
+            if (w0 > 0 && w0 <= 32 && m >= (size_t)1 << 18 && !std::getenv("ALLL_NO_STREAMED_UPLOAD")) {
+                // Streamed: the flatten threads fill the staging buffer unit by unit IN ORDER while this thread sits in
+                // alll_multi_upload_fixedk_streamed, which copies and lays out every 64 MB chunk as soon as the fill position
+                // has passed it -- the upload hides behind the flatten instead of following it.
+                ensure_stage(stage_lit, stage_lit_cap, m * w0);
+                ensure_handle();
+                have_upload = false;
+                Streamed st;
+                st.unit = (size_t)1 << 16;
+                st.n_units = (m + st.unit - 1) / st.unit;
+                st.m = m;
+                st.done.assign(st.n_units, 0);
+                vector<std::thread> th;
+                for (unsigned t = 0; t < nt; t++)
+                    th.emplace_back([&] {
+                        for (;;) {
+                            const size_t u = st.next.fetch_add(1);
+                            if (u >= st.n_units || st.abort.load()) return;
+                            const bool ok = for_range(u * st.unit, std::min(m, (u + 1) * st.unit), [&](size_t p, const Clause<T> *cl) {
+                                const vector<T> &ls = *cl->literals;
+                                if (ls.size() != w0) return false;
+                                uint32_t *dst = stage_lit + p * w0;
+                                for (size_t j = 0; j < w0; j++) dst[j] = (uint32_t)ls[j];
+                                return true;
+                            });
+                            if (!ok) { st.abort.store(1); return; }
+                            st.finish(u);
+                        }
+                    });
+                const int rc = alll_multi_upload_fixedk_streamed(handle, (uint64_t)n_vars, m, (uint32_t)w0, stage_lit, &Streamed::filled, &st);
+                for (auto &x : th) x.join();
+                flatten_ms = st.flatten_ms(t0);
+                if (rc == ALLL_OK) { have_upload = true; return; }
+                if (!st.abort.load()) check(rc, "alll_multi_upload_fixedk_streamed");
+                // a clause of another width: the general two-pass path below
+            } else if (w0 > 0 && w0 <= 32) {
                 ensure_stage(stage_lit, stage_lit_cap, m * w0);
                 vector<char> uniform(nt, 1);
                 run_threads(nt, [&](unsigned t) {

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ALLL_ABI_VERSION 6
+#define ALLL_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define ALLL_API __attribute__((visibility("default")))
@@ -136,6 +136,15 @@ ALLL_API int alll_upload_fixedk(alll_handle h, uint64_t n_vars, uint64_t m, uint
 /* (The host buffer is copied in 64 MB chunks on a stream of its own while the first layout pass already works on the
  * chunks that have arrived; page-locked `lit` gets the full PCIe rate -- 1.28 GB in 23 ms on B200 -- pageable memory about
  * a fifth of it.  `lit` is the caller's again when the call returns.) */
+/* Same with the host buffer still being PRODUCED while the call runs (the drop-in SATInstance flattens the caller's Clause
+ * objects into page-locked memory with all host threads): the copy and the layout passes of a 64 MB chunk run while the
+ * producer fills the next one, so upload time hides behind the flatten instead of following it.  `filled(user, c)` must block
+ * until rows [0, c) of `lit` are complete and return 0 (it is asked for increasing c, up to m; from several host threads at
+ * once in the multi-GPU form); a non-zero return means the producer gave up (e.g. found a clause of another width): the
+ * upload is abandoned with ALLL_BAD_ARG and no instance is loaded.  filled == NULL: the buffer is complete (== alll_upload_fixedk). */
+typedef int (*alll_filled_fn)(void *user, uint64_t rows_needed);
+ALLL_API int alll_upload_fixedk_streamed(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit,
+                                         alll_filled_fn filled, void *user);
 /* Same, literals already in device memory (row-major [m][k]); the buffer is only read during the call. */
 ALLL_API int alll_upload_fixedk_device(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *d_lit);
 /* Variable width: off[m+1] into lit[].  Uniform-width input is routed to the fixed-k layout; ragged input whose widest
@@ -320,6 +329,10 @@ ALLL_API const char *alll_multi_last_error(alll_multi_handle mh);      /* mh == 
 /* Replaces the flattening + ownership of SATInstance::solve's vector<ClauseArray*> (SATInstance.h:60-66) for N GPUs. */
 ALLL_API int alll_multi_upload_fixedk(alll_multi_handle mh, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit);
 ALLL_API int alll_multi_upload_csr(alll_multi_handle mh, uint64_t n_vars, uint64_t m, const uint64_t *off, const uint32_t *lit);
+/* alll_upload_fixedk_streamed over the device list: every device copies its own clause range as soon as the producer's fill
+ * position has passed it. */
+ALLL_API int alll_multi_upload_fixedk_streamed(alll_multi_handle mh, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit,
+                                               alll_filled_fn filled, void *user);
 ALLL_API int alll_multi_set_assignment(alll_multi_handle mh, const uint8_t *bools);
 ALLL_API int alll_multi_get_assignment(alll_multi_handle mh, uint8_t *bools);
 ALLL_API int alll_multi_randomize(alll_multi_handle mh, uint64_t seed);

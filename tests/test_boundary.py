@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(built):
     out = subprocess.run(["nm", "-D", "--defined-only", built], capture_output=True, text=True, check=True).stdout
     exported = sorted(re.findall(r" T (alll_\w+)", out))
     assert exported == declared_symbols()          # nothing else leaks out of the library
-    assert lib.alll_abi_version() == 6
+    assert lib.alll_abi_version() == 7
 
 
 def test_library_is_sm100a_only(built):

@@ -214,3 +214,22 @@ def test_dropin_solve_over_several_gpus_from_cpp(lib, cli, oracle, tmp_path):
     assert a.returncode == 0 and b.returncode == 0, a.stdout + a.stderr
     it = lambda t: re.search(r"# Iterations\t= (\d+)\n# Resamples\t= (\d+)", t).groups()
     assert it(a.stdout) == it(b.stdout) and a.stdout.rstrip().endswith("SATISFIABLE")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ragged", [0, 1], ids=["uniform_streamed", "other_width_in_the_last_clause"])
+def test_dropin_solve_streams_the_flatten_into_the_upload(lib, ragged):
+    """SATInstance::solve on an instance large enough for the streamed path (>= 2^18 clauses): the flatten threads fill the
+    page-locked staging buffer in order while alll_multi_upload_fixedk_streamed copies and lays out the chunks behind them.
+    Same results as the non-streamed path; a clause of another width found at the very end of the flatten abandons the
+    streamed upload and the general path takes over."""
+    subprocess.run([os.path.join(ROOT, "tools", "build_dropin_bench.sh")], check=True, capture_output=True)
+    exe = os.path.join(ROOT, "tools", "dropin_bench")
+    base = [exe, "--n", "120000", "--k", "7", "--d", "28", "--threads", "4", "--steps", "2", "--ragged", str(ragged)]
+    out = {}
+    for mode, env in (("streamed", {}), ("whole_buffer", {"ALLL_NO_STREAMED_UPLOAD": "1"})):
+        r = subprocess.run(base, capture_output=True, text=True, env={**os.environ, **env})
+        assert r.returncode == 0, r.stdout + r.stderr
+        out[mode] = json.loads(r.stdout.strip().splitlines()[-1])
+        assert out[mode]["all_ok"] and out[mode]["m"] >= 1 << 18
+    assert out["streamed"]["sweeps_per_solve"] == out["whole_buffer"]["sweeps_per_solve"]

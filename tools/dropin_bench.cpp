@@ -3,7 +3,7 @@
 // example/main.cpp:149-178 builds them (n_threads batches, one `new Clause(new vector)` per clause); the timed call
 // flattens them, uploads, solves on the GPU(s) and writes var_arr->vars.
 //
-//   dropin_bench [--n 1000000] [--k 7] [--d 28] [--threads 16] [--gpus 1[,2,...]] [--steps 3] [--seed 1]
+//   dropin_bench [--n 1000000] [--k 7] [--d 28] [--threads 16] [--gpus 1[,2,...]] [--steps 3] [--seed 1] [--ragged 0|1]
 //
 // Prints one JSON line per entry of --gpus (the object graph is built once).  Build: see tools/build_dropin_bench.sh (g++ against include/ + liballl_b200.so; no nvcc needed).
 #include <algorithm>
@@ -28,6 +28,7 @@ int main(int argc, char **argv)
 {
     uint64_t n = 1000000, seed = 1;
     int k = 7, d = 28, n_threads = (int)std::max(1u, std::thread::hardware_concurrency()), steps = 3;
+    int ragged = 0;          // 1: the LAST clause loses a literal -- a streamed flatten finds the other width only at its very end
     std::vector<int> gpu_list{1};
     for (int i = 1; i + 1 < argc; i += 2) {
         const std::string a = argv[i];
@@ -41,6 +42,7 @@ int main(int argc, char **argv)
         }
         else if (a == "--steps") steps = atoi(argv[i + 1]);
         else if (a == "--seed") seed = strtoull(argv[i + 1], nullptr, 0);
+        else if (a == "--ragged") ragged = atoi(argv[i + 1]);
     }
     // configuration model: d slots per variable, shuffle, cut into k-tuples, drop repeats
     double t0 = now_ms();
@@ -72,6 +74,10 @@ int main(int argc, char **argv)
         m++;
     }
     std::vector<UINT_T>().swap(slots);
+    if (ragged && m > 0) {
+        for (int t = n_threads - 1; t >= 0; t--)
+            if (!clauses->at(t)->empty()) { clauses->at(t)->back()->literals->pop_back(); break; }
+    }
     const double build_ms = now_ms() - t0;
 
     bool all = true;
