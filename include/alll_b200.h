@@ -133,9 +133,10 @@ ALLL_API int alll_host_free(void *p);
  * planes, clauses bucketed by variable range when the bit-packed assignment exceeds the
  * shared-memory budget.  Replaces the Clause object graph of Clause.h:17-28. */
 ALLL_API int alll_upload_fixedk(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit);
-/* (The host buffer is copied in 64 MB chunks on a stream of its own while the first layout pass already works on the
- * chunks that have arrived; page-locked `lit` gets the full PCIe rate -- 1.28 GB in 23 ms on B200 -- pageable memory about
- * a fifth of it.  `lit` is the caller's again when the call returns.) */
+/* (The host buffer is copied in 64 MB chunks on a stream of its own while ALL layout passes -- bucket count, device-side
+ * scan, scatter into the planes, packed eager planes, row-major copy -- already work on the chunks that have arrived, so
+ * the call ends ~0.2 ms after the last byte; page-locked `lit` gets the full PCIe rate -- 1.28 GB in 23.3 ms on B200 --
+ * pageable memory about a fifth of it.  `lit` is the caller's again when the call returns.) */
 /* Same with the host buffer still being PRODUCED while the call runs (the drop-in SATInstance flattens the caller's Clause
  * objects into page-locked memory with all host threads): the copy and the layout passes of a 64 MB chunk run while the
  * producer fills the next one, so upload time hides behind the flatten instead of following it.  `filled(user, c)` must block
