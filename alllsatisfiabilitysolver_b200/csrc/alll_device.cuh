@@ -364,6 +364,7 @@ struct SweepParams {
 };
 constexpr uint32_t TUNE_NO_TAIL_ROWS = 2u;         // survivors fetch their tail literals from the planes (one sector per literal)
 constexpr uint32_t TUNE_NO_PACKED_PLANES = 4u;     // the sweep streams planes 0..4 even where the packed eager planes apply
+constexpr uint32_t TUNE_NO_NEXT_SWEEP_PREFETCH = 8u; // no L2 prefetch of the next sweep's first tiles at the end of a round
 constexpr uint32_t TUNE_CG_LUBY_BARRIER = 1u;      // Luby steps end with grid.sync() + a counter of their own instead of luby_barrier_fused
 
 } // namespace alll

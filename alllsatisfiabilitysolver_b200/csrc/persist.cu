@@ -131,6 +131,19 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) solve_persistent_kernel(cons
             bar.sync();
             if (lead) finish_round(mp, round, n_u, 2u);
         }
+        // While the round's last barrier gathers the CTAs (in a small round 147 of them have been idle since the sweep):
+        // pull the first tiles of this CTA's next sweep from HBM into L2, so the sweep's first loads do not start cold.
+        if (threadIdx.x == 32 && sp.prefetch_tiles != 0 && !(sp.tune & TUNE_NO_NEXT_SWEEP_PREFETCH)) {
+            const uint32_t r0 = __ldg(sp.run_begin + blockIdx.x), r1 = __ldg(sp.run_begin + blockIdx.x + 1);
+            if (r0 < r1) {
+                const uint4 run = __ldg(reinterpret_cast<const uint4 *>(sp.runs) + r0);
+                const uint32_t *const stream = PK ? sp.packed : sp.planes;
+                constexpr int NS = PK ? 4 : E;
+                for (uint32_t t = run.x; t < run.y && t < run.x + 2u + sp.prefetch_tiles; t++)
+#pragma unroll
+                    for (int j = 0; j < NS; j++) tma_prefetch_l2(stream + (uint64_t)j * sp.m_pad + (uint64_t)t * TILE, TILE * 4);
+            }
+        }
         bar.sync();                                      // new assignment visible to every SM before it is staged again
         if (threadIdx.x == 0) s_prev_n_u = n_u;          // (read again after the __syncthreads() inside the next sweep's staging... and here:)
         __syncthreads();
