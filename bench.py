@@ -732,6 +732,44 @@ def other_workloads(device: int):
                    "clause_evals_per_sec": st3.n_clause_evals / (st3.solve_ms * 1e-3), "violated_after_cap": left,
                    "note": "whole-clause Moser-Tardos resampling plateaus at this density (the reference does not terminate either)"}
     del lits3
+    # SURVEY 8d's two optional companions: uniform 3-SAT at ratio 2.0 (the convergent counterpart of cfg3, same n) and
+    # cfg4's strict-LLL variant (d = 12: k (d - 1) = 88 <= 2^8 / e - 1).  Never lose the other entries to these.
+    try:
+        m3b = 2_000_000
+        lits3b = uniform_ksat_torch(c3["n"], c3["k"], m3b, INSTANCE_SEED_BASE + 13)
+        s.upload_fixedk_device(c3["n"], m3b, c3["k"], lits3b.data_ptr())
+        s.randomize(61)
+        st3b = s.solve(61, 4000)
+        ok3b = st3b.status == 0 and independent_check(lits3b, s.get_assignment())
+        out["cfg3_convergent"] = {"workload": f"uniform 3-SAT n={c3['n']} m={m3b} (ratio 2.0)", "round_cap": 4000,
+                                  "status": "OK" if st3b.status == 0 else "MAX_ROUNDS", "verified": bool(ok3b),
+                                  "time_to_sat_ms": st3b.solve_ms if st3b.status == 0 else None, "sweeps": st3b.n_iterations,
+                                  "us_per_round": st3b.solve_ms * 1e3 / max(st3b.n_iterations, 1),
+                                  "rounds_per_sec": (st3b.n_iterations - (1 if st3b.status == 0 else 0)) / (st3b.solve_ms * 1e-3),
+                                  "clause_evals_per_sec": st3b.n_clause_evals / (st3b.solve_ms * 1e-3)}
+        del lits3b
+    except Exception as e:
+        out["cfg3_convergent"] = {"error": repr(e)}
+    try:
+        c4s = CONFIGS["cfg4"]
+        lits4s = bounded_degree_ksat_torch(c4s["n"], c4s["k"], 12, INSTANCE_SEED_BASE + 14)
+        m4s = int(lits4s.shape[0])
+        s.upload_fixedk_device(c4s["n"], m4s, c4s["k"], lits4s.data_ptr())
+        for i in range(3):
+            s.randomize(90 + i)
+            st4s = s.solve(90 + i)
+        ok4s = st4s.status == 0 and independent_check(lits4s, s.get_assignment())
+        alg4s = 4 * c4s["k"] * m4s + c4s["n"] // 8
+        out["cfg4_strict_lll"] = {"workload": f"bounded-degree 8-SAT n={c4s['n']} m={m4s} d=12 (strict symmetric LLL: k(d-1)=88 <= 2^8/e-1)",
+                                  "time_to_sat_ms": st4s.solve_ms, "sweeps": st4s.n_iterations, "verified": bool(ok4s),
+                                  "clause_evals_per_sec": st4s.n_clause_evals / (st4s.solve_ms * 1e-3),
+                                  "sweep_in_solve_ms": st4s.sweep_ms / max(st4s.n_iterations, 1), "between_sweeps_ms": st4s.between_sweeps_ms,
+                                  "roofline": roof("hbm", alg4s * st4s.n_iterations / (st4s.solve_ms * 1e-3) / 1e9,
+                                                   "whole solve launch (solve_persistent_kernel): 0.48 GB of literals per sweep, 4x the L2",
+                                                   sweep_phase_GBps=alg4s / (st4s.sweep_ms / max(st4s.n_iterations, 1) * 1e-3) / 1e9 if st4s.sweep_ms else None)}
+        del lits4s
+    except Exception as e:
+        out["cfg4_strict_lll"] = {"error": repr(e)}
     c5 = CONFIGS["cfg5"]
     n_inst = 8192
     off, blits = bounded_degree_batch_torch(n_inst, c5["n"], c5["k"], c5["d"], INSTANCE_SEED_BASE + 5)
@@ -809,7 +847,38 @@ def other_workloads(device: int):
         out["csr_ragged_40M"] = {"error": repr(e)}
     s.close()
     torch.cuda.empty_cache()
+    out["dropin_cpp"] = dropin_cpp_records()
     return out
+
+
+def dropin_cpp_records(timeout_s: float = 170.0):
+    """The reference-facing C++ entry point end to end: tools/dropin_bench (compiled by build()) builds heap Clause objects the
+    way example/main.cpp:149-178 does and times SATInstance::solve(vector<ClauseArray*>*) (SATInstance.h:60-66) -- flatten,
+    upload, solve on the GPU, var_arr->vars written -- on cfg2 and cfg4; every result is re-checked clause by clause on the
+    host through the public Clause API.  A process of its own (C++ caller, own CUDA context), outside every timed region of
+    this file; the object graphs (40 M clauses: ~5 GB of host heap) are built before its timer starts."""
+    exe = os.path.join(ROOT, "tools", "dropin_bench")
+    if not os.path.exists(exe):
+        return {"error": "tools/dropin_bench is not built (__graft_entry__.build() compiles it)"}
+    recs = {}
+    t_start = time.perf_counter()
+    for name in ("cfg2", "cfg4"):
+        c = CONFIGS[name]
+        left = timeout_s - (time.perf_counter() - t_start)
+        if left < 20:
+            recs[name] = {"error": "skipped: time budget of the drop-in records used up"}
+            continue
+        try:
+            pkg = os.path.join(ROOT, "alllsatisfiabilitysolver_b200")
+            env = dict(os.environ, LD_LIBRARY_PATH=pkg + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+            p = subprocess.run([exe, "--n", str(c["n"]), "--k", str(c["k"]), "--d", str(c["d"]), "--steps", "3", "--gpus", "1"],
+                               capture_output=True, text=True, timeout=left, env=env)
+            line = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+            recs[name] = json.loads(line[-1]) if line else {"error": f"rc={p.returncode}: {p.stderr[-300:]}"}
+        except Exception as e:
+            recs[name] = {"error": repr(e)}
+    recs["call"] = "SATInstance<uint32_t>::solve(vector<ClauseArray*>*) on heap Clause objects, one process, one GPU; solve_call_ms is the whole call"
+    return recs
 
 
 def cfg5_over_ranks(rank, world, local_rank, n_seeds=8192, n_inst=8192, reps=3):
