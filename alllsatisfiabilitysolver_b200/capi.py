@@ -31,7 +31,7 @@ SYMBOLS = [
     "alll_upload_fixedk", "alll_upload_fixedk_device", "alll_upload_csr",
     "alll_set_assignment", "alll_get_assignment", "alll_randomize",
     "alll_eval", "alll_verify", "alll_round", "alll_solve",
-    "alll_time_sweep", "alll_launch_count", "alll_layout_info", "alll_sweep_info", "alll_upload_fixedk_streamed",
+    "alll_time_sweep", "alll_launch_count", "alll_layout_info", "alll_sweep_info", "alll_upload_info", "alll_upload_fixedk_streamed",
     "alll_multi_upload_fixedk_streamed",
     "alll_set_id_base", "alll_shard_sweep", "alll_shard_round", "alll_get_stats", "alll_reset_stats",
     "alll_batch_upload", "alll_batch_solve",
@@ -127,6 +127,7 @@ def load() -> C.CDLL:
     L.alll_launch_count.argtypes = [vp, C.POINTER(u64)]
     L.alll_layout_info.argtypes = [vp, C.POINTER(u64)]
     L.alll_sweep_info.argtypes = [vp, C.POINTER(u64)]
+    L.alll_upload_info.argtypes = [vp, C.POINTER(u64)]
     L.alll_set_id_base.argtypes = [vp, u64]
     L.alll_shard_sweep.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.alll_shard_round.argtypes = [vp, vp, C.POINTER(u64), u32, u64, u64, u32, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
@@ -390,6 +391,12 @@ class Solver:
         info = (C.c_uint64 * 4)()
         self._check(self.lib.alll_sweep_info(self.h, info))
         return dict(packed=bool(info[0]), bucket_relative_literals=info[1], streamed_bytes_per_clause=info[2], min_resident=info[3])
+
+    def upload_info(self) -> dict:
+        """How the last host-buffer upload crossed the link (packed H2D transport, include/alll_b200.h)."""
+        info = (C.c_uint64 * 4)()
+        self._check(self.lib.alll_upload_info(self.h, info))
+        return dict(link_bytes=info[0], packed_chunks=info[1], raw_chunks=info[2], pack_threads=info[3])
 
 
 class MultiSolver:

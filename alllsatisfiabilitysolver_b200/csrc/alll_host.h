@@ -98,6 +98,10 @@ cudaError_t launch_pack_bits(const uint8_t *bools, uint64_t n_vars, uint32_t *bi
 cudaError_t launch_unpack_bits(const uint32_t *bits, uint64_t n_vars, uint8_t *bools, cudaStream_t s);
 cudaError_t launch_randomize(uint32_t *bits, uint64_t n_vars, uint32_t n_words_alloc, uint64_t seed, cudaStream_t s);
 cudaError_t launch_fill_u64(unsigned long long *p, uint64_t n, unsigned long long value, cudaStream_t s);
+cudaError_t launch_unpack25(const uint8_t *lo3, const uint8_t *hi, uint32_t *out, uint64_t n, cudaStream_t s);    // packed H2D transport
+
+// hostpack.cpp: n literals -> lo3[3 n] (low three bytes of each) + hi[ceil(n / 8)] (bit 24 of eight literals per byte); returns their OR
+uint32_t host_pack25(const uint32_t *src, size_t n, uint8_t *lo3, uint8_t *hi);
 
 // capi.cu: what the single-process multi-GPU layer (multi.cu) needs beyond the C ABI
 int internal_upload_fixedk_streamed(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit, alll_filled_fn filled,
@@ -110,6 +114,7 @@ bool internal_p2p_persistent_possible(alll_handle h);
 int internal_solve_p2p_begin(alll_handle h, uint64_t seed, uint64_t max_rounds, uint32_t epoch, uint64_t *launches0);   // enqueue only
 int internal_solve_p2p_end(alll_handle h, uint64_t m_global, uint64_t launches0, alll_stats *stats);                    // wait + statistics
 int *internal_flag_ptr(alll_handle h);
+void internal_h2d_pack_default_off(alll_handle h);
 int internal_flag_attach(alll_handle h, int *word);
 int internal_device(alll_handle h);
 

@@ -4,10 +4,12 @@
 // no CPU compute path in this file: every clause evaluation, independent-set decision and resample happens
 // in the kernels of persist.cu / sweep.cu / mis.cu / layout.cu.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -15,6 +17,7 @@
 #include "../../include/alll_b200.h"
 #include "alll_host.h"
 #include "csr_body.cuh"
+#include "packpipe.h"
 
 using namespace alll;
 
@@ -26,6 +29,7 @@ constexpr uint32_t DEFAULT_SWEEP_SMEM = 192u * 1024u;
 constexpr int MAX_TIMED_ROUNDS = 256;
 constexpr uint64_t URECORD_CAP = 16384;  // violated-clause records are written for violated sets up to this size
 constexpr int ROUNDS_IN_FLIGHT = 3;      // rounds the host enqueues ahead of the last one it has seen retire
+constexpr uint64_t PACK_MIN_LITERALS = 32ull << 20;   // automatic mode: uploads of at least 128 MB of literals
 
 } // namespace
 
@@ -77,6 +81,13 @@ struct alll_solver {
     size_t h_bools_cap = 0;
     uint8_t *h_stage = nullptr;          // pinned staging for rows the library builds itself (padded ragged input; grow-only)
     size_t h_stage_cap = 0;
+    // packed H2D transport (PackPipe below): page-locked ring of PACK_SLOTS packed chunks, its device mirror, one event per
+    // slot (the device slot has been unpacked), the mode (ALLL_H2D_PACK: -1 automatic, 0 off, 1 always), the last upload's record
+    uint8_t *h_pack = nullptr, *d_pack = nullptr;
+    size_t h_pack_cap = 0;
+    cudaEvent_t ev_slot[PACK_SLOTS] = {};
+    int h2d_pack = -1;
+    uint64_t up_link_bytes = 0, up_packed_chunks = 0, up_raw_chunks = 0, up_pack_threads = 0;
     uint8_t *d_width = nullptr, *d_width_in = nullptr;   // padded planes: true clause widths by slot / by caller id
     bool use_width = false;
     Counters *d_ctr = nullptr;
@@ -177,7 +188,7 @@ void release_buffers(alll_handle h)
 {
     dfree(h->d_planes); dfree(h->d_packed); dfree(h->d_orig_id); dfree(h->d_segs); dfree(h->d_sweep_segs); dfree(h->d_runs); dfree(h->d_run_begin); dfree(h->d_off); dfree(h->d_csr_lit); dfree(h->d_csr_start); dfree(h->d_csr_rank);
     dfree(h->d_bits); dfree(h->d_claim); dfree(h->d_urec); dfree(h->d_viol); dfree(h->d_s); dfree(h->d_ids_out);
-    dfree(h->d_state); dfree(h->d_bools); dfree(h->d_width); dfree(h->d_width_in); dfree(h->d_tmp_bkt); dfree(h->d_tmp_cnt); dfree(h->d_tmp_err); dfree(h->d_stage);
+    dfree(h->d_state); dfree(h->d_bools); dfree(h->d_width); dfree(h->d_width_in); dfree(h->d_tmp_bkt); dfree(h->d_tmp_cnt); dfree(h->d_tmp_err); dfree(h->d_stage); dfree(h->d_pack);
     dfree(h->d_sh_planes); dfree(h->d_sh_ids); dfree(h->d_sh_iota); dfree(h->d_sh_s); dfree(h->d_sh_state);
     dfree(h->d_b_planes); dfree(h->d_b_off); dfree(h->d_b_m); dfree(h->d_b_bits); dfree(h->d_b_lit); dfree(h->d_b_src_off);
     dfree(h->d_b_seeds); dfree(h->d_b_stats); dfree(h->d_b_bytes); dfree(h->d_b_winner); dfree(h->d_b_retry);
@@ -333,6 +344,8 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
     if (host_lit && m) {
         const uint64_t per = bucket_pass_clauses_per_cta();
         uint64_t chunk = std::max<uint64_t>(per, ((64ull << 20) / (4ull * k)) / per * per);
+        if (const char *e = getenv("ALLL_H2D_CHUNK_ROWS"))               // test knob: small chunks, so that small instances exercise the chunked paths
+            if (const uint64_t v = strtoull(e, nullptr, 0)) chunk = align_up(v, per);
         if ((m + chunk - 1) / chunk > 32) chunk = align_up((m + 31) / 32, per);
         cut.clear();
         for (uint64_t c0 = 0; c0 < m; c0 += chunk) cut.push_back(c0);
@@ -340,11 +353,66 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
         CK(cudaEventRecord(h->ev_chunk[32], h->stream));                // the staging buffer may still be read by earlier work
         CK(cudaStreamWaitEvent(h->copy_stream, h->ev_chunk[32], 0));
     }
+    // Packed transport (PackPipe above): complete host buffers of literals that fit 25 bits; automatic for large uploads.
+    std::unique_ptr<PackPipe> pipe;
+    bool src_pinned = false;
+    size_t pack_slot_bytes = 0, pack_hi_off = 0;
+    uint32_t retired = 0;                            // chunks whose copy is known to have completed
+    h->up_link_bytes = h->up_packed_chunks = h->up_raw_chunks = h->up_pack_threads = 0;
+    if (host_lit && m && !filled && 2 * n_vars <= (1ull << 25) && h->h2d_pack != 0 && (h->h2d_pack == 1 || m * k >= PACK_MIN_LITERALS)) {
+        cudaPointerAttributes attr{};
+        src_pinned = cudaPointerGetAttributes(&attr, host_lit) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        uint64_t widest = 0;
+        for (size_t i = 0; i + 1 < cut.size(); i++) widest = std::max(widest, cut[i + 1] - cut[i]);
+        pack_hi_off = (size_t)align_up(3 * widest * k, 64);
+        pack_slot_bytes = pack_hi_off + (size_t)align_up((widest * k + 7) / 8, 64);
+        const size_t need = pack_slot_bytes * PACK_SLOTS;
+        if (h->h_pack_cap < need) {
+            if (h->h_pack) { cudaFreeHost(h->h_pack); h->h_pack = nullptr; h->h_pack_cap = 0; }
+            CK(cudaMallocHost(&h->h_pack, need));
+            h->h_pack_cap = need;
+        }
+        POOL(h->d_pack, need);
+        const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+        const uint32_t nt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint32_t>(hw, 24u), (m + PACK_UNIT_ROWS - 1) / PACK_UNIT_ROWS));
+        h->up_pack_threads = nt;
+        pipe.reset(new PackPipe(host_lit, k, cut, h->h_pack, pack_slot_bytes, pack_hi_off, nt));
+    }
     bool producer_gave_up = false;
     // chunk i: (streamed upload: wait until the producer has filled it,) enqueue its copy, make the layout stream wait for it
     auto chunk_ready = [&](size_t i) -> cudaError_t {
         if (!(host_lit && m)) return cudaSuccess;
         if (filled && filled(filled_user, filled_base + cut[i + 1]) != 0) { producer_gave_up = true; return cudaErrorUnknown; }
+        if (pipe) {
+            const uint32_t ci = (uint32_t)i;
+            // (from page-locked memory the chunk goes as it is when the link has run dry before it is packed)
+            const bool packed = pipe->wait_chunk(ci, src_pinned, [&] {
+                while (retired < ci && cudaEventQuery(h->ev_chunk[retired]) == cudaSuccess) ++retired;
+                return retired;
+            });
+            cudaGetLastError();                      // (cudaErrorNotReady of the polls)
+            if (packed) {
+                const uint32_t slot = ci % PACK_SLOTS;
+                const uint64_t n_l = (cut[i + 1] - cut[i]) * k;
+                uint8_t *hs = h->h_pack + (size_t)slot * pack_slot_bytes, *ds = h->d_pack + (size_t)slot * pack_slot_bytes;
+                cudaError_t e = cudaSuccess;
+                // (the device slot's previous content has been expanded: ev_slot is recorded behind its unpack kernel)
+                if (ci >= (uint32_t)PACK_SLOTS) e = cudaStreamWaitEvent(h->copy_stream, h->ev_slot[slot], 0);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(ds, hs, 3 * n_l, cudaMemcpyHostToDevice, h->copy_stream);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(ds + pack_hi_off, hs + pack_hi_off, (n_l + 7) / 8, cudaMemcpyHostToDevice, h->copy_stream);
+                if (e == cudaSuccess) e = cudaEventRecord(h->ev_chunk[i], h->copy_stream);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(h->stream, h->ev_chunk[i], 0);
+                if (e == cudaSuccess) e = launch_unpack25(ds, ds + pack_hi_off, const_cast<uint32_t *>(d_lit) + cut[i] * k, n_l, h->stream);
+                if (e == cudaSuccess) e = cudaEventRecord(h->ev_slot[slot], h->stream);
+                h->launches++;
+                h->up_packed_chunks++;
+                h->up_link_bytes += 3 * n_l + (n_l + 7) / 8;
+                return e;
+            }
+            h->up_raw_chunks++;
+        }
+        h->up_link_bytes += (cut[i + 1] - cut[i]) * k * 4;
         cudaError_t e = cudaMemcpyAsync(const_cast<uint32_t *>(d_lit) + cut[i] * k, host_lit + cut[i] * k, (cut[i + 1] - cut[i]) * k * 4,
                                         cudaMemcpyHostToDevice, h->copy_stream);
         if (e != cudaSuccess) return e;
@@ -416,6 +484,17 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
             segs.assign(h->n_segs, BucketSeg{0u, 0u, 0u, 0u});
             for (uint32_t i = 0; i < h->n_segs; i++) segs[i].bucket = i % nb;
             CK(cudaMemcpyAsync(h->d_segs, segs.data(), sizeof(BucketSeg) * h->n_segs, cudaMemcpyHostToDevice, h->stream));
+        }
+    }
+    if (pipe) {
+        // every chunk has been issued, so every unit is packed or skipped; a literal above 25 bits lost its top bits on the
+        // way (the device-side range check saw the truncated value): same answer as the plain path gives
+        const uint32_t ora = pipe->or_acc.load();
+        pipe.reset();
+        if (ora >> 25) {
+            cudaStreamSynchronize(h->copy_stream); cudaStreamSynchronize(h->stream);
+            free_instance(h);
+            return fail(h, ALLL_BAD_ARG, "a literal references a variable >= n_vars");
         }
     }
     if (h->n_buckets == 1) {
@@ -861,6 +940,7 @@ int alll_create(const alll_config *cfg, alll_handle *out)
     s->clock_khz = prop.clockRate;
     s->flags = cfg ? cfg->flags : 0;
     if (const char *e = getenv("ALLL_TUNE")) s->tune = (uint32_t)strtoul(e, nullptr, 0);
+    if (const char *e = getenv("ALLL_H2D_PACK")) s->h2d_pack = atoi(e) > 0 ? 1 : 0;
     const uint32_t wbuf_bytes = (SWEEP_THREADS / 32) * (WBUF + QBUF) * 4;
     const uint32_t max_bits = (uint32_t)prop.sharedMemPerBlockOptin - wbuf_bytes - 1024;
     s->smem_budget = (cfg && cfg->sweep_smem_bytes) ? cfg->sweep_smem_bytes : DEFAULT_SWEEP_SMEM;
@@ -870,6 +950,8 @@ int alll_create(const alll_config *cfg, alll_handle *out)
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaStreamCreate failed"));
     if (cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaStreamCreate failed"));
     for (auto &ev : s->ev_chunk)
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaEventCreate failed"));
+    for (auto &ev : s->ev_slot)
         if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaEventCreate failed"));
     if (cudaMalloc(&s->d_ctr, sizeof(Counters)) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaMalloc(counters) failed"));
     if (cudaMemset(s->d_ctr, 0, sizeof(Counters)) != cudaSuccess) return bail(fail(h, ALLL_CUDA_ERROR, "cudaMemset(counters) failed"));
@@ -900,10 +982,12 @@ int alll_destroy(alll_handle h)
     if (h->h_ring) cudaFreeHost(h->h_ring);
     if (h->h_bools) cudaFreeHost(h->h_bools);
     if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->h_pack) cudaFreeHost(h->h_pack);
     for (auto &ev : h->ev_round) if (ev) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (cudaEvent_t e : h->ev_chunk) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_slot) if (e) cudaEventDestroy(e);
     delete h;
     return ALLL_OK;
 }
@@ -1865,6 +1949,16 @@ int alll_sweep_info(alll_handle h, uint64_t info[4])
     return ALLL_OK;
 }
 
+int alll_upload_info(alll_handle h, uint64_t info[4])
+{
+    if (!h || !info) return ALLL_BAD_ARG;
+    info[0] = h->up_link_bytes;
+    info[1] = h->up_packed_chunks;
+    info[2] = h->up_raw_chunks;
+    info[3] = h->up_pack_threads;
+    return ALLL_OK;
+}
+
 } // extern "C"
 
 // ---- internal entry points for the single-process multi-GPU layer (multi.cu); not part of the C ABI -----------------
@@ -1926,6 +2020,10 @@ int internal_solve_p2p_end(alll_handle h, uint64_t m_global, uint64_t launches0,
 }
 
 int *internal_flag_ptr(alll_handle h) { return h ? h->d_flag : nullptr; }
+
+// multi.cu: several device slots upload side by side from one host -- their pack threads would oversubscribe its cores, so
+// the packed transport stays off there unless ALLL_H2D_PACK=1 asks for it
+void internal_h2d_pack_default_off(alll_handle h) { if (h && h->h2d_pack < 0) h->h2d_pack = 0; }
 
 // Same-process peer: use the winner word another handle of this process created (plain device pointer, peer access on).
 int internal_flag_attach(alll_handle h, int *word)

@@ -475,6 +475,46 @@ cudaError_t launch_randomize(uint32_t *bits, uint64_t n_vars, uint32_t n_words_a
     return cudaGetLastError();
 }
 
+// Device side of the packed host-to-device transport (hostpack.cpp): lo3[3 n] + hi[ceil(n / 8)] -> n 32-bit literals.
+// One thread per 8 literals: 24 + 1 bytes in (three 8-byte loads), two 16-byte stores out; the last, partial group byte-wise.
+__global__ void __launch_bounds__(256) unpack25_kernel(const uint8_t *__restrict__ lo3, const uint8_t *__restrict__ hi,
+                                                      uint32_t *__restrict__ out, uint64_t n)
+{
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, i = g * 8;
+    if (i >= n) return;
+    const uint32_t hb = hi[g];
+    if (i + 8 <= n) {
+        const uint2 *p = reinterpret_cast<const uint2 *>(lo3 + 3 * i);
+        const uint2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        const uint32_t w0 = a.x, w1 = a.y, w2 = b.x, w3 = b.y, w4 = c.x, w5 = c.y;
+        uint4 o0, o1;
+        o0.x = (w0 & 0xFFFFFFu) | ((hb & 1u) << 24);
+        o0.y = (w0 >> 24) | ((w1 & 0xFFFFu) << 8) | (((hb >> 1) & 1u) << 24);
+        o0.z = (w1 >> 16) | ((w2 & 0xFFu) << 16) | (((hb >> 2) & 1u) << 24);
+        o0.w = (w2 >> 8) | (((hb >> 3) & 1u) << 24);
+        o1.x = (w3 & 0xFFFFFFu) | (((hb >> 4) & 1u) << 24);
+        o1.y = (w3 >> 24) | ((w4 & 0xFFFFu) << 8) | (((hb >> 5) & 1u) << 24);
+        o1.z = (w4 >> 16) | ((w5 & 0xFFu) << 16) | (((hb >> 6) & 1u) << 24);
+        o1.w = (w5 >> 8) | (((hb >> 7) & 1u) << 24);
+        uint4 *q = reinterpret_cast<uint4 *>(out + i);
+        q[0] = o0;
+        q[1] = o1;
+    } else {
+        for (uint32_t j = 0; i + j < n; j++) {
+            const uint8_t *b = lo3 + 3 * (i + j);
+            out[i + j] = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | (((hb >> j) & 1u) << 24);
+        }
+    }
+}
+
+// lo3 8-byte aligned, out 16-byte aligned
+cudaError_t launch_unpack25(const uint8_t *lo3, const uint8_t *hi, uint32_t *out, uint64_t n, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    unpack25_kernel<<<blocks_for((n + 7) / 8, 256), 256, 0, s>>>(lo3, hi, out, n);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fill_u64(unsigned long long *p, uint64_t n, unsigned long long value, cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;

@@ -202,6 +202,7 @@ int alll_multi_create(const int32_t *devices, uint32_t n_devices, const alll_con
             delete mh;
             return mfail(nullptr, rc, msg);
         }
+        if (n_devices > 1) internal_h2d_pack_default_off(h);
         mh->h.push_back(h);
     }
     for (uint32_t r = 1; r < n_devices; r++) {

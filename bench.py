@@ -415,6 +415,8 @@ def run_ours(args):
     host_affinity = None if os.environ.get("ALLL_BENCH_NO_AFFINITY") else bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # N ranks copy their replicas from ONE host at the same time: N x the pack threads would oversubscribe its cores
+        os.environ.setdefault("ALLL_H2D_PACK", "0")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     host_group = dist.new_group(backend="gloo") if world > 1 else None     # barriers that keep the waiting ranks' GPUs idle
 
@@ -519,6 +521,7 @@ def run_ours(args):
         e2e_evals += e2e_step(i).n_clause_evals
     barrier()
     e2e_s = time.perf_counter() - t0
+    up = e2e_solver.upload_info()                    # how the last step's literals crossed the link (packed H2D transport)
     e2e_solver.close()
 
     # ---- other BASELINE configs, briefly (parity-test cases, not bench lines): cfg2 single solve, cfg5 batch ----
@@ -655,7 +658,13 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_evals_all / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": 4 * k * m,
                     "d2h_bytes_per_step": n, "ms_per_step": e2e_s_max / e2e_steps * 1e3, "steps": e2e_steps,
-                    "call": "alll_upload_fixedk(host) + alll_randomize + alll_solve + alll_get_assignment(host)"},
+                    "call": "alll_upload_fixedk(host) + alll_randomize + alll_solve + alll_get_assignment(host)",
+                    "h2d_transport": {"host_buffer_bytes": 4 * k * m, "link_bytes_last_step": int(up["link_bytes"]),
+                                      "chunks_packed": int(up["packed_chunks"]), "chunks_as_they_are": int(up["raw_chunks"]),
+                                      "pack_threads": int(up["pack_threads"]),
+                                      "note": "h2d_bytes_per_step counts the caller's host buffer (the tensor that is copied); the library's host "
+                                              "threads re-pack its chunks to 25 bits per literal inside the timed region before they cross PCIe "
+                                              "(include/alll_b200.h: alll_upload_info; ALLL_H2D_PACK=0 sends the words as they are)"}},
             "gpu_launches": int(launches_all),
             "clocks": clk,
             "between_sweeps_ms_per_solve": sum(s.between_sweeps_ms for s in stats) / args.steps,

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ALLL_ABI_VERSION 7
+#define ALLL_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define ALLL_API __attribute__((visibility("default")))
@@ -369,6 +369,16 @@ ALLL_API int alll_layout_info(alll_handle h, uint64_t info[6]);
  *  leading literals stored relative to their bucket (0 when unpacked), bytes streamed per clause (the remaining literals
  *  are fetched only for clauses that survive the streamed ones), minimum number of bucket-resident leading literals}. */
 ALLL_API int alll_sweep_info(alll_handle h, uint64_t info[4]);
+
+/* How the most recent host-buffer upload (alll_upload_fixedk / alll_upload_csr on a uniform-width instance) crossed the link:
+ * {bytes sent host -> device, chunks sent packed, chunks sent as they are, host threads that packed}.  Packed transport:
+ * with n_vars <= 2^24 a literal (2*var+neg, example/main.cpp:168) has 25 significant bits; for uploads of >= 128 MB the
+ * library's host threads re-pack every ~64 MB chunk to 25 bits per literal in page-locked memory while earlier chunks are
+ * on the link and a kernel expands it on the device -- 0.78 of the bytes cross PCIe, and a pageable caller buffer is read
+ * by all host threads instead of by the driver's staging copy.  A chunk whose packing is not finished when the link runs
+ * dry goes as it is (page-locked callers).  Environment ALLL_H2D_PACK=0 turns it off, =1 forces it at any size; handles
+ * behind alll_multi_create with several devices default to off.  The uploaded instance is bit-identical either way. */
+ALLL_API int alll_upload_info(alll_handle h, uint64_t info[4]);
 
 #ifdef __cplusplus
 }

@@ -36,7 +36,30 @@ def test_library_exports_every_declared_symbol(built):
     out = subprocess.run(["nm", "-D", "--defined-only", built], capture_output=True, text=True, check=True).stdout
     exported = sorted(re.findall(r" T (alll_\w+)", out))
     assert exported == declared_symbols()          # nothing else leaks out of the library
-    assert lib.alll_abi_version() == 7
+    assert lib.alll_abi_version() == 8
+
+
+def test_host_packer_of_the_packed_transport(tmp_path):
+    """csrc/hostpack.cpp (25 bits per literal for the H2D copy) is plain host code: its AVX2 path equals its scalar path byte for
+    byte, the literals come back through the device kernel's arithmetic, nothing is written past the arrays."""
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    exe = str(tmp_path / "hostpack_check")
+    subprocess.run([cxx, "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "cpp", "hostpack_check.cpp"),
+                    os.path.join(PKG, "csrc", "hostpack.cpp")], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "hostpack ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_pack_threads_keep_the_ring_discipline_against_a_simulated_link(tmp_path):
+    """csrc/packpipe.h (pack threads + 4-slot ring of the packed transport) against a simulated copy engine that reads a slot
+    well after the chunk was issued: every literal arrives intact for any relative speed of packers and link, with and
+    without the as-it-is fallback."""
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    exe = str(tmp_path / "packpipe_check")
+    subprocess.run([cxx, "-O2", "-std=c++17", "-pthread", "-I", os.path.join(PKG, "csrc"), "-o", exe,
+                    os.path.join(ROOT, "tests", "cpp", "packpipe_check.cpp"), os.path.join(PKG, "csrc", "hostpack.cpp")], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "packpipe ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
 def test_library_is_sm100a_only(built):

@@ -647,3 +647,84 @@ def test_host_upload_in_several_chunks_matches_device_upload_and_oracle(capi, or
             assert st.status == 0 and (st.n_iterations, st.n_resamples, st.sum_mis_size) == (so.n_iterations, so.n_resamples, so.sum_mis_size)
             assert np.array_equal(s.get_assignment(), v) and s.verify()
         assert oracle.verify(off, flat, v)
+
+
+@pytest.mark.parametrize("pinned", [False, True], ids=["pageable", "page_locked"])
+@pytest.mark.parametrize("smem", [0, 65536], ids=["unbucketed", "bucketed"])
+def test_packed_h2d_transport_uploads_the_same_instance(capi, oracle, monkeypatch, smem, pinned):
+    """Packed host-to-device transport (include/alll_b200.h: alll_upload_info; csrc/hostpack.cpp, unpack25_kernel): the host
+    threads re-pack every chunk to 25 bits per literal, the device expands it.  Forced on a small instance with small chunks
+    (10 chunks: the 4-slot ring wraps twice) and variables beyond 2^23 (bit 24 of the literals in use): violated sets,
+    trajectory and statistics equal the plain upload's and the oracle's; from page-locked memory chunks may also go as they
+    are when the link runs dry first."""
+    import torch
+
+    from alllsatisfiabilitysolver_b200.instances import uniform_ksat
+
+    n, k, m, seed = 12_000_000, 8, 600_000, 77
+    lits = uniform_ksat(n, k, m, seed=0xD1CE)
+    assert int(lits.max()) >= 1 << 24
+    if pinned:
+        t = torch.from_numpy(lits.astype(np.int32)).pin_memory()
+        src = t.numpy().view(np.uint32)
+    else:
+        src = lits
+    off = np.arange(m + 1, dtype=np.uint64) * np.uint64(k)
+    flat = lits.reshape(-1)
+    monkeypatch.setenv("ALLL_H2D_CHUNK_ROWS", "65536")
+    monkeypatch.setenv("ALLL_H2D_PACK", "1")
+    sp = capi.Solver(sweep_smem_bytes=smem)
+    monkeypatch.setenv("ALLL_H2D_PACK", "0")
+    su = capi.Solver(sweep_smem_bytes=smem)
+    try:
+        sp.upload_fixedk(n, src)
+        su.upload_fixedk(n, src)
+        ip, iu = sp.upload_info(), su.upload_info()
+        assert iu["packed_chunks"] == 0 and iu["link_bytes"] == m * k * 4
+        assert ip["packed_chunks"] + ip["raw_chunks"] == 10 and ip["pack_threads"] >= 1
+        if not pinned:
+            assert ip["raw_chunks"] == 0 and ip["link_bytes"] == 3 * m * k + m * k // 8
+        assert ip["packed_chunks"] >= 1
+        v = oracle.randomize(n, seed)
+        want = oracle.sweep(off, flat, v)
+        for s in (sp, su):
+            s.randomize(seed)
+            cnt, ids = s.eval()
+            assert cnt == len(want) and np.array_equal(np.sort(ids), want)
+        so = oracle.solve(n, off, flat, v, seed)
+        for s in (sp, su):
+            st = s.solve(seed)
+            assert st.status == 0 and (st.n_iterations, st.n_resamples, st.sum_mis_size) == (so.n_iterations, so.n_resamples, so.sum_mis_size)
+            assert np.array_equal(s.get_assignment(), v)
+        assert oracle.verify(off, flat, v)
+        # a second upload through the same handle reuses the ring; a ragged tail (literal count not a multiple of 32 or 8)
+        m2 = 65536 * 3 + 1001
+        sp.upload_fixedk(n, np.ascontiguousarray(src[:m2, :7]))
+        su.upload_fixedk(n, np.ascontiguousarray(src[:m2, :7]))
+        for s in (sp, su):
+            s.randomize(seed + 1)
+        (c1, i1), (c2, i2) = sp.eval(), su.eval()
+        want2 = oracle.sweep(np.arange(m2 + 1, dtype=np.uint64) * np.uint64(7), np.ascontiguousarray(lits[:m2, :7]).reshape(-1), oracle.randomize(n, seed + 1))
+        assert c1 == c2 == len(want2) and np.array_equal(np.sort(i1), want2) and np.array_equal(np.sort(i2), want2)
+    finally:
+        sp.close()
+        su.close()
+
+
+def test_packed_h2d_transport_reports_an_out_of_range_literal(capi, monkeypatch):
+    """A literal above 25 bits cannot ride the packed transport; the upload must fail like the plain one does."""
+    n, k, m = 100_000, 5, 40_000
+    rng = np.random.default_rng(3)
+    lits = (rng.integers(0, n, size=(m, k), dtype=np.uint32) * 2).astype(np.uint32)
+    lits[m // 2, 3] = np.uint32((1 << 27) + 2)
+    monkeypatch.setenv("ALLL_H2D_CHUNK_ROWS", "8192")
+    for mode in ("1", "0"):
+        monkeypatch.setenv("ALLL_H2D_PACK", mode)
+        with capi.Solver() as s:
+            with pytest.raises(capi.AlllError) as e:
+                s.upload_fixedk(n, lits)
+            assert e.value.status == capi.BAD_ARG and "variable >= n_vars" in str(e.value)
+            lits_ok = lits.copy()
+            lits_ok[m // 2, 3] = 0
+            s.upload_fixedk(n, lits_ok)                 # the handle is usable afterwards
+            assert s.upload_info()["packed_chunks"] == (5 if mode == "1" else 0)
