@@ -3,6 +3,8 @@
 // Host control flow replaces SATInstance::solve -> parallel_solve (SATInstance.h:60-66, :217-320).  There is
 // no CPU compute path in this file: every clause evaluation, independent-set decision and resample happens
 // in the kernels of persist.cu / sweep.cu / mis.cu / layout.cu.
+#include <sched.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
@@ -374,7 +376,12 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
             h->h_pack_cap = need;
         }
         POOL(h->d_pack, need);
-        const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+        // (the cores this process may run on: a rank bound to its GPU's NUMA node packs with that node's cores)
+        uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+        {
+            cpu_set_t cs;
+            if (sched_getaffinity(0, sizeof(cs), &cs) == 0 && CPU_COUNT(&cs) > 0) hw = (uint32_t)CPU_COUNT(&cs);
+        }
         const uint32_t nt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint32_t>(hw, 24u), (m + PACK_UNIT_ROWS - 1) / PACK_UNIT_ROWS));
         h->up_pack_threads = nt;
         pipe.reset(new PackPipe(host_lit, k, cut, h->h_pack, pack_slot_bytes, pack_hi_off, nt));
