@@ -514,11 +514,15 @@ def run_ours(args):
         e2e_solver.get_assignment(e2e_out)
         return st
 
-    e2e_step(-1)
+    for i in range(min(3, max(1, args.warmup))):     # (the first calls grow the pooled buffers and the page-locked ring)
+        e2e_step(-1 - i)
     barrier()
+    e2e_step_ms = []
     t0 = time.perf_counter()
     for i in range(e2e_steps):
+        ts = time.perf_counter()
         e2e_evals += e2e_step(i).n_clause_evals
+        e2e_step_ms.append(round((time.perf_counter() - ts) * 1e3, 3))
     barrier()
     e2e_s = time.perf_counter() - t0
     up = e2e_solver.upload_info()                    # how the last step's literals crossed the link (packed H2D transport)
@@ -658,6 +662,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_evals_all / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": 4 * k * m,
                     "d2h_bytes_per_step": n, "ms_per_step": e2e_s_max / e2e_steps * 1e3, "steps": e2e_steps,
+                    "rank0_ms_of_each_step": e2e_step_ms,
                     "call": "alll_upload_fixedk(host) + alll_randomize + alll_solve + alll_get_assignment(host)",
                     "h2d_transport": {"host_buffer_bytes": 4 * k * m, "link_bytes_last_step": int(up["link_bytes"]),
                                       "chunks_packed": int(up["packed_chunks"]), "chunks_as_they_are": int(up["raw_chunks"]),
@@ -1145,7 +1150,7 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=sorted(CONFIGS))
     ap.add_argument("--scale", type=float, default=1.0, help="scale n (and m) of the workload; 1.0 = BASELINE size")
     ap.add_argument("--max-rounds", type=int, default=100000)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the brief cfg2 / cfg5 runs at N=1")
     ap.add_argument("--no-sharded", action="store_true", help="skip the clause-range sharded solves at N>1")
