@@ -370,21 +370,23 @@ int upload_fixedk_device_impl(alll_handle h, uint64_t n_vars, uint64_t m, uint32
         pack_hi_off = (size_t)align_up(3 * widest * k, 64);
         pack_slot_bytes = pack_hi_off + (size_t)align_up((widest * k + 7) / 8, 64);
         const size_t need = pack_slot_bytes * PACK_SLOTS;
+        bool ring_ok = true;
         if (h->h_pack_cap < need) {
             if (h->h_pack) { cudaFreeHost(h->h_pack); h->h_pack = nullptr; h->h_pack_cap = 0; }
-            CK(cudaMallocHost(&h->h_pack, need));
-            h->h_pack_cap = need;
+            // (no page-locked memory to spare: the upload goes as it is -- the transport is an optimisation, not a requirement)
+            if (cudaMallocHost(&h->h_pack, need) == cudaSuccess) h->h_pack_cap = need;
+            else { h->h_pack = nullptr; cudaGetLastError(); ring_ok = false; }
         }
-        POOL(h->d_pack, need);
-        // (the cores this process may run on: a rank bound to its GPU's NUMA node packs with that node's cores)
-        uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
-        {
+        if (ring_ok) {
+            POOL(h->d_pack, need);
+            // (the cores this process may run on: a rank bound to its GPU's NUMA node packs with that node's cores)
+            uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
             cpu_set_t cs;
             if (sched_getaffinity(0, sizeof(cs), &cs) == 0 && CPU_COUNT(&cs) > 0) hw = (uint32_t)CPU_COUNT(&cs);
+            const uint32_t nt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint32_t>(hw, 24u), (m + PACK_UNIT_ROWS - 1) / PACK_UNIT_ROWS));
+            h->up_pack_threads = nt;
+            pipe.reset(new PackPipe(host_lit, k, cut, h->h_pack, pack_slot_bytes, pack_hi_off, nt));
         }
-        const uint32_t nt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint32_t>(hw, 24u), (m + PACK_UNIT_ROWS - 1) / PACK_UNIT_ROWS));
-        h->up_pack_threads = nt;
-        pipe.reset(new PackPipe(host_lit, k, cut, h->h_pack, pack_slot_bytes, pack_hi_off, nt));
     }
     bool producer_gave_up = false;
     // chunk i: (streamed upload: wait until the producer has filled it,) enqueue its copy, make the layout stream wait for it

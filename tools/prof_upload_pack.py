@@ -21,6 +21,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="cfg4")
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--pageable-steps", type=int, default=2)
+ap.add_argument("--chunk-rows", default="0", help="comma list of ALLL_H2D_CHUNK_ROWS values (0 = the library's 64 MB chunks)")
 a = ap.parse_args()
 cfg = CONFIGS[a.workload]
 n, k = cfg["n"], cfg["k"]
@@ -36,6 +37,13 @@ out = out_t.numpy()
 res = {"workload": a.workload, "n": n, "m": m, "k": k, "host_buffer_bytes": 4 * k * m, "host_threads": os.cpu_count()}
 ref_assign = None
 for src_name, src, steps in (("page_locked", pinned, a.steps), ("pageable", pageable, a.pageable_steps)):
+  if steps <= 0:
+    continue
+  for chunk_rows in [int(x) for x in a.chunk_rows.split(",")]:
+    if chunk_rows:
+        os.environ["ALLL_H2D_CHUNK_ROWS"] = str(chunk_rows)
+    else:
+        os.environ.pop("ALLL_H2D_CHUNK_ROWS", None)
     for mode in ("0", "1", "0", "1"):                       # twice each, interleaved
         os.environ["ALLL_H2D_PACK"] = mode
         s = capi.Solver(device=0)
@@ -65,7 +73,7 @@ for src_name, src, steps in (("page_locked", pinned, a.steps), ("pageable", page
         if ref_assign is None:
             ref_assign = got
         same = bool(np.array_equal(got, ref_assign))
-        key = f"{src_name}_pack{mode}"
+        key = f"{src_name}_chunk{chunk_rows}_pack{mode}"
         rec = {"e2e_ms": ts, "upload_only_ms": up_ms, "upload_info": s.upload_info(), "same_assignment_as_first_variant": same, "verified": bool(s.verify())}
         res.setdefault(key, []).append(rec)
         print(key, "e2e", ["%.2f" % x for x in ts], "upload", ["%.2f" % x for x in up_ms], rec["upload_info"], same, file=sys.stderr)
