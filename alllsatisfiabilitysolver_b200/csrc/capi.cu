@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <map>
 #include <memory>
 #include <string>
@@ -157,6 +158,16 @@ int fail(alll_handle h, int status, const std::string &msg)
     if (h) h->err = msg; else g_create_error = msg;
     return status;
 }
+
+// No C++ exception may cross the C boundary (a caller in C, Go or Python cannot catch it, and unwinding through foreign
+// frames is undefined): every extern "C" function that returns a status is a function-try-block that ends in ALLL_GUARD.
+int guard_fail(alll_handle h, const char *what) noexcept
+{
+    try { return fail(h, ALLL_CUDA_ERROR, std::string("host-side failure: ") + what); } catch (...) { return ALLL_CUDA_ERROR; }
+}
+#define ALLL_GUARD(h)                                                                                   \
+    catch (const std::exception &e__) { return guard_fail((h), e__.what()); }                           \
+    catch (...) { return guard_fail((h), "unknown exception"); }
 
 #define CK(call)                                                                                        \
     do {                                                                                                \
@@ -901,32 +912,35 @@ extern "C" {
 int alll_abi_version(void) { return ALLL_ABI_VERSION; }
 
 int alll_device_count(int32_t *n)
-{
+try {
     if (!n) return ALLL_BAD_ARG;
     int c = 0;
     if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); c = 0; }
     *n = c;
     return ALLL_OK;
 }
+ALLL_GUARD(nullptr)
 
 int alll_host_alloc(uint64_t bytes, void **out)
-{
+try {
     if (!out) return ALLL_BAD_ARG;
     *out = nullptr;
     if (cudaMallocHost(out, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return ALLL_CUDA_ERROR; }
     return ALLL_OK;
 }
+ALLL_GUARD(nullptr)
 
 int alll_host_free(void *p)
-{
+try {
     if (p && cudaFreeHost(p) != cudaSuccess) { cudaGetLastError(); return ALLL_CUDA_ERROR; }
     return ALLL_OK;
 }
+ALLL_GUARD(nullptr)
 
 const char *alll_last_error(alll_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int alll_create(const alll_config *cfg, alll_handle *out)
-{
+try {
     alll_handle h = nullptr;   // CK() routes the message to g_create_error while h == NULL
     if (!out) return fail(nullptr, ALLL_BAD_ARG, "out == NULL");
     *out = nullptr;
@@ -978,9 +992,10 @@ int alll_create(const alll_config *cfg, alll_handle *out)
     *out = s;
     return ALLL_OK;
 }
+ALLL_GUARD(nullptr)
 
 int alll_destroy(alll_handle h)
-{
+try {
     if (!h) return ALLL_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
@@ -1000,23 +1015,26 @@ int alll_destroy(alll_handle h)
     delete h;
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_upload_fixedk_device(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *d_lit)
-{
+try {
     if (!h) return ALLL_BAD_ARG;
     if (m && !d_lit) return fail(h, ALLL_BAD_ARG, "d_lit == NULL");
     CK(cudaSetDevice(h->device));
     CK(cudaDeviceSynchronize());   // the caller's buffer may have been produced on another stream
     return upload_fixedk_device_impl(h, n_vars, m, k, d_lit);
 }
+ALLL_GUARD(h)
 
 static int upload_fixedk_host(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit, alll_filled_fn filled,
                               void *user, uint64_t filled_base);
 
 int alll_upload_fixedk(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit)
-{
+try {
     return upload_fixedk_host(h, n_vars, m, k, lit, nullptr, nullptr, 0);
 }
+ALLL_GUARD(h)
 
 // alll_upload_fixedk with the host buffer still being produced: see include/alll_b200.h.  filled_base: position of lit's row 0
 // in the producer's numbering (multi.cu hands every device its own clause range of one buffer).
@@ -1041,12 +1059,13 @@ static int upload_fixedk_host(alll_handle h, uint64_t n_vars, uint64_t m, uint32
 }
 
 int alll_upload_fixedk_streamed(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit, alll_filled_fn filled, void *user)
-{
+try {
     return upload_fixedk_host(h, n_vars, m, k, lit, filled, user, 0);
 }
+ALLL_GUARD(h)
 
 int alll_upload_csr(alll_handle h, uint64_t n_vars, uint64_t m, const uint64_t *off, const uint32_t *lit)
-{
+try {
     if (!h) return ALLL_BAD_ARG;
     if (!off || (m && off[m] > off[0] && !lit)) return fail(h, ALLL_BAD_ARG, "off/lit == NULL");
     CK(cudaSetDevice(h->device));
@@ -1159,6 +1178,7 @@ int alll_upload_csr(alll_handle h, uint64_t n_vars, uint64_t m, const uint64_t *
     h->has_instance = true;
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 // The caller's bool array is pageable memory: stage it through a pinned buffer (one fast memcpy + one DMA instead of
 // the driver's chunked pageable path).
@@ -1185,16 +1205,17 @@ static int upload_generator_impl(alll_handle h, uint64_t n_vars, uint64_t m, uin
 
 int alll_upload_generator(alll_handle h, uint64_t n_vars, uint64_t m, uint32_t k, alll_gen_launch_fn launch, void *user,
                           uint64_t cap_records)
-{
+try {
     if (!h) return ALLL_BAD_ARG;
     CK(cudaSetDevice(h->device));
     free_instance(h);
     return upload_generator_impl(h, n_vars, m, k, launch, user, cap_records);
 }
+ALLL_GUARD(h)
 
 int alll_upload_builtin_generator(alll_handle h, uint32_t kind, uint64_t n_vars, uint64_t m, uint32_t k, uint64_t seed,
                                   uint32_t d, uint64_t cap_records)
-{
+try {
     if (!h) return ALLL_BAD_ARG;
     CK(cudaSetDevice(h->device));
     free_instance(h);
@@ -1205,13 +1226,15 @@ int alll_upload_builtin_generator(alll_handle h, uint32_t kind, uint64_t n_vars,
     h->gen_builtin = g;
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_builtin_generator_clause(uint32_t kind, uint64_t n_vars, uint64_t m, uint32_t k, uint64_t seed, uint32_t d,
                                   uint64_t index, uint32_t *lits)
-{
+try {
     if (!lits) return ALLL_BAD_ARG;
     return builtin_generator_clause(kind, n_vars, m, k, seed, d, index, lits) ? ALLL_BAD_ARG : ALLL_OK;
 }
+ALLL_GUARD(nullptr)
 
 // true when the caller's buffer is page-locked (cudaMallocHost / cudaHostRegister): the copy engine can then use it
 // directly and the pinned staging hop (a 10 MB memcpy at n = 10 M) is skipped
@@ -1232,7 +1255,7 @@ static int ensure_pinned_bools(alll_handle h)
 }
 
 int alll_set_assignment(alll_handle h, const uint8_t *bools)
-{
+try {
     NEED_INSTANCE();
     if (!bools) return fail(h, ALLL_BAD_ARG, "bools == NULL");
     const uint8_t *src = bools;
@@ -1246,9 +1269,10 @@ int alll_set_assignment(alll_handle h, const uint8_t *bools)
     CK(cudaStreamSynchronize(h->stream));
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_get_assignment(alll_handle h, uint8_t *bools)
-{
+try {
     NEED_INSTANCE();
     if (!bools) return fail(h, ALLL_BAD_ARG, "bools == NULL");
     const bool direct = caller_buffer_is_pinned(bools);
@@ -1260,17 +1284,19 @@ int alll_get_assignment(alll_handle h, uint8_t *bools)
     if (!direct) std::memcpy(bools, h->h_bools, h->n_vars);
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_randomize(alll_handle h, uint64_t seed)
-{
+try {
     NEED_INSTANCE();
     CK(launch_randomize(h->d_bits, h->n_vars, h->n_words_alloc, seed, h->stream)); h->launches++;
     CK(cudaStreamSynchronize(h->stream));
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_eval(alll_handle h, uint32_t *ids, uint64_t cap, uint64_t *n_violated)
-{
+try {
     NEED_INSTANCE();
     if (int rc = enqueue_sweep(h)) return rc;
     if (int rc = fetch_counters(h)) return rc;
@@ -1284,18 +1310,20 @@ int alll_eval(alll_handle h, uint32_t *ids, uint64_t cap, uint64_t *n_violated)
     if (overflow) return fail(h, ALLL_CAPACITY, "violated set exceeds cap_records of the enumerated instance");
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_verify(alll_handle h, int *valid)
-{
+try {
     uint64_t n = 0;
     const int rc = alll_eval(h, nullptr, 0, &n);
     if (rc == ALLL_OK && valid) *valid = n == 0;
     return rc;
 }
+ALLL_GUARD(h)
 
 int alll_round(alll_handle h, uint64_t seed, uint32_t round, uint32_t *u_ids, uint64_t u_cap, uint64_t *n_u,
                uint32_t *s_ids, uint64_t s_cap, uint64_t *n_s, uint64_t *n_resampled)
-{
+try {
     NEED_INSTANCE();
     if (int rc = enqueue_sweep(h, 0u, 0u, 0xFFFFFFFFu, true)) return rc;
     if (int rc = enqueue_mis_resample(h, seed, round)) return rc;
@@ -1313,9 +1341,10 @@ int alll_round(alll_handle h, uint64_t seed, uint32_t round, uint32_t *u_ids, ui
     if (int rc = copy_ids_out(h, h->d_s, c.last_n_s, s_ids, s_cap)) return rc;
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *stats)
-{
+try {
     NEED_INSTANCE();
     if (!stats) return fail(h, ALLL_BAD_ARG, "stats == NULL");
     std::memset(stats, 0, sizeof(*stats));
@@ -1492,19 +1521,21 @@ int alll_solve(alll_handle h, uint64_t seed, uint64_t max_rounds, alll_stats *st
     if (status == ALLL_CAPACITY) return fail(h, ALLL_CAPACITY, "violated set exceeds cap_records of the enumerated instance");
     return status;
 }
+ALLL_GUARD(h)
 
 // ---- clause-range sharded mode ----------------------------------------------------
 
 int alll_set_id_base(alll_handle h, uint64_t id_base)
-{
+try {
     if (!h) return ALLL_BAD_ARG;
     if (id_base > 0xFFFFFFFFull) return fail(h, ALLL_BAD_ARG, "id_base must fit 32 bits");
     h->id_base = (uint32_t)id_base;
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_shard_sweep(alll_handle h, uint32_t *d_records, uint64_t cap_records, uint64_t *n_local)
-{
+try {
     NEED_INSTANCE();
     if (!h->k || h->use_width || h->gen_mode) return fail(h, ALLL_BAD_ARG, "sharded mode needs stored clauses of uniform width");
     if (!d_records && cap_records) return fail(h, ALLL_BAD_ARG, "d_records == NULL");
@@ -1521,11 +1552,12 @@ int alll_shard_sweep(alll_handle h, uint32_t *d_records, uint64_t cap_records, u
     if (n > cap_records) return fail(h, ALLL_CAPACITY, "record buffer too small for the local violated set");
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_shard_round(alll_handle h, const uint32_t *d_records, const uint64_t *counts, uint32_t n_blocks,
                      uint64_t block_cap, uint64_t seed, uint32_t round, uint64_t *n_total, uint64_t *n_s,
                      uint64_t *n_resampled)
-{
+try {
     NEED_INSTANCE();
     if (!h->k || h->gen_mode) return fail(h, ALLL_BAD_ARG, "sharded mode needs the fixed-width layout");
     if (!counts || n_blocks == 0 || n_blocks > MAX_SHARDS) return fail(h, ALLL_BAD_ARG, "bad shard count");
@@ -1563,9 +1595,10 @@ int alll_shard_round(alll_handle h, const uint32_t *d_records, const uint64_t *c
     CK(cudaStreamSynchronize(h->stream));
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_get_stats(alll_handle h, alll_stats *stats)
-{
+try {
     NEED_INSTANCE();
     if (!stats) return fail(h, ALLL_BAD_ARG, "stats == NULL");
     if (int rc = fetch_counters(h)) return rc;
@@ -1580,19 +1613,21 @@ int alll_get_stats(alll_handle h, alll_stats *stats)
     stats->n_kernel_launches = h->launches;
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_reset_stats(alll_handle h)
-{
+try {
     NEED_INSTANCE();
     CK(launch_reset_counters(h->d_ctr, 1, h->stream)); h->launches++;
     CK(cudaStreamSynchronize(h->stream));
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 // ---- sharded mode with the exchange fused into the kernels (NVLink P2P stores, CUDA IPC mappings) ---------
 
 int alll_p2p_create(alll_handle h, uint32_t world, uint32_t rank, uint64_t cap_records, uint8_t handle_out[64])
-{
+try {
     if (!handle_out) return h ? fail(h, ALLL_BAD_ARG, "handle_out == NULL") : ALLL_BAD_ARG;
     bool fresh = false;
     if (int rc = p2p_region_setup(h, world, rank, cap_records, &fresh)) return rc;
@@ -1606,9 +1641,10 @@ int alll_p2p_create(alll_handle h, uint32_t world, uint32_t rank, uint64_t cap_r
     std::memcpy(handle_out, h->p2p_ipc, 64);
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_p2p_connect(alll_handle h, const uint8_t *handles)
-{
+try {
     NEED_INSTANCE();
     if (!h->d_p2p_region || !handles) return fail(h, ALLL_BAD_ARG, "call alll_p2p_create first");
     void *bases[MAX_SHARDS] = {};
@@ -1630,9 +1666,10 @@ int alll_p2p_connect(alll_handle h, const uint8_t *handles)
         if (h->p2p_peer[q]) { cudaIpcCloseMemHandle(h->p2p_peer[q]); h->p2p_peer[q] = nullptr; }
     return p2p_link_up(h, bases);
 }
+ALLL_GUARD(h)
 
 int alll_solve_p2p(alll_handle h, uint64_t seed, uint64_t max_rounds, uint64_t m_global, uint32_t epoch, alll_stats *stats)
-{
+try {
     NEED_INSTANCE();
     if (!stats) return fail(h, ALLL_BAD_ARG, "stats == NULL");
     if (!h->p2p_ready) return fail(h, ALLL_BAD_ARG, "call alll_p2p_create / alll_p2p_connect first");
@@ -1727,12 +1764,13 @@ int alll_solve_p2p(alll_handle h, uint64_t seed, uint64_t max_rounds, uint64_t m
     stats->status = status;
     return status;
 }
+ALLL_GUARD(h)
 
 // ---- batched small instances / seed portfolio -------------------------------------------------------------
 
 int alll_batch_upload(alll_handle h, uint32_t n_instances, uint64_t n_vars, uint32_t k, const uint64_t *clause_off,
                       const uint32_t *lit)
-{
+try {
     if (!h) return ALLL_BAD_ARG;
     CK(cudaSetDevice(h->device));
     h->has_batch = false;
@@ -1787,10 +1825,11 @@ int alll_batch_upload(alll_handle h, uint32_t n_instances, uint64_t n_vars, uint
     h->has_batch = true;
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_batch_solve(alll_handle h, uint32_t n_jobs, const uint64_t *seeds, uint64_t max_rounds, int portfolio,
                      uint8_t *assignments, alll_batch_stats *stats, int32_t *winner, double *device_ms)
-{
+try {
     if (!h) return ALLL_BAD_ARG;
     if (!h->has_batch) return fail(h, ALLL_NO_INSTANCE, "no batch uploaded");
     CK(cudaSetDevice(h->device));
@@ -1835,11 +1874,12 @@ int alll_batch_solve(alll_handle h, uint32_t n_jobs, const uint64_t *seeds, uint
     if (winner) *winner = w;
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 // ---- multi-GPU portfolio: the first-SAT word shared by all ranks ------------------------------
 
 int alll_flag_create(alll_handle h, uint8_t handle_out[64])
-{
+try {
     if (!h || !handle_out) return ALLL_BAD_ARG;
     CK(cudaSetDevice(h->device));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -1852,9 +1892,10 @@ int alll_flag_create(alll_handle h, uint8_t handle_out[64])
     std::memcpy(handle_out, &ipc, 64);
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_flag_open(alll_handle h, const uint8_t *handle)
-{
+try {
     if (!h || !handle) return ALLL_BAD_ARG;
     CK(cudaSetDevice(h->device));
     if (h->d_flag) { if (h->flag_owner) cudaFree(h->d_flag); else if (!h->flag_borrowed) cudaIpcCloseMemHandle(h->d_flag); h->d_flag = nullptr; h->flag_borrowed = false; }
@@ -1866,9 +1907,10 @@ int alll_flag_open(alll_handle h, const uint8_t *handle)
     h->flag_owner = false;
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_flag_reset(alll_handle h)
-{
+try {
     if (!h) return ALLL_BAD_ARG;
     if (!h->d_flag || !h->flag_owner) return fail(h, ALLL_BAD_ARG, "only the rank that created the flag resets it");
     CK(cudaSetDevice(h->device));
@@ -1876,9 +1918,10 @@ int alll_flag_reset(alll_handle h)
     CK(cudaStreamSynchronize(h->stream));
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_flag_read(alll_handle h, int64_t *value)
-{
+try {
     if (!h || !value) return ALLL_BAD_ARG;
     if (!h->d_flag) return fail(h, ALLL_BAD_ARG, "no flag");
     CK(cudaSetDevice(h->device));
@@ -1888,16 +1931,18 @@ int alll_flag_read(alll_handle h, int64_t *value)
     *value = w;
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_batch_set_job_base(alll_handle h, uint32_t job_base)
-{
+try {
     if (!h) return ALLL_BAD_ARG;
     h->b_job_base = job_base;
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_time_sweep(alll_handle h, uint32_t reps, double *ms_per_sweep, uint64_t *n_violated)
-{
+try {
     NEED_INSTANCE();
     if (reps == 0) return fail(h, ALLL_BAD_ARG, "reps == 0");
     double total = 0.0;
@@ -1925,16 +1970,18 @@ int alll_time_sweep(alll_handle h, uint32_t reps, double *ms_per_sweep, uint64_t
     if (ms_per_sweep) *ms_per_sweep = total / reps;
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_launch_count(alll_handle h, uint64_t *n)
-{
+try {
     if (!h || !n) return ALLL_BAD_ARG;
     *n = h->launches;
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_layout_info(alll_handle h, uint64_t info[6])
-{
+try {
     if (!h || !info) return ALLL_BAD_ARG;
     if (!h->has_instance) return fail(h, ALLL_NO_INSTANCE, "no instance uploaded");
     info[0] = h->m;
@@ -1945,9 +1992,10 @@ int alll_layout_info(alll_handle h, uint64_t info[6])
     info[5] = h->k ? sweep_planes_smem_bytes(h->bucket_words) : sweep_csr_smem_bytes(h->csr_staged_words, SWEEP_THREADS);
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_sweep_info(alll_handle h, uint64_t info[4])
-{
+try {
     if (!h || !info) return ALLL_BAD_ARG;
     if (!h->has_instance) return fail(h, ALLL_NO_INSTANCE, "no instance uploaded");
     const uint32_t eager = h->k ? std::min<uint32_t>(h->k, EAGER_PLANES) : 0u;
@@ -1957,9 +2005,10 @@ int alll_sweep_info(alll_handle h, uint64_t info[4])
     info[3] = h->min_resident;
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 int alll_upload_info(alll_handle h, uint64_t info[4])
-{
+try {
     if (!h || !info) return ALLL_BAD_ARG;
     info[0] = h->up_link_bytes;
     info[1] = h->up_packed_chunks;
@@ -1967,6 +2016,7 @@ int alll_upload_info(alll_handle h, uint64_t info[4])
     info[3] = h->up_pack_threads;
     return ALLL_OK;
 }
+ALLL_GUARD(h)
 
 } // extern "C"
 

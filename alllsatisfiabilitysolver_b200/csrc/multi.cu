@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <functional>
 #include <memory>
 #include <mutex>
@@ -96,6 +97,15 @@ int mfail(alll_multi_handle mh, int status, const std::string &msg)
     return status;
 }
 
+// (no C++ exception crosses the C boundary: see ALLL_GUARD in capi.cu)
+int mguard_fail(alll_multi_handle mh, const char *what) noexcept
+{
+    try { return mfail(mh, ALLL_CUDA_ERROR, std::string("host-side failure: ") + what); } catch (...) { return ALLL_CUDA_ERROR; }
+}
+#define ALLL_MGUARD(mh)                                                                \
+    catch (const std::exception &e__) { return mguard_fail((mh), e__.what()); }        \
+    catch (...) { return mguard_fail((mh), "unknown exception"); }
+
 // Runs fn(slot) for every slot, concurrently (one host thread per slot; slot 0 on the caller's thread).  Returns the
 // first non-OK status (and records that slot's error text).
 int for_all_slots(alll_multi_handle mh, uint32_t n, const std::function<int(uint32_t)> &fn, bool allow_max_rounds = false)
@@ -158,7 +168,7 @@ extern "C" {
 const char *alll_multi_last_error(alll_multi_handle mh) { return mh ? mh->err.c_str() : g_multi_create_error.c_str(); }
 
 int alll_multi_create(const int32_t *devices, uint32_t n_devices, const alll_config *cfg, alll_multi_handle *out)
-{
+try {
     if (!out) return mfail(nullptr, ALLL_BAD_ARG, "out == NULL");
     *out = nullptr;
     if (!devices || n_devices == 0 || n_devices > MAX_SHARDS) return mfail(nullptr, ALLL_BAD_ARG, "need 1.." + std::to_string(MAX_SHARDS) + " devices");
@@ -213,9 +223,10 @@ int alll_multi_create(const int32_t *devices, uint32_t n_devices, const alll_con
     *out = mh;
     return ALLL_OK;
 }
+ALLL_MGUARD(nullptr)
 
 int alll_multi_destroy(alll_multi_handle mh)
-{
+try {
     if (!mh) return ALLL_OK;
     for (auto &w : mh->workers) {
         { std::lock_guard<std::mutex> lk(w->mu); w->quit = true; w->cv.notify_all(); }
@@ -226,15 +237,17 @@ int alll_multi_destroy(alll_multi_handle mh)
     delete mh;
     return ALLL_OK;
 }
+ALLL_MGUARD(mh)
 
 int alll_multi_upload_fixedk(alll_multi_handle mh, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit)
-{
+try {
     return alll_multi_upload_fixedk_streamed(mh, n_vars, m, k, lit, nullptr, nullptr);
 }
+ALLL_MGUARD(mh)
 
 int alll_multi_upload_fixedk_streamed(alll_multi_handle mh, uint64_t n_vars, uint64_t m, uint32_t k, const uint32_t *lit,
                                       alll_filled_fn filled, void *user)
-{
+try {
     if (!mh) return ALLL_BAD_ARG;
     mh->has_instance = false;
     const uint32_t n = (uint32_t)mh->h.size();
@@ -270,9 +283,10 @@ int alll_multi_upload_fixedk_streamed(alll_multi_handle mh, uint64_t n_vars, uin
     mh->has_instance = true;
     return ALLL_OK;
 }
+ALLL_MGUARD(mh)
 
 int alll_multi_upload_csr(alll_multi_handle mh, uint64_t n_vars, uint64_t m, const uint64_t *off, const uint32_t *lit)
-{
+try {
     if (!mh) return ALLL_BAD_ARG;
     if (!off) return mfail(mh, ALLL_BAD_ARG, "off == NULL");
     // uniform width k <= 8 is what the sharded exchange carries; everything else goes to the first device alone
@@ -288,29 +302,33 @@ int alll_multi_upload_csr(alll_multi_handle mh, uint64_t n_vars, uint64_t m, con
     mh->has_instance = true;
     return ALLL_OK;
 }
+ALLL_MGUARD(mh)
 
 int alll_multi_set_assignment(alll_multi_handle mh, const uint8_t *bools)
-{
+try {
     MNEED_INSTANCE();
     return for_all_slots(mh, slots_in_use(mh), [&](uint32_t r) { return alll_set_assignment(mh->h[r], bools); });
 }
+ALLL_MGUARD(mh)
 
 int alll_multi_get_assignment(alll_multi_handle mh, uint8_t *bools)
-{
+try {
     MNEED_INSTANCE();
     MCALL(0, alll_get_assignment(mh->h[0], bools));          // the replicas are bit-identical
     return ALLL_OK;
 }
+ALLL_MGUARD(mh)
 
 int alll_multi_randomize(alll_multi_handle mh, uint64_t seed)
-{
+try {
     MNEED_INSTANCE();
     for (uint32_t r = 0; r < slots_in_use(mh); r++) MCALL(r, alll_randomize(mh->h[r], seed));
     return ALLL_OK;
 }
+ALLL_MGUARD(mh)
 
 int alll_multi_verify(alll_multi_handle mh, int *valid)
-{
+try {
     MNEED_INSTANCE();
     const uint32_t n = slots_in_use(mh);
     std::vector<int> ok(n, 0);
@@ -318,9 +336,10 @@ int alll_multi_verify(alll_multi_handle mh, int *valid)
     if (valid) *valid = std::all_of(ok.begin(), ok.end(), [](int v) { return v != 0; }) ? 1 : 0;
     return ALLL_OK;
 }
+ALLL_MGUARD(mh)
 
 int alll_multi_solve(alll_multi_handle mh, uint64_t seed, uint64_t max_rounds, alll_stats *stats)
-{
+try {
     MNEED_INSTANCE();
     if (!stats) return mfail(mh, ALLL_BAD_ARG, "stats == NULL");
     if (!mh->sharded) {
@@ -378,9 +397,10 @@ int alll_multi_solve(alll_multi_handle mh, uint64_t seed, uint64_t max_rounds, a
     }
     return stats->status;
 }
+ALLL_MGUARD(mh)
 
 int alll_multi_info(alll_multi_handle mh, uint64_t info[4])
-{
+try {
     MNEED_INSTANCE();
     if (!info) return ALLL_BAD_ARG;
     info[0] = slots_in_use(mh);
@@ -389,19 +409,21 @@ int alll_multi_info(alll_multi_handle mh, uint64_t info[4])
     info[3] = mh->sharded ? mh->cap_records : 0;
     return ALLL_OK;
 }
+ALLL_MGUARD(mh)
 
 int alll_multi_device_handle(alll_multi_handle mh, uint32_t i, alll_handle *out)
-{
+try {
     if (!mh || !out || i >= mh->h.size()) return ALLL_BAD_ARG;
     *out = mh->h[i];
     return ALLL_OK;
 }
+ALLL_MGUARD(mh)
 
 // ---- batched small instances / seed portfolio over the device list -------------------------------------------------
 
 int alll_multi_batch_upload(alll_multi_handle mh, uint32_t n_instances, uint64_t n_vars, uint32_t k, const uint64_t *clause_off,
                             const uint32_t *lit)
-{
+try {
     if (!mh) return ALLL_BAD_ARG;
     mh->has_batch = false;
     if (n_instances == 0 || !clause_off) return mfail(mh, ALLL_BAD_ARG, "no instances");
@@ -432,10 +454,11 @@ int alll_multi_batch_upload(alll_multi_handle mh, uint32_t n_instances, uint64_t
     mh->has_batch = true;
     return ALLL_OK;
 }
+ALLL_MGUARD(mh)
 
 int alll_multi_batch_solve(alll_multi_handle mh, uint32_t n_jobs, const uint64_t *seeds, uint64_t max_rounds, int portfolio,
                            uint8_t *assignments, alll_batch_stats *stats, int32_t *winner, double *device_ms)
-{
+try {
     if (!mh) return ALLL_BAD_ARG;
     if (!mh->has_batch) return mfail(mh, ALLL_NO_INSTANCE, "no batch uploaded");
     if (n_jobs == 0 || !seeds || !stats) return mfail(mh, ALLL_BAD_ARG, "n_jobs / seeds / stats");
@@ -472,5 +495,6 @@ int alll_multi_batch_solve(alll_multi_handle mh, uint32_t n_jobs, const uint64_t
     }
     return ALLL_OK;
 }
+ALLL_MGUARD(mh)
 
 } // extern "C"

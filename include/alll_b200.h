@@ -18,7 +18,10 @@
  *   - every function returns an alll_status; ALLL_OK == 0;
  *   - blocking calls from one host thread per handle (like SATInstance::solve);
  *   - there is NO CPU fallback: without a CUDA device every call fails with
- *     ALLL_CUDA_ERROR.
+ *     ALLL_CUDA_ERROR;
+ *   - no C++ exception leaves the library: a host-side failure inside a call (out of
+ *     memory, no thread to start) comes back as ALLL_CUDA_ERROR with the text
+ *     "host-side failure: ..." in alll_last_error / alll_multi_last_error.
  */
 #ifndef ALLL_B200_H
 #define ALLL_B200_H
@@ -42,7 +45,7 @@ typedef enum {
     ALLL_MAX_ROUNDS = 1,    /* round cap hit before all clauses were satisfied (reference: loops forever, SATInstance.h:260) */
     ALLL_EMPTY_CLAUSE = 2,  /* an empty clause can never be satisfied (Clause.h:35-45) -- refused at upload              */
     ALLL_BAD_ARG = 3,
-    ALLL_CUDA_ERROR = 4,
+    ALLL_CUDA_ERROR = 4,    /* a CUDA call failed, or the host side of a call did (see alll_last_error) */
     ALLL_NCCL_ERROR = 5,
     ALLL_NO_INSTANCE = 6,   /* call needs an uploaded instance */
     ALLL_CAPACITY = 7,      /* caller buffer too small */
