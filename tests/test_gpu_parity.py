@@ -682,9 +682,9 @@ def test_packed_h2d_transport_uploads_the_same_instance(capi, oracle, monkeypatc
         ip, iu = sp.upload_info(), su.upload_info()
         assert iu["packed_chunks"] == 0 and iu["link_bytes"] == m * k * 4
         assert ip["packed_chunks"] + ip["raw_chunks"] == 10 and ip["pack_threads"] >= 1
-        if not pinned:
-            assert ip["raw_chunks"] == 0 and ip["link_bytes"] == 3 * m * k + m * k // 8
-        assert ip["packed_chunks"] >= 1
+        if not pinned:                                  # (pageable memory never goes as it is: the driver's staging copy is the slow path)
+            assert ip["raw_chunks"] == 0 and ip["packed_chunks"] == 10 and ip["link_bytes"] == 3 * m * k + m * k // 8
+        # (page-locked: how many of these 2 MB chunks are packed before the link runs dry is a race by design -- any mix is correct)
         v = oracle.randomize(n, seed)
         want = oracle.sweep(off, flat, v)
         for s in (sp, su):
