@@ -291,7 +291,12 @@ private:
         if (buf) { alll_host_free(buf); buf = nullptr; cap = 0; }
         void *p = nullptr;
         const size_t want = count + count / 8 + 64;
-        if (alll_host_alloc(want * sizeof(U), &p) != ALLL_OK) throw std::runtime_error("alll_host_alloc failed");
+        if (alll_host_alloc(want * sizeof(U), &p) != ALLL_OK) {
+            int32_t visible = 0;
+            alll_device_count(&visible);
+            throw std::runtime_error(visible > 0 ? "alll_host_alloc failed (page-locked staging memory)"
+                                                 : "alll_host_alloc: no CUDA device: the solver has no CPU fallback");
+        }
         buf = static_cast<U *>(p);
         cap = want;
     }

@@ -127,6 +127,18 @@ def test_user_program_and_cli_build(cli, lib, tmp_path):
     assert os.path.exists(cli)
 
 
+def test_user_program_fails_loudly_without_a_device(lib, tmp_path):
+    """No CPU fallback behind the drop-in headers either: without a CUDA device SATInstance::solve throws and says so."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    exe = build(str(tmp_path), "dropin_user", [os.path.join(ROOT, "tests", "cpp", "dropin_user.cpp")],
+                extra=["-I" + os.path.join(PKG, "include")], libs=LINK)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode != 0 and "no CPU fallback" in out.stderr, out.stderr[-500:]
+
+
 # ---- GPU -------------------------------------------------------------------------------------------
 
 @pytest.mark.gpu
